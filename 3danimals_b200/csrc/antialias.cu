@@ -1,0 +1,393 @@
+// antialias.cu - silhouette antialiasing (+ fused alpha composite) and triangle edge adjacency on sm_100a.
+// Replaces nvdiffrast.torch.antialias and the lerp composite of render_mesh.composite_buffer (reference call sites
+// model/render/render.py:258-268).  Semantics and arithmetic: oracle/raster_ref.c (aa_analyze) - bit-identical.
+//
+// Design (B200-first): nvdiffrast scatters blends with atomics after a work-queue pass.  Here both directions are
+// GATHERS: each output element looks at its four pixel pairs (up, left, right, down - the oracle's accumulation
+// order), re-runs the pair analysis only where triangle ids differ (the silhouette: O(perimeter) pixels) and writes
+// its result once.  No atomics on image data, deterministic, coalesced one-thread-per-element streaming; the
+// composite lerp(bg, [color,1], id>0) is folded in so the composited image never exists in HBM.  Only the vertex
+// position gradient of silhouette pairs uses atomics (a few thousand per image).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// edge adjacency: open-addressing hash on the undirected edge, two lowest triangle ids per edge
+// ------------------------------------------------------------------------------------------------------------
+struct AdjWorkspace {
+    unsigned long long* keys;
+    int* t0;
+    int* t1;
+    uint32_t mask;
+};
+
+size_t adj_layout(int64_t F, void* base, AdjWorkspace* ws)
+{
+    uint64_t cap = 1024;
+    while (cap < (uint64_t)F * 6) cap <<= 1;
+    size_t kb = b2a_align(cap * 8), tb = b2a_align(cap * 4);
+    if (ws) {
+        char* p = (char*)base;
+        ws->keys = (unsigned long long*)p;
+        ws->t0 = (int*)(p + kb);
+        ws->t1 = (int*)(p + kb + tb);
+        ws->mask = (uint32_t)(cap - 1);
+    }
+    return kb + 2 * tb;
+}
+
+__device__ __forceinline__ uint32_t hash64(unsigned long long k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (uint32_t)k;
+}
+
+__device__ __forceinline__ bool edge_of(const int* __restrict__ tri, int64_t i, int64_t V, int& f, int& lo, int& hi)
+{
+    f = (int)(i / 3);
+    int e = (int)(i % 3);
+    int a = __ldg(tri + (size_t)f * 3 + (e + 1) % 3), b = __ldg(tri + (size_t)f * 3 + (e + 2) % 3);
+    if ((unsigned)a >= (unsigned)V || (unsigned)b >= (unsigned)V) return false;
+    lo = min(a, b); hi = max(a, b);
+    return true;
+}
+
+__global__ void adj_insert_kernel(const int* __restrict__ tri, int64_t F, int64_t V, AdjWorkspace ws)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * 3) return;
+    int f, lo, hi;
+    if (!edge_of(tri, i, V, f, lo, hi)) return;
+    unsigned long long key = (unsigned long long)lo * (unsigned long long)(V + 1) + (unsigned long long)hi + 1ull;
+    uint32_t slot = hash64(key) & ws.mask;
+    while (true) {
+        unsigned long long prev = atomicCAS(ws.keys + slot, 0ull, key);
+        if (prev == 0ull || prev == key) break;
+        slot = (slot + 1) & ws.mask;
+    }
+    atomicMin(ws.t0 + slot, f);
+}
+
+__device__ __forceinline__ uint32_t adj_find(const AdjWorkspace& ws, unsigned long long key)
+{
+    uint32_t slot = hash64(key) & ws.mask;
+    while (ws.keys[slot] != key) slot = (slot + 1) & ws.mask;
+    return slot;
+}
+
+__global__ void adj_second_kernel(const int* __restrict__ tri, int64_t F, int64_t V, AdjWorkspace ws)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * 3) return;
+    int f, lo, hi;
+    if (!edge_of(tri, i, V, f, lo, hi)) return;
+    uint32_t slot = adj_find(ws, (unsigned long long)lo * (unsigned long long)(V + 1) + (unsigned long long)hi + 1ull);
+    if (f != ws.t0[slot]) atomicMin(ws.t1 + slot, f);
+}
+
+__global__ void adj_emit_kernel(const int* __restrict__ tri, int64_t F, int64_t V, AdjWorkspace ws, int* __restrict__ opp)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * 3) return;
+    int f, lo, hi;
+    int ov = -1;
+    if (edge_of(tri, i, V, f, lo, hi)) {
+        uint32_t slot = adj_find(ws, (unsigned long long)lo * (unsigned long long)(V + 1) + (unsigned long long)hi + 1ull);
+        int a = ws.t0[slot], b = ws.t1[slot];
+        int partner = (f == a) ? b : a;
+        if (partner >= 0 && partner < F) {
+#pragma unroll
+            for (int c = 2; c >= 0; c--) {
+                int vv = __ldg(tri + (size_t)partner * 3 + c);
+                if (vv != lo && vv != hi) ov = vv;  // descending loop: the first match in ascending order wins
+            }
+        }
+    }
+    opp[i] = ov;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pair analysis (oracle/raster_ref.c aa_analyze)
+// ------------------------------------------------------------------------------------------------------------
+struct AAParams {
+    const float* color;
+    const float* bg;
+    const float* rast;
+    const float* pos;
+    const int* tri;
+    const int* opp;
+    int Bg, composite, B, H, W, C;
+    int64_t V, F;
+};
+
+struct AAPair {
+    float alpha;
+    int tri, di, px, py;
+};
+
+__device__ __forceinline__ bool same_sign(float a, float b) { return (__float_as_int(a) ^ __float_as_int(b)) >= 0; }
+
+#define B2A_F32_MAX 3.402823466e+38f
+
+// (px,py) = first pixel of the pair, d = 0: neighbour to the right, 1: neighbour below.  r0/r1 = rast of the two pixels.
+__device__ bool aa_analyze(const AAParams& P, const float* __restrict__ pos_b, float4 r0, float4 r1, int px, int py, int d, AAPair& r)
+{
+    int tri0 = (int)r0.w - 1, tri1 = (int)r1.w - 1;
+    if (tri0 == tri1) return false;
+    int t = (tri0 >= 0) ? tri0 : tri1;
+    if (tri0 >= 0 && tri1 >= 0) t = (r0.z < r1.z) ? tri0 : tri1;
+    if (t == tri1) { px += 1 - d; py += d; }
+    if (t < 0 || t >= P.F) return false;
+    int vi0 = __ldg(P.tri + (size_t)t * 3), vi1 = __ldg(P.tri + (size_t)t * 3 + 1), vi2 = __ldg(P.tri + (size_t)t * 3 + 2);
+    if ((unsigned)vi0 >= (unsigned)P.V || (unsigned)vi1 >= (unsigned)P.V || (unsigned)vi2 >= (unsigned)P.V) return false;
+    int op0 = __ldg(P.opp + (size_t)t * 3), op1 = __ldg(P.opp + (size_t)t * 3 + 1), op2 = __ldg(P.opp + (size_t)t * 3 + 2);
+    if (op0 < 0) op0 = vi0;
+    if (op1 < 0) op1 = vi1;
+    if (op2 < 0) op2 = vi2;
+    float4 p0 = ldg4(pos_b + (size_t)vi0 * 4), p1 = ldg4(pos_b + (size_t)vi1 * 4), p2 = ldg4(pos_b + (size_t)vi2 * 4);
+    float4 o0 = ldg4(pos_b + (size_t)op0 * 4), o1 = ldg4(pos_b + (size_t)op1 * 4), o2 = ldg4(pos_b + (size_t)op2 * 4);
+    float xh = 0.5f * (float)P.W, yh = 0.5f * (float)P.H;
+    float fx = (float)px + 0.5f - xh, fy = (float)py + 0.5f - yh;
+    float w0 = 1.f / p0.w, w1 = 1.f / p1.w, w2 = 1.f / p2.w;
+    float ow0 = 1.f / o0.w, ow1 = 1.f / o1.w, ow2 = 1.f / o2.w;
+    float x0 = p0.x * w0 * xh - fx, y0 = p0.y * w0 * yh - fy;
+    float x1 = p1.x * w1 * xh - fx, y1 = p1.y * w1 * yh - fy;
+    float x2 = p2.x * w2 * xh - fx, y2 = p2.y * w2 * yh - fy;
+    float ox0 = o0.x * ow0 * xh - fx, oy0 = o0.y * ow0 * yh - fy;
+    float ox1 = o1.x * ow1 * xh - fx, oy1 = o1.y * ow1 * yh - fy;
+    float ox2 = o2.x * ow2 * xh - fx, oy2 = o2.y * ow2 * yh - fy;
+    float bb = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+    float a0 = (x1 - ox0) * (y2 - oy0) - (x2 - ox0) * (y1 - oy0);
+    float a1 = (x2 - ox1) * (y0 - oy1) - (x0 - ox1) * (y2 - oy1);
+    float a2 = (x0 - ox2) * (y1 - oy2) - (x1 - ox2) * (y0 - oy2);
+    bool s0 = same_sign(a0, bb), s1 = same_sign(a1, bb), s2 = same_sign(a2, bb);
+    if (!(s0 || s1 || s2)) return false;
+    if (d) { float tmp; tmp = x0; x0 = y0; y0 = tmp; tmp = x1; x1 = y1; y1 = tmp; tmp = x2; x2 = y2; y2 = tmp; }
+    float dx0 = x2 - x1, dx1 = x0 - x2, dx2 = x1 - x0;
+    float dy0 = y2 - y1, dy1 = y0 - y2, dy2 = y1 - y0;
+    float ds = (t == tri0) ? 1.f : -1.f;
+    float c0 = -B2A_F32_MAX, c1 = -B2A_F32_MAX, c2 = -B2A_F32_MAX;
+    if (!same_sign(y1, y2)) c0 = ds * (x1 * dy0 - y1 * dx0) / dy0;
+    if (!same_sign(y2, y0)) c1 = ds * (x2 * dy1 - y2 * dx1) / dy1;
+    if (!same_sign(y0, y1)) c2 = ds * (x0 * dy2 - y0 * dx2) / dy2;
+    int di = 0;
+    float cm = c0;
+    if (c1 > cm) { di = 1; cm = c1; }
+    if (c2 > cm) { di = 2; cm = c2; }
+    float dc = -B2A_F32_MAX;
+    if (di == 0 && s0 && fabsf(dy0) >= fabsf(dx0)) dc = c0;
+    if (di == 1 && s1 && fabsf(dy1) >= fabsf(dx1)) dc = c1;
+    if (di == 2 && s2 && fabsf(dy2) >= fabsf(dx2)) dc = c2;
+    const float eps = 0.0625f;
+    if (dc > -eps && dc < 1.f + eps) {
+        dc = fminf(fmaxf(dc, 0.f), 1.f);
+        r.alpha = ds * (0.5f - dc);
+        r.tri = t; r.di = di; r.px = px; r.py = py;
+        return true;
+    }
+    return false;
+}
+
+// value of channel c of the (optionally composited) input image at pixel `pix` of image b
+__device__ __forceinline__ float comp_color(const AAParams& P, int b, int pix, int c, bool covered)
+{
+    const size_t HW = (size_t)P.H * P.W;
+    if (!P.composite) return __ldg(P.color + ((size_t)b * HW + pix) * P.C + c);
+    if (covered) return c < P.C - 1 ? __ldg(P.color + ((size_t)b * HW + pix) * (P.C - 1) + c) : 1.f;
+    return P.bg ? __ldg(P.bg + ((size_t)(P.Bg == 1 ? 0 : b) * HW + pix) * P.C + c) : 0.f;
+}
+
+// the four pixel pairs of pixel (px,py) in the oracle's accumulation order: (first pixel offset, direction)
+__constant__ int c_pair_dx[4] = {0, -1, 0, 0};
+__constant__ int c_pair_dy[4] = {-1, 0, 0, 0};
+__constant__ int c_pair_d[4] = {1, 0, 0, 1};
+
+__global__ void __launch_bounds__(256) aa_fwd_kernel(AAParams P, float* __restrict__ out)
+{
+    const int HW = P.H * P.W;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)HW * P.C) return;
+    const int b = blockIdx.y;
+    int p = (int)(idx / P.C), c = (int)(idx % P.C);
+    int px = p % P.W, py = p / P.W;
+    const float* rast_b = P.rast + (size_t)b * HW * 4;
+    float idc = __ldg(rast_b + (size_t)p * 4 + 3);
+    float acc = comp_color(P, b, p, c, idc > 0.f);
+    // quick reject: all four neighbours carry the same id
+    float idu = py > 0 ? __ldg(rast_b + (size_t)(p - P.W) * 4 + 3) : idc;
+    float idl = px > 0 ? __ldg(rast_b + (size_t)(p - 1) * 4 + 3) : idc;
+    float idr = px + 1 < P.W ? __ldg(rast_b + (size_t)(p + 1) * 4 + 3) : idc;
+    float idd = py + 1 < P.H ? __ldg(rast_b + (size_t)(p + P.W) * 4 + 3) : idc;
+    if (idu != idc || idl != idc || idr != idc || idd != idc) {
+        const float* pos_b = P.pos + (size_t)b * P.V * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int qx = px + c_pair_dx[k], qy = py + c_pair_dy[k], d = c_pair_d[k];
+            if (qx < 0 || qy < 0) continue;
+            if (d == 0 ? qx + 1 >= P.W : qy + 1 >= P.H) continue;
+            int q0 = qy * P.W + qx, q1 = q0 + (d ? P.W : 1);
+            float4 r0 = ldg4(rast_b + (size_t)q0 * 4), r1 = ldg4(rast_b + (size_t)q1 * 4);
+            AAPair r;
+            if (!aa_analyze(P, pos_b, r0, r1, qx, qy, d, r)) continue;
+            int target = r.alpha > 0.f ? q0 : q1;
+            if (target != p) continue;
+            acc += r.alpha * (comp_color(P, b, q1, c, r1.w > 0.f) - comp_color(P, b, q0, c, r0.w > 0.f));
+        }
+    }
+    out[((size_t)b * HW) * P.C + idx] = acc;
+}
+
+struct AAGrad {
+    const float* d_out;
+    int64_t sb, sy, sx, sc;
+    int Cg;
+};
+__device__ __forceinline__ float grad_at(const AAGrad& G, int W, int b, int pix, int c)
+{
+    if (c >= G.Cg) return 0.f;
+    return __ldg(G.d_out + (int64_t)b * G.sb + (int64_t)(pix / W) * G.sy + (int64_t)(pix % W) * G.sx + (int64_t)c * G.sc);
+}
+
+__global__ void __launch_bounds__(256) aa_bwd_kernel(AAParams P, AAGrad G, float* __restrict__ d_color, float* __restrict__ d_pos)
+{
+    const int HW = P.H * P.W;
+    const int Cc = P.composite ? P.C - 1 : P.C;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)HW * Cc) return;
+    const int b = blockIdx.y;
+    int p = (int)(idx / Cc), c = (int)(idx % Cc);
+    int px = p % P.W, py = p / P.W;
+    const float* rast_b = P.rast + (size_t)b * HW * 4;
+    float idc = __ldg(rast_b + (size_t)p * 4 + 3);
+    float acc = grad_at(G, P.W, b, p, c);
+    float idu = py > 0 ? __ldg(rast_b + (size_t)(p - P.W) * 4 + 3) : idc;
+    float idl = px > 0 ? __ldg(rast_b + (size_t)(p - 1) * 4 + 3) : idc;
+    float idr = px + 1 < P.W ? __ldg(rast_b + (size_t)(p + 1) * 4 + 3) : idc;
+    float idd = py + 1 < P.H ? __ldg(rast_b + (size_t)(p + P.W) * 4 + 3) : idc;
+    if (idu != idc || idl != idc || idr != idc || idd != idc) {
+        const float* pos_b = P.pos + (size_t)b * P.V * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int qx = px + c_pair_dx[k], qy = py + c_pair_dy[k], d = c_pair_d[k];
+            if (qx < 0 || qy < 0) continue;
+            if (d == 0 ? qx + 1 >= P.W : qy + 1 >= P.H) continue;
+            int q0 = qy * P.W + qx, q1 = q0 + (d ? P.W : 1);
+            float4 r0 = ldg4(rast_b + (size_t)q0 * 4), r1 = ldg4(rast_b + (size_t)q1 * 4);
+            AAPair r;
+            if (!aa_analyze(P, pos_b, r0, r1, qx, qy, d, r)) continue;
+            int target = r.alpha > 0.f ? q0 : q1;
+            float gy = grad_at(G, P.W, b, target, c);
+            if (p == q0) acc -= r.alpha * gy; else acc += r.alpha * gy;
+            // vertex-position gradient: once per pair, by channel-0 thread of the pair's first pixel
+            if (c != 0 || p != q0 || !d_pos) continue;
+            float dd = 0.f;
+            for (int cc = 0; cc < G.Cg; cc++)
+                dd += grad_at(G, P.W, b, target, cc) * (comp_color(P, b, q1, cc, r1.w > 0.f) - comp_color(P, b, q0, cc, r0.w > 0.f));
+            if (dd == 0.f || fabsf(r.alpha) >= 0.5f) continue;
+            int e1 = __ldg(P.tri + (size_t)r.tri * 3 + (r.di + 1) % 3), e2 = __ldg(P.tri + (size_t)r.tri * 3 + (r.di + 2) % 3);
+            float4 q1v = ldg4(pos_b + (size_t)e1 * 4), q2v = ldg4(pos_b + (size_t)e2 * 4);
+            float pxh = 0.5f * (float)P.W, pyh = 0.5f * (float)P.H;
+            float fx = (float)r.px + 0.5f - pxh, fy = (float)r.py + 0.5f - pyh;
+            if (d) {
+                float t_;
+                t_ = q1v.x; q1v.x = q1v.y; q1v.y = t_;
+                t_ = q2v.x; q2v.x = q2v.y; q2v.y = t_;
+                t_ = pxh; pxh = pyh; pyh = t_;
+                t_ = fx; fx = fy; fy = t_;
+            }
+            float w1 = 1.f / q1v.w, w2 = 1.f / q2v.w;
+            float x1 = q1v.x * w1 * pxh - fx, y1 = q1v.y * w1 * pyh - fy;
+            float x2 = q2v.x * w2 * pxh - fx, y2 = q2v.y * w2 * pyh - fy;
+            float dx = x2 - x1, dy = y2 - y1;
+            float db = x1 * dy - y1 * dx;
+            float ep = copysignf(1e-3f, dy);
+            float iy = 1.f / (dy + ep);
+            float dby = db * iy;
+            float iw1 = -w1 * iy * dd, iw2 = w2 * iy * dd;
+            float gp1x = iw1 * pxh * y2, gp2x = iw2 * pxh * y1;
+            float gp1y = iw1 * pyh * (dby - x2), gp2y = iw2 * pyh * (dby - x1);
+            float gp1w = -(q1v.x * gp1x + q1v.y * gp1y) * w1;
+            float gp2w = -(q2v.x * gp2x + q2v.y * gp2y) * w2;
+            if (d) { float t_; t_ = gp1x; gp1x = gp1y; gp1y = t_; t_ = gp2x; gp2x = gp2y; gp2y = t_; }
+            float* g1 = d_pos + ((size_t)b * P.V + e1) * 4;
+            float* g2 = d_pos + ((size_t)b * P.V + e2) * 4;
+            atomicAdd(g1, gp1x); atomicAdd(g1 + 1, gp1y); atomicAdd(g1 + 3, gp1w);
+            atomicAdd(g2, gp2x); atomicAdd(g2 + 1, gp2y); atomicAdd(g2 + 3, gp2w);
+        }
+    }
+    if (d_color) d_color[((size_t)b * HW) * Cc + idx] = (P.composite && !(idc > 0.f)) ? 0.f : acc;
+}
+
+int aa_check(const float* color, const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, int Bg, int composite, int B,
+             int64_t V, int64_t F, int H, int W, int C)
+{
+    B2A_CHECK_ARG(rast && pos && tri && opp, "null pointer");
+    B2A_CHECK_ARG(color || (composite && C == 1), "null color");
+    B2A_CHECK_ARG(B > 0 && B <= 65535 && V > 0 && F >= 0 && H > 0 && W > 0 && (int64_t)H * W < (1ll << 31) && C > 0 && C <= 1024, "shape");
+    B2A_CHECK_ARG(Bg == 1 || Bg == B, "bg batch");
+    B2A_CHECK_ARG(((uintptr_t)pos & 15) == 0 && ((uintptr_t)rast & 15) == 0, "pos/rast must be 16-byte aligned");
+    return 0;
+}
+
+}  // namespace
+
+B2A_API int b2a_edge_adjacency_workspace_bytes(int64_t F, size_t* bytes)
+{
+    B2A_CHECK_ARG(bytes && F >= 0, "sizes");
+    *bytes = adj_layout(F, nullptr, nullptr);
+    return 0;
+}
+
+B2A_API int b2a_edge_adjacency(const int32_t* tri, int64_t F, int64_t V, void* workspace, size_t workspace_bytes, int32_t* opp,
+                               b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(tri && workspace && opp, "null pointer");
+    B2A_CHECK_ARG(F >= 0 && F < (1ll << 29) && V > 0 && V < (1ll << 31), "sizes");
+    AdjWorkspace ws;
+    size_t need = adj_layout(F, workspace, &ws);
+    B2A_CHECK_ARG(need <= workspace_bytes, "workspace too small");
+    if (F == 0) return 0;
+    size_t kb = (size_t)((char*)ws.t0 - (char*)ws.keys);
+    B2A_CUDA_OK(cudaMemsetAsync(ws.keys, 0, kb, stream));
+    B2A_CUDA_OK(cudaMemsetAsync(ws.t0, 0x7f, need - kb, stream));
+    unsigned nb = b2a_blocks(F * 3, 256);
+    adj_insert_kernel<<<nb, 256, 0, stream>>>(tri, F, V, ws);
+    adj_second_kernel<<<nb, 256, 0, stream>>>(tri, F, V, ws);
+    adj_emit_kernel<<<nb, 256, 0, stream>>>(tri, F, V, ws, opp);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+B2A_API int b2a_antialias_fwd(const float* color, const float* bg, int Bg, int composite, const float* rast, const float* pos,
+                              const int32_t* tri, const int32_t* opp, int B, int64_t V, int64_t F, int H, int W, int C, float* out,
+                              b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = aa_check(color, rast, pos, tri, opp, Bg, composite, B, V, F, H, W, C);
+    if (rc) return rc;
+    B2A_CHECK_ARG(out, "null pointer");
+    AAParams P{color, bg, rast, pos, tri, opp, Bg, composite, B, H, W, C, V, F};
+    aa_fwd_kernel<<<dim3(b2a_blocks((int64_t)H * W * C, 256), B), 256, 0, stream>>>(P, out);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+B2A_API int b2a_antialias_bwd(const float* color, const float* bg, int Bg, int composite, const float* rast, const float* pos,
+                              const int32_t* tri, const int32_t* opp, const float* d_out, int64_t d_sb, int64_t d_sy, int64_t d_sx,
+                              int64_t d_sc, int Cg, int B, int64_t V, int64_t F, int H, int W, int C, float* d_color, float* d_pos,
+                              b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = aa_check(color, rast, pos, tri, opp, Bg, composite, B, V, F, H, W, C);
+    if (rc) return rc;
+    B2A_CHECK_ARG(d_out && Cg >= 0 && Cg <= C, "d_out");
+    int Cc = composite ? C - 1 : C;
+    if (Cc == 0) return 0;
+    AAParams P{color, bg, rast, pos, tri, opp, Bg, composite, B, H, W, C, V, F};
+    AAGrad G{d_out, d_sb, d_sy, d_sx, d_sc, Cg};
+    aa_bwd_kernel<<<dim3(b2a_blocks((int64_t)H * W * Cc, 256), B), 256, 0, stream>>>(P, G, d_color, d_pos);
+    B2A_LAUNCH_OK();
+    return 0;
+}

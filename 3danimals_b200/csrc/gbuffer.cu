@@ -1,0 +1,319 @@
+// gbuffer.cu - fused g-buffer pass on sm_100a: the geometry half of render_layer + shade in ONE kernel per direction.
+// Replaces (reference model/render/render.py): 4x dr.interpolate (:182 v_pos, :185-191 per-face normals, :195 v_nrm,
+// :209 prior v_pos), ru.prepare_shading_normal(use_python=True) (:72 -> renderutils/bsdf.py:46-51 with the constant
+// perturbed normal (0,0,1), renderutils/ops.py:217-218) and the camera-space normal safe_normalize(n . R_w2c^T) (:75).
+// The vertex tangent interpolation (:196) is numerically dead and is not computed.
+//
+// Why fused: the reference materialises gb_pos / gb_geometric_normal / gb_normal / gb_tangent (4 x 12 B/pixel, written
+// then re-read by ~20 elementwise kernels).  Only what the PyTorch field MLPs and the light consume has to cross the
+// kernel boundary: gb_tex_pos and the camera-space normal (12 B each) - every other buffer is optional (NULL).
+// Backward (Phase B of the graded raster backward) reads d_cam_nrm + d_tex_pos + rast and scatters
+// vertex gradients (d_v_pos, d_v_nrm, d_prior_pos, d_clip) with fp32 atomics that stay in the 126 MB L2.
+#include "common.cuh"
+
+namespace {
+
+struct GbParams {
+    const float* rast;
+    const int* tri;
+    const float* v_pos;
+    const float* v_nrm;
+    const float* prior;
+    const float* w2c;
+    const float* campos;
+    int spp, Bq, two_sided, B, H, W;
+    int64_t V, F;
+};
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 ld3(const float* p) { return V3{__ldg(p), __ldg(p + 1), __ldg(p + 2)}; }
+__device__ __forceinline__ void st3(float* p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ V3 neg(V3 a) { return V3{-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ V3 bary(V3 a, V3 b, V3 c, float u, float v, float w)
+{
+    return V3{(u * a.x + v * b.x) + w * c.x, (u * a.y + v * b.y) + w * c.y, (u * a.z + v * b.z) + w * c.z};
+}
+// y = x / max(|x|, eps)  (torch.nn.functional.normalize);  returns the clamped length
+__device__ __forceinline__ V3 fnormalize(V3 x, float eps, float& len)
+{
+    len = fmaxf(sqrtf(dot3(x, x)), eps);
+    return V3{x.x / len, x.y / len, x.z / len};
+}
+// adjoint of fnormalize: d_x = (g - y (y.g)) / len when unclamped, g / eps when clamped
+__device__ __forceinline__ V3 fnormalize_bwd(V3 x, V3 y, float len, float eps, V3 g)
+{
+    if (sqrtf(dot3(x, x)) > eps) {
+        float d = dot3(y, g);
+        return V3{(g.x - y.x * d) / len, (g.y - y.y * d) / len, (g.z - y.z * d) / len};
+    }
+    return V3{g.x / eps, g.y / eps, g.z / eps};
+}
+// y = x / sqrt(max(x.x, 1e-20))  (render/util.py:28-32 safe_normalize)
+__device__ __forceinline__ V3 snormalize(V3 x, float& len)
+{
+    len = sqrtf(fmaxf(dot3(x, x), 1e-20f));
+    return V3{x.x / len, x.y / len, x.z / len};
+}
+__device__ __forceinline__ V3 snormalize_bwd(V3 x, V3 y, float len, V3 g)
+{
+    if (dot3(x, x) > 1e-20f) {
+        float d = dot3(y, g);
+        return V3{(g.x - y.x * d) / len, (g.y - y.y * d) / len, (g.z - y.z * d) / len};
+    }
+    return V3{g.x / len, g.y / len, g.z / len};
+}
+
+struct GbPixel {  // forward intermediates of one covered pixel
+    int i0, i1, i2;
+    float u, v, w;
+    V3 P0, P1, P2, N0, N1, N2, Q0, Q1, Q2;
+    V3 n, fn, gpos, ggeo, gnrm, gtex;
+    float nlen;
+    V3 s1, sh, vv, view, shf, geof, out, cam, cn;
+    float ln, ls, lv, lc, tpre, t;
+    bool front;
+};
+
+__device__ __forceinline__ void gb_forward(const GbParams& P, int b, int f, float u, float v, GbPixel& g)
+{
+    g.u = u; g.v = v; g.w = 1.f - u - v;
+    g.i0 = __ldg(P.tri + (size_t)f * 3); g.i1 = __ldg(P.tri + (size_t)f * 3 + 1); g.i2 = __ldg(P.tri + (size_t)f * 3 + 2);
+    const float* vp = P.v_pos + (size_t)b * P.V * 3;
+    const float* vn = P.v_nrm + (size_t)b * P.V * 3;
+    const float* vq = P.prior + (size_t)(P.Bq == 1 ? 0 : b) * P.V * 3;
+    g.P0 = ld3(vp + (size_t)g.i0 * 3); g.P1 = ld3(vp + (size_t)g.i1 * 3); g.P2 = ld3(vp + (size_t)g.i2 * 3);
+    g.N0 = ld3(vn + (size_t)g.i0 * 3); g.N1 = ld3(vn + (size_t)g.i1 * 3); g.N2 = ld3(vn + (size_t)g.i2 * 3);
+    g.Q0 = ld3(vq + (size_t)g.i0 * 3); g.Q1 = ld3(vq + (size_t)g.i1 * 3); g.Q2 = ld3(vq + (size_t)g.i2 * 3);
+    g.gpos = bary(g.P0, g.P1, g.P2, g.u, g.v, g.w);
+    g.n = cross3(g.P1 - g.P0, g.P2 - g.P0);
+    g.fn = snormalize(g.n, g.nlen);
+    g.ggeo = bary(g.fn, g.fn, g.fn, g.u, g.v, g.w);
+    g.gnrm = bary(g.N0, g.N1, g.N2, g.u, g.v, g.w);
+    g.gtex = bary(g.Q0, g.Q1, g.Q2, g.u, g.v, g.w);
+    // shading normal (bsdf.py:46-51): normalize, (identity perturbation), normalize again, two-sided flip, bend
+    g.s1 = fnormalize(g.gnrm, 1e-12f, g.ln);
+    g.sh = fnormalize(g.s1, 1e-12f, g.ls);
+    V3 cp = ld3(P.campos + (size_t)b * 3);
+    g.vv = cp - g.gpos;
+    g.view = fnormalize(g.vv, 1e-12f, g.lv);
+    g.front = !P.two_sided || dot3(g.ggeo, g.view) > 0.f;
+    g.shf = g.front ? g.sh : neg(g.sh);
+    g.geof = g.front ? g.ggeo : neg(g.ggeo);
+    g.tpre = dot3(g.view, g.shf) / 0.1f;
+    g.t = fminf(fmaxf(g.tpre, 0.f), 1.f);
+    V3 diff = g.shf - g.geof;  // torch.lerp: two algebraically equal branches
+    g.out = g.t < 0.5f ? g.geof + diff * g.t : g.shf - diff * (1.f - g.t);
+    const float* m = P.w2c + (size_t)b * 16;
+    g.cam = V3{(g.out.x * __ldg(m + 0) + g.out.y * __ldg(m + 1)) + g.out.z * __ldg(m + 2),
+               (g.out.x * __ldg(m + 4) + g.out.y * __ldg(m + 5)) + g.out.z * __ldg(m + 6),
+               (g.out.x * __ldg(m + 8) + g.out.y * __ldg(m + 9)) + g.out.z * __ldg(m + 10)};
+    g.cn = snormalize(g.cam, g.lc);
+}
+
+__global__ void __launch_bounds__(256) gb_fwd_kernel(GbParams P, float* __restrict__ gb_pos, float* __restrict__ gb_geo,
+                                                     float* __restrict__ gb_shn, float* __restrict__ gb_cam, float* __restrict__ gb_tex)
+{
+    int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (ip >= P.H * P.W) return;
+    int px = ip % P.W, py = ip / P.W;
+    size_t ri = ((size_t)b * P.H * P.spp + (size_t)py * P.spp) * ((size_t)P.W * P.spp) + (size_t)px * P.spp;
+    float4 r = ldg4(P.rast + ri * 4);
+    size_t po = ((size_t)b * P.H * P.W + ip) * 3;
+    int f = (int)r.w - 1;
+    V3 z{0.f, 0.f, 0.f};
+    if (f < 0 || f >= P.F) {
+        if (gb_pos) st3(gb_pos + po, z);
+        if (gb_geo) st3(gb_geo + po, z);
+        if (gb_shn) st3(gb_shn + po, z);
+        if (gb_cam) st3(gb_cam + po, z);
+        if (gb_tex) st3(gb_tex + po, z);
+        return;
+    }
+    GbPixel g;
+    gb_forward(P, b, f, r.x, r.y, g);
+    if (gb_pos) st3(gb_pos + po, g.gpos);
+    if (gb_geo) st3(gb_geo + po, g.ggeo);
+    if (gb_shn) st3(gb_shn + po, g.out);
+    if (gb_cam) st3(gb_cam + po, g.cn);
+    if (gb_tex) st3(gb_tex + po, g.gtex);
+}
+
+__device__ __forceinline__ void atomic_add3(float* p, V3 a)
+{
+    atomicAdd(p, a.x); atomicAdd(p + 1, a.y); atomicAdd(p + 2, a.z);
+}
+
+__global__ void __launch_bounds__(256) gb_bwd_kernel(GbParams P, const float* __restrict__ pos_clip, const float* __restrict__ d_gb_pos,
+                                                     const float* __restrict__ d_gb_geo, const float* __restrict__ d_gb_shn,
+                                                     const float* __restrict__ d_gb_cam, const float* __restrict__ d_gb_tex,
+                                                     float* __restrict__ d_v_pos, float* __restrict__ d_v_nrm, float* __restrict__ d_prior,
+                                                     float* __restrict__ d_clip, float* __restrict__ d_w2c, float* __restrict__ d_campos)
+{
+    __shared__ float s_acc[12];
+    if (threadIdx.x < 12) s_acc[threadIdx.x] = 0.f;
+    __syncthreads();
+    int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    bool active = ip < P.H * P.W;
+    int px = 0, py = 0, f = -1;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+        px = ip % P.W; py = ip / P.W;
+        size_t ri = ((size_t)b * P.H * P.spp + (size_t)py * P.spp) * ((size_t)P.W * P.spp) + (size_t)px * P.spp;
+        r = ldg4(P.rast + ri * 4);
+        f = (int)r.w - 1;
+        active = f >= 0 && f < P.F;
+    }
+    V3 zero{0.f, 0.f, 0.f};
+    V3 d_cam = zero, d_out = zero, d_vv = zero;
+    GbPixel g;
+    if (active) {
+        size_t po = ((size_t)b * P.H * P.W + ip) * 3;
+        V3 g_pos = d_gb_pos ? ld3(d_gb_pos + po) : zero;
+        V3 g_geo = d_gb_geo ? ld3(d_gb_geo + po) : zero;
+        V3 g_shn = d_gb_shn ? ld3(d_gb_shn + po) : zero;
+        V3 g_cn = d_gb_cam ? ld3(d_gb_cam + po) : zero;
+        V3 g_tex = d_gb_tex ? ld3(d_gb_tex + po) : zero;
+        gb_forward(P, b, f, r.x, r.y, g);
+        // camera-space normal
+        d_cam = snormalize_bwd(g.cam, g.cn, g.lc, g_cn);
+        const float* m = P.w2c + (size_t)b * 16;
+        d_out = V3{g_shn.x + ((d_cam.x * __ldg(m + 0) + d_cam.y * __ldg(m + 4)) + d_cam.z * __ldg(m + 8)),
+                   g_shn.y + ((d_cam.x * __ldg(m + 1) + d_cam.y * __ldg(m + 5)) + d_cam.z * __ldg(m + 9)),
+                   g_shn.z + ((d_cam.x * __ldg(m + 2) + d_cam.y * __ldg(m + 6)) + d_cam.z * __ldg(m + 10))};
+        // bend (lerp) and clamp
+        V3 d_geof = d_out * (1.f - g.t), d_shf = d_out * g.t;
+        float d_t = dot3(d_out, g.shf - g.geof);
+        float d_dot = (g.tpre >= 0.f && g.tpre <= 1.f) ? d_t / 0.1f : 0.f;
+        V3 d_view = g.shf * d_dot;
+        d_shf = d_shf + g.view * d_dot;
+        // two-sided flip
+        V3 d_sh = g.front ? d_shf : neg(d_shf);
+        V3 d_ggeo = g_geo + (g.front ? d_geof : neg(d_geof));
+        // double normalisation of the smooth normal
+        V3 d_s1 = fnormalize_bwd(g.s1, g.sh, g.ls, 1e-12f, d_sh);
+        V3 d_gnrm = fnormalize_bwd(g.gnrm, g.s1, g.ln, 1e-12f, d_s1);
+        // view vector
+        d_vv = fnormalize_bwd(g.vv, g.view, g.lv, 1e-12f, d_view);
+        V3 d_gpos = g_pos - d_vv;
+        // face normal: ggeo = (u+v+w) fn ; fn = safe_normalize(e1 x e2)
+        V3 d_fn = d_ggeo * ((g.u + g.v) + g.w);
+        V3 d_n = snormalize_bwd(g.n, g.fn, g.nlen, d_fn);
+        V3 e1 = g.P1 - g.P0, e2 = g.P2 - g.P0;
+        V3 d_e1 = cross3(e2, d_n), d_e2 = cross3(d_n, e1);
+        // attribute scatter
+        if (d_v_pos) {
+            float* o = d_v_pos + (size_t)b * P.V * 3;
+            atomic_add3(o + (size_t)g.i0 * 3, d_gpos * g.u - (d_e1 + d_e2));
+            atomic_add3(o + (size_t)g.i1 * 3, d_gpos * g.v + d_e1);
+            atomic_add3(o + (size_t)g.i2 * 3, d_gpos * g.w + d_e2);
+        }
+        if (d_v_nrm) {
+            float* o = d_v_nrm + (size_t)b * P.V * 3;
+            atomic_add3(o + (size_t)g.i0 * 3, d_gnrm * g.u);
+            atomic_add3(o + (size_t)g.i1 * 3, d_gnrm * g.v);
+            atomic_add3(o + (size_t)g.i2 * 3, d_gnrm * g.w);
+        }
+        if (d_prior) {
+            float* o = d_prior + (size_t)(P.Bq == 1 ? 0 : b) * P.V * 3;
+            atomic_add3(o + (size_t)g.i0 * 3, g_tex * g.u);
+            atomic_add3(o + (size_t)g.i1 * 3, g_tex * g.v);
+            atomic_add3(o + (size_t)g.i2 * 3, g_tex * g.w);
+        }
+        // barycentric gradients -> clip-space positions (rasterize backward, oracle/raster_ref.c orc_rasterize_bwd)
+        if (d_clip) {
+            float du = (dot3(d_gpos, g.P0 - g.P2) + dot3(d_gnrm, g.N0 - g.N2)) + dot3(g_tex, g.Q0 - g.Q2);
+            float dv = (dot3(d_gpos, g.P1 - g.P2) + dot3(d_gnrm, g.N1 - g.N2)) + dot3(g_tex, g.Q1 - g.Q2);
+            if (du != 0.f || dv != 0.f) {
+                const float* pb = pos_clip + (size_t)b * P.V * 4;
+                float4 p0 = ldg4(pb + (size_t)g.i0 * 4), p1 = ldg4(pb + (size_t)g.i1 * 4), p2 = ldg4(pb + (size_t)g.i2 * 4);
+                float fx, fy;
+                pixel_ndc(px * P.spp, py * P.spp, P.H * P.spp, P.W * P.spp, fx, fy);
+                float q0x = p0.x - fx * p0.w, q0y = p0.y - fy * p0.w;
+                float q1x = p1.x - fx * p1.w, q1y = p1.y - fy * p1.w;
+                float q2x = p2.x - fx * p2.w, q2y = p2.y - fy * p2.w;
+                float a0 = q1x * q2y - q1y * q2x, a1 = q2x * q0y - q2y * q0x, a2 = q0x * q1y - q0y * q1x;
+                float iw = 1.f / ((a0 + a1) + a2);
+                float uu = a0 * iw, vv = a1 * iw;
+                float gs = uu * du + vv * dv;
+                float ga0 = (du - gs) * iw, ga1 = (dv - gs) * iw, ga2 = -gs * iw;
+                float gq0x = ga2 * q1y - ga1 * q2y, gq0y = ga1 * q2x - ga2 * q1x;
+                float gq1x = ga0 * q2y - ga2 * q0y, gq1y = ga2 * q0x - ga0 * q2x;
+                float gq2x = ga1 * q0y - ga0 * q1y, gq2y = ga0 * q1x - ga1 * q0x;
+                float* gb = d_clip + (size_t)b * P.V * 4;
+                atomicAdd(gb + (size_t)g.i0 * 4, gq0x); atomicAdd(gb + (size_t)g.i0 * 4 + 1, gq0y); atomicAdd(gb + (size_t)g.i0 * 4 + 3, -(fx * gq0x + fy * gq0y));
+                atomicAdd(gb + (size_t)g.i1 * 4, gq1x); atomicAdd(gb + (size_t)g.i1 * 4 + 1, gq1y); atomicAdd(gb + (size_t)g.i1 * 4 + 3, -(fx * gq1x + fy * gq1y));
+                atomicAdd(gb + (size_t)g.i2 * 4, gq2x); atomicAdd(gb + (size_t)g.i2 * 4 + 1, gq2y); atomicAdd(gb + (size_t)g.i2 * 4 + 3, -(fx * gq2x + fy * gq2y));
+            }
+        }
+    } else {
+        g.out = zero;
+    }
+    // camera gradients: d_w2c[i][j] += d_cam[i] out[j] ; d_campos += d_vv  (block-reduced, one atomic set per block)
+    if (d_w2c || d_campos) {
+        if (__ballot_sync(0xffffffffu, active)) {
+            float vals[12] = {d_cam.x * g.out.x, d_cam.x * g.out.y, d_cam.x * g.out.z, d_cam.y * g.out.x, d_cam.y * g.out.y, d_cam.y * g.out.z,
+                              d_cam.z * g.out.x, d_cam.z * g.out.y, d_cam.z * g.out.z, d_vv.x, d_vv.y, d_vv.z};
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                float s = warp_sum(active ? vals[i] : 0.f);
+                if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(&s_acc[i], s);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 9 && d_w2c && s_acc[threadIdx.x] != 0.f)
+            atomicAdd(d_w2c + (size_t)b * 16 + (threadIdx.x / 3) * 4 + threadIdx.x % 3, s_acc[threadIdx.x]);
+        if (threadIdx.x >= 9 && threadIdx.x < 12 && d_campos && s_acc[threadIdx.x] != 0.f)
+            atomicAdd(d_campos + (size_t)b * 3 + (threadIdx.x - 9), s_acc[threadIdx.x]);
+    }
+}
+
+int gb_check(const float* rast, int spp, const int32_t* tri, const float* v_pos, const float* v_nrm, const float* prior_pos, int Bq,
+             const float* w2c, const float* campos, int B, int64_t V, int64_t F, int H, int W)
+{
+    B2A_CHECK_ARG(rast && tri && v_pos && v_nrm && prior_pos && w2c && campos, "null pointer");
+    B2A_CHECK_ARG(B > 0 && B <= 65535 && (Bq == 1 || Bq == B) && V > 0 && F >= 0 && H > 0 && W > 0 && spp >= 1 &&
+                      (int64_t)H * W * spp * spp < (1ll << 31), "shape");
+    B2A_CHECK_ARG(((uintptr_t)rast & 15) == 0, "rast must be 16-byte aligned");
+    return 0;
+}
+
+}  // namespace
+
+B2A_API int b2a_gbuffer_fwd(const float* rast, int spp, const int32_t* tri, const float* v_pos, const float* v_nrm,
+                            const float* prior_pos, int Bq, const float* w2c, const float* campos, int two_sided, int B, int64_t V,
+                            int64_t F, int H, int W, float* gb_pos, float* gb_geo_nrm, float* gb_shading_nrm, float* gb_cam_nrm,
+                            float* gb_tex_pos, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = gb_check(rast, spp, tri, v_pos, v_nrm, prior_pos, Bq, w2c, campos, B, V, F, H, W);
+    if (rc) return rc;
+    GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F};
+    gb_fwd_kernel<<<dim3(b2a_blocks((int64_t)H * W, 256), B), 256, 0, stream>>>(P, gb_pos, gb_geo_nrm, gb_shading_nrm, gb_cam_nrm, gb_tex_pos);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+B2A_API int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, const int32_t* tri, const float* v_pos,
+                            const float* v_nrm, const float* prior_pos, int Bq, const float* w2c, const float* campos, int two_sided,
+                            int B, int64_t V, int64_t F, int H, int W, const float* d_gb_pos, const float* d_gb_geo_nrm,
+                            const float* d_gb_shading_nrm, const float* d_gb_cam_nrm, const float* d_gb_tex_pos, float* d_v_pos,
+                            float* d_v_nrm, float* d_prior_pos, float* d_clip, float* d_w2c, float* d_campos, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = gb_check(rast, spp, tri, v_pos, v_nrm, prior_pos, Bq, w2c, campos, B, V, F, H, W);
+    if (rc) return rc;
+    B2A_CHECK_ARG(!d_clip || (pos_clip && ((uintptr_t)pos_clip & 15) == 0), "pos_clip");
+    GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F};
+    gb_bwd_kernel<<<dim3(b2a_blocks((int64_t)H * W, 256), B), 256, 0, stream>>>(P, pos_clip, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm,
+                                                                               d_gb_cam_nrm, d_gb_tex_pos, d_v_pos, d_v_nrm, d_prior_pos,
+                                                                               d_clip, d_w2c, d_campos);
+    B2A_LAUNCH_OK();
+    return 0;
+}

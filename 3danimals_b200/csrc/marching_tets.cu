@@ -1,0 +1,294 @@
+// marching_tets.cu - DMTet SDF -> mesh extraction on sm_100a.
+// Replaces DMTet.__call__ (reference model/geometry/dmtet.py:104-155): same vertex order (lexicographic order of
+// the unique sorted crossing edges, i.e. torch.unique(dim=0) order) and same face order ([1-triangle tets in tet
+// order][2-triangle tets in tet order]) without any runtime sort: a static per-grid CSR of unique edges, crossing
+// counts per min-vertex, and device-wide exclusive scans.  HBM-bound: algorithmic bytes per extraction are
+// 4*Vg (sdf) + 4*(Vg+E) (edge CSR) + 16*T (tets) + small.
+#include "common.cuh"
+
+namespace {
+
+constexpr int MT_BLOCK = 512;
+
+__constant__ int8_t c_tri_table[16][6] = {
+    {-1, -1, -1, -1, -1, -1}, {1, 0, 2, -1, -1, -1}, {4, 0, 3, -1, -1, -1}, {1, 4, 2, 1, 3, 4},
+    {3, 1, 5, -1, -1, -1},    {2, 3, 0, 2, 5, 3},    {1, 4, 0, 1, 5, 4},    {4, 2, 5, -1, -1, -1},
+    {4, 5, 2, -1, -1, -1},    {4, 1, 0, 4, 5, 1},    {3, 2, 0, 3, 5, 2},    {1, 3, 5, -1, -1, -1},
+    {4, 1, 2, 4, 3, 1},       {3, 0, 4, -1, -1, -1}, {2, 0, 1, -1, -1, -1}, {-1, -1, -1, -1, -1, -1}};
+__constant__ int8_t c_num_tri[16] = {0, 1, 1, 2, 1, 2, 2, 1, 1, 2, 2, 1, 2, 1, 1, 0};
+__constant__ int8_t c_base_edges[12] = {0, 1, 0, 2, 0, 3, 1, 2, 1, 3, 2, 3};
+
+struct MtWorkspace {
+    uint32_t* occ_bits;   // [ceil(Vg/32)]
+    uint8_t* vcnt;        // [Vg]
+    int* vtile;           // [nVT]
+    uint8_t* tetidx;      // [T]
+    int* t1tile;          // [nTT]
+    int* t2tile;          // [nTT]
+    int* edge_vidx;       // [E]
+    int* err;             // [1]
+    int64_t nVT, nTT;
+};
+
+size_t mt_layout(int64_t Vg, int64_t E, int64_t T, void* base, MtWorkspace* ws)
+{
+    int64_t nVT = (Vg + MT_BLOCK - 1) / MT_BLOCK, nTT = (T + MT_BLOCK - 1) / MT_BLOCK;
+    size_t off = 0;
+    char* p = (char*)base;
+    auto take = [&](size_t bytes) { size_t o = off; off += b2a_align(bytes); return p ? (void*)(p + o) : nullptr; };
+    void* occ = take((size_t)((Vg + 31) / 32) * 4);
+    void* vcnt = take((size_t)Vg);
+    void* vtile = take((size_t)nVT * 4);
+    void* tetidx = take((size_t)T);
+    void* t1 = take((size_t)nTT * 4);
+    void* t2 = take((size_t)nTT * 4);
+    void* ev = take((size_t)E * 4);
+    void* err = take(256);
+    if (ws) {
+        ws->occ_bits = (uint32_t*)occ; ws->vcnt = (uint8_t*)vcnt; ws->vtile = (int*)vtile;
+        ws->tetidx = (uint8_t*)tetidx; ws->t1tile = (int*)t1; ws->t2tile = (int*)t2;
+        ws->edge_vidx = (int*)ev; ws->err = (int*)err; ws->nVT = nVT; ws->nTT = nTT;
+    }
+    return off;
+}
+
+__device__ __forceinline__ bool occ_at(const uint32_t* __restrict__ bits, int v) { return (__ldg(bits + (v >> 5)) >> (v & 31)) & 1u; }
+
+// occupancy bitmask: occ = sdf > 0  (dmtet.py:106)
+__global__ void __launch_bounds__(MT_BLOCK) mt_occ_kernel(const float* __restrict__ sdf, int64_t Vg, uint32_t* __restrict__ bits)
+{
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool o = v < Vg && __ldg(sdf + v) > 0.f;
+    uint32_t m = __ballot_sync(0xffffffffu, o);
+    if ((threadIdx.x & 31) == 0 && v < Vg) bits[v >> 5] = m;
+}
+
+// crossing edges per min-vertex + per-tile totals
+__global__ void __launch_bounds__(MT_BLOCK) mt_vcount_kernel(const int* __restrict__ edge_start, const int* __restrict__ edge_b,
+                                                             const uint32_t* __restrict__ bits, int64_t Vg,
+                                                             uint8_t* __restrict__ vcnt, int* __restrict__ vtile, int* __restrict__ err)
+{
+    __shared__ int sm[34];
+    int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = 0;
+    if (a < Vg) {
+        int s = __ldg(edge_start + a), e = __ldg(edge_start + a + 1);
+        bool oa = occ_at(bits, (int)a);
+        for (int i = s; i < e; i++) cnt += (occ_at(bits, __ldg(edge_b + i)) != oa);
+        if (cnt > 255) { atomicExch(err, 1); cnt = 255; }
+        vcnt[a] = (uint8_t)cnt;
+    }
+    int total;
+    block_exclusive_scan(cnt, sm, &total);
+    if (threadIdx.x == 0) vtile[blockIdx.x] = total;
+}
+
+// tet case index + per-tile totals of 1-triangle and 2-triangle tets  (dmtet.py:107-109,135-137)
+__global__ void __launch_bounds__(MT_BLOCK) mt_tcount_kernel(const int4* __restrict__ tets, const uint32_t* __restrict__ bits,
+                                                             int64_t T, uint8_t* __restrict__ tetidx, int* __restrict__ t1tile,
+                                                             int* __restrict__ t2tile)
+{
+    __shared__ int sm[34];
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int n = 0;
+    if (t < T) {
+        int4 q = __ldg(tets + t);
+        int ti = (int)occ_at(bits, q.x) | ((int)occ_at(bits, q.y) << 1) | ((int)occ_at(bits, q.z) << 2) | ((int)occ_at(bits, q.w) << 3);
+        tetidx[t] = (uint8_t)ti;
+        n = c_num_tri[ti];
+    }
+    int tot1, tot2;
+    block_exclusive_scan(n == 1, sm, &tot1);
+    block_exclusive_scan(n == 2, sm, &tot2);
+    if (threadIdx.x == 0) { t1tile[blockIdx.x] = tot1; t2tile[blockIdx.x] = tot2; }
+}
+
+// One block per array: in-place exclusive scan of up to three tile-sum arrays; totals -> counts[which].
+struct ScanJob { int* data; int64_t n; };
+__global__ void __launch_bounds__(1024) mt_scan_tiles_kernel(ScanJob j0, ScanJob j1, ScanJob j2, int* __restrict__ counts)
+{
+    __shared__ int sm[34];
+    __shared__ int carry_s;
+    ScanJob j = blockIdx.x == 0 ? j0 : (blockIdx.x == 1 ? j1 : j2);
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < j.n; base += blockDim.x) {
+        int64_t i = base + threadIdx.x;
+        int v = i < j.n ? j.data[i] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, sm, &total);
+        int carry = carry_s;
+        if (i < j.n) j.data[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[blockIdx.x] = carry_s;
+}
+
+// emit vertices: v = p_a*((-s_b)/den) + p_b*(s_a/den), den = s_a - s_b  (dmtet.py:124-131), unfused fp32 ops
+__global__ void __launch_bounds__(MT_BLOCK) mt_vemit_kernel(const float* __restrict__ pos, const float* __restrict__ sdf,
+                                                            const int* __restrict__ edge_start, const int* __restrict__ edge_b,
+                                                            const uint32_t* __restrict__ bits, const uint8_t* __restrict__ vcnt,
+                                                            const int* __restrict__ vtile, int64_t Vg, float* __restrict__ verts,
+                                                            int* __restrict__ vert_edge, int* __restrict__ edge_vidx)
+{
+    __shared__ int sm[34];
+    int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt = a < Vg ? (int)vcnt[a] : 0;
+    int total;
+    int ex = block_exclusive_scan(cnt, sm, &total);
+    if (cnt == 0) return;
+    int out = vtile[blockIdx.x] + ex;
+    int s = __ldg(edge_start + a), e = __ldg(edge_start + a + 1);
+    bool oa = occ_at(bits, (int)a);
+    float sa = __ldg(sdf + a);
+    float ax = __ldg(pos + a * 3), ay = __ldg(pos + a * 3 + 1), az = __ldg(pos + a * 3 + 2);
+    for (int i = s; i < e; i++) {
+        int b = __ldg(edge_b + i);
+        if (occ_at(bits, b) == oa) continue;
+        float sb = -__ldg(sdf + b);
+        float den = sa + sb;
+        float wa = sb / den, wb = sa / den;
+        float bx = __ldg(pos + (int64_t)b * 3), by = __ldg(pos + (int64_t)b * 3 + 1), bz = __ldg(pos + (int64_t)b * 3 + 2);
+        verts[(int64_t)out * 3 + 0] = ax * wa + bx * wb;
+        verts[(int64_t)out * 3 + 1] = ay * wa + by * wb;
+        verts[(int64_t)out * 3 + 2] = az * wa + bz * wb;
+        vert_edge[(int64_t)out * 2 + 0] = (int)a;
+        vert_edge[(int64_t)out * 2 + 1] = b;
+        edge_vidx[i] = out;
+        out++;
+    }
+}
+
+__device__ __forceinline__ int find_edge_vertex(const int* __restrict__ edge_start, const int* __restrict__ edge_b,
+                                                const int* __restrict__ edge_vidx, int va, int vb)
+{
+    int lo = min(va, vb), hi = max(va, vb);
+    int s = __ldg(edge_start + lo), e = __ldg(edge_start + lo + 1);
+    for (int i = s; i < e; i++)
+        if (__ldg(edge_b + i) == hi) return edge_vidx[i];
+    return -1;
+}
+
+// emit faces (dmtet.py:139-151) and uv indices (map_uv :86-96)
+__global__ void __launch_bounds__(MT_BLOCK) mt_temit_kernel(const int4* __restrict__ tets, const uint8_t* __restrict__ tetidx,
+                                                            const int* __restrict__ t1tile, const int* __restrict__ t2tile,
+                                                            const int* __restrict__ edge_start, const int* __restrict__ edge_b,
+                                                            const int* __restrict__ edge_vidx, int64_t T, int64_t N1,
+                                                            int* __restrict__ faces32, long long* __restrict__ faces64,
+                                                            long long* __restrict__ uv64)
+{
+    __shared__ int sm[34];
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int ti = t < T ? (int)tetidx[t] : 0;
+    int n = c_num_tri[ti];
+    int tot;
+    int e1 = block_exclusive_scan(n == 1, sm, &tot);
+    int e2 = block_exclusive_scan(n == 2, sm, &tot);
+    if (n == 0) return;
+    int64_t fbase = n == 1 ? (int64_t)t1tile[blockIdx.x] + e1 : N1 + 2 * ((int64_t)t2tile[blockIdx.x] + e2);
+    int4 q = __ldg(tets + t);
+    int tv[4] = {q.x, q.y, q.z, q.w};
+    for (int k = 0; k < n; k++) {
+        int64_t f = fbase + k;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            int le = c_tri_table[ti][k * 3 + c];
+            int vid = find_edge_vertex(edge_start, edge_b, edge_vidx, tv[c_base_edges[le * 2]], tv[c_base_edges[le * 2 + 1]]);
+            if (faces32) faces32[f * 3 + c] = vid;
+            if (faces64) faces64[f * 3 + c] = vid;
+        }
+        if (uv64) {
+            long long g = (long long)t * 4;
+            uv64[f * 3 + 0] = g;
+            uv64[f * 3 + 1] = g + k + 1;
+            uv64[f * 3 + 2] = g + k + 2;
+        }
+    }
+}
+
+// backward of the vertex interpolation w.r.t. sdf (and optionally pos)
+__global__ void mt_bwd_kernel(const float* __restrict__ pos, const float* __restrict__ sdf, const int* __restrict__ vert_edge,
+                              const float* __restrict__ d_verts, int64_t V, float* __restrict__ d_sdf, float* __restrict__ d_pos)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    int a = vert_edge[i * 2], b = vert_edge[i * 2 + 1];
+    float sa = __ldg(sdf + a), sb = __ldg(sdf + b);
+    float den = sa - sb, id2 = 1.f / (den * den);
+    float gx = d_verts[i * 3], gy = d_verts[i * 3 + 1], gz = d_verts[i * 3 + 2];
+    float dx = __ldg(pos + (int64_t)a * 3) - __ldg(pos + (int64_t)b * 3);
+    float dy = __ldg(pos + (int64_t)a * 3 + 1) - __ldg(pos + (int64_t)b * 3 + 1);
+    float dz = __ldg(pos + (int64_t)a * 3 + 2) - __ldg(pos + (int64_t)b * 3 + 2);
+    float g = gx * dx + gy * dy + gz * dz;
+    atomicAdd(d_sdf + a, g * sb * id2);
+    atomicAdd(d_sdf + b, -g * sa * id2);
+    if (d_pos) {
+        float wa = -sb / den, wb = sa / den;
+        atomicAdd(d_pos + (int64_t)a * 3 + 0, gx * wa); atomicAdd(d_pos + (int64_t)a * 3 + 1, gy * wa); atomicAdd(d_pos + (int64_t)a * 3 + 2, gz * wa);
+        atomicAdd(d_pos + (int64_t)b * 3 + 0, gx * wb); atomicAdd(d_pos + (int64_t)b * 3 + 1, gy * wb); atomicAdd(d_pos + (int64_t)b * 3 + 2, gz * wb);
+    }
+}
+
+}  // namespace
+
+B2A_API int b2a_mt_workspace_bytes(int64_t Vg, int64_t E, int64_t T, size_t* bytes)
+{
+    B2A_CHECK_ARG(bytes && Vg >= 0 && E >= 0 && T >= 0, "sizes");
+    *bytes = mt_layout(Vg, E, T, nullptr, nullptr);
+    return 0;
+}
+
+B2A_API int b2a_mt_count(const float* sdf, const int32_t* tets, const int32_t* edge_start, const int32_t* edge_b,
+                         int64_t Vg, int64_t E, int64_t T, void* workspace, size_t workspace_bytes, int32_t* counts,
+                         b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(sdf && tets && edge_start && edge_b && workspace && counts, "null pointer");
+    B2A_CHECK_ARG(Vg > 0 && T > 0 && Vg < (1ll << 31) && E < (1ll << 31) && T < (1ll << 29), "grid size");
+    B2A_CHECK_ARG(((uintptr_t)tets & 15) == 0, "tets must be 16-byte aligned");
+    MtWorkspace ws;
+    B2A_CHECK_ARG(mt_layout(Vg, E, T, workspace, &ws) <= workspace_bytes, "workspace too small");
+    B2A_CUDA_OK(cudaMemsetAsync(ws.err, 0, 4, stream));
+    mt_occ_kernel<<<b2a_blocks(Vg, MT_BLOCK), MT_BLOCK, 0, stream>>>(sdf, Vg, ws.occ_bits);
+    mt_vcount_kernel<<<(unsigned)ws.nVT, MT_BLOCK, 0, stream>>>(edge_start, edge_b, ws.occ_bits, Vg, ws.vcnt, ws.vtile, ws.err);
+    mt_tcount_kernel<<<(unsigned)ws.nTT, MT_BLOCK, 0, stream>>>((const int4*)tets, ws.occ_bits, T, ws.tetidx, ws.t1tile, ws.t2tile);
+    ScanJob j0{ws.vtile, ws.nVT}, j1{ws.t1tile, ws.nTT}, j2{ws.t2tile, ws.nTT};
+    mt_scan_tiles_kernel<<<3, 1024, 0, stream>>>(j0, j1, j2, counts);
+    B2A_CUDA_OK(cudaMemcpyAsync(counts + 3, ws.err, 4, cudaMemcpyDeviceToDevice, stream));
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+B2A_API int b2a_mt_emit(const float* pos, const float* sdf, const int32_t* tets, const int32_t* edge_start,
+                        const int32_t* edge_b, int64_t Vg, int64_t E, int64_t T, void* workspace, size_t workspace_bytes,
+                        int64_t V, int64_t N1, int64_t N2, float* verts, int32_t* vert_edge, int32_t* faces_i32,
+                        int64_t* faces_i64, int64_t* uv_idx_i64, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(pos && sdf && tets && edge_start && edge_b && workspace, "null pointer");
+    MtWorkspace ws;
+    B2A_CHECK_ARG(mt_layout(Vg, E, T, workspace, &ws) <= workspace_bytes, "workspace too small");
+    if (V > 0) {
+        B2A_CHECK_ARG(verts && vert_edge, "null vertex outputs");
+        mt_vemit_kernel<<<(unsigned)ws.nVT, MT_BLOCK, 0, stream>>>(pos, sdf, edge_start, edge_b, ws.occ_bits, ws.vcnt, ws.vtile,
+                                                                    Vg, verts, vert_edge, ws.edge_vidx);
+    }
+    if (N1 + N2 > 0 && (faces_i32 || faces_i64 || uv_idx_i64))
+        mt_temit_kernel<<<(unsigned)ws.nTT, MT_BLOCK, 0, stream>>>((const int4*)tets, ws.tetidx, ws.t1tile, ws.t2tile, edge_start,
+                                                                    edge_b, ws.edge_vidx, T, N1, faces_i32,
+                                                                    (long long*)faces_i64, (long long*)uv_idx_i64);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+B2A_API int b2a_mt_bwd(const float* pos, const float* sdf, const int32_t* vert_edge, const float* d_verts, int64_t V,
+                       float* d_sdf, float* d_pos, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(pos && sdf && vert_edge && d_verts && d_sdf, "null pointer");
+    if (V > 0) mt_bwd_kernel<<<b2a_blocks(V, 256), 256, 0, stream>>>(pos, sdf, vert_edge, d_verts, V, d_sdf, d_pos);
+    B2A_LAUNCH_OK();
+    return 0;
+}

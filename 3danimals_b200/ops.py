@@ -1,0 +1,469 @@
+"""torch.autograd wrappers over the C-ABI CUDA library (include/b2a.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape; every number on the hot path is
+produced by a hand-written sm_100a kernel in libb2a.so.  All ops require CUDA fp32 tensors and raise otherwise -
+there is no eager / CPU fallback.
+"""
+import torch
+
+from . import _lib
+
+_i32 = torch.int32
+
+
+def _L():
+    return _lib.lib()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t, name):
+    if not torch.is_tensor(t) or not t.is_cuda:
+        raise _lib.B2AError("%s must be a CUDA tensor (the B200 hot path has no CPU fallback)" % name)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _idx32(t, name):
+    if not torch.is_tensor(t) or not t.is_cuda:
+        raise _lib.B2AError("%s must be a CUDA tensor" % name)
+    if t.dtype != _i32:
+        t = t.to(_i32)
+    return t.contiguous()
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _size(fn, *args):
+    import ctypes
+    out = ctypes.c_size_t(0)
+    _lib.check(fn(*args, ctypes.byref(out)))
+    return out.value
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Marching tetrahedra (reference model/geometry/dmtet.py:104-155)
+# ---------------------------------------------------------------------------------------------------------------
+_BASE_EDGES = (0, 1, 0, 2, 0, 3, 1, 2, 1, 3, 2, 3)
+
+
+class TetGrid:
+    """Static per-grid tables, built once when a grid is loaded (reference DMTetGeometry.load_tets, dmtet.py:214-226,
+    and generate_edges :283-288): int32 tets and the CSR of the unique sorted (min,max) grid edges in lexicographic
+    order - the order torch.unique(dim=0) gives the reference's crossing edges, hence its vertex numbering."""
+
+    def __init__(self, tets, num_verts):
+        if not tets.is_cuda:
+            raise _lib.B2AError("TetGrid needs CUDA tensors")
+        tets = tets.long()
+        self.Vg = int(num_verts)
+        self.T = int(tets.shape[0])
+        n = self.Vg + 1
+        be = torch.tensor(_BASE_EDGES, device=tets.device)
+        keys = None
+        step = 1 << 24  # bound the transient memory of the one-off table build on very large grids
+        for s in range(0, self.T, step):
+            e = tets[s:s + step][:, be].reshape(-1, 2)
+            k = torch.unique(e.min(1).values * n + e.max(1).values)
+            keys = k if keys is None else torch.unique(torch.cat([keys, k]))
+        a = keys // n
+        self.E = int(keys.numel())
+        self.edge_b = (keys % n).to(_i32).contiguous()
+        start = torch.zeros(self.Vg + 1, dtype=torch.int64, device=tets.device)
+        start[1:] = torch.cumsum(torch.bincount(a, minlength=self.Vg), 0)
+        self.edge_start = start.to(_i32).contiguous()
+        self.tets = tets.to(_i32).contiguous()
+        self.workspace = _workspace(_size(_L().b2a_mt_workspace_bytes, self.Vg, self.E, self.T), tets.device)
+        self.counts = torch.zeros(4, dtype=_i32, device=tets.device)
+
+    def all_edges(self):
+        """[E,2] int64, identical to the reference's DMTetGeometry.all_edges."""
+        a = torch.repeat_interleave(torch.arange(self.Vg, device=self.tets.device),
+                                    (self.edge_start[1:] - self.edge_start[:-1]).long())
+        return torch.stack([a, self.edge_b.long()], -1)
+
+
+class _MarchingTets(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, sdf, grid):
+        L = _L()
+        pos_c = _f32(pos, "pos").reshape(-1, 3)
+        sdf_c = _f32(sdf, "sdf").reshape(-1)
+        if pos_c.shape[0] != grid.Vg or sdf_c.shape[0] != grid.Vg:
+            raise _lib.B2AError("marching_tets: pos/sdf do not match the grid (%d verts)" % grid.Vg)
+        st = _stream()
+        _lib.check(L.b2a_mt_count(_p(sdf_c), _p(grid.tets), _p(grid.edge_start), _p(grid.edge_b), grid.Vg, grid.E, grid.T,
+                                  _p(grid.workspace), grid.workspace.numel(), _p(grid.counts), st))
+        V, N1, N2, err = grid.counts.tolist()  # the one device->host read of the extraction (output sizes)
+        if err:
+            raise _lib.B2AError("marching_tets: a grid vertex has more than 255 crossing edges")
+        Fn = N1 + 2 * N2
+        dev = pos_c.device
+        verts = torch.empty(V, 3, device=dev)
+        vert_edge = torch.empty(V, 2, dtype=_i32, device=dev)
+        faces = torch.empty(Fn, 3, dtype=torch.int64, device=dev)
+        faces32 = torch.empty(Fn, 3, dtype=_i32, device=dev)
+        uv_idx = torch.empty(Fn, 3, dtype=torch.int64, device=dev)
+        _lib.check(L.b2a_mt_emit(_p(pos_c), _p(sdf_c), _p(grid.tets), _p(grid.edge_start), _p(grid.edge_b), grid.Vg, grid.E,
+                                 grid.T, _p(grid.workspace), grid.workspace.numel(), V, N1, N2, _p(verts), _p(vert_edge),
+                                 _p(faces32), _p(faces), _p(uv_idx), st))
+        ctx.save_for_backward(pos_c, sdf_c, vert_edge)
+        ctx.shapes = (pos.shape, sdf.shape)
+        ctx.mark_non_differentiable(faces, faces32, uv_idx, vert_edge)
+        return verts, faces, uv_idx, faces32, vert_edge
+
+    @staticmethod
+    def backward(ctx, d_verts, *_):
+        pos_c, sdf_c, vert_edge = ctx.saved_tensors
+        need_pos = ctx.needs_input_grad[0]
+        d_sdf = torch.zeros_like(sdf_c)
+        d_pos = torch.zeros_like(pos_c) if need_pos else None
+        V = vert_edge.shape[0]
+        if V > 0:
+            g = _f32(d_verts, "d_verts")
+            _lib.check(_L().b2a_mt_bwd(_p(pos_c), _p(sdf_c), _p(vert_edge), _p(g), V, _p(d_sdf), _p(d_pos), _stream()))
+        return (d_pos.reshape(ctx.shapes[0]) if need_pos else None), d_sdf.reshape(ctx.shapes[1]), None
+
+
+def marching_tets(pos, sdf, grid):
+    """-> verts [V,3] f32 (differentiable w.r.t. sdf and pos), faces [F,3] i64, uv_idx [F,3] i64, faces_i32, vert_edge."""
+    return _MarchingTets.apply(pos, sdf, grid)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Linear blend skinning (reference model/geometry/skinning.py:369-439)
+# ---------------------------------------------------------------------------------------------------------------
+def chain_tables(kinematic_tree, num_bones, device):
+    """kinematic_tree: list of (bone_id, [dependent bone ids]) (skinning.py:25-46).  For bone k the product runs over
+    ancestors(k) in list order (root first) followed by k (skinning.py:389-417).  -> chain_ptr [K+1], chain_ids."""
+    chains = {}
+    for bone_id, _ in kinematic_tree:
+        chains[int(bone_id)] = [int(p) for p, children in kinematic_tree if bone_id in children] + [int(bone_id)]
+    ptr, ids = [0], []
+    for k in range(num_bones):
+        c = chains.get(k, [k])
+        if len(c) > 16:
+            raise _lib.B2AError("kinematic chain deeper than 16 is not supported")
+        ids += c
+        ptr.append(len(ids))
+    return (torch.tensor(ptr, dtype=_i32, device=device), torch.tensor(ids, dtype=_i32, device=device))
+
+
+class _LBS(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v_pos, bones, angles, chain_ptr, chain_ids, temperature, want_weights):
+        L = _L()
+        v_pos = _f32(v_pos, "v_pos"); bones = _f32(bones, "bones"); angles = _f32(angles, "angles")
+        B, K = angles.shape[0], angles.shape[1]
+        Bv, V = v_pos.shape[0], v_pos.shape[1]
+        Bb = bones.shape[0]
+        dev = v_pos.device
+        st = _stream()
+        T_local = torch.empty(B, K, 12, device=dev)
+        G = torch.empty(B, K, 12, device=dev)
+        posed = torch.empty(B, K, 2, 3, device=dev)
+        _lib.check(L.b2a_lbs_bone_transforms(_p(bones), _p(angles), _p(chain_ptr), _p(chain_ids), B, Bb, K, _p(T_local), _p(G),
+                                             _p(posed), st))
+        out = torch.empty(B, V, 3, device=dev)
+        Bw = max(Bv, Bb)
+        weights = torch.empty(K, Bw, V, device=dev) if want_weights else None
+        _lib.check(L.b2a_lbs_fwd(_p(v_pos), _p(bones), _p(G), B, Bv, Bb, K, V, 1.0 / float(temperature), _p(out), _p(weights), st))
+        ctx.save_for_backward(v_pos, bones, angles, chain_ptr, chain_ids, T_local, G)
+        ctx.inv_t = 1.0 / float(temperature)
+        if weights is None:
+            weights = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(weights)
+        return out, posed, weights
+
+    @staticmethod
+    def backward(ctx, d_out, d_posed, _):
+        L = _L()
+        v_pos, bones, angles, chain_ptr, chain_ids, T_local, G = ctx.saved_tensors
+        B, K = angles.shape[0], angles.shape[1]
+        Bv, V = v_pos.shape[0], v_pos.shape[1]
+        Bb = bones.shape[0]
+        dev = v_pos.device
+        st = _stream()
+        d_G = torch.zeros(B, K, 12, device=dev)
+        d_v = None
+        if ctx.needs_input_grad[0]:
+            d_v = torch.zeros(Bv, V, 3, device=dev)
+        if d_out is not None and V > 0:
+            g = _f32(d_out, "d_out")
+            _lib.check(L.b2a_lbs_bwd(_p(v_pos), _p(bones), _p(G), _p(g), B, Bv, Bb, K, V, ctx.inv_t, _p(d_v), _p(d_G), st))
+        d_angles = None
+        if ctx.needs_input_grad[2]:
+            d_T = torch.zeros(B, K, 12, device=dev)
+            d_angles = torch.empty(B, K, 3, device=dev)
+            gp = _f32(d_posed, "d_posed") if d_posed is not None else None
+            _lib.check(L.b2a_lbs_bone_transforms_bwd(_p(bones), _p(angles), _p(chain_ptr), _p(chain_ids), _p(T_local), _p(d_G),
+                                                     _p(gp), B, Bb, K, _p(d_T), _p(d_angles), st))
+        return d_v, None, d_angles, None, None, None, None
+
+
+def lbs(v_pos, bones, angles, chain_ptr, chain_ids, temperature=1.0, want_weights=False):
+    """v_pos [Bv,V,3], bones [Bb,K,2,3], angles [B,K,3] -> posed verts [B,V,3], posed bones [B,K,2,3], weights [K,Bw,V]|None."""
+    out, posed, w = _LBS.apply(v_pos, bones, angles, chain_ptr, chain_ids, temperature, want_weights)
+    return out, posed, (w if want_weights else None)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Vertex normals (reference model/render/mesh.py:276-304)
+# ---------------------------------------------------------------------------------------------------------------
+class _VertexNormals(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v_pos, tri):
+        v_pos = _f32(v_pos, "v_pos")
+        B, V = v_pos.shape[0], v_pos.shape[1]
+        F = tri.shape[0]
+        nsum = torch.empty_like(v_pos)
+        nrm = torch.empty_like(v_pos)
+        _lib.check(_L().b2a_vertex_normals_fwd(_p(v_pos), _p(tri), B, V, F, _p(nsum), _p(nrm), _stream()))
+        ctx.save_for_backward(v_pos, tri, nsum)
+        return nrm
+
+    @staticmethod
+    def backward(ctx, g):
+        v_pos, tri, nsum = ctx.saved_tensors
+        B, V = v_pos.shape[0], v_pos.shape[1]
+        g = _f32(g, "d_nrm")
+        scratch = torch.empty_like(v_pos)
+        d_pos = torch.zeros_like(v_pos)
+        _lib.check(_L().b2a_vertex_normals_bwd(_p(v_pos), _p(tri), _p(nsum), _p(g), B, V, tri.shape[0], _p(scratch), _p(d_pos),
+                                               _stream()))
+        return d_pos, None
+
+
+def vertex_normals(v_pos, tri):
+    """v_pos [B,V,3], tri [F,3] -> smooth area-weighted vertex normals [B,V,3]."""
+    return _VertexNormals.apply(v_pos, _idx32(tri, "tri"))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Clip transform (reference model/render/renderutils/ops.py:524-525)
+# ---------------------------------------------------------------------------------------------------------------
+class _XfmPoints(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pts, mtx):
+        pts = _f32(pts, "points"); mtx = _f32(mtx, "matrix")
+        B, Bp, V = mtx.shape[0], pts.shape[0], pts.shape[1]
+        out = torch.empty(B, V, 4, device=pts.device)
+        _lib.check(_L().b2a_xfm_points_fwd(_p(pts), _p(mtx), B, Bp, V, _p(out), _stream()))
+        ctx.save_for_backward(pts, mtx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pts, mtx = ctx.saved_tensors
+        B, Bp, V = mtx.shape[0], pts.shape[0], pts.shape[1]
+        g = _f32(g, "d_out")
+        d_pts = torch.zeros_like(pts) if ctx.needs_input_grad[0] else None
+        d_mtx = torch.zeros_like(mtx) if ctx.needs_input_grad[1] else None
+        _lib.check(_L().b2a_xfm_points_bwd(_p(pts), _p(mtx), _p(g), B, Bp, V, _p(d_pts), _p(d_mtx), _stream()))
+        return d_pts, d_mtx
+
+
+def xfm_points(points, matrix):
+    """points [B or 1,V,3], matrix [B,4,4] -> homogeneous clip-space points [B,V,4]."""
+    return _XfmPoints.apply(points, matrix)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Rasterize / interpolate / antialias (nvdiffrast.torch ops used by reference model/render/render.py:24,264,292,351)
+# ---------------------------------------------------------------------------------------------------------------
+class _Rasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, tri, H, W):
+        L = _L()
+        pos = _f32(pos, "pos")
+        B, V = pos.shape[0], pos.shape[1]
+        F = tri.shape[0]
+        ws = _workspace(_size(L.b2a_rasterize_workspace_bytes, B, F, H, W), pos.device)
+        rast = torch.empty(B, H, W, 4, device=pos.device)
+        _lib.check(L.b2a_rasterize_fwd(_p(pos), _p(tri), B, V, F, H, W, _p(ws), ws.numel(), _p(rast), _stream()))
+        ctx.save_for_backward(pos, tri, rast)
+        return rast
+
+    @staticmethod
+    def backward(ctx, g):
+        pos, tri, rast = ctx.saved_tensors
+        B, V = pos.shape[0], pos.shape[1]
+        H, W = rast.shape[1], rast.shape[2]
+        g = _f32(g, "d_rast")
+        d_pos = torch.zeros_like(pos)
+        _lib.check(_L().b2a_rasterize_bwd(_p(pos), _p(tri), _p(rast), _p(g), B, V, tri.shape[0], H, W, _p(d_pos), _stream()))
+        return d_pos, None, None, None
+
+
+def rasterize(pos, tri, resolution):
+    """pos [B,V,4] clip space, tri [F,3], resolution (H,W) -> rast [B,H,W,4] = (u, v, z/w, triangle_id+1)."""
+    if pos.dim() != 3 or pos.shape[-1] != 4:
+        raise _lib.B2AError("rasterize: pos must be [B,V,4] (instanced mode)")
+    return _Rasterize.apply(pos, _idx32(tri, "tri"), int(resolution[0]), int(resolution[1]))
+
+
+class _Interpolate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, attr, rast, tri):
+        attr = _f32(attr, "attr"); rast = _f32(rast, "rast")
+        B, H, W = rast.shape[0], rast.shape[1], rast.shape[2]
+        Ba, V, Cc = attr.shape
+        out = torch.empty(B, H, W, Cc, device=attr.device)
+        _lib.check(_L().b2a_interpolate_fwd(_p(attr), _p(rast), _p(tri), B, Ba, V, tri.shape[0], H, W, Cc, _p(out), _stream()))
+        ctx.save_for_backward(attr, rast, tri)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        attr, rast, tri = ctx.saved_tensors
+        B, H, W = rast.shape[0], rast.shape[1], rast.shape[2]
+        Ba, V, Cc = attr.shape
+        g = _f32(g, "d_out")
+        d_attr = torch.zeros_like(attr) if ctx.needs_input_grad[0] else None
+        d_rast = torch.empty_like(rast) if ctx.needs_input_grad[1] else None
+        _lib.check(_L().b2a_interpolate_bwd(_p(attr), _p(rast), _p(tri), _p(g), B, Ba, V, tri.shape[0], H, W, Cc, _p(d_attr),
+                                            _p(d_rast), _stream()))
+        return d_attr, d_rast, None
+
+
+def interpolate(attr, rast, tri):
+    """attr [B or 1,V,C], rast [B,H,W,4], tri [F,3] -> [B,H,W,C]."""
+    if attr.dim() != 3 or (attr.shape[0] != 1 and attr.shape[0] != rast.shape[0]):
+        raise _lib.B2AError("interpolate: attr must be [B or 1,V,C]")
+    return _Interpolate.apply(attr, rast, _idx32(tri, "tri"))
+
+
+def edge_adjacency(tri, num_verts):
+    """tri [F,3] -> opp [F,3] int32: the vertex opposite each edge in the neighbouring triangle (-1: boundary)."""
+    L = _L()
+    tri = _idx32(tri, "tri")
+    F = tri.shape[0]
+    ws = _workspace(_size(L.b2a_edge_adjacency_workspace_bytes, F), tri.device)
+    opp = torch.empty(F, 3, dtype=_i32, device=tri.device)
+    _lib.check(L.b2a_edge_adjacency(_p(tri), F, int(num_verts), _p(ws), ws.numel(), _p(opp), _stream()))
+    return opp
+
+
+class _Antialias(torch.autograd.Function):
+    """composite=False: plain antialias(color[B,H,W,C]).  composite=True: color is [B,H,W,C-1] and the blended input is
+    lerp(bg, [color,1], id>0) (render.py:258-262), never materialised.  `keep` = how many leading output channels the
+    caller uses (the rest are sliced off, render.py:320-331), so their gradient is known to be zero."""
+
+    @staticmethod
+    def forward(ctx, color, bg, rast, pos, tri, opp, composite, keep):
+        color = _f32(color, "color"); rast = _f32(rast, "rast"); pos = _f32(pos, "pos")
+        bg = _f32(bg, "background") if bg is not None else None
+        B, H, W = rast.shape[0], rast.shape[1], rast.shape[2]
+        Cc = color.shape[-1] + (1 if composite else 0)
+        if color.shape[:3] != rast.shape[:3]:
+            raise _lib.B2AError("antialias: color %s does not match rast %s" % (tuple(color.shape), tuple(rast.shape)))
+        Bg = 1
+        if bg is not None:
+            if bg.shape[1:] != (H, W, Cc) or bg.shape[0] not in (1, B):
+                raise _lib.B2AError("antialias: background shape %s, expected [1|B,%d,%d,%d]" % (tuple(bg.shape), H, W, Cc))
+            Bg = bg.shape[0]
+        out = torch.empty(B, H, W, Cc, device=color.device)
+        _lib.check(_L().b2a_antialias_fwd(_p(color), _p(bg), Bg, int(composite), _p(rast), _p(pos), _p(tri), _p(opp), B, pos.shape[1],
+                                          tri.shape[0], H, W, Cc, _p(out), _stream()))
+        ctx.save_for_backward(color, bg, rast, pos, tri, opp)
+        ctx.cfg = (bool(composite), Bg, Cc, int(keep))
+        if keep < Cc:
+            out = out[..., :keep]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        color, bg, rast, pos, tri, opp = ctx.saved_tensors
+        composite, Bg, Cc, keep = ctx.cfg
+        B, H, W = rast.shape[0], rast.shape[1], rast.shape[2]
+        if g.dtype != torch.float32:
+            g = g.float()
+        d_color = torch.empty_like(color) if ctx.needs_input_grad[0] else None
+        d_pos = torch.zeros_like(pos) if ctx.needs_input_grad[3] else None
+        sb, sy, sx, sc = g.stride()
+        _lib.check(_L().b2a_antialias_bwd(_p(color), _p(bg), Bg, int(composite), _p(rast), _p(pos), _p(tri), _p(opp), _p(g), sb, sy, sx,
+                                          sc, keep, B, pos.shape[1], tri.shape[0], H, W, Cc, _p(d_color), _p(d_pos), _stream()))
+        return d_color, None, None, d_pos, None, None, None, None
+
+
+def antialias(color, rast, pos, tri, opp=None):
+    """nvdiffrast.torch.antialias semantics: color [B,H,W,C], rast [B,H,W,4], pos [B,V,4], tri [F,3]."""
+    tri = _idx32(tri, "tri")
+    if opp is None:
+        opp = edge_adjacency(tri, pos.shape[1])
+    return _Antialias.apply(color, None, rast, pos, tri, opp, False, color.shape[-1])
+
+
+def composite_antialias(color, background, rast, pos, tri, opp, antialias_edges=True, keep=None):
+    """Fused lerp(background, [color,1], id>0) (+ antialias).  color [B,H,W,C-1]; background [1|B,H,W,C] or None (zeros).
+    Returns [B,H,W,keep] (keep defaults to C)."""
+    tri = _idx32(tri, "tri")
+    Cc = color.shape[-1] + 1
+    keep = Cc if keep is None else keep
+    if not antialias_edges:
+        # composite only: same kernel with an adjacency table that marks every edge interior is not available, so the
+        # un-antialiased keys (kd, normal, geo_normal) take the plain torch lerp below; they are logging-only modes.
+        alpha = (rast[..., -1:] > 0).float()
+        bgt = background if background is not None else torch.zeros(1, *color.shape[1:3], Cc, device=color.device)
+        acc = torch.lerp(bgt.expand(color.shape[0], -1, -1, -1), torch.cat((color, torch.ones_like(color[..., :1])), -1), alpha)
+        return acc[..., :keep]
+    return _Antialias.apply(color, background, rast, pos, tri, opp, True, keep)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fused g-buffer (reference model/render/render.py:160-209 + :72-75)
+# ---------------------------------------------------------------------------------------------------------------
+GB_KEYS = ("pos", "geo_nrm", "shading_nrm", "cam_nrm", "tex_pos")
+
+
+class _GBuffer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, two_sided, want):
+        rast = _f32(rast, "rast"); pos_clip = _f32(pos_clip, "pos_clip"); v_pos = _f32(v_pos, "v_pos"); v_nrm = _f32(v_nrm, "v_nrm")
+        prior_pos = _f32(prior_pos, "prior_pos"); w2c = _f32(w2c, "w2c"); campos = _f32(campos, "campos")
+        B, V = v_pos.shape[0], v_pos.shape[1]
+        H, W = rast.shape[1] // spp, rast.shape[2] // spp
+        if rast.shape[0] != B or w2c.shape != (B, 4, 4) or campos.shape != (B, 3) or v_nrm.shape != v_pos.shape:
+            raise _lib.B2AError("gbuffer: inconsistent batch shapes")
+        outs = [torch.empty(B, H, W, 3, device=rast.device) if k in want else None for k in GB_KEYS]
+        _lib.check(_L().b2a_gbuffer_fwd(_p(rast), spp, _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0], _p(w2c),
+                                        _p(campos), int(two_sided), B, V, tri.shape[0], H, W, *[_p(o) for o in outs], _stream()))
+        ctx.save_for_backward(rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos)
+        ctx.cfg = (spp, int(two_sided), H, W, tuple(o is not None for o in outs))
+        return tuple(o if o is not None else torch.empty(0, device=rast.device) for o in outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos = ctx.saved_tensors
+        spp, two_sided, H, W, present = ctx.cfg
+        B, V = v_pos.shape[0], v_pos.shape[1]
+        gs = [(_f32(g, "d_gb") if (g is not None and p) else None) for g, p in zip(grads, present)]
+        need = ctx.needs_input_grad
+        d_clip = torch.zeros_like(pos_clip) if need[1] else None
+        d_v_pos = torch.zeros_like(v_pos) if need[3] else None
+        d_v_nrm = torch.zeros_like(v_nrm) if need[4] else None
+        d_prior = torch.zeros_like(prior_pos) if need[5] else None
+        d_w2c = torch.zeros_like(w2c) if need[6] else None
+        d_campos = torch.zeros_like(campos) if need[7] else None
+        if any(g is not None for g in gs):
+            _lib.check(_L().b2a_gbuffer_bwd(_p(rast), spp, _p(pos_clip), _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0],
+                                            _p(w2c), _p(campos), two_sided, B, V, tri.shape[0], H, W, *[_p(g) for g in gs], _p(d_v_pos),
+                                            _p(d_v_nrm), _p(d_prior), _p(d_clip), _p(d_w2c), _p(d_campos), _stream()))
+        return None, d_clip, None, d_v_pos, d_v_nrm, d_prior, d_w2c, d_campos, None, None, None
+
+
+def gbuffer(rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp=1, two_sided=True, want=("cam_nrm", "tex_pos")):
+    """Fused g-buffer pass.  rast [B,H*spp,W*spp,4] (not differentiated: visibility is piecewise constant; barycentric
+    gradients go straight to pos_clip).  Returns a dict with the requested keys of GB_KEYS, each [B,H,W,3]."""
+    outs = _GBuffer.apply(rast.detach(), pos_clip, _idx32(tri, "tri"), v_pos, v_nrm, prior_pos, w2c, campos, int(spp), bool(two_sided),
+                          tuple(want))
+    return {k: o for k, o in zip(GB_KEYS, outs) if k in want}

@@ -1,0 +1,145 @@
+"""The hot path end to end on synthetic MagicPony-horse inputs: what bench.py times and smoke() runs.
+
+    sdf values on the tet grid -> DMTet extraction -> make_mesh (normals)            [prior shape, batch 1]
+      -> estimate_bones -> skinning (LBS) -> make_mesh (normals)                     [B posed instances]
+      -> render_mesh(['shaded','dino_pred'])                                         [clip, raster, g-buffer, shade, AA]
+      -> backward from upstream image gradients to d_sdf and d_articulation.
+
+It calls the package's public drop-in API (geometry.dmtet / geometry.skinning / render.mesh / render.render), i.e. the
+same entry points the reference's predictors and AnimalModel.render use (InstancePredictorBase.py:513-598,
+AnimalModel.py:217-258).  The field networks are PyTorch modules: an analytic colour field (M1a: kernels only) or
+CoordMLPs of the reference's sizes (M1b; magicpony.yaml:43-51,65-74).
+"""
+import numpy as np
+import torch
+
+from . import synthetic
+from .geometry import dmtet as dmtet_mod
+from .geometry import skinning as skinning_mod
+from .render import mesh as mesh_mod
+from .render import render as render_mod
+
+
+class SyntheticScene:
+    """Seeded numpy inputs shared by the CUDA path and the CPU oracle (same bytes on both sides)."""
+
+    def __init__(self, grid_res=128, batch=16, image_res=256, n_body_bones=8, n_leg_bones=3, dino_dim=16, spatial_scale=7.0,
+                 sdf_noise=0.01, seed=0):
+        self.grid_res, self.batch, self.image_res = grid_res, batch, image_res
+        self.n_body_bones, self.n_leg_bones, self.dino_dim = n_body_bones, n_leg_bones, dino_dim
+        self.num_bones = n_body_bones + 4 * n_leg_bones
+        v, t = synthetic.kuhn_tet_grid(grid_res)
+        self.grid_verts = (v * np.float32(spatial_scale)).astype(np.float32)
+        self.tets = t
+        self.sdf = synthetic.sdf_horse(self.grid_verts, sigma=sdf_noise, seed=seed)
+        rng = np.random.RandomState(seed + 1)
+        self.angles = rng.uniform(-0.3, 0.3, size=(batch, 1, self.num_bones, 3)).astype(np.float32)
+        self.mvp, self.w2c, self.campos = synthetic.cameras(batch, seed=seed + 3)
+        rng = np.random.RandomState(seed + 2)
+        self.feat = rng.randn(batch, 256).astype(np.float32)
+        self.light = np.array([0.3, 0.5, 0.8, 0.4, 0.6], np.float32)   # dir(3, normalised below), ambient, diffuse
+        self.light[:3] /= np.linalg.norm(self.light[:3])
+        self.w_kd = (rng.randn(3, 3) * 1.5).astype(np.float32)
+        self.w_dino = (rng.randn(3, dino_dim) * 1.5).astype(np.float32)
+
+    def upstream_grads(self, seed=7):
+        rng = np.random.RandomState(seed)
+        r = self.image_res
+        return ((rng.randn(self.batch, 4, r, r) * 1e-3).astype(np.float32),
+                (rng.randn(self.batch, self.dino_dim, r, r) * 1e-3).astype(np.float32))
+
+
+class AnalyticField(torch.nn.Module):
+    """Fixed smooth colour / feature field standing in for the texture and DINO CoordMLPs (M1a)."""
+
+    def __init__(self, weight, squash):
+        super().__init__()
+        self.register_buffer("weight", weight)
+        self.squash = squash
+        self.bsdf = None
+
+    def sample(self, x, feat=None):
+        y = torch.matmul(x, self.weight)
+        if self.squash:  # texture: 9 channels (kd, ks, normal) in [0,1]
+            y = torch.sigmoid(y)
+            return torch.cat([y, y, y], -1)
+        return torch.sin(y)
+
+
+class FixedLight(torch.nn.Module):
+    """DirectionalLight.shade arithmetic (reference model/render/light.py:186-193) with fixed light parameters."""
+
+    def __init__(self, params):
+        super().__init__()
+        self.register_buffer("params", params)
+
+    def shade(self, feat, kd, normal):
+        ldir, amb, diff = self.params[:3], self.params[3], self.params[4]
+        shading = amb + diff * torch.clamp(torch.sum(ldir * normal, -1, keepdim=True), min=0.0)
+        return shading * kd, shading
+
+
+class HotPath(torch.nn.Module):
+    def __init__(self, scene, device="cuda", mlps=False):
+        super().__init__()
+        s = self.scene = scene
+        dev = torch.device(device)
+        self.grid_verts = torch.from_numpy(s.grid_verts).to(dev)
+        self.tets = torch.from_numpy(s.tets).to(dev)
+        self.dmtet = dmtet_mod.DMTet()
+        self.grid = self.dmtet.grid_for(self.tets, self.grid_verts.shape[0])
+        self.sdf = torch.nn.Parameter(torch.from_numpy(s.sdf).to(dev)[:, None])
+        self.angles = torch.nn.Parameter(torch.from_numpy(s.angles).to(dev))
+        self.mvp = torch.from_numpy(s.mvp).to(dev)
+        self.w2c = torch.from_numpy(s.w2c).to(dev)
+        self.campos = torch.from_numpy(s.campos).to(dev)
+        self.feat = torch.from_numpy(s.feat).to(dev)
+        self.light = FixedLight(torch.from_numpy(s.light).to(dev))
+        if mlps:
+            from .networks import CoordMLP
+            mm = torch.tensor([[0., 1.]] * 9, device=dev)
+            self.material = CoordMLP(3, 9, 8, nf=256, activation="sigmoid", min_max=mm, n_harmonic_functions=10,
+                                     embedder_scalar=2 * np.pi / 7.0 * 0.9, extra_feat_dim=256, symmetrize=True).to(dev)
+            self.dino_net = CoordMLP(3, s.dino_dim, 5, nf=256, activation="sigmoid", n_harmonic_functions=8,
+                                     embedder_scalar=2 * np.pi / 7.0 * 0.9, symmetrize=True).to(dev)
+        else:
+            self.material = AnalyticField(torch.from_numpy(s.w_kd).to(dev), True)
+            self.dino_net = AnalyticField(torch.from_numpy(s.w_dino).to(dev), False)
+        self.mlps = mlps
+        self.bone_aux = None
+        self.kinematic_chain = None
+
+    def forward(self, sdf=None, render_modes=("shaded", "dino_pred")):
+        s = self.scene
+        sdf = self.sdf if sdf is None else sdf
+        # prior shape: extraction + normals (DMTetGeometry.getMesh, dmtet.py:294-310)
+        verts, faces, uv_idx, faces32 = self.dmtet.extract(self.grid_verts, sdf, self.grid)
+        prior = mesh_mod.make_mesh(verts[None], faces[None], None, uv_idx[None], None, faces_i32=faces32)
+        # bones from the prior shape (InstancePredictorBase.py:319-335); chain lists only the first time
+        if self.bone_aux is None:
+            bones, self.kinematic_chain, self.bone_aux = skinning_mod.estimate_bones(
+                prior.v_pos[:, None].detach(), s.n_body_bones, n_legs=4, n_leg_bones=s.n_leg_bones, body_bones_mode="z_minmax_y+",
+                compute_kinematic_chain=True)
+        else:
+            bones = skinning_mod.estimate_bones(prior.v_pos[:, None].detach(), s.n_body_bones, n_legs=4, n_leg_bones=s.n_leg_bones,
+                                                body_bones_mode="z_minmax_y+", compute_kinematic_chain=False, aux=self.bone_aux)
+        # articulation (InstancePredictorBase.py:578-586)
+        posed, aux = skinning_mod.skinning(prior.v_pos[:, None], bones, self.kinematic_chain, self.angles, output_posed_bones=True,
+                                           temperature=0.05)
+        inst = mesh_mod.make_mesh(posed[:, 0], prior.t_pos_idx, None, prior.t_tex_idx, None, faces_i32=prior.tri_i32())
+        inst._opp = prior._opp
+        res = (s.image_res, s.image_res)
+        feat = self.feat if self.mlps else None
+        out = render_mod.render_mesh(None, inst, self.mvp, self.w2c, self.campos, self.material, self.light, res, spp=1,
+                                     num_layers=1, msaa=True, background=None, bsdf="diffuse", feat=feat,
+                                     render_modes=list(render_modes), prior_mesh=prior, dino_net=self.dino_net)
+        self.last = dict(prior=prior, inst=inst, bones=bones, posed_bones=aux["posed_bones"])
+        return out
+
+    def step(self, d_shaded, d_dino):
+        """One fwd+bwd pass; returns (d_sdf [Vg,1], d_angles [B,1,K,3])."""
+        self.sdf.grad = None
+        self.angles.grad = None
+        shaded, dino = self.forward()
+        torch.autograd.backward([shaded, dino], [d_shaded, d_dino])
+        return self.sdf.grad, self.angles.grad

@@ -1,0 +1,153 @@
+"""Drop-in for the reference's model/render/render.py: render_mesh (+ shade / render_layer folded in) and render_uv.
+
+Same signature, same list-of-NCHW return (reference render.py:228-337).  What changed underneath:
+  * clip transform, rasterizer, g-buffer interpolation + shading normal + camera normal, composite + antialias are
+    sm_100a kernels of libb2a.so (ops.xfm_points / rasterize / gbuffer / composite_antialias) - no nvdiffrast;
+  * the five dr.interpolate calls and ~20 elementwise shading-normal kernels of render_layer/shade (render.py:182-209,
+    :72-75) are ONE fused launch; only gb_tex_pos and the camera-space normal cross into PyTorch for the field MLPs
+    and the light (which stay PyTorch modules);
+  * lerp-composite + dr.antialias per key (render.py:258-268) is one gather kernel per key, no composited image in HBM.
+"""
+import torch
+
+from .. import ops
+
+
+def interpolate(attr, rast, attr_idx, rast_db=None):
+    """Reference render.py:23-24 helper (kept for callers such as render_uv); returns (out, None) like dr.interpolate."""
+    return ops.interpolate(attr.contiguous(), rast, attr_idx), None
+
+
+def _nearest_up(x, spp):
+    return x.repeat_interleave(spp, dim=1).repeat_interleave(spp, dim=2) if spp > 1 else x
+
+
+def _as_b3(x, B, device):
+    x = torch.as_tensor(x, dtype=torch.float32, device=device)
+    x = x.reshape(-1, 3)
+    return x.expand(B, 3) if x.shape[0] == 1 and B > 1 else x
+
+
+_AA_KEYS = ("shaded", "flow", "dino_pred", "depth", "shading")
+_BG_KEYS = ("shaded", "geo_normal", "shading")
+_KEEP = {"kd": 3, "ks": 3, "normal": 3, "geo_normal": 3, "shading": 1, "flow": 2, "depth": 1}
+
+
+def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp=1, num_layers=1, msaa=False, background=None,
+                bsdf=None, feat=None, render_modes=None, prior_mesh=None, two_sided_shading=True, dino_net=None,
+                num_frames=None, class_vector=None):
+    assert mesh.t_pos_idx.shape[1] > 0, "Got empty training triangle mesh (unrecoverable discontinuity)"
+    assert background is None or (background.shape[1] == resolution[0] and background.shape[2] == resolution[1])
+    if num_layers != 1:
+        raise NotImplementedError("depth peeling beyond the first layer is never requested (AnimalModel.py:247)")
+    if render_modes is None:
+        render_modes = ["shaded"]
+    dev = mesh.v_pos.device
+    B = mesh.v_pos.shape[0]
+    H, W = int(resolution[0]), int(resolution[1])
+    shade_spp = spp if (spp > 1 and msaa) else 1          # g-buffer is shaded at [H,W] only when msaa is on
+    full_res = (H * spp, W * spp)
+    gH, gW = (H, W) if shade_spp > 1 else full_res
+    mtx_in = torch.as_tensor(mtx_in, dtype=torch.float32, device=dev)
+    campos = _as_b3(view_pos, B, dev)
+    w2c = w2c.float()
+    tri = mesh.tri_i32()
+    opp = mesh.edge_adjacency()
+    if prior_mesh is None:
+        prior_mesh = mesh
+
+    # clip-space transform + rasterize (render.py:278, :292-294)
+    v_pos_clip = ops.xfm_points(mesh.v_pos, mtx_in)
+    rast = ops.rasterize(v_pos_clip, tri, full_res)
+    rast_s = rast[:, ::shade_spp, ::shade_spp].contiguous() if shade_spp > 1 else rast
+
+    # fused g-buffer
+    want = ["cam_nrm", "tex_pos"]
+    if "geo_normal" in render_modes:
+        want.append("geo_nrm")
+    if "normal" in render_modes:
+        want.append("shading_nrm")
+    if "depth" in render_modes:
+        want.append("pos")
+    gb = ops.gbuffer(rast, v_pos_clip, tri, mesh.v_pos, mesh.v_nrm, prior_mesh.v_pos, w2c, campos, spp=shade_spp,
+                     two_sided=two_sided_shading, want=tuple(want))
+    gb_tex_pos, cam_normal = gb["tex_pos"], gb["cam_nrm"]
+
+    # pixel shader: field MLPs + light stay PyTorch (render.py:50-94)
+    if material is not None:
+        all_tex = material.sample(gb_tex_pos, feat=feat)
+    else:
+        all_tex = torch.ones(*gb_tex_pos.shape[:-1], 9, device=dev)
+    kd, ks = all_tex[..., :3], all_tex[..., 3:6]
+    bsdf = bsdf if bsdf is not None else getattr(material, "bsdf", None)
+    assert bsdf is not None, "Material must specify a BSDF type"
+    shading = None
+    if bsdf == "diffuse":
+        if lgt is None:
+            shaded_col = kd
+        elif type(lgt).__name__ == "EnvironmentLight":
+            raise NotImplementedError("EnvironmentLight is used by no shipped config (SURVEY.md §2 #11)")
+        else:
+            shaded_col, shading = lgt.shade(feat, kd, cam_normal)
+    else:
+        raise NotImplementedError("bsdf '%s': only 'diffuse' is used by the shipped configs" % bsdf)
+    buffers = {"shaded": shaded_col, "kd": kd, "ks": ks}
+    if "geo_nrm" in gb:
+        buffers["geo_normal"] = (gb["geo_nrm"] + 1.0) * 0.5
+    if "shading_nrm" in gb:
+        buffers["normal"] = (gb["shading_nrm"] + 1.0) * 0.5
+    if shading is not None:
+        buffers["shading"] = shading
+    if dino_net is not None:
+        buffers["dino_pred"] = dino_net.sample(gb_tex_pos, feat=class_vector)
+    if "flow" in render_modes:  # render.py:281-288
+        c2 = v_pos_clip[..., :2] / v_pos_clip[..., -1:]
+        c2 = c2.view(-1, num_frames, *c2.shape[1:])
+        dxy = c2[:, 1:] - c2[:, :-1]
+        dxy = torch.cat([dxy, torch.zeros_like(dxy[:, :1])], dim=1).view(-1, *c2.shape[2:])
+        buffers["flow"] = ops.interpolate(dxy, rast_s, tri)
+    if "depth" in render_modes:  # render.py:102-108
+        gb_pos = gb["pos"]
+        hom = torch.cat([gb_pos, torch.ones_like(gb_pos[..., :1])], dim=-1)
+        depth = torch.matmul(hom.view(B, -1, 4), w2c.transpose(-1, -2)).view(B, gH, gW, 4)[..., 2]
+        dmin, dmax = depth.amin(dim=(1, 2), keepdim=True), depth.amax(dim=(1, 2), keepdim=True)
+        buffers["depth"] = ((depth - dmin) / (dmax - dmin)).unsqueeze(-1)
+
+    # background (render.py:298-304)
+    if background is not None:
+        bg_full = _nearest_up(background.float(), spp)
+        bg_full = torch.cat((bg_full, torch.zeros_like(bg_full[..., 0:1])), dim=-1)
+    else:
+        bg_full = None
+
+    out_buffers = []
+    for key in render_modes:
+        if key not in buffers:
+            out_buffers.append(None)
+            continue
+        color = _nearest_up(buffers[key].float(), shade_spp)
+        bg = bg_full if key in _BG_KEYS else None
+        if key == "shading" and bg is not None:
+            bg = bg[..., 2:].contiguous()
+        Cc = color.shape[-1] + 1
+        keep = Cc if key == "shaded" else (Cc - 1 if key == "dino_pred" else _KEEP[key])
+        accum = ops.composite_antialias(color, bg, rast, v_pos_clip, tri, opp, antialias_edges=key in _AA_KEYS, keep=keep)
+        if spp > 1:
+            accum = torch.nn.functional.avg_pool2d(accum.permute(0, 3, 1, 2), spp)
+            out_buffers.append(accum)
+        else:
+            out_buffers.append(accum.permute(0, 3, 1, 2))
+    return out_buffers
+
+
+def render_uv(ctx, mesh, resolution, mlp_texture, feat=None):
+    """Reference render.py:342-360: rasterize the UV atlas and sample the texture field at world positions."""
+    uv_clip = mesh.v_tex * 2.0 - 1.0
+    uv_clip4 = torch.cat((uv_clip, torch.zeros_like(uv_clip[..., 0:1]), torch.ones_like(uv_clip[..., 0:1])), dim=-1)
+    rast = ops.rasterize(uv_clip4.contiguous(), mesh.t_tex_idx[0].int(), resolution)
+    gb_pos, _ = interpolate(mesh.v_pos, rast, mesh.t_pos_idx[0].int())
+    all_tex = mlp_texture.sample(gb_pos, feat=feat)
+    assert all_tex.shape[-1] == 9 or all_tex.shape[-1] == 10, "Combined kd_ks_normal must be 9 or 10 channels"
+    nrm = all_tex[..., -3:]
+    nrm = nrm / torch.sqrt(torch.clamp(torch.sum(nrm * nrm, -1, keepdim=True), min=1e-20))
+    return (rast[..., -1:] > 0).float(), all_tex[..., :-6], all_tex[..., -6:-3], nrm

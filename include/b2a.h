@@ -1,0 +1,167 @@
+/*
+ * b2a.h - C ABI of libb2a.so: the B200-native (sm_100a) reconstruction hot path of 3DAnimals.
+ *
+ * Drop-in boundary.  Every entry point takes plain device pointers + sizes + a cudaStream_t and
+ * returns 0 on success / non-zero on error (message: b2a_last_error_string(), thread-local).  The library never
+ * allocates, frees or retains device memory; the caller owns inputs, outputs and workspaces and keeps them alive
+ * until the stream work completes.  No host synchronisation happens inside any call.  All floating point is fp32,
+ * contiguous row-major; index buffers are int32 unless a parameter says i64.
+ *
+ * Each group cites the reference interface it replaces (paths relative to the reference repo root).
+ */
+#ifndef B2A_H
+#define B2A_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b2a_stream_t; /* cudaStream_t */
+
+#define B2A_VERSION 100
+
+int b2a_version(void);
+const char* b2a_last_error_string(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Marching tetrahedra.  Replaces DMTet.__call__ (model/geometry/dmtet.py:104-155) and its autograd backward.
+ * Static per-grid tables (built once at load_tets time, dmtet.py:214-226 / generate_edges :283-288):
+ *   edge_start [Vg+1], edge_b [E]  = CSR of the unique sorted (min,max) grid edges, lexicographic.
+ * Two phases so the caller can size exact outputs with ONE device->host read of `counts`:
+ *   count: counts[0]=V (crossing edges), counts[1]=N1 (tets with 1 triangle), counts[2]=N2 (tets with 2).
+ *   emit : verts [V,3], vert_edge [V,2] (grid-vertex pair of each output vertex, for the backward),
+ *          faces ordered [1-triangle tets in tet order][2-triangle tets in tet order] (dmtet.py:140-143),
+ *          uv_idx = (4t, 4t+k+1, 4t+k+2) for tet t / k-th triangle (map_uv :69-98).  Any of the face outputs
+ *          may be NULL.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_mt_workspace_bytes(int64_t Vg, int64_t E, int64_t T, size_t* bytes);
+int b2a_mt_count(const float* sdf, const int32_t* tets, const int32_t* edge_start, const int32_t* edge_b,
+                 int64_t Vg, int64_t E, int64_t T, void* workspace, size_t workspace_bytes,
+                 int32_t* counts /* device [4] */, b2a_stream_t stream);
+int b2a_mt_emit(const float* pos, const float* sdf, const int32_t* tets, const int32_t* edge_start,
+                const int32_t* edge_b, int64_t Vg, int64_t E, int64_t T, void* workspace, size_t workspace_bytes,
+                int64_t V, int64_t N1, int64_t N2,
+                float* verts, int32_t* vert_edge, int32_t* faces_i32, int64_t* faces_i64, int64_t* uv_idx_i64,
+                b2a_stream_t stream);
+/* d_sdf [Vg] and d_pos [Vg,3] (nullable) must be zero-initialised by the caller; gradients are accumulated. */
+int b2a_mt_bwd(const float* pos, const float* sdf, const int32_t* vert_edge, const float* d_verts, int64_t V,
+               float* d_sdf, float* d_pos, b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Linear blend skinning.  Replaces skinning() (model/geometry/skinning.py:369-439) incl.
+ * _compute_vertices_to_bones_weights (:16-22), line_segment_distance (geometry/util.py:30-53),
+ * _estimate_bone_rotation (:251-270), euler_angles_to_matrix 'XYZ' (:315-340).
+ * B = batch*frames.  bones [Bb,K,2,3] (Bb in {1,B}), angles [B,K,3] rad, v_pos [Bv,V,3] (Bv in {1,B}).
+ * chain_ptr [K+1], chain_ids: for bone k the bones whose local transforms are multiplied, root first, k last.
+ * G, T_local: [B,K,12] row-major 3x4 affine.  weights (nullable): [K,Bw,V], Bw = max(Bv,Bb).
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_lbs_bone_transforms(const float* bones, const float* angles, const int32_t* chain_ptr,
+                            const int32_t* chain_ids, int B, int Bb, int K, float* T_local, float* G,
+                            float* posed_bones /* nullable [B,K,2,3] */, b2a_stream_t stream);
+int b2a_lbs_fwd(const float* v_pos, const float* bones, const float* G, int B, int Bv, int Bb, int K, int64_t V,
+                float inv_temperature, float* out /* [B,V,3] */, float* weights /* nullable */, b2a_stream_t stream);
+/* d_v_pos [Bv,V,3] zero-initialised when Bv==1<B (accumulated), else written; d_G [B,K,12] zero-initialised. */
+int b2a_lbs_bwd(const float* v_pos, const float* bones, const float* G, const float* d_out, int B, int Bv, int Bb,
+                int K, int64_t V, float inv_temperature, float* d_v_pos /* nullable */, float* d_G,
+                b2a_stream_t stream);
+/* d_G is consumed (d_posed_bones, nullable, is folded into it); d_T_local [B,K,12] is zero-initialised scratch. */
+int b2a_lbs_bone_transforms_bwd(const float* bones, const float* angles, const int32_t* chain_ptr,
+                                const int32_t* chain_ids, const float* T_local, float* d_G,
+                                const float* d_posed_bones, int B, int Bb, int K, float* d_T_local,
+                                float* d_angles /* [B,K,3] */, b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Smooth vertex normals.  Replaces mesh.auto_normals (model/render/mesh.py:276-304).
+ * nsum [B,V,3] is the un-normalised area-weighted sum (kept for the backward).
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_vertex_normals_fwd(const float* v_pos, const int32_t* tri, int B, int64_t V, int64_t F, float* nsum,
+                           float* v_nrm, b2a_stream_t stream);
+/* scratch [B,V,3]; d_v_pos [B,V,3] zero-initialised by the caller (accumulated). */
+int b2a_vertex_normals_bwd(const float* v_pos, const int32_t* tri, const float* nsum, const float* d_v_nrm, int B,
+                           int64_t V, int64_t F, float* scratch, float* d_v_pos, b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Clip-space transform.  Replaces ru.xfm_points(use_python=True) (model/render/renderutils/ops.py:524-525).
+ * pts [Bp,V,3] (Bp in {1,B}), mtx [B,4,4] -> out [B,V,4].  Backward: d_pts accumulated when Bp==1<B (zero-init),
+ * d_mtx [B,16] accumulated (zero-init); either may be NULL.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_xfm_points_fwd(const float* pts, const float* mtx, int B, int Bp, int64_t V, float* out, b2a_stream_t stream);
+int b2a_xfm_points_bwd(const float* pts, const float* mtx, const float* d_out, int B, int Bp, int64_t V,
+                       float* d_pts, float* d_mtx, b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Rasterizer.  Replaces nvdiffrast.torch.rasterize / DepthPeeler first layer (call sites model/render/render.py:
+ * 292-294, :351).  pos [B,V,4] clip space, tri [F,3]; rast [B,H,W,4] = (u, v, z/w, id+1).  Fill rule: oracle/
+ * raster_ref.c header.  workspace: b2a_rasterize_workspace_bytes (z-buffer keys + large-triangle queue).
+ * Backward: d_rast[...,0:2] -> d_pos (x,y,w), accumulated into zero-initialised d_pos [B,V,4].
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_rasterize_workspace_bytes(int B, int64_t F, int H, int W, size_t* bytes);
+int b2a_rasterize_fwd(const float* pos, const int32_t* tri, int B, int64_t V, int64_t F, int H, int W,
+                      void* workspace, size_t workspace_bytes, float* rast, b2a_stream_t stream);
+int b2a_rasterize_bwd(const float* pos, const int32_t* tri, const float* rast, const float* d_rast, int B, int64_t V,
+                      int64_t F, int H, int W, float* d_pos, b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Attribute interpolation.  Replaces nvdiffrast.torch.interpolate (render.py:24, :182-209).
+ * attr [Ba,V,C] (Ba in {1,B}); out [B,H,W,C].  Backward: d_attr accumulated (zero-init, nullable),
+ * d_rast [B,H,W,4] written (u,v grads; z,w = 0; nullable).
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_interpolate_fwd(const float* attr, const float* rast, const int32_t* tri, int B, int Ba, int64_t V, int64_t F,
+                        int H, int W, int C, float* out, b2a_stream_t stream);
+int b2a_interpolate_bwd(const float* attr, const float* rast, const int32_t* tri, const float* d_out, int B, int Ba,
+                        int64_t V, int64_t F, int H, int W, int C, float* d_attr, float* d_rast, b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Antialiasing (+ optional fused composite).  Replaces nvdiffrast.torch.antialias and the lerp composite in
+ * render_mesh.composite_buffer (model/render/render.py:258-268).
+ *   edge adjacency: opp [F,3] = vertex opposite edge e in the neighbouring triangle, -1 if none
+ *                   (e=0:(v1,v2), 1:(v2,v0), 2:(v0,v1)); built once per topology.
+ *   composite = 0 : `color` is [B,H,W,C]; out [B,H,W,C].
+ *   composite = 1 : `color` is [B,H,W,C-1] (no alpha, C >= 2); the blended input is
+ *                   lerp(bg, [color,1], id>0) with bg [Bg,H,W,C] (Bg in {1,B}) or NULL (zeros).
+ * Backward: d_out has Cg <= C channels (the channels the caller sliced off carry zero gradient) and arbitrary
+ * element strides (sb,sy,sx,sc) (NCHW or NHWC views both fine); d_color (nullable) has the layout of `color`;
+ * d_pos [B,V,4] accumulated (zero-init, nullable).
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_edge_adjacency_workspace_bytes(int64_t F, size_t* bytes);
+int b2a_edge_adjacency(const int32_t* tri, int64_t F, int64_t V, void* workspace, size_t workspace_bytes,
+                       int32_t* opp, b2a_stream_t stream);
+int b2a_antialias_fwd(const float* color, const float* bg, int Bg, int composite, const float* rast, const float* pos,
+                      const int32_t* tri, const int32_t* opp, int B, int64_t V, int64_t F, int H, int W, int C,
+                      float* out, b2a_stream_t stream);
+int b2a_antialias_bwd(const float* color, const float* bg, int Bg, int composite, const float* rast, const float* pos,
+                      const int32_t* tri, const int32_t* opp, const float* d_out, int64_t d_sb, int64_t d_sy,
+                      int64_t d_sx, int64_t d_sc, int Cg, int B, int64_t V, int64_t F, int H, int W, int C,
+                      float* d_color, float* d_pos, b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused g-buffer pass (fast path of render_layer + shade's geometry part, model/render/render.py:160-209, :72-75):
+ * interpolate v_pos, v_nrm, prior v_pos and the per-face normal at each covered pixel; prepare_shading_normal
+ * (renderutils/ops.py:194-227 -> bsdf.py:46-51 with perturbed normal (0,0,1)); camera-space normal
+ * safe_normalize(n . R_w2c^T) (render.py:75).
+ * rast is the rasterizer output at [B,H*spp,W*spp,4]; the g-buffer is shaded at [H,W] from the nearest-downscaled
+ * rast (pixel (x*spp, y*spp)), which is what render_layer does when msaa is on (render.py:170-172).
+ * Outputs (each nullable): gb_pos, gb_geo_nrm, gb_shading_nrm, gb_cam_nrm, gb_tex_pos [B,H,W,3].
+ * v_pos, v_nrm [B,V,3]; prior_pos [Bq,V,3] (Bq in {1,B}); w2c [B,4,4]; campos [B,3].
+ * Backward consumes the same inputs, pos_clip [B,V,4] and the (nullable) output grads and accumulates into
+ * zero-initialised (each nullable) d_v_pos [B,V,3], d_v_nrm [B,V,3], d_prior_pos [Bq,V,3], d_clip [B,V,4] (x,y,w),
+ * d_w2c [B,16], d_campos [B,3].
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_gbuffer_fwd(const float* rast, int spp, const int32_t* tri, const float* v_pos, const float* v_nrm,
+                    const float* prior_pos, int Bq, const float* w2c, const float* campos, int two_sided, int B,
+                    int64_t V, int64_t F, int H, int W, float* gb_pos, float* gb_geo_nrm, float* gb_shading_nrm,
+                    float* gb_cam_nrm, float* gb_tex_pos, b2a_stream_t stream);
+int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, const int32_t* tri, const float* v_pos,
+                    const float* v_nrm, const float* prior_pos, int Bq, const float* w2c, const float* campos,
+                    int two_sided, int B, int64_t V, int64_t F, int H, int W, const float* d_gb_pos,
+                    const float* d_gb_geo_nrm, const float* d_gb_shading_nrm, const float* d_gb_cam_nrm,
+                    const float* d_gb_tex_pos, float* d_v_pos, float* d_v_nrm, float* d_prior_pos, float* d_clip,
+                    float* d_w2c, float* d_campos, b2a_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2A_H */

@@ -1,0 +1,96 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own Python (build container only: needs /root/reference).
+
+    python tests/golden/make_goldens.py
+
+The reference ships no golden vectors or tests for the hot path, so these pin it: the reference's
+`DMTet.__call__`, `estimate_bones`, `skinning` (+ autograd grads) and `bsdf_prepare_shading_normal`, loaded by file
+path on CPU tensors (oracle/reference_loader.py), on small seeded inputs.  The fixtures travel to the GPU box; the
+reference tree does not.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import reference_loader  # noqa: E402
+
+syn = importlib.import_module("3danimals_b200.synthetic")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def mt_cases():
+    ref = reference_loader.load()
+    mt = reference_loader.reference_dmtet("cpu")
+    for res in (12, 20):
+        v, t = syn.kuhn_tet_grid(res)
+        v = v * np.float32(7.0)
+        for name, sdf in (("ellipsoid", syn.sdf_ellipsoid(v)), ("noisy_sphere", syn.sdf_noisy_sphere(v, 1.75, 0.05, 0)),
+                          ("two_blobs", syn.sdf_two_blobs(v)), ("horse", syn.sdf_horse(v, 0.01, 0))):
+            pos = torch.from_numpy(v)
+            s = torch.from_numpy(sdf)[:, None].clone().requires_grad_(True)
+            verts, faces, uvs, uv_idx = mt(pos, s, torch.from_numpy(t))
+            g = torch.from_numpy(np.random.RandomState(5).randn(*verts.shape).astype(np.float32))
+            (verts * g).sum().backward()
+            np.savez_compressed(os.path.join(OUT, "mt_%s_%d.npz" % (name, res)), res=res, sdf=sdf, verts=verts.detach().numpy(),
+                                faces=faces.numpy().astype(np.int32), uv_idx=uv_idx.numpy().astype(np.int64),
+                                uvs_shape=np.array(uvs.shape), uvs_head=uvs[:64].numpy(), uvs_sum=uvs.double().sum().item(),
+                                d_verts=g.numpy(), d_sdf=s.grad.numpy().reshape(-1))
+    del ref
+
+
+def skin_cases():
+    ref = reference_loader.load()
+    mt = reference_loader.reference_dmtet("cpu")
+    v, t = syn.kuhn_tet_grid(20)
+    v = v * np.float32(7.0)
+    verts, faces, _, _ = mt(torch.from_numpy(v), torch.from_numpy(syn.sdf_horse(v, 0.0, 0))[:, None], torch.from_numpy(t))
+    verts = verts.detach()
+    for name, n_leg, mode, B in (("horse", 3, "z_minmax_y+", 2), ("bird", 0, "z_minmax", 3)):
+        bones, chain, aux = ref.skinning.estimate_bones(verts[None, None], 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode,
+                                                        compute_kinematic_chain=True)
+        bones2 = ref.skinning.estimate_bones(verts[None, None] * 1.01, 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode,
+                                             compute_kinematic_chain=False, aux=aux)
+        K = bones.shape[2]
+        rng = np.random.RandomState(11)
+        ang = torch.from_numpy(rng.uniform(-0.5, 0.5, (B, 1, K, 3)).astype(np.float32)).requires_grad_(True)
+        vp = verts[None, None].clone().requires_grad_(True)
+        out, saux = ref.skinning.skinning(vp, bones, chain, ang, output_posed_bones=True, temperature=0.05)
+        g = torch.from_numpy(rng.randn(*out.shape).astype(np.float32))
+        gp = torch.from_numpy(rng.randn(*saux["posed_bones"].shape).astype(np.float32))
+        ((out * g).sum() + (saux["posed_bones"] * gp).sum()).backward()
+        np.savez_compressed(os.path.join(OUT, "skin_%s.npz" % name), verts=verts.numpy(), faces=faces.numpy().astype(np.int32),
+                            n_leg_bones=n_leg, mode=mode, bones=bones.numpy(), bones_rescaled=bones2.numpy(),
+                            chain_ids=np.array([b for b, _ in chain]), chain_dep=np.array([",".join(map(str, d)) for _, d in chain]),
+                            angles=ang.detach().numpy(), out=out.detach().numpy(), posed_bones=saux["posed_bones"].detach().numpy(),
+                            weights=saux["vertices_to_bones"].detach().numpy(), g_out=g.numpy(), g_posed=gp.numpy(),
+                            d_angles=ang.grad.numpy(), d_verts=vp.grad.numpy())
+
+
+def shading_case():
+    ref = reference_loader.load()
+    rng = np.random.RandomState(21)
+    shp = (2, 6, 5, 3)
+    t = lambda: torch.from_numpy(rng.randn(*shp).astype(np.float32))
+    pos, nrm, tng, geo = t(), t(), t(), t()
+    view = torch.from_numpy(rng.randn(2, 1, 1, 3).astype(np.float32) * 3)
+    for x in (pos, nrm, geo):
+        x.requires_grad_(True)
+    pert = torch.tensor([0, 0, 1], dtype=torch.float32)[None, None, None]
+    out = ref.bsdf.bsdf_prepare_shading_normal(pos, view, pert, nrm, tng, geo, True, True)
+    g = t()
+    (out * g).sum().backward()
+    np.savez_compressed(os.path.join(OUT, "shading_normal.npz"), pos=pos.detach().numpy(), view=view.numpy(), nrm=nrm.detach().numpy(),
+                        tng=tng.numpy(), geo=geo.detach().numpy(), out=out.detach().numpy(), g=g.numpy(), d_pos=pos.grad.numpy(),
+                        d_nrm=nrm.grad.numpy(), d_geo=geo.grad.numpy())
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    mt_cases()
+    skin_cases()
+    shading_case()
+    print(sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))

@@ -1,0 +1,69 @@
+"""The CPU oracle against the committed golden vectors (generated from the reference's own Python by
+tests/golden/make_goldens.py).  This is what pins the oracle everywhere, including the GPU box."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_files, pkg, rel_err
+from oracle import geometry_np as gnp
+from oracle import torch_ref as T
+
+syn = pkg("synthetic")
+
+
+@pytest.mark.parametrize("name", golden_files("mt_"))
+def test_marching_tets_matches_reference(name):
+    g = golden(name)
+    v, t = syn.kuhn_tet_grid(int(g["res"]))
+    v = v * np.float32(7.0)
+    o = gnp.marching_tets(v, g["sdf"], t, with_uvs=True)
+    assert np.array_equal(o["faces"], g["faces"])          # bit-exact index buffers
+    assert np.array_equal(o["uv_idx"], g["uv_idx"])
+    assert o["verts"].shape == g["verts"].shape
+    assert rel_err(o["verts"], g["verts"]) < 1e-6
+    assert tuple(o["uvs"].shape) == tuple(g["uvs_shape"])
+    assert np.allclose(o["uvs"][:64], g["uvs_head"], atol=1e-7)
+    d_sdf, _ = gnp.lerp_vertices_bwd(v, g["sdf"], o["interp_v"], g["d_verts"])
+    assert rel_err(d_sdf, g["d_sdf"]) < 1e-4
+
+
+def _chain(g):
+    return [(int(b), [int(x) for x in str(d).split(",") if x != ""]) for b, d in zip(g["chain_ids"], g["chain_dep"])]
+
+
+@pytest.mark.parametrize("name", golden_files("skin_"))
+def test_bones_and_skinning_match_reference(name):
+    g = golden(name)
+    verts = g["verts"]
+    n_leg, mode = int(g["n_leg_bones"]), str(g["mode"])
+    bones, chain, aux = gnp.estimate_bones(verts[None, None], 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode)
+    assert chain == _chain(g)
+    assert np.allclose(bones, g["bones"], atol=1e-6)
+    bones2 = gnp.estimate_bones(verts[None, None] * np.float32(1.01), 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode,
+                                compute_kinematic_chain=False, aux=aux)
+    assert np.allclose(bones2, g["bones_rescaled"], atol=1e-6)
+    out, w, posed = gnp.skinning(verts[None, None], g["bones"], chain, g["angles"], temperature=0.05)
+    assert rel_err(out, g["out"]) < 1e-5
+    assert rel_err(posed, g["posed_bones"]) < 1e-5
+    assert np.abs(w - g["weights"]).max() < 1e-5
+    # torch twin incl. gradients
+    ang = torch.from_numpy(g["angles"]).requires_grad_(True)
+    vp = torch.from_numpy(verts)[None, None].clone().requires_grad_(True)
+    o2, aux2 = T.skinning(vp, torch.from_numpy(g["bones"]), chain, ang, temperature=0.05)
+    ((o2 * torch.from_numpy(g["g_out"])).sum() + (aux2["posed_bones"] * torch.from_numpy(g["g_posed"])).sum()).backward()
+    assert rel_err(o2.detach().numpy(), g["out"]) < 1e-5
+    assert rel_err(ang.grad.numpy(), g["d_angles"]) < 1e-4
+    assert rel_err(vp.grad.numpy(), g["d_verts"]) < 1e-4
+
+
+def test_shading_normal_matches_reference():
+    g = golden("shading_normal.npz")
+    t = lambda k: torch.from_numpy(g[k]).requires_grad_(True)
+    pos, nrm, geo = t("pos"), t("nrm"), t("geo")
+    for tng in (torch.from_numpy(g["tng"]), None):  # the tangent is numerically dead
+        out = T.prepare_shading_normal(pos, torch.from_numpy(g["view"]), nrm, tng, geo, True)
+        assert rel_err(out.detach().numpy(), g["out"]) < 1e-6
+    (out * torch.from_numpy(g["g"])).sum().backward()
+    assert rel_err(pos.grad.numpy(), g["d_pos"]) < 1e-4
+    assert rel_err(nrm.grad.numpy(), g["d_nrm"]) < 1e-4
+    assert rel_err(geo.grad.numpy(), g["d_geo"]) < 1e-4
