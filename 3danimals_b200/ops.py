@@ -43,6 +43,58 @@ def _workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+# kernels launched by each C-ABI entry point (memsets / memcpys are not kernels) - the source of bench.py's gpu_launches
+KERNELS_PER_CALL = {
+    "b2a_mt_count": 4, "b2a_mt_emit": 2, "b2a_mt_bwd": 1, "b2a_lbs_bone_transforms": 2, "b2a_lbs_fwd": 1, "b2a_lbs_bwd": 1,
+    "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1,
+    "b2a_xfm_points_bwd": 1, "b2a_rasterize_fwd": 3, "b2a_rasterize_bwd": 1, "b2a_interpolate_fwd": 1, "b2a_interpolate_bwd": 1,
+    "b2a_edge_adjacency": 3, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 1, "b2a_gbuffer_fwd": 1, "b2a_gbuffer_bwd": 1,
+}
+
+
+class CallStats:
+    """Launch counter and optional per-call CUDA-event timer (events are recorded on the stream the kernels are
+    launched on).  bench.py enables timing to measure the raster-backward kernels live inside the timed step."""
+
+    def __init__(self):
+        self.launches = 0
+        self.calls = {}
+        self.timing = False
+        self.events = []      # (name, tag, start_event, end_event)
+        self.tag = ""
+
+    def reset(self):
+        self.launches = 0
+        self.calls = {}
+        self.events = []
+
+    def durations_ms(self):
+        """{(name, tag): [ms, ...]} - call after torch.cuda.synchronize()."""
+        out = {}
+        for name, tag, e0, e1 in self.events:
+            out.setdefault((name, tag), []).append(e0.elapsed_time(e1))
+        return out
+
+
+stats = CallStats()
+
+
+def _call(name, args):
+    fn = getattr(_L(), name)
+    if stats.timing:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        stats.events.append((name, stats.tag, e0, e1))
+    else:
+        rc = fn(*args)
+    stats.launches += KERNELS_PER_CALL[name]
+    stats.calls[name] = stats.calls.get(name, 0) + 1
+    _lib.check(rc)
+
+
 def _size(fn, *args):
     import ctypes
     out = ctypes.c_size_t(0)
@@ -101,7 +153,7 @@ class _MarchingTets(torch.autograd.Function):
         if pos_c.shape[0] != grid.Vg or sdf_c.shape[0] != grid.Vg:
             raise _lib.B2AError("marching_tets: pos/sdf do not match the grid (%d verts)" % grid.Vg)
         st = _stream()
-        _lib.check(L.b2a_mt_count(_p(sdf_c), _p(grid.tets), _p(grid.edge_start), _p(grid.edge_b), grid.Vg, grid.E, grid.T,
+        _call("b2a_mt_count", (_p(sdf_c), _p(grid.tets), _p(grid.edge_start), _p(grid.edge_b), grid.Vg, grid.E, grid.T,
                                   _p(grid.workspace), grid.workspace.numel(), _p(grid.counts), st))
         V, N1, N2, err = grid.counts.tolist()  # the one device->host read of the extraction (output sizes)
         if err:
@@ -113,7 +165,7 @@ class _MarchingTets(torch.autograd.Function):
         faces = torch.empty(Fn, 3, dtype=torch.int64, device=dev)
         faces32 = torch.empty(Fn, 3, dtype=_i32, device=dev)
         uv_idx = torch.empty(Fn, 3, dtype=torch.int64, device=dev)
-        _lib.check(L.b2a_mt_emit(_p(pos_c), _p(sdf_c), _p(grid.tets), _p(grid.edge_start), _p(grid.edge_b), grid.Vg, grid.E,
+        _call("b2a_mt_emit", (_p(pos_c), _p(sdf_c), _p(grid.tets), _p(grid.edge_start), _p(grid.edge_b), grid.Vg, grid.E,
                                  grid.T, _p(grid.workspace), grid.workspace.numel(), V, N1, N2, _p(verts), _p(vert_edge),
                                  _p(faces32), _p(faces), _p(uv_idx), st))
         ctx.save_for_backward(pos_c, sdf_c, vert_edge)
@@ -130,7 +182,7 @@ class _MarchingTets(torch.autograd.Function):
         V = vert_edge.shape[0]
         if V > 0:
             g = _f32(d_verts, "d_verts")
-            _lib.check(_L().b2a_mt_bwd(_p(pos_c), _p(sdf_c), _p(vert_edge), _p(g), V, _p(d_sdf), _p(d_pos), _stream()))
+            _call("b2a_mt_bwd", (_p(pos_c), _p(sdf_c), _p(vert_edge), _p(g), V, _p(d_sdf), _p(d_pos), _stream()))
         return (d_pos.reshape(ctx.shapes[0]) if need_pos else None), d_sdf.reshape(ctx.shapes[1]), None
 
 
@@ -171,12 +223,12 @@ class _LBS(torch.autograd.Function):
         T_local = torch.empty(B, K, 12, device=dev)
         G = torch.empty(B, K, 12, device=dev)
         posed = torch.empty(B, K, 2, 3, device=dev)
-        _lib.check(L.b2a_lbs_bone_transforms(_p(bones), _p(angles), _p(chain_ptr), _p(chain_ids), B, Bb, K, _p(T_local), _p(G),
+        _call("b2a_lbs_bone_transforms", (_p(bones), _p(angles), _p(chain_ptr), _p(chain_ids), B, Bb, K, _p(T_local), _p(G),
                                              _p(posed), st))
         out = torch.empty(B, V, 3, device=dev)
         Bw = max(Bv, Bb)
         weights = torch.empty(K, Bw, V, device=dev) if want_weights else None
-        _lib.check(L.b2a_lbs_fwd(_p(v_pos), _p(bones), _p(G), B, Bv, Bb, K, V, 1.0 / float(temperature), _p(out), _p(weights), st))
+        _call("b2a_lbs_fwd", (_p(v_pos), _p(bones), _p(G), B, Bv, Bb, K, V, 1.0 / float(temperature), _p(out), _p(weights), st))
         ctx.save_for_backward(v_pos, bones, angles, chain_ptr, chain_ids, T_local, G)
         ctx.inv_t = 1.0 / float(temperature)
         if weights is None:
@@ -199,13 +251,13 @@ class _LBS(torch.autograd.Function):
             d_v = torch.zeros(Bv, V, 3, device=dev)
         if d_out is not None and V > 0:
             g = _f32(d_out, "d_out")
-            _lib.check(L.b2a_lbs_bwd(_p(v_pos), _p(bones), _p(G), _p(g), B, Bv, Bb, K, V, ctx.inv_t, _p(d_v), _p(d_G), st))
+            _call("b2a_lbs_bwd", (_p(v_pos), _p(bones), _p(G), _p(g), B, Bv, Bb, K, V, ctx.inv_t, _p(d_v), _p(d_G), st))
         d_angles = None
         if ctx.needs_input_grad[2]:
             d_T = torch.zeros(B, K, 12, device=dev)
             d_angles = torch.empty(B, K, 3, device=dev)
             gp = _f32(d_posed, "d_posed") if d_posed is not None else None
-            _lib.check(L.b2a_lbs_bone_transforms_bwd(_p(bones), _p(angles), _p(chain_ptr), _p(chain_ids), _p(T_local), _p(d_G),
+            _call("b2a_lbs_bone_transforms_bwd", (_p(bones), _p(angles), _p(chain_ptr), _p(chain_ids), _p(T_local), _p(d_G),
                                                      _p(gp), B, Bb, K, _p(d_T), _p(d_angles), st))
         return d_v, None, d_angles, None, None, None, None
 
@@ -227,7 +279,7 @@ class _VertexNormals(torch.autograd.Function):
         F = tri.shape[0]
         nsum = torch.empty_like(v_pos)
         nrm = torch.empty_like(v_pos)
-        _lib.check(_L().b2a_vertex_normals_fwd(_p(v_pos), _p(tri), B, V, F, _p(nsum), _p(nrm), _stream()))
+        _call("b2a_vertex_normals_fwd", (_p(v_pos), _p(tri), B, V, F, _p(nsum), _p(nrm), _stream()))
         ctx.save_for_backward(v_pos, tri, nsum)
         return nrm
 
@@ -238,7 +290,7 @@ class _VertexNormals(torch.autograd.Function):
         g = _f32(g, "d_nrm")
         scratch = torch.empty_like(v_pos)
         d_pos = torch.zeros_like(v_pos)
-        _lib.check(_L().b2a_vertex_normals_bwd(_p(v_pos), _p(tri), _p(nsum), _p(g), B, V, tri.shape[0], _p(scratch), _p(d_pos),
+        _call("b2a_vertex_normals_bwd", (_p(v_pos), _p(tri), _p(nsum), _p(g), B, V, tri.shape[0], _p(scratch), _p(d_pos),
                                                _stream()))
         return d_pos, None
 
@@ -257,7 +309,7 @@ class _XfmPoints(torch.autograd.Function):
         pts = _f32(pts, "points"); mtx = _f32(mtx, "matrix")
         B, Bp, V = mtx.shape[0], pts.shape[0], pts.shape[1]
         out = torch.empty(B, V, 4, device=pts.device)
-        _lib.check(_L().b2a_xfm_points_fwd(_p(pts), _p(mtx), B, Bp, V, _p(out), _stream()))
+        _call("b2a_xfm_points_fwd", (_p(pts), _p(mtx), B, Bp, V, _p(out), _stream()))
         ctx.save_for_backward(pts, mtx)
         return out
 
@@ -268,7 +320,7 @@ class _XfmPoints(torch.autograd.Function):
         g = _f32(g, "d_out")
         d_pts = torch.zeros_like(pts) if ctx.needs_input_grad[0] else None
         d_mtx = torch.zeros_like(mtx) if ctx.needs_input_grad[1] else None
-        _lib.check(_L().b2a_xfm_points_bwd(_p(pts), _p(mtx), _p(g), B, Bp, V, _p(d_pts), _p(d_mtx), _stream()))
+        _call("b2a_xfm_points_bwd", (_p(pts), _p(mtx), _p(g), B, Bp, V, _p(d_pts), _p(d_mtx), _stream()))
         return d_pts, d_mtx
 
 
@@ -289,7 +341,7 @@ class _Rasterize(torch.autograd.Function):
         F = tri.shape[0]
         ws = _workspace(_size(L.b2a_rasterize_workspace_bytes, B, F, H, W), pos.device)
         rast = torch.empty(B, H, W, 4, device=pos.device)
-        _lib.check(L.b2a_rasterize_fwd(_p(pos), _p(tri), B, V, F, H, W, _p(ws), ws.numel(), _p(rast), _stream()))
+        _call("b2a_rasterize_fwd", (_p(pos), _p(tri), B, V, F, H, W, _p(ws), ws.numel(), _p(rast), _stream()))
         ctx.save_for_backward(pos, tri, rast)
         return rast
 
@@ -300,7 +352,7 @@ class _Rasterize(torch.autograd.Function):
         H, W = rast.shape[1], rast.shape[2]
         g = _f32(g, "d_rast")
         d_pos = torch.zeros_like(pos)
-        _lib.check(_L().b2a_rasterize_bwd(_p(pos), _p(tri), _p(rast), _p(g), B, V, tri.shape[0], H, W, _p(d_pos), _stream()))
+        _call("b2a_rasterize_bwd", (_p(pos), _p(tri), _p(rast), _p(g), B, V, tri.shape[0], H, W, _p(d_pos), _stream()))
         return d_pos, None, None, None
 
 
@@ -318,7 +370,7 @@ class _Interpolate(torch.autograd.Function):
         B, H, W = rast.shape[0], rast.shape[1], rast.shape[2]
         Ba, V, Cc = attr.shape
         out = torch.empty(B, H, W, Cc, device=attr.device)
-        _lib.check(_L().b2a_interpolate_fwd(_p(attr), _p(rast), _p(tri), B, Ba, V, tri.shape[0], H, W, Cc, _p(out), _stream()))
+        _call("b2a_interpolate_fwd", (_p(attr), _p(rast), _p(tri), B, Ba, V, tri.shape[0], H, W, Cc, _p(out), _stream()))
         ctx.save_for_backward(attr, rast, tri)
         return out
 
@@ -330,7 +382,7 @@ class _Interpolate(torch.autograd.Function):
         g = _f32(g, "d_out")
         d_attr = torch.zeros_like(attr) if ctx.needs_input_grad[0] else None
         d_rast = torch.empty_like(rast) if ctx.needs_input_grad[1] else None
-        _lib.check(_L().b2a_interpolate_bwd(_p(attr), _p(rast), _p(tri), _p(g), B, Ba, V, tri.shape[0], H, W, Cc, _p(d_attr),
+        _call("b2a_interpolate_bwd", (_p(attr), _p(rast), _p(tri), _p(g), B, Ba, V, tri.shape[0], H, W, Cc, _p(d_attr),
                                             _p(d_rast), _stream()))
         return d_attr, d_rast, None
 
@@ -349,7 +401,7 @@ def edge_adjacency(tri, num_verts):
     F = tri.shape[0]
     ws = _workspace(_size(L.b2a_edge_adjacency_workspace_bytes, F), tri.device)
     opp = torch.empty(F, 3, dtype=_i32, device=tri.device)
-    _lib.check(L.b2a_edge_adjacency(_p(tri), F, int(num_verts), _p(ws), ws.numel(), _p(opp), _stream()))
+    _call("b2a_edge_adjacency", (_p(tri), F, int(num_verts), _p(ws), ws.numel(), _p(opp), _stream()))
     return opp
 
 
@@ -372,7 +424,7 @@ class _Antialias(torch.autograd.Function):
                 raise _lib.B2AError("antialias: background shape %s, expected [1|B,%d,%d,%d]" % (tuple(bg.shape), H, W, Cc))
             Bg = bg.shape[0]
         out = torch.empty(B, H, W, Cc, device=color.device)
-        _lib.check(_L().b2a_antialias_fwd(_p(color), _p(bg), Bg, int(composite), _p(rast), _p(pos), _p(tri), _p(opp), B, pos.shape[1],
+        _call("b2a_antialias_fwd", (_p(color), _p(bg), Bg, int(composite), _p(rast), _p(pos), _p(tri), _p(opp), B, pos.shape[1],
                                           tri.shape[0], H, W, Cc, _p(out), _stream()))
         ctx.save_for_backward(color, bg, rast, pos, tri, opp)
         ctx.cfg = (bool(composite), Bg, Cc, int(keep))
@@ -390,7 +442,7 @@ class _Antialias(torch.autograd.Function):
         d_color = torch.empty_like(color) if ctx.needs_input_grad[0] else None
         d_pos = torch.zeros_like(pos) if ctx.needs_input_grad[3] else None
         sb, sy, sx, sc = g.stride()
-        _lib.check(_L().b2a_antialias_bwd(_p(color), _p(bg), Bg, int(composite), _p(rast), _p(pos), _p(tri), _p(opp), _p(g), sb, sy, sx,
+        _call("b2a_antialias_bwd", (_p(color), _p(bg), Bg, int(composite), _p(rast), _p(pos), _p(tri), _p(opp), _p(g), sb, sy, sx,
                                           sc, keep, B, pos.shape[1], tri.shape[0], H, W, Cc, _p(d_color), _p(d_pos), _stream()))
         return d_color, None, None, d_pos, None, None, None, None
 
@@ -435,7 +487,7 @@ class _GBuffer(torch.autograd.Function):
         if rast.shape[0] != B or w2c.shape != (B, 4, 4) or campos.shape != (B, 3) or v_nrm.shape != v_pos.shape:
             raise _lib.B2AError("gbuffer: inconsistent batch shapes")
         outs = [torch.empty(B, H, W, 3, device=rast.device) if k in want else None for k in GB_KEYS]
-        _lib.check(_L().b2a_gbuffer_fwd(_p(rast), spp, _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0], _p(w2c),
+        _call("b2a_gbuffer_fwd", (_p(rast), spp, _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0], _p(w2c),
                                         _p(campos), int(two_sided), B, V, tri.shape[0], H, W, *[_p(o) for o in outs], _stream()))
         ctx.save_for_backward(rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos)
         ctx.cfg = (spp, int(two_sided), H, W, tuple(o is not None for o in outs))
@@ -455,7 +507,7 @@ class _GBuffer(torch.autograd.Function):
         d_w2c = torch.zeros_like(w2c) if need[6] else None
         d_campos = torch.zeros_like(campos) if need[7] else None
         if any(g is not None for g in gs):
-            _lib.check(_L().b2a_gbuffer_bwd(_p(rast), spp, _p(pos_clip), _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0],
+            _call("b2a_gbuffer_bwd", (_p(rast), spp, _p(pos_clip), _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0],
                                             _p(w2c), _p(campos), two_sided, B, V, tri.shape[0], H, W, *[_p(g) for g in gs], _p(d_v_pos),
                                             _p(d_v_nrm), _p(d_prior), _p(d_clip), _p(d_w2c), _p(d_campos), _stream()))
         return None, d_clip, None, d_v_pos, d_v_nrm, d_prior, d_w2c, d_campos, None, None, None

@@ -13,8 +13,8 @@ Contents
   the restatements below and to generate ``tests/golden/*.npz``.
 * ``geometry_np``       numpy restatement of marching tets (R2), vertex normals
   (R3), bone estimation (R4), linear blend skinning (R5).
-* ``shading_np``        numpy/torch-free restatement of the shading-normal and
-  directional-light arithmetic (R8) plus clip transform / composite (R6, R9).
+* ``torch_ref``         torch-CPU restatement with autograd of R3/R5/R8 and render_mesh (R6-R9) over the C ops.
+* ``pipeline_ref``      the whole hot path on host cores (parity checker and CPU baseline of bench.py).
 * ``raster_ref.c``      C (OpenMP) restatement of the un-vendored nvdiffrast ops
   used by ``model/render/render.py`` (rasterize, interpolate, antialias) with
   forward and backward passes; built into ``oracle/_build/liboracle.so``.

@@ -302,8 +302,8 @@ def render_mesh(v_pos, v_nrm, faces, mtx, w2c, view_pos, shade_fn, resolution, s
             col = _scale_nearest(col, full)                                                    # :217-219
         aa = key in ("shaded", "flow", "dino_pred", "depth", "shading")                        # :311
         bg = bgf if key in ("shaded", "geo_normal", "shading") else torch.zeros(*col.shape[:-1], col.shape[-1] + 1)
-        if key == "shading" and background is not None:
-            bg = bg[..., 2:]
+        if key == "shading":                                                                   # :313-314 (always true there:
+            bg = bg[..., 2:]                                                                   #  `background` was reassigned :304)
         alpha = (rast[..., -1:] > 0).float()                                                   # :261
         accum = torch.lerp(bg.expand(B, -1, -1, -1), torch.cat((col, torch.ones_like(col[..., :1])), -1), alpha)
         if aa:

@@ -1,0 +1,371 @@
+"""GPU parity: every kernel of libb2a.so (called through the C-ABI wrappers in 3danimals_b200.ops) against the CPU
+oracle on the same seeded inputs.  Bar: bit-exact for index buffers (faces, uv indices, triangle ids, adjacency);
+<= 1e-4 relative (of the tensor's max magnitude) for fp32 buffers and gradients."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_files, pkg, rel_err
+from oracle import geometry_np as gnp
+from oracle import raster as R
+from oracle import torch_ref as T
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+syn = pkg("synthetic")
+
+
+def _ops():
+    return pkg("ops")
+
+
+def dev(x, cuda):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(cuda)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# marching tets
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_files("mt_"))
+def test_marching_tets_golden(cuda, name):
+    """Against the reference's own DMTet output (committed fixture)."""
+    ops = _ops()
+    g = golden(name)
+    v, t = syn.kuhn_tet_grid(int(g["res"]))
+    v = v * np.float32(7.0)
+    grid = ops.TetGrid(dev(t, cuda), v.shape[0])
+    sdf = dev(g["sdf"], cuda)[:, None].requires_grad_(True)
+    verts, faces, uv_idx, faces32, _ = ops.marching_tets(dev(v, cuda), sdf, grid)
+    assert np.array_equal(faces.cpu().numpy(), g["faces"])
+    assert np.array_equal(faces32.cpu().numpy(), g["faces"])
+    assert np.array_equal(uv_idx.cpu().numpy(), g["uv_idx"])
+    assert rel_err(verts.detach().cpu().numpy(), g["verts"]) < 1e-6
+    (verts * dev(g["d_verts"], cuda)).sum().backward()
+    assert rel_err(sdf.grad.cpu().numpy().reshape(-1), g["d_sdf"]) < TOL
+
+
+@pytest.mark.parametrize("res", [16, 32, 64])
+@pytest.mark.parametrize("kind", ["ellipsoid", "noisy_sphere", "horse"])
+def test_marching_tets_oracle(cuda, res, kind):
+    ops = _ops()
+    v, t = syn.kuhn_tet_grid(res)
+    v = v * np.float32(7.0)
+    sdf = {"ellipsoid": syn.sdf_ellipsoid(v), "noisy_sphere": syn.sdf_noisy_sphere(v, 1.75, 0.05, 1),
+           "horse": syn.sdf_horse(v, 0.01, 2)}[kind]
+    o = gnp.marching_tets(v, sdf, t, with_uvs=False)
+    grid = ops.TetGrid(dev(t, cuda), v.shape[0])
+    assert np.array_equal(grid.all_edges().cpu().numpy(), gnp.unique_sorted_edges(t))
+    sdf_d = dev(sdf, cuda).requires_grad_(True)
+    pos_d = dev(v, cuda).requires_grad_(True)
+    verts, faces, uv_idx, faces32, vert_edge = ops.marching_tets(pos_d, sdf_d, grid)
+    assert np.array_equal(faces.cpu().numpy(), o["faces"])            # bit-exact
+    assert np.array_equal(uv_idx.cpu().numpy(), o["uv_idx"])
+    assert np.array_equal(vert_edge.cpu().numpy(), o["interp_v"])
+    assert np.array_equal(verts.detach().cpu().numpy(), o["verts"])   # same unfused fp32 op order -> identical bits
+    gv = np.random.RandomState(3).randn(*o["verts"].shape).astype(np.float32)
+    (verts * dev(gv, cuda)).sum().backward()
+    d_sdf, d_pos = gnp.lerp_vertices_bwd(v, sdf, o["interp_v"], gv)
+    assert rel_err(sdf_d.grad.cpu().numpy(), d_sdf) < TOL
+    assert rel_err(pos_d.grad.cpu().numpy(), d_pos) < TOL
+
+
+def test_marching_tets_empty(cuda):
+    ops = _ops()
+    v, t = syn.kuhn_tet_grid(8)
+    grid = ops.TetGrid(dev(t, cuda), v.shape[0])
+    verts, faces, uv_idx, faces32, _ = ops.marching_tets(dev(v, cuda), torch.full((v.shape[0],), -1.0, device=cuda), grid)
+    assert verts.shape == (0, 3) and faces.shape == (0, 3) and uv_idx.shape == (0, 3)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# LBS
+# ----------------------------------------------------------------------------------------------------------------
+def _chain(g):
+    return [(int(b), [int(x) for x in str(d).split(",") if x != ""]) for b, d in zip(g["chain_ids"], g["chain_dep"])]
+
+
+@pytest.mark.parametrize("name", golden_files("skin_"))
+def test_skinning_golden(cuda, name):
+    """Drop-in skinning() against the reference's own skinning output + autograd gradients (fixture)."""
+    sk = pkg("geometry.skinning")
+    g = golden(name)
+    chain = _chain(g)
+    vp = dev(g["verts"], cuda)[None, None].clone().requires_grad_(True)
+    ang = dev(g["angles"], cuda).requires_grad_(True)
+    out, aux = sk.skinning(vp, dev(g["bones"], cuda), chain, ang, output_posed_bones=True, temperature=0.05)
+    assert rel_err(out.detach().cpu().numpy(), g["out"]) < TOL
+    assert rel_err(aux["posed_bones"].detach().cpu().numpy(), g["posed_bones"]) < TOL
+    assert np.abs(aux["vertices_to_bones"].cpu().numpy() - g["weights"]).max() < TOL
+    ((out * dev(g["g_out"], cuda)).sum() + (aux["posed_bones"] * dev(g["g_posed"], cuda)).sum()).backward()
+    assert rel_err(ang.grad.cpu().numpy(), g["d_angles"]) < TOL
+    assert rel_err(vp.grad.cpu().numpy(), g["d_verts"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_files("skin_"))
+def test_estimate_bones_golden(cuda, name):
+    sk = pkg("geometry.skinning")
+    g = golden(name)
+    verts = dev(g["verts"], cuda)[None, None]
+    n_leg, mode = int(g["n_leg_bones"]), str(g["mode"])
+    bones, chain, aux = sk.estimate_bones(verts, 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode)
+    assert [(b, list(d)) for b, d in chain] == _chain(g)
+    assert np.allclose(bones.cpu().numpy(), g["bones"], atol=1e-5)
+    bones2 = sk.estimate_bones(verts * 1.01, 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode, compute_kinematic_chain=False, aux=aux)
+    assert np.allclose(bones2.cpu().numpy(), g["bones_rescaled"], atol=1e-5)
+
+
+@pytest.mark.parametrize("Bv,Bb", [(1, 1), (3, 1), (3, 3)])
+def test_lbs_batched_oracle(cuda, Bv, Bb):
+    ops = _ops()
+    g = golden("skin_horse.npz")
+    chain = _chain(g)
+    rng = np.random.RandomState(4)
+    B, K = 3, g["bones"].shape[2]
+    verts = np.stack([g["verts"] * np.float32(1 + 0.02 * i) for i in range(Bv)])[:, None]          # [Bv,1,V,3]
+    bones = np.concatenate([g["bones"] * np.float32(1 + 0.02 * i) for i in range(Bb)], 0)          # [Bb,1,K,2,3]
+    ang = rng.uniform(-0.4, 0.4, (B, 1, K, 3)).astype(np.float32)
+    vt = torch.from_numpy(verts).requires_grad_(True)
+    at = torch.from_numpy(ang).requires_grad_(True)
+    ref, raux = T.skinning(vt, torch.from_numpy(bones), chain, at, temperature=0.05)
+    go = rng.randn(*ref.shape).astype(np.float32)
+    gp = rng.randn(B, 1, K, 2, 3).astype(np.float32)
+    ((ref * torch.from_numpy(go)).sum() + (raux["posed_bones"] * torch.from_numpy(gp)).sum()).backward()
+    cp, ci = ops.chain_tables(chain, K, cuda)
+    vd = dev(verts[:, 0], cuda).requires_grad_(True)
+    ad = dev(ang[:, 0], cuda).requires_grad_(True)
+    out, posed, w = ops.lbs(vd, dev(bones[:, 0], cuda), ad, cp, ci, 0.05, want_weights=True)
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().numpy()[:, 0]) < TOL
+    assert rel_err(posed.detach().cpu().numpy(), raux["posed_bones"].detach().numpy()[:, 0]) < TOL
+    assert np.abs(w.cpu().numpy() - raux["vertices_to_bones"].detach().numpy()[:, :, 0]).max() < TOL
+    ((out * dev(go[:, 0], cuda)).sum() + (posed * dev(gp[:, 0], cuda)).sum()).backward()
+    assert rel_err(ad.grad.cpu().numpy(), at.grad.numpy()[:, 0]) < TOL
+    assert rel_err(vd.grad.cpu().numpy(), vt.grad.numpy()[:, 0]) < TOL
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# normals, clip transform
+# ----------------------------------------------------------------------------------------------------------------
+def _mesh(res=20, batch=2, seed=0):
+    v, t = syn.kuhn_tet_grid(res)
+    v = v * np.float32(7.0)
+    o = gnp.marching_tets(v, syn.sdf_horse(v, 0.0, 0), t, with_uvs=False)
+    rng = np.random.RandomState(seed)
+    verts = np.stack([o["verts"] + rng.randn(*o["verts"].shape).astype(np.float32) * 0.003 for _ in range(batch)])
+    return verts.astype(np.float32), o["faces"].astype(np.int32), o["verts"]
+
+
+def test_vertex_normals_oracle(cuda):
+    ops = _ops()
+    verts, faces, _ = _mesh()
+    vt = torch.from_numpy(verts).requires_grad_(True)
+    ref = T.auto_normals(vt, torch.from_numpy(faces).long())       # the reference's torch ops (mesh.py:276-304)
+    g = np.random.RandomState(1).randn(*verts.shape).astype(np.float32)
+    (ref * torch.from_numpy(g)).sum().backward()
+    vd = dev(verts, cuda).requires_grad_(True)
+    nrm = ops.vertex_normals(vd, dev(faces, cuda))
+    assert rel_err(nrm.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+    (nrm * dev(g, cuda)).sum().backward()
+    assert rel_err(vd.grad.cpu().numpy(), vt.grad.numpy()) < TOL
+    # degenerate input: isolated vertex gets the (0,0,1) fallback
+    v2 = np.concatenate([verts, np.zeros((2, 1, 3), np.float32)], 1)
+    n2 = ops.vertex_normals(dev(v2, cuda), dev(faces, cuda)).cpu().numpy()
+    assert np.array_equal(n2[:, -1], np.array([[0, 0, 1], [0, 0, 1]], np.float32))
+
+
+@pytest.mark.parametrize("Bp", [1, 3])
+def test_xfm_points_oracle(cuda, Bp):
+    ops = _ops()
+    rng = np.random.RandomState(2)
+    pts = rng.randn(Bp, 777, 3).astype(np.float32)
+    mtx = rng.randn(3, 4, 4).astype(np.float32)
+    pt = torch.from_numpy(pts).requires_grad_(True)
+    mt = torch.from_numpy(mtx).requires_grad_(True)
+    ref = T.xfm_points(pt, mt)
+    g = rng.randn(3, 777, 4).astype(np.float32)
+    (ref * torch.from_numpy(g)).sum().backward()
+    pd, md = dev(pts, cuda).requires_grad_(True), dev(mtx, cuda).requires_grad_(True)
+    out = ops.xfm_points(pd, md)
+    assert np.array_equal(out.detach().cpu().numpy(), R.xfm_points(pts, mtx))   # same op order as the C oracle
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+    (out * dev(g, cuda)).sum().backward()
+    assert rel_err(pd.grad.cpu().numpy(), pt.grad.numpy()) < TOL
+    assert rel_err(md.grad.cpu().numpy(), mt.grad.numpy()) < TOL
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# rasterize / interpolate / antialias
+# ----------------------------------------------------------------------------------------------------------------
+def _scene(res=24, batch=3, image=96, seed=0):
+    verts, faces, prior = _mesh(res, batch, seed)
+    mvp, w2c, campos = syn.cameras(batch, seed=seed + 3)
+    clip = R.xfm_points(verts, mvp)
+    return verts, faces, prior, mvp, w2c, campos, clip
+
+
+ANALYTIC = {
+    "single_triangle": (np.array([[[-0.6, -0.5, 0.1, 1], [0.7, -0.4, 0.2, 1], [0.0, 0.8, 0.3, 1]]], np.float32), np.array([[0, 1, 2]], np.int32)),
+    "overlapping_quads": (np.array([[[-0.8, -0.8, 0.5, 1], [0.4, -0.8, 0.5, 1], [0.4, 0.4, 0.5, 1], [-0.8, 0.4, 0.5, 1],
+                                     [-0.3, -0.3, 0.2, 1], [0.9, -0.3, 0.2, 1], [0.9, 0.9, 0.2, 1], [-0.3, 0.9, 0.2, 1]]], np.float32),
+                          np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7]], np.int32)),
+    "shared_edge_fan": (np.array([[[0, 0, 0.3, 1], [0.9, 0, 0.3, 1], [0.6, 0.7, 0.3, 1], [-0.2, 0.9, 0.3, 1], [-0.8, 0.3, 0.3, 1],
+                                   [-0.7, -0.6, 0.3, 1], [0.2, -0.9, 0.3, 1]]], np.float32),
+                        np.array([[0, 1, 2], [0, 2, 3], [0, 3, 4], [0, 4, 5], [0, 5, 6], [0, 6, 1]], np.int32)),
+    "slivers": (np.array([[[-0.9, -0.9, 0.1, 1], [0.9, -0.89, 0.1, 1], [0.9, -0.88, 0.1, 1], [-0.5, 0.1, 0.4, 1], [-0.49, 0.9, 0.4, 1],
+                           [-0.48, 0.1, 0.4, 1]]], np.float32), np.array([[0, 1, 2], [3, 4, 5]], np.int32)),
+    "behind_camera": (np.array([[[-0.5, -0.5, 0.2, 1.0], [0.5, -0.5, 0.2, 1.0], [0.0, 0.5, -0.8, -0.5], [0.3, 0.3, 1.5, 1.0],
+                                 [0.8, 0.3, 0.5, 1.0], [0.5, 0.9, 0.5, 1.0]]], np.float32), np.array([[0, 1, 2], [3, 4, 5]], np.int32)),
+    "perspective_w": (np.array([[[-1.2, -1.0, 0.4, 2.0], [1.5, -0.8, 1.0, 3.0], [0.1, 0.9, 0.2, 1.0]]], np.float32), np.array([[0, 1, 2]], np.int32)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(ANALYTIC))
+@pytest.mark.parametrize("res", [(16, 16), (37, 53)])
+def test_rasterize_analytic(cuda, name, res):
+    ops = _ops()
+    pos, tri = ANALYTIC[name]
+    ref = R.rasterize(pos, tri, res)
+    out = ops.rasterize(dev(pos, cuda), dev(tri, cuda), res).cpu().numpy()
+    assert np.array_equal(out[..., 3], ref[..., 3])            # bit-exact triangle ids
+    assert np.array_equal(out, ref)                            # and identical barycentrics / depth bits
+
+
+@pytest.mark.parametrize("image", [64, 256])
+def test_rasterize_mesh_oracle(cuda, image):
+    ops = _ops()
+    verts, faces, prior, mvp, w2c, campos, clip = _scene(image=image)
+    ref = R.rasterize(clip, faces, (image, image))
+    cd = dev(clip, cuda).requires_grad_(True)
+    out = ops.rasterize(cd, dev(faces, cuda), (image, image))
+    assert (ref[..., 3] > 0).mean() > 0.05
+    assert np.array_equal(out.detach().cpu().numpy()[..., 3], ref[..., 3])
+    assert np.array_equal(out.detach().cpu().numpy(), ref)
+    g = np.random.RandomState(0).randn(*ref.shape).astype(np.float32)
+    (out * dev(g, cuda)).sum().backward()
+    assert rel_err(cd.grad.cpu().numpy(), R.rasterize_bwd(clip, faces, ref, g)) < TOL
+
+
+@pytest.mark.parametrize("Ba,C", [(3, 3), (1, 3), (3, 16), (3, 1)])
+def test_interpolate_oracle(cuda, Ba, C):
+    ops = _ops()
+    verts, faces, prior, mvp, w2c, campos, clip = _scene()
+    rast = R.rasterize(clip, faces, (96, 96))
+    rng = np.random.RandomState(5)
+    attr = rng.randn(Ba, verts.shape[1], C).astype(np.float32)
+    ref = R.interpolate(attr, rast, faces)
+    ad = dev(attr, cuda).requires_grad_(True)
+    rd = dev(rast, cuda).requires_grad_(True)
+    out = ops.interpolate(ad, rd, dev(faces, cuda))
+    assert np.array_equal(out.detach().cpu().numpy(), ref)
+    g = rng.randn(*ref.shape).astype(np.float32)
+    (out * dev(g, cuda)).sum().backward()
+    da, dr = R.interpolate_bwd(attr, rast, faces, g)
+    assert rel_err(ad.grad.cpu().numpy(), da) < TOL
+    assert rel_err(rd.grad.cpu().numpy(), dr) < TOL
+
+
+def test_edge_adjacency_oracle(cuda):
+    ops = _ops()
+    verts, faces, _ = _mesh(24)
+    for tri, V in ((faces, verts.shape[1]), (ANALYTIC["shared_edge_fan"][1], 7), (ANALYTIC["overlapping_quads"][1], 8),
+                   (np.array([[0, 1, 2], [2, 1, 0], [0, 1, 3], [1, 1, 2]], np.int32), 4)):   # duplicate + non-manifold + degenerate
+        assert np.array_equal(ops.edge_adjacency(dev(tri, cuda), V).cpu().numpy(), R.edge_adjacency(tri, V))
+
+
+@pytest.mark.parametrize("C", [4, 17, 2])
+def test_antialias_oracle(cuda, C):
+    ops = _ops()
+    verts, faces, prior, mvp, w2c, campos, clip = _scene()
+    rast = R.rasterize(clip, faces, (96, 96))
+    rng = np.random.RandomState(6)
+    color = rng.rand(3, 96, 96, C).astype(np.float32)
+    color[..., -1] = (rast[..., 3] > 0)
+    opp = R.edge_adjacency(faces, verts.shape[1])
+    ref = R.antialias(color, rast, clip, faces, opp)
+    assert np.abs(ref - color).max() > 0.05      # the case does blend something
+    cd = dev(color, cuda).requires_grad_(True)
+    pd = dev(clip, cuda).requires_grad_(True)
+    out = ops.antialias(cd, dev(rast, cuda), pd, dev(faces, cuda))
+    assert np.array_equal(out.detach().cpu().numpy(), ref)   # gather in the oracle's accumulation order -> identical bits
+    g = rng.randn(*ref.shape).astype(np.float32)
+    (out * dev(g, cuda)).sum().backward()
+    dc, dp = R.antialias_bwd(color, rast, clip, faces, g, opp)
+    assert rel_err(cd.grad.cpu().numpy(), dc) < TOL
+    assert np.abs(dp).max() > 0
+    assert rel_err(pd.grad.cpu().numpy(), dp) < TOL
+
+
+@pytest.mark.parametrize("C,keep,with_bg", [(4, 4, True), (17, 16, False), (2, 1, True)])
+def test_composite_antialias_oracle(cuda, C, keep, with_bg):
+    """Fused lerp(bg,[color,1],id>0) + antialias + channel slice vs the unfused torch/oracle sequence (render.py:258-331)."""
+    ops = _ops()
+    verts, faces, prior, mvp, w2c, campos, clip = _scene()
+    rast = R.rasterize(clip, faces, (96, 96))
+    rng = np.random.RandomState(7)
+    color = rng.rand(3, 96, 96, C - 1).astype(np.float32)
+    bg = rng.rand(3, 96, 96, C).astype(np.float32) if with_bg else None
+    opp = R.edge_adjacency(faces, verts.shape[1])
+    ct = torch.from_numpy(color).requires_grad_(True)
+    pt = torch.from_numpy(clip).requires_grad_(True)
+    alpha = torch.from_numpy((rast[..., 3:] > 0).astype(np.float32))
+    bgt = torch.from_numpy(bg) if with_bg else torch.zeros(1, 96, 96, C)
+    acc = torch.lerp(bgt.expand(3, -1, -1, -1), torch.cat((ct, torch.ones_like(ct[..., :1])), -1), alpha)
+    ref = T.antialias(acc.contiguous(), torch.from_numpy(rast), pt, torch.from_numpy(faces), torch.from_numpy(opp))[..., :keep].permute(0, 3, 1, 2)
+    g = rng.randn(*ref.shape).astype(np.float32)
+    (ref * torch.from_numpy(g)).sum().backward()
+    cd = dev(color, cuda).requires_grad_(True)
+    pd = dev(clip, cuda).requires_grad_(True)
+    out = ops.composite_antialias(cd, dev(bg, cuda) if with_bg else None, dev(rast, cuda), pd, dev(faces, cuda), dev(opp, cuda),
+                                  True, keep).permute(0, 3, 1, 2)
+    assert np.array_equal(out.detach().cpu().numpy(), ref.detach().numpy())
+    (out * dev(g, cuda)).sum().backward()     # NCHW-contiguous upstream gradient: exercises the strided d_out path
+    assert rel_err(cd.grad.cpu().numpy(), ct.grad.numpy()) < TOL
+    assert rel_err(pd.grad.cpu().numpy(), pt.grad.numpy()) < TOL
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused g-buffer
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("spp,Bq,two_sided", [(1, 1, True), (1, 3, False), (2, 1, True)])
+def test_gbuffer_oracle(cuda, spp, Bq, two_sided):
+    """One fused kernel vs the reference's sequence: 4x interpolate + prepare_shading_normal + camera normal."""
+    ops = _ops()
+    verts, faces, prior, mvp, w2c, campos, clip = _scene()
+    H = W = 64
+    rast = R.rasterize(clip, faces, (H * spp, W * spp))
+    rng = np.random.RandomState(8)
+    prior_b = np.stack([prior * np.float32(1 + 0.01 * i) for i in range(Bq)])
+    vt = torch.from_numpy(verts).requires_grad_(True)
+    qt = torch.from_numpy(prior_b).requires_grad_(True)
+    ct = torch.from_numpy(clip).requires_grad_(True)
+    wt = torch.from_numpy(w2c).requires_grad_(True)
+    pt = torch.from_numpy(campos).requires_grad_(True)
+    ft = torch.from_numpy(faces).long()
+    nt = T.auto_normals(vt.detach(), ft).requires_grad_(True)
+    # reference sequence on the CPU oracle
+    rast_full = T._Rasterize.apply(ct, torch.from_numpy(faces), (H * spp, W * spp))
+    assert np.array_equal(rast_full.detach().numpy(), rast)
+    rs = rast_full[:, ::spp, ::spp].contiguous()
+    tri = torch.from_numpy(faces)
+    gb_pos = T.interpolate(vt, rs, tri)
+    v0, v1, v2 = vt[:, ft[:, 0]], vt[:, ft[:, 1]], vt[:, ft[:, 2]]
+    fn = T.safe_normalize(torch.cross(v1 - v0, v2 - v0, dim=-1))
+    gb_geo = T.interpolate(fn, rs, torch.arange(faces.shape[0])[:, None].repeat(1, 3))
+    gb_nrm = T.interpolate(nt, rs, tri)
+    gb_tex = T.interpolate(qt, rs, tri)
+    gb_shn = T.prepare_shading_normal(gb_pos, pt[:, None, None, :], gb_nrm, None, gb_geo, two_sided)
+    gb_cam = T.safe_normalize(torch.matmul(gb_shn.view(3, -1, 3), wt[:, :3, :3].transpose(2, 1))).view(3, H, W, 3)
+    refs = dict(pos=gb_pos, geo_nrm=gb_geo, shading_nrm=gb_shn, cam_nrm=gb_cam, tex_pos=gb_tex)
+    gs = {k: rng.randn(3, H, W, 3).astype(np.float32) for k in refs}
+    sum((refs[k] * torch.from_numpy(gs[k])).sum() for k in refs).backward()
+    # fused kernel
+    vd, nd, qd = (dev(x.detach().numpy(), cuda).requires_grad_(True) for x in (vt, nt, qt))
+    cd, wd, pd = (dev(x.detach().numpy(), cuda).requires_grad_(True) for x in (ct, wt, pt))
+    out = ops.gbuffer(dev(rast, cuda), cd, dev(faces, cuda), vd, nd, qd, wd, pd, spp=spp, two_sided=two_sided, want=tuple(refs))
+    covered = rast[:, ::spp, ::spp, 3] > 0
+    for k in refs:
+        assert rel_err(out[k].detach().cpu().numpy(), refs[k].detach().numpy()) < TOL, k
+        assert np.all(out[k].detach().cpu().numpy()[~covered] == 0)
+    sum((out[k] * dev(gs[k], cuda)).sum() for k in refs).backward()
+    for name, a, b in (("v_pos", vd, vt), ("v_nrm", nd, nt), ("prior", qd, qt), ("clip", cd, ct), ("w2c", wd, wt), ("campos", pd, pt)):
+        assert rel_err(a.grad.cpu().numpy(), b.grad.numpy()) < 2e-4, name
