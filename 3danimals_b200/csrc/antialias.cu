@@ -238,6 +238,41 @@ __global__ void __launch_bounds__(256) aa_fwd_kernel(AAParams P, float* __restri
     out[((size_t)b * HW) * P.C + idx] = acc;
 }
 
+// gradient of one blended pair w.r.t. the clip-space positions of the silhouette edge's two vertices
+// (oracle/raster_ref.c orc_antialias_bwd); dd = sum_c d_out[target,c] * (color[p1,c] - color[p0,c])
+__device__ void aa_pos_grad(const AAParams& P, const float* __restrict__ pos_b, const AAPair& r, int d, float dd, float* __restrict__ d_pos_b)
+{
+    int e1 = __ldg(P.tri + (size_t)r.tri * 3 + (r.di + 1) % 3), e2 = __ldg(P.tri + (size_t)r.tri * 3 + (r.di + 2) % 3);
+    float4 q1v = ldg4(pos_b + (size_t)e1 * 4), q2v = ldg4(pos_b + (size_t)e2 * 4);
+    float pxh = 0.5f * (float)P.W, pyh = 0.5f * (float)P.H;
+    float fx = (float)r.px + 0.5f - pxh, fy = (float)r.py + 0.5f - pyh;
+    if (d) {
+        float t_;
+        t_ = q1v.x; q1v.x = q1v.y; q1v.y = t_;
+        t_ = q2v.x; q2v.x = q2v.y; q2v.y = t_;
+        t_ = pxh; pxh = pyh; pyh = t_;
+        t_ = fx; fx = fy; fy = t_;
+    }
+    float w1 = 1.f / q1v.w, w2 = 1.f / q2v.w;
+    float x1 = q1v.x * w1 * pxh - fx, y1 = q1v.y * w1 * pyh - fy;
+    float x2 = q2v.x * w2 * pxh - fx, y2 = q2v.y * w2 * pyh - fy;
+    float dx = x2 - x1, dy = y2 - y1;
+    float db = x1 * dy - y1 * dx;
+    float ep = copysignf(1e-3f, dy);
+    float iy = 1.f / (dy + ep);
+    float dby = db * iy;
+    float iw1 = -w1 * iy * dd, iw2 = w2 * iy * dd;
+    float gp1x = iw1 * pxh * y2, gp2x = iw2 * pxh * y1;
+    float gp1y = iw1 * pyh * (dby - x2), gp2y = iw2 * pyh * (dby - x1);
+    float gp1w = -(q1v.x * gp1x + q1v.y * gp1y) * w1;
+    float gp2w = -(q2v.x * gp2x + q2v.y * gp2y) * w2;
+    if (d) { float t_; t_ = gp1x; gp1x = gp1y; gp1y = t_; t_ = gp2x; gp2x = gp2y; gp2y = t_; }
+    float* g1 = d_pos_b + (size_t)e1 * 4;
+    float* g2 = d_pos_b + (size_t)e2 * 4;
+    atomicAdd(g1, gp1x); atomicAdd(g1 + 1, gp1y); atomicAdd(g1 + 3, gp1w);
+    atomicAdd(g2, gp2x); atomicAdd(g2 + 1, gp2y); atomicAdd(g2 + 3, gp2w);
+}
+
 struct AAGrad {
     const float* d_out;
     int64_t sb, sy, sx, sc;
@@ -285,38 +320,226 @@ __global__ void __launch_bounds__(256) aa_bwd_kernel(AAParams P, AAGrad G, float
             for (int cc = 0; cc < G.Cg; cc++)
                 dd += grad_at(G, P.W, b, target, cc) * (comp_color(P, b, q1, cc, r1.w > 0.f) - comp_color(P, b, q0, cc, r0.w > 0.f));
             if (dd == 0.f || fabsf(r.alpha) >= 0.5f) continue;
-            int e1 = __ldg(P.tri + (size_t)r.tri * 3 + (r.di + 1) % 3), e2 = __ldg(P.tri + (size_t)r.tri * 3 + (r.di + 2) % 3);
-            float4 q1v = ldg4(pos_b + (size_t)e1 * 4), q2v = ldg4(pos_b + (size_t)e2 * 4);
-            float pxh = 0.5f * (float)P.W, pyh = 0.5f * (float)P.H;
-            float fx = (float)r.px + 0.5f - pxh, fy = (float)r.py + 0.5f - pyh;
-            if (d) {
-                float t_;
-                t_ = q1v.x; q1v.x = q1v.y; q1v.y = t_;
-                t_ = q2v.x; q2v.x = q2v.y; q2v.y = t_;
-                t_ = pxh; pxh = pyh; pyh = t_;
-                t_ = fx; fx = fy; fy = t_;
-            }
-            float w1 = 1.f / q1v.w, w2 = 1.f / q2v.w;
-            float x1 = q1v.x * w1 * pxh - fx, y1 = q1v.y * w1 * pyh - fy;
-            float x2 = q2v.x * w2 * pxh - fx, y2 = q2v.y * w2 * pyh - fy;
-            float dx = x2 - x1, dy = y2 - y1;
-            float db = x1 * dy - y1 * dx;
-            float ep = copysignf(1e-3f, dy);
-            float iy = 1.f / (dy + ep);
-            float dby = db * iy;
-            float iw1 = -w1 * iy * dd, iw2 = w2 * iy * dd;
-            float gp1x = iw1 * pxh * y2, gp2x = iw2 * pxh * y1;
-            float gp1y = iw1 * pyh * (dby - x2), gp2y = iw2 * pyh * (dby - x1);
-            float gp1w = -(q1v.x * gp1x + q1v.y * gp1y) * w1;
-            float gp2w = -(q2v.x * gp2x + q2v.y * gp2y) * w2;
-            if (d) { float t_; t_ = gp1x; gp1x = gp1y; gp1y = t_; t_ = gp2x; gp2x = gp2y; gp2y = t_; }
-            float* g1 = d_pos + ((size_t)b * P.V + e1) * 4;
-            float* g2 = d_pos + ((size_t)b * P.V + e2) * 4;
-            atomicAdd(g1, gp1x); atomicAdd(g1 + 1, gp1y); atomicAdd(g1 + 3, gp1w);
-            atomicAdd(g2, gp2x); atomicAdd(g2 + 1, gp2y); atomicAdd(g2 + 3, gp2w);
+            aa_pos_grad(P, pos_b, r, d, dd, d_pos + (size_t)b * P.V * 4);
         }
     }
     if (d_color) d_color[((size_t)b * HW) * Cc + idx] = (P.composite && !(idc > 0.f)) ? 0.f : acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Fast path (composite mode = the training path): prepare once per render, then stream + fix up.
+//   aa_prepare   : one pass over rast -> coverage bitmask (1 bit/pixel) + compact list of silhouette pixels (pixels
+//                  with a 4-neighbour of different triangle id).  Shared by every antialias launch of the render
+//                  (2 keys x fwd/bwd), which therefore never read rast's 16 B/pixel again.
+//   aa_*_stream  : pure HBM streaming - forward: masked composite copy NHWC(C-1) -> NHWC(C); backward: masked copy of
+//                  the upstream gradient (NHWC, or NCHW transposed through a per-warp shared-memory tile) -> NHWC.
+//                  No barriers, no divergence, a handful of registers.
+//   aa_*_fix     : one thread per silhouette pixel adds the blend terms in the generic kernel's order (bit-identical
+//                  results) and, backward, scatters the edge-vertex position gradients.
+// ------------------------------------------------------------------------------------------------------------
+struct AAContext {
+    uint32_t* cover;   // [ceil(B*HW/32)] coverage bits
+    int* count;        // [1] silhouette pixels
+    int* list;         // [B*HW] flat pixel index b*HW + p
+};
+
+size_t aa_ctx_layout(int B, int H, int W, void* base, AAContext* ctx)
+{
+    size_t npix = (size_t)B * H * W;
+    size_t cb = b2a_align(((npix + 31) / 32) * 4);
+    if (ctx) {
+        char* p = (char*)base;
+        ctx->cover = (uint32_t*)p;
+        ctx->count = (int*)(p + cb);
+        ctx->list = (int*)(p + cb + 256);
+    }
+    return cb + 256 + b2a_align(npix * 4);
+}
+
+// grid-stride over all B*HW pixels (HW % 32 == 0, so a warp never straddles two images)
+__global__ void __launch_bounds__(256) aa_prepare_kernel(const float* __restrict__ rast, int B, int H, int W, AAContext ctx)
+{
+    const int HW = H * W;
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)B * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int p = (int)(i % HW);
+        int px = p % W, py = p / W;
+        float idc = __ldg(rast + i * 4 + 3);
+        float idl = __shfl_up_sync(0xffffffffu, idc, 1), idr = __shfl_down_sync(0xffffffffu, idc, 1);
+        if (lane == 0 && px > 0) idl = __ldg(rast + (i - 1) * 4 + 3);
+        if (lane == 31 && px + 1 < W) idr = __ldg(rast + (i + 1) * 4 + 3);
+        if (px == 0) idl = idc;
+        if (px + 1 >= W) idr = idc;
+        float idu = py > 0 ? __ldg(rast + (i - W) * 4 + 3) : idc;
+        float idd = py + 1 < H ? __ldg(rast + (i + W) * 4 + 3) : idc;
+        bool sil = idu != idc || idl != idc || idr != idc || idd != idc;
+        uint32_t cov = __ballot_sync(0xffffffffu, idc > 0.f);
+        uint32_t sm = __ballot_sync(0xffffffffu, sil);
+        if (lane == 0) ctx.cover[i >> 5] = cov;
+        if (sm) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(ctx.count, __popc(sm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (sil) ctx.list[base + __popc(sm & ((1u << lane) - 1u))] = (int)i;
+        }
+    }
+}
+
+// forward stream: out[pp*C + c] = covered ? (c < C-1 ? color[pp*(C-1) + c] : 1) : bg.   One thread per output element.
+template <int C>
+__global__ void __launch_bounds__(256) aa_fwd_stream_kernel(const float* __restrict__ color, const float* __restrict__ bg, int Bg,
+                                                            const uint32_t* __restrict__ cover, int HW, float* __restrict__ out)
+{
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;   // < HW*C (< 2^31 checked on the host)
+    if (e >= HW * C) return;
+    const int pp = e / C, c = e - pp * C;
+    const bool covered = (__ldg(cover + (((size_t)b * HW + pp) >> 5)) >> (pp & 31)) & 1u;
+    float v;
+    if (covered) v = c < C - 1 ? __ldg(color + (size_t)b * HW * (C - 1) + (e - pp)) : 1.f;
+    else v = bg ? __ldg(bg + (size_t)(Bg == 1 ? 0 : b) * HW * C + e) : 0.f;
+    out[(size_t)b * HW * C + e] = v;
+}
+
+// backward stream, NHWC-contiguous gradient: d_color[pp*CC + c] = covered && c < CG ? g[pp*CG + c] : 0
+template <int CC, int CG>
+__global__ void __launch_bounds__(256) aa_bwd_stream_nhwc_kernel(const float* __restrict__ g, int64_t sb, const uint32_t* __restrict__ cover,
+                                                                 int HW, float* __restrict__ d_color)
+{
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= HW * CC) return;
+    const int pp = e / CC, c = e - pp * CC;
+    const bool covered = (__ldg(cover + (((size_t)b * HW + pp) >> 5)) >> (pp & 31)) & 1u;
+    d_color[(size_t)b * HW * CC + e] = (covered && c < CG) ? __ldg(g + (int64_t)b * sb + (int64_t)pp * CG + c) : 0.f;
+}
+
+// backward stream, NCHW gradient (sx == 1): each warp owns 32 consecutive pixels of a row; CG coalesced 128-byte row
+// loads -> per-warp smem tile -> CC coalesced 128-byte stores.  Warp-autonomous: __syncwarp only.
+template <int CC, int CG>
+__global__ void __launch_bounds__(256) aa_bwd_stream_nchw_kernel(const float* __restrict__ g, int64_t sb, int64_t sy, int64_t sc,
+                                                                 const uint32_t* __restrict__ cover, int HW, int W,
+                                                                 float* __restrict__ d_color)
+{
+    __shared__ float tile[8][CG][33];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int t0 = (blockIdx.x * 8 + w) * 32;   // first pixel of this warp's tile
+    if (t0 >= HW) return;
+    const int py = t0 / W, px0 = t0 - py * W;
+    const float* gp = g + (int64_t)b * sb + (int64_t)py * sy + px0 + lane;
+    float v[CG];
+#pragma unroll
+    for (int c = 0; c < CG; c++) v[c] = __ldg(gp + (int64_t)c * sc);
+    const uint32_t m = __ldg(cover + (((size_t)b * HW + t0) >> 5));
+#pragma unroll
+    for (int c = 0; c < CG; c++) tile[w][c][lane] = v[c];
+    __syncwarp();
+    float* o = d_color + ((size_t)b * HW + t0) * CC;
+#pragma unroll
+    for (int i = 0; i < CC; i++) {
+        const int e = i * 32 + lane;
+        const int pp = e / CC, c = e - pp * CC;
+        o[e] = (c < CG && ((m >> pp) & 1u)) ? tile[w][c < CG ? c : 0][pp] : 0.f;
+    }
+}
+
+// the four pair analyses of one silhouette pixel
+struct AAPixelPairs {
+    float sgn[4];      // signed blend weight applied to this pixel's gradient / colour (0 = pair inactive)
+    int target[4];     // pixel receiving the blend
+    int q0[4], q1[4];
+    bool cov0[4], cov1[4];
+    AAPair pair[2];    // analysis of the two pairs this pixel owns (k = 2: right, k = 3: down)
+    bool own[2];
+};
+
+__device__ __forceinline__ void aa_pixel_pairs(const AAParams& P, const float* __restrict__ rast_b, const float* __restrict__ pos_b, int p,
+                                               AAPixelPairs& pp, bool bwd)
+{
+    const int px = p % P.W, py = p / P.W;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        pp.sgn[k] = 0.f; pp.target[k] = p; pp.q0[k] = p; pp.q1[k] = p; pp.cov0[k] = pp.cov1[k] = false;
+        if (k >= 2) pp.own[k - 2] = false;
+        int qx = px + c_pair_dx[k], qy = py + c_pair_dy[k], d = c_pair_d[k];
+        if (qx < 0 || qy < 0) continue;
+        if (d == 0 ? qx + 1 >= P.W : qy + 1 >= P.H) continue;
+        int q0 = qy * P.W + qx, q1 = q0 + (d ? P.W : 1);
+        float4 r0 = ldg4(rast_b + (size_t)q0 * 4), r1 = ldg4(rast_b + (size_t)q1 * 4);
+        AAPair r;
+        if (!aa_analyze(P, pos_b, r0, r1, qx, qy, d, r)) continue;
+        int target = r.alpha > 0.f ? q0 : q1;
+        pp.target[k] = target; pp.q0[k] = q0; pp.q1[k] = q1; pp.cov0[k] = r0.w > 0.f; pp.cov1[k] = r1.w > 0.f;
+        if (bwd) pp.sgn[k] = (p == q0) ? -r.alpha : r.alpha;          // d_color[p] -= / += alpha * g[target]
+        else pp.sgn[k] = (target == p) ? r.alpha : 0.f;               // out[p] += alpha * (c[q1] - c[q0]) when p is the target
+        if (k >= 2) { pp.pair[k - 2] = r; pp.own[k - 2] = true; }     // k = 2,3 have q0 == p
+    }
+}
+
+__global__ void __launch_bounds__(128) aa_fwd_fix_kernel(AAParams P, AAContext ctx, float* __restrict__ out)
+{
+    const int HW = P.H * P.W;
+    const int count = *ctx.count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const int flat = ctx.list[i];
+        const int b = flat / HW, p = flat - b * HW;
+        AAPixelPairs pp;
+        aa_pixel_pairs(P, P.rast + (size_t)b * HW * 4, P.pos + (size_t)b * P.V * 4, p, pp, false);
+        if (pp.sgn[0] == 0.f && pp.sgn[1] == 0.f && pp.sgn[2] == 0.f && pp.sgn[3] == 0.f) continue;
+        float* o = out + ((size_t)b * HW + p) * P.C;
+#pragma unroll 2
+        for (int c = 0; c < P.C; c++) {
+            float acc = o[c];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (pp.sgn[k] != 0.f) acc += pp.sgn[k] * (comp_color(P, b, pp.q1[k], c, pp.cov1[k]) - comp_color(P, b, pp.q0[k], c, pp.cov0[k]));
+            o[c] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) aa_bwd_fix_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
+                                                         float* __restrict__ d_pos)
+{
+    const int HW = P.H * P.W;
+    const int Cc = P.C - 1;
+    const int count = *ctx.count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const int flat = ctx.list[i];
+        const int b = flat / HW, p = flat - b * HW;
+        const float* rast_b = P.rast + (size_t)b * HW * 4;
+        const float* pos_b = P.pos + (size_t)b * P.V * 4;
+        AAPixelPairs pp;
+        aa_pixel_pairs(P, rast_b, pos_b, p, pp, true);
+        const bool covered = __ldg(rast_b + (size_t)p * 4 + 3) > 0.f;
+        const bool any = pp.sgn[0] != 0.f || pp.sgn[1] != 0.f || pp.sgn[2] != 0.f || pp.sgn[3] != 0.f;
+        if (!any && !pp.own[0] && !pp.own[1]) continue;
+        float dd0 = 0.f, dd1 = 0.f;
+        float* o = d_color ? d_color + ((size_t)b * HW + p) * Cc : nullptr;
+        const bool want_pos = d_pos != nullptr;
+#pragma unroll 2
+        for (int c = 0; c < G.Cg; c++) {
+            float gy[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) gy[k] = (pp.sgn[k] != 0.f || (k >= 2 && pp.own[k - 2])) ? grad_at(G, P.W, b, pp.target[k], c) : 0.f;
+            if (o && covered && c < Cc && any) {
+                float acc = o[c];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (pp.sgn[k] != 0.f) acc += pp.sgn[k] * gy[k];
+                o[c] = acc;
+            }
+            if (want_pos) {
+                if (pp.own[0]) dd0 += gy[2] * (comp_color(P, b, pp.q1[2], c, pp.cov1[2]) - comp_color(P, b, pp.q0[2], c, pp.cov0[2]));
+                if (pp.own[1]) dd1 += gy[3] * (comp_color(P, b, pp.q1[3], c, pp.cov1[3]) - comp_color(P, b, pp.q0[3], c, pp.cov0[3]));
+            }
+        }
+        if (want_pos) {
+            if (pp.own[0] && dd0 != 0.f && fabsf(pp.pair[0].alpha) < 0.5f) aa_pos_grad(P, pos_b, pp.pair[0], 0, dd0, d_pos + (size_t)b * P.V * 4);
+            if (pp.own[1] && dd1 != 0.f && fabsf(pp.pair[1].alpha) < 0.5f) aa_pos_grad(P, pos_b, pp.pair[1], 1, dd1, d_pos + (size_t)b * P.V * 4);
+        }
+    }
 }
 
 int aa_check(const float* color, const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, int Bg, int composite, int B,
@@ -360,24 +583,88 @@ B2A_API int b2a_edge_adjacency(const int32_t* tri, int64_t F, int64_t V, void* w
     return 0;
 }
 
+B2A_API int b2a_antialias_workspace_bytes(int B, int H, int W, size_t* bytes)
+{
+    B2A_CHECK_ARG(bytes && B > 0 && H > 0 && W > 0, "shape");
+    *bytes = aa_ctx_layout(B, H, W, nullptr, nullptr);
+    return 0;
+}
+
+B2A_API int b2a_antialias_prepare(const float* rast, int B, int H, int W, void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(rast && aa_ctx, "null pointer");
+    B2A_CHECK_ARG(B > 0 && H > 0 && W > 0 && (int64_t)B * H * W < (1ll << 31), "shape");
+    B2A_CHECK_ARG(((int64_t)H * W) % 32 == 0, "H*W must be a multiple of 32 for the prepared fast path");
+    AAContext ctx;
+    B2A_CHECK_ARG(aa_ctx_layout(B, H, W, aa_ctx, &ctx) <= aa_ctx_bytes, "context workspace too small");
+    B2A_CUDA_OK(cudaMemsetAsync(ctx.count, 0, sizeof(int), stream));
+    int64_t n = (int64_t)B * H * W;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (blocks > 148u * 16u) blocks = 148u * 16u;
+    aa_prepare_kernel<<<blocks, 256, 0, stream>>>(rast, B, H, W, ctx);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+namespace {
+bool aa_fast_ok(int composite, const void* aa_ctx, size_t aa_ctx_bytes, int B, int H, int W, int C, AAContext* ctx)
+{
+    if (!composite || !aa_ctx) return false;
+    if (((int64_t)H * W) % 32 != 0 || (int64_t)H * W * C >= (1ll << 31)) return false;
+    return aa_ctx_layout(B, H, W, const_cast<void*>(aa_ctx), ctx) <= aa_ctx_bytes;
+}
+}  // namespace
+
 B2A_API int b2a_antialias_fwd(const float* color, const float* bg, int Bg, int composite, const float* rast, const float* pos,
                               const int32_t* tri, const int32_t* opp, int B, int64_t V, int64_t F, int H, int W, int C, float* out,
-                              b2a_stream_t stream_)
+                              const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = aa_check(color, rast, pos, tri, opp, Bg, composite, B, V, F, H, W, C);
     if (rc) return rc;
     B2A_CHECK_ARG(out, "null pointer");
     AAParams P{color, bg, rast, pos, tri, opp, Bg, composite, B, H, W, C, V, F};
-    aa_fwd_kernel<<<dim3(b2a_blocks((int64_t)H * W * C, 256), B), 256, 0, stream>>>(P, out);
+    AAContext ctx;
+    const int HW = H * W;
+    bool fast = aa_fast_ok(composite, aa_ctx, aa_ctx_bytes, B, H, W, C, &ctx);
+    if (fast) {
+        dim3 grid(b2a_blocks((int64_t)HW * C, 256), B);
+        switch (C) {
+            case 2: aa_fwd_stream_kernel<2><<<grid, 256, 0, stream>>>(color, bg, Bg, ctx.cover, HW, out); break;
+            case 3: aa_fwd_stream_kernel<3><<<grid, 256, 0, stream>>>(color, bg, Bg, ctx.cover, HW, out); break;
+            case 4: aa_fwd_stream_kernel<4><<<grid, 256, 0, stream>>>(color, bg, Bg, ctx.cover, HW, out); break;
+            case 17: aa_fwd_stream_kernel<17><<<grid, 256, 0, stream>>>(color, bg, Bg, ctx.cover, HW, out); break;
+            default: fast = false;
+        }
+    }
+    if (fast) aa_fwd_fix_kernel<<<148 * 2, 128, 0, stream>>>(P, ctx, out);
+    else aa_fwd_kernel<<<dim3(b2a_blocks((int64_t)HW * C, 256), B), 256, 0, stream>>>(P, out);
     B2A_LAUNCH_OK();
     return 0;
 }
 
+namespace {
+template <int CC, int CG>
+bool aa_bwd_stream(const AAGrad& G, const AAContext& ctx, int B, int H, int W, float* d_color, cudaStream_t stream)
+{
+    const int HW = H * W;
+    if (G.sc == 1 && G.sx == CG && G.sy == (int64_t)W * CG) {
+        aa_bwd_stream_nhwc_kernel<CC, CG><<<dim3(b2a_blocks((int64_t)HW * CC, 256), B), 256, 0, stream>>>(G.d_out, G.sb, ctx.cover, HW, d_color);
+        return true;
+    }
+    if (G.sx == 1 && W % 32 == 0) {
+        aa_bwd_stream_nchw_kernel<CC, CG><<<dim3(b2a_blocks(HW / 32, 8), B), 256, 0, stream>>>(G.d_out, G.sb, G.sy, G.sc, ctx.cover, HW, W, d_color);
+        return true;
+    }
+    return false;
+}
+}  // namespace
+
 B2A_API int b2a_antialias_bwd(const float* color, const float* bg, int Bg, int composite, const float* rast, const float* pos,
                               const int32_t* tri, const int32_t* opp, const float* d_out, int64_t d_sb, int64_t d_sy, int64_t d_sx,
                               int64_t d_sc, int Cg, int B, int64_t V, int64_t F, int H, int W, int C, float* d_color, float* d_pos,
-                              b2a_stream_t stream_)
+                              const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = aa_check(color, rast, pos, tri, opp, Bg, composite, B, V, F, H, W, C);
@@ -387,7 +674,17 @@ B2A_API int b2a_antialias_bwd(const float* color, const float* bg, int Bg, int c
     if (Cc == 0) return 0;
     AAParams P{color, bg, rast, pos, tri, opp, Bg, composite, B, H, W, C, V, F};
     AAGrad G{d_out, d_sb, d_sy, d_sx, d_sc, Cg};
-    aa_bwd_kernel<<<dim3(b2a_blocks((int64_t)H * W * Cc, 256), B), 256, 0, stream>>>(P, G, d_color, d_pos);
+    AAContext ctx;
+    bool fast = d_color && aa_fast_ok(composite, aa_ctx, aa_ctx_bytes, B, H, W, C, &ctx);
+    if (fast) {
+        if (Cc == 3 && Cg == 4) fast = aa_bwd_stream<3, 4>(G, ctx, B, H, W, d_color, stream);
+        else if (Cc == 16 && Cg == 16) fast = aa_bwd_stream<16, 16>(G, ctx, B, H, W, d_color, stream);
+        else if (Cc == 1 && Cg == 1) fast = aa_bwd_stream<1, 1>(G, ctx, B, H, W, d_color, stream);
+        else if (Cc == 2 && Cg == 2) fast = aa_bwd_stream<2, 2>(G, ctx, B, H, W, d_color, stream);
+        else fast = false;
+    }
+    if (fast) aa_bwd_fix_kernel<<<148 * 2, 128, 0, stream>>>(P, G, ctx, d_color, d_pos);
+    else aa_bwd_kernel<<<dim3(b2a_blocks((int64_t)H * W * Cc, 256), B), 256, 0, stream>>>(P, G, d_color, d_pos);
     B2A_LAUNCH_OK();
     return 0;
 }

@@ -153,12 +153,38 @@ __device__ __forceinline__ float seg_dist(const float* bn, float px, float py, f
     return sqrtf(sx * sx + sy * sy + sz * sz + 1e-6f);
 }
 
+// Soft bone weights of one vertex: w_k = softmax_k(-dist_k / T).  Distances/exponentials are evaluated once and kept in
+// a per-thread column of shared memory (K <= LBS_CACHE_K), so the blend / gradient loops only read them back.
+constexpr int LBS_CACHE_K = 32;
+
+template <bool CACHE>
+__device__ __forceinline__ float lbs_weights(const float* __restrict__ s_bones, float (*s_w)[LBS_BLOCK], int K, float px, float py, float pz,
+                                             float inv_temp, float& xmax)
+{
+    xmax = -3.4e38f;
+    for (int k = 0; k < K; k++) {
+        float x = -seg_dist(s_bones + k * 6, px, py, pz) * inv_temp;
+        if (CACHE) s_w[k][threadIdx.x] = x;
+        xmax = fmaxf(xmax, x);
+    }
+    float sum = 0.f;
+    for (int k = 0; k < K; k++) {
+        float x = CACHE ? s_w[k][threadIdx.x] : -seg_dist(s_bones + k * 6, px, py, pz) * inv_temp;
+        float e = expf(x - xmax);
+        if (CACHE) s_w[k][threadIdx.x] = e;
+        sum += e;
+    }
+    return 1.f / sum;
+}
+
+template <bool CACHE>
 __global__ void __launch_bounds__(LBS_BLOCK) lbs_fwd_kernel(const float* __restrict__ v_pos, const float* __restrict__ bones,
                                                             const float* __restrict__ G, int B, int Bv, int Bb, int K, int64_t V,
                                                             float inv_temp, float* __restrict__ out, float* __restrict__ weights)
 {
     __shared__ float s_bones[LBS_MAX_K * 6];
     __shared__ float s_G[LBS_MAX_K * 12];
+    __shared__ float s_w[CACHE ? LBS_CACHE_K : 1][LBS_BLOCK];
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < K * 6; i += blockDim.x) s_bones[i] = bones[(size_t)(Bb == 1 ? 0 : b) * K * 6 + i];
     for (int i = threadIdx.x; i < K * 12; i += blockDim.x) s_G[i] = G[(size_t)b * K * 12 + i];
@@ -167,18 +193,16 @@ __global__ void __launch_bounds__(LBS_BLOCK) lbs_fwd_kernel(const float* __restr
     if (v >= V) return;
     const float* p = v_pos + ((size_t)(Bv == 1 ? 0 : b) * V + v) * 3;
     float px = p[0], py = p[1], pz = p[2];
-    float xmax = -3.4e38f;
-    for (int k = 0; k < K; k++) xmax = fmaxf(xmax, -seg_dist(s_bones + k * 6, px, py, pz) * inv_temp);
-    float sum = 0.f, ox = 0.f, oy = 0.f, oz = 0.f;
+    float xmax;
+    float inv = lbs_weights<CACHE>(s_bones, s_w, K, px, py, pz, inv_temp, xmax);
+    float ox = 0.f, oy = 0.f, oz = 0.f;
     for (int k = 0; k < K; k++) {
-        float e = expf(-seg_dist(s_bones + k * 6, px, py, pz) * inv_temp - xmax);
+        float e = CACHE ? s_w[k][threadIdx.x] : expf(-seg_dist(s_bones + k * 6, px, py, pz) * inv_temp - xmax);
         const float* g = s_G + k * 12;
-        sum += e;
         ox += e * (g[0] * px + g[1] * py + g[2] * pz + g[3]);
         oy += e * (g[4] * px + g[5] * py + g[6] * pz + g[7]);
         oz += e * (g[8] * px + g[9] * py + g[10] * pz + g[11]);
     }
-    float inv = 1.f / sum;
     float* o = out + ((size_t)b * V + v) * 3;
     o[0] = ox * inv; o[1] = oy * inv; o[2] = oz * inv;
     if (weights) {
@@ -186,13 +210,45 @@ __global__ void __launch_bounds__(LBS_BLOCK) lbs_fwd_kernel(const float* __restr
         int Bw = max(Bv, Bb);
         if (Bw == B || b == 0) {
             int bw = Bw == 1 ? 0 : b;
-            for (int k = 0; k < K; k++)
-                weights[((size_t)k * Bw + bw) * V + v] = expf(-seg_dist(s_bones + k * 6, px, py, pz) * inv_temp - xmax) * inv;
+            for (int k = 0; k < K; k++) {
+                float e = CACHE ? s_w[k][threadIdx.x] : expf(-seg_dist(s_bones + k * 6, px, py, pz) * inv_temp - xmax);
+                weights[((size_t)k * Bw + bw) * V + v] = e * inv;
+            }
         }
     }
 }
 
+// Sum 16 per-lane values over the 32 lanes of a warp with a transposing butterfly: 8+4+2+1+1 = 16 shuffles (a plain
+// per-value butterfly needs 80).  Returns, in every lane, the warp total of value index (lane >> 1).
+__device__ __forceinline__ float warp_reduce16(const float (&v)[16], int lane)
+{
+    float a[8], b4[4], c2[2];
+    bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float keep = hi ? v[i + 8] : v[i], send = hi ? v[i] : v[i + 8];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float keep = hi ? a[i + 4] : a[i], send = hi ? a[i] : a[i + 4];
+        b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        float keep = hi ? b4[i + 2] : b4[i], send = hi ? b4[i] : b4[i + 2];
+        c2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    hi = lane & 2;
+    float keep = hi ? c2[1] : c2[0], send = hi ? c2[0] : c2[1];
+    float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
+
 // backward: d_v = sum_k w_k R_k^T g ; d_G[b,k] += w_k g (x) [v,1]  (warp-ballot skips bones with no weight in the warp)
+template <bool CACHE>
 __global__ void __launch_bounds__(LBS_BLOCK) lbs_bwd_kernel(const float* __restrict__ v_pos, const float* __restrict__ bones,
                                                             const float* __restrict__ G, const float* __restrict__ d_out, int B, int Bv,
                                                             int Bb, int K, int64_t V, float inv_temp, float* __restrict__ d_v_pos,
@@ -201,6 +257,7 @@ __global__ void __launch_bounds__(LBS_BLOCK) lbs_bwd_kernel(const float* __restr
     __shared__ float s_bones[LBS_MAX_K * 6];
     __shared__ float s_G[LBS_MAX_K * 12];
     __shared__ float s_dG[LBS_MAX_K * 12];
+    __shared__ float s_w[CACHE ? LBS_CACHE_K : 1][LBS_BLOCK];
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < K * 6; i += blockDim.x) s_bones[i] = bones[(size_t)(Bb == 1 ? 0 : b) * K * 6 + i];
     for (int i = threadIdx.x; i < K * 12; i += blockDim.x) { s_G[i] = G[(size_t)b * K * 12 + i]; s_dG[i] = 0.f; }
@@ -214,27 +271,22 @@ __global__ void __launch_bounds__(LBS_BLOCK) lbs_bwd_kernel(const float* __restr
         const float* g = d_out + ((size_t)b * V + v) * 3;
         gx = g[0]; gy = g[1]; gz = g[2];
     }
-    float xmax = -3.4e38f;
-    for (int k = 0; k < K; k++) xmax = fmaxf(xmax, -seg_dist(s_bones + k * 6, px, py, pz) * inv_temp);
-    float sum = 0.f;
-    for (int k = 0; k < K; k++) sum += expf(-seg_dist(s_bones + k * 6, px, py, pz) * inv_temp - xmax);
-    float inv = valid ? 1.f / sum : 0.f;
+    float xmax;
+    float inv = lbs_weights<CACHE>(s_bones, s_w, K, px, py, pz, inv_temp, xmax);
+    if (!valid) inv = 0.f;
     float dvx = 0.f, dvy = 0.f, dvz = 0.f;
     const int lane = threadIdx.x & 31;
     for (int k = 0; k < K; k++) {
-        float w = expf(-seg_dist(s_bones + k * 6, px, py, pz) * inv_temp - xmax) * inv;
+        float w = (CACHE ? s_w[k][threadIdx.x] : expf(-seg_dist(s_bones + k * 6, px, py, pz) * inv_temp - xmax)) * inv;
         const float* g = s_G + k * 12;
         dvx += w * (g[0] * gx + g[4] * gy + g[8] * gz);
         dvy += w * (g[1] * gx + g[5] * gy + g[9] * gz);
         dvz += w * (g[2] * gx + g[6] * gy + g[10] * gz);
         if (__ballot_sync(0xffffffffu, w > 1e-10f) == 0u) continue;  // < fp32 eps of the dominant terms
         float wx = w * gx, wy = w * gy, wz = w * gz;
-        float r[12] = {wx * px, wx * py, wx * pz, wx, wy * px, wy * py, wy * pz, wy, wz * px, wz * py, wz * pz, wz};
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            float s = warp_sum(r[i]);
-            if (lane == 0) atomicAdd(&s_dG[k * 12 + i], s);
-        }
+        const float r[16] = {wx * px, wx * py, wx * pz, wx, wy * px, wy * py, wy * pz, wy, wz * px, wz * py, wz * pz, wz, 0.f, 0.f, 0.f, 0.f};
+        float tot = warp_reduce16(r, lane);
+        if (!(lane & 1) && (lane >> 1) < 12) atomicAdd(&s_dG[k * 12 + (lane >> 1)], tot);
     }
     if (valid && d_v_pos) {
         if (Bv == 1 && B > 1) {
@@ -354,7 +406,8 @@ B2A_API int b2a_lbs_fwd(const float* v_pos, const float* bones, const float* G, 
     B2A_CHECK_ARG(B > 0 && B <= 65535 && K > 0 && K <= LBS_MAX_K && (Bb == 1 || Bb == B) && (Bv == 1 || Bv == B), "shape");
     if (V == 0) return 0;
     dim3 grid(b2a_blocks(V, LBS_BLOCK), B);
-    lbs_fwd_kernel<<<grid, LBS_BLOCK, 0, stream>>>(v_pos, bones, G, B, Bv, Bb, K, V, inv_temperature, out, weights);
+    if (K <= LBS_CACHE_K) lbs_fwd_kernel<true><<<grid, LBS_BLOCK, 0, stream>>>(v_pos, bones, G, B, Bv, Bb, K, V, inv_temperature, out, weights);
+    else lbs_fwd_kernel<false><<<grid, LBS_BLOCK, 0, stream>>>(v_pos, bones, G, B, Bv, Bb, K, V, inv_temperature, out, weights);
     B2A_LAUNCH_OK();
     return 0;
 }
@@ -367,7 +420,8 @@ B2A_API int b2a_lbs_bwd(const float* v_pos, const float* bones, const float* G, 
     B2A_CHECK_ARG(B > 0 && B <= 65535 && K > 0 && K <= LBS_MAX_K && (Bb == 1 || Bb == B) && (Bv == 1 || Bv == B), "shape");
     if (V == 0) return 0;
     dim3 grid(b2a_blocks(V, LBS_BLOCK), B);
-    lbs_bwd_kernel<<<grid, LBS_BLOCK, 0, stream>>>(v_pos, bones, G, d_out, B, Bv, Bb, K, V, inv_temperature, d_v_pos, d_G);
+    if (K <= LBS_CACHE_K) lbs_bwd_kernel<true><<<grid, LBS_BLOCK, 0, stream>>>(v_pos, bones, G, d_out, B, Bv, Bb, K, V, inv_temperature, d_v_pos, d_G);
+    else lbs_bwd_kernel<false><<<grid, LBS_BLOCK, 0, stream>>>(v_pos, bones, G, d_out, B, Bv, Bb, K, V, inv_temperature, d_v_pos, d_G);
     B2A_LAUNCH_OK();
     return 0;
 }

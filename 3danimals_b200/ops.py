@@ -48,7 +48,7 @@ KERNELS_PER_CALL = {
     "b2a_mt_count": 4, "b2a_mt_emit": 2, "b2a_mt_bwd": 1, "b2a_lbs_bone_transforms": 2, "b2a_lbs_fwd": 1, "b2a_lbs_bwd": 1,
     "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1,
     "b2a_xfm_points_bwd": 1, "b2a_rasterize_fwd": 3, "b2a_rasterize_bwd": 1, "b2a_interpolate_fwd": 1, "b2a_interpolate_bwd": 1,
-    "b2a_edge_adjacency": 3, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 1, "b2a_gbuffer_fwd": 1, "b2a_gbuffer_bwd": 1,
+    "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 1, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 1, "b2a_gbuffer_fwd": 1, "b2a_gbuffer_bwd": 1,
 }
 
 
@@ -79,18 +79,19 @@ class CallStats:
 stats = CallStats()
 
 
-def _call(name, args):
+def _call(name, args, tag=None, launches=None):
     fn = getattr(_L(), name)
+    tag = stats.tag if tag is None else tag
     if stats.timing:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = fn(*args)
         e1.record()
-        stats.events.append((name, stats.tag, e0, e1))
+        stats.events.append((name, tag, e0, e1))
     else:
         rc = fn(*args)
-    stats.launches += KERNELS_PER_CALL[name]
+    stats.launches += KERNELS_PER_CALL[name] if launches is None else launches
     stats.calls[name] = stats.calls.get(name, 0) + 1
     _lib.check(rc)
 
@@ -411,7 +412,7 @@ class _Antialias(torch.autograd.Function):
     caller uses (the rest are sliced off, render.py:320-331), so their gradient is known to be zero."""
 
     @staticmethod
-    def forward(ctx, color, bg, rast, pos, tri, opp, composite, keep):
+    def forward(ctx, color, bg, rast, pos, tri, opp, composite, keep, aa_ctx=None):
         color = _f32(color, "color"); rast = _f32(rast, "rast"); pos = _f32(pos, "pos")
         bg = _f32(bg, "background") if bg is not None else None
         B, H, W = rast.shape[0], rast.shape[1], rast.shape[2]
@@ -425,8 +426,9 @@ class _Antialias(torch.autograd.Function):
             Bg = bg.shape[0]
         out = torch.empty(B, H, W, Cc, device=color.device)
         _call("b2a_antialias_fwd", (_p(color), _p(bg), Bg, int(composite), _p(rast), _p(pos), _p(tri), _p(opp), B, pos.shape[1],
-                                          tri.shape[0], H, W, Cc, _p(out), _stream()))
-        ctx.save_for_backward(color, bg, rast, pos, tri, opp)
+                                          tri.shape[0], H, W, Cc, _p(out), _p(aa_ctx), 0 if aa_ctx is None else aa_ctx.numel(), _stream()),
+              tag="C%d" % Cc, launches=1 if aa_ctx is None else 2)
+        ctx.save_for_backward(color, bg, rast, pos, tri, opp, aa_ctx)
         ctx.cfg = (bool(composite), Bg, Cc, int(keep))
         if keep < Cc:
             out = out[..., :keep]
@@ -434,7 +436,7 @@ class _Antialias(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        color, bg, rast, pos, tri, opp = ctx.saved_tensors
+        color, bg, rast, pos, tri, opp, aa_ctx = ctx.saved_tensors
         composite, Bg, Cc, keep = ctx.cfg
         B, H, W = rast.shape[0], rast.shape[1], rast.shape[2]
         if g.dtype != torch.float32:
@@ -443,8 +445,23 @@ class _Antialias(torch.autograd.Function):
         d_pos = torch.zeros_like(pos) if ctx.needs_input_grad[3] else None
         sb, sy, sx, sc = g.stride()
         _call("b2a_antialias_bwd", (_p(color), _p(bg), Bg, int(composite), _p(rast), _p(pos), _p(tri), _p(opp), _p(g), sb, sy, sx,
-                                          sc, keep, B, pos.shape[1], tri.shape[0], H, W, Cc, _p(d_color), _p(d_pos), _stream()))
-        return d_color, None, None, d_pos, None, None, None, None
+                                          sc, keep, B, pos.shape[1], tri.shape[0], H, W, Cc, _p(d_color), _p(d_pos), _p(aa_ctx),
+                                          0 if aa_ctx is None else aa_ctx.numel(), _stream()), tag="C%d" % Cc,
+              launches=1 if aa_ctx is None else 2)
+        return d_color, None, None, d_pos, None, None, None, None, None
+
+
+def antialias_prepare(rast):
+    """One pass over rast [B,H,W,4] -> opaque per-render context (coverage bitmask + silhouette pixel list) shared by all
+    composite_antialias launches of that render.  Returns None when the shape does not qualify (H*W % 32 != 0)."""
+    L = _L()
+    rast = _f32(rast, "rast")
+    B, H, W = rast.shape[0], rast.shape[1], rast.shape[2]
+    if (H * W) % 32 != 0:
+        return None
+    ws = _workspace(_size(L.b2a_antialias_workspace_bytes, B, H, W), rast.device)
+    _call("b2a_antialias_prepare", (_p(rast), B, H, W, _p(ws), ws.numel(), _stream()))
+    return ws
 
 
 def antialias(color, rast, pos, tri, opp=None):
@@ -455,7 +472,7 @@ def antialias(color, rast, pos, tri, opp=None):
     return _Antialias.apply(color, None, rast, pos, tri, opp, False, color.shape[-1])
 
 
-def composite_antialias(color, background, rast, pos, tri, opp, antialias_edges=True, keep=None):
+def composite_antialias(color, background, rast, pos, tri, opp, antialias_edges=True, keep=None, aa_ctx=None):
     """Fused lerp(background, [color,1], id>0) (+ antialias).  color [B,H,W,C-1]; background [1|B,H,W,C] or None (zeros).
     Returns [B,H,W,keep] (keep defaults to C)."""
     tri = _idx32(tri, "tri")
@@ -468,7 +485,7 @@ def composite_antialias(color, background, rast, pos, tri, opp, antialias_edges=
         bgt = background if background is not None else torch.zeros(1, *color.shape[1:3], Cc, device=color.device)
         acc = torch.lerp(bgt.expand(color.shape[0], -1, -1, -1), torch.cat((color, torch.ones_like(color[..., :1])), -1), alpha)
         return acc[..., :keep]
-    return _Antialias.apply(color, background, rast, pos, tri, opp, True, keep)
+    return _Antialias.apply(color, background, rast, pos, tri, opp, True, keep, aa_ctx)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -120,6 +120,7 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
     else:
         bg_full = None
 
+    aa_ctx = ops.antialias_prepare(rast) if any(k in _AA_KEYS and k in buffers for k in render_modes) else None
     out_buffers = []
     for key in render_modes:
         if key not in buffers:
@@ -131,7 +132,7 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
             bg = bg[..., 2:].contiguous()
         Cc = color.shape[-1] + 1
         keep = Cc if key == "shaded" else (Cc - 1 if key == "dino_pred" else _KEEP[key])
-        accum = ops.composite_antialias(color, bg, rast, v_pos_clip, tri, opp, antialias_edges=key in _AA_KEYS, keep=keep)
+        accum = ops.composite_antialias(color, bg, rast, v_pos_clip, tri, opp, antialias_edges=key in _AA_KEYS, keep=keep, aa_ctx=aa_ctx)
         if spp > 1:
             accum = torch.nn.functional.avg_pool2d(accum.permute(0, 3, 1, 2), spp)
             out_buffers.append(accum)

@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py - rendered-images/sec (fwd+bwd) of the 3DAnimals reconstruction hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mlps]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+DMTet extraction (res-128 Kuhn tet grid, capsule-"horse" SDF) -> normals -> bones -> LBS (20 bones) -> normals ->
+render 16 x 256^2 ['shaded','dino_pred'] -> backward from upstream image gradients to d_sdf and d_articulation.
+Workload = BASELINE.json configs[1] ("train_magicpony_horse batch 16, 256^2, DMTet res 128, 20 bones, 1xB200").
+
+Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same step driven
+through the public API from pinned HOST buffers (per-step H2D of the target images, loss on device, D2H of the loss);
+`roofline` = the dominant raster-backward kernel timed live with CUDA events; `cpu_baseline` = the CPU oracle twin on
+this box's host cores.  `--impl reference` times that CPU twin alone (the reference's path has no other runnable form
+here: nvdiffrast is absent).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rendered-images/sec (fwd+bwd) 256^2 horse batch"
+WORKLOAD = dict(workload="train_magicpony_horse: batch 16/GPU, 256x256, DMTet res 128 (Kuhn grid 2.15M verts / 12.6M tets), 20 bones, "
+                         "modes shaded+dino_pred(16ch), fwd+bwd, analytic colour field (M1a)",
+                grid_res=128, batch_per_gpu=16, image_res=256, bones=20, dino_dim=16,
+                l2="inputs larger than L2: every step streams the 201 MB tet index buffer (+8.6 MB sdf, 60 MB edge CSR)")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU twin (cpu_baseline / --impl reference)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_arm(scene, steps, warmup, images):
+    """Times the CPU oracle twin (oracle/pipeline_ref.py: restated reference geometry in torch-CPU + C/OpenMP raster ops)
+    with all host threads; each step = one fwd+bwd over `images` images of the workload.  -> (images/s, seconds/step, cores)."""
+    import torch
+    from oracle import pipeline_ref as P
+    from oracle import raster as R
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g1, g2 = scene.upstream_grads()
+    for _ in range(warmup):
+        P.step(scene, g1, g2, images=images)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        P.step(scene, g1, g2, images=images)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return images / dt, dt, max(cores, R.num_threads())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pipe = importlib.import_module("3danimals_b200.pipeline")
+    scene = pipe.SyntheticScene(grid_res=WORKLOAD["grid_res"], batch=WORKLOAD["batch_per_gpu"], image_res=WORKLOAD["image_res"])
+    images = WORKLOAD["batch_per_gpu"]
+    ips, dt, cores = cpu_arm(scene, args.steps, min(args.warmup, 1), images)
+    sample = "full step: extraction + %d images fwd+bwd per step, %d steps" % (images, args.steps)
+    line = dict(metric=METRIC, value=ips, unit="images/s", n_gpus=args.gpus, steps=args.steps, warmup=min(args.warmup, 1),
+                ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=WORKLOAD, impl="reference",
+                cpu_baseline=dict(value=ips, unit="images/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=ips, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# ours
+# ----------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(scene_stats):
+    """Algorithmic bytes per launch of the raster-backward kernels (DESIGN.md 'Kernels and rooflines'): every tensor that
+    must cross the kernel boundary counted once; silhouette-pair reads are O(perimeter) and counted as 0."""
+    B, HW, V, F, D = scene_stats["B"], scene_stats["HW"], scene_stats["V"], scene_stats["F"], scene_stats["D"]
+    aa_shaded = B * HW * (4 * 4 + 3 * 4) + B * HW // 8        # read d_out RGBA + coverage bit, write d_color RGB
+    aa_dino = B * HW * (D * 4 + D * 4) + B * HW // 8          # read d_out D ch + coverage bit, write d_color D ch
+    gb = B * HW * (16 + 12 + 12) + B * V * ((12 + 12 + 16) * 2 + (12 + 12 + 16)) + V * (12 * 2 + 12) + F * 12
+    return {"aa_bwd_shaded": aa_shaded, "aa_bwd_dino": aa_dino, "gb_bwd": gb}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the B200 hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pipe = importlib.import_module("3danimals_b200.pipeline")
+    ops = importlib.import_module("3danimals_b200.ops")
+    B, r = WORKLOAD["batch_per_gpu"], WORKLOAD["image_res"]
+    scene = pipe.SyntheticScene(grid_res=WORKLOAD["grid_res"], batch=B, image_res=r, seed=rank)   # image-parallel shard
+    hp = pipe.HotPath(scene, dev, mlps=args.mlps)
+    g1, g2 = scene.upstream_grads()
+    d_shaded, d_dino = torch.from_numpy(g1).to(dev), torch.from_numpy(g2).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        d_sdf, d_ang = hp.step(d_shaded, d_dino)
+        if world > 1:   # DDP semantics: all-reduce on (the stand-in for) parameter gradients only
+            dist.all_reduce(d_sdf)
+        return d_sdf, d_ang
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # ---- timed region: exactly K steps, device-timed, max over ranks ------------------------------------------
+    ops.stats.reset()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    profiling = os.environ.get("B2A_PROFILE", "0") == "1"    # ncu --profile-from-start off: capture steady-state steps only
+    if profiling:
+        torch.cuda.profiler.start()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    if profiling:
+        torch.cuda.profiler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = ops.stats.launches
+    ms_per_step = float(ms.item()) / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- live per-kernel timing of the raster backward (same step, CUDA events on the launching stream) --------
+    ops.stats.reset()
+    ops.stats.timing = True
+    for _ in range(min(args.steps, 5)):
+        step()
+    torch.cuda.synchronize()
+    ops.stats.timing = False
+    durs = ops.stats.durations_ms()
+    prior, inst = hp.last["prior"], hp.last["inst"]
+    st = dict(B=B, HW=r * r, V=int(inst.v_pos.shape[1]), F=int(inst.t_pos_idx.shape[1]), D=scene.dino_dim)
+    ab = algorithmic_bytes(st)
+    mean = lambda xs: sum(xs) / len(xs) if xs else float("nan")
+    t_aa_sh = mean(durs.get(("b2a_antialias_bwd", "C4"), []))
+    t_aa_dn = mean(durs.get(("b2a_antialias_bwd", "C%d" % (scene.dino_dim + 1)), []))
+    t_gb = mean(durs.get(("b2a_gbuffer_bwd", ""), []))
+    peak, peak_src = peaks()
+    kern = {
+        "aa_bwd_dino": dict(ms=t_aa_dn, bytes=ab["aa_bwd_dino"]),
+        "aa_bwd_shaded": dict(ms=t_aa_sh, bytes=ab["aa_bwd_shaded"]),
+        "gb_bwd": dict(ms=t_gb, bytes=ab["gb_bwd"]),
+    }
+    for k in kern.values():
+        k["gbs"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        k["frac"] = k["gbs"] / peak
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    group_bytes = sum(k["bytes"] for k in kern.values())
+    group_ms = sum(k["ms"] for k in kern.values())
+    roofline = dict(bound="hbm", kernel=dom, achieved=kern[dom]["gbs"], peak=peak, unit="GB/s", frac=kern[dom]["frac"], traffic=None,
+                    peak_source=peak_src, us_per_launch=kern[dom]["ms"] * 1e3,
+                    raster_backward_group=dict(kernels=kern, bytes=group_bytes, ms=group_ms, achieved=group_bytes / (group_ms * 1e-3) / 1e9,
+                                               frac=group_bytes / (group_ms * 1e-3) / 1e9 / peak),
+                    per_call_ms={(n + ":" + t if t else n): sum(v) / len(v) for (n, t), v in sorted(durs.items())})
+
+    # ---- end to end through the public API from pinned host buffers -------------------------------------------
+    rng_t = torch.Generator().manual_seed(5)
+    tgt_rgba = torch.rand(B, 4, r, r, generator=rng_t).pin_memory()
+    tgt_dino = torch.rand(B, scene.dino_dim, r, r, generator=rng_t).pin_memory()
+    loss_host = torch.zeros(1).pin_memory()
+
+    def e2e_step():
+        a = tgt_rgba.to(dev, non_blocking=True)
+        b = tgt_dino.to(dev, non_blocking=True)
+        hp.sdf.grad = None
+        hp.angles.grad = None
+        shaded, dino = hp.forward()
+        loss = ((shaded - a) ** 2).mean() + ((dino - b) ** 2).mean()
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(hp.sdf.grad)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2.item()) / args.steps
+    clocks = sampler.stop() if sampler else None     # sampled over the timed region, the per-kernel pass and the e2e region
+    e2e = dict(value=world * B / (e2e_ms * 1e-3), unit="images/s", ms_per_step=e2e_ms,
+               h2d_bytes_per_step=int(tgt_rgba.numel() * 4 + tgt_dino.numel() * 4), d2h_bytes_per_step=4,
+               what="pinned host targets -> H2D -> HotPath.forward (public drop-in API) -> MSE loss -> backward -> D2H loss")
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ---------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        reps = 3
+        ips, dt, cores = cpu_arm(scene, reps, 1, B)
+        cpu = dict(value=ips, unit="images/s", cores=cores, kind="port", seconds_per_step=dt,
+                   sample="full step (extraction + %d images fwd+bwd), %d steps after 1 warm-up; oracle/pipeline_ref.py" % (B, reps))
+
+    if rank == 0:
+        cfg = dict(WORKLOAD)
+        cfg.update(mesh_verts=st["V"], mesh_faces=st["F"], field="CoordMLP texture 8x256 + DINO 5x256 (M1b)" if args.mlps else "analytic (M1a)",
+                   parallelism="image-parallel dp%d, NCCL all-reduce on d_sdf only" % world)
+        line = dict(metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=cfg, clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, impl="ours")
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mlps", action="store_true", help="M1b: real CoordMLP texture/DINO fields instead of the analytic field")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

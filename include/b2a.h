@@ -129,13 +129,18 @@ int b2a_interpolate_bwd(const float* attr, const float* rast, const int32_t* tri
 int b2a_edge_adjacency_workspace_bytes(int64_t F, size_t* bytes);
 int b2a_edge_adjacency(const int32_t* tri, int64_t F, int64_t V, void* workspace, size_t workspace_bytes,
                        int32_t* opp, b2a_stream_t stream);
+/* Optional per-render context (composite mode, H*W % 32 == 0): one pass over rast builds a 1-bit/pixel coverage mask and
+ * the compact list of silhouette pixels; every antialias launch of that render (each key, fwd and bwd) then streams
+ * without touching rast.  aa_ctx may be NULL (generic kernels). */
+int b2a_antialias_workspace_bytes(int B, int H, int W, size_t* bytes);
+int b2a_antialias_prepare(const float* rast, int B, int H, int W, void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
 int b2a_antialias_fwd(const float* color, const float* bg, int Bg, int composite, const float* rast, const float* pos,
                       const int32_t* tri, const int32_t* opp, int B, int64_t V, int64_t F, int H, int W, int C,
-                      float* out, b2a_stream_t stream);
+                      float* out, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
 int b2a_antialias_bwd(const float* color, const float* bg, int Bg, int composite, const float* rast, const float* pos,
                       const int32_t* tri, const int32_t* opp, const float* d_out, int64_t d_sb, int64_t d_sy,
                       int64_t d_sx, int64_t d_sc, int Cg, int B, int64_t V, int64_t F, int H, int W, int C,
-                      float* d_color, float* d_pos, b2a_stream_t stream);
+                      float* d_color, float* d_pos, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused g-buffer pass (fast path of render_layer + shade's geometry part, model/render/render.py:160-209, :72-75):

@@ -1,0 +1,67 @@
+"""The C-ABI boundary (include/b2a.h <-> libb2a.so) without a GPU: every declared symbol is exported, the header parser
+that derives the ctypes prototypes sees them all, and the host-only entry points (version, workspace sizes, error
+reporting) behave.  No compute call is made here."""
+import ctypes
+import os
+import subprocess
+
+from conftest import ROOT, pkg
+
+EXPECTED = {
+    "b2a_version", "b2a_last_error_string", "b2a_mt_workspace_bytes", "b2a_mt_count", "b2a_mt_emit", "b2a_mt_bwd",
+    "b2a_lbs_bone_transforms", "b2a_lbs_fwd", "b2a_lbs_bwd", "b2a_lbs_bone_transforms_bwd", "b2a_vertex_normals_fwd",
+    "b2a_vertex_normals_bwd", "b2a_xfm_points_fwd", "b2a_xfm_points_bwd", "b2a_rasterize_workspace_bytes", "b2a_rasterize_fwd",
+    "b2a_rasterize_bwd", "b2a_interpolate_fwd", "b2a_interpolate_bwd", "b2a_edge_adjacency_workspace_bytes", "b2a_edge_adjacency",
+    "b2a_antialias_workspace_bytes", "b2a_antialias_prepare", "b2a_antialias_fwd", "b2a_antialias_bwd", "b2a_gbuffer_fwd", "b2a_gbuffer_bwd",
+}
+
+
+def test_header_declares_expected_surface():
+    protos = pkg("_lib").parse_header()
+    assert set(protos) == EXPECTED
+    # no torch / C++ types cross the boundary: plain pointers, sizes, scalars, an opaque stream handle
+    import re
+    text = open(os.path.join(ROOT, "include", "b2a.h")).read()
+    code = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)          # comments cite nvdiffrast.torch; the declarations must not
+    assert "torch" not in code and "at::" not in code and "std::" not in code and 'extern "C"' in code
+    rt, params = protos["b2a_antialias_bwd"]
+    assert rt is ctypes.c_int and [p[1] for p in params][-1] == "stream"
+
+
+def test_library_exports_every_declared_symbol():
+    lib_mod = pkg("_lib")
+    handle = lib_mod.lib()          # raises if the .so is missing or lacks any symbol declared in the header
+    exported = subprocess.run(["nm", "-D", "--defined-only", lib_mod.LIB_PATH], capture_output=True, text=True).stdout
+    names = {line.split()[-1] for line in exported.splitlines() if " T " in line}
+    assert EXPECTED <= names
+    assert {n for n in names if n.startswith("b2a_")} == EXPECTED       # and nothing undeclared leaks out
+    assert handle.b2a_version() == 100
+
+
+def test_workspace_sizes_and_error_convention():
+    lib_mod = pkg("_lib")
+    h = lib_mod.lib()
+    out = ctypes.c_size_t(0)
+    assert h.b2a_rasterize_workspace_bytes(16, 50000, 256, 256, ctypes.byref(out)) == 0
+    assert out.value >= 16 * 256 * 256 * 8
+    assert h.b2a_mt_workspace_bytes(1000, 7000, 6000, ctypes.byref(out)) == 0 and out.value > 7000 * 4
+    assert h.b2a_edge_adjacency_workspace_bytes(100, ctypes.byref(out)) == 0 and out.value >= 1024 * 16
+    # errors: non-zero return + thread-local message, Python side raises
+    assert h.b2a_rasterize_workspace_bytes(0, 1, 1, 1, ctypes.byref(out)) != 0
+    assert b"invalid argument" in h.b2a_last_error_string()
+    try:
+        lib_mod.check(2)
+        raise AssertionError("check() must raise")
+    except lib_mod.B2AError as e:
+        assert "invalid argument" in str(e)
+
+
+def test_sass_is_sm100a():
+    """The shipped library carries sm_100a SASS only (no multi-arch fallback)."""
+    lib_mod = pkg("_lib")
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump):
+        return
+    out = subprocess.run([cuobjdump, "-lelf", lib_mod.LIB_PATH], capture_output=True, text=True).stdout
+    archs = {tok for line in out.splitlines() for tok in line.replace(".", " ").split() if tok.startswith("sm_")}
+    assert archs == {"sm_100a"}, archs

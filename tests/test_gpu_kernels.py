@@ -295,31 +295,41 @@ def test_antialias_oracle(cuda, C):
     assert rel_err(pd.grad.cpu().numpy(), dp) < TOL
 
 
-@pytest.mark.parametrize("C,keep,with_bg", [(4, 4, True), (17, 16, False), (2, 1, True)])
-def test_composite_antialias_oracle(cuda, C, keep, with_bg):
-    """Fused lerp(bg,[color,1],id>0) + antialias + channel slice vs the unfused torch/oracle sequence (render.py:258-331)."""
+@pytest.mark.parametrize("image,layout,prepared", [(96, "nchw", False), (96, "nchw", True), (128, "nchw", True), (128, "nhwc", True),
+                                                   (100, "nchw", True)])   # prepared: stream + fix-up kernels; else generic
+@pytest.mark.parametrize("C,keep,with_bg", [(4, 4, True), (17, 16, False), (2, 1, True), (3, 2, False)])
+def test_composite_antialias_oracle(cuda, C, keep, with_bg, image, layout, prepared):
+    """Fused lerp(bg,[color,1],id>0) + antialias + channel slice vs the unfused torch/oracle sequence (render.py:258-331),
+    with the upstream gradient arriving NCHW-contiguous (a loss on the permuted view) or NHWC-contiguous."""
     ops = _ops()
     verts, faces, prior, mvp, w2c, campos, clip = _scene()
-    rast = R.rasterize(clip, faces, (96, 96))
+    S = image
+    rast = R.rasterize(clip, faces, (S, S))
     rng = np.random.RandomState(7)
-    color = rng.rand(3, 96, 96, C - 1).astype(np.float32)
-    bg = rng.rand(3, 96, 96, C).astype(np.float32) if with_bg else None
+    color = rng.rand(3, S, S, C - 1).astype(np.float32)
+    bg = rng.rand(3, S, S, C).astype(np.float32) if with_bg else None
     opp = R.edge_adjacency(faces, verts.shape[1])
     ct = torch.from_numpy(color).requires_grad_(True)
     pt = torch.from_numpy(clip).requires_grad_(True)
     alpha = torch.from_numpy((rast[..., 3:] > 0).astype(np.float32))
-    bgt = torch.from_numpy(bg) if with_bg else torch.zeros(1, 96, 96, C)
+    bgt = torch.from_numpy(bg) if with_bg else torch.zeros(1, S, S, C)
     acc = torch.lerp(bgt.expand(3, -1, -1, -1), torch.cat((ct, torch.ones_like(ct[..., :1])), -1), alpha)
     ref = T.antialias(acc.contiguous(), torch.from_numpy(rast), pt, torch.from_numpy(faces), torch.from_numpy(opp))[..., :keep].permute(0, 3, 1, 2)
     g = rng.randn(*ref.shape).astype(np.float32)
     (ref * torch.from_numpy(g)).sum().backward()
     cd = dev(color, cuda).requires_grad_(True)
     pd = dev(clip, cuda).requires_grad_(True)
+    aa_ctx = ops.antialias_prepare(dev(rast, cuda)) if prepared else None
+    assert (aa_ctx is not None) == (prepared and (S * S) % 32 == 0)
     out = ops.composite_antialias(cd, dev(bg, cuda) if with_bg else None, dev(rast, cuda), pd, dev(faces, cuda), dev(opp, cuda),
-                                  True, keep).permute(0, 3, 1, 2)
+                                  True, keep, aa_ctx=aa_ctx).permute(0, 3, 1, 2)
     assert np.array_equal(out.detach().cpu().numpy(), ref.detach().numpy())
-    (out * dev(g, cuda)).sum().backward()     # NCHW-contiguous upstream gradient: exercises the strided d_out path
+    gd = dev(g, cuda)
+    if layout == "nhwc":
+        gd = gd.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    out.backward(gd)
     assert rel_err(cd.grad.cpu().numpy(), ct.grad.numpy()) < TOL
+    assert np.abs(pt.grad.numpy()).max() > 0
     assert rel_err(pd.grad.cpu().numpy(), pt.grad.numpy()) < TOL
 
 

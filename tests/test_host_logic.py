@@ -1,0 +1,137 @@
+"""Host-side logic that needs no GPU: the torch restatement of estimate_bones (runs on CPU tensors), kinematic-chain
+tables, the module overlay, synthetic inputs, Mesh bookkeeping."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_files, pkg
+from oracle import geometry_np as gnp
+
+
+def _chain(g):
+    return [(int(b), [int(x) for x in str(d).split(",") if x != ""]) for b, d in zip(g["chain_ids"], g["chain_dep"])]
+
+
+@pytest.mark.parametrize("name", golden_files("skin_"))
+def test_estimate_bones_matches_reference_golden(name):
+    """estimate_bones is plain torch (device-agnostic): check it on CPU tensors against the reference's output."""
+    sk = pkg("geometry.skinning")
+    g = golden(name)
+    verts = torch.from_numpy(g["verts"])[None, None]
+    n_leg, mode = int(g["n_leg_bones"]), str(g["mode"])
+    bones, chain, aux = sk.estimate_bones(verts, 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode)
+    assert [(b, list(d)) for b, d in chain] == _chain(g)
+    assert np.allclose(bones.numpy(), g["bones"], atol=1e-6)
+    assert not bones.requires_grad
+    bones2 = sk.estimate_bones(verts * 1.01, 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode, compute_kinematic_chain=False, aux=aux)
+    assert np.allclose(bones2.numpy(), g["bones_rescaled"], atol=1e-6)
+
+
+def test_estimate_bones_batched_matches_numpy_oracle():
+    """B x F > 1 (per-instance deformation on, InstancePredictorBase.py:514-518): vectorised masked arg-min vs the oracle's
+    per-(b,f) loops, including the 'attachment index fixed on the first (b,f)' behaviour (skinning.py:190-192)."""
+    sk = pkg("geometry.skinning")
+    g = golden("skin_horse.npz")
+    rng = np.random.RandomState(0)
+    shapes = np.stack([g["verts"] * np.float32(1 + 0.05 * i) + rng.randn(*g["verts"].shape).astype(np.float32) * 0.01
+                       for i in range(6)]).reshape(3, 2, -1, 3)
+    ref_b, ref_chain, ref_aux = gnp.estimate_bones(shapes, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+")
+    bones, chain, aux = sk.estimate_bones(torch.from_numpy(shapes), 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+")
+    assert [(b, list(d)) for b, d in chain] == [(b, list(d)) for b, d in ref_chain]
+    assert np.allclose(bones.numpy(), ref_b, atol=1e-6)
+    assert [l["body_bone_idx"] for l in aux["legs"]] == [l["body_bone_idx"] for l in ref_aux["legs"]]
+
+
+def test_euler_and_chain_tables():
+    sk, ops = pkg("geometry.skinning"), pkg("ops")
+    a = torch.tensor([[0.3, -0.2, 0.5]])
+    assert np.allclose(sk.euler_angles_to_matrix(a, "XYZ").numpy(), gnp.euler_xyz(a.numpy()), atol=1e-6)
+    with pytest.raises(ValueError):
+        sk.euler_angles_to_matrix(a, "XXY")
+    chain = [(2, [0, 1]), (1, [0]), (0, []), (3, [])]
+    ptr, ids = ops.chain_tables(chain, 4, "cpu")
+    # bone 0's ancestors are the bones listing it among their dependents, in list order, root first (skinning.py:389-396)
+    assert ptr.tolist() == [0, 3, 5, 6, 7] and ids.tolist() == [2, 1, 0, 2, 1, 2, 3]
+    assert gnp.chain_lists(chain) == {2: [2], 1: [2, 1], 0: [2, 1, 0], 3: [3]}
+
+
+def test_synthetic_grid_schema(tmp_path):
+    syn = pkg("synthetic")
+    v, t = syn.kuhn_tet_grid(4)
+    assert v.shape == (125, 3) and t.shape == (6 * 64, 4) and v.dtype == np.float32 and t.dtype == np.int64
+    # every tet has positive volume magnitude and the 6 tets tile each cube exactly
+    p = v[t]
+    vol = np.abs(np.einsum("ni,ni->n", np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), p[:, 3] - p[:, 0])) / 6
+    assert np.allclose(vol.sum(), 1.0, atol=1e-5) and vol.min() > 0
+    path = syn.write_tet_npz(4, str(tmp_path))
+    z = np.load(path)
+    assert set(z.files) == {"vertices", "indices"}          # the reference's npz schema (dmtet.py:223-225)
+    mvp, w2c, campos = syn.cameras(3)
+    assert mvp.shape == (3, 4, 4) and np.allclose(mvp, syn.perspective(25 / 180 * np.pi, 1.0, 0.1, 1000.0) @ w2c, atol=1e-5)
+    assert np.allclose(campos, -np.einsum("bji,bj->bi", w2c[:, :3, :3], w2c[:, :3, 3]), atol=1e-5)
+
+
+def test_overlay_aliases_reference_module_names():
+    ov = pkg("overlay")
+    ov.install()
+    try:
+        import nvdiffrast.torch as dr
+        assert dr.__name__ == "3danimals_b200.nvdiffrast_shim.torch"
+        assert hasattr(dr, "RasterizeGLContext") and hasattr(dr, "DepthPeeler") and hasattr(dr, "antialias")
+        for alias, target in ov.ALIASES.items():
+            if alias.startswith("model."):
+                # parent packages come from the reference tree; resolve the alias through the finder directly
+                spec = ov._finder.find_spec(alias)
+                assert spec is not None and spec.loader.create_module(spec).__name__ == target
+        with pytest.raises(NotImplementedError):
+            dr.texture()
+    finally:
+        ov.uninstall()
+    assert "nvdiffrast.torch" not in sys.modules
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference tree only exists in the build container")
+def test_overlay_lets_reference_predictor_import_our_geometry():
+    """A reference file that imports the hot path (`from ..geometry.dmtet import DMTetGeometry`, BasePredictorBase.py:10)
+    binds to the B200 modules once the overlay is installed, with the rest of `model.*` still from the reference."""
+    import types
+    ov = pkg("overlay")
+    saved = {k: v for k, v in sys.modules.items() if k == "model" or k.startswith("model.")}
+    ov.install()
+    try:
+        for name, rel in (("model", "model"), ("model.geometry", "model/geometry"), ("model.render", "model/render"),
+                          ("model.networks", "model/networks"), ("model.predictors", "model/predictors"), ("model.utils", "model/utils")):
+            m = types.ModuleType(name)
+            m.__path__ = [os.path.join("/root/reference", rel)]
+            sys.modules[name] = m
+        for stub in ("imageio", "omegaconf", "omegaconf.errors"):
+            sys.modules.setdefault(stub, types.ModuleType(stub))
+        sys.modules["omegaconf.errors"].ConfigAttributeError = AttributeError
+        mod = importlib.import_module("model.predictors.BasePredictorBase")
+        assert mod.DMTetGeometry.__module__ == "3danimals_b200.geometry.dmtet"
+        assert importlib.import_module("model.render.render").__name__ == "3danimals_b200.render.render"
+        assert importlib.import_module("model.networks.MLPs").__file__.startswith("/root/reference")
+    finally:
+        ov.uninstall()
+        for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_mesh_bookkeeping_cpu():
+    """Mesh container logic that involves no kernel: lazy UV broadcast, copy_none, clone."""
+    mesh = pkg("render.mesh")
+    v = torch.rand(3, 5, 3)
+    f = torch.tensor([[[0, 1, 2], [2, 3, 4]]])
+    uv = torch.rand(1, 8, 2)
+    m = mesh.Mesh(v, f, v_tex=uv, t_tex_idx=f)
+    assert m.v_tex.shape == (3, 8, 2) and m.v_tex.data_ptr() == uv.data_ptr()      # expand, not repeat
+    c = m.clone()
+    assert c.v_pos is not m.v_pos and torch.equal(c.v_pos, m.v_pos) and len(c) == 3
+    assert mesh.Mesh(base=m).t_pos_idx is f
+    assert torch.equal(mesh.compute_edges(f), torch.tensor([[0, 1], [0, 2], [1, 2], [2, 3], [2, 4], [3, 4]]))
+    assert m.tri_i32().dtype == torch.int32

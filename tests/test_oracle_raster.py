@@ -1,0 +1,142 @@
+"""Self-consistency of the C restatement of the nvdiffrast ops (oracle/raster_ref.c).  No reference golden exists at
+this boundary (parity unpinned), so the restatement is held to analytic answers and to finite differences
+of its own forward passes."""
+import numpy as np
+import pytest
+
+from oracle import raster as R
+
+
+def test_single_triangle_coverage_and_barycentrics():
+    pos = np.array([[[-1, -1, 0.25, 1], [1, -1, 0.25, 1], [-1, 1, 0.25, 1]]], np.float32)
+    tri = np.array([[0, 1, 2]], np.int32)
+    H = W = 8
+    rast = R.rasterize(pos, tri, (H, W))
+    for py in range(H):
+        for px in range(W):
+            fx, fy = (px + 0.5) / W * 2 - 1, (py + 0.5) / H * 2 - 1          # row 0 is clip y = -1
+            inside = fx + fy <= 1e-6
+            assert (rast[0, py, px, 3] == 1.0) == inside, (px, py)
+            if inside and fx + fy < -1e-3:
+                u, v = rast[0, py, px, 0], rast[0, py, px, 1]
+                # weights of vertices 0 and 1: p = u*v0 + v*v1 + (1-u-v)*v2
+                assert abs((u * -1 + v * 1 + (1 - u - v) * -1) - fx) < 1e-5
+                assert abs((u * -1 + v * -1 + (1 - u - v) * 1) - fy) < 1e-5
+                assert abs(rast[0, py, px, 2] - 0.25) < 1e-6
+    assert np.all(rast[rast[..., 3] == 0] == 0)
+
+
+def test_depth_order_tie_break_and_clipping():
+    quad = lambda z: [[-0.9, -0.9, z, 1], [0.9, -0.9, z, 1], [0.9, 0.9, z, 1], [-0.9, 0.9, z, 1]]
+    pos = np.array([quad(0.5) + quad(0.2) + quad(0.2)], np.float32)
+    tri = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7], [8, 9, 10], [8, 10, 11]], np.int32)
+    ids = R.rasterize(pos, tri, (16, 16))[0, ..., 3]
+    assert set(np.unique(ids)) <= {0.0, 3.0, 4.0}            # nearer quad wins; equal depth -> lowest triangle index
+    # depth outside [-1,1] and geometry behind the eye are rejected
+    far = np.array([[[-1, -1, 1.5, 1], [1, -1, 1.5, 1], [0, 1, 1.5, 1], [-1, -1, 0, -1], [1, -1, 0, -1], [0, 1, 0, -1]]], np.float32)
+    assert np.all(R.rasterize(far, np.array([[0, 1, 2], [3, 4, 5]], np.int32), (8, 8))[..., 3] == 0)
+    # perspective-correct barycentrics: w varies across the triangle
+    p = np.array([[[-2, -2, 0.2, 2.0], [3, -3, 0.9, 3.0], [0, 1, 0.1, 1.0]]], np.float32)
+    r = R.rasterize(p, np.array([[0, 1, 2]], np.int32), (32, 32))
+    m = r[0, ..., 3] > 0
+    u, v = r[0, ..., 0][m], r[0, ..., 1][m]
+    clip = u[:, None] * p[0, 0] + v[:, None] * p[0, 1] + (1 - u - v)[:, None] * p[0, 2]
+    ys, xs = np.nonzero(m)
+    assert np.allclose(clip[:, 0] / clip[:, 3], (xs + 0.5) / 32 * 2 - 1, atol=2e-5)
+    assert np.allclose(clip[:, 1] / clip[:, 3], (ys + 0.5) / 32 * 2 - 1, atol=2e-5)
+    assert np.allclose(clip[:, 2] / clip[:, 3], r[0, ..., 2][m], atol=2e-5)
+
+
+def _fd(f, x, g, idx, eps):
+    """directional finite difference of sum(f(x) * g) along coordinate idx (float64 accumulation)"""
+    xp, xm = x.copy(), x.copy()
+    xp[idx] += eps
+    xm[idx] -= eps
+    return float(((f(xp).astype(np.float64) - f(xm).astype(np.float64)) * g).sum() / (2 * eps))
+
+
+def _small_scene():
+    rng = np.random.RandomState(0)
+    pos = np.array([[[-0.7, -0.6, 0.3, 1.0], [0.8, -0.5, 0.4, 1.2], [0.1, 0.75, 0.2, 0.9], [0.9, 0.8, 0.6, 1.1], [-0.8, 0.7, 0.5, 1.0]]], np.float32)
+    tri = np.array([[0, 1, 2], [1, 3, 2], [0, 2, 4]], np.int32)
+    return rng, pos, tri
+
+
+def test_interpolate_and_rasterize_backward_match_finite_differences():
+    rng, pos, tri = _small_scene()
+    res = (24, 24)
+    rast = R.rasterize(pos, tri, res)
+    attr = rng.randn(1, 5, 3).astype(np.float32)
+    g = rng.randn(1, 24, 24, 3)
+    da, dr = R.interpolate_bwd(attr, rast, tri, g.astype(np.float32))
+    for idx in [(0, 0, 0), (0, 2, 1), (0, 4, 2)]:
+        assert abs(_fd(lambda a: R.interpolate(a, rast, tri), attr, g, idx, 1e-2) - da[idx]) < 2e-3 * max(1, abs(da[idx]))
+    # barycentric gradient -> clip positions: differentiate interpolate(rasterize(pos)) with triangle ids held fixed,
+    # i.e. only on pixels whose id does not change under the perturbation
+    d_pos = R.rasterize_bwd(pos, tri, rast, dr)
+    for idx in [(0, 0, 0), (0, 1, 1), (0, 2, 3), (0, 3, 0)]:
+        eps = 1e-3
+        xp, xm = pos.copy(), pos.copy()
+        xp[idx] += eps
+        xm[idx] -= eps
+        rp, rm = R.rasterize(xp, tri, res), R.rasterize(xm, tri, res)
+        keep = (rp[..., 3] == rast[..., 3]) & (rm[..., 3] == rast[..., 3]) & (rast[..., 3] > 0)
+        # keep only pixels strictly inside (unsaturated barycentrics) for a clean derivative
+        fd = (((R.interpolate(attr, rp, tri).astype(np.float64) - R.interpolate(attr, rm, tri)) * g).sum(-1) * keep).sum() / (2 * eps)
+        ref = R.rasterize_bwd(pos, tri, rast, dr * keep[..., None])[idx]
+        assert abs(fd - ref) < 2e-2 * max(1.0, abs(ref)), (idx, fd, ref)
+    assert np.all(d_pos[..., 2] == 0)        # nothing flows through z (only x, y, w)
+
+
+def test_antialias_blends_silhouette_only_and_backward_matches_finite_differences():
+    rng, pos, tri = _small_scene()
+    res = (24, 24)
+    rast = R.rasterize(pos, tri, res)
+    opp = R.edge_adjacency(tri, 5)
+    assert opp.tolist() == [[3, 4, -1], [-1, 0, -1], [-1, -1, 1]]
+    color = rng.rand(1, 24, 24, 3).astype(np.float32) * (rast[..., 3:] > 0) + 0.1
+    out = R.antialias(color, rast, pos, tri, opp)
+    changed = np.abs(out - color).max(-1)[0] > 0
+    ids = rast[0, ..., 3]
+    # only pixels next to an id change can be touched, and interior shared edges (0-1-2 / 1-3-2) are not silhouettes
+    nb = np.zeros_like(changed)
+    nb[:, 1:] |= ids[:, 1:] != ids[:, :-1]
+    nb[:, :-1] |= ids[:, 1:] != ids[:, :-1]
+    nb[1:, :] |= ids[1:, :] != ids[:-1, :]
+    nb[:-1, :] |= ids[1:, :] != ids[:-1, :]
+    assert changed.any() and not (changed & ~nb).any()
+    inner = (ids > 0)
+    both_fg = np.zeros_like(changed)
+    both_fg[:, 1:] |= (ids[:, 1:] != ids[:, :-1]) & inner[:, 1:] & inner[:, :-1]
+    g = rng.randn(1, 24, 24, 3)
+    dc, dp = R.antialias_bwd(color, rast, pos, tri, g.astype(np.float32), opp)
+    for idx in [(0, 5, 7, 1), (0, 12, 12, 0), (0, 20, 3, 2)]:
+        fd = _fd(lambda c: R.antialias(c, rast, pos, tri, opp), color, g, idx, 1e-2)
+        assert abs(fd - dc[idx]) < 2e-3 * max(1, abs(dc[idx]))
+    # position gradient (the silhouette / mask-loss gradient): finite differences with the rast buffer held fixed.
+    # The upstream gradient is constant per channel: where a pair's blend weight crosses zero the blend moves from one
+    # pixel of the pair to the other (continuous, but a kink), which a per-pixel random gradient would turn into FD noise.
+    gc = np.broadcast_to(rng.randn(3), g.shape).copy()
+    dc, dp = R.antialias_bwd(color, rast, pos, tri, gc.astype(np.float32), opp)
+    assert np.abs(dp).max() > 0
+    worst = 0.0
+    for v in range(5):
+        for c in (0, 1, 3):
+            fd = _fd(lambda p: R.antialias(color, rast, p, tri, opp), pos, gc, (0, v, c), 2e-4)
+            worst = max(worst, abs(fd - dp[0, v, c]) / max(1.0, np.abs(dp).max()))
+    assert worst < 1e-2, worst
+
+
+def test_vertex_normals_c_matches_numpy_restatement():
+    from oracle import geometry_np as gnp
+    rng = np.random.RandomState(1)
+    v = rng.randn(2, 30, 3).astype(np.float32)
+    f = rng.randint(0, 29, size=(50, 3)).astype(np.int32)        # vertex 29 is isolated -> (0,0,1) fallback
+    n_c, nsum = R.vertex_normals(v, f)
+    assert np.allclose(n_c, gnp.auto_normals(v, f.astype(np.int64)), atol=1e-6)
+    assert np.array_equal(n_c[:, 29], np.array([[0, 0, 1], [0, 0, 1]], np.float32))
+    g = rng.randn(2, 30, 3)
+    dp = R.vertex_normals_bwd(v, f, nsum, g.astype(np.float32))
+    for idx in [(0, 3, 0), (1, 10, 2), (0, 20, 1)]:
+        fd = _fd(lambda x: R.vertex_normals(x, f)[0], v, g, idx, 1e-3)
+        assert abs(fd - dp[idx]) < 2e-2 * max(1, abs(dp[idx]))
