@@ -327,33 +327,46 @@ __global__ void __launch_bounds__(256) aa_bwd_kernel(AAParams P, AAGrad G, float
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Fast path (composite mode = the training path): prepare once per render, then stream + fix up.
-//   aa_prepare   : one pass over rast -> coverage bitmask (1 bit/pixel) + compact list of silhouette pixels (pixels
-//                  with a 4-neighbour of different triangle id).  Shared by every antialias launch of the render
-//                  (2 keys x fwd/bwd), which therefore never read rast's 16 B/pixel again.
-//   aa_*_stream  : pure HBM streaming - forward: masked composite copy NHWC(C-1) -> NHWC(C); backward: masked copy of
-//                  the upstream gradient (NHWC, or NCHW transposed through a per-warp shared-memory tile) -> NHWC.
-//                  No barriers, no divergence, a handful of registers.
-//   aa_*_fix     : one thread per silhouette pixel adds the blend terms in the generic kernel's order (bit-identical
-//                  results) and, backward, scatters the edge-vertex position gradients.
+// Fast path (composite mode = the training path): analyse once per render, then every launch is ONE streaming pass.
+//   aa_prepare   : one pass over rast -> coverage bitmask + silhouette bitmask (1 bit/pixel each; silhouette = a
+//                  4-neighbour carries a different triangle id) + compact list of silhouette pixels.
+//   aa_pairs     : one thread per (silhouette pixel, owned pair: right / down) runs the pair analysis ONCE and stores
+//                  (alpha, triangle, edge) in a dense per-pixel record touched only at silhouette pixels.  The 2 keys x
+//                  (fwd, bwd) launches of a render share it, so none of them reads rast / pos / tri again.
+//   aa_fwd_tile  : warp-autonomous 32-pixel tiles: float4 loads of NHWC(C-1) colour -> smem -> float4 stores of the
+//                  composited NHWC(C) image; elements of silhouette pixels add their <=4 blend terms in the generic
+//                  kernel's order (bit-identical results).
+//   aa_bwd_tile  : same shape for the gradient: NCHW rows or NHWC float4s -> smem -> masked NHWC(C-1) float4 stores,
+//                  silhouette elements gather their pair terms; the first AA_POS_BLOCKS blocks of the same launch
+//                  scatter the edge-vertex position gradients (16 lanes per pair, channels across lanes).
 // ------------------------------------------------------------------------------------------------------------
 struct AAContext {
-    uint32_t* cover;   // [ceil(B*HW/32)] coverage bits
-    int* count;        // [1] silhouette pixels
-    int* list;         // [B*HW] flat pixel index b*HW + p
+    uint32_t* cover;   // [B*HW/32] coverage bits
+    uint32_t* act;     // [B*HW/32] pixels with at least one active (blending) pair - the true silhouette
+    int* count;        // [0] pixels whose 4-neighbourhood carries another triangle id (candidates), [1] active pixels
+    int* list;         // [B*HW] candidate pixels (flat index b*HW + p)
+    int* alist;        // [B*HW] active pixels
+    int2* ainfo;       // [B*HW] per active-list entry: (triangle << 3) | (edge << 1) | shifted of the owned pairs (p,right), (p,down)
+    float4* rec;       // [B*HW] dense, valid where the act bit is set: blend weights of the pixel's four pairs in the
+                       //        generic kernel's order (up,p) (left,p) (p,right) (p,down); 0 = inactive
 };
 
 size_t aa_ctx_layout(int B, int H, int W, void* base, AAContext* ctx)
 {
     size_t npix = (size_t)B * H * W;
     size_t cb = b2a_align(((npix + 31) / 32) * 4);
+    size_t lb = b2a_align(npix * 4);
     if (ctx) {
         char* p = (char*)base;
         ctx->cover = (uint32_t*)p;
-        ctx->count = (int*)(p + cb);
-        ctx->list = (int*)(p + cb + 256);
+        ctx->act = (uint32_t*)(p + cb);
+        ctx->count = (int*)(p + 2 * cb);
+        ctx->list = (int*)(p + 2 * cb + 256);
+        ctx->alist = (int*)(p + 2 * cb + 256 + lb);
+        ctx->ainfo = (int2*)(p + 2 * cb + 256 + 2 * lb);
+        ctx->rec = (float4*)(p + 2 * cb + 256 + 4 * lb);
     }
-    return cb + 256 + b2a_align(npix * 4);
+    return 2 * cb + 256 + 4 * lb + b2a_align(npix * sizeof(float4));
 }
 
 // grid-stride over all B*HW pixels (HW % 32 == 0, so a warp never straddles two images)
@@ -373,172 +386,270 @@ __global__ void __launch_bounds__(256) aa_prepare_kernel(const float* __restrict
         if (px + 1 >= W) idr = idc;
         float idu = py > 0 ? __ldg(rast + (i - W) * 4 + 3) : idc;
         float idd = py + 1 < H ? __ldg(rast + (i + W) * 4 + 3) : idc;
-        bool sil = idu != idc || idl != idc || idr != idc || idd != idc;
+        bool cand = idu != idc || idl != idc || idr != idc || idd != idc;
         uint32_t cov = __ballot_sync(0xffffffffu, idc > 0.f);
-        uint32_t sm = __ballot_sync(0xffffffffu, sil);
+        uint32_t cm = __ballot_sync(0xffffffffu, cand);
         if (lane == 0) ctx.cover[i >> 5] = cov;
-        if (sm) {
+        if (cm) {
             int base = 0;
-            if (lane == 0) base = atomicAdd(ctx.count, __popc(sm));
+            if (lane == 0) base = atomicAdd(ctx.count, __popc(cm));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (sil) ctx.list[base + __popc(sm & ((1u << lane) - 1u))] = (int)i;
+            if (cand) ctx.list[base + __popc(cm & ((1u << lane) - 1u))] = (int)i;
         }
     }
 }
 
-// forward stream: out[pp*C + c] = covered ? (c < C-1 ? color[pp*(C-1) + c] : 1) : bg.   One thread per output element.
+// four lanes per candidate pixel, one per pair k = 0 (up,p)  1 (left,p)  2 (p,right)  3 (p,down).  Each pair is analysed
+// from both of its pixels (identical arithmetic), so a pixel's record holds everything its fix-up needs.  Pixels with
+// a blending pair (few: the silhouette proper) get a record, an act bit and an entry in the active list.
+__global__ void __launch_bounds__(128) aa_pairs_kernel(AAParams P, AAContext ctx)
+{
+    const int HW = P.H * P.W;
+    const int count = ctx.count[0];
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < 4 * count; base += gridDim.x * blockDim.x) {
+        const int i = base + lane, k = i & 3;
+        float alpha = 0.f;
+        int info = 0, flat = 0;
+        if (i < 4 * count) {
+            flat = ctx.list[i >> 2];
+            const int b = flat / HW, p = flat - b * HW;
+            const int qx = p % P.W + c_pair_dx[k], qy = p / P.W + c_pair_dy[k], d = c_pair_d[k];
+            if (qx >= 0 && qy >= 0 && (d == 0 ? qx + 1 < P.W : qy + 1 < P.H)) {
+                const float* rast_b = P.rast + (size_t)b * HW * 4;
+                const int q0 = qy * P.W + qx;
+                float4 r0 = ldg4(rast_b + (size_t)q0 * 4), r1 = ldg4(rast_b + (size_t)(q0 + (d ? P.W : 1)) * 4);
+                AAPair r;
+                if (aa_analyze(P, P.pos + (size_t)b * P.V * 4, r0, r1, qx, qy, d, r)) {
+                    alpha = r.alpha;
+                    info = (r.tri << 3) | (r.di << 1) | ((r.px != qx || r.py != qy) ? 1 : 0);
+                }
+            }
+        }
+        const int g0 = lane & ~3;
+        float4 a;
+        a.x = __shfl_sync(0xffffffffu, alpha, g0);
+        a.y = __shfl_sync(0xffffffffu, alpha, g0 + 1);
+        a.z = __shfl_sync(0xffffffffu, alpha, g0 + 2);
+        a.w = __shfl_sync(0xffffffffu, alpha, g0 + 3);
+        int i2 = __shfl_sync(0xffffffffu, info, g0 + 2), i3 = __shfl_sync(0xffffffffu, info, g0 + 3);
+        if (k == 0 && (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f)) {
+            ctx.rec[flat] = a;
+            atomicOr(ctx.act + (flat >> 5), 1u << (flat & 31));
+            int slot = atomicAdd(ctx.count + 1, 1);
+            ctx.alist[slot] = flat;
+            ctx.ainfo[slot] = make_int2(i2, i3);
+        }
+    }
+}
+
+__device__ __forceinline__ bool aa_bit(const uint32_t* __restrict__ bits, size_t flat) { return (__ldg(bits + (flat >> 5)) >> (flat & 31)) & 1u; }
+
+// composited colour of channel c at flat pixel q (image b): colour [.,C-1] | 1 where covered, bg (or 0) elsewhere
 template <int C>
-__global__ void __launch_bounds__(256) aa_fwd_stream_kernel(const float* __restrict__ color, const float* __restrict__ bg, int Bg,
-                                                            const uint32_t* __restrict__ cover, int HW, float* __restrict__ out)
+__device__ __forceinline__ float aa_comp(const float* __restrict__ color, const float* __restrict__ bg, int Bg, const uint32_t* __restrict__ cover,
+                                         int b, int HW, size_t q, int c)
 {
-    const int b = blockIdx.y;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;   // < HW*C (< 2^31 checked on the host)
-    if (e >= HW * C) return;
-    const int pp = e / C, c = e - pp * C;
-    const bool covered = (__ldg(cover + (((size_t)b * HW + pp) >> 5)) >> (pp & 31)) & 1u;
-    float v;
-    if (covered) v = c < C - 1 ? __ldg(color + (size_t)b * HW * (C - 1) + (e - pp)) : 1.f;
-    else v = bg ? __ldg(bg + (size_t)(Bg == 1 ? 0 : b) * HW * C + e) : 0.f;
-    out[(size_t)b * HW * C + e] = v;
+    if (aa_bit(cover, q)) return c < C - 1 ? __ldg(color + q * (C - 1) + c) : 1.f;
+    return bg ? __ldg(bg + (Bg == 1 ? q - (size_t)b * HW : q) * C + c) : 0.f;
 }
 
-// backward stream, NHWC-contiguous gradient: d_color[pp*CC + c] = covered && c < CG ? g[pp*CG + c] : 0
-template <int CC, int CG>
-__global__ void __launch_bounds__(256) aa_bwd_stream_nhwc_kernel(const float* __restrict__ g, int64_t sb, const uint32_t* __restrict__ cover,
-                                                                 int HW, float* __restrict__ d_color)
-{
-    const int b = blockIdx.y;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= HW * CC) return;
-    const int pp = e / CC, c = e - pp * CC;
-    const bool covered = (__ldg(cover + (((size_t)b * HW + pp) >> 5)) >> (pp & 31)) & 1u;
-    d_color[(size_t)b * HW * CC + e] = (covered && c < CG) ? __ldg(g + (int64_t)b * sb + (int64_t)pp * CG + c) : 0.f;
-}
+// j-th (0-based) set bit of m
+__device__ __forceinline__ int nth_bit(uint32_t m, int j) { return (int)__fns(m, 0, j + 1); }
 
-// backward stream, NCHW gradient (sx == 1): each warp owns 32 consecutive pixels of a row; CG coalesced 128-byte row
-// loads -> per-warp smem tile -> CC coalesced 128-byte stores.  Warp-autonomous: __syncwarp only.
-template <int CC, int CG>
-__global__ void __launch_bounds__(256) aa_bwd_stream_nchw_kernel(const float* __restrict__ g, int64_t sb, int64_t sy, int64_t sc,
-                                                                 const uint32_t* __restrict__ cover, int HW, int W,
-                                                                 float* __restrict__ d_color)
+// Forward.  The smem tile holds the composited image of 32 pixels in OUTPUT layout [pp*C + c]; elements of active
+// pixels are fixed in place (work items = active pixel x channel, spread over the lanes) before the float4 stores.
+template <int C>
+__global__ void __launch_bounds__(256) aa_fwd_tile_kernel(const float* __restrict__ color, const float* __restrict__ bg, int Bg, AAContext ctx,
+                                                          int B, int H, int W, float* __restrict__ out)
 {
-    __shared__ float tile[8][CG][33];
-    const int b = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int t0 = (blockIdx.x * 8 + w) * 32;   // first pixel of this warp's tile
-    if (t0 >= HW) return;
-    const int py = t0 / W, px0 = t0 - py * W;
-    const float* gp = g + (int64_t)b * sb + (int64_t)py * sy + px0 + lane;
-    float v[CG];
+    constexpr int CI = C - 1;
+    __shared__ __align__(16) float s_tile[8][32 * C];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int HW = H * W;
+    const int t = blockIdx.x * 8 + w;                 // 32-pixel tile
+    if ((int64_t)t * 32 >= (int64_t)B * HW) return;
+    const size_t P0 = (size_t)t * 32;
+    const int b = (int)(P0 / HW);
+    const uint32_t cov = __ldg(ctx.cover + t), act = __ldg(ctx.act + t);
+    float* tile = s_tile[w];
+    float4* dst = reinterpret_cast<float4*>(out + P0 * C);
+    // background (or zeros) in output layout
+    if (cov != 0xffffffffu) {
+        const float4* bsrc = bg ? reinterpret_cast<const float4*>(bg + (Bg == 1 ? P0 - (size_t)b * HW : P0) * C) : nullptr;
+        if (cov == 0u && act == 0u) {      // pure background tile: straight copy
 #pragma unroll
-    for (int c = 0; c < CG; c++) v[c] = __ldg(gp + (int64_t)c * sc);
-    const uint32_t m = __ldg(cover + (((size_t)b * HW + t0) >> 5));
+            for (int i = lane; i < 8 * C; i += 32) dst[i] = bsrc ? __ldg(bsrc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            return;
+        }
 #pragma unroll
-    for (int c = 0; c < CG; c++) tile[w][c][lane] = v[c];
+        for (int i = lane; i < 8 * C; i += 32) reinterpret_cast<float4*>(tile)[i] = bsrc ? __ldg(bsrc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+    }
+    if (cov) {
+        const float4* src = reinterpret_cast<const float4*>(color + P0 * CI);
+#pragma unroll
+        for (int i = lane; i < 8 * CI; i += 32) {
+            float4 x = __ldg(src + i);
+            float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int e = 4 * i + j;
+                const int pp = e / CI, c = e - pp * CI;
+                if ((cov >> pp) & 1u) tile[pp * C + c] = xv[j];
+            }
+        }
+        if ((cov >> lane) & 1u) tile[lane * C + CI] = 1.f;
+    }
     __syncwarp();
-    float* o = d_color + ((size_t)b * HW + t0) * CC;
-#pragma unroll
-    for (int i = 0; i < CC; i++) {
-        const int e = i * 32 + lane;
-        const int pp = e / CC, c = e - pp * CC;
-        o[e] = (c < CG && ((m >> pp) & 1u)) ? tile[w][c < CG ? c : 0][pp] : 0.f;
+    if (act) {
+        const int items = __popc(act) * C;
+        for (int item = lane; item < items; item += 32) {
+            const int j = item / C, c = item - j * C;
+            const int pp = nth_bit(act, j);
+            const size_t flat = P0 + pp;
+            const float4 a = __ldg(ctx.rec + flat);
+            const float own = tile[pp * C + c];
+            // this pixel is the blend target of (up,p)/(left,p) when alpha < 0 and of (p,right)/(p,down) when alpha > 0.
+            // Neighbour colours come from global memory (the unblended input), loaded up front so the loads overlap.
+            const bool k0 = a.x < 0.f, k1 = a.y < 0.f, k2 = a.z > 0.f, k3 = a.w > 0.f;
+            const float cu = k0 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - W, c) : own;
+            const float cl = k1 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - 1, c) : own;
+            const float cr = k2 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + 1, c) : own;
+            const float cd = k3 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + W, c) : own;
+            float acc = own;
+            if (k0) acc += a.x * (own - cu);
+            if (k1) acc += a.y * (own - cl);
+            if (k2) acc += a.z * (cr - own);
+            if (k3) acc += a.w * (cd - own);
+            tile[pp * C + c] = acc;     // each item touches only its own slot
+        }
+        __syncwarp();
     }
+#pragma unroll
+    for (int i = lane; i < 8 * C; i += 32) dst[i] = reinterpret_cast<const float4*>(tile)[i];
 }
 
-// the four pair analyses of one silhouette pixel
-struct AAPixelPairs {
-    float sgn[4];      // signed blend weight applied to this pixel's gradient / colour (0 = pair inactive)
-    int target[4];     // pixel receiving the blend
-    int q0[4], q1[4];
-    bool cov0[4], cov1[4];
-    AAPair pair[2];    // analysis of the two pairs this pixel owns (k = 2: right, k = 3: down)
-    bool own[2];
-};
+constexpr int AA_POS_BLOCKS = 148 * 4;
 
-__device__ __forceinline__ void aa_pixel_pairs(const AAParams& P, const float* __restrict__ rast_b, const float* __restrict__ pos_b, int p,
-                                               AAPixelPairs& pp, bool bwd)
-{
-    const int px = p % P.W, py = p / P.W;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        pp.sgn[k] = 0.f; pp.target[k] = p; pp.q0[k] = p; pp.q1[k] = p; pp.cov0[k] = pp.cov1[k] = false;
-        if (k >= 2) pp.own[k - 2] = false;
-        int qx = px + c_pair_dx[k], qy = py + c_pair_dy[k], d = c_pair_d[k];
-        if (qx < 0 || qy < 0) continue;
-        if (d == 0 ? qx + 1 >= P.W : qy + 1 >= P.H) continue;
-        int q0 = qy * P.W + qx, q1 = q0 + (d ? P.W : 1);
-        float4 r0 = ldg4(rast_b + (size_t)q0 * 4), r1 = ldg4(rast_b + (size_t)q1 * 4);
-        AAPair r;
-        if (!aa_analyze(P, pos_b, r0, r1, qx, qy, d, r)) continue;
-        int target = r.alpha > 0.f ? q0 : q1;
-        pp.target[k] = target; pp.q0[k] = q0; pp.q1[k] = q1; pp.cov0[k] = r0.w > 0.f; pp.cov1[k] = r1.w > 0.f;
-        if (bwd) pp.sgn[k] = (p == q0) ? -r.alpha : r.alpha;          // d_color[p] -= / += alpha * g[target]
-        else pp.sgn[k] = (target == p) ? r.alpha : 0.f;               // out[p] += alpha * (c[q1] - c[q0]) when p is the target
-        if (k >= 2) { pp.pair[k - 2] = r; pp.own[k - 2] = true; }     // k = 2,3 have q0 == p
-    }
-}
-
-__global__ void __launch_bounds__(128) aa_fwd_fix_kernel(AAParams P, AAContext ctx, float* __restrict__ out)
+// d_pos role: one half-warp per owned pair of an active pixel, channels across the 16 lanes
+template <int C>
+__device__ void aa_bwd_pos_role(const AAParams& P, const AAGrad& G, const AAContext& ctx, float* __restrict__ d_pos)
 {
     const int HW = P.H * P.W;
-    const int count = *ctx.count;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const int flat = ctx.list[i];
+    const int lane = threadIdx.x & 31, sub = lane & 15, d = lane >> 4;
+    const int count = ctx.count[1];
+    const int nwarp = AA_POS_BLOCKS * (blockDim.x >> 5);
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += nwarp) {
+        const int flat = ctx.alist[i];
         const int b = flat / HW, p = flat - b * HW;
-        AAPixelPairs pp;
-        aa_pixel_pairs(P, P.rast + (size_t)b * HW * 4, P.pos + (size_t)b * P.V * 4, p, pp, false);
-        if (pp.sgn[0] == 0.f && pp.sgn[1] == 0.f && pp.sgn[2] == 0.f && pp.sgn[3] == 0.f) continue;
-        float* o = out + ((size_t)b * HW + p) * P.C;
-#pragma unroll 2
-        for (int c = 0; c < P.C; c++) {
-            float acc = o[c];
+        const float4 av = __ldg(ctx.rec + flat);
+        const float a = d ? av.w : av.z;
+        const bool on = a != 0.f && fabsf(a) < 0.5f;
+        float dd = 0.f;
+        const size_t q0 = (size_t)flat, q1 = q0 + (d ? P.W : 1);
+        if (on) {
+            const int target = a > 0.f ? p : p + (d ? P.W : 1);
+            for (int c = sub; c < G.Cg; c += 16)
+                dd += grad_at(G, P.W, b, target, c) * (aa_comp<C>(P.color, P.bg, P.Bg, ctx.cover, b, HW, q1, c) -
+                                                       aa_comp<C>(P.color, P.bg, P.Bg, ctx.cover, b, HW, q0, c));
+        }
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (pp.sgn[k] != 0.f) acc += pp.sgn[k] * (comp_color(P, b, pp.q1[k], c, pp.cov1[k]) - comp_color(P, b, pp.q0[k], c, pp.cov0[k]));
-            o[c] = acc;
+        for (int o = 8; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+        if (on && sub == 0 && dd != 0.f) {
+            const int2 inf = __ldg(ctx.ainfo + i);
+            const int info = d ? inf.y : inf.x;
+            AAPair r;
+            r.alpha = a; r.tri = info >> 3; r.di = (info >> 1) & 3;
+            r.px = p % P.W + ((info & 1) ? 1 - d : 0);
+            r.py = p / P.W + ((info & 1) ? d : 0);
+            aa_pos_grad(P, P.pos + (size_t)b * P.V * 4, r, d, dd, d_pos + (size_t)b * P.V * 4);
         }
     }
 }
 
-__global__ void __launch_bounds__(128) aa_bwd_fix_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
-                                                         float* __restrict__ d_pos)
+// Backward.  CC = colour channels written, CG = gradient channels read (CG >= CC; CG == CC + 1 when the alpha channel is
+// kept).  NCHW: the gradient's x stride is 1 (each warp loads CC coalesced 128-byte rows); else NHWC-contiguous (float4s).
+// The smem tile [pp*ST + c] holds g; covered silhouette elements gather their pair terms in place, then masked stores.
+template <int C, int CC, int CG, bool NCHW>
+__global__ void __launch_bounds__(256) aa_bwd_tile_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
+                                                          float* __restrict__ d_pos)
 {
+    constexpr int ST = CG + 1;   // padded pixel stride: conflict-free for both access patterns
+    __shared__ float s_tile[8][32 * ST];
+    if (blockIdx.x < AA_POS_BLOCKS) {
+        if (d_pos) aa_bwd_pos_role<C>(P, G, ctx, d_pos);
+        return;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int HW = P.H * P.W;
-    const int Cc = P.C - 1;
-    const int count = *ctx.count;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const int flat = ctx.list[i];
-        const int b = flat / HW, p = flat - b * HW;
-        const float* rast_b = P.rast + (size_t)b * HW * 4;
-        const float* pos_b = P.pos + (size_t)b * P.V * 4;
-        AAPixelPairs pp;
-        aa_pixel_pairs(P, rast_b, pos_b, p, pp, true);
-        const bool covered = __ldg(rast_b + (size_t)p * 4 + 3) > 0.f;
-        const bool any = pp.sgn[0] != 0.f || pp.sgn[1] != 0.f || pp.sgn[2] != 0.f || pp.sgn[3] != 0.f;
-        if (!any && !pp.own[0] && !pp.own[1]) continue;
-        float dd0 = 0.f, dd1 = 0.f;
-        float* o = d_color ? d_color + ((size_t)b * HW + p) * Cc : nullptr;
-        const bool want_pos = d_pos != nullptr;
-#pragma unroll 2
-        for (int c = 0; c < G.Cg; c++) {
-            float gy[4];
+    const int t = (blockIdx.x - AA_POS_BLOCKS) * 8 + w;
+    if ((int64_t)t * 32 >= (int64_t)P.B * HW) return;
+    const size_t P0 = (size_t)t * 32;
+    const int b = (int)(P0 / HW), p0 = (int)(P0 - (size_t)b * HW);
+    const uint32_t cov = __ldg(ctx.cover + t), act = __ldg(ctx.act + t) & cov;
+    float* tile = s_tile[w];
+    float4* dst = reinterpret_cast<float4*>(d_color + P0 * CC);
+    if (cov == 0u) {   // nothing covered in this tile: the colour gradient is zero (background pixels never reach `color`)
 #pragma unroll
-            for (int k = 0; k < 4; k++) gy[k] = (pp.sgn[k] != 0.f || (k >= 2 && pp.own[k - 2])) ? grad_at(G, P.W, b, pp.target[k], c) : 0.f;
-            if (o && covered && c < Cc && any) {
-                float acc = o[c];
+        for (int i = lane; i < 8 * CC; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    if (NCHW) {
+        const int py = p0 / P.W, px0 = p0 - py * P.W;   // W % 32 == 0: the tile lies in one row
+        const float* gp = G.d_out + (int64_t)b * G.sb + (int64_t)py * G.sy + px0 + lane;
+        float v[CC];
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (pp.sgn[k] != 0.f) acc += pp.sgn[k] * gy[k];
-                o[c] = acc;
-            }
-            if (want_pos) {
-                if (pp.own[0]) dd0 += gy[2] * (comp_color(P, b, pp.q1[2], c, pp.cov1[2]) - comp_color(P, b, pp.q0[2], c, pp.cov0[2]));
-                if (pp.own[1]) dd1 += gy[3] * (comp_color(P, b, pp.q1[3], c, pp.cov1[3]) - comp_color(P, b, pp.q0[3], c, pp.cov0[3]));
+        for (int c = 0; c < CC; c++) v[c] = __ldg(gp + (int64_t)c * G.sc);
+#pragma unroll
+        for (int c = 0; c < CC; c++) tile[lane * ST + c] = v[c];
+    } else {
+        const float4* src = reinterpret_cast<const float4*>(G.d_out + (int64_t)b * G.sb + (int64_t)p0 * CG);
+#pragma unroll
+        for (int i = lane; i < 8 * CG; i += 32) {
+            float4 x = __ldg(src + i);
+            float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int e = 4 * i + j;
+                const int pp = e / CG, c = e - pp * CG;
+                tile[pp * ST + c] = xv[j];
             }
         }
-        if (want_pos) {
-            if (pp.own[0] && dd0 != 0.f && fabsf(pp.pair[0].alpha) < 0.5f) aa_pos_grad(P, pos_b, pp.pair[0], 0, dd0, d_pos + (size_t)b * P.V * 4);
-            if (pp.own[1] && dd1 != 0.f && fabsf(pp.pair[1].alpha) < 0.5f) aa_pos_grad(P, pos_b, pp.pair[1], 1, dd1, d_pos + (size_t)b * P.V * 4);
+    }
+    __syncwarp();
+    if (act) {
+        const int items = __popc(act) * CC;
+        for (int item = lane; item < items; item += 32) {
+            const int j = item / CC, c = item - j * CC;
+            const int pp = nth_bit(act, j);
+            const int p = p0 + pp;
+            const float4 a = __ldg(ctx.rec + P0 + pp);
+            const float own = tile[pp * ST + c];
+            // d_color[p] = g[p] + a_up g[t] + a_left g[t] - a_right g[t] - a_down g[t], t = the pair's blend target
+            const float gu = a.x != 0.f ? (a.x > 0.f ? grad_at(G, P.W, b, p - P.W, c) : own) : 0.f;
+            const float gl = a.y != 0.f ? (a.y > 0.f ? grad_at(G, P.W, b, p - 1, c) : own) : 0.f;
+            const float gr = a.z != 0.f ? (a.z > 0.f ? own : grad_at(G, P.W, b, p + 1, c)) : 0.f;
+            const float gd = a.w != 0.f ? (a.w > 0.f ? own : grad_at(G, P.W, b, p + P.W, c)) : 0.f;
+            float acc = own;
+            if (a.x != 0.f) acc += a.x * gu;
+            if (a.y != 0.f) acc += a.y * gl;
+            if (a.z != 0.f) acc -= a.z * gr;
+            if (a.w != 0.f) acc -= a.w * gd;
+            tile[pp * ST + c] = acc;    // each item touches only its own slot
         }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int i = lane; i < 8 * CC; i += 32) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int e = 4 * i + j;
+            const int pp = e / CC, c = e - pp * CC;
+            v[j] = ((cov >> pp) & 1u) ? tile[pp * ST + c] : 0.f;
+        }
+        dst[i] = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -590,29 +701,44 @@ B2A_API int b2a_antialias_workspace_bytes(int B, int H, int W, size_t* bytes)
     return 0;
 }
 
-B2A_API int b2a_antialias_prepare(const float* rast, int B, int H, int W, void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream_)
+B2A_API int b2a_antialias_prepare(const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, int B, int64_t V, int64_t F,
+                                  int H, int W, void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    B2A_CHECK_ARG(rast && aa_ctx, "null pointer");
-    B2A_CHECK_ARG(B > 0 && H > 0 && W > 0 && (int64_t)B * H * W < (1ll << 31), "shape");
+    B2A_CHECK_ARG(rast && pos && tri && opp && aa_ctx, "null pointer");
+    B2A_CHECK_ARG(B > 0 && H > 0 && W > 0 && (int64_t)B * H * W < (1ll << 31) && V > 0 && F >= 0 && F < (1ll << 28), "shape");
     B2A_CHECK_ARG(((int64_t)H * W) % 32 == 0, "H*W must be a multiple of 32 for the prepared fast path");
+    B2A_CHECK_ARG(((uintptr_t)pos & 15) == 0 && ((uintptr_t)rast & 15) == 0 && ((uintptr_t)aa_ctx & 15) == 0, "pos/rast/aa_ctx must be 16-byte aligned");
     AAContext ctx;
     B2A_CHECK_ARG(aa_ctx_layout(B, H, W, aa_ctx, &ctx) <= aa_ctx_bytes, "context workspace too small");
-    B2A_CUDA_OK(cudaMemsetAsync(ctx.count, 0, sizeof(int), stream));
     int64_t n = (int64_t)B * H * W;
+    B2A_CUDA_OK(cudaMemsetAsync(ctx.act, 0, (size_t)((char*)ctx.count - (char*)ctx.act) + 2 * sizeof(int), stream));
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (blocks > 148u * 16u) blocks = 148u * 16u;
     aa_prepare_kernel<<<blocks, 256, 0, stream>>>(rast, B, H, W, ctx);
+    AAParams P{nullptr, nullptr, rast, pos, tri, opp, 1, 1, B, H, W, 0, V, F};
+    unsigned pblocks = (unsigned)((4 * n + 127) / 128);
+    if (pblocks > 148u * 16u) pblocks = 148u * 16u;
+    aa_pairs_kernel<<<pblocks, 128, 0, stream>>>(P, ctx);
     B2A_LAUNCH_OK();
     return 0;
 }
 
 namespace {
+bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
 bool aa_fast_ok(int composite, const void* aa_ctx, size_t aa_ctx_bytes, int B, int H, int W, int C, AAContext* ctx)
 {
     if (!composite || !aa_ctx) return false;
-    if (((int64_t)H * W) % 32 != 0 || (int64_t)H * W * C >= (1ll << 31)) return false;
+    if (((int64_t)H * W) % 32 != 0 || (int64_t)B * H * W * C >= (1ll << 31)) return false;
     return aa_ctx_layout(B, H, W, const_cast<void*>(aa_ctx), ctx) <= aa_ctx_bytes;
+}
+
+template <int C>
+void aa_fwd_tile(const float* color, const float* bg, int Bg, const AAContext& ctx, int B, int H, int W, float* out, cudaStream_t stream)
+{
+    unsigned tiles = (unsigned)(((int64_t)B * H * W) / 32);
+    aa_fwd_tile_kernel<C><<<b2a_blocks(tiles, 8), 256, 0, stream>>>(color, bg, Bg, ctx, B, H, W, out);
 }
 }  // namespace
 
@@ -626,35 +752,33 @@ B2A_API int b2a_antialias_fwd(const float* color, const float* bg, int Bg, int c
     B2A_CHECK_ARG(out, "null pointer");
     AAParams P{color, bg, rast, pos, tri, opp, Bg, composite, B, H, W, C, V, F};
     AAContext ctx;
-    const int HW = H * W;
-    bool fast = aa_fast_ok(composite, aa_ctx, aa_ctx_bytes, B, H, W, C, &ctx);
+    bool fast = aa_fast_ok(composite, aa_ctx, aa_ctx_bytes, B, H, W, C, &ctx) && aligned16(color) && aligned16(bg) && aligned16(out);
     if (fast) {
-        dim3 grid(b2a_blocks((int64_t)HW * C, 256), B);
         switch (C) {
-            case 2: aa_fwd_stream_kernel<2><<<grid, 256, 0, stream>>>(color, bg, Bg, ctx.cover, HW, out); break;
-            case 3: aa_fwd_stream_kernel<3><<<grid, 256, 0, stream>>>(color, bg, Bg, ctx.cover, HW, out); break;
-            case 4: aa_fwd_stream_kernel<4><<<grid, 256, 0, stream>>>(color, bg, Bg, ctx.cover, HW, out); break;
-            case 17: aa_fwd_stream_kernel<17><<<grid, 256, 0, stream>>>(color, bg, Bg, ctx.cover, HW, out); break;
+            case 2: aa_fwd_tile<2>(color, bg, Bg, ctx, B, H, W, out, stream); break;
+            case 3: aa_fwd_tile<3>(color, bg, Bg, ctx, B, H, W, out, stream); break;
+            case 4: aa_fwd_tile<4>(color, bg, Bg, ctx, B, H, W, out, stream); break;
+            case 17: aa_fwd_tile<17>(color, bg, Bg, ctx, B, H, W, out, stream); break;
             default: fast = false;
         }
     }
-    if (fast) aa_fwd_fix_kernel<<<148 * 2, 128, 0, stream>>>(P, ctx, out);
-    else aa_fwd_kernel<<<dim3(b2a_blocks((int64_t)HW * C, 256), B), 256, 0, stream>>>(P, out);
+    if (!fast) aa_fwd_kernel<<<dim3(b2a_blocks((int64_t)H * W * C, 256), B), 256, 0, stream>>>(P, out);
     B2A_LAUNCH_OK();
     return 0;
 }
 
 namespace {
-template <int CC, int CG>
-bool aa_bwd_stream(const AAGrad& G, const AAContext& ctx, int B, int H, int W, float* d_color, cudaStream_t stream)
+template <int C, int CC, int CG>
+bool aa_bwd_tile(const AAParams& P, const AAGrad& G, const AAContext& ctx, float* d_color, float* d_pos, cudaStream_t stream)
 {
-    const int HW = H * W;
-    if (G.sc == 1 && G.sx == CG && G.sy == (int64_t)W * CG) {
-        aa_bwd_stream_nhwc_kernel<CC, CG><<<dim3(b2a_blocks((int64_t)HW * CC, 256), B), 256, 0, stream>>>(G.d_out, G.sb, ctx.cover, HW, d_color);
+    unsigned tiles = (unsigned)(((int64_t)P.B * P.H * P.W) / 32);
+    unsigned grid = AA_POS_BLOCKS + b2a_blocks(tiles, 8);
+    if (G.sc == 1 && G.sx == CG && G.sy == (int64_t)P.W * CG && G.sb % 4 == 0 && aligned16(G.d_out)) {
+        aa_bwd_tile_kernel<C, CC, CG, false><<<grid, 256, 0, stream>>>(P, G, ctx, d_color, d_pos);
         return true;
     }
-    if (G.sx == 1 && W % 32 == 0) {
-        aa_bwd_stream_nchw_kernel<CC, CG><<<dim3(b2a_blocks(HW / 32, 8), B), 256, 0, stream>>>(G.d_out, G.sb, G.sy, G.sc, ctx.cover, HW, W, d_color);
+    if (G.sx == 1 && P.W % 32 == 0) {
+        aa_bwd_tile_kernel<C, CC, CG, true><<<grid, 256, 0, stream>>>(P, G, ctx, d_color, d_pos);
         return true;
     }
     return false;
@@ -675,16 +799,16 @@ B2A_API int b2a_antialias_bwd(const float* color, const float* bg, int Bg, int c
     AAParams P{color, bg, rast, pos, tri, opp, Bg, composite, B, H, W, C, V, F};
     AAGrad G{d_out, d_sb, d_sy, d_sx, d_sc, Cg};
     AAContext ctx;
-    bool fast = d_color && aa_fast_ok(composite, aa_ctx, aa_ctx_bytes, B, H, W, C, &ctx);
+    bool fast = d_color && aa_fast_ok(composite, aa_ctx, aa_ctx_bytes, B, H, W, C, &ctx) && aligned16(d_color);
     if (fast) {
-        if (Cc == 3 && Cg == 4) fast = aa_bwd_stream<3, 4>(G, ctx, B, H, W, d_color, stream);
-        else if (Cc == 16 && Cg == 16) fast = aa_bwd_stream<16, 16>(G, ctx, B, H, W, d_color, stream);
-        else if (Cc == 1 && Cg == 1) fast = aa_bwd_stream<1, 1>(G, ctx, B, H, W, d_color, stream);
-        else if (Cc == 2 && Cg == 2) fast = aa_bwd_stream<2, 2>(G, ctx, B, H, W, d_color, stream);
+        if (C == 4 && Cg == 4) fast = aa_bwd_tile<4, 3, 4>(P, G, ctx, d_color, d_pos, stream);
+        else if (C == 4 && Cg == 3) fast = aa_bwd_tile<4, 3, 3>(P, G, ctx, d_color, d_pos, stream);
+        else if (C == 17 && Cg == 16) fast = aa_bwd_tile<17, 16, 16>(P, G, ctx, d_color, d_pos, stream);
+        else if (C == 2 && Cg == 1) fast = aa_bwd_tile<2, 1, 1>(P, G, ctx, d_color, d_pos, stream);
+        else if (C == 3 && Cg == 2) fast = aa_bwd_tile<3, 2, 2>(P, G, ctx, d_color, d_pos, stream);
         else fast = false;
     }
-    if (fast) aa_bwd_fix_kernel<<<148 * 2, 128, 0, stream>>>(P, G, ctx, d_color, d_pos);
-    else aa_bwd_kernel<<<dim3(b2a_blocks((int64_t)H * W * Cc, 256), B), 256, 0, stream>>>(P, G, d_color, d_pos);
+    if (!fast) aa_bwd_kernel<<<dim3(b2a_blocks((int64_t)H * W * Cc, 256), B), 256, 0, stream>>>(P, G, d_color, d_pos);
     B2A_LAUNCH_OK();
     return 0;
 }

@@ -144,93 +144,85 @@ __global__ void __launch_bounds__(256) gb_fwd_kernel(GbParams P, float* __restri
     if (gb_tex) st3(gb_tex + po, g.gtex);
 }
 
-__device__ __forceinline__ void atomic_add3(float* p, V3 a)
+// Vertex-gradient accumulator: one 48-byte row per (image, vertex), three 16-byte vector reductions per touched
+// vertex instead of twelve scalar ones (the backward is bound by the SMs' RED issue rate, not by bytes):
+//   A0 = (d_v_pos.xyz, d_clip.w)   A1 = (d_v_nrm.xyz, d_clip.x)   A2 = (d_prior.xyz, d_clip.y)
+__device__ __forceinline__ void red4(float* p, float x, float y, float z, float w)
 {
-    atomicAdd(p, a.x); atomicAdd(p + 1, a.y); atomicAdd(p + 2, a.z);
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(x, y, z, w));   // red.global.add.v4.f32 (sm_90+)
 }
 
-__global__ void __launch_bounds__(256) gb_bwd_kernel(GbParams P, const float* __restrict__ pos_clip, const float* __restrict__ d_gb_pos,
+// LIST: threads walk the compact covered-pixel list written by the rasterizer (dense warps; DMTet renders cover ~20 %
+// of the image); otherwise one thread per pixel of the [B,H,W] grid (spp > 1 or no list).
+template <bool LIST>
+__global__ void __launch_bounds__(128) gb_bwd_kernel(GbParams P, const float* __restrict__ pos_clip, const int* __restrict__ cov_list,
+                                                     const int* __restrict__ cov_count, const float* __restrict__ d_gb_pos,
                                                      const float* __restrict__ d_gb_geo, const float* __restrict__ d_gb_shn,
                                                      const float* __restrict__ d_gb_cam, const float* __restrict__ d_gb_tex,
-                                                     float* __restrict__ d_v_pos, float* __restrict__ d_v_nrm, float* __restrict__ d_prior,
-                                                     float* __restrict__ d_clip, float* __restrict__ d_w2c, float* __restrict__ d_campos)
+                                                     float* __restrict__ acc, float* __restrict__ d_w2c, float* __restrict__ d_campos)
 {
-    __shared__ float s_acc[12];
-    if (threadIdx.x < 12) s_acc[threadIdx.x] = 0.f;
-    __syncthreads();
-    int ip = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    bool active = ip < P.H * P.W;
-    int px = 0, py = 0, f = -1;
-    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-        px = ip % P.W; py = ip / P.W;
-        size_t ri = ((size_t)b * P.H * P.spp + (size_t)py * P.spp) * ((size_t)P.W * P.spp) + (size_t)px * P.spp;
-        r = ldg4(P.rast + ri * 4);
-        f = (int)r.w - 1;
-        active = f >= 0 && f < P.F;
-    }
-    V3 zero{0.f, 0.f, 0.f};
-    V3 d_cam = zero, d_out = zero, d_vv = zero;
-    GbPixel g;
-    if (active) {
-        size_t po = ((size_t)b * P.H * P.W + ip) * 3;
-        V3 g_pos = d_gb_pos ? ld3(d_gb_pos + po) : zero;
-        V3 g_geo = d_gb_geo ? ld3(d_gb_geo + po) : zero;
-        V3 g_shn = d_gb_shn ? ld3(d_gb_shn + po) : zero;
-        V3 g_cn = d_gb_cam ? ld3(d_gb_cam + po) : zero;
-        V3 g_tex = d_gb_tex ? ld3(d_gb_tex + po) : zero;
-        gb_forward(P, b, f, r.x, r.y, g);
-        // camera-space normal
-        d_cam = snormalize_bwd(g.cam, g.cn, g.lc, g_cn);
-        const float* m = P.w2c + (size_t)b * 16;
-        d_out = V3{g_shn.x + ((d_cam.x * __ldg(m + 0) + d_cam.y * __ldg(m + 4)) + d_cam.z * __ldg(m + 8)),
-                   g_shn.y + ((d_cam.x * __ldg(m + 1) + d_cam.y * __ldg(m + 5)) + d_cam.z * __ldg(m + 9)),
-                   g_shn.z + ((d_cam.x * __ldg(m + 2) + d_cam.y * __ldg(m + 6)) + d_cam.z * __ldg(m + 10))};
-        // bend (lerp) and clamp
-        V3 d_geof = d_out * (1.f - g.t), d_shf = d_out * g.t;
-        float d_t = dot3(d_out, g.shf - g.geof);
-        float d_dot = (g.tpre >= 0.f && g.tpre <= 1.f) ? d_t / 0.1f : 0.f;
-        V3 d_view = g.shf * d_dot;
-        d_shf = d_shf + g.view * d_dot;
-        // two-sided flip
-        V3 d_sh = g.front ? d_shf : neg(d_shf);
-        V3 d_ggeo = g_geo + (g.front ? d_geof : neg(d_geof));
-        // double normalisation of the smooth normal
-        V3 d_s1 = fnormalize_bwd(g.s1, g.sh, g.ls, 1e-12f, d_sh);
-        V3 d_gnrm = fnormalize_bwd(g.gnrm, g.s1, g.ln, 1e-12f, d_s1);
-        // view vector
-        d_vv = fnormalize_bwd(g.vv, g.view, g.lv, 1e-12f, d_view);
-        V3 d_gpos = g_pos - d_vv;
-        // face normal: ggeo = (u+v+w) fn ; fn = safe_normalize(e1 x e2)
-        V3 d_fn = d_ggeo * ((g.u + g.v) + g.w);
-        V3 d_n = snormalize_bwd(g.n, g.fn, g.nlen, d_fn);
-        V3 e1 = g.P1 - g.P0, e2 = g.P2 - g.P0;
-        V3 d_e1 = cross3(e2, d_n), d_e2 = cross3(d_n, e1);
-        // attribute scatter
-        if (d_v_pos) {
-            float* o = d_v_pos + (size_t)b * P.V * 3;
-            atomic_add3(o + (size_t)g.i0 * 3, d_gpos * g.u - (d_e1 + d_e2));
-            atomic_add3(o + (size_t)g.i1 * 3, d_gpos * g.v + d_e1);
-            atomic_add3(o + (size_t)g.i2 * 3, d_gpos * g.w + d_e2);
+    const int HW = P.H * P.W;
+    const int64_t total = LIST ? (int64_t)*cov_count : (int64_t)P.B * HW;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t span = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t it = first - (threadIdx.x & 31); it < total; it += span) {   // warp-uniform trip count
+        const int64_t idx = it + (threadIdx.x & 31);
+        bool active = idx < total;
+        int b = 0, ip = 0, px = 0, py = 0, f = -1;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) {
+            const int64_t flat = LIST ? (int64_t)__ldg(cov_list + idx) : idx;
+            b = (int)(flat / HW); ip = (int)(flat - (int64_t)b * HW);
+            px = ip % P.W; py = ip / P.W;
+            size_t ri = ((size_t)b * P.H * P.spp + (size_t)py * P.spp) * ((size_t)P.W * P.spp) + (size_t)px * P.spp;
+            r = ldg4(P.rast + ri * 4);
+            f = (int)r.w - 1;
+            active = f >= 0 && f < P.F;
         }
-        if (d_v_nrm) {
-            float* o = d_v_nrm + (size_t)b * P.V * 3;
-            atomic_add3(o + (size_t)g.i0 * 3, d_gnrm * g.u);
-            atomic_add3(o + (size_t)g.i1 * 3, d_gnrm * g.v);
-            atomic_add3(o + (size_t)g.i2 * 3, d_gnrm * g.w);
-        }
-        if (d_prior) {
-            float* o = d_prior + (size_t)(P.Bq == 1 ? 0 : b) * P.V * 3;
-            atomic_add3(o + (size_t)g.i0 * 3, g_tex * g.u);
-            atomic_add3(o + (size_t)g.i1 * 3, g_tex * g.v);
-            atomic_add3(o + (size_t)g.i2 * 3, g_tex * g.w);
-        }
-        // barycentric gradients -> clip-space positions (rasterize backward, oracle/raster_ref.c orc_rasterize_bwd)
-        if (d_clip) {
+        V3 zero{0.f, 0.f, 0.f};
+        V3 d_cam = zero, d_vv = zero;
+        GbPixel g;
+        g.out = zero;
+        if (active) {
+            size_t po = ((size_t)b * HW + ip) * 3;
+            V3 g_pos = d_gb_pos ? ld3(d_gb_pos + po) : zero;
+            V3 g_geo = d_gb_geo ? ld3(d_gb_geo + po) : zero;
+            V3 g_shn = d_gb_shn ? ld3(d_gb_shn + po) : zero;
+            V3 g_cn = d_gb_cam ? ld3(d_gb_cam + po) : zero;
+            V3 g_tex = d_gb_tex ? ld3(d_gb_tex + po) : zero;
+            gb_forward(P, b, f, r.x, r.y, g);
+            // camera-space normal
+            d_cam = snormalize_bwd(g.cam, g.cn, g.lc, g_cn);
+            const float* m = P.w2c + (size_t)b * 16;
+            V3 d_out = V3{g_shn.x + ((d_cam.x * __ldg(m + 0) + d_cam.y * __ldg(m + 4)) + d_cam.z * __ldg(m + 8)),
+                          g_shn.y + ((d_cam.x * __ldg(m + 1) + d_cam.y * __ldg(m + 5)) + d_cam.z * __ldg(m + 9)),
+                          g_shn.z + ((d_cam.x * __ldg(m + 2) + d_cam.y * __ldg(m + 6)) + d_cam.z * __ldg(m + 10))};
+            // bend (lerp) and clamp
+            V3 d_geof = d_out * (1.f - g.t), d_shf = d_out * g.t;
+            float d_t = dot3(d_out, g.shf - g.geof);
+            float d_dot = (g.tpre >= 0.f && g.tpre <= 1.f) ? d_t / 0.1f : 0.f;
+            V3 d_view = g.shf * d_dot;
+            d_shf = d_shf + g.view * d_dot;
+            // two-sided flip
+            V3 d_sh = g.front ? d_shf : neg(d_shf);
+            V3 d_ggeo = g_geo + (g.front ? d_geof : neg(d_geof));
+            // double normalisation of the smooth normal
+            V3 d_s1 = fnormalize_bwd(g.s1, g.sh, g.ls, 1e-12f, d_sh);
+            V3 d_gnrm = fnormalize_bwd(g.gnrm, g.s1, g.ln, 1e-12f, d_s1);
+            // view vector
+            d_vv = fnormalize_bwd(g.vv, g.view, g.lv, 1e-12f, d_view);
+            V3 d_gpos = g_pos - d_vv;
+            // face normal: ggeo = (u+v+w) fn ; fn = safe_normalize(e1 x e2)
+            V3 d_fn = d_ggeo * ((g.u + g.v) + g.w);
+            V3 d_n = snormalize_bwd(g.n, g.fn, g.nlen, d_fn);
+            V3 e1 = g.P1 - g.P0, e2 = g.P2 - g.P0;
+            V3 d_e1 = cross3(e2, d_n), d_e2 = cross3(d_n, e1);
+            V3 dp0 = d_gpos * g.u - (d_e1 + d_e2), dp1 = d_gpos * g.v + d_e1, dp2 = d_gpos * g.w + d_e2;
+            // barycentric gradients -> clip-space positions (rasterize backward, oracle/raster_ref.c orc_rasterize_bwd)
+            float c0x = 0.f, c0y = 0.f, c0w = 0.f, c1x = 0.f, c1y = 0.f, c1w = 0.f, c2x = 0.f, c2y = 0.f, c2w = 0.f;
             float du = (dot3(d_gpos, g.P0 - g.P2) + dot3(d_gnrm, g.N0 - g.N2)) + dot3(g_tex, g.Q0 - g.Q2);
             float dv = (dot3(d_gpos, g.P1 - g.P2) + dot3(d_gnrm, g.N1 - g.N2)) + dot3(g_tex, g.Q1 - g.Q2);
-            if (du != 0.f || dv != 0.f) {
+            if (pos_clip && (du != 0.f || dv != 0.f)) {
                 const float* pb = pos_clip + (size_t)b * P.V * 4;
                 float4 p0 = ldg4(pb + (size_t)g.i0 * 4), p1 = ldg4(pb + (size_t)g.i1 * 4), p2 = ldg4(pb + (size_t)g.i2 * 4);
                 float fx, fy;
@@ -243,35 +235,65 @@ __global__ void __launch_bounds__(256) gb_bwd_kernel(GbParams P, const float* __
                 float uu = a0 * iw, vv = a1 * iw;
                 float gs = uu * du + vv * dv;
                 float ga0 = (du - gs) * iw, ga1 = (dv - gs) * iw, ga2 = -gs * iw;
-                float gq0x = ga2 * q1y - ga1 * q2y, gq0y = ga1 * q2x - ga2 * q1x;
-                float gq1x = ga0 * q2y - ga2 * q0y, gq1y = ga2 * q0x - ga0 * q2x;
-                float gq2x = ga1 * q0y - ga0 * q1y, gq2y = ga0 * q1x - ga1 * q0x;
-                float* gb = d_clip + (size_t)b * P.V * 4;
-                atomicAdd(gb + (size_t)g.i0 * 4, gq0x); atomicAdd(gb + (size_t)g.i0 * 4 + 1, gq0y); atomicAdd(gb + (size_t)g.i0 * 4 + 3, -(fx * gq0x + fy * gq0y));
-                atomicAdd(gb + (size_t)g.i1 * 4, gq1x); atomicAdd(gb + (size_t)g.i1 * 4 + 1, gq1y); atomicAdd(gb + (size_t)g.i1 * 4 + 3, -(fx * gq1x + fy * gq1y));
-                atomicAdd(gb + (size_t)g.i2 * 4, gq2x); atomicAdd(gb + (size_t)g.i2 * 4 + 1, gq2y); atomicAdd(gb + (size_t)g.i2 * 4 + 3, -(fx * gq2x + fy * gq2y));
+                c0x = ga2 * q1y - ga1 * q2y; c0y = ga1 * q2x - ga2 * q1x;
+                c1x = ga0 * q2y - ga2 * q0y; c1y = ga2 * q0x - ga0 * q2x;
+                c2x = ga1 * q0y - ga0 * q1y; c2y = ga0 * q1x - ga1 * q0x;
+                c0w = -(fx * c0x + fy * c0y); c1w = -(fx * c1x + fy * c1y); c2w = -(fx * c2x + fy * c2y);
             }
+            float* a = acc + (size_t)b * P.V * 12;
+            float* a0p = a + (size_t)g.i0 * 12;
+            float* a1p = a + (size_t)g.i1 * 12;
+            float* a2p = a + (size_t)g.i2 * 12;
+            red4(a0p, dp0.x, dp0.y, dp0.z, c0w); red4(a0p + 4, d_gnrm.x * g.u, d_gnrm.y * g.u, d_gnrm.z * g.u, c0x); red4(a0p + 8, g_tex.x * g.u, g_tex.y * g.u, g_tex.z * g.u, c0y);
+            red4(a1p, dp1.x, dp1.y, dp1.z, c1w); red4(a1p + 4, d_gnrm.x * g.v, d_gnrm.y * g.v, d_gnrm.z * g.v, c1x); red4(a1p + 8, g_tex.x * g.v, g_tex.y * g.v, g_tex.z * g.v, c1y);
+            red4(a2p, dp2.x, dp2.y, dp2.z, c2w); red4(a2p + 4, d_gnrm.x * g.w, d_gnrm.y * g.w, d_gnrm.z * g.w, c2x); red4(a2p + 8, g_tex.x * g.w, g_tex.y * g.w, g_tex.z * g.w, c2y);
         }
-    } else {
-        g.out = zero;
-    }
-    // camera gradients: d_w2c[i][j] += d_cam[i] out[j] ; d_campos += d_vv  (block-reduced, one atomic set per block)
-    if (d_w2c || d_campos) {
-        if (__ballot_sync(0xffffffffu, active)) {
-            float vals[12] = {d_cam.x * g.out.x, d_cam.x * g.out.y, d_cam.x * g.out.z, d_cam.y * g.out.x, d_cam.y * g.out.y, d_cam.y * g.out.z,
-                              d_cam.z * g.out.x, d_cam.z * g.out.y, d_cam.z * g.out.z, d_vv.x, d_vv.y, d_vv.z};
+        // camera gradients: d_w2c[i][j] += d_cam[i] out[j] ; d_campos += d_vv  (warp-reduced when the warp is in one image)
+        if (d_w2c || d_campos) {
+            const unsigned am = __ballot_sync(0xffffffffu, active);
+            if (am) {
+                const int b0 = __shfl_sync(0xffffffffu, b, __ffs(am) - 1);
+                const bool uniform = __all_sync(0xffffffffu, !active || b == b0);
+                float vals[12] = {d_cam.x * g.out.x, d_cam.x * g.out.y, d_cam.x * g.out.z, d_cam.y * g.out.x, d_cam.y * g.out.y, d_cam.y * g.out.z,
+                                  d_cam.z * g.out.x, d_cam.z * g.out.y, d_cam.z * g.out.z, d_vv.x, d_vv.y, d_vv.z};
 #pragma unroll
-            for (int i = 0; i < 12; i++) {
-                float s = warp_sum(active ? vals[i] : 0.f);
-                if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(&s_acc[i], s);
+                for (int i = 0; i < 12; i++) {
+                    float* dst = i < 9 ? (d_w2c ? d_w2c + (i / 3) * 4 + i % 3 : nullptr) : (d_campos ? d_campos + (i - 9) : nullptr);
+                    const int stride = i < 9 ? 16 : 3;
+                    if (!dst) continue;
+                    if (uniform) {
+                        float s = warp_sum(active ? vals[i] : 0.f);
+                        if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(dst + (size_t)b0 * stride, s);
+                    } else if (active && vals[i] != 0.f) {
+                        atomicAdd(dst + (size_t)b * stride, vals[i]);
+                    }
+                }
             }
         }
-        __syncthreads();
-        if (threadIdx.x < 9 && d_w2c && s_acc[threadIdx.x] != 0.f)
-            atomicAdd(d_w2c + (size_t)b * 16 + (threadIdx.x / 3) * 4 + threadIdx.x % 3, s_acc[threadIdx.x]);
-        if (threadIdx.x >= 9 && threadIdx.x < 12 && d_campos && s_acc[threadIdx.x] != 0.f)
-            atomicAdd(d_campos + (size_t)b * 3 + (threadIdx.x - 9), s_acc[threadIdx.x]);
     }
+}
+
+// accumulator rows -> gradient tensors (each nullable); d_prior sums over the batch in a fixed order when Bq == 1
+__global__ void __launch_bounds__(256) gb_bwd_finalize_kernel(const float* __restrict__ acc, int B, int Bq, int64_t V, float* __restrict__ d_v_pos,
+                                                              float* __restrict__ d_v_nrm, float* __restrict__ d_prior, float* __restrict__ d_clip)
+{
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+#pragma unroll 4
+    for (int b = 0; b < B; b++) {
+        const float4* a = reinterpret_cast<const float4*>(acc + ((size_t)b * V + v) * 12);
+        float4 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
+        size_t o = ((size_t)b * V + v) * 3;
+        if (d_v_pos) { d_v_pos[o] = a0.x; d_v_pos[o + 1] = a0.y; d_v_pos[o + 2] = a0.z; }
+        if (d_v_nrm) { d_v_nrm[o] = a1.x; d_v_nrm[o + 1] = a1.y; d_v_nrm[o + 2] = a1.z; }
+        if (d_clip) reinterpret_cast<float4*>(d_clip)[(size_t)b * V + v] = make_float4(a1.w, a2.w, 0.f, a0.w);
+        if (d_prior) {
+            if (Bq == 1) { qx += a2.x; qy += a2.y; qz += a2.z; }
+            else { d_prior[o] = a2.x; d_prior[o + 1] = a2.y; d_prior[o + 2] = a2.z; }
+        }
+    }
+    if (d_prior && Bq == 1) { d_prior[v * 3] = qx; d_prior[v * 3 + 1] = qy; d_prior[v * 3 + 2] = qz; }
 }
 
 int gb_check(const float* rast, int spp, const int32_t* tri, const float* v_pos, const float* v_nrm, const float* prior_pos, int Bq,
@@ -300,20 +322,40 @@ B2A_API int b2a_gbuffer_fwd(const float* rast, int spp, const int32_t* tri, cons
     return 0;
 }
 
+B2A_API int b2a_gbuffer_bwd_workspace_bytes(int B, int64_t V, size_t* bytes)
+{
+    B2A_CHECK_ARG(bytes && B > 0 && V >= 0, "shape");
+    *bytes = b2a_align((size_t)B * V * 12 * sizeof(float));
+    return 0;
+}
+
 B2A_API int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, const int32_t* tri, const float* v_pos,
                             const float* v_nrm, const float* prior_pos, int Bq, const float* w2c, const float* campos, int two_sided,
-                            int B, int64_t V, int64_t F, int H, int W, const float* d_gb_pos, const float* d_gb_geo_nrm,
-                            const float* d_gb_shading_nrm, const float* d_gb_cam_nrm, const float* d_gb_tex_pos, float* d_v_pos,
-                            float* d_v_nrm, float* d_prior_pos, float* d_clip, float* d_w2c, float* d_campos, b2a_stream_t stream_)
+                            int B, int64_t V, int64_t F, int H, int W, const int32_t* cov_list, const int32_t* cov_count,
+                            const float* d_gb_pos, const float* d_gb_geo_nrm, const float* d_gb_shading_nrm, const float* d_gb_cam_nrm,
+                            const float* d_gb_tex_pos, void* workspace, size_t workspace_bytes, float* d_v_pos, float* d_v_nrm,
+                            float* d_prior_pos, float* d_clip, float* d_w2c, float* d_campos, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = gb_check(rast, spp, tri, v_pos, v_nrm, prior_pos, Bq, w2c, campos, B, V, F, H, W);
     if (rc) return rc;
-    B2A_CHECK_ARG(!d_clip || (pos_clip && ((uintptr_t)pos_clip & 15) == 0), "pos_clip");
+    B2A_CHECK_ARG(!d_clip || (pos_clip && ((uintptr_t)pos_clip & 15) == 0 && ((uintptr_t)d_clip & 15) == 0), "pos_clip / d_clip");
+    B2A_CHECK_ARG(workspace && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= (size_t)B * V * 12 * sizeof(float), "workspace");
+    B2A_CHECK_ARG((cov_list == nullptr) == (cov_count == nullptr) && (!cov_list || spp == 1), "covered-pixel list");
+    float* acc = (float*)workspace;
+    B2A_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)B * V * 12 * sizeof(float), stream));
     GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F};
-    gb_bwd_kernel<<<dim3(b2a_blocks((int64_t)H * W, 256), B), 256, 0, stream>>>(P, pos_clip, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm,
-                                                                               d_gb_cam_nrm, d_gb_tex_pos, d_v_pos, d_v_nrm, d_prior_pos,
-                                                                               d_clip, d_w2c, d_campos);
+    const float* pc = d_clip ? pos_clip : nullptr;
+    if (cov_list) {
+        gb_bwd_kernel<true><<<148 * 8, 128, 0, stream>>>(P, pc, cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
+                                                         d_gb_tex_pos, acc, d_w2c, d_campos);
+    } else {
+        unsigned blocks = b2a_blocks((int64_t)B * H * W, 128);
+        gb_bwd_kernel<false><<<blocks, 128, 0, stream>>>(P, pc, nullptr, nullptr, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
+                                                         d_gb_tex_pos, acc, d_w2c, d_campos);
+    }
+    if (d_v_pos || d_v_nrm || d_prior_pos || d_clip)
+        gb_bwd_finalize_kernel<<<b2a_blocks(V, 256), 256, 0, stream>>>(acc, B, Bq, V, d_v_pos, d_v_nrm, d_prior_pos, d_clip);
     B2A_LAUNCH_OK();
     return 0;
 }

@@ -176,28 +176,44 @@ __global__ void __launch_bounds__(256) raster_large_kernel(const float* __restri
     }
 }
 
+// keys -> (u, v, z/w, id+1); optionally appends the covered pixels (flat index b*H*W + p) to a compact list that lets
+// the g-buffer backward run dense warps (warp-aggregated append: one atomic per warp)
 __global__ void __launch_bounds__(256) raster_resolve_kernel(const unsigned long long* __restrict__ zbuf, const float* __restrict__ pos,
-                                                             const int* __restrict__ tri, int64_t V, int H, int W, float* __restrict__ rast)
+                                                             const int* __restrict__ tri, int64_t V, int H, int W, float* __restrict__ rast,
+                                                             int* __restrict__ cov_list, int* __restrict__ cov_count)
 {
     int ip = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
-    if (ip >= H * W) return;
-    int px = ip % W, py = ip / W;
+    const bool in = ip < H * W;
+    bool covered = false;
     size_t pi = (size_t)b * H * W + ip;
-    unsigned long long key = zbuf[pi];
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (key != 0xffffffffffffffffull) {
-        int f = (int)(unsigned)key;
-        const float* pb = pos + (size_t)b * V * 4;
-        float4 p0 = ldg4(pb + (size_t)__ldg(tri + (size_t)f * 3) * 4);
-        float4 p1 = ldg4(pb + (size_t)__ldg(tri + (size_t)f * 3 + 1) * 4);
-        float4 p2 = ldg4(pb + (size_t)__ldg(tri + (size_t)f * 3 + 2) * 4);
-        float fx, fy;
-        pixel_ndc(px, py, H, W, fx, fy);
-        TriEval e;
-        if (tri_eval(p0, p1, p2, fx, fy, e)) o = make_float4(e.u, e.v, e.zw, (float)(f + 1));
+    if (in) {
+        int px = ip % W, py = ip / W;
+        unsigned long long key = zbuf[pi];
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (key != 0xffffffffffffffffull) {
+            int f = (int)(unsigned)key;
+            const float* pb = pos + (size_t)b * V * 4;
+            float4 p0 = ldg4(pb + (size_t)__ldg(tri + (size_t)f * 3) * 4);
+            float4 p1 = ldg4(pb + (size_t)__ldg(tri + (size_t)f * 3 + 1) * 4);
+            float4 p2 = ldg4(pb + (size_t)__ldg(tri + (size_t)f * 3 + 2) * 4);
+            float fx, fy;
+            pixel_ndc(px, py, H, W, fx, fy);
+            TriEval e;
+            if (tri_eval(p0, p1, p2, fx, fy, e)) { o = make_float4(e.u, e.v, e.zw, (float)(f + 1)); covered = true; }
+        }
+        reinterpret_cast<float4*>(rast)[pi] = o;
     }
-    reinterpret_cast<float4*>(rast)[pi] = o;
+    if (cov_list) {
+        const unsigned m = __ballot_sync(0xffffffffu, covered);
+        if (m) {
+            const int lane = threadIdx.x & 31;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cov_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (covered) cov_list[base + __popc(m & ((1u << lane) - 1u))] = (int)pi;
+        }
+    }
 }
 
 // d(u,v) -> d(x,y,w) of the three vertices
@@ -287,14 +303,16 @@ B2A_API int b2a_rasterize_workspace_bytes(int B, int64_t F, int H, int W, size_t
 }
 
 B2A_API int b2a_rasterize_fwd(const float* pos, const int32_t* tri, int B, int64_t V, int64_t F, int H, int W, void* workspace,
-                              size_t workspace_bytes, float* rast, b2a_stream_t stream_)
+                              size_t workspace_bytes, float* rast, int32_t* cov_list, int32_t* cov_count, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2A_CHECK_ARG(rast, "null pointer");
+    B2A_CHECK_ARG((cov_list == nullptr) == (cov_count == nullptr) && (!cov_list || (int64_t)B * H * W < (1ll << 31)), "covered-pixel list");
     RasterWorkspace ws;
     int rc = raster_zbuffer_impl(pos, tri, B, V, F, H, W, workspace, workspace_bytes, &ws, stream);
     if (rc) return rc;
-    raster_resolve_kernel<<<dim3(b2a_blocks((int64_t)H * W, 256), B), 256, 0, stream>>>(ws.zbuf, pos, tri, V, H, W, rast);
+    if (cov_count) B2A_CUDA_OK(cudaMemsetAsync(cov_count, 0, sizeof(int), stream));
+    raster_resolve_kernel<<<dim3(b2a_blocks((int64_t)H * W, 256), B), 256, 0, stream>>>(ws.zbuf, pos, tri, V, H, W, rast, cov_list, cov_count);
     B2A_LAUNCH_OK();
     return 0;
 }

@@ -50,6 +50,63 @@ def _take_vertex(seq_shape, idx):
     return seq_shape.gather(2, idx[..., None, None].expand(-1, -1, 1, 3)).squeeze(2)
 
 
+def _body_chain(n_body_bones):
+    """Body part of the kinematic chain and bone->joint table (reference skinning.py:111-131)."""
+    half = n_body_bones // 2
+    bones_to_joints, kinematic_chain, dependents, bone_idx = [], [], [], 0
+    for i in range(half):
+        bones_to_joints.append((i + 1, i))
+        kinematic_chain = [(bone_idx, dependents)] + kinematic_chain
+        dependents = dependents + [bone_idx]
+        bone_idx += 1
+    dependents = []
+    for i in range(n_body_bones - 1, half - 1, -1):
+        bones_to_joints.append((i, i + 1))
+        kinematic_chain = [(bone_idx, dependents)] + kinematic_chain
+        dependents = dependents + [bone_idx]
+        bone_idx += 1
+    return bones_to_joints, kinematic_chain
+
+
+_MODES = {"z_minmax": 0, "z_minmax_y+": 1}
+
+
+def _estimate_bones_fused(seq_shape, n_body_bones, n_leg_bones, body_bones_mode, compute_kinematic_chain, aux, attach_legs_to_body,
+                          legs_to_body_joint_indices):
+    """The sm_100a path (csrc/estimate_bones.cu): steady state = 1 memset + 4 launches, no host sync.  Building the
+    Python kinematic-chain lists (once per epoch in MagicPony, InstancePredictorBase.py:319-335) needs the leg attachment
+    indices on the host: one 16-byte read."""
+    mode = _MODES[body_bones_mode]
+    if not compute_kinematic_chain:
+        attach = [leg["body_bone_idx"] for leg in aux["legs"]] if n_leg_bones > 0 else (-1, -1, -1, -1)
+        return ops.estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, attach)
+    aux = {}
+    bones_to_joints, kinematic_chain = _body_chain(n_body_bones)
+    aux["bones_to_joints"] = bones_to_joints
+    if n_leg_bones > 0:
+        cfg = legs_to_body_joint_indices if legs_to_body_joint_indices is not None else [None, None, None, None]
+        first = [-1 if cfg[i] is None else int(cfg[i]) for i in range(2)]
+        if -1 in first:
+            _, att = ops.estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, first + [-1, -1], want_attach=True)
+            first = att[:2].tolist()
+        # legs 2 and 3 reuse the joints chosen for legs 1 and 0 (skinning.py:214-217)
+        attach = [first[0], first[1], first[1], first[0]]
+        for i in range(4):
+            cfg[i] = attach[i]
+        start_bone_idx, leg_auxs = n_body_bones, []
+        for i in range(4):
+            leg_b2j, leg_chain, leg_ids = build_kinematic_chain(n_leg_bones, start_bone_idx)
+            kinematic_chain = update_body_kinematic_chain(kinematic_chain, leg_chain, attach[i], leg_ids, attach_legs_to_body)
+            leg_auxs.append({"body_bone_idx": attach[i], "leg_bones_to_joints": leg_b2j})
+            start_bone_idx += n_leg_bones
+        aux["legs"] = leg_auxs
+    else:
+        attach = (-1, -1, -1, -1)
+    aux["kinematic_chain"] = kinematic_chain
+    bones = ops.estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, attach)
+    return bones, kinematic_chain, aux
+
+
 @torch.no_grad()
 def estimate_bones(seq_shape, n_body_bones, resample=False, n_legs=4, n_leg_bones=0, body_bones_mode="z_minmax",
                    compute_kinematic_chain=True, aux=None, attach_legs_to_body=True, legs_to_body_joint_indices=None,
@@ -57,6 +114,21 @@ def estimate_bones(seq_shape, n_body_bones, resample=False, n_legs=4, n_leg_bone
     """seq_shape [B,F,V,3] -> bones [B,F,K,2,3] (+ kinematic_chain, aux when compute_kinematic_chain)."""
     if resample:
         raise NotImplementedError("resample=True is never set by any caller of the reference (SURVEY.md §2 #5)")
+    assert n_body_bones % 2 == 0
+    if n_leg_bones > 0:
+        assert n_legs == 4
+    if bone_y_threshold is None and body_bones_mode in _MODES and seq_shape.is_cuda:
+        return _estimate_bones_fused(seq_shape, n_body_bones, n_leg_bones, body_bones_mode, compute_kinematic_chain, aux,
+                                     attach_legs_to_body, legs_to_body_joint_indices)
+    return _estimate_bones_torch(seq_shape, n_body_bones, n_leg_bones, body_bones_mode, compute_kinematic_chain, aux, attach_legs_to_body,
+                                 legs_to_body_joint_indices, bone_y_threshold)
+
+
+def _estimate_bones_torch(seq_shape, n_body_bones, n_leg_bones, body_bones_mode, compute_kinematic_chain, aux, attach_legs_to_body,
+                          legs_to_body_joint_indices, bone_y_threshold):
+    """Device-side torch formulation, used for Fauna's bone_y_threshold variant (InstancePredictorFauna.py:20,90: seven
+    masked quantiles) which the fused kernel does not cover yet."""
+    n_legs = 4
     zs_all = seq_shape[..., 2]
     if body_bones_mode == "z_minmax":
         point_a = _take_vertex(seq_shape, zs_all.argmax(dim=2))

@@ -15,7 +15,14 @@ def _L():
     return _lib.lib()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """Raw cudaStream_t of torch's current stream on the current device (kernels are launched where the reference's
+    plugin launches: torch_bindings.cpp:170).  The private fast accessor avoids ~20 us of Stream-object churn per call."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -45,10 +52,10 @@ def _workspace(nbytes, device):
 
 # kernels launched by each C-ABI entry point (memsets / memcpys are not kernels) - the source of bench.py's gpu_launches
 KERNELS_PER_CALL = {
-    "b2a_mt_count": 4, "b2a_mt_emit": 2, "b2a_mt_bwd": 1, "b2a_lbs_bone_transforms": 2, "b2a_lbs_fwd": 1, "b2a_lbs_bwd": 1,
+    "b2a_mt_count": 4, "b2a_mt_emit": 2, "b2a_mt_bwd": 1, "b2a_estimate_bones": 4, "b2a_lbs_bone_transforms": 2, "b2a_lbs_fwd": 1, "b2a_lbs_bwd": 1,
     "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1,
     "b2a_xfm_points_bwd": 1, "b2a_rasterize_fwd": 3, "b2a_rasterize_bwd": 1, "b2a_interpolate_fwd": 1, "b2a_interpolate_bwd": 1,
-    "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 1, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 1, "b2a_gbuffer_fwd": 1, "b2a_gbuffer_bwd": 1,
+    "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 1, "b2a_gbuffer_fwd": 1, "b2a_gbuffer_bwd": 2,
 }
 
 
@@ -269,6 +276,28 @@ def lbs(v_pos, bones, angles, chain_ptr, chain_ids, temperature=1.0, want_weight
     return out, posed, (w if want_weights else None)
 
 
+_eb_ws = {}
+
+
+def estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, attach=(-1, -1, -1, -1), want_attach=False):
+    """seq_shape [B,F,V,3] -> bones [B,F,K,2,3] in one memset + 4 launches, no host sync (reference skinning.py:49-248).
+    attach: body-bone index per leg, -1 = auto.  want_attach: also return the device int32[4] with instance 0's choice."""
+    L = _L()
+    x = _f32(seq_shape, "seq_shape")
+    B, Fr, V = x.shape[0], x.shape[1], x.shape[2]
+    K = n_body_bones + (4 * n_leg_bones if n_leg_bones > 0 else 0)
+    dev = x.device
+    ws = _eb_ws.get(dev)
+    if ws is None:
+        ws = _eb_ws[dev] = _workspace(_size(L.b2a_estimate_bones_workspace_bytes), dev)
+    bones = torch.empty(B, Fr, K, 2, 3, device=dev)
+    att = torch.empty(4, dtype=_i32, device=dev) if want_attach else None
+    _call("b2a_estimate_bones", (_p(x), B * Fr, V, int(n_body_bones), int(n_leg_bones), int(mode), int(attach[0]), int(attach[1]),
+                                     int(attach[2]), int(attach[3]), _p(ws), ws.numel(), _p(bones), _p(att), None, _stream()),
+          launches=4 if n_leg_bones > 0 else 1)
+    return (bones, att) if want_attach else bones
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Vertex normals (reference model/render/mesh.py:276-304)
 # ---------------------------------------------------------------------------------------------------------------
@@ -335,33 +364,40 @@ def xfm_points(points, matrix):
 # ---------------------------------------------------------------------------------------------------------------
 class _Rasterize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pos, tri, H, W):
+    def forward(ctx, pos, tri, H, W, want_cov):
         L = _L()
         pos = _f32(pos, "pos")
         B, V = pos.shape[0], pos.shape[1]
         F = tri.shape[0]
         ws = _workspace(_size(L.b2a_rasterize_workspace_bytes, B, F, H, W), pos.device)
         rast = torch.empty(B, H, W, 4, device=pos.device)
-        _call("b2a_rasterize_fwd", (_p(pos), _p(tri), B, V, F, H, W, _p(ws), ws.numel(), _p(rast), _stream()))
+        cov_list = torch.empty(B * H * W if want_cov else 0, dtype=_i32, device=pos.device)
+        cov_count = torch.empty(1 if want_cov else 0, dtype=_i32, device=pos.device)
+        _call("b2a_rasterize_fwd", (_p(pos), _p(tri), B, V, F, H, W, _p(ws), ws.numel(), _p(rast), _p(cov_list) if want_cov else None,
+                                        _p(cov_count) if want_cov else None, _stream()))
         ctx.save_for_backward(pos, tri, rast)
-        return rast
+        ctx.mark_non_differentiable(cov_list, cov_count)
+        return rast, cov_list, cov_count
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, *_):
         pos, tri, rast = ctx.saved_tensors
         B, V = pos.shape[0], pos.shape[1]
         H, W = rast.shape[1], rast.shape[2]
         g = _f32(g, "d_rast")
         d_pos = torch.zeros_like(pos)
         _call("b2a_rasterize_bwd", (_p(pos), _p(tri), _p(rast), _p(g), B, V, tri.shape[0], H, W, _p(d_pos), _stream()))
-        return d_pos, None, None, None
+        return d_pos, None, None, None, None
 
 
-def rasterize(pos, tri, resolution):
-    """pos [B,V,4] clip space, tri [F,3], resolution (H,W) -> rast [B,H,W,4] = (u, v, z/w, triangle_id+1)."""
+def rasterize(pos, tri, resolution, with_coverage=False):
+    """pos [B,V,4] clip space, tri [F,3], resolution (H,W) -> rast [B,H,W,4] = (u, v, z/w, triangle_id+1).
+    with_coverage: also return (cov_list int32 [B*H*W], cov_count int32 [1]) - the compact list of covered pixels that
+    lets ops.gbuffer's backward run dense warps."""
     if pos.dim() != 3 or pos.shape[-1] != 4:
         raise _lib.B2AError("rasterize: pos must be [B,V,4] (instanced mode)")
-    return _Rasterize.apply(pos, _idx32(tri, "tri"), int(resolution[0]), int(resolution[1]))
+    rast, cl, cc = _Rasterize.apply(pos, _idx32(tri, "tri"), int(resolution[0]), int(resolution[1]), bool(with_coverage))
+    return (rast, (cl, cc)) if with_coverage else rast
 
 
 class _Interpolate(torch.autograd.Function):
@@ -427,7 +463,7 @@ class _Antialias(torch.autograd.Function):
         out = torch.empty(B, H, W, Cc, device=color.device)
         _call("b2a_antialias_fwd", (_p(color), _p(bg), Bg, int(composite), _p(rast), _p(pos), _p(tri), _p(opp), B, pos.shape[1],
                                           tri.shape[0], H, W, Cc, _p(out), _p(aa_ctx), 0 if aa_ctx is None else aa_ctx.numel(), _stream()),
-              tag="C%d" % Cc, launches=1 if aa_ctx is None else 2)
+              tag="C%d" % Cc)
         ctx.save_for_backward(color, bg, rast, pos, tri, opp, aa_ctx)
         ctx.cfg = (bool(composite), Bg, Cc, int(keep))
         if keep < Cc:
@@ -446,21 +482,23 @@ class _Antialias(torch.autograd.Function):
         sb, sy, sx, sc = g.stride()
         _call("b2a_antialias_bwd", (_p(color), _p(bg), Bg, int(composite), _p(rast), _p(pos), _p(tri), _p(opp), _p(g), sb, sy, sx,
                                           sc, keep, B, pos.shape[1], tri.shape[0], H, W, Cc, _p(d_color), _p(d_pos), _p(aa_ctx),
-                                          0 if aa_ctx is None else aa_ctx.numel(), _stream()), tag="C%d" % Cc,
-              launches=1 if aa_ctx is None else 2)
+                                          0 if aa_ctx is None else aa_ctx.numel(), _stream()), tag="C%d" % Cc)
         return d_color, None, None, d_pos, None, None, None, None, None
 
 
-def antialias_prepare(rast):
-    """One pass over rast [B,H,W,4] -> opaque per-render context (coverage bitmask + silhouette pixel list) shared by all
-    composite_antialias launches of that render.  Returns None when the shape does not qualify (H*W % 32 != 0)."""
+def antialias_prepare(rast, pos, tri, opp):
+    """One pass over rast [B,H,W,4] + one pair-analysis launch -> opaque per-render context (coverage / silhouette
+    bitmasks, silhouette pixel list, per-pair blend records) shared by all composite_antialias launches of that render.
+    Returns None when the shape does not qualify (H*W % 32 != 0)."""
     L = _L()
-    rast = _f32(rast, "rast")
+    rast = _f32(rast, "rast"); pos = _f32(pos, "pos")
+    tri = _idx32(tri, "tri"); opp = _idx32(opp, "opp")
     B, H, W = rast.shape[0], rast.shape[1], rast.shape[2]
-    if (H * W) % 32 != 0:
+    if (H * W) % 32 != 0 or tri.shape[0] >= (1 << 28):
         return None
     ws = _workspace(_size(L.b2a_antialias_workspace_bytes, B, H, W), rast.device)
-    _call("b2a_antialias_prepare", (_p(rast), B, H, W, _p(ws), ws.numel(), _stream()))
+    _call("b2a_antialias_prepare", (_p(rast), _p(pos), _p(tri), _p(opp), B, pos.shape[1], tri.shape[0], H, W, _p(ws), ws.numel(),
+                                        _stream()))
     return ws
 
 
@@ -496,7 +534,7 @@ GB_KEYS = ("pos", "geo_nrm", "shading_nrm", "cam_nrm", "tex_pos")
 
 class _GBuffer(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, two_sided, want):
+    def forward(ctx, rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, two_sided, want, cov_list, cov_count):
         rast = _f32(rast, "rast"); pos_clip = _f32(pos_clip, "pos_clip"); v_pos = _f32(v_pos, "v_pos"); v_nrm = _f32(v_nrm, "v_nrm")
         prior_pos = _f32(prior_pos, "prior_pos"); w2c = _f32(w2c, "w2c"); campos = _f32(campos, "campos")
         B, V = v_pos.shape[0], v_pos.shape[1]
@@ -506,33 +544,43 @@ class _GBuffer(torch.autograd.Function):
         outs = [torch.empty(B, H, W, 3, device=rast.device) if k in want else None for k in GB_KEYS]
         _call("b2a_gbuffer_fwd", (_p(rast), spp, _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0], _p(w2c),
                                         _p(campos), int(two_sided), B, V, tri.shape[0], H, W, *[_p(o) for o in outs], _stream()))
-        ctx.save_for_backward(rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos)
+        ctx.save_for_backward(rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, cov_list, cov_count)
         ctx.cfg = (spp, int(two_sided), H, W, tuple(o is not None for o in outs))
         return tuple(o if o is not None else torch.empty(0, device=rast.device) for o in outs)
 
     @staticmethod
     def backward(ctx, *grads):
-        rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos = ctx.saved_tensors
+        L = _L()
+        rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, cov_list, cov_count = ctx.saved_tensors
         spp, two_sided, H, W, present = ctx.cfg
         B, V = v_pos.shape[0], v_pos.shape[1]
         gs = [(_f32(g, "d_gb") if (g is not None and p) else None) for g, p in zip(grads, present)]
         need = ctx.needs_input_grad
-        d_clip = torch.zeros_like(pos_clip) if need[1] else None
-        d_v_pos = torch.zeros_like(v_pos) if need[3] else None
-        d_v_nrm = torch.zeros_like(v_nrm) if need[4] else None
-        d_prior = torch.zeros_like(prior_pos) if need[5] else None
+        # vertex gradients are WRITTEN by the kernel (from its [B,V,12] accumulator): no zero fills
+        d_clip = torch.empty_like(pos_clip) if need[1] else None
+        d_v_pos = torch.empty_like(v_pos) if need[3] else None
+        d_v_nrm = torch.empty_like(v_nrm) if need[4] else None
+        d_prior = torch.empty_like(prior_pos) if need[5] else None
         d_w2c = torch.zeros_like(w2c) if need[6] else None
         d_campos = torch.zeros_like(campos) if need[7] else None
         if any(g is not None for g in gs):
+            ws = _workspace(_size(L.b2a_gbuffer_bwd_workspace_bytes, B, V), rast.device)
             _call("b2a_gbuffer_bwd", (_p(rast), spp, _p(pos_clip), _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0],
-                                            _p(w2c), _p(campos), two_sided, B, V, tri.shape[0], H, W, *[_p(g) for g in gs], _p(d_v_pos),
-                                            _p(d_v_nrm), _p(d_prior), _p(d_clip), _p(d_w2c), _p(d_campos), _stream()))
-        return None, d_clip, None, d_v_pos, d_v_nrm, d_prior, d_w2c, d_campos, None, None, None
+                                            _p(w2c), _p(campos), two_sided, B, V, tri.shape[0], H, W, _p(cov_list), _p(cov_count),
+                                            *[_p(g) for g in gs], _p(ws), ws.numel(), _p(d_v_pos), _p(d_v_nrm), _p(d_prior), _p(d_clip),
+                                            _p(d_w2c), _p(d_campos), _stream()))
+        else:
+            for t in (d_clip, d_v_pos, d_v_nrm, d_prior):
+                if t is not None:
+                    t.zero_()
+        return None, d_clip, None, d_v_pos, d_v_nrm, d_prior, d_w2c, d_campos, None, None, None, None, None
 
 
-def gbuffer(rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp=1, two_sided=True, want=("cam_nrm", "tex_pos")):
+def gbuffer(rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp=1, two_sided=True, want=("cam_nrm", "tex_pos"), coverage=None):
     """Fused g-buffer pass.  rast [B,H*spp,W*spp,4] (not differentiated: visibility is piecewise constant; barycentric
-    gradients go straight to pos_clip).  Returns a dict with the requested keys of GB_KEYS, each [B,H,W,3]."""
+    gradients go straight to pos_clip).  coverage: the (cov_list, cov_count) pair of ops.rasterize(with_coverage=True)
+    (used when spp == 1).  Returns a dict with the requested keys of GB_KEYS, each [B,H,W,3]."""
+    cl, cc = coverage if (coverage is not None and int(spp) == 1) else (None, None)
     outs = _GBuffer.apply(rast.detach(), pos_clip, _idx32(tri, "tri"), v_pos, v_nrm, prior_pos, w2c, campos, int(spp), bool(two_sided),
-                          tuple(want))
+                          tuple(want), cl, cc)
     return {k: o for k, o in zip(GB_KEYS, outs) if k in want}

@@ -58,7 +58,7 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
 
     # clip-space transform + rasterize (render.py:278, :292-294)
     v_pos_clip = ops.xfm_points(mesh.v_pos, mtx_in)
-    rast = ops.rasterize(v_pos_clip, tri, full_res)
+    rast, coverage = ops.rasterize(v_pos_clip, tri, full_res, with_coverage=True)
     rast_s = rast[:, ::shade_spp, ::shade_spp].contiguous() if shade_spp > 1 else rast
 
     # fused g-buffer
@@ -70,7 +70,7 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
     if "depth" in render_modes:
         want.append("pos")
     gb = ops.gbuffer(rast, v_pos_clip, tri, mesh.v_pos, mesh.v_nrm, prior_mesh.v_pos, w2c, campos, spp=shade_spp,
-                     two_sided=two_sided_shading, want=tuple(want))
+                     two_sided=two_sided_shading, want=tuple(want), coverage=coverage)
     gb_tex_pos, cam_normal = gb["tex_pos"], gb["cam_nrm"]
 
     # pixel shader: field MLPs + light stay PyTorch (render.py:50-94)
@@ -120,7 +120,7 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
     else:
         bg_full = None
 
-    aa_ctx = ops.antialias_prepare(rast) if any(k in _AA_KEYS and k in buffers for k in render_modes) else None
+    aa_ctx = ops.antialias_prepare(rast, v_pos_clip.detach(), tri, opp) if any(k in _AA_KEYS and k in buffers for k in render_modes) else None
     out_buffers = []
     for key in render_modes:
         if key not in buffers:

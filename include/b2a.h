@@ -74,6 +74,21 @@ int b2a_lbs_bone_transforms_bwd(const float* bones, const float* angles, const i
                                 float* d_angles /* [B,K,3] */, b2a_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Bone placement heuristic.  Replaces estimate_bones (model/geometry/skinning.py:49-248) for body_bones_mode
+ * 'z_minmax' (mode 0) / 'z_minmax_y+' (mode 1), bone_y_threshold=None, resample=False.
+ * verts [N,V,3] (N = batch*frames) -> bones [N,K,2,3], K = n_body_bones + 4*n_leg_bones (legs only if n_leg_bones>0).
+ * attach0..3: index of the body bone whose end joint each leg attaches to (aux['legs'][i]['body_bone_idx']); -1 = pick
+ * the body bone closest in z to that instance's own foot (skinning.py:190-192) - attach_out [4] (nullable) receives
+ * instance 0's choice, which is the one the reference then reuses for every instance.
+ * The 5 %/95 % x-quantiles are taken over the WHOLE batch (skinning.py:157) by exact radix select, no sort, no sync.
+ * stats_out (nullable) [N,8]: x_margin, mean xyz, bit-cast arg-max/arg-min vertex ids (test hook).
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_estimate_bones_workspace_bytes(size_t* bytes);
+int b2a_estimate_bones(const float* verts, int N, int64_t V, int n_body_bones, int n_leg_bones, int mode, int attach0,
+                       int attach1, int attach2, int attach3, void* workspace, size_t workspace_bytes, float* bones,
+                       int32_t* attach_out, float* stats_out, b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Smooth vertex normals.  Replaces mesh.auto_normals (model/render/mesh.py:276-304).
  * nsum [B,V,3] is the un-normalised area-weighted sum (kept for the backward).
  * ---------------------------------------------------------------------------------------------------------- */
@@ -99,8 +114,11 @@ int b2a_xfm_points_bwd(const float* pts, const float* mtx, const float* d_out, i
  * Backward: d_rast[...,0:2] -> d_pos (x,y,w), accumulated into zero-initialised d_pos [B,V,4].
  * ---------------------------------------------------------------------------------------------------------- */
 int b2a_rasterize_workspace_bytes(int B, int64_t F, int H, int W, size_t* bytes);
+/* cov_list [B*H*W] / cov_count [1] (both nullable): compact list of covered pixels (flat index b*H*W + y*W + x, unordered)
+ * for b2a_gbuffer_bwd. */
 int b2a_rasterize_fwd(const float* pos, const int32_t* tri, int B, int64_t V, int64_t F, int H, int W,
-                      void* workspace, size_t workspace_bytes, float* rast, b2a_stream_t stream);
+                      void* workspace, size_t workspace_bytes, float* rast, int32_t* cov_list, int32_t* cov_count,
+                      b2a_stream_t stream);
 int b2a_rasterize_bwd(const float* pos, const int32_t* tri, const float* rast, const float* d_rast, int B, int64_t V,
                       int64_t F, int H, int W, float* d_pos, b2a_stream_t stream);
 
@@ -129,11 +147,13 @@ int b2a_interpolate_bwd(const float* attr, const float* rast, const int32_t* tri
 int b2a_edge_adjacency_workspace_bytes(int64_t F, size_t* bytes);
 int b2a_edge_adjacency(const int32_t* tri, int64_t F, int64_t V, void* workspace, size_t workspace_bytes,
                        int32_t* opp, b2a_stream_t stream);
-/* Optional per-render context (composite mode, H*W % 32 == 0): one pass over rast builds a 1-bit/pixel coverage mask and
- * the compact list of silhouette pixels; every antialias launch of that render (each key, fwd and bwd) then streams
- * without touching rast.  aa_ctx may be NULL (generic kernels). */
+/* Optional per-render context (composite mode, H*W % 32 == 0): one pass over rast builds 1-bit/pixel coverage and
+ * silhouette masks and the compact list of silhouette pixels, a second small launch runs the pixel-pair analysis once
+ * per silhouette pair (needs pos [B,V,4], tri, opp).  Every antialias launch of that render (each key, fwd and bwd) is
+ * then a single streaming pass that never touches rast / pos / tri.  aa_ctx may be NULL (generic kernels). */
 int b2a_antialias_workspace_bytes(int B, int H, int W, size_t* bytes);
-int b2a_antialias_prepare(const float* rast, int B, int H, int W, void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
+int b2a_antialias_prepare(const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, int B, int64_t V,
+                          int64_t F, int H, int W, void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
 int b2a_antialias_fwd(const float* color, const float* bg, int Bg, int composite, const float* rast, const float* pos,
                       const int32_t* tri, const int32_t* opp, int B, int64_t V, int64_t F, int H, int W, int C,
                       float* out, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
@@ -151,20 +171,24 @@ int b2a_antialias_bwd(const float* color, const float* bg, int Bg, int composite
  * rast (pixel (x*spp, y*spp)), which is what render_layer does when msaa is on (render.py:170-172).
  * Outputs (each nullable): gb_pos, gb_geo_nrm, gb_shading_nrm, gb_cam_nrm, gb_tex_pos [B,H,W,3].
  * v_pos, v_nrm [B,V,3]; prior_pos [Bq,V,3] (Bq in {1,B}); w2c [B,4,4]; campos [B,3].
- * Backward consumes the same inputs, pos_clip [B,V,4] and the (nullable) output grads and accumulates into
- * zero-initialised (each nullable) d_v_pos [B,V,3], d_v_nrm [B,V,3], d_prior_pos [Bq,V,3], d_clip [B,V,4] (x,y,w),
- * d_w2c [B,16], d_campos [B,3].
+ * Backward consumes the same inputs, pos_clip [B,V,4] and the (nullable) output grads.  Vertex gradients are summed with
+ * 16-byte vector reductions into a [B,V,12] accumulator (workspace, zeroed inside the call) and then WRITTEN (not
+ * accumulated) to the nullable d_v_pos [B,V,3], d_v_nrm [B,V,3], d_prior_pos [Bq,V,3], d_clip [B,V,4] (x,y,w; z = 0);
+ * d_w2c [B,16] and d_campos [B,3] (nullable) are accumulated into zero-initialised buffers.
+ * cov_list / cov_count (nullable, spp == 1 only): the rasterizer's compact covered-pixel list - dense warps.
  * ---------------------------------------------------------------------------------------------------------- */
 int b2a_gbuffer_fwd(const float* rast, int spp, const int32_t* tri, const float* v_pos, const float* v_nrm,
                     const float* prior_pos, int Bq, const float* w2c, const float* campos, int two_sided, int B,
                     int64_t V, int64_t F, int H, int W, float* gb_pos, float* gb_geo_nrm, float* gb_shading_nrm,
                     float* gb_cam_nrm, float* gb_tex_pos, b2a_stream_t stream);
+int b2a_gbuffer_bwd_workspace_bytes(int B, int64_t V, size_t* bytes);
 int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, const int32_t* tri, const float* v_pos,
                     const float* v_nrm, const float* prior_pos, int Bq, const float* w2c, const float* campos,
-                    int two_sided, int B, int64_t V, int64_t F, int H, int W, const float* d_gb_pos,
-                    const float* d_gb_geo_nrm, const float* d_gb_shading_nrm, const float* d_gb_cam_nrm,
-                    const float* d_gb_tex_pos, float* d_v_pos, float* d_v_nrm, float* d_prior_pos, float* d_clip,
-                    float* d_w2c, float* d_campos, b2a_stream_t stream);
+                    int two_sided, int B, int64_t V, int64_t F, int H, int W, const int32_t* cov_list,
+                    const int32_t* cov_count, const float* d_gb_pos, const float* d_gb_geo_nrm,
+                    const float* d_gb_shading_nrm, const float* d_gb_cam_nrm, const float* d_gb_tex_pos,
+                    void* workspace, size_t workspace_bytes, float* d_v_pos, float* d_v_nrm, float* d_prior_pos,
+                    float* d_clip, float* d_w2c, float* d_campos, b2a_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,52 @@ def test_estimate_bones_golden(cuda, name):
     assert np.allclose(bones2.cpu().numpy(), g["bones_rescaled"], atol=1e-5)
 
 
+@pytest.mark.parametrize("n_leg,mode", [(3, "z_minmax_y+"), (0, "z_minmax"), (2, "z_minmax")])
+def test_estimate_bones_batched_oracle(cuda, n_leg, mode):
+    """Fused kernel, B x F > 1 (per-instance deformation on, InstancePredictorBase.py:514-518): whole-batch x quantiles by
+    radix select, per-(b,f) masked arg-min, attachment index fixed by the first (b,f) (skinning.py:190-192) vs the oracle."""
+    sk = pkg("geometry.skinning")
+    g = golden("skin_horse.npz")
+    rng = np.random.RandomState(0)
+    shapes = np.stack([g["verts"] * np.float32(1 + 0.05 * i) + rng.randn(*g["verts"].shape).astype(np.float32) * 0.01
+                       for i in range(6)]).reshape(3, 2, -1, 3)
+    ref_b, ref_chain, ref_aux = gnp.estimate_bones(shapes, 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode)
+    bones, chain, aux = sk.estimate_bones(dev(shapes, cuda), 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode)
+    assert [(b, list(d)) for b, d in chain] == [(b, list(d)) for b, d in ref_chain]
+    assert np.allclose(bones.cpu().numpy(), ref_b, atol=1e-5)
+    if n_leg:
+        assert [l["body_bone_idx"] for l in aux["legs"]] == [l["body_bone_idx"] for l in ref_aux["legs"]]
+    bones2 = sk.estimate_bones(dev(shapes, cuda) * 1.01, 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode, compute_kinematic_chain=False,
+                               aux=aux)
+    ref2 = gnp.estimate_bones(shapes * np.float32(1.01), 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode, compute_kinematic_chain=False,
+                              aux=ref_aux)
+    assert np.allclose(bones2.cpu().numpy(), ref2, atol=1e-5)
+    # configured attachment joints (ponymation.yaml:114)
+    b3, c3, a3 = sk.estimate_bones(dev(shapes, cuda), 8, n_legs=4, n_leg_bones=max(n_leg, 1), body_bones_mode=mode,
+                                   legs_to_body_joint_indices=[2, 7, 7, 2])
+    r3, rc3, ra3 = gnp.estimate_bones(shapes, 8, n_legs=4, n_leg_bones=max(n_leg, 1), body_bones_mode=mode, legs_to_body_joint_indices=[2, 7, 7, 2])
+    assert np.allclose(b3.cpu().numpy(), r3, atol=1e-5) and [(b, list(d)) for b, d in c3] == [(b, list(d)) for b, d in rc3]
+
+
+def test_estimate_bones_quantile_exact(cuda):
+    """The radix-select quantiles equal torch.quantile on the same device bits (x_margin exposed through the stats hook)."""
+    ops = _ops()
+    lib = pkg("_lib")
+    rng = np.random.RandomState(3)
+    for n_inst, V in ((1, 1000), (4, 2357), (2, 50001)):
+        x = dev(rng.randn(n_inst, 1, V, 3).astype(np.float32) * 3, cuda)
+        x[0, 0, :7, 0] = x[0, 0, 7, 0]          # ties
+        ws = torch.empty(ops._size(lib.lib().b2a_estimate_bones_workspace_bytes), dtype=torch.uint8, device=cuda)
+        bones = torch.empty(n_inst, 20, 2, 3, device=cuda)
+        stats = torch.zeros(n_inst, 8, device=cuda)
+        ops._call("b2a_estimate_bones", (x.data_ptr(), n_inst, V, 8, 3, 1, -1, -1, -1, -1, ws.data_ptr(), ws.numel(), bones.data_ptr(), None,
+                                         stats.data_ptr(), ops._stream()), launches=4)
+        xs = x[..., 0]
+        ref = (xs.quantile(0.95) - xs.quantile(0.05)) * 0.2
+        assert torch.all(stats[:, 0] == ref), (stats[:, 0], ref)
+        assert torch.allclose(stats[:, 1:4], x.mean(2)[:, 0], atol=1e-6)
+
+
 @pytest.mark.parametrize("Bv,Bb", [(1, 1), (3, 1), (3, 3)])
 def test_lbs_batched_oracle(cuda, Bv, Bb):
     ops = _ops()
@@ -319,7 +365,7 @@ def test_composite_antialias_oracle(cuda, C, keep, with_bg, image, layout, prepa
     (ref * torch.from_numpy(g)).sum().backward()
     cd = dev(color, cuda).requires_grad_(True)
     pd = dev(clip, cuda).requires_grad_(True)
-    aa_ctx = ops.antialias_prepare(dev(rast, cuda)) if prepared else None
+    aa_ctx = ops.antialias_prepare(dev(rast, cuda), pd.detach(), dev(faces, cuda), dev(opp, cuda)) if prepared else None
     assert (aa_ctx is not None) == (prepared and (S * S) % 32 == 0)
     out = ops.composite_antialias(cd, dev(bg, cuda) if with_bg else None, dev(rast, cuda), pd, dev(faces, cuda), dev(opp, cuda),
                                   True, keep, aa_ctx=aa_ctx).permute(0, 3, 1, 2)
@@ -336,8 +382,8 @@ def test_composite_antialias_oracle(cuda, C, keep, with_bg, image, layout, prepa
 # ----------------------------------------------------------------------------------------------------------------
 # fused g-buffer
 # ----------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("spp,Bq,two_sided", [(1, 1, True), (1, 3, False), (2, 1, True)])
-def test_gbuffer_oracle(cuda, spp, Bq, two_sided):
+@pytest.mark.parametrize("spp,Bq,two_sided,use_cov", [(1, 1, True, True), (1, 1, True, False), (1, 3, False, True), (2, 1, True, False)])
+def test_gbuffer_oracle(cuda, spp, Bq, two_sided, use_cov):
     """One fused kernel vs the reference's sequence: 4x interpolate + prepare_shading_normal + camera normal."""
     ops = _ops()
     verts, faces, prior, mvp, w2c, campos, clip = _scene()
@@ -371,7 +417,15 @@ def test_gbuffer_oracle(cuda, spp, Bq, two_sided):
     # fused kernel
     vd, nd, qd = (dev(x.detach().numpy(), cuda).requires_grad_(True) for x in (vt, nt, qt))
     cd, wd, pd = (dev(x.detach().numpy(), cuda).requires_grad_(True) for x in (ct, wt, pt))
-    out = ops.gbuffer(dev(rast, cuda), cd, dev(faces, cuda), vd, nd, qd, wd, pd, spp=spp, two_sided=two_sided, want=tuple(refs))
+    coverage = None
+    if use_cov:   # the rasterizer's compact covered-pixel list (dense-warp backward)
+        rast_d, coverage = ops.rasterize(cd.detach(), dev(faces, cuda), (H, W), with_coverage=True)
+        assert np.array_equal(rast_d.cpu().numpy(), rast)
+        n_cov = int(coverage[1].item())
+        assert n_cov == int((rast[..., 3] > 0).sum())
+        assert np.array_equal(np.sort(coverage[0][:n_cov].cpu().numpy()), np.flatnonzero(rast[..., 3].reshape(-1) > 0))
+    out = ops.gbuffer(dev(rast, cuda), cd, dev(faces, cuda), vd, nd, qd, wd, pd, spp=spp, two_sided=two_sided, want=tuple(refs),
+                      coverage=coverage)
     covered = rast[:, ::spp, ::spp, 3] > 0
     for k in refs:
         assert rel_err(out[k].detach().cpu().numpy(), refs[k].detach().numpy()) < TOL, k
