@@ -239,8 +239,14 @@ __global__ void __launch_bounds__(256) aa_fwd_kernel(AAParams P, float* __restri
 }
 
 // gradient of one blended pair w.r.t. the clip-space positions of the silhouette edge's two vertices
-// (oracle/raster_ref.c orc_antialias_bwd); dd = sum_c d_out[target,c] * (color[p1,c] - color[p0,c])
-__device__ void aa_pos_grad(const AAParams& P, const float* __restrict__ pos_b, const AAPair& r, int d, float dd, float* __restrict__ d_pos_b)
+// (oracle/raster_ref.c orc_antialias_bwd) is linear in dd = sum_c d_out[target,c] * (color[p1,c] - color[p0,c]):
+// d_pos[e1] += dd * (g[0], g[1], 0, g[2]),  d_pos[e2] += dd * (g[3], g[4], 0, g[5]).
+struct AAPosCoef {
+    int e1, e2;
+    float g[6];
+};
+
+__device__ void aa_pos_coef(const AAParams& P, const float* __restrict__ pos_b, const AAPair& r, int d, AAPosCoef& c)
 {
     int e1 = __ldg(P.tri + (size_t)r.tri * 3 + (r.di + 1) % 3), e2 = __ldg(P.tri + (size_t)r.tri * 3 + (r.di + 2) % 3);
     float4 q1v = ldg4(pos_b + (size_t)e1 * 4), q2v = ldg4(pos_b + (size_t)e2 * 4);
@@ -261,16 +267,29 @@ __device__ void aa_pos_grad(const AAParams& P, const float* __restrict__ pos_b, 
     float ep = copysignf(1e-3f, dy);
     float iy = 1.f / (dy + ep);
     float dby = db * iy;
-    float iw1 = -w1 * iy * dd, iw2 = w2 * iy * dd;
+    float iw1 = -w1 * iy, iw2 = w2 * iy;
     float gp1x = iw1 * pxh * y2, gp2x = iw2 * pxh * y1;
     float gp1y = iw1 * pyh * (dby - x2), gp2y = iw2 * pyh * (dby - x1);
     float gp1w = -(q1v.x * gp1x + q1v.y * gp1y) * w1;
     float gp2w = -(q2v.x * gp2x + q2v.y * gp2y) * w2;
     if (d) { float t_; t_ = gp1x; gp1x = gp1y; gp1y = t_; t_ = gp2x; gp2x = gp2y; gp2y = t_; }
-    float* g1 = d_pos_b + (size_t)e1 * 4;
-    float* g2 = d_pos_b + (size_t)e2 * 4;
-    atomicAdd(g1, gp1x); atomicAdd(g1 + 1, gp1y); atomicAdd(g1 + 3, gp1w);
-    atomicAdd(g2, gp2x); atomicAdd(g2 + 1, gp2y); atomicAdd(g2 + 3, gp2w);
+    c.e1 = e1; c.e2 = e2;
+    c.g[0] = gp1x; c.g[1] = gp1y; c.g[2] = gp1w; c.g[3] = gp2x; c.g[4] = gp2y; c.g[5] = gp2w;
+}
+
+__device__ __forceinline__ void aa_pos_apply(const AAPosCoef& c, float dd, float* __restrict__ d_pos_b)
+{
+    float* g1 = d_pos_b + (size_t)c.e1 * 4;
+    float* g2 = d_pos_b + (size_t)c.e2 * 4;
+    atomicAdd(g1, dd * c.g[0]); atomicAdd(g1 + 1, dd * c.g[1]); atomicAdd(g1 + 3, dd * c.g[2]);
+    atomicAdd(g2, dd * c.g[3]); atomicAdd(g2 + 1, dd * c.g[4]); atomicAdd(g2 + 3, dd * c.g[5]);
+}
+
+__device__ void aa_pos_grad(const AAParams& P, const float* __restrict__ pos_b, const AAPair& r, int d, float dd, float* __restrict__ d_pos_b)
+{
+    AAPosCoef c;
+    aa_pos_coef(P, pos_b, r, d, c);
+    aa_pos_apply(c, dd, d_pos_b);
 }
 
 struct AAGrad {
@@ -346,7 +365,7 @@ struct AAContext {
     int* count;        // [0] pixels whose 4-neighbourhood carries another triangle id (candidates), [1] active pixels
     int* list;         // [B*HW] candidate pixels (flat index b*HW + p)
     int* alist;        // [B*HW] active pixels
-    int2* ainfo;       // [B*HW] per active-list entry: (triangle << 3) | (edge << 1) | shifted of the owned pairs (p,right), (p,down)
+    AAPosCoef* acoef;  // [2*B*HW] per active-list entry: position-gradient coefficients of the owned pairs (p,right), (p,down)
     float4* rec;       // [B*HW] dense, valid where the act bit is set: blend weights of the pixel's four pairs in the
                        //        generic kernel's order (up,p) (left,p) (p,right) (p,down); 0 = inactive
 };
@@ -363,10 +382,10 @@ size_t aa_ctx_layout(int B, int H, int W, void* base, AAContext* ctx)
         ctx->count = (int*)(p + 2 * cb);
         ctx->list = (int*)(p + 2 * cb + 256);
         ctx->alist = (int*)(p + 2 * cb + 256 + lb);
-        ctx->ainfo = (int2*)(p + 2 * cb + 256 + 2 * lb);
-        ctx->rec = (float4*)(p + 2 * cb + 256 + 4 * lb);
+        ctx->rec = (float4*)(p + 2 * cb + 256 + 2 * lb);
+        ctx->acoef = (AAPosCoef*)(p + 2 * cb + 256 + 2 * lb + b2a_align(npix * sizeof(float4)));
     }
-    return 2 * cb + 256 + 4 * lb + b2a_align(npix * sizeof(float4));
+    return 2 * cb + 256 + 2 * lb + b2a_align(npix * sizeof(float4)) + b2a_align(npix * 2 * sizeof(AAPosCoef));
 }
 
 // grid-stride over all B*HW pixels (HW % 32 == 0, so a warp never straddles two images)
@@ -410,19 +429,24 @@ __global__ void __launch_bounds__(128) aa_pairs_kernel(AAParams P, AAContext ctx
     for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < 4 * count; base += gridDim.x * blockDim.x) {
         const int i = base + lane, k = i & 3;
         float alpha = 0.f;
-        int info = 0, flat = 0;
+        int flat = 0;
+        AAPosCoef coef;
+        coef.e1 = coef.e2 = 0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) coef.g[q] = 0.f;
         if (i < 4 * count) {
             flat = ctx.list[i >> 2];
             const int b = flat / HW, p = flat - b * HW;
             const int qx = p % P.W + c_pair_dx[k], qy = p / P.W + c_pair_dy[k], d = c_pair_d[k];
             if (qx >= 0 && qy >= 0 && (d == 0 ? qx + 1 < P.W : qy + 1 < P.H)) {
                 const float* rast_b = P.rast + (size_t)b * HW * 4;
+                const float* pos_b = P.pos + (size_t)b * P.V * 4;
                 const int q0 = qy * P.W + qx;
                 float4 r0 = ldg4(rast_b + (size_t)q0 * 4), r1 = ldg4(rast_b + (size_t)(q0 + (d ? P.W : 1)) * 4);
                 AAPair r;
-                if (aa_analyze(P, P.pos + (size_t)b * P.V * 4, r0, r1, qx, qy, d, r)) {
+                if (aa_analyze(P, pos_b, r0, r1, qx, qy, d, r)) {
                     alpha = r.alpha;
-                    info = (r.tri << 3) | (r.di << 1) | ((r.px != qx || r.py != qy) ? 1 : 0);
+                    if (k >= 2 && fabsf(alpha) < 0.5f) aa_pos_coef(P, pos_b, r, d, coef);   // owned pair: position-gradient coefficients
                 }
             }
         }
@@ -432,14 +456,16 @@ __global__ void __launch_bounds__(128) aa_pairs_kernel(AAParams P, AAContext ctx
         a.y = __shfl_sync(0xffffffffu, alpha, g0 + 1);
         a.z = __shfl_sync(0xffffffffu, alpha, g0 + 2);
         a.w = __shfl_sync(0xffffffffu, alpha, g0 + 3);
-        int i2 = __shfl_sync(0xffffffffu, info, g0 + 2), i3 = __shfl_sync(0xffffffffu, info, g0 + 3);
-        if (k == 0 && (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f)) {
+        const bool live = a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f;
+        int slot = 0;
+        if (k == 0 && live) {
             ctx.rec[flat] = a;
             atomicOr(ctx.act + (flat >> 5), 1u << (flat & 31));
-            int slot = atomicAdd(ctx.count + 1, 1);
+            slot = atomicAdd(ctx.count + 1, 1);
             ctx.alist[slot] = flat;
-            ctx.ainfo[slot] = make_int2(i2, i3);
         }
+        slot = __shfl_sync(0xffffffffu, slot, g0);
+        if (k >= 2 && live) ctx.acoef[(size_t)slot * 2 + (k - 2)] = coef;
     }
 }
 
@@ -459,88 +485,115 @@ __device__ __forceinline__ int nth_bit(uint32_t m, int j) { return (int)__fns(m,
 
 // Forward.  The smem tile holds the composited image of 32 pixels in OUTPUT layout [pp*C + c]; elements of active
 // pixels are fixed in place (work items = active pixel x channel, spread over the lanes) before the float4 stores.
-template <int C>
-__global__ void __launch_bounds__(256) aa_fwd_tile_kernel(const float* __restrict__ color, const float* __restrict__ bg, int Bg, AAContext ctx,
+// A warp owns TPW consecutive tiles and issues the colour loads of all of them up front (bytes in flight).
+template <int C, int TPW>
+__global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_fwd_tile_kernel(const float* __restrict__ color, const float* __restrict__ bg, int Bg, AAContext ctx,
                                                           int B, int H, int W, float* __restrict__ out)
 {
     constexpr int CI = C - 1;
+    constexpr int NV = (8 * CI + 31) / 32;   // float4 colour loads per lane per tile
     __shared__ __align__(16) float s_tile[8][32 * C];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int HW = H * W;
-    const int t = blockIdx.x * 8 + w;                 // 32-pixel tile
-    if ((int64_t)t * 32 >= (int64_t)B * HW) return;
-    const size_t P0 = (size_t)t * 32;
-    const int b = (int)(P0 / HW);
-    const uint32_t cov = __ldg(ctx.cover + t), act = __ldg(ctx.act + t);
+    const int64_t ntiles = ((int64_t)B * HW) / 32;
+    const int64_t t0 = ((int64_t)blockIdx.x * 8 + w) * TPW;
+    if (t0 >= ntiles) return;
     float* tile = s_tile[w];
-    float4* dst = reinterpret_cast<float4*>(out + P0 * C);
-    // background (or zeros) in output layout
-    if (cov != 0xffffffffu) {
+    uint32_t cov[TPW], act[TPW];
+    float4 cv[TPW][NV];
+#pragma unroll
+    for (int tt = 0; tt < TPW; tt++) {
+        const int64_t t = t0 + tt;
+        cov[tt] = t < ntiles ? __ldg(ctx.cover + t) : 0u;
+        act[tt] = t < ntiles ? __ldg(ctx.act + t) : 0u;
+    }
+#pragma unroll
+    for (int tt = 0; tt < TPW; tt++) {
+        if (cov[tt] == 0u) continue;
+        const float4* src = reinterpret_cast<const float4*>(color + (size_t)(t0 + tt) * 32 * CI);
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+            if (k * 32 + lane < 8 * CI) cv[tt][k] = __ldg(src + k * 32 + lane);
+    }
+#pragma unroll
+    for (int tt = 0; tt < TPW; tt++) {
+        if (t0 + tt >= ntiles) break;
+        const size_t P0 = (size_t)(t0 + tt) * 32;
+        const int b = (int)(P0 / HW);
+        const uint32_t cm = cov[tt], am = act[tt];
+        float4* dst = reinterpret_cast<float4*>(out + P0 * C);
         const float4* bsrc = bg ? reinterpret_cast<const float4*>(bg + (Bg == 1 ? P0 - (size_t)b * HW : P0) * C) : nullptr;
-        if (cov == 0u && act == 0u) {      // pure background tile: straight copy
+        if (cm == 0u && am == 0u) {      // pure background tile: straight copy
 #pragma unroll
             for (int i = lane; i < 8 * C; i += 32) dst[i] = bsrc ? __ldg(bsrc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            return;
+            continue;
         }
-#pragma unroll
-        for (int i = lane; i < 8 * C; i += 32) reinterpret_cast<float4*>(tile)[i] = bsrc ? __ldg(bsrc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
-    }
-    if (cov) {
-        const float4* src = reinterpret_cast<const float4*>(color + P0 * CI);
+        if (cm != 0xffffffffu) {         // background (or zeros) in output layout
 #pragma unroll
-        for (int i = lane; i < 8 * CI; i += 32) {
-            float4 x = __ldg(src + i);
-            float xv[4] = {x.x, x.y, x.z, x.w};
+            for (int i = lane; i < 8 * C; i += 32) reinterpret_cast<float4*>(tile)[i] = bsrc ? __ldg(bsrc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+        }
+        if (cm) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int e = 4 * i + j;
-                const int pp = e / CI, c = e - pp * CI;
-                if ((cov >> pp) & 1u) tile[pp * C + c] = xv[j];
+            for (int k = 0; k < NV; k++) {
+                const int i = k * 32 + lane;
+                if (i < 8 * CI) {
+                    const float4 x = cv[tt][k];
+                    const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int e = 4 * i + j;
+                        const int pp = e / CI, c = e - pp * CI;
+                        if ((cm >> pp) & 1u) tile[pp * C + c] = xv[j];
+                    }
+                }
             }
-        }
-        if ((cov >> lane) & 1u) tile[lane * C + CI] = 1.f;
-    }
-    __syncwarp();
-    if (act) {
-        const int items = __popc(act) * C;
-        for (int item = lane; item < items; item += 32) {
-            const int j = item / C, c = item - j * C;
-            const int pp = nth_bit(act, j);
-            const size_t flat = P0 + pp;
-            const float4 a = __ldg(ctx.rec + flat);
-            const float own = tile[pp * C + c];
-            // this pixel is the blend target of (up,p)/(left,p) when alpha < 0 and of (p,right)/(p,down) when alpha > 0.
-            // Neighbour colours come from global memory (the unblended input), loaded up front so the loads overlap.
-            const bool k0 = a.x < 0.f, k1 = a.y < 0.f, k2 = a.z > 0.f, k3 = a.w > 0.f;
-            const float cu = k0 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - W, c) : own;
-            const float cl = k1 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - 1, c) : own;
-            const float cr = k2 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + 1, c) : own;
-            const float cd = k3 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + W, c) : own;
-            float acc = own;
-            if (k0) acc += a.x * (own - cu);
-            if (k1) acc += a.y * (own - cl);
-            if (k2) acc += a.z * (cr - own);
-            if (k3) acc += a.w * (cd - own);
-            tile[pp * C + c] = acc;     // each item touches only its own slot
+            if ((cm >> lane) & 1u) tile[lane * C + CI] = 1.f;
         }
         __syncwarp();
-    }
+        if (am) {
+            const int items = __popc(am) * C;
+            for (int item = lane; item < items; item += 32) {
+                const int j = item / C, c = item - j * C;
+                const int pp = nth_bit(am, j);
+                const size_t flat = P0 + pp;
+                const float4 a = __ldg(ctx.rec + flat);
+                const float own = tile[pp * C + c];
+                // this pixel is the blend target of (up,p)/(left,p) when alpha < 0 and of (p,right)/(p,down) when alpha > 0.
+                // Neighbour colours come from global memory (the unblended input), loaded up front so the loads overlap.
+                const bool k0 = a.x < 0.f, k1 = a.y < 0.f, k2 = a.z > 0.f, k3 = a.w > 0.f;
+                const float cu = k0 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - W, c) : own;
+                const float cl = k1 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - 1, c) : own;
+                const float cr = k2 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + 1, c) : own;
+                const float cd = k3 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + W, c) : own;
+                float acc = own;
+                if (k0) acc += a.x * (own - cu);
+                if (k1) acc += a.y * (own - cl);
+                if (k2) acc += a.z * (cr - own);
+                if (k3) acc += a.w * (cd - own);
+                tile[pp * C + c] = acc;     // each item touches only its own slot
+            }
+            __syncwarp();
+        }
 #pragma unroll
-    for (int i = lane; i < 8 * C; i += 32) dst[i] = reinterpret_cast<const float4*>(tile)[i];
+        for (int i = lane; i < 8 * C; i += 32) dst[i] = reinterpret_cast<const float4*>(tile)[i];
+    }
 }
 
 constexpr int AA_POS_BLOCKS = 148 * 4;
 
-// d_pos role: one half-warp per owned pair of an active pixel, channels across the 16 lanes
+// vertex-position gradient role: one half-warp per owned pair of an active pixel, channels across the 16 lanes.  All
+// geometry was folded into per-pair coefficients by aa_pairs_kernel, so this is a short gather + six atomics and costs
+// the streaming kernel no registers; it runs in the LAST blocks of the same launch.
 template <int C>
-__device__ void aa_bwd_pos_role(const AAParams& P, const AAGrad& G, const AAContext& ctx, float* __restrict__ d_pos)
+__device__ __forceinline__ void aa_bwd_pos_role(const AAParams& P, const AAGrad& G, const AAContext& ctx, float* __restrict__ d_pos, int role_block)
 {
     const int HW = P.H * P.W;
     const int lane = threadIdx.x & 31, sub = lane & 15, d = lane >> 4;
     const int count = ctx.count[1];
     const int nwarp = AA_POS_BLOCKS * (blockDim.x >> 5);
-    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += nwarp) {
+    for (int i = role_block * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += nwarp) {
         const int flat = ctx.alist[i];
         const int b = flat / HW, p = flat - b * HW;
         const float4 av = __ldg(ctx.rec + flat);
@@ -557,99 +610,132 @@ __device__ void aa_bwd_pos_role(const AAParams& P, const AAGrad& G, const AACont
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
         if (on && sub == 0 && dd != 0.f) {
-            const int2 inf = __ldg(ctx.ainfo + i);
-            const int info = d ? inf.y : inf.x;
-            AAPair r;
-            r.alpha = a; r.tri = info >> 3; r.di = (info >> 1) & 3;
-            r.px = p % P.W + ((info & 1) ? 1 - d : 0);
-            r.py = p / P.W + ((info & 1) ? d : 0);
-            aa_pos_grad(P, P.pos + (size_t)b * P.V * 4, r, d, dd, d_pos + (size_t)b * P.V * 4);
+            const AAPosCoef* cp = ctx.acoef + (size_t)i * 2 + d;
+            const int4 c0 = __ldg(reinterpret_cast<const int4*>(cp));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(cp) + 1);
+            float* g1 = d_pos + ((size_t)b * P.V + c0.x) * 4;
+            float* g2 = d_pos + ((size_t)b * P.V + c0.y) * 4;
+            atomicAdd(g1, dd * __int_as_float(c0.z)); atomicAdd(g1 + 1, dd * __int_as_float(c0.w)); atomicAdd(g1 + 3, dd * c1.x);
+            atomicAdd(g2, dd * c1.y); atomicAdd(g2 + 1, dd * c1.z); atomicAdd(g2 + 3, dd * c1.w);
         }
     }
 }
 
 // Backward.  CC = colour channels written, CG = gradient channels read (CG >= CC; CG == CC + 1 when the alpha channel is
 // kept).  NCHW: the gradient's x stride is 1 (each warp loads CC coalesced 128-byte rows); else NHWC-contiguous (float4s).
-// The smem tile [pp*ST + c] holds g; covered silhouette elements gather their pair terms in place, then masked stores.
-template <int C, int CC, int CG, bool NCHW>
-__global__ void __launch_bounds__(256) aa_bwd_tile_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
-                                                          float* __restrict__ d_pos)
+// A warp owns TPW consecutive 32-pixel tiles and issues the loads of all of them before touching any (bytes in flight:
+// the narrow keys are latency-bound otherwise).  Per tile the smem tile [pp*ST + c] holds g; covered silhouette elements
+// gather their pair terms in place, then masked float4 stores.
+template <int C, int CC, int CG, bool NCHW, int TPW>
+__global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_bwd_tile_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
+                                                                            float* __restrict__ d_pos, int tile_blocks)
 {
     constexpr int ST = CG + 1;   // padded pixel stride: conflict-free for both access patterns
+    constexpr int NV = NCHW ? CC : (8 * CG + 31) / 32;   // registers per lane per tile: scalars (NCHW) or float4s (NHWC)
     __shared__ float s_tile[8][32 * ST];
-    if (blockIdx.x < AA_POS_BLOCKS) {
-        if (d_pos) aa_bwd_pos_role<C>(P, G, ctx, d_pos);
+    if ((int)blockIdx.x >= tile_blocks) {
+        aa_bwd_pos_role<C>(P, G, ctx, d_pos, (int)blockIdx.x - tile_blocks);
         return;
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int HW = P.H * P.W;
-    const int t = (blockIdx.x - AA_POS_BLOCKS) * 8 + w;
-    if ((int64_t)t * 32 >= (int64_t)P.B * HW) return;
-    const size_t P0 = (size_t)t * 32;
-    const int b = (int)(P0 / HW), p0 = (int)(P0 - (size_t)b * HW);
-    const uint32_t cov = __ldg(ctx.cover + t), act = __ldg(ctx.act + t) & cov;
+    const int64_t ntiles = ((int64_t)P.B * HW) / 32;
+    const int64_t t0 = ((int64_t)blockIdx.x * 8 + w) * TPW;
+    if (t0 >= ntiles) return;
     float* tile = s_tile[w];
-    float4* dst = reinterpret_cast<float4*>(d_color + P0 * CC);
-    if (cov == 0u) {   // nothing covered in this tile: the colour gradient is zero (background pixels never reach `color`)
+    uint32_t cov[TPW], act[TPW];
+    float vs[NCHW ? TPW : 1][NCHW ? NV : 1];
+    float4 vv[NCHW ? 1 : TPW][NCHW ? 1 : NV];
 #pragma unroll
-        for (int i = lane; i < 8 * CC; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
+    for (int tt = 0; tt < TPW; tt++) {
+        const int64_t t = t0 + tt;
+        cov[tt] = t < ntiles ? __ldg(ctx.cover + t) : 0u;
+        act[tt] = t < ntiles ? __ldg(ctx.act + t) & cov[tt] : 0u;
     }
-    if (NCHW) {
-        const int py = p0 / P.W, px0 = p0 - py * P.W;   // W % 32 == 0: the tile lies in one row
-        const float* gp = G.d_out + (int64_t)b * G.sb + (int64_t)py * G.sy + px0 + lane;
-        float v[CC];
 #pragma unroll
-        for (int c = 0; c < CC; c++) v[c] = __ldg(gp + (int64_t)c * G.sc);
+    for (int tt = 0; tt < TPW; tt++) {
+        if (cov[tt] == 0u) continue;
+        const size_t P0 = (size_t)(t0 + tt) * 32;
+        const int b = (int)(P0 / HW), p0 = (int)(P0 - (size_t)b * HW);
+        if (NCHW) {
+            const int py = p0 / P.W, px0 = p0 - py * P.W;   // W % 32 == 0: the tile lies in one row
+            const float* gp = G.d_out + (int64_t)b * G.sb + (int64_t)py * G.sy + px0 + lane;
 #pragma unroll
-        for (int c = 0; c < CC; c++) tile[lane * ST + c] = v[c];
-    } else {
-        const float4* src = reinterpret_cast<const float4*>(G.d_out + (int64_t)b * G.sb + (int64_t)p0 * CG);
+            for (int c = 0; c < NV; c++) vs[NCHW ? tt : 0][NCHW ? c : 0] = __ldg(gp + (int64_t)c * G.sc);
+        } else {
+            const float4* src = reinterpret_cast<const float4*>(G.d_out + (int64_t)b * G.sb + (int64_t)p0 * CG);
 #pragma unroll
-        for (int i = lane; i < 8 * CG; i += 32) {
-            float4 x = __ldg(src + i);
-            float xv[4] = {x.x, x.y, x.z, x.w};
+            for (int k = 0; k < NV; k++)
+                if (k * 32 + lane < 8 * CG) vv[NCHW ? 0 : tt][NCHW ? 0 : k] = __ldg(src + k * 32 + lane);
+        }
+    }
+#pragma unroll
+    for (int tt = 0; tt < TPW; tt++) {
+        if (t0 + tt >= ntiles) break;
+        const size_t P0 = (size_t)(t0 + tt) * 32;
+        const int b = (int)(P0 / HW), p0 = (int)(P0 - (size_t)b * HW);
+        float4* dst = reinterpret_cast<float4*>(d_color + P0 * CC);
+        if (cov[tt] == 0u) {   // nothing covered in this tile: the colour gradient is zero (background never reaches `color`)
+#pragma unroll
+            for (int i = lane; i < 8 * CC; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        __syncwarp();
+        if (NCHW) {
+#pragma unroll
+            for (int c = 0; c < NV; c++) tile[lane * ST + c] = vs[NCHW ? tt : 0][NCHW ? c : 0];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                const int i = k * 32 + lane;
+                if (i < 8 * CG) {
+                    const float4 x = vv[NCHW ? 0 : tt][NCHW ? 0 : k];
+                    const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int e = 4 * i + j;
+                        const int pp = e / CG, c = e - pp * CG;
+                        tile[pp * ST + c] = xv[j];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (act[tt]) {
+            const uint32_t am = act[tt];
+            const int items = __popc(am) * CC;
+            for (int item = lane; item < items; item += 32) {
+                const int j = item / CC, c = item - j * CC;
+                const int pp = nth_bit(am, j);
+                const int p = p0 + pp;
+                const float4 a = __ldg(ctx.rec + P0 + pp);
+                const float own = tile[pp * ST + c];
+                // d_color[p] = g[p] + a_up g[t] + a_left g[t] - a_right g[t] - a_down g[t], t = the pair's blend target
+                const float gu = a.x != 0.f ? (a.x > 0.f ? grad_at(G, P.W, b, p - P.W, c) : own) : 0.f;
+                const float gl = a.y != 0.f ? (a.y > 0.f ? grad_at(G, P.W, b, p - 1, c) : own) : 0.f;
+                const float gr = a.z != 0.f ? (a.z > 0.f ? own : grad_at(G, P.W, b, p + 1, c)) : 0.f;
+                const float gd = a.w != 0.f ? (a.w > 0.f ? own : grad_at(G, P.W, b, p + P.W, c)) : 0.f;
+                float acc = own;
+                if (a.x != 0.f) acc += a.x * gu;
+                if (a.y != 0.f) acc += a.y * gl;
+                if (a.z != 0.f) acc -= a.z * gr;
+                if (a.w != 0.f) acc -= a.w * gd;
+                tile[pp * ST + c] = acc;    // each item touches only its own slot
+            }
+            __syncwarp();
+        }
+        const uint32_t cm = cov[tt];
+#pragma unroll
+        for (int i = lane; i < 8 * CC; i += 32) {
+            float v[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int e = 4 * i + j;
-                const int pp = e / CG, c = e - pp * CG;
-                tile[pp * ST + c] = xv[j];
+                const int pp = e / CC, c = e - pp * CC;
+                v[j] = ((cm >> pp) & 1u) ? tile[pp * ST + c] : 0.f;
             }
+            dst[i] = make_float4(v[0], v[1], v[2], v[3]);
         }
-    }
-    __syncwarp();
-    if (act) {
-        const int items = __popc(act) * CC;
-        for (int item = lane; item < items; item += 32) {
-            const int j = item / CC, c = item - j * CC;
-            const int pp = nth_bit(act, j);
-            const int p = p0 + pp;
-            const float4 a = __ldg(ctx.rec + P0 + pp);
-            const float own = tile[pp * ST + c];
-            // d_color[p] = g[p] + a_up g[t] + a_left g[t] - a_right g[t] - a_down g[t], t = the pair's blend target
-            const float gu = a.x != 0.f ? (a.x > 0.f ? grad_at(G, P.W, b, p - P.W, c) : own) : 0.f;
-            const float gl = a.y != 0.f ? (a.y > 0.f ? grad_at(G, P.W, b, p - 1, c) : own) : 0.f;
-            const float gr = a.z != 0.f ? (a.z > 0.f ? own : grad_at(G, P.W, b, p + 1, c)) : 0.f;
-            const float gd = a.w != 0.f ? (a.w > 0.f ? own : grad_at(G, P.W, b, p + P.W, c)) : 0.f;
-            float acc = own;
-            if (a.x != 0.f) acc += a.x * gu;
-            if (a.y != 0.f) acc += a.y * gl;
-            if (a.z != 0.f) acc -= a.z * gr;
-            if (a.w != 0.f) acc -= a.w * gd;
-            tile[pp * ST + c] = acc;    // each item touches only its own slot
-        }
-        __syncwarp();
-    }
-#pragma unroll
-    for (int i = lane; i < 8 * CC; i += 32) {
-        float v[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int e = 4 * i + j;
-            const int pp = e / CC, c = e - pp * CC;
-            v[j] = ((cov >> pp) & 1u) ? tile[pp * ST + c] : 0.f;
-        }
-        dst[i] = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -737,8 +823,9 @@ bool aa_fast_ok(int composite, const void* aa_ctx, size_t aa_ctx_bytes, int B, i
 template <int C>
 void aa_fwd_tile(const float* color, const float* bg, int Bg, const AAContext& ctx, int B, int H, int W, float* out, cudaStream_t stream)
 {
+    constexpr int TPW = C >= 9 ? 1 : 4;
     unsigned tiles = (unsigned)(((int64_t)B * H * W) / 32);
-    aa_fwd_tile_kernel<C><<<b2a_blocks(tiles, 8), 256, 0, stream>>>(color, bg, Bg, ctx, B, H, W, out);
+    aa_fwd_tile_kernel<C, TPW><<<b2a_blocks(tiles, 8 * TPW), 256, 0, stream>>>(color, bg, Bg, ctx, B, H, W, out);
 }
 }  // namespace
 
@@ -771,17 +858,16 @@ namespace {
 template <int C, int CC, int CG>
 bool aa_bwd_tile(const AAParams& P, const AAGrad& G, const AAContext& ctx, float* d_color, float* d_pos, cudaStream_t stream)
 {
+    constexpr int TPW = CC >= 8 ? 1 : 4;   // tiles per warp: keep >= ~12 loads in flight per lane
     unsigned tiles = (unsigned)(((int64_t)P.B * P.H * P.W) / 32);
-    unsigned grid = AA_POS_BLOCKS + b2a_blocks(tiles, 8);
-    if (G.sc == 1 && G.sx == CG && G.sy == (int64_t)P.W * CG && G.sb % 4 == 0 && aligned16(G.d_out)) {
-        aa_bwd_tile_kernel<C, CC, CG, false><<<grid, 256, 0, stream>>>(P, G, ctx, d_color, d_pos);
-        return true;
-    }
-    if (G.sx == 1 && P.W % 32 == 0) {
-        aa_bwd_tile_kernel<C, CC, CG, true><<<grid, 256, 0, stream>>>(P, G, ctx, d_color, d_pos);
-        return true;
-    }
-    return false;
+    unsigned grid = b2a_blocks(tiles, 8 * TPW);
+    const bool nhwc = G.sc == 1 && G.sx == CG && G.sy == (int64_t)P.W * CG && G.sb % 4 == 0 && aligned16(G.d_out);
+    const bool nchw = G.sx == 1 && P.W % 32 == 0;
+    if (!nhwc && !nchw) return false;
+    const unsigned total = grid + (d_pos ? AA_POS_BLOCKS : 0);
+    if (nhwc) aa_bwd_tile_kernel<C, CC, CG, false, TPW><<<total, 256, 0, stream>>>(P, G, ctx, d_color, d_pos, (int)grid);
+    else aa_bwd_tile_kernel<C, CC, CG, true, TPW><<<total, 256, 0, stream>>>(P, G, ctx, d_color, d_pos, (int)grid);
+    return true;
 }
 }  // namespace
 

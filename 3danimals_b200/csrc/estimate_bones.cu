@@ -48,49 +48,70 @@ __device__ __forceinline__ void eb_ranks(int64_t n, unsigned rank[EB_T], float w
     }
 }
 
-// Whole block: smallest bin whose inclusive cumulative count exceeds k; *krem = k - (count before that bin).
-// hist has `nbins` (<= 8 * blockDim.x) entries.  smem: 34 ints.
-__device__ void eb_select_bin(const unsigned* __restrict__ hist, int nbins, unsigned k, int* smem, unsigned* bin, unsigned* krem)
+// One warp: smallest bin whose inclusive cumulative count exceeds k; *krem = k - (count before that bin).  Each lane owns
+// nbins/32 consecutive bins (register-resident), one shuffle scan locates the lane, that lane walks its bins.
+template <int NB>
+__device__ __forceinline__ void eb_select_bin_warp(const unsigned* __restrict__ hist, unsigned k, unsigned* bin, unsigned* krem)
 {
-    const int per = (nbins + blockDim.x - 1) / blockDim.x;
-    const int b0 = threadIdx.x * per;
-    int local = 0;
-    for (int i = 0; i < per; i++)
-        if (b0 + i < nbins) local += (int)hist[b0 + i];
-    int total;
-    int before = block_exclusive_scan(local, smem, &total);
-    if ((unsigned)before <= k && k < (unsigned)(before + local)) {
-        unsigned acc = (unsigned)before;
-        for (int i = 0; i < per; i++) {
-            unsigned h = hist[b0 + i];
-            if (k < acc + h) { smem[33] = b0 + i; smem[32] = (int)(k - acc); break; }
-            acc += h;
+    constexpr int PER = NB / 32;
+    const int lane = threadIdx.x & 31;
+    unsigned h[PER];
+    unsigned local = 0;
+#pragma unroll
+    for (int i = 0; i < PER; i++) { h[i] = hist[lane * PER + i]; local += h[i]; }
+    unsigned inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const unsigned before = inc - local;
+    unsigned rb = 0, rk = 0;
+    const bool mine = before <= k && k < inc;
+    if (mine) {
+        unsigned acc = before;
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            if (k >= acc && k < acc + h[i]) { rb = lane * PER + i; rk = k - acc; }
+            acc += h[i];
         }
     }
-    __syncthreads();
-    *bin = (unsigned)smem[33];
-    *krem = (unsigned)smem[32];
-    __syncthreads();
+    const unsigned who = __ballot_sync(0xffffffffu, mine);
+    const int src = who ? __ffs(who) - 1 : 0;
+    *bin = __shfl_sync(0xffffffffu, rb, src);
+    *krem = __shfl_sync(0xffffffffu, rk, src);
 }
 
-// prefix (already selected high bits) and remaining rank of every target after `pass` completed passes
+// prefix (already selected high bits) and remaining rank of every target after `passes` completed passes.  Warp t of
+// the block resolves target t (the four selections run concurrently); results are broadcast through shared memory.
+// Needs blockDim.x >= 128.  smem: 2 * EB_T unsigned.
 __device__ void eb_resolve(const EbWorkspace& ws, int passes, int64_t n, int* smem, unsigned prefix[EB_T], unsigned krem[EB_T])
 {
     float w[2];
     eb_ranks(n, krem, w);
 #pragma unroll
     for (int t = 0; t < EB_T; t++) prefix[t] = 0u;
-    for (int p = 0; p < passes; p++) {
-        const int nbins = p == 2 ? 1024 : EB_BINS;
-        const int bits = p == 2 ? 10 : 11;
-        for (int t = 0; t < EB_T; t++) {
-            unsigned bin, kr;
+    const int warp = threadIdx.x >> 5;
+    if (warp < EB_T && passes > 0) {
+        const int t = warp;
+        unsigned pf = 0u, kr = krem[t];
+        for (int p = 0; p < passes; p++) {
+            unsigned bin, k2;
             // pass 0 has one shared histogram (slot 0); later passes one per target
-            eb_select_bin(ws.hist + ((size_t)p * EB_T + (p == 0 ? 0 : t)) * EB_BINS, nbins, krem[t], smem, &bin, &kr);
-            prefix[t] = (prefix[t] << bits) | bin;
-            krem[t] = kr;
+            const unsigned* h = ws.hist + ((size_t)p * EB_T + (p == 0 ? 0 : t)) * EB_BINS;
+            if (p == 2) eb_select_bin_warp<1024>(h, kr, &bin, &k2);
+            else eb_select_bin_warp<EB_BINS>(h, kr, &bin, &k2);
+            pf = (pf << (p == 2 ? 10 : 11)) | bin;
+            kr = k2;
         }
+        if ((threadIdx.x & 31) == 0) { smem[t] = (int)pf; smem[EB_T + t] = (int)kr; }
     }
+    __syncthreads();
+    if (passes > 0) {
+#pragma unroll
+        for (int t = 0; t < EB_T; t++) { prefix[t] = (unsigned)smem[t]; krem[t] = (unsigned)smem[EB_T + t]; }
+    }
+    __syncthreads();
 }
 
 // x coordinate of flat vertex i of verts [n,3]
@@ -107,6 +128,7 @@ __global__ void __launch_bounds__(EB_HIST_THREADS) eb_hist_kernel(const float* _
     unsigned prefix[EB_T], krem[EB_T];
     eb_resolve(ws, PASS, n, s_scan, prefix, krem);   // includes __syncthreads
     __syncthreads();
+#pragma unroll 4
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         unsigned key = sortable_key(__ldg(verts + i * 3));
         unsigned digit = (key >> SHIFT) & MASK;
@@ -219,6 +241,7 @@ __global__ void __launch_bounds__(1024) eb_final_kernel(const float* __restrict_
 
     // mean (deterministic: fixed strided partial sums in double, fixed tree)
     double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll 4
     for (int64_t v = threadIdx.x; v < V; v += blockDim.x) {
         sx += (double)__ldg(vp + v * 3); sy += (double)__ldg(vp + v * 3 + 1); sz += (double)__ldg(vp + v * 3 + 2);
     }
@@ -231,6 +254,7 @@ __global__ void __launch_bounds__(1024) eb_final_kernel(const float* __restrict_
     const float ythr = my - 0.5f;
     ArgVal amax{3.4e38f, 0x7fffffff}, amin{3.4e38f, 0x7fffffff};
     ArgVal foot[4] = {{3.4e38f, 0x7fffffff}, {3.4e38f, 0x7fffffff}, {3.4e38f, 0x7fffffff}, {3.4e38f, 0x7fffffff}};
+#pragma unroll 4
     for (int64_t v = threadIdx.x; v < V; v += blockDim.x) {
         float x = __ldg(vp + v * 3), y = __ldg(vp + v * 3 + 1), z = __ldg(vp + v * 3 + 2);
         bool up = mode == 0 || y > ythr;
@@ -351,7 +375,7 @@ B2A_API int b2a_estimate_bones(const float* verts, int N, int64_t V, int n_body_
     const int64_t n = (int64_t)N * V;
     if (n_leg_bones > 0) {
         B2A_CUDA_OK(cudaMemsetAsync(ws.hist, 0, (size_t)3 * EB_T * EB_BINS * sizeof(unsigned), stream));
-        unsigned blocks = b2a_blocks(n, EB_HIST_THREADS * 8);
+        unsigned blocks = b2a_blocks(n, EB_HIST_THREADS * 2);
         if (blocks > 148u * 4u) blocks = 148u * 4u;
         eb_hist_kernel<0><<<blocks, EB_HIST_THREADS, 0, stream>>>(verts, n, ws);
         eb_hist_kernel<1><<<blocks, EB_HIST_THREADS, 0, stream>>>(verts, n, ws);

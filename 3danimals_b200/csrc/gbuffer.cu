@@ -155,7 +155,7 @@ __device__ __forceinline__ void red4(float* p, float x, float y, float z, float 
 // LIST: threads walk the compact covered-pixel list written by the rasterizer (dense warps; DMTet renders cover ~20 %
 // of the image); otherwise one thread per pixel of the [B,H,W] grid (spp > 1 or no list).
 template <bool LIST>
-__global__ void __launch_bounds__(128) gb_bwd_kernel(GbParams P, const float* __restrict__ pos_clip, const int* __restrict__ cov_list,
+__global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float* __restrict__ pos_clip, const int* __restrict__ cov_list,
                                                      const int* __restrict__ cov_count, const float* __restrict__ d_gb_pos,
                                                      const float* __restrict__ d_gb_geo, const float* __restrict__ d_gb_shn,
                                                      const float* __restrict__ d_gb_cam, const float* __restrict__ d_gb_tex,
@@ -273,27 +273,39 @@ __global__ void __launch_bounds__(128) gb_bwd_kernel(GbParams P, const float* __
     }
 }
 
-// accumulator rows -> gradient tensors (each nullable); d_prior sums over the batch in a fixed order when Bq == 1
+// accumulator rows -> gradient tensors (each nullable).  Block = 32 vertices x 8 image lanes; d_prior sums over the batch
+// (Bq == 1) in a fixed order: per-lane partial sums over b = ty, ty+8, ..., then a fixed 8-term sum through smem.
 __global__ void __launch_bounds__(256) gb_bwd_finalize_kernel(const float* __restrict__ acc, int B, int Bq, int64_t V, float* __restrict__ d_v_pos,
                                                               float* __restrict__ d_v_nrm, float* __restrict__ d_prior, float* __restrict__ d_clip)
 {
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= V) return;
+    __shared__ float s_q[8][32][3];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t v = (int64_t)blockIdx.x * 32 + tx;
     float qx = 0.f, qy = 0.f, qz = 0.f;
-#pragma unroll 4
-    for (int b = 0; b < B; b++) {
-        const float4* a = reinterpret_cast<const float4*>(acc + ((size_t)b * V + v) * 12);
-        float4 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
-        size_t o = ((size_t)b * V + v) * 3;
-        if (d_v_pos) { d_v_pos[o] = a0.x; d_v_pos[o + 1] = a0.y; d_v_pos[o + 2] = a0.z; }
-        if (d_v_nrm) { d_v_nrm[o] = a1.x; d_v_nrm[o + 1] = a1.y; d_v_nrm[o + 2] = a1.z; }
-        if (d_clip) reinterpret_cast<float4*>(d_clip)[(size_t)b * V + v] = make_float4(a1.w, a2.w, 0.f, a0.w);
-        if (d_prior) {
-            if (Bq == 1) { qx += a2.x; qy += a2.y; qz += a2.z; }
-            else { d_prior[o] = a2.x; d_prior[o + 1] = a2.y; d_prior[o + 2] = a2.z; }
+    if (v < V) {
+        for (int b = ty; b < B; b += 8) {
+            const float4* a = reinterpret_cast<const float4*>(acc + ((size_t)b * V + v) * 12);
+            float4 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
+            size_t o = ((size_t)b * V + v) * 3;
+            if (d_v_pos) { d_v_pos[o] = a0.x; d_v_pos[o + 1] = a0.y; d_v_pos[o + 2] = a0.z; }
+            if (d_v_nrm) { d_v_nrm[o] = a1.x; d_v_nrm[o + 1] = a1.y; d_v_nrm[o + 2] = a1.z; }
+            if (d_clip) reinterpret_cast<float4*>(d_clip)[(size_t)b * V + v] = make_float4(a1.w, a2.w, 0.f, a0.w);
+            if (d_prior) {
+                if (Bq == 1) { qx += a2.x; qy += a2.y; qz += a2.z; }
+                else { d_prior[o] = a2.x; d_prior[o + 1] = a2.y; d_prior[o + 2] = a2.z; }
+            }
         }
     }
-    if (d_prior && Bq == 1) { d_prior[v * 3] = qx; d_prior[v * 3 + 1] = qy; d_prior[v * 3 + 2] = qz; }
+    if (d_prior && Bq == 1) {
+        s_q[ty][tx][0] = qx; s_q[ty][tx][1] = qy; s_q[ty][tx][2] = qz;
+        __syncthreads();
+        if (ty == 0 && v < V) {
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { sx += s_q[j][tx][0]; sy += s_q[j][tx][1]; sz += s_q[j][tx][2]; }
+            d_prior[v * 3] = sx; d_prior[v * 3 + 1] = sy; d_prior[v * 3 + 2] = sz;
+        }
+    }
 }
 
 int gb_check(const float* rast, int spp, const int32_t* tri, const float* v_pos, const float* v_nrm, const float* prior_pos, int Bq,
@@ -347,7 +359,10 @@ B2A_API int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, c
     GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F};
     const float* pc = d_clip ? pos_clip : nullptr;
     if (cov_list) {
-        gb_bwd_kernel<true><<<148 * 8, 128, 0, stream>>>(P, pc, cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
+        // about one covered pixel per thread at typical coverage (~25 %); the grid-stride loop absorbs the rest
+        unsigned lblocks = b2a_blocks(((int64_t)B * H * W + 3) / 4, 128);
+        if (lblocks > 148u * 32u) lblocks = 148u * 32u;
+        gb_bwd_kernel<true><<<lblocks, 128, 0, stream>>>(P, pc, cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
                                                          d_gb_tex_pos, acc, d_w2c, d_campos);
     } else {
         unsigned blocks = b2a_blocks((int64_t)B * H * W, 128);
@@ -355,7 +370,7 @@ B2A_API int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, c
                                                          d_gb_tex_pos, acc, d_w2c, d_campos);
     }
     if (d_v_pos || d_v_nrm || d_prior_pos || d_clip)
-        gb_bwd_finalize_kernel<<<b2a_blocks(V, 256), 256, 0, stream>>>(acc, B, Bq, V, d_v_pos, d_v_nrm, d_prior_pos, d_clip);
+        gb_bwd_finalize_kernel<<<b2a_blocks(V, 32), 256, 0, stream>>>(acc, B, Bq, V, d_v_pos, d_v_nrm, d_prior_pos, d_clip);
     B2A_LAUNCH_OK();
     return 0;
 }

@@ -304,6 +304,125 @@ __global__ void __launch_bounds__(LBS_BLOCK) lbs_bwd_kernel(const float* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Shared-weight fast path (Bv == 1 and Bb == 1: one prior shape and one bone set for the whole batch - the reference's
+// regime while per-instance deformation is off, InstancePredictorBase.py:514-518).  The soft weights depend only on
+// (vertex, bones), so a thread owns a vertex, evaluates its K distances / exponentials ONCE and loops over a chunk of
+// LBS_BC images; the generic kernels above redo that transcendental work per (image, vertex).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int LBS_BC = 4;
+constexpr int LBS_SBLOCK = 128;
+
+__device__ __forceinline__ float lbs_weights_shared(const float* __restrict__ s_bones, float (*s_w)[LBS_SBLOCK], int K, float px, float py,
+                                                    float pz, float inv_temp)
+{
+    float xmax = -3.4e38f;
+    for (int k = 0; k < K; k++) {
+        float x = -seg_dist(s_bones + k * 6, px, py, pz) * inv_temp;
+        s_w[k][threadIdx.x] = x;
+        xmax = fmaxf(xmax, x);
+    }
+    float sum = 0.f;
+    for (int k = 0; k < K; k++) {
+        float e = expf(s_w[k][threadIdx.x] - xmax);
+        s_w[k][threadIdx.x] = e;
+        sum += e;
+    }
+    return 1.f / sum;
+}
+
+__global__ void __launch_bounds__(LBS_SBLOCK) lbs_fwd_shared_kernel(const float* __restrict__ v_pos, const float* __restrict__ bones,
+                                                                    const float* __restrict__ G, int B, int K, int64_t V, float inv_temp,
+                                                                    float* __restrict__ out, float* __restrict__ weights)
+{
+    __shared__ float s_bones[LBS_CACHE_K * 6];
+    __shared__ float s_G[LBS_BC * LBS_CACHE_K * 12];
+    __shared__ float s_w[LBS_CACHE_K][LBS_SBLOCK];
+    const int b0 = blockIdx.y * LBS_BC, nb = min(LBS_BC, B - b0);
+    for (int i = threadIdx.x; i < K * 6; i += blockDim.x) s_bones[i] = bones[i];
+    for (int i = threadIdx.x; i < nb * K * 12; i += blockDim.x) s_G[i] = G[(size_t)b0 * K * 12 + i];
+    __syncthreads();
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const float px = v_pos[v * 3], py = v_pos[v * 3 + 1], pz = v_pos[v * 3 + 2];
+    const float inv = lbs_weights_shared(s_bones, s_w, K, px, py, pz, inv_temp);
+    for (int bb = 0; bb < nb; bb++) {
+        float ox = 0.f, oy = 0.f, oz = 0.f;
+        const float* gb = s_G + bb * K * 12;
+        for (int k = 0; k < K; k++) {
+            const float e = s_w[k][threadIdx.x];
+            const float* g = gb + k * 12;
+            ox += e * (g[0] * px + g[1] * py + g[2] * pz + g[3]);
+            oy += e * (g[4] * px + g[5] * py + g[6] * pz + g[7]);
+            oz += e * (g[8] * px + g[9] * py + g[10] * pz + g[11]);
+        }
+        float* o = out + ((size_t)(b0 + bb) * V + v) * 3;
+        o[0] = ox * inv; o[1] = oy * inv; o[2] = oz * inv;
+    }
+    if (weights && blockIdx.y == 0)
+        for (int k = 0; k < K; k++) weights[(size_t)k * V + v] = s_w[k][threadIdx.x] * inv;
+}
+
+// d_v_pos [1,V,3] is accumulated (zero-initialised by the caller) because image chunks run in different blocks
+__global__ void __launch_bounds__(LBS_SBLOCK) lbs_bwd_shared_kernel(const float* __restrict__ v_pos, const float* __restrict__ bones,
+                                                                    const float* __restrict__ G, const float* __restrict__ d_out, int B, int K,
+                                                                    int64_t V, float inv_temp, float* __restrict__ d_v_pos,
+                                                                    float* __restrict__ d_G)
+{
+    __shared__ float s_bones[LBS_CACHE_K * 6];
+    __shared__ float s_G[LBS_BC * LBS_CACHE_K * 12];
+    __shared__ float s_dG[LBS_BC * LBS_CACHE_K * 12];
+    __shared__ float s_w[LBS_CACHE_K][LBS_SBLOCK];
+    const int b0 = blockIdx.y * LBS_BC, nb = min(LBS_BC, B - b0);
+    for (int i = threadIdx.x; i < K * 6; i += blockDim.x) s_bones[i] = bones[i];
+    for (int i = threadIdx.x; i < nb * K * 12; i += blockDim.x) { s_G[i] = G[(size_t)b0 * K * 12 + i]; s_dG[i] = 0.f; }
+    __syncthreads();
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = v < V;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (valid) { px = v_pos[v * 3]; py = v_pos[v * 3 + 1]; pz = v_pos[v * 3 + 2]; }
+    float inv = lbs_weights_shared(s_bones, s_w, K, px, py, pz, inv_temp);
+    if (!valid) inv = 0.f;
+    const int lane = threadIdx.x & 31;
+    // bones that carry weight somewhere in this warp (the soft-max at temperature 0.05 is sparse)
+    unsigned live = 0u;
+    for (int k = 0; k < K; k++) {
+        float w = s_w[k][threadIdx.x] * inv;
+        s_w[k][threadIdx.x] = w;
+        if (__ballot_sync(0xffffffffu, w > 1e-10f)) live |= 1u << k;   // < fp32 eps of the dominant terms
+    }
+    float dvx = 0.f, dvy = 0.f, dvz = 0.f;
+    for (int bb = 0; bb < nb; bb++) {
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        if (valid) {
+            const float* g = d_out + ((size_t)(b0 + bb) * V + v) * 3;
+            gx = g[0]; gy = g[1]; gz = g[2];
+        }
+        const float* gb = s_G + bb * K * 12;
+        for (unsigned m = live; m; m &= m - 1) {
+            const int k = __ffs(m) - 1;
+            const float w = s_w[k][threadIdx.x];
+            const float* g = gb + k * 12;
+            dvx += w * (g[0] * gx + g[4] * gy + g[8] * gz);
+            dvy += w * (g[1] * gx + g[5] * gy + g[9] * gz);
+            dvz += w * (g[2] * gx + g[6] * gy + g[10] * gz);
+            float wx = w * gx, wy = w * gy, wz = w * gz;
+            const float r[16] = {wx * px, wx * py, wx * pz, wx, wy * px, wy * py, wy * pz, wy, wz * px, wz * py, wz * pz, wz, 0.f, 0.f, 0.f, 0.f};
+            float tot = warp_reduce16(r, lane);
+            if (!(lane & 1) && (lane >> 1) < 12) atomicAdd(&s_dG[(bb * K + k) * 12 + (lane >> 1)], tot);
+        }
+    }
+    if (valid && d_v_pos) {
+        float* o = d_v_pos + (size_t)v * 3;
+        atomicAdd(o, dvx); atomicAdd(o + 1, dvy); atomicAdd(o + 2, dvz);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * K * 12; i += blockDim.x) {
+        float s = s_dG[i];
+        if (s != 0.f) atomicAdd(&d_G[(size_t)b0 * K * 12 + i], s);
+    }
+}
+
 // chain backward: d_T_local[b, c_j] += P_j^T dG S_j^T  (affine algebra), after folding d_posed into dG
 __global__ void lbs_chain_bwd_kernel(const float* __restrict__ T_local, const float* __restrict__ bones, const int* __restrict__ chain_ptr,
                                      const int* __restrict__ chain_ids, float* __restrict__ d_G, const float* __restrict__ d_posed,
@@ -405,6 +524,12 @@ B2A_API int b2a_lbs_fwd(const float* v_pos, const float* bones, const float* G, 
     B2A_CHECK_ARG(v_pos && bones && G && out, "null pointer");
     B2A_CHECK_ARG(B > 0 && B <= 65535 && K > 0 && K <= LBS_MAX_K && (Bb == 1 || Bb == B) && (Bv == 1 || Bv == B), "shape");
     if (V == 0) return 0;
+    if (Bv == 1 && Bb == 1 && B > 1 && K <= LBS_CACHE_K) {
+        lbs_fwd_shared_kernel<<<dim3(b2a_blocks(V, LBS_SBLOCK), (B + LBS_BC - 1) / LBS_BC), LBS_SBLOCK, 0, stream>>>(v_pos, bones, G, B, K, V,
+                                                                                                                 inv_temperature, out, weights);
+        B2A_LAUNCH_OK();
+        return 0;
+    }
     dim3 grid(b2a_blocks(V, LBS_BLOCK), B);
     if (K <= LBS_CACHE_K) lbs_fwd_kernel<true><<<grid, LBS_BLOCK, 0, stream>>>(v_pos, bones, G, B, Bv, Bb, K, V, inv_temperature, out, weights);
     else lbs_fwd_kernel<false><<<grid, LBS_BLOCK, 0, stream>>>(v_pos, bones, G, B, Bv, Bb, K, V, inv_temperature, out, weights);
@@ -419,6 +544,12 @@ B2A_API int b2a_lbs_bwd(const float* v_pos, const float* bones, const float* G, 
     B2A_CHECK_ARG(v_pos && bones && G && d_out && d_G, "null pointer");
     B2A_CHECK_ARG(B > 0 && B <= 65535 && K > 0 && K <= LBS_MAX_K && (Bb == 1 || Bb == B) && (Bv == 1 || Bv == B), "shape");
     if (V == 0) return 0;
+    if (Bv == 1 && Bb == 1 && B > 1 && K <= LBS_CACHE_K) {
+        lbs_bwd_shared_kernel<<<dim3(b2a_blocks(V, LBS_SBLOCK), (B + LBS_BC - 1) / LBS_BC), LBS_SBLOCK, 0, stream>>>(v_pos, bones, G, d_out, B, K,
+                                                                                                                 V, inv_temperature, d_v_pos, d_G);
+        B2A_LAUNCH_OK();
+        return 0;
+    }
     dim3 grid(b2a_blocks(V, LBS_BLOCK), B);
     if (K <= LBS_CACHE_K) lbs_bwd_kernel<true><<<grid, LBS_BLOCK, 0, stream>>>(v_pos, bones, G, d_out, B, Bv, Bb, K, V, inv_temperature, d_v_pos, d_G);
     else lbs_bwd_kernel<false><<<grid, LBS_BLOCK, 0, stream>>>(v_pos, bones, G, d_out, B, Bv, Bb, K, V, inv_temperature, d_v_pos, d_G);

@@ -38,10 +38,10 @@ size_t mt_layout(int64_t Vg, int64_t E, int64_t T, void* base, MtWorkspace* ws)
     auto take = [&](size_t bytes) { size_t o = off; off += b2a_align(bytes); return p ? (void*)(p + o) : nullptr; };
     void* occ = take((size_t)((Vg + 31) / 32) * 4);
     void* vcnt = take((size_t)Vg);
-    void* vtile = take((size_t)nVT * 4);
+    void* vtile = take((size_t)(nVT + 1) * 4);
     void* tetidx = take((size_t)T);
-    void* t1 = take((size_t)nTT * 4);
-    void* t2 = take((size_t)nTT * 4);
+    void* t1 = take((size_t)(nTT + 1) * 4);
+    void* t2 = take((size_t)(nTT + 1) * 4);
     void* ev = take((size_t)E * 4);
     void* err = take(256);
     if (ws) {
@@ -54,13 +54,20 @@ size_t mt_layout(int64_t Vg, int64_t E, int64_t T, void* base, MtWorkspace* ws)
 
 __device__ __forceinline__ bool occ_at(const uint32_t* __restrict__ bits, int v) { return (__ldg(bits + (v >> 5)) >> (v & 31)) & 1u; }
 
-// occupancy bitmask: occ = sdf > 0  (dmtet.py:106)
+// occupancy bitmask: occ = sdf > 0  (dmtet.py:106).  Each warp packs four 32-vertex words (four loads in flight per lane).
 __global__ void __launch_bounds__(MT_BLOCK) mt_occ_kernel(const float* __restrict__ sdf, int64_t Vg, uint32_t* __restrict__ bits)
 {
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool o = v < Vg && __ldg(sdf + v) > 0.f;
-    uint32_t m = __ballot_sync(0xffffffffu, o);
-    if ((threadIdx.x & 31) == 0 && v < Vg) bits[v >> 5] = m;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t v0 = warp * 128 + lane;
+    float x[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) x[k] = v0 + k * 32 < Vg ? __ldg(sdf + v0 + k * 32) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t m = __ballot_sync(0xffffffffu, x[k] > 0.f);
+        if (lane == 0 && warp * 128 + k * 32 < Vg) bits[warp * 4 + k] = m;
+    }
 }
 
 // crossing edges per min-vertex + per-tile totals
@@ -78,86 +85,159 @@ __global__ void __launch_bounds__(MT_BLOCK) mt_vcount_kernel(const int* __restri
         if (cnt > 255) { atomicExch(err, 1); cnt = 255; }
         vcnt[a] = (uint8_t)cnt;
     }
-    int total;
-    block_exclusive_scan(cnt, sm, &total);
-    if (threadIdx.x == 0) vtile[blockIdx.x] = total;
+    // only the tile total is needed here
+    int wsum = warp_sum_i(cnt);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = wsum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int x = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0;
+        x = warp_sum_i(x);
+        if (threadIdx.x == 0) vtile[blockIdx.x] = x;
+    }
 }
 
-// tet case index + per-tile totals of 1-triangle and 2-triangle tets  (dmtet.py:107-109,135-137)
+// tet case index + per-tile totals of 1-triangle and 2-triangle tets  (dmtet.py:107-109,135-137).  A tile is MT_BLOCK
+// consecutive tets; a block streams MT_TPB tiles, four 16-byte tet loads in flight per thread; only the tile TOTALS are
+// needed here (warp ballots + one shared-memory atomic per warp), the ordered positions are recomputed by the emit
+// kernel for the few tiles that hold triangles.
+constexpr int MT_TPB = 4;
 __global__ void __launch_bounds__(MT_BLOCK) mt_tcount_kernel(const int4* __restrict__ tets, const uint32_t* __restrict__ bits,
                                                              int64_t T, uint8_t* __restrict__ tetidx, int* __restrict__ t1tile,
                                                              int* __restrict__ t2tile)
 {
-    __shared__ int sm[34];
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int n = 0;
-    if (t < T) {
-        int4 q = __ldg(tets + t);
-        int ti = (int)occ_at(bits, q.x) | ((int)occ_at(bits, q.y) << 1) | ((int)occ_at(bits, q.z) << 2) | ((int)occ_at(bits, q.w) << 3);
-        tetidx[t] = (uint8_t)ti;
-        n = c_num_tri[ti];
+    __shared__ int s_cnt[MT_TPB][2];
+    if (threadIdx.x < MT_TPB * 2) (&s_cnt[0][0])[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t tile0 = (int64_t)blockIdx.x * MT_TPB;
+    int4 q[MT_TPB];
+#pragma unroll
+    for (int k = 0; k < MT_TPB; k++) {
+        const int64_t t = (tile0 + k) * MT_BLOCK + threadIdx.x;
+        q[k] = t < T ? __ldg(tets + t) : make_int4(0, 0, 0, 0);
     }
-    int tot1, tot2;
-    block_exclusive_scan(n == 1, sm, &tot1);
-    block_exclusive_scan(n == 2, sm, &tot2);
-    if (threadIdx.x == 0) { t1tile[blockIdx.x] = tot1; t2tile[blockIdx.x] = tot2; }
+#pragma unroll
+    for (int k = 0; k < MT_TPB; k++) {
+        const int64_t t = (tile0 + k) * MT_BLOCK + threadIdx.x;
+        int n = 0;
+        if (t < T) {
+            int ti = (int)occ_at(bits, q[k].x) | ((int)occ_at(bits, q[k].y) << 1) | ((int)occ_at(bits, q[k].z) << 2) | ((int)occ_at(bits, q[k].w) << 3);
+            tetidx[t] = (uint8_t)ti;
+            n = c_num_tri[ti];
+        }
+        const unsigned m1 = __ballot_sync(0xffffffffu, n == 1), m2 = __ballot_sync(0xffffffffu, n == 2);
+        if ((threadIdx.x & 31) == 0) {
+            if (m1) atomicAdd(&s_cnt[k][0], __popc(m1));
+            if (m2) atomicAdd(&s_cnt[k][1], __popc(m2));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < MT_TPB && (tile0 + threadIdx.x) * MT_BLOCK < T) {
+        t1tile[tile0 + threadIdx.x] = s_cnt[threadIdx.x][0];
+        t2tile[tile0 + threadIdx.x] = s_cnt[threadIdx.x][1];
+    }
 }
 
-// One block per array: in-place exclusive scan of up to three tile-sum arrays; totals -> counts[which].
+// One block per array: in-place exclusive scan of up to three tile-sum arrays; totals -> counts[which].  Each warp owns
+// a contiguous segment and walks it in coalesced 32-element rows (pass 1: segment total; block scan of the 32 warp
+// totals; pass 2: shuffle scan per row with a running carry).  The array keeps one extra slot [n] = total so that tile
+// b's own count is data[b+1] - data[b].
 struct ScanJob { int* data; int64_t n; };
 __global__ void __launch_bounds__(1024) mt_scan_tiles_kernel(ScanJob j0, ScanJob j1, ScanJob j2, int* __restrict__ counts)
 {
-    __shared__ int sm[34];
-    __shared__ int carry_s;
+    __shared__ int s_warp[32];
     ScanJob j = blockIdx.x == 0 ? j0 : (blockIdx.x == 1 ? j1 : j2);
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int64_t base = 0; base < j.n; base += blockDim.x) {
-        int64_t i = base + threadIdx.x;
-        int v = i < j.n ? j.data[i] : 0;
-        int total;
-        int ex = block_exclusive_scan(v, sm, &total);
-        int carry = carry_s;
-        if (i < j.n) j.data[i] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + total;
-        __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t rows = (j.n + 31) / 32;
+    const int64_t rows_per_warp = (rows + 31) / 32;
+    const int64_t r0 = (int64_t)warp * rows_per_warp, r1 = min(r0 + rows_per_warp, rows);
+    int local = 0;
+#pragma unroll 4
+    for (int64_t r = r0; r < r1; r++) {
+        int64_t i = r * 32 + lane;
+        local += i < j.n ? j.data[i] : 0;
     }
-    if (threadIdx.x == 0) counts[blockIdx.x] = carry_s;
+    local = warp_sum_i(local);
+    if (lane == 0) s_warp[warp] = local;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane], inc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        s_warp[lane] = inc - w;
+        if (lane == 31) { j.data[j.n] = inc; counts[blockIdx.x] = inc; }
+    }
+    __syncthreads();
+    int carry = s_warp[warp];
+#pragma unroll 4
+    for (int64_t r = r0; r < r1; r++) {
+        int64_t i = r * 32 + lane;
+        int v = i < j.n ? j.data[i] : 0, inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (i < j.n) j.data[i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
 }
 
 // emit vertices: v = p_a*((-s_b)/den) + p_b*(s_a/den), den = s_a - s_b  (dmtet.py:124-131), unfused fp32 ops
 __global__ void __launch_bounds__(MT_BLOCK) mt_vemit_kernel(const float* __restrict__ pos, const float* __restrict__ sdf,
                                                             const int* __restrict__ edge_start, const int* __restrict__ edge_b,
                                                             const uint32_t* __restrict__ bits, const uint8_t* __restrict__ vcnt,
-                                                            const int* __restrict__ vtile, int64_t Vg, float* __restrict__ verts,
+                                                            const int* __restrict__ vtile, int64_t Vg, int64_t nVT, float* __restrict__ verts,
                                                             int* __restrict__ vert_edge, int* __restrict__ edge_vidx)
 {
     __shared__ int sm[34];
-    int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int cnt = a < Vg ? (int)vcnt[a] : 0;
-    int total;
-    int ex = block_exclusive_scan(cnt, sm, &total);
-    if (cnt == 0) return;
-    int out = vtile[blockIdx.x] + ex;
-    int s = __ldg(edge_start + a), e = __ldg(edge_start + a + 1);
-    bool oa = occ_at(bits, (int)a);
-    float sa = __ldg(sdf + a);
-    float ax = __ldg(pos + a * 3), ay = __ldg(pos + a * 3 + 1), az = __ldg(pos + a * 3 + 2);
-    for (int i = s; i < e; i++) {
-        int b = __ldg(edge_b + i);
-        if (occ_at(bits, b) == oa) continue;
-        float sb = -__ldg(sdf + b);
-        float den = sa + sb;
-        float wa = sb / den, wb = sa / den;
-        float bx = __ldg(pos + (int64_t)b * 3), by = __ldg(pos + (int64_t)b * 3 + 1), bz = __ldg(pos + (int64_t)b * 3 + 2);
-        verts[(int64_t)out * 3 + 0] = ax * wa + bx * wb;
-        verts[(int64_t)out * 3 + 1] = ay * wa + by * wb;
-        verts[(int64_t)out * 3 + 2] = az * wa + bz * wb;
-        vert_edge[(int64_t)out * 2 + 0] = (int)a;
-        vert_edge[(int64_t)out * 2 + 1] = b;
-        edge_vidx[i] = out;
-        out++;
+    __shared__ int s_list[MT_BLOCK];
+    __shared__ int s_n;
+    // Phase A: one thread per tile finds the tiles where a crossing edge
+    // starts (few: the surface) - one round of loads instead of a serial walk; phase B: emit those tiles.
+    // (tiles are dealt round-robin: the surface occupies a contiguous band of tiles, contiguous ranges would pile it
+    // onto a few blocks)
+    for (int64_t chunk = blockIdx.x; chunk < nVT; chunk += (int64_t)gridDim.x * MT_BLOCK) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    {
+        const int64_t tile = chunk + (int64_t)threadIdx.x * gridDim.x;
+        if (tile < nVT && vtile[tile + 1] != vtile[tile]) s_list[atomicAdd(&s_n, 1)] = (int)threadIdx.x;
+    }
+    __syncthreads();
+    const int n_live = s_n;
+    for (int li = 0; li < n_live; li++) {
+        const int64_t tile = chunk + (int64_t)s_list[li] * gridDim.x;
+        const int tile_base = vtile[tile];
+        int64_t a = tile * blockDim.x + threadIdx.x;
+        int cnt = a < Vg ? (int)vcnt[a] : 0;
+        int total;
+        int ex = block_exclusive_scan(cnt, sm, &total);
+        if (cnt == 0) continue;
+        int out = tile_base + ex;
+        int s = __ldg(edge_start + a), e = __ldg(edge_start + a + 1);
+        bool oa = occ_at(bits, (int)a);
+        float sa = __ldg(sdf + a);
+        float ax = __ldg(pos + a * 3), ay = __ldg(pos + a * 3 + 1), az = __ldg(pos + a * 3 + 2);
+        for (int i = s; i < e; i++) {
+            int b = __ldg(edge_b + i);
+            if (occ_at(bits, b) == oa) continue;
+            float sb = -__ldg(sdf + b);
+            float den = sa + sb;
+            float wa = sb / den, wb = sa / den;
+            float bx = __ldg(pos + (int64_t)b * 3), by = __ldg(pos + (int64_t)b * 3 + 1), bz = __ldg(pos + (int64_t)b * 3 + 2);
+            verts[(int64_t)out * 3 + 0] = ax * wa + bx * wb;
+            verts[(int64_t)out * 3 + 1] = ay * wa + by * wb;
+            verts[(int64_t)out * 3 + 2] = az * wa + bz * wb;
+            vert_edge[(int64_t)out * 2 + 0] = (int)a;
+            vert_edge[(int64_t)out * 2 + 1] = b;
+            edge_vidx[i] = out;
+            out++;
+        }
+    }
+    __syncthreads();
     }
 }
 
@@ -175,36 +255,57 @@ __device__ __forceinline__ int find_edge_vertex(const int* __restrict__ edge_sta
 __global__ void __launch_bounds__(MT_BLOCK) mt_temit_kernel(const int4* __restrict__ tets, const uint8_t* __restrict__ tetidx,
                                                             const int* __restrict__ t1tile, const int* __restrict__ t2tile,
                                                             const int* __restrict__ edge_start, const int* __restrict__ edge_b,
-                                                            const int* __restrict__ edge_vidx, int64_t T, int64_t N1,
+                                                            const int* __restrict__ edge_vidx, int64_t T, int64_t nTT, int64_t N1,
                                                             int* __restrict__ faces32, long long* __restrict__ faces64,
                                                             long long* __restrict__ uv64)
 {
     __shared__ int sm[34];
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int ti = t < T ? (int)tetidx[t] : 0;
-    int n = c_num_tri[ti];
-    int tot;
-    int e1 = block_exclusive_scan(n == 1, sm, &tot);
-    int e2 = block_exclusive_scan(n == 2, sm, &tot);
-    if (n == 0) return;
-    int64_t fbase = n == 1 ? (int64_t)t1tile[blockIdx.x] + e1 : N1 + 2 * ((int64_t)t2tile[blockIdx.x] + e2);
-    int4 q = __ldg(tets + t);
-    int tv[4] = {q.x, q.y, q.z, q.w};
-    for (int k = 0; k < n; k++) {
-        int64_t f = fbase + k;
+    __shared__ int s_list[MT_BLOCK];
+    __shared__ int s_n;
+    // Phase A: one thread per tile finds the tiles that hold surface
+    // (few) - one round of loads instead of a serial walk; phase B: emit those tiles.
+    // (tiles are dealt round-robin: the surface occupies a contiguous band of tiles, contiguous ranges would pile it
+    // onto a few blocks)
+    for (int64_t chunk = blockIdx.x; chunk < nTT; chunk += (int64_t)gridDim.x * MT_BLOCK) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    {
+        const int64_t tile = chunk + (int64_t)threadIdx.x * gridDim.x;
+        if (tile < nTT && (t1tile[tile + 1] != t1tile[tile] || t2tile[tile + 1] != t2tile[tile])) s_list[atomicAdd(&s_n, 1)] = (int)threadIdx.x;
+    }
+    __syncthreads();
+    const int n_live = s_n;
+    for (int li = 0; li < n_live; li++) {
+        const int64_t tile = chunk + (int64_t)s_list[li] * gridDim.x;
+        const int base1 = t1tile[tile], base2 = t2tile[tile];
+        int64_t t = tile * blockDim.x + threadIdx.x;
+        int ti = t < T ? (int)tetidx[t] : 0;
+        int n = c_num_tri[ti];
+        int tot;
+        int ex = block_exclusive_scan((int)(n == 1) | ((int)(n == 2) << 16), sm, &tot);   // both counts in one scan (MT_BLOCK < 2^16)
+        int e1 = ex & 0xffff, e2 = ex >> 16;
+        if (n == 0) continue;
+        int64_t fbase = n == 1 ? (int64_t)base1 + e1 : N1 + 2 * ((int64_t)base2 + e2);
+        int4 q = __ldg(tets + t);
+        int tv[4] = {q.x, q.y, q.z, q.w};
+        for (int k = 0; k < n; k++) {
+            int64_t f = fbase + k;
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            int le = c_tri_table[ti][k * 3 + c];
-            int vid = find_edge_vertex(edge_start, edge_b, edge_vidx, tv[c_base_edges[le * 2]], tv[c_base_edges[le * 2 + 1]]);
-            if (faces32) faces32[f * 3 + c] = vid;
-            if (faces64) faces64[f * 3 + c] = vid;
+            for (int c = 0; c < 3; c++) {
+                int le = c_tri_table[ti][k * 3 + c];
+                int vid = find_edge_vertex(edge_start, edge_b, edge_vidx, tv[c_base_edges[le * 2]], tv[c_base_edges[le * 2 + 1]]);
+                if (faces32) faces32[f * 3 + c] = vid;
+                if (faces64) faces64[f * 3 + c] = vid;
+            }
+            if (uv64) {
+                long long g = (long long)t * 4;
+                uv64[f * 3 + 0] = g;
+                uv64[f * 3 + 1] = g + k + 1;
+                uv64[f * 3 + 2] = g + k + 2;
+            }
         }
-        if (uv64) {
-            long long g = (long long)t * 4;
-            uv64[f * 3 + 0] = g;
-            uv64[f * 3 + 1] = g + k + 1;
-            uv64[f * 3 + 2] = g + k + 2;
-        }
+    }
+    __syncthreads();
     }
 }
 
@@ -251,9 +352,9 @@ B2A_API int b2a_mt_count(const float* sdf, const int32_t* tets, const int32_t* e
     MtWorkspace ws;
     B2A_CHECK_ARG(mt_layout(Vg, E, T, workspace, &ws) <= workspace_bytes, "workspace too small");
     B2A_CUDA_OK(cudaMemsetAsync(ws.err, 0, 4, stream));
-    mt_occ_kernel<<<b2a_blocks(Vg, MT_BLOCK), MT_BLOCK, 0, stream>>>(sdf, Vg, ws.occ_bits);
+    mt_occ_kernel<<<b2a_blocks(Vg, MT_BLOCK * 4), MT_BLOCK, 0, stream>>>(sdf, Vg, ws.occ_bits);
     mt_vcount_kernel<<<(unsigned)ws.nVT, MT_BLOCK, 0, stream>>>(edge_start, edge_b, ws.occ_bits, Vg, ws.vcnt, ws.vtile, ws.err);
-    mt_tcount_kernel<<<(unsigned)ws.nTT, MT_BLOCK, 0, stream>>>((const int4*)tets, ws.occ_bits, T, ws.tetidx, ws.t1tile, ws.t2tile);
+    mt_tcount_kernel<<<(unsigned)((ws.nTT + MT_TPB - 1) / MT_TPB), MT_BLOCK, 0, stream>>>((const int4*)tets, ws.occ_bits, T, ws.tetidx, ws.t1tile, ws.t2tile);
     ScanJob j0{ws.vtile, ws.nVT}, j1{ws.t1tile, ws.nTT}, j2{ws.t2tile, ws.nTT};
     mt_scan_tiles_kernel<<<3, 1024, 0, stream>>>(j0, j1, j2, counts);
     B2A_CUDA_OK(cudaMemcpyAsync(counts + 3, ws.err, 4, cudaMemcpyDeviceToDevice, stream));
@@ -272,13 +373,13 @@ B2A_API int b2a_mt_emit(const float* pos, const float* sdf, const int32_t* tets,
     B2A_CHECK_ARG(mt_layout(Vg, E, T, workspace, &ws) <= workspace_bytes, "workspace too small");
     if (V > 0) {
         B2A_CHECK_ARG(verts && vert_edge, "null vertex outputs");
-        mt_vemit_kernel<<<(unsigned)ws.nVT, MT_BLOCK, 0, stream>>>(pos, sdf, edge_start, edge_b, ws.occ_bits, ws.vcnt, ws.vtile,
-                                                                    Vg, verts, vert_edge, ws.edge_vidx);
+        mt_vemit_kernel<<<(unsigned)min((int64_t)148 * 4, ws.nVT), MT_BLOCK, 0, stream>>>(pos, sdf, edge_start, edge_b, ws.occ_bits, ws.vcnt,
+                                                                                          ws.vtile, Vg, ws.nVT, verts, vert_edge, ws.edge_vidx);
     }
     if (N1 + N2 > 0 && (faces_i32 || faces_i64 || uv_idx_i64))
-        mt_temit_kernel<<<(unsigned)ws.nTT, MT_BLOCK, 0, stream>>>((const int4*)tets, ws.tetidx, ws.t1tile, ws.t2tile, edge_start,
-                                                                    edge_b, ws.edge_vidx, T, N1, faces_i32,
-                                                                    (long long*)faces_i64, (long long*)uv_idx_i64);
+        mt_temit_kernel<<<(unsigned)min((int64_t)148 * 4, ws.nTT), MT_BLOCK, 0, stream>>>((const int4*)tets, ws.tetidx, ws.t1tile, ws.t2tile,
+                                                                                          edge_start, edge_b, ws.edge_vidx, T, ws.nTT, N1, faces_i32,
+                                                                                          (long long*)faces_i64, (long long*)uv_idx_i64);
     B2A_LAUNCH_OK();
     return 0;
 }

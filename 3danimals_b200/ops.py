@@ -55,7 +55,7 @@ KERNELS_PER_CALL = {
     "b2a_mt_count": 4, "b2a_mt_emit": 2, "b2a_mt_bwd": 1, "b2a_estimate_bones": 4, "b2a_lbs_bone_transforms": 2, "b2a_lbs_fwd": 1, "b2a_lbs_bwd": 1,
     "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1,
     "b2a_xfm_points_bwd": 1, "b2a_rasterize_fwd": 3, "b2a_rasterize_bwd": 1, "b2a_interpolate_fwd": 1, "b2a_interpolate_bwd": 1,
-    "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 1, "b2a_gbuffer_fwd": 1, "b2a_gbuffer_bwd": 2,
+    "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 2, "b2a_gbuffer_fwd": 1, "b2a_gbuffer_bwd": 2,
 }
 
 
@@ -67,6 +67,7 @@ class CallStats:
         self.launches = 0
         self.calls = {}
         self.timing = False
+        self.spin_cycles = 0  # device busy-wait enqueued before each timed call (see _call)
         self.events = []      # (name, tag, start_event, end_event)
         self.tag = ""
 
@@ -92,6 +93,10 @@ def _call(name, args, tag=None, launches=None):
     if stats.timing:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
+        if stats.spin_cycles:
+            # keep the stream busy while the host enqueues (event, launches, event): otherwise, in a host-bound step,
+            # the start event fires on an idle GPU and the host's enqueue latency is billed to the kernel
+            torch.cuda._sleep(stats.spin_cycles)
         e0.record()
         rc = fn(*args)
         e1.record()
@@ -482,7 +487,8 @@ class _Antialias(torch.autograd.Function):
         sb, sy, sx, sc = g.stride()
         _call("b2a_antialias_bwd", (_p(color), _p(bg), Bg, int(composite), _p(rast), _p(pos), _p(tri), _p(opp), _p(g), sb, sy, sx,
                                           sc, keep, B, pos.shape[1], tri.shape[0], H, W, Cc, _p(d_color), _p(d_pos), _p(aa_ctx),
-                                          0 if aa_ctx is None else aa_ctx.numel(), _stream()), tag="C%d" % Cc)
+                                          0 if aa_ctx is None else aa_ctx.numel(), _stream()), tag="C%d" % Cc,
+              launches=1)
         return d_color, None, None, d_pos, None, None, None, None, None
 
 
