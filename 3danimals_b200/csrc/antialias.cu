@@ -585,7 +585,7 @@ constexpr int AA_POS_BLOCKS = 148 * 4;
 
 // vertex-position gradient role: one half-warp per owned pair of an active pixel, channels across the 16 lanes.  All
 // geometry was folded into per-pair coefficients by aa_pairs_kernel, so this is a short gather + six atomics and costs
-// the streaming kernel no registers; it runs in the LAST blocks of the same launch.
+// the streaming kernel no registers; it runs in the FIRST blocks of the same launch.
 template <int C>
 __device__ __forceinline__ void aa_bwd_pos_role(const AAParams& P, const AAGrad& G, const AAContext& ctx, float* __restrict__ d_pos, int role_block)
 {
@@ -628,19 +628,19 @@ __device__ __forceinline__ void aa_bwd_pos_role(const AAParams& P, const AAGrad&
 // gather their pair terms in place, then masked float4 stores.
 template <int C, int CC, int CG, bool NCHW, int TPW>
 __global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_bwd_tile_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
-                                                                            float* __restrict__ d_pos, int tile_blocks)
+                                                                            float* __restrict__ d_pos, int pos_blocks)
 {
     constexpr int ST = CG + 1;   // padded pixel stride: conflict-free for both access patterns
     constexpr int NV = NCHW ? CC : (8 * CG + 31) / 32;   // registers per lane per tile: scalars (NCHW) or float4s (NHWC)
     __shared__ float s_tile[8][32 * ST];
-    if ((int)blockIdx.x >= tile_blocks) {
-        aa_bwd_pos_role<C>(P, G, ctx, d_pos, (int)blockIdx.x - tile_blocks);
+    if ((int)blockIdx.x < pos_blocks) {   // first in the grid: their latency chains overlap the streaming blocks
+        aa_bwd_pos_role<C>(P, G, ctx, d_pos, (int)blockIdx.x);
         return;
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int HW = P.H * P.W;
     const int64_t ntiles = ((int64_t)P.B * HW) / 32;
-    const int64_t t0 = ((int64_t)blockIdx.x * 8 + w) * TPW;
+    const int64_t t0 = ((int64_t)(blockIdx.x - pos_blocks) * 8 + w) * TPW;
     if (t0 >= ntiles) return;
     float* tile = s_tile[w];
     uint32_t cov[TPW], act[TPW];
@@ -739,6 +739,106 @@ __global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_bwd_tile_kernel(AAPa
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Narrow keys (C <= 4: shaded RGBA, shading, flow, depth): one thread per PIXEL, no shared memory, ~24 registers ->
+// full occupancy.  The warp-tile kernels above pay a fixed per-tile latency chain that only amortises over wide rows.
+// ------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) aa_fwd_pix_kernel(const float* __restrict__ color, const float* __restrict__ bg, int Bg, AAContext ctx,
+                                                         int B, int H, int W, float* __restrict__ out)
+{
+    constexpr int CI = C - 1;
+    const int HW = H * W;
+    const int64_t flat = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (flat >= (int64_t)B * HW) return;
+    const int b = (int)(flat / HW);
+    const uint32_t cw = __ldg(ctx.cover + (flat >> 5)), aw = __ldg(ctx.act + (flat >> 5));
+    const bool covered = (cw >> (flat & 31)) & 1u, active = (aw >> (flat & 31)) & 1u;
+    float v[C];
+    if (covered) {
+#pragma unroll
+        for (int c = 0; c < CI; c++) v[c] = __ldg(color + flat * CI + c);
+        v[CI] = 1.f;
+    } else {
+        const float* bp = bg ? bg + (Bg == 1 ? flat - (int64_t)b * HW : flat) * C : nullptr;
+#pragma unroll
+        for (int c = 0; c < C; c++) v[c] = bp ? __ldg(bp + c) : 0.f;
+    }
+    if (active) {
+        const float4 a = __ldg(ctx.rec + flat);
+        const bool k0 = a.x < 0.f, k1 = a.y < 0.f, k2 = a.z > 0.f, k3 = a.w > 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const float own = v[c];
+            const float cu = k0 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - W, c) : own;
+            const float cl = k1 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - 1, c) : own;
+            const float cr = k2 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + 1, c) : own;
+            const float cd = k3 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + W, c) : own;
+            float acc = own;
+            if (k0) acc += a.x * (own - cu);
+            if (k1) acc += a.y * (own - cl);
+            if (k2) acc += a.z * (cr - own);
+            if (k3) acc += a.w * (cd - own);
+            v[c] = acc;
+        }
+    }
+    float* o = out + flat * C;
+    if (C == 4) reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[C - 1]);
+    else if (C == 2) reinterpret_cast<float2*>(o)[0] = make_float2(v[0], v[C - 1]);
+    else {
+#pragma unroll
+        for (int c = 0; c < C; c++) o[c] = v[c];
+    }
+}
+
+template <int C, int CC, int CG>
+__global__ void __launch_bounds__(256, 6) aa_bwd_pix_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
+                                                         float* __restrict__ d_pos, int pos_blocks)
+{
+    if ((int)blockIdx.x < pos_blocks) {
+        aa_bwd_pos_role<C>(P, G, ctx, d_pos, (int)blockIdx.x);
+        return;
+    }
+    const int HW = P.H * P.W;
+    const int64_t flat = (int64_t)(blockIdx.x - pos_blocks) * blockDim.x + threadIdx.x;
+    if (flat >= (int64_t)P.B * HW) return;
+    const int b = (int)(flat / HW), p = (int)(flat - (int64_t)b * HW);
+    const uint32_t cw = __ldg(ctx.cover + (flat >> 5)), aw = __ldg(ctx.act + (flat >> 5));
+    const bool covered = (cw >> (flat & 31)) & 1u, active = covered && ((aw >> (flat & 31)) & 1u);
+    float v[CC];
+#pragma unroll
+    for (int c = 0; c < CC; c++) v[c] = 0.f;
+    if (covered) {
+        const int py = p / P.W, px = p - py * P.W;
+        const float* gp = G.d_out + (int64_t)b * G.sb + (int64_t)py * G.sy + (int64_t)px * G.sx;
+#pragma unroll
+        for (int c = 0; c < CC; c++) v[c] = __ldg(gp + (int64_t)c * G.sc);
+        if (active) {
+            const float4 a = __ldg(ctx.rec + flat);
+#pragma unroll
+            for (int c = 0; c < CC; c++) {
+                const float own = v[c];
+                const float gu = a.x != 0.f ? (a.x > 0.f ? grad_at(G, P.W, b, p - P.W, c) : own) : 0.f;
+                const float gl = a.y != 0.f ? (a.y > 0.f ? grad_at(G, P.W, b, p - 1, c) : own) : 0.f;
+                const float gr = a.z != 0.f ? (a.z > 0.f ? own : grad_at(G, P.W, b, p + 1, c)) : 0.f;
+                const float gd = a.w != 0.f ? (a.w > 0.f ? own : grad_at(G, P.W, b, p + P.W, c)) : 0.f;
+                float acc = own;
+                if (a.x != 0.f) acc += a.x * gu;
+                if (a.y != 0.f) acc += a.y * gl;
+                if (a.z != 0.f) acc -= a.z * gr;
+                if (a.w != 0.f) acc -= a.w * gd;
+                v[c] = acc;
+            }
+        }
+    }
+    float* o = d_color + flat * CC;
+    if (CC == 2) reinterpret_cast<float2*>(o)[0] = make_float2(v[0], v[CC - 1]);
+    else {
+#pragma unroll
+        for (int c = 0; c < CC; c++) o[c] = v[c];
+    }
+}
+
 int aa_check(const float* color, const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, int Bg, int composite, int B,
              int64_t V, int64_t F, int H, int W, int C)
 {
@@ -823,6 +923,10 @@ bool aa_fast_ok(int composite, const void* aa_ctx, size_t aa_ctx_bytes, int B, i
 template <int C>
 void aa_fwd_tile(const float* color, const float* bg, int Bg, const AAContext& ctx, int B, int H, int W, float* out, cudaStream_t stream)
 {
+    if constexpr (C <= 4) {   // narrow keys: one thread per pixel
+        aa_fwd_pix_kernel<C><<<b2a_blocks((int64_t)B * H * W, 256), 256, 0, stream>>>(color, bg, Bg, ctx, B, H, W, out);
+        return;
+    }
     constexpr int TPW = C >= 9 ? 1 : 4;
     unsigned tiles = (unsigned)(((int64_t)B * H * W) / 32);
     aa_fwd_tile_kernel<C, TPW><<<b2a_blocks(tiles, 8 * TPW), 256, 0, stream>>>(color, bg, Bg, ctx, B, H, W, out);
@@ -858,15 +962,21 @@ namespace {
 template <int C, int CC, int CG>
 bool aa_bwd_tile(const AAParams& P, const AAGrad& G, const AAContext& ctx, float* d_color, float* d_pos, cudaStream_t stream)
 {
+    const int pos_blocks = d_pos ? AA_POS_BLOCKS : 0;
+    if constexpr (CC <= 4) {   // narrow keys: one thread per pixel, any gradient strides
+        unsigned grid = b2a_blocks((int64_t)P.B * P.H * P.W, 256) + pos_blocks;
+        aa_bwd_pix_kernel<C, CC, CG><<<grid, 256, 0, stream>>>(P, G, ctx, d_color, d_pos, pos_blocks);
+        return true;
+    }
     constexpr int TPW = CC >= 8 ? 1 : 4;   // tiles per warp: keep >= ~12 loads in flight per lane
     unsigned tiles = (unsigned)(((int64_t)P.B * P.H * P.W) / 32);
     unsigned grid = b2a_blocks(tiles, 8 * TPW);
     const bool nhwc = G.sc == 1 && G.sx == CG && G.sy == (int64_t)P.W * CG && G.sb % 4 == 0 && aligned16(G.d_out);
     const bool nchw = G.sx == 1 && P.W % 32 == 0;
     if (!nhwc && !nchw) return false;
-    const unsigned total = grid + (d_pos ? AA_POS_BLOCKS : 0);
-    if (nhwc) aa_bwd_tile_kernel<C, CC, CG, false, TPW><<<total, 256, 0, stream>>>(P, G, ctx, d_color, d_pos, (int)grid);
-    else aa_bwd_tile_kernel<C, CC, CG, true, TPW><<<total, 256, 0, stream>>>(P, G, ctx, d_color, d_pos, (int)grid);
+    const unsigned total = grid + pos_blocks;
+    if (nhwc) aa_bwd_tile_kernel<C, CC, CG, false, TPW><<<total, 256, 0, stream>>>(P, G, ctx, d_color, d_pos, pos_blocks);
+    else aa_bwd_tile_kernel<C, CC, CG, true, TPW><<<total, 256, 0, stream>>>(P, G, ctx, d_color, d_pos, pos_blocks);
     return true;
 }
 }  // namespace

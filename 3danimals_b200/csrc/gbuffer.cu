@@ -23,6 +23,8 @@ struct GbParams {
     const float* campos;
     int spp, Bq, two_sided, B, H, W;
     int64_t V, F;
+    const float4* pn;   // packed (P.xyz, N.x | N.y, N.z, -, -) [B,V,2] or NULL: vertex attributes as 16-byte gathers
+    const float4* q4;   // packed prior positions [Bq,V] (xyz, -) or NULL
 };
 
 struct V3 { float x, y, z; };
@@ -79,16 +81,29 @@ struct GbPixel {  // forward intermediates of one covered pixel
     bool front;
 };
 
+// f >= 0: vertex ids come from the triangle table; f < 0: the caller already set g.i0..i2 (covered-pixel list entry)
 __device__ __forceinline__ void gb_forward(const GbParams& P, int b, int f, float u, float v, GbPixel& g)
 {
     g.u = u; g.v = v; g.w = 1.f - u - v;
-    g.i0 = __ldg(P.tri + (size_t)f * 3); g.i1 = __ldg(P.tri + (size_t)f * 3 + 1); g.i2 = __ldg(P.tri + (size_t)f * 3 + 2);
+    if (f >= 0) { g.i0 = __ldg(P.tri + (size_t)f * 3); g.i1 = __ldg(P.tri + (size_t)f * 3 + 1); g.i2 = __ldg(P.tri + (size_t)f * 3 + 2); }
     const float* vp = P.v_pos + (size_t)b * P.V * 3;
     const float* vn = P.v_nrm + (size_t)b * P.V * 3;
     const float* vq = P.prior + (size_t)(P.Bq == 1 ? 0 : b) * P.V * 3;
-    g.P0 = ld3(vp + (size_t)g.i0 * 3); g.P1 = ld3(vp + (size_t)g.i1 * 3); g.P2 = ld3(vp + (size_t)g.i2 * 3);
-    g.N0 = ld3(vn + (size_t)g.i0 * 3); g.N1 = ld3(vn + (size_t)g.i1 * 3); g.N2 = ld3(vn + (size_t)g.i2 * 3);
-    g.Q0 = ld3(vq + (size_t)g.i0 * 3); g.Q1 = ld3(vq + (size_t)g.i1 * 3); g.Q2 = ld3(vq + (size_t)g.i2 * 3);
+    if (P.pn) {
+        // the gather is bound by L1 wavefronts per instruction, not bytes: 9 x 16-byte loads instead of 27 scalar ones
+        const float4* pn = P.pn + (size_t)b * P.V * 2;
+        const float4* q4 = P.q4 + (size_t)(P.Bq == 1 ? 0 : b) * P.V;
+        float4 a0 = __ldg(pn + (size_t)g.i0 * 2), b0 = __ldg(pn + (size_t)g.i0 * 2 + 1), c0 = __ldg(q4 + g.i0);
+        float4 a1 = __ldg(pn + (size_t)g.i1 * 2), b1 = __ldg(pn + (size_t)g.i1 * 2 + 1), c1 = __ldg(q4 + g.i1);
+        float4 a2 = __ldg(pn + (size_t)g.i2 * 2), b2 = __ldg(pn + (size_t)g.i2 * 2 + 1), c2 = __ldg(q4 + g.i2);
+        g.P0 = V3{a0.x, a0.y, a0.z}; g.N0 = V3{a0.w, b0.x, b0.y}; g.Q0 = V3{c0.x, c0.y, c0.z};
+        g.P1 = V3{a1.x, a1.y, a1.z}; g.N1 = V3{a1.w, b1.x, b1.y}; g.Q1 = V3{c1.x, c1.y, c1.z};
+        g.P2 = V3{a2.x, a2.y, a2.z}; g.N2 = V3{a2.w, b2.x, b2.y}; g.Q2 = V3{c2.x, c2.y, c2.z};
+    } else {
+        g.P0 = ld3(vp + (size_t)g.i0 * 3); g.P1 = ld3(vp + (size_t)g.i1 * 3); g.P2 = ld3(vp + (size_t)g.i2 * 3);
+        g.N0 = ld3(vn + (size_t)g.i0 * 3); g.N1 = ld3(vn + (size_t)g.i1 * 3); g.N2 = ld3(vn + (size_t)g.i2 * 3);
+        g.Q0 = ld3(vq + (size_t)g.i0 * 3); g.Q1 = ld3(vq + (size_t)g.i1 * 3); g.Q2 = ld3(vq + (size_t)g.i2 * 3);
+    }
     g.gpos = bary(g.P0, g.P1, g.P2, g.u, g.v, g.w);
     g.n = cross3(g.P1 - g.P0, g.P2 - g.P0);
     g.fn = snormalize(g.n, g.nlen);
@@ -113,6 +128,22 @@ __device__ __forceinline__ void gb_forward(const GbParams& P, int b, int f, floa
                (g.out.x * __ldg(m + 4) + g.out.y * __ldg(m + 5)) + g.out.z * __ldg(m + 6),
                (g.out.x * __ldg(m + 8) + g.out.y * __ldg(m + 9)) + g.out.z * __ldg(m + 10)};
     g.cn = snormalize(g.cam, g.lc);
+}
+
+// vertex attributes -> 16-byte records (see GbParams::pn / q4); one thread per (image, vertex)
+__global__ void __launch_bounds__(256) gb_pack_kernel(const float* __restrict__ v_pos, const float* __restrict__ v_nrm,
+                                                      const float* __restrict__ prior, int B, int Bq, int64_t V, float4* __restrict__ pn,
+                                                      float4* __restrict__ q4)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * V) return;
+    V3 p = ld3(v_pos + i * 3), n = ld3(v_nrm + i * 3);
+    pn[i * 2] = make_float4(p.x, p.y, p.z, n.x);
+    pn[i * 2 + 1] = make_float4(n.y, n.z, 0.f, 0.f);
+    if (i < (int64_t)Bq * V) {
+        V3 q = ld3(prior + i * 3);
+        q4[i] = make_float4(q.x, q.y, q.z, 0.f);
+    }
 }
 
 __global__ void __launch_bounds__(256) gb_fwd_kernel(GbParams P, float* __restrict__ gb_pos, float* __restrict__ gb_geo,
@@ -154,8 +185,8 @@ __device__ __forceinline__ void red4(float* p, float x, float y, float z, float 
 
 // LIST: threads walk the compact covered-pixel list written by the rasterizer (dense warps; DMTet renders cover ~20 %
 // of the image); otherwise one thread per pixel of the [B,H,W] grid (spp > 1 or no list).
-template <bool LIST>
-__global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float* __restrict__ pos_clip, const int* __restrict__ cov_list,
+template <bool LIST, bool CAMGRAD>
+__global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float* __restrict__ pos_clip, const int4* __restrict__ cov_list,
                                                      const int* __restrict__ cov_count, const float* __restrict__ d_gb_pos,
                                                      const float* __restrict__ d_gb_geo, const float* __restrict__ d_gb_shn,
                                                      const float* __restrict__ d_gb_cam, const float* __restrict__ d_gb_tex,
@@ -170,18 +201,22 @@ __global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float*
         bool active = idx < total;
         int b = 0, ip = 0, px = 0, py = 0, f = -1;
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        GbPixel g;
         if (active) {
-            const int64_t flat = LIST ? (int64_t)__ldg(cov_list + idx) : idx;
+            int64_t flat = idx;
+            if (LIST) {   // 16-byte entry: pixel + vertex ids, so the vertex gathers do not wait for rast -> tri
+                const int4 e = __ldg(cov_list + idx);
+                flat = e.x; g.i0 = e.y; g.i1 = e.z; g.i2 = e.w;
+            }
             b = (int)(flat / HW); ip = (int)(flat - (int64_t)b * HW);
             px = ip % P.W; py = ip / P.W;
             size_t ri = ((size_t)b * P.H * P.spp + (size_t)py * P.spp) * ((size_t)P.W * P.spp) + (size_t)px * P.spp;
             r = ldg4(P.rast + ri * 4);
             f = (int)r.w - 1;
-            active = f >= 0 && f < P.F;
+            active = LIST || (f >= 0 && f < P.F);
         }
         V3 zero{0.f, 0.f, 0.f};
         V3 d_cam = zero, d_vv = zero;
-        GbPixel g;
         g.out = zero;
         if (active) {
             size_t po = ((size_t)b * HW + ip) * 3;
@@ -190,7 +225,13 @@ __global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float*
             V3 g_shn = d_gb_shn ? ld3(d_gb_shn + po) : zero;
             V3 g_cn = d_gb_cam ? ld3(d_gb_cam + po) : zero;
             V3 g_tex = d_gb_tex ? ld3(d_gb_tex + po) : zero;
-            gb_forward(P, b, f, r.x, r.y, g);
+            // clip-space positions: fetched up front with the other vertex attributes (one latency level, not a second)
+            float4 p0 = make_float4(0.f, 0.f, 0.f, 1.f), p1 = p0, p2 = p0;
+            if (LIST && pos_clip) {
+                const float* pb = pos_clip + (size_t)b * P.V * 4;
+                p0 = ldg4(pb + (size_t)g.i0 * 4); p1 = ldg4(pb + (size_t)g.i1 * 4); p2 = ldg4(pb + (size_t)g.i2 * 4);
+            }
+            gb_forward(P, b, LIST ? -1 : f, r.x, r.y, g);
             // camera-space normal
             d_cam = snormalize_bwd(g.cam, g.cn, g.lc, g_cn);
             const float* m = P.w2c + (size_t)b * 16;
@@ -223,8 +264,10 @@ __global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float*
             float du = (dot3(d_gpos, g.P0 - g.P2) + dot3(d_gnrm, g.N0 - g.N2)) + dot3(g_tex, g.Q0 - g.Q2);
             float dv = (dot3(d_gpos, g.P1 - g.P2) + dot3(d_gnrm, g.N1 - g.N2)) + dot3(g_tex, g.Q1 - g.Q2);
             if (pos_clip && (du != 0.f || dv != 0.f)) {
-                const float* pb = pos_clip + (size_t)b * P.V * 4;
-                float4 p0 = ldg4(pb + (size_t)g.i0 * 4), p1 = ldg4(pb + (size_t)g.i1 * 4), p2 = ldg4(pb + (size_t)g.i2 * 4);
+                if (!LIST) {
+                    const float* pb = pos_clip + (size_t)b * P.V * 4;
+                    p0 = ldg4(pb + (size_t)g.i0 * 4); p1 = ldg4(pb + (size_t)g.i1 * 4); p2 = ldg4(pb + (size_t)g.i2 * 4);
+                }
                 float fx, fy;
                 pixel_ndc(px * P.spp, py * P.spp, P.H * P.spp, P.W * P.spp, fx, fy);
                 float q0x = p0.x - fx * p0.w, q0y = p0.y - fy * p0.w;
@@ -249,7 +292,7 @@ __global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float*
             red4(a2p, dp2.x, dp2.y, dp2.z, c2w); red4(a2p + 4, d_gnrm.x * g.w, d_gnrm.y * g.w, d_gnrm.z * g.w, c2x); red4(a2p + 8, g_tex.x * g.w, g_tex.y * g.w, g_tex.z * g.w, c2y);
         }
         // camera gradients: d_w2c[i][j] += d_cam[i] out[j] ; d_campos += d_vv  (warp-reduced when the warp is in one image)
-        if (d_w2c || d_campos) {
+        if (CAMGRAD && (d_w2c || d_campos)) {
             const unsigned am = __ballot_sync(0xffffffffu, active);
             if (am) {
                 const int b0 = __shfl_sync(0xffffffffu, b, __ffs(am) - 1);
@@ -275,7 +318,7 @@ __global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float*
 
 // accumulator rows -> gradient tensors (each nullable).  Block = 32 vertices x 8 image lanes; d_prior sums over the batch
 // (Bq == 1) in a fixed order: per-lane partial sums over b = ty, ty+8, ..., then a fixed 8-term sum through smem.
-__global__ void __launch_bounds__(256) gb_bwd_finalize_kernel(const float* __restrict__ acc, int B, int Bq, int64_t V, float* __restrict__ d_v_pos,
+__global__ void __launch_bounds__(256) gb_bwd_finalize_kernel(float* __restrict__ acc, int rezero, int B, int Bq, int64_t V, float* __restrict__ d_v_pos,
                                                               float* __restrict__ d_v_nrm, float* __restrict__ d_prior, float* __restrict__ d_clip)
 {
     __shared__ float s_q[8][32][3];
@@ -283,16 +326,33 @@ __global__ void __launch_bounds__(256) gb_bwd_finalize_kernel(const float* __res
     const int64_t v = (int64_t)blockIdx.x * 32 + tx;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (v < V) {
-        for (int b = ty; b < B; b += 8) {
-            const float4* a = reinterpret_cast<const float4*>(acc + ((size_t)b * V + v) * 12);
-            float4 a0 = __ldg(a), a1 = __ldg(a + 1), a2 = __ldg(a + 2);
-            size_t o = ((size_t)b * V + v) * 3;
-            if (d_v_pos) { d_v_pos[o] = a0.x; d_v_pos[o + 1] = a0.y; d_v_pos[o + 2] = a0.z; }
-            if (d_v_nrm) { d_v_nrm[o] = a1.x; d_v_nrm[o + 1] = a1.y; d_v_nrm[o + 2] = a1.z; }
-            if (d_clip) reinterpret_cast<float4*>(d_clip)[(size_t)b * V + v] = make_float4(a1.w, a2.w, 0.f, a0.w);
-            if (d_prior) {
-                if (Bq == 1) { qx += a2.x; qy += a2.y; qz += a2.z; }
-                else { d_prior[o] = a2.x; d_prior[o + 1] = a2.y; d_prior[o + 2] = a2.z; }
+        for (int b0 = ty; b0 < B; b0 += 32) {   // four image rows per round: all twelve 16-byte loads issued before any store
+            float4 r[4][3];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int b = b0 + 8 * j;
+                if (b < B) {
+                    const float4* a = reinterpret_cast<const float4*>(acc + ((size_t)b * V + v) * 12);
+                    r[j][0] = a[0]; r[j][1] = a[1]; r[j][2] = a[2];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int b = b0 + 8 * j;
+                if (b >= B) continue;
+                const float4 a0 = r[j][0], a1 = r[j][1], a2 = r[j][2];
+                size_t o = ((size_t)b * V + v) * 3;
+                if (d_v_pos) { d_v_pos[o] = a0.x; d_v_pos[o + 1] = a0.y; d_v_pos[o + 2] = a0.z; }
+                if (d_v_nrm) { d_v_nrm[o] = a1.x; d_v_nrm[o + 1] = a1.y; d_v_nrm[o + 2] = a1.z; }
+                if (d_clip) reinterpret_cast<float4*>(d_clip)[(size_t)b * V + v] = make_float4(a1.w, a2.w, 0.f, a0.w);
+                if (rezero) {   // hand the accumulator back zeroed: a caller that keeps it needs no memset next time
+                    float4* az = reinterpret_cast<float4*>(acc + ((size_t)b * V + v) * 12);
+                    az[0] = az[1] = az[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (d_prior) {
+                    if (Bq == 1) { qx += a2.x; qy += a2.y; qz += a2.z; }
+                    else { d_prior[o] = a2.x; d_prior[o + 1] = a2.y; d_prior[o + 2] = a2.z; }
+                }
             }
         }
     }
@@ -320,15 +380,38 @@ int gb_check(const float* rast, int spp, const int32_t* tri, const float* v_pos,
 
 }  // namespace
 
+B2A_API int b2a_gbuffer_pack_bytes(int B, int Bq, int64_t V, size_t* bytes)
+{
+    B2A_CHECK_ARG(bytes && B > 0 && (Bq == 1 || Bq == B) && V >= 0, "shape");
+    *bytes = b2a_align((size_t)B * V * 2 * sizeof(float4)) + b2a_align((size_t)Bq * V * sizeof(float4));
+    return 0;
+}
+
+namespace {
+// packed vertex records live in a caller-owned buffer written by the forward and re-used by the backward
+void gb_packed(void* packed, int B, int Bq, int64_t V, GbParams* P)
+{
+    P->pn = (const float4*)packed;
+    P->q4 = packed ? (const float4*)((char*)packed + b2a_align((size_t)B * V * 2 * sizeof(float4))) : nullptr;
+}
+}  // namespace
+
 B2A_API int b2a_gbuffer_fwd(const float* rast, int spp, const int32_t* tri, const float* v_pos, const float* v_nrm,
                             const float* prior_pos, int Bq, const float* w2c, const float* campos, int two_sided, int B, int64_t V,
-                            int64_t F, int H, int W, float* gb_pos, float* gb_geo_nrm, float* gb_shading_nrm, float* gb_cam_nrm,
-                            float* gb_tex_pos, b2a_stream_t stream_)
+                            int64_t F, int H, int W, void* packed, size_t packed_bytes, float* gb_pos, float* gb_geo_nrm,
+                            float* gb_shading_nrm, float* gb_cam_nrm, float* gb_tex_pos, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = gb_check(rast, spp, tri, v_pos, v_nrm, prior_pos, Bq, w2c, campos, B, V, F, H, W);
     if (rc) return rc;
-    GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F};
+    GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F, nullptr, nullptr};
+    if (packed) {
+        size_t need;
+        b2a_gbuffer_pack_bytes(B, Bq, V, &need);
+        B2A_CHECK_ARG(packed_bytes >= need && ((uintptr_t)packed & 15) == 0, "packed buffer");
+        gb_packed(packed, B, Bq, V, &P);
+        gb_pack_kernel<<<b2a_blocks((int64_t)B * V, 256), 256, 0, stream>>>(v_pos, v_nrm, prior_pos, B, Bq, V, (float4*)P.pn, (float4*)P.q4);
+    }
     gb_fwd_kernel<<<dim3(b2a_blocks((int64_t)H * W, 256), B), 256, 0, stream>>>(P, gb_pos, gb_geo_nrm, gb_shading_nrm, gb_cam_nrm, gb_tex_pos);
     B2A_LAUNCH_OK();
     return 0;
@@ -343,10 +426,10 @@ B2A_API int b2a_gbuffer_bwd_workspace_bytes(int B, int64_t V, size_t* bytes)
 
 B2A_API int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, const int32_t* tri, const float* v_pos,
                             const float* v_nrm, const float* prior_pos, int Bq, const float* w2c, const float* campos, int two_sided,
-                            int B, int64_t V, int64_t F, int H, int W, const int32_t* cov_list, const int32_t* cov_count,
-                            const float* d_gb_pos, const float* d_gb_geo_nrm, const float* d_gb_shading_nrm, const float* d_gb_cam_nrm,
-                            const float* d_gb_tex_pos, void* workspace, size_t workspace_bytes, float* d_v_pos, float* d_v_nrm,
-                            float* d_prior_pos, float* d_clip, float* d_w2c, float* d_campos, b2a_stream_t stream_)
+                            int B, int64_t V, int64_t F, int H, int W, const void* packed, size_t packed_bytes, const int32_t* cov_list,
+                            const int32_t* cov_count, const float* d_gb_pos, const float* d_gb_geo_nrm, const float* d_gb_shading_nrm, const float* d_gb_cam_nrm,
+                            const float* d_gb_tex_pos, void* workspace, size_t workspace_bytes, int workspace_is_zero, float* d_v_pos,
+                            float* d_v_nrm, float* d_prior_pos, float* d_clip, float* d_w2c, float* d_campos, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = gb_check(rast, spp, tri, v_pos, v_nrm, prior_pos, Bq, w2c, campos, B, V, F, H, W);
@@ -355,22 +438,37 @@ B2A_API int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, c
     B2A_CHECK_ARG(workspace && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= (size_t)B * V * 12 * sizeof(float), "workspace");
     B2A_CHECK_ARG((cov_list == nullptr) == (cov_count == nullptr) && (!cov_list || spp == 1), "covered-pixel list");
     float* acc = (float*)workspace;
-    B2A_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)B * V * 12 * sizeof(float), stream));
-    GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F};
+    if (!workspace_is_zero) B2A_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)B * V * 12 * sizeof(float), stream));
+    GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F, nullptr, nullptr};
+    if (packed) {
+        size_t need;
+        b2a_gbuffer_pack_bytes(B, Bq, V, &need);
+        B2A_CHECK_ARG(packed_bytes >= need && ((uintptr_t)packed & 15) == 0, "packed buffer");
+        gb_packed(const_cast<void*>(packed), B, Bq, V, &P);
+    }
     const float* pc = d_clip ? pos_clip : nullptr;
+    const bool cam = d_w2c || d_campos;   // camera gradients cost registers (12 warp reductions): separate instantiation
     if (cov_list) {
         // about one covered pixel per thread at typical coverage (~25 %); the grid-stride loop absorbs the rest
         unsigned lblocks = b2a_blocks(((int64_t)B * H * W + 3) / 4, 128);
         if (lblocks > 148u * 32u) lblocks = 148u * 32u;
-        gb_bwd_kernel<true><<<lblocks, 128, 0, stream>>>(P, pc, cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
-                                                         d_gb_tex_pos, acc, d_w2c, d_campos);
+        if (cam)
+            gb_bwd_kernel<true, true><<<lblocks, 128, 0, stream>>>(P, pc, (const int4*)cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm,
+                                                                   d_gb_cam_nrm, d_gb_tex_pos, acc, d_w2c, d_campos);
+        else
+            gb_bwd_kernel<true, false><<<lblocks, 128, 0, stream>>>(P, pc, (const int4*)cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm,
+                                                                    d_gb_cam_nrm, d_gb_tex_pos, acc, d_w2c, d_campos);
     } else {
         unsigned blocks = b2a_blocks((int64_t)B * H * W, 128);
-        gb_bwd_kernel<false><<<blocks, 128, 0, stream>>>(P, pc, nullptr, nullptr, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
-                                                         d_gb_tex_pos, acc, d_w2c, d_campos);
+        if (cam)
+            gb_bwd_kernel<false, true><<<blocks, 128, 0, stream>>>(P, pc, nullptr, nullptr, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
+                                                                   d_gb_tex_pos, acc, d_w2c, d_campos);
+        else
+            gb_bwd_kernel<false, false><<<blocks, 128, 0, stream>>>(P, pc, nullptr, nullptr, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
+                                                                    d_gb_tex_pos, acc, d_w2c, d_campos);
     }
-    if (d_v_pos || d_v_nrm || d_prior_pos || d_clip)
-        gb_bwd_finalize_kernel<<<b2a_blocks(V, 32), 256, 0, stream>>>(acc, B, Bq, V, d_v_pos, d_v_nrm, d_prior_pos, d_clip);
+    if (d_v_pos || d_v_nrm || d_prior_pos || d_clip || workspace_is_zero)
+        gb_bwd_finalize_kernel<<<b2a_blocks(V, 32), 256, 0, stream>>>(acc, workspace_is_zero, B, Bq, V, d_v_pos, d_v_nrm, d_prior_pos, d_clip);
     B2A_LAUNCH_OK();
     return 0;
 }

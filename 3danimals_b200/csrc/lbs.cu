@@ -363,63 +363,109 @@ __global__ void __launch_bounds__(LBS_SBLOCK) lbs_fwd_shared_kernel(const float*
         for (int k = 0; k < K; k++) weights[(size_t)k * V + v] = s_w[k][threadIdx.x] * inv;
 }
 
-// d_v_pos [1,V,3] is accumulated (zero-initialised by the caller) because image chunks run in different blocks
-__global__ void __launch_bounds__(LBS_SBLOCK) lbs_bwd_shared_kernel(const float* __restrict__ v_pos, const float* __restrict__ bones,
-                                                                    const float* __restrict__ G, const float* __restrict__ d_out, int B, int K,
-                                                                    int64_t V, float inv_temp, float* __restrict__ d_v_pos,
-                                                                    float* __restrict__ d_G)
+// Backward of the shared-weight path.  d_G[b,k] = sum_v w[k,v] * g[b,v] (x) [p_v,1] is a small contraction over the
+// vertices (K x V times V x 12B): instead of reducing every vertex's outer product across the warp (shuffles + shared
+// atomics per (vertex, image, bone) - instruction-bound), each block stages a chunk of LBS_VC vertices in shared
+// memory (weights, [p,1], upstream gradients) and thread (k, c) accumulates its 3 x LBS_BC2 outputs in REGISTERS over
+// the chunk; one global atomic per output per block at the very end.  d_v = sum_b (sum_k w_k R[b,k])^T g[b] is
+// per-vertex work done in the staging phase.  d_v_pos [1,V,3] is accumulated (zero-initialised by the caller).
+constexpr int LBS_VC = 128;    // vertices per chunk == threads per block
+constexpr int LBS_BC2 = 4;     // images per block
+
+__global__ void __launch_bounds__(LBS_VC, 5) lbs_bwd_shared_kernel(const float* __restrict__ v_pos, const float* __restrict__ bones,
+                                                                const float* __restrict__ G, const float* __restrict__ d_out, int B, int K,
+                                                                int64_t V, float inv_temp, float* __restrict__ d_v_pos, float* __restrict__ d_G)
 {
     __shared__ float s_bones[LBS_CACHE_K * 6];
-    __shared__ float s_G[LBS_BC * LBS_CACHE_K * 12];
-    __shared__ float s_dG[LBS_BC * LBS_CACHE_K * 12];
-    __shared__ float s_w[LBS_CACHE_K][LBS_SBLOCK];
-    const int b0 = blockIdx.y * LBS_BC, nb = min(LBS_BC, B - b0);
-    for (int i = threadIdx.x; i < K * 6; i += blockDim.x) s_bones[i] = bones[i];
-    for (int i = threadIdx.x; i < nb * K * 12; i += blockDim.x) { s_G[i] = G[(size_t)b0 * K * 12 + i]; s_dG[i] = 0.f; }
+    __shared__ __align__(16) float s_G[LBS_BC2 * LBS_CACHE_K * 12];
+    __shared__ float s_w[LBS_CACHE_K][LBS_VC + 1];
+    __shared__ __align__(16) float4 s_g[LBS_BC2][LBS_VC];
+    __shared__ __align__(16) float4 s_ph[LBS_VC];
+    const int t = threadIdx.x;
+    const int b0 = blockIdx.y * LBS_BC2, nb = min(LBS_BC2, B - b0);
+    for (int i = t; i < K * 6; i += blockDim.x) s_bones[i] = bones[i];
+    for (int i = t; i < nb * K * 12; i += blockDim.x) s_G[i] = G[(size_t)b0 * K * 12 + i];
+    const int k2 = t >> 2, c2 = t & 3;           // contraction role: output column c2 of bone k2, all 3 rows, all images
+    const bool role = k2 < K;
+    float acc[LBS_BC2][3];
+#pragma unroll
+    for (int bb = 0; bb < LBS_BC2; bb++) acc[bb][0] = acc[bb][1] = acc[bb][2] = 0.f;
     __syncthreads();
-    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = v < V;
-    float px = 0.f, py = 0.f, pz = 0.f;
-    if (valid) { px = v_pos[v * 3]; py = v_pos[v * 3 + 1]; pz = v_pos[v * 3 + 2]; }
-    float inv = lbs_weights_shared(s_bones, s_w, K, px, py, pz, inv_temp);
-    if (!valid) inv = 0.f;
-    const int lane = threadIdx.x & 31;
-    // bones that carry weight somewhere in this warp (the soft-max at temperature 0.05 is sparse)
-    unsigned live = 0u;
-    for (int k = 0; k < K; k++) {
-        float w = s_w[k][threadIdx.x] * inv;
-        s_w[k][threadIdx.x] = w;
-        if (__ballot_sync(0xffffffffu, w > 1e-10f)) live |= 1u << k;   // < fp32 eps of the dominant terms
-    }
-    float dvx = 0.f, dvy = 0.f, dvz = 0.f;
-    for (int bb = 0; bb < nb; bb++) {
-        float gx = 0.f, gy = 0.f, gz = 0.f;
-        if (valid) {
-            const float* g = d_out + ((size_t)(b0 + bb) * V + v) * 3;
-            gx = g[0]; gy = g[1]; gz = g[2];
+    for (int64_t chunk = blockIdx.x; chunk * LBS_VC < V; chunk += gridDim.x) {
+        // ---- staging: this thread's vertex ----
+        const int64_t v = chunk * LBS_VC + t;
+        const bool valid = v < V;
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (valid) { px = v_pos[v * 3]; py = v_pos[v * 3 + 1]; pz = v_pos[v * 3 + 2]; }
+        float xmax = -3.4e38f;
+        for (int k = 0; k < K; k++) {
+            float x = -seg_dist(s_bones + k * 6, px, py, pz) * inv_temp;
+            s_w[k][t] = x;
+            xmax = fmaxf(xmax, x);
         }
-        const float* gb = s_G + bb * K * 12;
-        for (unsigned m = live; m; m &= m - 1) {
-            const int k = __ffs(m) - 1;
-            const float w = s_w[k][threadIdx.x];
-            const float* g = gb + k * 12;
-            dvx += w * (g[0] * gx + g[4] * gy + g[8] * gz);
-            dvy += w * (g[1] * gx + g[5] * gy + g[9] * gz);
-            dvz += w * (g[2] * gx + g[6] * gy + g[10] * gz);
-            float wx = w * gx, wy = w * gy, wz = w * gz;
-            const float r[16] = {wx * px, wx * py, wx * pz, wx, wy * px, wy * py, wy * pz, wy, wz * px, wz * py, wz * pz, wz, 0.f, 0.f, 0.f, 0.f};
-            float tot = warp_reduce16(r, lane);
-            if (!(lane & 1) && (lane >> 1) < 12) atomicAdd(&s_dG[(bb * K + k) * 12 + (lane >> 1)], tot);
+        float sum = 0.f;
+        for (int k = 0; k < K; k++) {
+            float e = expf(s_w[k][t] - xmax);
+            s_w[k][t] = e;
+            sum += e;
         }
+        const float inv = valid ? 1.f / sum : 0.f;
+        for (int k = 0; k < K; k++) s_w[k][t] *= inv;
+        s_ph[t] = make_float4(px, py, pz, 1.f);
+        float dvx = 0.f, dvy = 0.f, dvz = 0.f;
+        for (int bb = 0; bb < nb; bb++) {
+            float gx = 0.f, gy = 0.f, gz = 0.f;
+            if (valid) {
+                const float* g = d_out + ((size_t)(b0 + bb) * V + v) * 3;
+                gx = g[0]; gy = g[1]; gz = g[2];
+            }
+            s_g[bb][t] = make_float4(gx, gy, gz, 0.f);
+            // blended rotation of this vertex in image bb, then its transpose applied to g
+            float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f, m4 = 0.f, m5 = 0.f, m6 = 0.f, m7 = 0.f, m8 = 0.f;
+            const float4* Gb = reinterpret_cast<const float4*>(s_G + (size_t)bb * K * 12);
+            for (int k = 0; k < K; k++) {
+                const float w = s_w[k][t];
+                const float4 r0 = Gb[k * 3], r1 = Gb[k * 3 + 1], r2 = Gb[k * 3 + 2];
+                m0 += w * r0.x; m1 += w * r0.y; m2 += w * r0.z;
+                m3 += w * r1.x; m4 += w * r1.y; m5 += w * r1.z;
+                m6 += w * r2.x; m7 += w * r2.y; m8 += w * r2.z;
+            }
+            dvx += m0 * gx + m3 * gy + m6 * gz;
+            dvy += m1 * gx + m4 * gy + m7 * gz;
+            dvz += m2 * gx + m5 * gy + m8 * gz;
+        }
+        if (valid && d_v_pos) {
+            float* o = d_v_pos + (size_t)v * 3;
+            atomicAdd(o, dvx); atomicAdd(o + 1, dvy); atomicAdd(o + 2, dvz);
+        }
+        __syncthreads();
+        // ---- contraction over the chunk ----
+        if (role) {
+            const float* phc = reinterpret_cast<const float*>(s_ph) + c2;
+#pragma unroll 4
+            for (int vv = 0; vv < LBS_VC; vv++) {
+                const float wp = s_w[k2][vv] * phc[vv * 4];
+#pragma unroll
+                for (int bb = 0; bb < LBS_BC2; bb++) {
+                    if (bb < nb) {
+                        const float4 g4 = s_g[bb][vv];
+                        acc[bb][0] += wp * g4.x; acc[bb][1] += wp * g4.y; acc[bb][2] += wp * g4.z;
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
-    if (valid && d_v_pos) {
-        float* o = d_v_pos + (size_t)v * 3;
-        atomicAdd(o, dvx); atomicAdd(o + 1, dvy); atomicAdd(o + 2, dvz);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < nb * K * 12; i += blockDim.x) {
-        float s = s_dG[i];
-        if (s != 0.f) atomicAdd(&d_G[(size_t)b0 * K * 12 + i], s);
+    if (role) {
+#pragma unroll
+        for (int bb = 0; bb < LBS_BC2; bb++) {
+            if (bb < nb) {
+                float* o = d_G + ((size_t)(b0 + bb) * K + k2) * 12 + c2;
+                if (acc[bb][0] != 0.f) atomicAdd(o, acc[bb][0]);
+                if (acc[bb][1] != 0.f) atomicAdd(o + 4, acc[bb][1]);
+                if (acc[bb][2] != 0.f) atomicAdd(o + 8, acc[bb][2]);
+            }
+        }
     }
 }
 
@@ -545,8 +591,11 @@ B2A_API int b2a_lbs_bwd(const float* v_pos, const float* bones, const float* G, 
     B2A_CHECK_ARG(B > 0 && B <= 65535 && K > 0 && K <= LBS_MAX_K && (Bb == 1 || Bb == B) && (Bv == 1 || Bv == B), "shape");
     if (V == 0) return 0;
     if (Bv == 1 && Bb == 1 && B > 1 && K <= LBS_CACHE_K) {
-        lbs_bwd_shared_kernel<<<dim3(b2a_blocks(V, LBS_SBLOCK), (B + LBS_BC - 1) / LBS_BC), LBS_SBLOCK, 0, stream>>>(v_pos, bones, G, d_out, B, K,
-                                                                                                                 V, inv_temperature, d_v_pos, d_G);
+        unsigned chunks = b2a_blocks(V, LBS_VC);
+        unsigned by = (B + LBS_BC2 - 1) / LBS_BC2;
+        unsigned cap = 148u * 6u / by;      // ~6 resident blocks per SM
+        dim3 sgrid(chunks < cap ? chunks : (cap ? cap : 1u), by);
+        lbs_bwd_shared_kernel<<<sgrid, LBS_VC, 0, stream>>>(v_pos, bones, G, d_out, B, K, V, inv_temperature, d_v_pos, d_G);
         B2A_LAUNCH_OK();
         return 0;
     }

@@ -6,6 +6,8 @@
 
 namespace {
 
+// nsum is the library's own buffer (kept for the backward): rows are padded to 16 bytes so that each corner takes ONE
+// vector reduction instead of three scalar ones - the splat is bound by the SMs' RED issue rate.
 __global__ void normals_splat_kernel(const float* __restrict__ v_pos, const int* __restrict__ tri, int64_t V, int64_t F,
                                      float* __restrict__ nsum)
 {
@@ -13,22 +15,22 @@ __global__ void normals_splat_kernel(const float* __restrict__ v_pos, const int*
     if (f >= F) return;
     const int b = blockIdx.y;
     const float* p = v_pos + (size_t)b * V * 3;
-    float* s = nsum + (size_t)b * V * 3;
+    float4* s = reinterpret_cast<float4*>(nsum) + (size_t)b * V;
     int i0 = __ldg(tri + f * 3), i1 = __ldg(tri + f * 3 + 1), i2 = __ldg(tri + f * 3 + 2);
     float ax = p[(size_t)i0 * 3], ay = p[(size_t)i0 * 3 + 1], az = p[(size_t)i0 * 3 + 2];
     float e1x = p[(size_t)i1 * 3] - ax, e1y = p[(size_t)i1 * 3 + 1] - ay, e1z = p[(size_t)i1 * 3 + 2] - az;
     float e2x = p[(size_t)i2 * 3] - ax, e2y = p[(size_t)i2 * 3 + 1] - ay, e2z = p[(size_t)i2 * 3 + 2] - az;
     float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
-    atomicAdd(s + (size_t)i0 * 3, nx); atomicAdd(s + (size_t)i0 * 3 + 1, ny); atomicAdd(s + (size_t)i0 * 3 + 2, nz);
-    atomicAdd(s + (size_t)i1 * 3, nx); atomicAdd(s + (size_t)i1 * 3 + 1, ny); atomicAdd(s + (size_t)i1 * 3 + 2, nz);
-    atomicAdd(s + (size_t)i2 * 3, nx); atomicAdd(s + (size_t)i2 * 3 + 1, ny); atomicAdd(s + (size_t)i2 * 3 + 2, nz);
+    const float4 n4 = make_float4(nx, ny, nz, 0.f);
+    atomicAdd(s + i0, n4); atomicAdd(s + i1, n4); atomicAdd(s + i2, n4);
 }
 
 __global__ void normals_normalize_kernel(const float* __restrict__ nsum, int64_t n, float* __restrict__ v_nrm)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float x = nsum[i * 3], y = nsum[i * 3 + 1], z = nsum[i * 3 + 2];
+    const float4 s4 = reinterpret_cast<const float4*>(nsum)[i];
+    float x = s4.x, y = s4.y, z = s4.z;
     float d = (x * x + y * y) + z * z;
     if (!(d > 1e-20f)) { x = 0.f; y = 0.f; z = 1.f; d = 1.f; }
     float inv = 1.f / sqrtf(fmaxf(d, 1e-20f));
@@ -41,7 +43,8 @@ __global__ void normals_normalize_bwd_kernel(const float* __restrict__ nsum, con
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float x = nsum[i * 3], y = nsum[i * 3 + 1], z = nsum[i * 3 + 2];
+    const float4 s4 = reinterpret_cast<const float4*>(nsum)[i];
+    float x = s4.x, y = s4.y, z = s4.z;
     float d = (x * x + y * y) + z * z;
     float ox = 0.f, oy = 0.f, oz = 0.f;
     if (d > 1e-20f) {
@@ -51,7 +54,7 @@ __global__ void normals_normalize_bwd_kernel(const float* __restrict__ nsum, con
         float dt = nx * gx + ny * gy + nz * gz;
         ox = (gx - nx * dt) * inv; oy = (gy - ny * dt) * inv; oz = (gz - nz * dt) * inv;
     }
-    d_nsum[i * 3] = ox; d_nsum[i * 3 + 1] = oy; d_nsum[i * 3 + 2] = oz;
+    reinterpret_cast<float4*>(d_nsum)[i] = make_float4(ox, oy, oz, 0.f);   // padded like nsum: 16-byte gathers in the splat backward
 }
 
 __global__ void normals_splat_bwd_kernel(const float* __restrict__ v_pos, const int* __restrict__ tri, const float* __restrict__ d_nsum,
@@ -61,10 +64,12 @@ __global__ void normals_splat_bwd_kernel(const float* __restrict__ v_pos, const 
     if (f >= F) return;
     const int b = blockIdx.y;
     const float* p = v_pos + (size_t)b * V * 3;
-    const float* gs = d_nsum + (size_t)b * V * 3;
+    const float4* gs = reinterpret_cast<const float4*>(d_nsum) + (size_t)b * V;
     float* gp = d_v_pos + (size_t)b * V * 3;
-    size_t i0 = (size_t)__ldg(tri + f * 3) * 3, i1 = (size_t)__ldg(tri + f * 3 + 1) * 3, i2 = (size_t)__ldg(tri + f * 3 + 2) * 3;
-    float gx = gs[i0] + gs[i1] + gs[i2], gy = gs[i0 + 1] + gs[i1 + 1] + gs[i2 + 1], gz = gs[i0 + 2] + gs[i1 + 2] + gs[i2 + 2];
+    const int j0 = __ldg(tri + f * 3), j1 = __ldg(tri + f * 3 + 1), j2 = __ldg(tri + f * 3 + 2);
+    const float4 g0 = __ldg(gs + j0), g1 = __ldg(gs + j1), g2 = __ldg(gs + j2);
+    size_t i0 = (size_t)j0 * 3, i1 = (size_t)j1 * 3, i2 = (size_t)j2 * 3;
+    float gx = g0.x + g1.x + g2.x, gy = g0.y + g1.y + g2.y, gz = g0.z + g1.z + g2.z;
     if (gx == 0.f && gy == 0.f && gz == 0.f) return;
     float e1x = p[i1] - p[i0], e1y = p[i1 + 1] - p[i0 + 1], e1z = p[i1 + 2] - p[i0 + 2];
     float e2x = p[i2] - p[i0], e2y = p[i2 + 1] - p[i0 + 1], e2z = p[i2 + 2] - p[i0 + 2];
@@ -84,7 +89,8 @@ B2A_API int b2a_vertex_normals_fwd(const float* v_pos, const int32_t* tri, int B
     cudaStream_t stream = (cudaStream_t)stream_;
     B2A_CHECK_ARG(v_pos && tri && nsum && v_nrm, "null pointer");
     B2A_CHECK_ARG(B > 0 && B <= 65535 && V > 0 && F >= 0, "shape");
-    B2A_CUDA_OK(cudaMemsetAsync(nsum, 0, (size_t)B * V * 3 * sizeof(float), stream));
+    B2A_CHECK_ARG(((uintptr_t)nsum & 15) == 0, "nsum must be 16-byte aligned");
+    B2A_CUDA_OK(cudaMemsetAsync(nsum, 0, (size_t)B * V * 4 * sizeof(float), stream));
     if (F > 0) normals_splat_kernel<<<dim3(b2a_blocks(F, 256), B), 256, 0, stream>>>(v_pos, tri, V, F, nsum);
     normals_normalize_kernel<<<b2a_blocks((int64_t)B * V, 256), 256, 0, stream>>>(nsum, (int64_t)B * V, v_nrm);
     B2A_LAUNCH_OK();
@@ -97,6 +103,7 @@ B2A_API int b2a_vertex_normals_bwd(const float* v_pos, const int32_t* tri, const
     cudaStream_t stream = (cudaStream_t)stream_;
     B2A_CHECK_ARG(v_pos && tri && nsum && d_v_nrm && scratch && d_v_pos, "null pointer");
     B2A_CHECK_ARG(B > 0 && B <= 65535 && V > 0 && F >= 0, "shape");
+    B2A_CHECK_ARG(((uintptr_t)nsum & 15) == 0 && ((uintptr_t)scratch & 15) == 0, "nsum / scratch must be 16-byte aligned");
     normals_normalize_bwd_kernel<<<b2a_blocks((int64_t)B * V, 256), 256, 0, stream>>>(nsum, d_v_nrm, (int64_t)B * V, scratch);
     if (F > 0) normals_splat_bwd_kernel<<<dim3(b2a_blocks(F, 256), B), 256, 0, stream>>>(v_pos, tri, scratch, V, F, d_v_pos);
     B2A_LAUNCH_OK();

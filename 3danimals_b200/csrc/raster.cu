@@ -176,16 +176,18 @@ __global__ void __launch_bounds__(256) raster_large_kernel(const float* __restri
     }
 }
 
-// keys -> (u, v, z/w, id+1); optionally appends the covered pixels (flat index b*H*W + p) to a compact list that lets
-// the g-buffer backward run dense warps (warp-aggregated append: one atomic per warp)
+// keys -> (u, v, z/w, id+1); optionally appends the covered pixels to a compact list of 16-byte entries
+// (flat pixel index b*H*W + p, vertex ids i0, i1, i2) that lets the g-buffer backward run dense warps and start its
+// vertex gathers without the rast -> triangle -> index chain (warp-aggregated append: one atomic per warp)
 __global__ void __launch_bounds__(256) raster_resolve_kernel(const unsigned long long* __restrict__ zbuf, const float* __restrict__ pos,
                                                              const int* __restrict__ tri, int64_t V, int H, int W, float* __restrict__ rast,
-                                                             int* __restrict__ cov_list, int* __restrict__ cov_count)
+                                                             int4* __restrict__ cov_list, int* __restrict__ cov_count)
 {
     int ip = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     const bool in = ip < H * W;
     bool covered = false;
+    int i0 = 0, i1 = 0, i2 = 0;
     size_t pi = (size_t)b * H * W + ip;
     if (in) {
         int px = ip % W, py = ip / W;
@@ -194,9 +196,10 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(const unsigned long
         if (key != 0xffffffffffffffffull) {
             int f = (int)(unsigned)key;
             const float* pb = pos + (size_t)b * V * 4;
-            float4 p0 = ldg4(pb + (size_t)__ldg(tri + (size_t)f * 3) * 4);
-            float4 p1 = ldg4(pb + (size_t)__ldg(tri + (size_t)f * 3 + 1) * 4);
-            float4 p2 = ldg4(pb + (size_t)__ldg(tri + (size_t)f * 3 + 2) * 4);
+            i0 = __ldg(tri + (size_t)f * 3); i1 = __ldg(tri + (size_t)f * 3 + 1); i2 = __ldg(tri + (size_t)f * 3 + 2);
+            float4 p0 = ldg4(pb + (size_t)i0 * 4);
+            float4 p1 = ldg4(pb + (size_t)i1 * 4);
+            float4 p2 = ldg4(pb + (size_t)i2 * 4);
             float fx, fy;
             pixel_ndc(px, py, H, W, fx, fy);
             TriEval e;
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(const unsigned long
             int base = 0;
             if (lane == 0) base = atomicAdd(cov_count, __popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (covered) cov_list[base + __popc(m & ((1u << lane) - 1u))] = (int)pi;
+            if (covered) cov_list[base + __popc(m & ((1u << lane) - 1u))] = make_int4((int)pi, i0, i1, i2);
         }
     }
 }
@@ -312,7 +315,8 @@ B2A_API int b2a_rasterize_fwd(const float* pos, const int32_t* tri, int B, int64
     int rc = raster_zbuffer_impl(pos, tri, B, V, F, H, W, workspace, workspace_bytes, &ws, stream);
     if (rc) return rc;
     if (cov_count) B2A_CUDA_OK(cudaMemsetAsync(cov_count, 0, sizeof(int), stream));
-    raster_resolve_kernel<<<dim3(b2a_blocks((int64_t)H * W, 256), B), 256, 0, stream>>>(ws.zbuf, pos, tri, V, H, W, rast, cov_list, cov_count);
+    B2A_CHECK_ARG(!cov_list || ((uintptr_t)cov_list & 15) == 0, "cov_list must be 16-byte aligned");
+    raster_resolve_kernel<<<dim3(b2a_blocks((int64_t)H * W, 256), B), 256, 0, stream>>>(ws.zbuf, pos, tri, V, H, W, rast, (int4*)cov_list, cov_count);
     B2A_LAUNCH_OK();
     return 0;
 }

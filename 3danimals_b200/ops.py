@@ -55,7 +55,7 @@ KERNELS_PER_CALL = {
     "b2a_mt_count": 4, "b2a_mt_emit": 2, "b2a_mt_bwd": 1, "b2a_estimate_bones": 4, "b2a_lbs_bone_transforms": 2, "b2a_lbs_fwd": 1, "b2a_lbs_bwd": 1,
     "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1,
     "b2a_xfm_points_bwd": 1, "b2a_rasterize_fwd": 3, "b2a_rasterize_bwd": 1, "b2a_interpolate_fwd": 1, "b2a_interpolate_bwd": 1,
-    "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 2, "b2a_gbuffer_fwd": 1, "b2a_gbuffer_bwd": 2,
+    "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 2, "b2a_gbuffer_fwd": 2, "b2a_gbuffer_bwd": 2,
 }
 
 
@@ -312,7 +312,7 @@ class _VertexNormals(torch.autograd.Function):
         v_pos = _f32(v_pos, "v_pos")
         B, V = v_pos.shape[0], v_pos.shape[1]
         F = tri.shape[0]
-        nsum = torch.empty_like(v_pos)
+        nsum = torch.empty(B, V, 4, device=v_pos.device)
         nrm = torch.empty_like(v_pos)
         _call("b2a_vertex_normals_fwd", (_p(v_pos), _p(tri), B, V, F, _p(nsum), _p(nrm), _stream()))
         ctx.save_for_backward(v_pos, tri, nsum)
@@ -323,7 +323,7 @@ class _VertexNormals(torch.autograd.Function):
         v_pos, tri, nsum = ctx.saved_tensors
         B, V = v_pos.shape[0], v_pos.shape[1]
         g = _f32(g, "d_nrm")
-        scratch = torch.empty_like(v_pos)
+        scratch = torch.empty_like(nsum)
         d_pos = torch.zeros_like(v_pos)
         _call("b2a_vertex_normals_bwd", (_p(v_pos), _p(tri), _p(nsum), _p(g), B, V, tri.shape[0], _p(scratch), _p(d_pos),
                                                _stream()))
@@ -376,7 +376,7 @@ class _Rasterize(torch.autograd.Function):
         F = tri.shape[0]
         ws = _workspace(_size(L.b2a_rasterize_workspace_bytes, B, F, H, W), pos.device)
         rast = torch.empty(B, H, W, 4, device=pos.device)
-        cov_list = torch.empty(B * H * W if want_cov else 0, dtype=_i32, device=pos.device)
+        cov_list = torch.empty((B * H * W if want_cov else 0, 4), dtype=_i32, device=pos.device)
         cov_count = torch.empty(1 if want_cov else 0, dtype=_i32, device=pos.device)
         _call("b2a_rasterize_fwd", (_p(pos), _p(tri), B, V, F, H, W, _p(ws), ws.numel(), _p(rast), _p(cov_list) if want_cov else None,
                                         _p(cov_count) if want_cov else None, _stream()))
@@ -397,8 +397,8 @@ class _Rasterize(torch.autograd.Function):
 
 def rasterize(pos, tri, resolution, with_coverage=False):
     """pos [B,V,4] clip space, tri [F,3], resolution (H,W) -> rast [B,H,W,4] = (u, v, z/w, triangle_id+1).
-    with_coverage: also return (cov_list int32 [B*H*W], cov_count int32 [1]) - the compact list of covered pixels that
-    lets ops.gbuffer's backward run dense warps."""
+    with_coverage: also return (cov_list int32 [B*H*W,4], cov_count int32 [1]) - the compact list of covered pixels
+    (flat pixel index, vertex ids of the visible triangle) that lets ops.gbuffer's backward run dense warps."""
     if pos.dim() != 3 or pos.shape[-1] != 4:
         raise _lib.B2AError("rasterize: pos must be [B,V,4] (instanced mode)")
     rast, cl, cc = _Rasterize.apply(pos, _idx32(tri, "tri"), int(resolution[0]), int(resolution[1]), bool(with_coverage))
@@ -538,6 +538,19 @@ def composite_antialias(color, background, rast, pos, tri, opp, antialias_edges=
 GB_KEYS = ("pos", "geo_nrm", "shading_nrm", "cam_nrm", "tex_pos")
 
 
+_gb_acc = {}
+
+
+def _gb_accumulator(nbytes, device):
+    """Per-(device, stream) [B,V,12] vertex-gradient accumulator kept ZEROED between calls (the backward's finalize pass
+    re-zeroes what it read), so the steady state issues no memset.  Grown (and zeroed once) on demand."""
+    key = (device, _stream())
+    ws = _gb_acc.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _gb_acc[key] = torch.zeros(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+    return ws
+
+
 class _GBuffer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, two_sided, want, cov_list, cov_count):
@@ -548,16 +561,18 @@ class _GBuffer(torch.autograd.Function):
         if rast.shape[0] != B or w2c.shape != (B, 4, 4) or campos.shape != (B, 3) or v_nrm.shape != v_pos.shape:
             raise _lib.B2AError("gbuffer: inconsistent batch shapes")
         outs = [torch.empty(B, H, W, 3, device=rast.device) if k in want else None for k in GB_KEYS]
+        packed = _workspace(_size(_L().b2a_gbuffer_pack_bytes, B, prior_pos.shape[0], V), rast.device)
         _call("b2a_gbuffer_fwd", (_p(rast), spp, _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0], _p(w2c),
-                                        _p(campos), int(two_sided), B, V, tri.shape[0], H, W, *[_p(o) for o in outs], _stream()))
-        ctx.save_for_backward(rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, cov_list, cov_count)
+                                        _p(campos), int(two_sided), B, V, tri.shape[0], H, W, _p(packed), packed.numel(),
+                                        *[_p(o) for o in outs], _stream()))
+        ctx.save_for_backward(rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, cov_list, cov_count, packed)
         ctx.cfg = (spp, int(two_sided), H, W, tuple(o is not None for o in outs))
         return tuple(o if o is not None else torch.empty(0, device=rast.device) for o in outs)
 
     @staticmethod
     def backward(ctx, *grads):
         L = _L()
-        rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, cov_list, cov_count = ctx.saved_tensors
+        rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, cov_list, cov_count, packed = ctx.saved_tensors
         spp, two_sided, H, W, present = ctx.cfg
         B, V = v_pos.shape[0], v_pos.shape[1]
         gs = [(_f32(g, "d_gb") if (g is not None and p) else None) for g, p in zip(grads, present)]
@@ -570,10 +585,10 @@ class _GBuffer(torch.autograd.Function):
         d_w2c = torch.zeros_like(w2c) if need[6] else None
         d_campos = torch.zeros_like(campos) if need[7] else None
         if any(g is not None for g in gs):
-            ws = _workspace(_size(L.b2a_gbuffer_bwd_workspace_bytes, B, V), rast.device)
+            ws = _gb_accumulator(_size(L.b2a_gbuffer_bwd_workspace_bytes, B, V), rast.device)
             _call("b2a_gbuffer_bwd", (_p(rast), spp, _p(pos_clip), _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0],
-                                            _p(w2c), _p(campos), two_sided, B, V, tri.shape[0], H, W, _p(cov_list), _p(cov_count),
-                                            *[_p(g) for g in gs], _p(ws), ws.numel(), _p(d_v_pos), _p(d_v_nrm), _p(d_prior), _p(d_clip),
+                                            _p(w2c), _p(campos), two_sided, B, V, tri.shape[0], H, W, _p(packed), packed.numel(), _p(cov_list),
+                                            _p(cov_count), *[_p(g) for g in gs], _p(ws), ws.numel(), 1, _p(d_v_pos), _p(d_v_nrm), _p(d_prior), _p(d_clip),
                                             _p(d_w2c), _p(d_campos), _stream()))
         else:
             for t in (d_clip, d_v_pos, d_v_nrm, d_prior):

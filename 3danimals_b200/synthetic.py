@@ -31,6 +31,14 @@ def kuhn_tet_grid(res):
             path.append(vid(p))
         tets.append(np.stack(path, -1))
     tets = np.stack(tets, 1).reshape(-1, 4)
+    # The six monotone paths alternate in orientation with the parity of the axis permutation.  Marching tetrahedra takes
+    # its triangle winding from the tet's vertex order (triangle_table, dmtet.py:26-45), so a mixed grid yields a mesh
+    # whose faces point in and out at random (area-weighted vertex normals then cancel).  Swap the last two vertices of
+    # the positively oriented tets: every tet gets the same handedness and the extracted surface a consistent OUTWARD
+    # winding, like the Quartet grids the reference downloads.
+    p = verts[tets]
+    vol = np.einsum("ni,ni->n", np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), p[:, 3] - p[:, 0])
+    tets[vol > 0] = tets[vol > 0][:, [0, 1, 3, 2]]
     return verts, tets
 
 

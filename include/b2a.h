@@ -90,11 +90,11 @@ int b2a_estimate_bones(const float* verts, int N, int64_t V, int n_body_bones, i
 
 /* ------------------------------------------------------------------------------------------------------------
  * Smooth vertex normals.  Replaces mesh.auto_normals (model/render/mesh.py:276-304).
- * nsum [B,V,3] is the un-normalised area-weighted sum (kept for the backward).
+ * nsum [B,V,4] is the un-normalised area-weighted sum (xyz, 0), rows padded to 16 bytes (kept for the backward).
  * ---------------------------------------------------------------------------------------------------------- */
 int b2a_vertex_normals_fwd(const float* v_pos, const int32_t* tri, int B, int64_t V, int64_t F, float* nsum,
                            float* v_nrm, b2a_stream_t stream);
-/* scratch [B,V,3]; d_v_pos [B,V,3] zero-initialised by the caller (accumulated). */
+/* scratch [B,V,4]; d_v_pos [B,V,3] zero-initialised by the caller (accumulated). */
 int b2a_vertex_normals_bwd(const float* v_pos, const int32_t* tri, const float* nsum, const float* d_v_nrm, int B,
                            int64_t V, int64_t F, float* scratch, float* d_v_pos, b2a_stream_t stream);
 
@@ -114,8 +114,8 @@ int b2a_xfm_points_bwd(const float* pts, const float* mtx, const float* d_out, i
  * Backward: d_rast[...,0:2] -> d_pos (x,y,w), accumulated into zero-initialised d_pos [B,V,4].
  * ---------------------------------------------------------------------------------------------------------- */
 int b2a_rasterize_workspace_bytes(int B, int64_t F, int H, int W, size_t* bytes);
-/* cov_list [B*H*W] / cov_count [1] (both nullable): compact list of covered pixels (flat index b*H*W + y*W + x, unordered)
- * for b2a_gbuffer_bwd. */
+/* cov_list [B*H*W,4] / cov_count [1] (both nullable): compact, unordered list of covered pixels for b2a_gbuffer_bwd;
+ * entry = (flat pixel index b*H*W + y*W + x, vertex ids i0, i1, i2 of the visible triangle); 16-byte aligned. */
 int b2a_rasterize_fwd(const float* pos, const int32_t* tri, int B, int64_t V, int64_t F, int H, int W,
                       void* workspace, size_t workspace_bytes, float* rast, int32_t* cov_list, int32_t* cov_count,
                       b2a_stream_t stream);
@@ -175,20 +175,25 @@ int b2a_antialias_bwd(const float* color, const float* bg, int Bg, int composite
  * 16-byte vector reductions into a [B,V,12] accumulator (workspace, zeroed inside the call) and then WRITTEN (not
  * accumulated) to the nullable d_v_pos [B,V,3], d_v_nrm [B,V,3], d_prior_pos [Bq,V,3], d_clip [B,V,4] (x,y,w; z = 0);
  * d_w2c [B,16] and d_campos [B,3] (nullable) are accumulated into zero-initialised buffers.
+ * workspace_is_zero = 1: the caller guarantees the accumulator is all zeros on entry (no memset is issued) and gets
+ * it back zeroed - for callers that keep one accumulator per device across calls.
  * cov_list / cov_count (nullable, spp == 1 only): the rasterizer's compact covered-pixel list - dense warps.
  * ---------------------------------------------------------------------------------------------------------- */
+/* packed (nullable): caller-owned scratch of b2a_gbuffer_pack_bytes bytes; the forward re-lays the vertex attributes out
+ * as 16-byte records there (the per-pixel gather is bound by load instructions, not bytes) and the backward re-uses it. */
+int b2a_gbuffer_pack_bytes(int B, int Bq, int64_t V, size_t* bytes);
 int b2a_gbuffer_fwd(const float* rast, int spp, const int32_t* tri, const float* v_pos, const float* v_nrm,
                     const float* prior_pos, int Bq, const float* w2c, const float* campos, int two_sided, int B,
-                    int64_t V, int64_t F, int H, int W, float* gb_pos, float* gb_geo_nrm, float* gb_shading_nrm,
-                    float* gb_cam_nrm, float* gb_tex_pos, b2a_stream_t stream);
+                    int64_t V, int64_t F, int H, int W, void* packed, size_t packed_bytes, float* gb_pos,
+                    float* gb_geo_nrm, float* gb_shading_nrm, float* gb_cam_nrm, float* gb_tex_pos, b2a_stream_t stream);
 int b2a_gbuffer_bwd_workspace_bytes(int B, int64_t V, size_t* bytes);
 int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, const int32_t* tri, const float* v_pos,
                     const float* v_nrm, const float* prior_pos, int Bq, const float* w2c, const float* campos,
-                    int two_sided, int B, int64_t V, int64_t F, int H, int W, const int32_t* cov_list,
-                    const int32_t* cov_count, const float* d_gb_pos, const float* d_gb_geo_nrm,
+                    int two_sided, int B, int64_t V, int64_t F, int H, int W, const void* packed, size_t packed_bytes,
+                    const int32_t* cov_list, const int32_t* cov_count, const float* d_gb_pos, const float* d_gb_geo_nrm,
                     const float* d_gb_shading_nrm, const float* d_gb_cam_nrm, const float* d_gb_tex_pos,
-                    void* workspace, size_t workspace_bytes, float* d_v_pos, float* d_v_nrm, float* d_prior_pos,
-                    float* d_clip, float* d_w2c, float* d_campos, b2a_stream_t stream);
+                    void* workspace, size_t workspace_bytes, int workspace_is_zero, float* d_v_pos, float* d_v_nrm,
+                    float* d_prior_pos, float* d_clip, float* d_w2c, float* d_campos, b2a_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -423,7 +423,11 @@ def test_gbuffer_oracle(cuda, spp, Bq, two_sided, use_cov):
         assert np.array_equal(rast_d.cpu().numpy(), rast)
         n_cov = int(coverage[1].item())
         assert n_cov == int((rast[..., 3] > 0).sum())
-        assert np.array_equal(np.sort(coverage[0][:n_cov].cpu().numpy()), np.flatnonzero(rast[..., 3].reshape(-1) > 0))
+        cl = coverage[0][:n_cov].cpu().numpy()
+        order = np.argsort(cl[:, 0])
+        flat = np.flatnonzero(rast[..., 3].reshape(-1) > 0)
+        assert np.array_equal(cl[order, 0], flat)
+        assert np.array_equal(cl[order, 1:], faces[rast[..., 3].reshape(-1)[flat].astype(np.int64) - 1])   # vertex ids of the visible triangle
     out = ops.gbuffer(dev(rast, cuda), cd, dev(faces, cuda), vd, nd, qd, wd, pd, spp=spp, two_sided=two_sided, want=tuple(refs),
                       coverage=coverage)
     covered = rast[:, ::spp, ::spp, 3] > 0

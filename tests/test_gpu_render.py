@@ -28,6 +28,8 @@ def _stage_inputs(grid_res=24, batch=2, image=64):
     (1, ("shaded", "shading", "kd", "geo_normal", "normal"), True),
     (2, ("shaded", "shading", "kd"), True),          # visualisation path: msaa, spp>1 (visualize_results.py:275-278)
     (1, ("shaded", "depth", "bogus"), False),
+    (1, ("shaded", "dino_pred", "flow"), False),      # ponymation: frame-to-frame flow of the clip positions (render.py:281-288)
+    (4, ("shaded",), True),                           # C0 / C4 visualisation: 4 samples per pixel
 ])
 def test_render_mesh_matches_oracle(cuda, spp, modes, with_bg):
     """Identical posed vertices on both sides -> bit-exact triangle ids, images and all input gradients <= 1e-4."""
@@ -56,8 +58,10 @@ def test_render_mesh_matches_oracle(cuda, spp, modes, with_bg):
 
     known = [m for m in modes if m != "bogus"]
     v_nrm = T.auto_normals(posed, faces)
+    num_frames = B if "flow" in modes else None
     out_ref = T.render_mesh(posed, v_nrm, faces, mvp_t, w2c_t, cam_t, shade_fn, (r, r), spp=spp,
-                            background=torch.from_numpy(bg) if with_bg else None, render_modes=known, prior_v_pos=prior)
+                            background=torch.from_numpy(bg) if with_bg else None, render_modes=known, prior_v_pos=prior,
+                            num_frames=num_frames)
     gs = {k: rng.randn(*out_ref[k].shape).astype(np.float32) for k in known}
     sum((out_ref[k] * torch.from_numpy(gs[k])).sum() for k in known).backward()
 
@@ -72,7 +76,7 @@ def test_render_mesh_matches_oracle(cuda, spp, modes, with_bg):
     light = pipe.FixedLight(dev(sc.light, cuda))
     outs = render_mod.render_mesh(None, inst, mvp_d, w2c_d, cam_d, material, light, (r, r), spp=spp, msaa=True,
                                   background=dev(bg, cuda) if with_bg else None, bsdf="diffuse", render_modes=list(modes),
-                                  prior_mesh=prior_mesh, dino_net=dino)
+                                  prior_mesh=prior_mesh, dino_net=dino, num_frames=num_frames)
     assert len(outs) == len(modes)
     total = 0
     for m, o in zip(modes, outs):
@@ -89,6 +93,48 @@ def test_render_mesh_matches_oracle(cuda, spp, modes, with_bg):
             assert a.grad is None or float(a.grad.abs().max()) == 0, name
             continue
         assert rel_err(a.grad.cpu().numpy(), b.grad.numpy()) < 3e-4, name
+
+
+def test_render_mesh_without_material_and_light(cuda):
+    """Fauna's random-view regulariser renders ['shaded'] with texture=None, light=None (Fauna.py:145-163): all-ones
+    texture (render.py:56) and shaded = kd (render.py:89-90) - the mask is the only signal."""
+    mesh_mod, render_mod = pkg("render.mesh"), pkg("render.render")
+    pipe, sc, ref = _stage_inputs()
+    B, r = sc.batch, sc.image_res
+    posed = ref["posed"][:, 0].detach().clone().requires_grad_(True)
+    faces = ref["faces"]
+    mvp_t, w2c_t, cam_t = (torch.from_numpy(x) for x in (sc.mvp, sc.w2c, sc.campos))
+    ones = lambda gb_tex, cam_normal, gbuf: {"shaded": torch.ones_like(gb_tex)}
+    out_ref = T.render_mesh(posed, T.auto_normals(posed, faces), faces, mvp_t, w2c_t, cam_t, ones, (r, r), render_modes=("shaded",))
+    g = np.random.RandomState(3).randn(*out_ref["shaded"].shape).astype(np.float32)
+    (out_ref["shaded"] * torch.from_numpy(g)).sum().backward()
+    posed_d = dev(posed.detach().numpy(), cuda).requires_grad_(True)
+    inst = mesh_mod.make_mesh(posed_d, dev(faces.numpy(), cuda)[None], None, None, None)
+    out, = render_mod.render_mesh(None, inst, dev(sc.mvp, cuda), dev(sc.w2c, cuda), dev(sc.campos, cuda), None, None, (r, r),
+                                  render_modes=["shaded"], bsdf="diffuse")
+    a, b = out.detach().cpu().numpy(), out_ref["shaded"].detach().numpy()
+    assert rel_err(a, b) < TOL                        # clip positions differ by fp32 rounding (GPU vs CPU transform) -> blend weights by ulps
+    assert np.array_equal(a == 0, b == 0) and np.array_equal(a == 1, b == 1)                     # same coverage, same untouched interior
+    (out * dev(g, cuda)).sum().backward()
+    assert float(posed.grad.abs().max()) > 0                                                     # silhouette gradient exists
+    assert rel_err(posed_d.grad.cpu().numpy(), posed.grad.numpy()) < 3e-4
+
+
+def test_half_precision_colours_are_promoted(cuda):
+    """Bird config runs the field MLPs under fp16 autocast; the reference casts to fp32 before the nvdiffrast calls
+    (render.py:265,292).  Half inputs must give exactly the result of their fp32 promotion."""
+    ops = pkg("ops")
+    pipe, sc, ref = _stage_inputs()
+    B, r = sc.batch, sc.image_res
+    clip = T.xfm_points(ref["posed"][:, 0].detach(), torch.from_numpy(sc.mvp)).contiguous()
+    cd, tri = clip.to(cuda), ref["faces"].int().to(cuda)
+    rast = ops.rasterize(cd, tri, (r, r))
+    opp = ops.edge_adjacency(tri, cd.shape[1])
+    ctx = ops.antialias_prepare(rast, cd, tri, opp)
+    col16 = torch.rand(B, r, r, 16, device=cuda).half()
+    a = ops.composite_antialias(col16, None, rast, cd, tri, opp, True, 16, aa_ctx=ctx)
+    b = ops.composite_antialias(col16.float(), None, rast, cd, tri, opp, True, 16, aa_ctx=ctx)
+    assert a.dtype == torch.float32 and torch.equal(a, b)
 
 
 def test_render_mesh_asserts(cuda):
@@ -109,8 +155,8 @@ def test_ops_refuse_cpu_tensors():
         ops.xfm_points(torch.zeros(1, 4, 3), torch.eye(4)[None])
 
 
-@pytest.mark.parametrize("grid_res,batch,image", [(32, 2, 64), (48, 3, 128)])
-def test_hot_path_matches_oracle(cuda, grid_res, batch, image):
+@pytest.mark.parametrize("grid_res,batch,image,n_leg", [(32, 2, 64, 3), (48, 3, 128, 3), (32, 3, 64, 0)])   # n_leg 0: bird (8 bones)
+def test_hot_path_matches_oracle(cuda, grid_res, batch, image, n_leg):
     """Whole path (extraction -> bones -> LBS -> normals -> render -> backward).  Vertex positions now differ by fp32
     rounding between CPU and GPU (different exp / summation order in LBS), so a handful of edge pixels may pick the
     neighbouring triangle: allow <= 0.2 % of pixels to differ, everything else <= 1e-4.  Gradients: the antialias
@@ -119,7 +165,7 @@ def test_hot_path_matches_oracle(cuda, grid_res, batch, image):
     the end-to-end gradient bar is 5e-2; the 1e-4-level gradient checks are the stage tests above, which feed both
     sides identical inputs."""
     pipe = pkg("pipeline")
-    sc = pipe.SyntheticScene(grid_res=grid_res, batch=batch, image_res=image, sdf_noise=0.01)
+    sc = pipe.SyntheticScene(grid_res=grid_res, batch=batch, image_res=image, sdf_noise=0.01, n_leg_bones=n_leg)
     g1, g2 = sc.upstream_grads()
     d_sdf_ref, d_ang_ref, ref = P.step(sc, g1, g2)
     hp = pipe.HotPath(sc, cuda)
@@ -138,3 +184,74 @@ def test_hot_path_matches_oracle(cuda, grid_res, batch, image):
         assert bad.mean() < 2e-3, (k, bad.mean())
     assert rel_err(d_ang.cpu().numpy(), d_ang_ref.numpy()) < 5e-2
     assert rel_err(d_sdf.cpu().numpy(), d_sdf_ref.numpy()) < 5e-2
+
+
+def test_full_size_properties(cuda):
+    """BASELINE configs[1] at full size (res-128 grid, 16 x 256^2, 20 bones), where the CPU oracle is too slow to be the
+    checker: size-independent properties of every stage."""
+    pipe, ops = pkg("pipeline"), pkg("ops")
+    sc = pipe.SyntheticScene(grid_res=128, batch=16, image_res=256)
+    hp = pipe.HotPath(sc, cuda)
+    g1, g2 = sc.upstream_grads()
+    d1, d2 = dev(g1, cuda), dev(g2, cuda)
+    d_sdf, d_ang = (x.clone() for x in hp.step(d1, d2))
+    prior, inst = hp.last["prior"], hp.last["inst"]
+    V, F = prior.v_pos.shape[1], prior.t_pos_idx.shape[1]
+    faces = prior.t_pos_idx[0]
+    # extraction: indices in range, every vertex used, closed 2-manifold (each undirected edge in exactly two faces,
+    # with opposite orientation) and Euler characteristic 2 per connected component of the capsule union (genus 0)
+    assert int(faces.min()) == 0 and int(faces.max()) == V - 1 and torch.unique(faces).numel() == V
+    e = torch.cat([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]])
+    key_dir = e[:, 0] * V + e[:, 1]
+    assert torch.unique(key_dir).numel() == key_dir.numel()                               # no directed edge twice
+    und, cnt = torch.unique(torch.minimum(e[:, 0], e[:, 1]) * V + torch.maximum(e[:, 0], e[:, 1]), return_counts=True)
+    assert bool((cnt == 2).all())
+    assert (V - und.numel() + F) % 2 == 0 and V - und.numel() + F >= 2
+    assert int((prior.edge_adjacency() < 0).sum()) == 0                                   # adjacency table: no boundary edge
+    # vertices lie on grid edges between an inside and an outside grid vertex
+    verts2, _, _, _, vert_edge = ops.marching_tets(hp.grid_verts, hp.sdf.detach(), hp.grid)
+    sa, sb = hp.sdf.detach()[vert_edge[:, 0].long(), 0], hp.sdf.detach()[vert_edge[:, 1].long(), 0]
+    assert bool(((sa > 0) != (sb > 0)).all()) and bool((vert_edge[:, 0] < vert_edge[:, 1]).all())
+    key = vert_edge[:, 0].long() * (hp.grid.Vg + 1) + vert_edge[:, 1].long()
+    assert bool((key[1:] > key[:-1]).all())                                               # torch.unique(dim=0) order
+    # skinning: weights are a partition of unity; zero articulation is the identity
+    sk = pkg("geometry.skinning")
+    posed0, aux0 = sk.skinning(prior.v_pos[:, None].detach(), hp.last["bones"], hp.kinematic_chain, torch.zeros_like(hp.angles),
+                               output_posed_bones=True, temperature=0.05)
+    assert rel_err(posed0[0, 0].cpu().numpy(), prior.v_pos[0].detach().cpu().numpy()) < 1e-5
+    w = aux0["vertices_to_bones"]
+    assert float((w.sum(0) - 1).abs().max()) < 1e-5 and float(w.min()) >= 0
+    # normals are unit length
+    assert float((inst.v_nrm.norm(dim=-1) - 1).abs().max()) < 1e-4
+    # rasterizer: ids within range, barycentrics in [0,1], depth in [-1,1]; the covered list matches
+    clip = ops.xfm_points(inst.v_pos.detach(), hp.mvp)
+    rast, (cl, cc) = ops.rasterize(clip, prior.tri_i32(), (256, 256), with_coverage=True)
+    ids = rast[..., 3]
+    assert float(ids.min()) == 0 and float(ids.max()) <= F and bool((ids == ids.round()).all())
+    cov = ids > 0
+    assert 0.05 < float(cov.float().mean()) < 0.6
+    assert bool(((rast[..., :2] >= 0) & (rast[..., :2] <= 1)).all()) and bool((rast[..., 0] + rast[..., 1] <= 1 + 1e-6)[cov].all())
+    assert bool((rast[..., 2][cov].abs() <= 1).all()) and bool((rast[~cov] == 0).all())
+    assert int(cc.item()) == int(cov.sum()) and torch.equal(torch.sort(cl[:int(cc.item()), 0]).values.long(), torch.nonzero(cov.reshape(-1))[:, 0])
+    # two forward passes agree: visibility bit-for-bit (atomicMin z-buffer), images up to the summation order of the
+    # vertex-normal splat (float atomics, like the reference's scatter_add); the mask channel (no shading) bit-for-bit
+    s1, f1 = hp.forward()
+    s2, f2 = hp.forward()
+    rast2, _ = ops.rasterize(ops.xfm_points(hp.last["inst"].v_pos.detach(), hp.mvp), prior.tri_i32(), (256, 256), with_coverage=True)
+    assert torch.equal(rast, rast2)
+    assert torch.equal(s1[:, 3], s2[:, 3]) and torch.equal(f1, f2)
+    assert float((s1 - s2).abs().max()) < 1e-5
+    assert bool(torch.isfinite(s1).all()) and bool(torch.isfinite(f1).all())
+    alpha = s1[:, 3]
+    assert float(alpha.min()) >= 0 and float(alpha.max()) <= 1
+    interior = torch.nn.functional.max_pool2d(cov.float()[:, None], 3, 1, 1)[:, 0] == 0    # no covered pixel in the 3x3 ring
+    assert float(s1.permute(0, 2, 3, 1)[interior].abs().max()) == 0 and float(f1.permute(0, 2, 3, 1)[interior].abs().max()) == 0
+    # backward is linear in the upstream gradient and finite
+    d_sdf3, d_ang3 = hp.step(3 * d1, 3 * d2)
+    assert bool(torch.isfinite(d_sdf3).all()) and bool(torch.isfinite(d_ang3).all()) and float(d_ang.abs().max()) > 0
+    assert rel_err(d_ang3.cpu().numpy(), 3 * d_ang.cpu().numpy()) < 1e-3
+    assert rel_err(d_sdf3.cpu().numpy(), 3 * d_sdf.cpu().numpy()) < 1e-3
+    # gradients touch only grid vertices on crossing edges
+    touched = torch.zeros(hp.grid.Vg, dtype=torch.bool, device=cuda)
+    touched[vert_edge.reshape(-1).long()] = True
+    assert float(d_sdf[~touched].abs().max()) == 0
