@@ -316,56 +316,32 @@ __global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float*
     }
 }
 
-// accumulator rows -> gradient tensors (each nullable).  Block = 32 vertices x 8 image lanes; d_prior sums over the batch
-// (Bq == 1) in a fixed order: per-lane partial sums over b = ty, ty+8, ..., then a fixed 8-term sum through smem.
+// accumulator rows -> gradient tensors (each nullable), one thread per (image, vertex): three 16-byte loads, the outputs,
+// and (rezero) the row handed back zeroed.  With a shared prior (Bq == 1) d_prior sums over the batch with scalar
+// reductions into a zero-initialised [V,3] (B-way contention per address, but only 3 V B of them).
 __global__ void __launch_bounds__(256) gb_bwd_finalize_kernel(float* __restrict__ acc, int rezero, int B, int Bq, int64_t V, float* __restrict__ d_v_pos,
                                                               float* __restrict__ d_v_nrm, float* __restrict__ d_prior, float* __restrict__ d_clip)
 {
-    __shared__ float s_q[8][32][3];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int64_t v = (int64_t)blockIdx.x * 32 + tx;
-    float qx = 0.f, qy = 0.f, qz = 0.f;
-    if (v < V) {
-        for (int b0 = ty; b0 < B; b0 += 32) {   // four image rows per round: all twelve 16-byte loads issued before any store
-            float4 r[4][3];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int b = b0 + 8 * j;
-                if (b < B) {
-                    const float4* a = reinterpret_cast<const float4*>(acc + ((size_t)b * V + v) * 12);
-                    r[j][0] = a[0]; r[j][1] = a[1]; r[j][2] = a[2];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int b = b0 + 8 * j;
-                if (b >= B) continue;
-                const float4 a0 = r[j][0], a1 = r[j][1], a2 = r[j][2];
-                size_t o = ((size_t)b * V + v) * 3;
-                if (d_v_pos) { d_v_pos[o] = a0.x; d_v_pos[o + 1] = a0.y; d_v_pos[o + 2] = a0.z; }
-                if (d_v_nrm) { d_v_nrm[o] = a1.x; d_v_nrm[o + 1] = a1.y; d_v_nrm[o + 2] = a1.z; }
-                if (d_clip) reinterpret_cast<float4*>(d_clip)[(size_t)b * V + v] = make_float4(a1.w, a2.w, 0.f, a0.w);
-                if (rezero) {   // hand the accumulator back zeroed: a caller that keeps it needs no memset next time
-                    float4* az = reinterpret_cast<float4*>(acc + ((size_t)b * V + v) * 12);
-                    az[0] = az[1] = az[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                if (d_prior) {
-                    if (Bq == 1) { qx += a2.x; qy += a2.y; qz += a2.z; }
-                    else { d_prior[o] = a2.x; d_prior[o + 1] = a2.y; d_prior[o + 2] = a2.z; }
-                }
-            }
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const int b = blockIdx.y;
+    float4* a = reinterpret_cast<float4*>(acc + ((size_t)b * V + v) * 12);
+    const float4 a0 = a[0], a1 = a[1], a2 = a[2];
+    const size_t o = ((size_t)b * V + v) * 3;
+    if (d_v_pos) { d_v_pos[o] = a0.x; d_v_pos[o + 1] = a0.y; d_v_pos[o + 2] = a0.z; }
+    if (d_v_nrm) { d_v_nrm[o] = a1.x; d_v_nrm[o + 1] = a1.y; d_v_nrm[o + 2] = a1.z; }
+    if (d_clip) reinterpret_cast<float4*>(d_clip)[(size_t)b * V + v] = make_float4(a1.w, a2.w, 0.f, a0.w);
+    if (d_prior) {
+        if (Bq == 1) {
+            float* q = d_prior + (size_t)v * 3;
+            if (a2.x != 0.f) atomicAdd(q, a2.x);
+            if (a2.y != 0.f) atomicAdd(q + 1, a2.y);
+            if (a2.z != 0.f) atomicAdd(q + 2, a2.z);
+        } else {
+            d_prior[o] = a2.x; d_prior[o + 1] = a2.y; d_prior[o + 2] = a2.z;
         }
     }
-    if (d_prior && Bq == 1) {
-        s_q[ty][tx][0] = qx; s_q[ty][tx][1] = qy; s_q[ty][tx][2] = qz;
-        __syncthreads();
-        if (ty == 0 && v < V) {
-            float sx = 0.f, sy = 0.f, sz = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; j++) { sx += s_q[j][tx][0]; sy += s_q[j][tx][1]; sz += s_q[j][tx][2]; }
-            d_prior[v * 3] = sx; d_prior[v * 3 + 1] = sy; d_prior[v * 3 + 2] = sz;
-        }
-    }
+    if (rezero) a[0] = a[1] = a[2] = make_float4(0.f, 0.f, 0.f, 0.f);   // a caller that keeps the accumulator needs no memset next time
 }
 
 int gb_check(const float* rast, int spp, const int32_t* tri, const float* v_pos, const float* v_nrm, const float* prior_pos, int Bq,
@@ -467,8 +443,10 @@ B2A_API int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, c
             gb_bwd_kernel<false, false><<<blocks, 128, 0, stream>>>(P, pc, nullptr, nullptr, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
                                                                     d_gb_tex_pos, acc, d_w2c, d_campos);
     }
-    if (d_v_pos || d_v_nrm || d_prior_pos || d_clip || workspace_is_zero)
-        gb_bwd_finalize_kernel<<<b2a_blocks(V, 32), 256, 0, stream>>>(acc, workspace_is_zero, B, Bq, V, d_v_pos, d_v_nrm, d_prior_pos, d_clip);
+    if (d_v_pos || d_v_nrm || d_prior_pos || d_clip || workspace_is_zero) {
+        if (d_prior_pos && Bq == 1) B2A_CUDA_OK(cudaMemsetAsync(d_prior_pos, 0, (size_t)V * 3 * sizeof(float), stream));
+        gb_bwd_finalize_kernel<<<dim3(b2a_blocks(V, 256), B), 256, 0, stream>>>(acc, workspace_is_zero, B, Bq, V, d_v_pos, d_v_nrm, d_prior_pos, d_clip);
+    }
     B2A_LAUNCH_OK();
     return 0;
 }

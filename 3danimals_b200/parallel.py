@@ -24,10 +24,17 @@ def allreduce_gradients(tensors, average=True, group=None):
     grads = [t for t in tensors if t is not None]
     if not grads or not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
+    world = dist.get_world_size(group)
+    if len(grads) == 1 and grads[0].is_contiguous():
+        # single bucket already: reduce in place (no flatten / copy-back launches)
+        dist.all_reduce(grads[0], op=dist.ReduceOp.SUM, group=group)
+        if average:
+            grads[0].div_(world)
+        return grads[0].numel() * grads[0].element_size()
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
-        flat /= dist.get_world_size(group)
+        flat /= world
     off = 0
     for g in grads:
         n = g.numel()

@@ -57,6 +57,7 @@ class AnalyticField(torch.nn.Module):
         self.register_buffer("weight", weight)
         self.squash = squash
         self.bsdf = None
+        self.dense_only = True   # three flops per pixel: gathering the covered rows would cost more than evaluating everywhere
 
     def sample(self, x, feat=None):
         y = torch.matmul(x, self.weight)
@@ -106,6 +107,7 @@ class HotPath(torch.nn.Module):
             self.material = AnalyticField(torch.from_numpy(s.w_kd).to(dev), True)
             self.dino_net = AnalyticField(torch.from_numpy(s.w_dino).to(dev), False)
         self.mlps = mlps
+        self.sparse_fields = True
         self.bone_aux = None
         self.kinematic_chain = None
 
@@ -132,7 +134,8 @@ class HotPath(torch.nn.Module):
         feat = self.feat if self.mlps else None
         out = render_mod.render_mesh(None, inst, self.mvp, self.w2c, self.campos, self.material, self.light, res, spp=1,
                                      num_layers=1, msaa=True, background=None, bsdf="diffuse", feat=feat,
-                                     render_modes=list(render_modes), prior_mesh=prior, dino_net=self.dino_net)
+                                     render_modes=list(render_modes), prior_mesh=prior, dino_net=self.dino_net,
+                                     sparse_fields=self.sparse_fields)
         self.last = dict(prior=prior, inst=inst, bones=bones, posed_bones=aux["posed_bones"])
         return out
 

@@ -28,6 +28,30 @@ def _as_b3(x, B, device):
     return x.expand(B, 3) if x.shape[0] == 1 and B > 1 else x
 
 
+def _covered_rows(rast_s):
+    """Flat indices (into [B*h*w]) of the pixels where a triangle is visible, image index of each, and the grid shape.
+    One device->host read (the row count) per render."""
+    B, h, w = rast_s.shape[:3]
+    idx = torch.nonzero(rast_s[..., 3].reshape(-1) > 0).squeeze(1)
+    return idx, torch.div(idx, h * w, rounding_mode="floor"), (B, h, w)
+
+
+def _sample_field(net, gb_tex_pos, feat, sparse):
+    """net.sample on every pixel (sparse=None: the reference's evaluation) or on the covered rows only, scattered back
+    into a zero image.  Identical on covered pixels; uncovered pixels never reach an output (alpha = 0 in the composite,
+    render.py:258-262)."""
+    if sparse is None or getattr(net, "dense_only", False):
+        return net.sample(gb_tex_pos, feat=feat)
+    idx, img, (B, h, w) = sparse
+    x = gb_tex_pos.reshape(-1, gb_tex_pos.shape[-1]).index_select(0, idx)
+    f = None
+    if feat is not None:
+        f = feat.index_select(0, img) if feat.shape[0] == B else feat.expand(B, -1).index_select(0, img)
+    y = net.sample(x, feat=f)
+    out = y.new_zeros(B * h * w, y.shape[-1]).index_copy(0, idx, y)
+    return out.view(B, h, w, y.shape[-1])
+
+
 _AA_KEYS = ("shaded", "flow", "dino_pred", "depth", "shading")
 _BG_KEYS = ("shaded", "geo_normal", "shading")
 _KEEP = {"kd": 3, "ks": 3, "normal": 3, "geo_normal": 3, "shading": 1, "flow": 2, "depth": 1}
@@ -35,7 +59,7 @@ _KEEP = {"kd": 3, "ks": 3, "normal": 3, "geo_normal": 3, "shading": 1, "flow": 2
 
 def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp=1, num_layers=1, msaa=False, background=None,
                 bsdf=None, feat=None, render_modes=None, prior_mesh=None, two_sided_shading=True, dino_net=None,
-                num_frames=None, class_vector=None):
+                num_frames=None, class_vector=None, sparse_fields=True):
     assert mesh.t_pos_idx.shape[1] > 0, "Got empty training triangle mesh (unrecoverable discontinuity)"
     assert background is None or (background.shape[1] == resolution[0] and background.shape[2] == resolution[1])
     if num_layers != 1:
@@ -73,9 +97,12 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
                      two_sided=two_sided_shading, want=tuple(want), coverage=coverage)
     gb_tex_pos, cam_normal = gb["tex_pos"], gb["cam_nrm"]
 
-    # pixel shader: field MLPs + light stay PyTorch (render.py:50-94)
+    # pixel shader: field MLPs + light stay PyTorch (render.py:50-94).  The fields are evaluated on COVERED pixels only
+    # (SURVEY.md §8f-1): the reference runs both MLPs (1.6 MFLOP/pixel) on every pixel of the frame although the
+    # composite discards everything where no triangle is visible - ~80 % of a 256^2 training view.
+    sparse = _covered_rows(rast_s) if (sparse_fields and (material is not None or dino_net is not None)) else None
     if material is not None:
-        all_tex = material.sample(gb_tex_pos, feat=feat)
+        all_tex = _sample_field(material, gb_tex_pos, feat, sparse)
     else:
         all_tex = torch.ones(*gb_tex_pos.shape[:-1], 9, device=dev)
     kd, ks = all_tex[..., :3], all_tex[..., 3:6]
@@ -99,7 +126,7 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
     if shading is not None:
         buffers["shading"] = shading
     if dino_net is not None:
-        buffers["dino_pred"] = dino_net.sample(gb_tex_pos, feat=class_vector)
+        buffers["dino_pred"] = _sample_field(dino_net, gb_tex_pos, class_vector, sparse)
     if "flow" in render_modes:  # render.py:281-288
         c2 = v_pos_clip[..., :2] / v_pos_clip[..., -1:]
         c2 = c2.view(-1, num_frames, *c2.shape[1:])
