@@ -743,81 +743,114 @@ __global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_bwd_tile_kernel(AAPa
 // Narrow keys (C <= 4: shaded RGBA, shading, flow, depth): one thread per PIXEL, no shared memory, ~24 registers ->
 // full occupancy.  The warp-tile kernels above pay a fixed per-tile latency chain that only amortises over wide rows.
 // ------------------------------------------------------------------------------------------------------------
+constexpr int AA_PPT = 1;   // pixels per thread (measured: 4 pixels per thread with batched loads was 40 % SLOWER - fewer, fatter threads)
+
 template <int C>
 __global__ void __launch_bounds__(256) aa_fwd_pix_kernel(const float* __restrict__ color, const float* __restrict__ bg, int Bg, AAContext ctx,
                                                          int B, int H, int W, float* __restrict__ out)
 {
     constexpr int CI = C - 1;
     const int HW = H * W;
-    const int64_t flat = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (flat >= (int64_t)B * HW) return;
-    const int b = (int)(flat / HW);
-    const uint32_t cw = __ldg(ctx.cover + (flat >> 5)), aw = __ldg(ctx.act + (flat >> 5));
-    const bool covered = (cw >> (flat & 31)) & 1u, active = (aw >> (flat & 31)) & 1u;
-    float v[C];
-    if (covered) {
+    const int64_t n = (int64_t)B * HW;
+    const int64_t base = (int64_t)blockIdx.x * (blockDim.x * AA_PPT) + threadIdx.x;
+    uint32_t cw[AA_PPT], aw[AA_PPT];
+    float v[AA_PPT][C];
 #pragma unroll
-        for (int c = 0; c < CI; c++) v[c] = __ldg(color + flat * CI + c);
-        v[CI] = 1.f;
-    } else {
-        const float* bp = bg ? bg + (Bg == 1 ? flat - (int64_t)b * HW : flat) * C : nullptr;
-#pragma unroll
-        for (int c = 0; c < C; c++) v[c] = bp ? __ldg(bp + c) : 0.f;
+    for (int j = 0; j < AA_PPT; j++) {
+        const int64_t flat = base + j * blockDim.x;
+        cw[j] = flat < n ? __ldg(ctx.cover + (flat >> 5)) : 0u;
+        aw[j] = flat < n ? __ldg(ctx.act + (flat >> 5)) : 0u;
     }
-    if (active) {
-        const float4 a = __ldg(ctx.rec + flat);
-        const bool k0 = a.x < 0.f, k1 = a.y < 0.f, k2 = a.z > 0.f, k3 = a.w > 0.f;
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            const float own = v[c];
-            const float cu = k0 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - W, c) : own;
-            const float cl = k1 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - 1, c) : own;
-            const float cr = k2 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + 1, c) : own;
-            const float cd = k3 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + W, c) : own;
-            float acc = own;
-            if (k0) acc += a.x * (own - cu);
-            if (k1) acc += a.y * (own - cl);
-            if (k2) acc += a.z * (cr - own);
-            if (k3) acc += a.w * (cd - own);
-            v[c] = acc;
+    for (int j = 0; j < AA_PPT; j++) {
+        const int64_t flat = base + j * blockDim.x;
+        if (flat >= n) continue;
+        if ((cw[j] >> (flat & 31)) & 1u) {
+#pragma unroll
+            for (int c = 0; c < CI; c++) v[j][c] = __ldg(color + flat * CI + c);
+            v[j][CI] = 1.f;
+        } else {
+            const int b = (int)(flat / HW);
+            const float* bp = bg ? bg + (Bg == 1 ? flat - (int64_t)b * HW : flat) * C : nullptr;
+#pragma unroll
+            for (int c = 0; c < C; c++) v[j][c] = bp ? __ldg(bp + c) : 0.f;
         }
     }
-    float* o = out + flat * C;
-    if (C == 4) reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[C - 1]);
-    else if (C == 2) reinterpret_cast<float2*>(o)[0] = make_float2(v[0], v[C - 1]);
-    else {
 #pragma unroll
-        for (int c = 0; c < C; c++) o[c] = v[c];
+    for (int j = 0; j < AA_PPT; j++) {
+        const int64_t flat = base + j * blockDim.x;
+        if (flat >= n) continue;
+        if ((aw[j] >> (flat & 31)) & 1u) {
+            const int b = (int)(flat / HW);
+            const float4 a = __ldg(ctx.rec + flat);
+            const bool k0 = a.x < 0.f, k1 = a.y < 0.f, k2 = a.z > 0.f, k3 = a.w > 0.f;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const float own = v[j][c];
+                const float cu = k0 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - W, c) : own;
+                const float cl = k1 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat - 1, c) : own;
+                const float cr = k2 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + 1, c) : own;
+                const float cd = k3 ? aa_comp<C>(color, bg, Bg, ctx.cover, b, HW, flat + W, c) : own;
+                float acc = own;
+                if (k0) acc += a.x * (own - cu);
+                if (k1) acc += a.y * (own - cl);
+                if (k2) acc += a.z * (cr - own);
+                if (k3) acc += a.w * (cd - own);
+                v[j][c] = acc;
+            }
+        }
+        float* o = out + flat * C;
+        if (C == 4) reinterpret_cast<float4*>(o)[0] = make_float4(v[j][0], v[j][1], v[j][2], v[j][C - 1]);
+        else if (C == 2) reinterpret_cast<float2*>(o)[0] = make_float2(v[j][0], v[j][C - 1]);
+        else {
+#pragma unroll
+            for (int c = 0; c < C; c++) o[c] = v[j][c];
+        }
     }
 }
 
 template <int C, int CC, int CG>
 __global__ void __launch_bounds__(256, 6) aa_bwd_pix_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
-                                                         float* __restrict__ d_pos, int pos_blocks)
+                                                            float* __restrict__ d_pos, int pos_blocks)
 {
     if ((int)blockIdx.x < pos_blocks) {
         aa_bwd_pos_role<C>(P, G, ctx, d_pos, (int)blockIdx.x);
         return;
     }
     const int HW = P.H * P.W;
-    const int64_t flat = (int64_t)(blockIdx.x - pos_blocks) * blockDim.x + threadIdx.x;
-    if (flat >= (int64_t)P.B * HW) return;
-    const int b = (int)(flat / HW), p = (int)(flat - (int64_t)b * HW);
-    const uint32_t cw = __ldg(ctx.cover + (flat >> 5)), aw = __ldg(ctx.act + (flat >> 5));
-    const bool covered = (cw >> (flat & 31)) & 1u, active = covered && ((aw >> (flat & 31)) & 1u);
-    float v[CC];
+    const int64_t n = (int64_t)P.B * HW;
+    const int64_t base = (int64_t)(blockIdx.x - pos_blocks) * (blockDim.x * AA_PPT) + threadIdx.x;
+    uint32_t cw[AA_PPT], aw[AA_PPT];
+    float v[AA_PPT][CC];
 #pragma unroll
-    for (int c = 0; c < CC; c++) v[c] = 0.f;
-    if (covered) {
-        const int py = p / P.W, px = p - py * P.W;
-        const float* gp = G.d_out + (int64_t)b * G.sb + (int64_t)py * G.sy + (int64_t)px * G.sx;
+    for (int j = 0; j < AA_PPT; j++) {
+        const int64_t flat = base + j * blockDim.x;
+        cw[j] = flat < n ? __ldg(ctx.cover + (flat >> 5)) : 0u;
+        aw[j] = flat < n ? __ldg(ctx.act + (flat >> 5)) : 0u;
+    }
 #pragma unroll
-        for (int c = 0; c < CC; c++) v[c] = __ldg(gp + (int64_t)c * G.sc);
-        if (active) {
+    for (int j = 0; j < AA_PPT; j++) {
+        const int64_t flat = base + j * blockDim.x;
+#pragma unroll
+        for (int c = 0; c < CC; c++) v[j][c] = 0.f;
+        if (flat < n && ((cw[j] >> (flat & 31)) & 1u)) {
+            const int b = (int)(flat / HW), p = (int)(flat - (int64_t)b * HW);
+            const int py = p / P.W, px = p - py * P.W;
+            const float* gp = G.d_out + (int64_t)b * G.sb + (int64_t)py * G.sy + (int64_t)px * G.sx;
+#pragma unroll
+            for (int c = 0; c < CC; c++) v[j][c] = __ldg(gp + (int64_t)c * G.sc);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < AA_PPT; j++) {
+        const int64_t flat = base + j * blockDim.x;
+        if (flat >= n) continue;
+        if (((cw[j] & aw[j]) >> (flat & 31)) & 1u) {
+            const int b = (int)(flat / HW), p = (int)(flat - (int64_t)b * HW);
             const float4 a = __ldg(ctx.rec + flat);
 #pragma unroll
             for (int c = 0; c < CC; c++) {
-                const float own = v[c];
+                const float own = v[j][c];
                 const float gu = a.x != 0.f ? (a.x > 0.f ? grad_at(G, P.W, b, p - P.W, c) : own) : 0.f;
                 const float gl = a.y != 0.f ? (a.y > 0.f ? grad_at(G, P.W, b, p - 1, c) : own) : 0.f;
                 const float gr = a.z != 0.f ? (a.z > 0.f ? own : grad_at(G, P.W, b, p + 1, c)) : 0.f;
@@ -827,15 +860,15 @@ __global__ void __launch_bounds__(256, 6) aa_bwd_pix_kernel(AAParams P, AAGrad G
                 if (a.y != 0.f) acc += a.y * gl;
                 if (a.z != 0.f) acc -= a.z * gr;
                 if (a.w != 0.f) acc -= a.w * gd;
-                v[c] = acc;
+                v[j][c] = acc;
             }
         }
-    }
-    float* o = d_color + flat * CC;
-    if (CC == 2) reinterpret_cast<float2*>(o)[0] = make_float2(v[0], v[CC - 1]);
-    else {
+        float* o = d_color + flat * CC;
+        if (CC == 2) reinterpret_cast<float2*>(o)[0] = make_float2(v[j][0], v[j][CC - 1]);
+        else {
 #pragma unroll
-        for (int c = 0; c < CC; c++) o[c] = v[c];
+            for (int c = 0; c < CC; c++) o[c] = v[j][c];
+        }
     }
 }
 
@@ -924,7 +957,7 @@ template <int C>
 void aa_fwd_tile(const float* color, const float* bg, int Bg, const AAContext& ctx, int B, int H, int W, float* out, cudaStream_t stream)
 {
     if constexpr (C <= 4) {   // narrow keys: one thread per pixel
-        aa_fwd_pix_kernel<C><<<b2a_blocks((int64_t)B * H * W, 256), 256, 0, stream>>>(color, bg, Bg, ctx, B, H, W, out);
+        aa_fwd_pix_kernel<C><<<b2a_blocks((int64_t)B * H * W, 256 * AA_PPT), 256, 0, stream>>>(color, bg, Bg, ctx, B, H, W, out);
         return;
     }
     constexpr int TPW = C >= 9 ? 1 : 4;
@@ -964,7 +997,7 @@ bool aa_bwd_tile(const AAParams& P, const AAGrad& G, const AAContext& ctx, float
 {
     const int pos_blocks = d_pos ? AA_POS_BLOCKS : 0;
     if constexpr (CC <= 4) {   // narrow keys: one thread per pixel, any gradient strides
-        unsigned grid = b2a_blocks((int64_t)P.B * P.H * P.W, 256) + pos_blocks;
+        unsigned grid = b2a_blocks((int64_t)P.B * P.H * P.W, 256 * AA_PPT) + pos_blocks;
         aa_bwd_pix_kernel<C, CC, CG><<<grid, 256, 0, stream>>>(P, G, ctx, d_color, d_pos, pos_blocks);
         return true;
     }

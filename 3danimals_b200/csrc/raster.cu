@@ -36,8 +36,11 @@ __global__ void xfm_fwd_kernel(const float* __restrict__ pts, const float* __res
     reinterpret_cast<float4*>(out)[(size_t)b * V + v] = o;
 }
 
-__global__ void xfm_bwd_kernel(const float* __restrict__ pts, const float* __restrict__ mtx, const float* __restrict__ d_out, int B, int Bp,
-                               int64_t V, float* __restrict__ d_pts, float* __restrict__ d_mtx)
+// d_out2 (nullable): a second upstream gradient added to d_out (the fused render node sums the antialias and g-buffer
+// contributions here instead of in a separate add launch); accumulate: d_pts += instead of = (Bp == B case)
+__global__ void xfm_bwd_kernel(const float* __restrict__ pts, const float* __restrict__ mtx, const float* __restrict__ d_out,
+                               const float* __restrict__ d_out2, int accumulate, int B, int Bp, int64_t V, float* __restrict__ d_pts,
+                               float* __restrict__ d_mtx)
 {
     __shared__ float m[16];
     __shared__ float acc[16];
@@ -49,6 +52,10 @@ __global__ void xfm_bwd_kernel(const float* __restrict__ pts, const float* __res
     float x = 0.f, y = 0.f, z = 0.f, one = 0.f;
     if (v < V) {
         g = reinterpret_cast<const float4*>(d_out)[(size_t)b * V + v];
+        if (d_out2) {
+            const float4 g2 = reinterpret_cast<const float4*>(d_out2)[(size_t)b * V + v];
+            g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+        }
         if (d_mtx) {
             const float* p = pts + ((size_t)(Bp == 1 ? 0 : b) * V + v) * 3;
             x = p[0]; y = p[1]; z = p[2]; one = 1.f;
@@ -62,7 +69,8 @@ __global__ void xfm_bwd_kernel(const float* __restrict__ pts, const float* __res
                 atomicAdd(o, dx); atomicAdd(o + 1, dy); atomicAdd(o + 2, dz);
             } else {
                 float* o = d_pts + ((size_t)b * V + v) * 3;
-                o[0] = dx; o[1] = dy; o[2] = dz;
+                if (accumulate) { o[0] += dx; o[1] += dy; o[2] += dz; }
+                else { o[0] = dx; o[1] = dy; o[2] = dz; }
             }
         }
     }
@@ -96,13 +104,15 @@ __device__ __forceinline__ bool tri_bbox(const float4 p0, const float4 p1, const
         float mnx = fminf(sx0, fminf(sx1, sx2)), mxx = fmaxf(sx0, fmaxf(sx1, sx2));
         float mny = fminf(sy0, fminf(sy1, sy2)), mxy = fmaxf(sy0, fmaxf(sy1, sy2));
         if (!(mxx >= 0.f && mnx <= fW && mxy >= 0.f && mny <= fH)) return false;
-        // pixel centre px+.5 in [mn,mx] -> px in [mn-.5, mx-.5]; 1/16 px slack >> fp32 projection error (the oracle
-        // uses a full pixel; the box only has to be conservative, coverage itself is decided by tri_eval)
-        x0 = (int)fmaxf(floorf(mnx - 0.5625f), 0.f);
-        x1 = (int)fminf(ceilf(mxx - 0.4375f), fW - 1.f);
-        y0 = (int)fmaxf(floorf(mny - 0.5625f), 0.f);
-        y1 = (int)fminf(ceilf(mxy - 0.4375f), fH - 1.f);
-        return true;
+        // pixel centre px+.5 in [mn,mx] -> px in [mn-.5, mx-.5], widened by 1/16 px (>> fp32 projection error, ~1e-4 px;
+        // the oracle uses a full pixel; the box only has to be conservative, coverage itself is decided by tri_eval).
+        // Rounding INWARD (ceil / floor): most DMTet triangles are sub-pixel and contain no pixel centre at all - an
+        // outward-rounded box made them evaluate 4 pixels each.
+        x0 = (int)fmaxf(ceilf(mnx - 0.5625f), 0.f);
+        x1 = (int)fminf(floorf(mxx - 0.4375f), fW - 1.f);
+        y0 = (int)fmaxf(ceilf(mny - 0.5625f), 0.f);
+        y1 = (int)fminf(floorf(mxy - 0.4375f), fH - 1.f);
+        return x0 <= x1 && y0 <= y1;
     }
     x0 = 0; x1 = W - 1; y0 = 0; y1 = H - 1;
     return true;
@@ -286,14 +296,15 @@ B2A_API int b2a_xfm_points_fwd(const float* pts, const float* mtx, int B, int Bp
     return 0;
 }
 
-B2A_API int b2a_xfm_points_bwd(const float* pts, const float* mtx, const float* d_out, int B, int Bp, int64_t V, float* d_pts,
-                               float* d_mtx, b2a_stream_t stream_)
+B2A_API int b2a_xfm_points_bwd(const float* pts, const float* mtx, const float* d_out, const float* d_out2, int accumulate, int B, int Bp,
+                               int64_t V, float* d_pts, float* d_mtx, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2A_CHECK_ARG(pts && mtx && d_out, "null pointer");
     B2A_CHECK_ARG(B > 0 && B <= 65535 && (Bp == 1 || Bp == B) && V >= 0, "shape");
+    B2A_CHECK_ARG(((uintptr_t)d_out & 15) == 0 && ((uintptr_t)d_out2 & 15) == 0, "gradients must be 16-byte aligned");
     if (V > 0 && (d_pts || d_mtx))
-        xfm_bwd_kernel<<<dim3(b2a_blocks(V, 256), B), 256, 0, stream>>>(pts, mtx, d_out, B, Bp, V, d_pts, d_mtx);
+        xfm_bwd_kernel<<<dim3(b2a_blocks(V, 256), B), 256, 0, stream>>>(pts, mtx, d_out, d_out2, accumulate, B, Bp, V, d_pts, d_mtx);
     B2A_LAUNCH_OK();
     return 0;
 }

@@ -355,7 +355,7 @@ class _XfmPoints(torch.autograd.Function):
         g = _f32(g, "d_out")
         d_pts = torch.zeros_like(pts) if ctx.needs_input_grad[0] else None
         d_mtx = torch.zeros_like(mtx) if ctx.needs_input_grad[1] else None
-        _call("b2a_xfm_points_bwd", (_p(pts), _p(mtx), _p(g), B, Bp, V, _p(d_pts), _p(d_mtx), _stream()))
+        _call("b2a_xfm_points_bwd", (_p(pts), _p(mtx), _p(g), None, 0, B, Bp, V, _p(d_pts), _p(d_mtx), _stream()))
         return d_pts, d_mtx
 
 
@@ -605,3 +605,91 @@ def gbuffer(rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp=1, tw
     outs = _GBuffer.apply(rast.detach(), pos_clip, _idx32(tri, "tri"), v_pos, v_nrm, prior_pos, w2c, campos, int(spp), bool(two_sided),
                           tuple(want), cl, cc)
     return {k: o for k, o in zip(GB_KEYS, outs) if k in want}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fused geometry half of render_mesh: clip transform -> rasterize -> g-buffer (-> antialias analysis) as ONE autograd
+# node.  Same kernels as the separate ops above; what it removes is host work per step (three autograd nodes forward and
+# backward, two gradient-sum launches, two zero fills): the hot path at B=16 is host-bound.
+# ---------------------------------------------------------------------------------------------------------------
+class _RenderGeometry(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v_pos, v_nrm, prior_pos, mtx, w2c, campos, tri, opp, H, W, spp, two_sided, want, need_aa):
+        L = _L()
+        v_pos = _f32(v_pos, "v_pos"); v_nrm = _f32(v_nrm, "v_nrm"); prior_pos = _f32(prior_pos, "prior_pos")
+        mtx = _f32(mtx, "matrix"); w2c = _f32(w2c, "w2c"); campos = _f32(campos, "campos")
+        B, V = mtx.shape[0], v_pos.shape[1]
+        Bp, Bq, F = v_pos.shape[0], prior_pos.shape[0], tri.shape[0]
+        if Bp != B or w2c.shape != (B, 4, 4) or campos.shape != (B, 3) or v_nrm.shape != v_pos.shape:
+            raise _lib.B2AError("render geometry: inconsistent batch shapes")
+        dev = v_pos.device
+        st = _stream()
+        fH, fW = H * spp, W * spp
+        clip = torch.empty(B, V, 4, device=dev)
+        _call("b2a_xfm_points_fwd", (_p(v_pos), _p(mtx), B, Bp, V, _p(clip), st))
+        ws = _workspace(_size(L.b2a_rasterize_workspace_bytes, B, F, fH, fW), dev)
+        rast = torch.empty(B, fH, fW, 4, device=dev)
+        use_cov = spp == 1
+        cov_list = torch.empty((B * fH * fW, 4), dtype=_i32, device=dev) if use_cov else None
+        cov_count = torch.empty(1, dtype=_i32, device=dev) if use_cov else None
+        _call("b2a_rasterize_fwd", (_p(clip), _p(tri), B, V, F, fH, fW, _p(ws), ws.numel(), _p(rast), _p(cov_list), _p(cov_count), st))
+        outs = [torch.empty(B, H, W, 3, device=dev) if k in want else None for k in GB_KEYS]
+        packed = _workspace(_size(L.b2a_gbuffer_pack_bytes, B, Bq, V), dev)
+        _call("b2a_gbuffer_fwd", (_p(rast), spp, _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), Bq, _p(w2c), _p(campos), int(two_sided), B, V, F,
+                                        H, W, _p(packed), packed.numel(), *[_p(o) for o in outs], st))
+        aa_ctx = None
+        if need_aa and (fH * fW) % 32 == 0 and F < (1 << 28):
+            aa_ctx = _workspace(_size(L.b2a_antialias_workspace_bytes, B, fH, fW), dev)
+            _call("b2a_antialias_prepare", (_p(rast), _p(clip), _p(tri), _p(opp), B, V, F, fH, fW, _p(aa_ctx), aa_ctx.numel(), st))
+        ctx.save_for_backward(rast, clip, tri, v_pos, v_nrm, prior_pos, mtx, w2c, campos, cov_list, cov_count, packed)
+        ctx.cfg = (spp, int(two_sided), H, W, tuple(o is not None for o in outs))
+        ctx.set_materialize_grads(False)   # an unused output (rast outside 'flow' mode) must arrive as None, not as a zero tensor
+        aa_out = aa_ctx if aa_ctx is not None else torch.empty(0, dtype=torch.uint8, device=dev)
+        ctx.mark_non_differentiable(aa_out)
+        return (clip, rast, aa_out) + tuple(o if o is not None else torch.empty(0, device=dev) for o in outs)
+
+    @staticmethod
+    def backward(ctx, d_clip_up, d_rast, _aa, *grads):
+        L = _L()
+        rast, clip, tri, v_pos, v_nrm, prior_pos, mtx, w2c, campos, cov_list, cov_count, packed = ctx.saved_tensors
+        spp, two_sided, H, W, present = ctx.cfg
+        B, V, F = v_pos.shape[0], v_pos.shape[1], tri.shape[0]
+        st = _stream()
+        need = ctx.needs_input_grad
+        gs = [(_f32(g, "d_gb") if (g is not None and p) else None) for g, p in zip(grads, present)]
+        have_gb = any(g is not None for g in gs)
+        d_v_pos = torch.empty_like(v_pos) if (need[0] or True) else None      # also the accumulator of the clip-transform adjoint
+        d_v_nrm = torch.empty_like(v_nrm) if need[1] else None
+        d_prior = torch.empty_like(prior_pos) if need[2] else None
+        d_mtx = torch.zeros_like(mtx) if need[3] else None
+        d_w2c = torch.zeros_like(w2c) if need[4] else None
+        d_campos = torch.zeros_like(campos) if need[5] else None
+        d_clip = torch.empty_like(clip)
+        if have_gb:
+            acc = _gb_accumulator(_size(L.b2a_gbuffer_bwd_workspace_bytes, B, V), rast.device)
+            _call("b2a_gbuffer_bwd", (_p(rast), spp, _p(clip), _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0], _p(w2c),
+                                            _p(campos), two_sided, B, V, F, H, W, _p(packed), packed.numel(), _p(cov_list), _p(cov_count),
+                                            *[_p(g) for g in gs], _p(acc), acc.numel(), 1, _p(d_v_pos), _p(d_v_nrm), _p(d_prior), _p(d_clip),
+                                            _p(d_w2c), _p(d_campos), st))
+        else:
+            d_v_pos.zero_(); d_clip.zero_()
+            for t in (d_v_nrm, d_prior):
+                if t is not None:
+                    t.zero_()
+        if d_rast is not None:      # only the 'flow' mode interpolates with a differentiable rast (render.py:281-288)
+            _call("b2a_rasterize_bwd", (_p(clip), _p(tri), _p(rast), _p(_f32(d_rast, "d_rast")), B, V, F, rast.shape[1], rast.shape[2],
+                                              _p(d_clip), st))
+        up = _f32(d_clip_up, "d_clip") if d_clip_up is not None else None
+        # clip-transform adjoint of (g-buffer/raster contribution + antialias contribution), accumulated into d_v_pos
+        _call("b2a_xfm_points_bwd", (_p(v_pos), _p(mtx), _p(d_clip), _p(up), 1, B, B, V, _p(d_v_pos), _p(d_mtx), st))
+        return (d_v_pos if need[0] else None, d_v_nrm, d_prior, d_mtx, d_w2c, d_campos, None, None, None, None, None, None, None, None)
+
+
+def render_geometry(v_pos, v_nrm, prior_pos, mtx, w2c, campos, tri, opp, resolution, spp=1, two_sided=True, want=("cam_nrm", "tex_pos"),
+                    need_aa=True):
+    """-> (v_pos_clip [B,V,4], rast [B,H*spp,W*spp,4], aa_ctx | None, dict of g-buffers [B,H,W,3]).  rast is differentiable
+    (barycentric gradients of a later ops.interpolate flow into the clip positions, as with nvdiffrast)."""
+    outs = _RenderGeometry.apply(v_pos, v_nrm, prior_pos, mtx, w2c, campos, _idx32(tri, "tri"), _idx32(opp, "opp"), int(resolution[0]),
+                                 int(resolution[1]), int(spp), bool(two_sided), tuple(want), bool(need_aa))
+    clip, rast, aa = outs[0], outs[1], outs[2]
+    return clip, rast, (aa if aa.numel() else None), {k: o for k, o in zip(GB_KEYS, outs[3:]) if k in want}

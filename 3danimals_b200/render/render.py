@@ -80,12 +80,7 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
     if prior_mesh is None:
         prior_mesh = mesh
 
-    # clip-space transform + rasterize (render.py:278, :292-294)
-    v_pos_clip = ops.xfm_points(mesh.v_pos, mtx_in)
-    rast, coverage = ops.rasterize(v_pos_clip, tri, full_res, with_coverage=True)
-    rast_s = rast[:, ::shade_spp, ::shade_spp].contiguous() if shade_spp > 1 else rast
-
-    # fused g-buffer
+    # clip-space transform + rasterize (render.py:278, :292-294) + fused g-buffer + antialias analysis: one autograd node
     want = ["cam_nrm", "tex_pos"]
     if "geo_normal" in render_modes:
         want.append("geo_nrm")
@@ -93,14 +88,20 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
         want.append("shading_nrm")
     if "depth" in render_modes:
         want.append("pos")
-    gb = ops.gbuffer(rast, v_pos_clip, tri, mesh.v_pos, mesh.v_nrm, prior_mesh.v_pos, w2c, campos, spp=shade_spp,
-                     two_sided=two_sided_shading, want=tuple(want), coverage=coverage)
+    need_aa = any(k in _AA_KEYS for k in render_modes)
+    # msaa: rasterize at [H*spp, W*spp], shade the g-buffer at [H,W] from the nearest-downscaled rast (render.py:170-172);
+    # otherwise the g-buffer lives at the raster resolution
+    gres, gspp = ((H, W), spp) if shade_spp > 1 else (full_res, 1)
+    v_pos_clip, rast, aa_ctx, gb = ops.render_geometry(mesh.v_pos, mesh.v_nrm, prior_mesh.v_pos, mtx_in, w2c, campos, tri, opp, gres,
+                                                       spp=gspp, two_sided=two_sided_shading, want=tuple(want), need_aa=need_aa)
+    rast_s = rast[:, ::shade_spp, ::shade_spp].contiguous() if shade_spp > 1 else rast
     gb_tex_pos, cam_normal = gb["tex_pos"], gb["cam_nrm"]
 
     # pixel shader: field MLPs + light stay PyTorch (render.py:50-94).  The fields are evaluated on COVERED pixels only
     # (SURVEY.md §8f-1): the reference runs both MLPs (1.6 MFLOP/pixel) on every pixel of the frame although the
     # composite discards everything where no triangle is visible - ~80 % of a 256^2 training view.
-    sparse = _covered_rows(rast_s) if (sparse_fields and (material is not None or dino_net is not None)) else None
+    nets = [n for n in (material, dino_net) if n is not None and not getattr(n, "dense_only", False)]
+    sparse = _covered_rows(rast_s) if (sparse_fields and nets) else None
     if material is not None:
         all_tex = _sample_field(material, gb_tex_pos, feat, sparse)
     else:
@@ -147,7 +148,6 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
     else:
         bg_full = None
 
-    aa_ctx = ops.antialias_prepare(rast, v_pos_clip.detach(), tri, opp) if any(k in _AA_KEYS and k in buffers for k in render_modes) else None
     out_buffers = []
     for key in render_modes:
         if key not in buffers:

@@ -201,7 +201,7 @@ def run_ours(args):
     # ---- live per-kernel timing of the raster backward (same step, CUDA events on the launching stream) --------
     ops.stats.reset()
     ops.stats.timing = True
-    ops.stats.spin_cycles = 60000     # ~30 us of device spin before each start event: launches are queued when it fires
+    ops.stats.spin_cycles = 300000    # ~150 us of device spin before each start event: launches are queued when it fires
     for _ in range(min(args.steps, 5)):
         step()
     torch.cuda.synchronize()

@@ -100,12 +100,13 @@ int b2a_vertex_normals_bwd(const float* v_pos, const int32_t* tri, const float* 
 
 /* ------------------------------------------------------------------------------------------------------------
  * Clip-space transform.  Replaces ru.xfm_points(use_python=True) (model/render/renderutils/ops.py:524-525).
- * pts [Bp,V,3] (Bp in {1,B}), mtx [B,4,4] -> out [B,V,4].  Backward: d_pts accumulated when Bp==1<B (zero-init),
+ * pts [Bp,V,3] (Bp in {1,B}), mtx [B,4,4] -> out [B,V,4].  Backward: upstream gradient d_out (+ d_out2, nullable: a second
+ * contribution summed on the fly); d_pts accumulated when Bp==1<B (zero-init) or when `accumulate` is set, else written;
  * d_mtx [B,16] accumulated (zero-init); either may be NULL.
  * ---------------------------------------------------------------------------------------------------------- */
 int b2a_xfm_points_fwd(const float* pts, const float* mtx, int B, int Bp, int64_t V, float* out, b2a_stream_t stream);
-int b2a_xfm_points_bwd(const float* pts, const float* mtx, const float* d_out, int B, int Bp, int64_t V,
-                       float* d_pts, float* d_mtx, b2a_stream_t stream);
+int b2a_xfm_points_bwd(const float* pts, const float* mtx, const float* d_out, const float* d_out2, int accumulate,
+                       int B, int Bp, int64_t V, float* d_pts, float* d_mtx, b2a_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Rasterizer.  Replaces nvdiffrast.torch.rasterize / DepthPeeler first layer (call sites model/render/render.py:
