@@ -35,7 +35,7 @@ def parse_header(path=HEADER):
                 typ = a[: -len(pname)].strip()
                 if typ.endswith("*"):
                     base = typ[:-1].replace("const", "").strip()
-                    ctype = C.POINTER(C.c_size_t) if base == "size_t" else C.c_void_p
+                    ctype = C.POINTER(C.c_size_t) if base == "size_t" else (C.POINTER(C.c_int) if base == "int" else C.c_void_p)
                 else:
                     ctype = _SCALARS[typ.replace("const", "").strip()]
                 params.append((ctype, pname))

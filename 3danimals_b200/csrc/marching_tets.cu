@@ -20,6 +20,7 @@ __constant__ int8_t c_base_edges[12] = {0, 1, 0, 2, 0, 3, 1, 2, 1, 3, 2, 3};
 
 struct MtWorkspace {
     uint32_t* occ_bits;   // [ceil(Vg/32)]
+    uint32_t* cand_bits;  // [ceil(Vg/32)] vertices of tets that straddle the surface (the only ones that can own a crossing edge)
     uint8_t* vcnt;        // [Vg]
     int* vtile;           // [nVT]
     uint8_t* tetidx;      // [T]
@@ -37,6 +38,7 @@ size_t mt_layout(int64_t Vg, int64_t E, int64_t T, void* base, MtWorkspace* ws)
     char* p = (char*)base;
     auto take = [&](size_t bytes) { size_t o = off; off += b2a_align(bytes); return p ? (void*)(p + o) : nullptr; };
     void* occ = take((size_t)((Vg + 31) / 32) * 4);
+    void* cand = take((size_t)((Vg + 31) / 32) * 4);
     void* vcnt = take((size_t)Vg);
     void* vtile = take((size_t)(nVT + 1) * 4);
     void* tetidx = take((size_t)T);
@@ -45,7 +47,7 @@ size_t mt_layout(int64_t Vg, int64_t E, int64_t T, void* base, MtWorkspace* ws)
     void* ev = take((size_t)E * 4);
     void* err = take(256);
     if (ws) {
-        ws->occ_bits = (uint32_t*)occ; ws->vcnt = (uint8_t*)vcnt; ws->vtile = (int*)vtile;
+        ws->occ_bits = (uint32_t*)occ; ws->cand_bits = (uint32_t*)cand; ws->vcnt = (uint8_t*)vcnt; ws->vtile = (int*)vtile;
         ws->tetidx = (uint8_t*)tetidx; ws->t1tile = (int*)t1; ws->t2tile = (int*)t2;
         ws->edge_vidx = (int*)ev; ws->err = (int*)err; ws->nVT = nVT; ws->nTT = nTT;
     }
@@ -70,19 +72,28 @@ __global__ void __launch_bounds__(MT_BLOCK) mt_occ_kernel(const float* __restric
     }
 }
 
-// crossing edges per min-vertex + per-tile totals
+// crossing edges per min-vertex + per-tile totals.  Runs after mt_tcount: only vertices of surface-straddling tets
+// (cand bits) can own a crossing edge, so a tile without candidates leaves after one 64-byte read and the 60 MB edge CSR
+// is only touched along the surface.
 __global__ void __launch_bounds__(MT_BLOCK) mt_vcount_kernel(const int* __restrict__ edge_start, const int* __restrict__ edge_b,
-                                                             const uint32_t* __restrict__ bits, int64_t Vg,
+                                                             const uint32_t* __restrict__ bits, const uint32_t* __restrict__ cand, int64_t Vg,
                                                              uint8_t* __restrict__ vcnt, int* __restrict__ vtile, int* __restrict__ err)
 {
     __shared__ int sm[34];
     int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cw = a < Vg ? __ldg(cand + (a >> 5)) : 0u;
+    if (!__syncthreads_or(cw != 0u)) {
+        if (threadIdx.x == 0) vtile[blockIdx.x] = 0;
+        return;
+    }
     int cnt = 0;
     if (a < Vg) {
-        int s = __ldg(edge_start + a), e = __ldg(edge_start + a + 1);
-        bool oa = occ_at(bits, (int)a);
-        for (int i = s; i < e; i++) cnt += (occ_at(bits, __ldg(edge_b + i)) != oa);
-        if (cnt > 255) { atomicExch(err, 1); cnt = 255; }
+        if ((cw >> (a & 31)) & 1u) {
+            int s = __ldg(edge_start + a), e = __ldg(edge_start + a + 1);
+            bool oa = occ_at(bits, (int)a);
+            for (int i = s; i < e; i++) cnt += (occ_at(bits, __ldg(edge_b + i)) != oa);
+            if (cnt > 255) { atomicExch(err, 1); cnt = 255; }
+        }
         vcnt[a] = (uint8_t)cnt;
     }
     // only the tile total is needed here
@@ -100,29 +111,52 @@ __global__ void __launch_bounds__(MT_BLOCK) mt_vcount_kernel(const int* __restri
 // consecutive tets; a block streams MT_TPB tiles, four 16-byte tet loads in flight per thread; only the tile TOTALS are
 // needed here (warp ballots + one shared-memory atomic per warp), the ordered positions are recomputed by the emit
 // kernel for the few tiles that hold triangles.
+// tile_words (nullable): static per-grid table [nTT, MT_TILE_WORDS] of the occupancy words a tile's tets touch (built once
+// when the grid is loaded; -1 in slot 0: too many to list).  If all of them are all-zero or all-one the tile cannot
+// straddle the surface and its 8 KB of tet indices are never read: the extraction streams the surface band, not the grid.
 constexpr int MT_TPB = 4;
+constexpr int MT_TILE_WORDS = 32;
 __global__ void __launch_bounds__(MT_BLOCK) mt_tcount_kernel(const int4* __restrict__ tets, const uint32_t* __restrict__ bits,
-                                                             int64_t T, uint8_t* __restrict__ tetidx, int* __restrict__ t1tile,
-                                                             int* __restrict__ t2tile)
+                                                             const int* __restrict__ tile_words, int64_t T, int64_t nTT,
+                                                             uint8_t* __restrict__ tetidx, int* __restrict__ t1tile, int* __restrict__ t2tile,
+                                                             uint32_t* __restrict__ cand)
 {
     __shared__ int s_cnt[MT_TPB][2];
+    __shared__ int s_live[MT_TPB];
     if (threadIdx.x < MT_TPB * 2) (&s_cnt[0][0])[threadIdx.x] = 0;
-    __syncthreads();
     const int64_t tile0 = (int64_t)blockIdx.x * MT_TPB;
+    if (threadIdx.x < MT_TPB * 32) {
+        const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        bool live = true;
+        if (tile_words && tile0 + k < nTT) {
+            const int widx = __ldg(tile_words + (tile0 + k) * MT_TILE_WORDS + lane);
+            const bool always = __shfl_sync(0xffffffffu, widx, 0) < 0;
+            const uint32_t w = (always || widx < 0) ? 1u : __ldg(bits + widx);
+            const bool z = __all_sync(0xffffffffu, w == 0u), o = __all_sync(0xffffffffu, w == 0xffffffffu);
+            live = always || !(z || o);
+        }
+        if (lane == 0) s_live[k] = live;
+    }
+    __syncthreads();
     int4 q[MT_TPB];
 #pragma unroll
     for (int k = 0; k < MT_TPB; k++) {
         const int64_t t = (tile0 + k) * MT_BLOCK + threadIdx.x;
-        q[k] = t < T ? __ldg(tets + t) : make_int4(0, 0, 0, 0);
+        q[k] = (s_live[k] && t < T) ? __ldg(tets + t) : make_int4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int k = 0; k < MT_TPB; k++) {
+        if (!s_live[k]) continue;
         const int64_t t = (tile0 + k) * MT_BLOCK + threadIdx.x;
         int n = 0;
         if (t < T) {
             int ti = (int)occ_at(bits, q[k].x) | ((int)occ_at(bits, q[k].y) << 1) | ((int)occ_at(bits, q[k].z) << 2) | ((int)occ_at(bits, q[k].w) << 3);
             tetidx[t] = (uint8_t)ti;
             n = c_num_tri[ti];
+            if (n) {   // straddles the surface: its vertices are the candidates for crossing edges
+                atomicOr(cand + (q[k].x >> 5), 1u << (q[k].x & 31)); atomicOr(cand + (q[k].y >> 5), 1u << (q[k].y & 31));
+                atomicOr(cand + (q[k].z >> 5), 1u << (q[k].z & 31)); atomicOr(cand + (q[k].w >> 5), 1u << (q[k].w & 31));
+            }
         }
         const unsigned m1 = __ballot_sync(0xffffffffu, n == 1), m2 = __ballot_sync(0xffffffffu, n == 2);
         if ((threadIdx.x & 31) == 0) {
@@ -131,7 +165,7 @@ __global__ void __launch_bounds__(MT_BLOCK) mt_tcount_kernel(const int4* __restr
         }
     }
     __syncthreads();
-    if (threadIdx.x < MT_TPB && (tile0 + threadIdx.x) * MT_BLOCK < T) {
+    if (threadIdx.x < MT_TPB && tile0 + threadIdx.x < nTT) {
         t1tile[tile0 + threadIdx.x] = s_cnt[threadIdx.x][0];
         t2tile[tile0 + threadIdx.x] = s_cnt[threadIdx.x][1];
     }
@@ -241,14 +275,23 @@ __global__ void __launch_bounds__(MT_BLOCK) mt_vemit_kernel(const float* __restr
     }
 }
 
+// output-vertex id of grid edge (va,vb): position of max(va,vb) in the CSR row of min(va,vb).  The first 16 row entries
+// are fetched with independent predicated loads (one latency instead of a serial compare-and-branch walk; Kuhn rows hold
+// <= 14 entries), longer rows continue with a loop.
 __device__ __forceinline__ int find_edge_vertex(const int* __restrict__ edge_start, const int* __restrict__ edge_b,
                                                 const int* __restrict__ edge_vidx, int va, int vb)
 {
     int lo = min(va, vb), hi = max(va, vb);
     int s = __ldg(edge_start + lo), e = __ldg(edge_start + lo + 1);
-    for (int i = s; i < e; i++)
-        if (__ldg(edge_b + i) == hi) return edge_vidx[i];
-    return -1;
+    int hit = -1;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        int b = s + j < e ? __ldg(edge_b + s + j) : -1;
+        if (b == hi) hit = s + j;
+    }
+    for (int i = s + 16; i < e && hit < 0; i++)
+        if (__ldg(edge_b + i) == hi) hit = i;
+    return hit >= 0 ? edge_vidx[hit] : -1;
 }
 
 // emit faces (dmtet.py:139-151) and uv indices (map_uv :86-96)
@@ -261,7 +304,8 @@ __global__ void __launch_bounds__(MT_BLOCK) mt_temit_kernel(const int4* __restri
 {
     __shared__ int sm[34];
     __shared__ int s_list[MT_BLOCK];
-    __shared__ int s_n;
+    __shared__ int s_n, s_m;
+    __shared__ int s_rec[MT_BLOCK][7];
     // Phase A: one thread per tile finds the tiles that hold surface
     // (few) - one round of loads instead of a serial walk; phase B: emit those tiles.
     // (tiles are dealt round-robin: the surface occupies a contiguous band of tiles, contiguous ranges would pile it
@@ -284,24 +328,31 @@ __global__ void __launch_bounds__(MT_BLOCK) mt_temit_kernel(const int4* __restri
         int tot;
         int ex = block_exclusive_scan((int)(n == 1) | ((int)(n == 2) << 16), sm, &tot);   // both counts in one scan (MT_BLOCK < 2^16)
         int e1 = ex & 0xffff, e2 = ex >> 16;
-        if (n == 0) continue;
-        int64_t fbase = n == 1 ? (int64_t)base1 + e1 : N1 + 2 * ((int64_t)base2 + e2);
-        int4 q = __ldg(tets + t);
-        int tv[4] = {q.x, q.y, q.z, q.w};
-        for (int k = 0; k < n; k++) {
-            int64_t f = fbase + k;
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                int le = c_tri_table[ti][k * 3 + c];
-                int vid = find_edge_vertex(edge_start, edge_b, edge_vidx, tv[c_base_edges[le * 2]], tv[c_base_edges[le * 2 + 1]]);
-                if (faces32) faces32[f * 3 + c] = vid;
-                if (faces64) faces64[f * 3 + c] = vid;
-            }
+        // surface tets of the tile -> shared list; then ONE (tet, triangle corner) lookup per thread, all in flight together
+        // (a thread walking its own 3-6 corners serialises ~20 dependent L2 round trips)
+        if (threadIdx.x == 0) s_m = 0;
+        __syncthreads();
+        if (n) {
+            int64_t fbase = n == 1 ? (int64_t)base1 + e1 : N1 + 2 * ((int64_t)base2 + e2);
+            int slot = atomicAdd(&s_m, 1);
+            int4 q = __ldg(tets + t);
+            s_rec[slot][0] = (int)fbase; s_rec[slot][1] = ti | (n << 8); s_rec[slot][2] = threadIdx.x;
+            s_rec[slot][3] = q.x; s_rec[slot][4] = q.y; s_rec[slot][5] = q.z; s_rec[slot][6] = q.w;
+        }
+        __syncthreads();
+        const int items = s_m * 6;
+        for (int it = threadIdx.x; it < items; it += blockDim.x) {
+            const int r = it / 6, slot6 = it - r * 6, k = slot6 / 3, c = slot6 - k * 3;
+            const int tin = s_rec[r][1], ti2 = tin & 0xff, n2 = tin >> 8;
+            if (k >= n2) continue;
+            const int64_t f = (int64_t)s_rec[r][0] + k;
+            const int le = c_tri_table[ti2][k * 3 + c];
+            const int vid = find_edge_vertex(edge_start, edge_b, edge_vidx, s_rec[r][3 + c_base_edges[le * 2]], s_rec[r][3 + c_base_edges[le * 2 + 1]]);
+            if (faces32) faces32[f * 3 + c] = vid;
+            if (faces64) faces64[f * 3 + c] = vid;
             if (uv64) {
-                long long g = (long long)t * 4;
-                uv64[f * 3 + 0] = g;
-                uv64[f * 3 + 1] = g + k + 1;
-                uv64[f * 3 + 2] = g + k + 2;
+                const long long g = (long long)(tile * blockDim.x + s_rec[r][2]) * 4;
+                uv64[f * 3 + c] = c == 0 ? g : g + k + c;     // (4t, 4t+k+1, 4t+k+2)
             }
         }
     }
@@ -341,9 +392,17 @@ B2A_API int b2a_mt_workspace_bytes(int64_t Vg, int64_t E, int64_t T, size_t* byt
     return 0;
 }
 
+B2A_API int b2a_mt_tile_shape(int* tile_tets, int* tile_words)
+{
+    B2A_CHECK_ARG(tile_tets && tile_words, "null pointer");
+    *tile_tets = MT_BLOCK;
+    *tile_words = MT_TILE_WORDS;
+    return 0;
+}
+
 B2A_API int b2a_mt_count(const float* sdf, const int32_t* tets, const int32_t* edge_start, const int32_t* edge_b,
-                         int64_t Vg, int64_t E, int64_t T, void* workspace, size_t workspace_bytes, int32_t* counts,
-                         b2a_stream_t stream_)
+                         const int32_t* tile_words, int64_t Vg, int64_t E, int64_t T, void* workspace, size_t workspace_bytes,
+                         int32_t* counts, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2A_CHECK_ARG(sdf && tets && edge_start && edge_b && workspace && counts, "null pointer");
@@ -352,9 +411,11 @@ B2A_API int b2a_mt_count(const float* sdf, const int32_t* tets, const int32_t* e
     MtWorkspace ws;
     B2A_CHECK_ARG(mt_layout(Vg, E, T, workspace, &ws) <= workspace_bytes, "workspace too small");
     B2A_CUDA_OK(cudaMemsetAsync(ws.err, 0, 4, stream));
+    B2A_CUDA_OK(cudaMemsetAsync(ws.cand_bits, 0, (size_t)((Vg + 31) / 32) * 4, stream));
     mt_occ_kernel<<<b2a_blocks(Vg, MT_BLOCK * 4), MT_BLOCK, 0, stream>>>(sdf, Vg, ws.occ_bits);
-    mt_vcount_kernel<<<(unsigned)ws.nVT, MT_BLOCK, 0, stream>>>(edge_start, edge_b, ws.occ_bits, Vg, ws.vcnt, ws.vtile, ws.err);
-    mt_tcount_kernel<<<(unsigned)((ws.nTT + MT_TPB - 1) / MT_TPB), MT_BLOCK, 0, stream>>>((const int4*)tets, ws.occ_bits, T, ws.tetidx, ws.t1tile, ws.t2tile);
+    mt_tcount_kernel<<<(unsigned)((ws.nTT + MT_TPB - 1) / MT_TPB), MT_BLOCK, 0, stream>>>((const int4*)tets, ws.occ_bits, tile_words, T, ws.nTT,
+                                                                                          ws.tetidx, ws.t1tile, ws.t2tile, ws.cand_bits);
+    mt_vcount_kernel<<<(unsigned)ws.nVT, MT_BLOCK, 0, stream>>>(edge_start, edge_b, ws.occ_bits, ws.cand_bits, Vg, ws.vcnt, ws.vtile, ws.err);
     ScanJob j0{ws.vtile, ws.nVT}, j1{ws.t1tile, ws.nTT}, j2{ws.t2tile, ws.nTT};
     mt_scan_tiles_kernel<<<3, 1024, 0, stream>>>(j0, j1, j2, counts);
     B2A_CUDA_OK(cudaMemcpyAsync(counts + 3, ws.err, 4, cudaMemcpyDeviceToDevice, stream));

@@ -147,8 +147,38 @@ class TetGrid:
         start[1:] = torch.cumsum(torch.bincount(a, minlength=self.Vg), 0)
         self.edge_start = start.to(_i32).contiguous()
         self.tets = tets.to(_i32).contiguous()
+        self.tile_words = self._build_tile_words()
         self.workspace = _workspace(_size(_L().b2a_mt_workspace_bytes, self.Vg, self.E, self.T), tets.device)
         self.counts = torch.zeros(4, dtype=_i32, device=tets.device)
+
+    def _build_tile_words(self):
+        """Static skip table of the extraction (csrc/marching_tets.cu mt_tcount): for every tile of consecutive tets the
+        (<= 32) occupancy words its vertices live in.  One-off, chunked to bound the transient memory."""
+        import ctypes
+        tt, tw = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(_L().b2a_mt_tile_shape(ctypes.byref(tt), ctypes.byref(tw)))
+        tile, Wn = tt.value, tw.value
+        dev = self.tets.device
+        nTT = (self.T + tile - 1) // tile
+        out = torch.empty(nTT, Wn, dtype=_i32, device=dev)
+        step = 2048                                   # tiles per chunk: 2048 x 2048 entries
+        for t0 in range(0, nTT, step):
+            t1 = min(t0 + step, nTT)
+            w = (self.tets[t0 * tile:min(t1 * tile, self.T)] >> 5).reshape(-1)
+            need = (t1 - t0) * tile * 4
+            if w.numel() < need:                      # last tile: pad by repeating the final tet's words
+                w = torch.cat([w, w[-4:].repeat((need - w.numel()) // 4)])
+            ws = torch.sort(w.view(t1 - t0, tile * 4), dim=1).values
+            first = torch.ones_like(ws, dtype=torch.bool)
+            first[:, 1:] = ws[:, 1:] != ws[:, :-1]
+            rank = torch.cumsum(first, 1) - 1
+            chunk = ws[:, :1].expand(-1, Wn).clone()
+            sel = first & (rank < Wn)
+            rows = torch.arange(t1 - t0, device=dev)[:, None].expand_as(ws)[sel]
+            chunk[rows, rank[sel]] = ws[sel]
+            chunk[rank[:, -1] >= Wn, 0] = -1          # touches more words than the table holds: never skipped
+            out[t0:t1] = chunk
+        return out.contiguous()
 
     def all_edges(self):
         """[E,2] int64, identical to the reference's DMTetGeometry.all_edges."""
@@ -166,7 +196,7 @@ class _MarchingTets(torch.autograd.Function):
         if pos_c.shape[0] != grid.Vg or sdf_c.shape[0] != grid.Vg:
             raise _lib.B2AError("marching_tets: pos/sdf do not match the grid (%d verts)" % grid.Vg)
         st = _stream()
-        _call("b2a_mt_count", (_p(sdf_c), _p(grid.tets), _p(grid.edge_start), _p(grid.edge_b), grid.Vg, grid.E, grid.T,
+        _call("b2a_mt_count", (_p(sdf_c), _p(grid.tets), _p(grid.edge_start), _p(grid.edge_b), _p(grid.tile_words), grid.Vg, grid.E, grid.T,
                                   _p(grid.workspace), grid.workspace.numel(), _p(grid.counts), st))
         V, N1, N2, err = grid.counts.tolist()  # the one device->host read of the extraction (output sizes)
         if err:

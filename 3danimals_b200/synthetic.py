@@ -42,6 +42,34 @@ def kuhn_tet_grid(res):
     return verts, tets
 
 
+def kuhn_tet_grid_torch(res, device):
+    """kuhn_tet_grid on a torch device (identical tets in identical order; vertices equal up to linspace rounding): the
+    res-256 grid has 100 M tets - minutes in numpy, a second on the GPU.  Returns vertices [Vg,3] f32, indices [T,4] i64."""
+    import torch
+    n = res + 1
+    lin = torch.linspace(-0.5, 0.5, n, dtype=torch.float32, device=device)
+    gx, gy, gz = torch.meshgrid(lin, lin, lin, indexing="ij")
+    verts = torch.stack([gx, gy, gz], -1).reshape(-1, 3)
+    r = torch.arange(res, device=device)
+    ci, cj, ck = torch.meshgrid(r, r, r, indexing="ij")
+    base = torch.stack([ci, cj, ck], -1).reshape(-1, 3)
+    vid = lambda p: (p[:, 0] * n + p[:, 1]) * n + p[:, 2]
+    tets = []
+    for perm in itertools.permutations(range(3)):
+        p = base.clone()
+        path = [vid(p)]
+        for ax in perm:
+            p = p.clone()
+            p[:, ax] += 1
+            path.append(vid(p))
+        # orientation = parity of the axis permutation (see kuhn_tet_grid): even permutations are the positively oriented ones
+        parity = sum(1 for a in range(3) for b in range(a + 1, 3) if perm[a] > perm[b]) % 2
+        if parity == 0:
+            path[2], path[3] = path[3], path[2]
+        tets.append(torch.stack(path, -1))
+    return verts, torch.stack(tets, 1).reshape(-1, 4)
+
+
 def write_tet_npz(res, root="data/tets"):
     """Writes data/tets/{res}_tets.npz in the reference schema (dmtet.py:223)."""
     os.makedirs(root, exist_ok=True)

@@ -38,8 +38,12 @@ const char* b2a_last_error_string(void);
  *          may be NULL.
  * ---------------------------------------------------------------------------------------------------------- */
 int b2a_mt_workspace_bytes(int64_t Vg, int64_t E, int64_t T, size_t* bytes);
+/* tile_words (nullable): static per-grid table [ceil(T/tile_tets), tile_words] int32 of the occupancy words (vertex >> 5)
+ * touched by each tile of tile_tets consecutive tets, padded by repeating an entry; -1 in slot 0 = "too many, never skip".
+ * Tiles whose words are uniformly inside or outside are not read at all.  Shape constants: b2a_mt_tile_shape. */
+int b2a_mt_tile_shape(int* tile_tets, int* tile_words);
 int b2a_mt_count(const float* sdf, const int32_t* tets, const int32_t* edge_start, const int32_t* edge_b,
-                 int64_t Vg, int64_t E, int64_t T, void* workspace, size_t workspace_bytes,
+                 const int32_t* tile_words, int64_t Vg, int64_t E, int64_t T, void* workspace, size_t workspace_bytes,
                  int32_t* counts /* device [4] */, b2a_stream_t stream);
 int b2a_mt_emit(const float* pos, const float* sdf, const int32_t* tets, const int32_t* edge_start,
                 const int32_t* edge_b, int64_t Vg, int64_t E, int64_t T, void* workspace, size_t workspace_bytes,

@@ -239,6 +239,34 @@ def test_xfm_points_oracle(cuda, Bp):
     assert rel_err(md.grad.cpu().numpy(), mt.grad.numpy()) < TOL
 
 
+def test_marching_tets_res256_capacity(cuda):
+    """BASELINE configs[4] grid size (DMTet res 256: 17 M grid vertices, 100 M tets, 1.6 GB of tet indices): the extraction
+    runs, agrees with a second run bit for bit, and yields a closed, consistently oriented surface of the expected size
+    (vertex count scales ~4x per resolution doubling)."""
+    ops = _ops()
+    v, t = syn.kuhn_tet_grid_torch(256, cuda)
+    v = v * 7.0
+    q = v.clone()
+    q[:, 2] = q[:, 2] / 2
+    sdf = (1.05 - q.norm(dim=-1))[:, None].contiguous()          # the reference's ellipsoid init (dmtet.py:246-250)
+    grid = ops.TetGrid(t, v.shape[0])
+    del t, q
+    assert grid.T == 6 * 256 ** 3 and grid.Vg == 257 ** 3
+    assert int((grid.tile_words[:, 0] < 0).sum()) == 0          # every tile of the lattice fits the skip table
+    verts, faces, uv_idx, faces32, vert_edge = ops.marching_tets(v, sdf, grid)
+    verts2, faces2, _, _, _ = ops.marching_tets(v, sdf, grid)
+    assert torch.equal(verts, verts2) and torch.equal(faces, faces2)
+    V, F = verts.shape[0], faces.shape[0]
+    assert 100_000 < V < 200_000 and F == 2 * V - 4               # genus-0 closed triangle mesh: F = 2V - 4
+    e = torch.cat([faces[:, [0, 1]], faces[:, [1, 2]], faces[:, [2, 0]]])
+    assert torch.unique(e[:, 0] * V + e[:, 1]).numel() == e.shape[0]                       # consistently oriented
+    _, cnt = torch.unique(torch.minimum(e[:, 0], e[:, 1]) * V + torch.maximum(e[:, 0], e[:, 1]), return_counts=True)
+    assert bool((cnt == 2).all())                                                          # closed 2-manifold
+    r = (verts * torch.tensor([1.0, 1.0, 0.5], device=cuda)).norm(dim=-1)
+    assert float((r - 1.05).abs().max()) < 1e-3                                            # vertices lie on the iso-surface
+    assert torch.equal(uv_idx[:, 0] % 4, torch.zeros_like(uv_idx[:, 0]))
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # rasterize / interpolate / antialias
 # ----------------------------------------------------------------------------------------------------------------
