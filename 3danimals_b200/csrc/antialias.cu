@@ -487,18 +487,17 @@ __device__ __forceinline__ int nth_bit(uint32_t m, int j) { return (int)__fns(m,
 // pixels are fixed in place (work items = active pixel x channel, spread over the lanes) before the float4 stores.
 // A warp owns TPW consecutive tiles and issues the colour loads of all of them up front (bytes in flight).
 template <int C, int TPW>
-__global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_fwd_tile_kernel(const float* __restrict__ color, const float* __restrict__ bg, int Bg, AAContext ctx,
-                                                          int B, int H, int W, float* __restrict__ out)
+__device__ __forceinline__ void aa_fwd_tile_body(const float* __restrict__ color, const float* __restrict__ bg, int Bg, const AAContext& ctx,
+                                                 int B, int H, int W, float* __restrict__ out, int64_t vblock, float* __restrict__ smem)
 {
     constexpr int CI = C - 1;
     constexpr int NV = (8 * CI + 31) / 32;   // float4 colour loads per lane per tile
-    __shared__ __align__(16) float s_tile[8][32 * C];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int HW = H * W;
     const int64_t ntiles = ((int64_t)B * HW) / 32;
-    const int64_t t0 = ((int64_t)blockIdx.x * 8 + w) * TPW;
+    const int64_t t0 = (vblock * 8 + w) * TPW;
     if (t0 >= ntiles) return;
-    float* tile = s_tile[w];
+    float* tile = smem + w * (32 * C);
     uint32_t cov[TPW], act[TPW];
     float4 cv[TPW][NV];
 #pragma unroll
@@ -581,6 +580,14 @@ __global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_fwd_tile_kernel(cons
     }
 }
 
+template <int C, int TPW>
+__global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_fwd_tile_kernel(const float* __restrict__ color, const float* __restrict__ bg, int Bg, AAContext ctx,
+                                                          int B, int H, int W, float* __restrict__ out)
+{
+    __shared__ __align__(16) float s_tile[8 * 32 * C];
+    aa_fwd_tile_body<C, TPW>(color, bg, Bg, ctx, B, H, W, out, (int64_t)blockIdx.x, s_tile);
+}
+
 constexpr int AA_POS_BLOCKS = 148 * 4;
 
 // vertex-position gradient role: one half-warp per owned pair of an active pixel, channels across the 16 lanes.  All
@@ -627,22 +634,17 @@ __device__ __forceinline__ void aa_bwd_pos_role(const AAParams& P, const AAGrad&
 // the narrow keys are latency-bound otherwise).  Per tile the smem tile [pp*ST + c] holds g; covered silhouette elements
 // gather their pair terms in place, then masked float4 stores.
 template <int C, int CC, int CG, bool NCHW, int TPW>
-__global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_bwd_tile_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
-                                                                            float* __restrict__ d_pos, int pos_blocks)
+__device__ __forceinline__ void aa_bwd_tile_body(const AAParams& P, const AAGrad& G, const AAContext& ctx, float* __restrict__ d_color,
+                                                 int64_t vblock, float* __restrict__ smem)
 {
     constexpr int ST = CG + 1;   // padded pixel stride: conflict-free for both access patterns
     constexpr int NV = NCHW ? CC : (8 * CG + 31) / 32;   // registers per lane per tile: scalars (NCHW) or float4s (NHWC)
-    __shared__ float s_tile[8][32 * ST];
-    if ((int)blockIdx.x < pos_blocks) {   // first in the grid: their latency chains overlap the streaming blocks
-        aa_bwd_pos_role<C>(P, G, ctx, d_pos, (int)blockIdx.x);
-        return;
-    }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int HW = P.H * P.W;
     const int64_t ntiles = ((int64_t)P.B * HW) / 32;
-    const int64_t t0 = ((int64_t)(blockIdx.x - pos_blocks) * 8 + w) * TPW;
+    const int64_t t0 = (vblock * 8 + w) * TPW;
     if (t0 >= ntiles) return;
-    float* tile = s_tile[w];
+    float* tile = smem + w * (32 * ST);
     uint32_t cov[TPW], act[TPW];
     float vs[NCHW ? TPW : 1][NCHW ? NV : 1];
     float4 vv[NCHW ? 1 : TPW][NCHW ? 1 : NV];
@@ -739,6 +741,18 @@ __global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_bwd_tile_kernel(AAPa
     }
 }
 
+template <int C, int CC, int CG, bool NCHW, int TPW>
+__global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_bwd_tile_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
+                                                                            float* __restrict__ d_pos, int pos_blocks)
+{
+    __shared__ float s_tile[8 * 32 * (CG + 1)];
+    if ((int)blockIdx.x < pos_blocks) {   // first in the grid: their latency chains overlap the streaming blocks
+        aa_bwd_pos_role<C>(P, G, ctx, d_pos, (int)blockIdx.x);
+        return;
+    }
+    aa_bwd_tile_body<C, CC, CG, NCHW, TPW>(P, G, ctx, d_color, (int64_t)blockIdx.x - pos_blocks, s_tile);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Narrow keys (C <= 4: shaded RGBA, shading, flow, depth): one thread per PIXEL, no shared memory, ~24 registers ->
 // full occupancy.  The warp-tile kernels above pay a fixed per-tile latency chain that only amortises over wide rows.
@@ -746,13 +760,13 @@ __global__ void __launch_bounds__(256, TPW == 1 ? 5 : 4) aa_bwd_tile_kernel(AAPa
 constexpr int AA_PPT = 1;   // pixels per thread (measured: 4 pixels per thread with batched loads was 40 % SLOWER - fewer, fatter threads)
 
 template <int C>
-__global__ void __launch_bounds__(256) aa_fwd_pix_kernel(const float* __restrict__ color, const float* __restrict__ bg, int Bg, AAContext ctx,
-                                                         int B, int H, int W, float* __restrict__ out)
+__device__ __forceinline__ void aa_fwd_pix_body(const float* __restrict__ color, const float* __restrict__ bg, int Bg, const AAContext& ctx,
+                                                int B, int H, int W, float* __restrict__ out, int64_t vblock)
 {
     constexpr int CI = C - 1;
     const int HW = H * W;
     const int64_t n = (int64_t)B * HW;
-    const int64_t base = (int64_t)blockIdx.x * (blockDim.x * AA_PPT) + threadIdx.x;
+    const int64_t base = vblock * (blockDim.x * AA_PPT) + threadIdx.x;
     uint32_t cw[AA_PPT], aw[AA_PPT];
     float v[AA_PPT][C];
 #pragma unroll
@@ -809,17 +823,19 @@ __global__ void __launch_bounds__(256) aa_fwd_pix_kernel(const float* __restrict
     }
 }
 
-template <int C, int CC, int CG>
-__global__ void __launch_bounds__(256, 6) aa_bwd_pix_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
-                                                            float* __restrict__ d_pos, int pos_blocks)
+template <int C>
+__global__ void __launch_bounds__(256) aa_fwd_pix_kernel(const float* __restrict__ color, const float* __restrict__ bg, int Bg, AAContext ctx,
+                                                         int B, int H, int W, float* __restrict__ out)
 {
-    if ((int)blockIdx.x < pos_blocks) {
-        aa_bwd_pos_role<C>(P, G, ctx, d_pos, (int)blockIdx.x);
-        return;
-    }
+    aa_fwd_pix_body<C>(color, bg, Bg, ctx, B, H, W, out, (int64_t)blockIdx.x);
+}
+
+template <int C, int CC, int CG>
+__device__ __forceinline__ void aa_bwd_pix_body(const AAParams& P, const AAGrad& G, const AAContext& ctx, float* __restrict__ d_color, int64_t vblock)
+{
     const int HW = P.H * P.W;
     const int64_t n = (int64_t)P.B * HW;
-    const int64_t base = (int64_t)(blockIdx.x - pos_blocks) * (blockDim.x * AA_PPT) + threadIdx.x;
+    const int64_t base = vblock * (blockDim.x * AA_PPT) + threadIdx.x;
     uint32_t cw[AA_PPT], aw[AA_PPT];
     float v[AA_PPT][CC];
 #pragma unroll
@@ -870,6 +886,50 @@ __global__ void __launch_bounds__(256, 6) aa_bwd_pix_kernel(AAParams P, AAGrad G
             for (int c = 0; c < CC; c++) o[c] = v[j][c];
         }
     }
+}
+
+template <int C, int CC, int CG>
+__global__ void __launch_bounds__(256, 6) aa_bwd_pix_kernel(AAParams P, AAGrad G, AAContext ctx, float* __restrict__ d_color,
+                                                            float* __restrict__ d_pos, int pos_blocks)
+{
+    if ((int)blockIdx.x < pos_blocks) {
+        aa_bwd_pos_role<C>(P, G, ctx, d_pos, (int)blockIdx.x);
+        return;
+    }
+    aa_bwd_pix_body<C, CC, CG>(P, G, ctx, d_color, (int64_t)blockIdx.x - pos_blocks);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Two keys of one render in ONE launch (the training pair: a wide key, e.g. dino_pred [16+1], and a narrow key, e.g.
+// shaded [3+1]).  Both share the render's prepared context; the wide key's tiles go first (longest blocks), the narrow
+// key's pixels fill in behind them, and in the backward the position-gradient roles of both keys lead the grid and add
+// into one d_pos.  Saves a launch ramp + tail per direction and lets the narrow key's latency-bound blocks overlap
+// the wide key's bandwidth-bound ones.
+// ------------------------------------------------------------------------------------------------------------
+template <int CW, int CN>
+__global__ void __launch_bounds__(256, 5) aa_fwd_pair_kernel(const float* __restrict__ color_w, const float* __restrict__ bg_w, int Bg_w,
+                                                             float* __restrict__ out_w, const float* __restrict__ color_n,
+                                                             const float* __restrict__ bg_n, int Bg_n, float* __restrict__ out_n, AAContext ctx,
+                                                             int B, int H, int W, int wide_blocks)
+{
+    __shared__ __align__(16) float s_tile[8 * 32 * CW];
+    if ((int)blockIdx.x < wide_blocks) aa_fwd_tile_body<CW, 1>(color_w, bg_w, Bg_w, ctx, B, H, W, out_w, (int64_t)blockIdx.x, s_tile);
+    else aa_fwd_pix_body<CN>(color_n, bg_n, Bg_n, ctx, B, H, W, out_n, (int64_t)blockIdx.x - wide_blocks);
+}
+
+template <int CW, int CGW, bool NCHW, int CN, int CGN>
+__global__ void __launch_bounds__(256, 5) aa_bwd_pair_kernel(AAParams Pw, AAGrad Gw, float* __restrict__ d_color_w, AAParams Pn, AAGrad Gn,
+                                                             float* __restrict__ d_color_n, AAContext ctx, float* __restrict__ d_pos,
+                                                             int pos_blocks, int wide_blocks)
+{
+    __shared__ float s_tile[8 * 32 * (CGW + 1)];
+    int bx = (int)blockIdx.x;
+    if (bx < pos_blocks) { aa_bwd_pos_role<CW>(Pw, Gw, ctx, d_pos, bx); return; }
+    bx -= pos_blocks;
+    if (bx < pos_blocks) { aa_bwd_pos_role<CN>(Pn, Gn, ctx, d_pos, bx); return; }
+    bx -= pos_blocks;
+    if (bx < wide_blocks) aa_bwd_tile_body<CW, CW - 1, CGW, NCHW, 1>(Pw, Gw, ctx, d_color_w, (int64_t)bx, s_tile);
+    else aa_bwd_pix_body<CN, CN - 1, CGN>(Pn, Gn, ctx, d_color_n, (int64_t)bx - wide_blocks);
 }
 
 int aa_check(const float* color, const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, int Bg, int composite, int B,
@@ -1038,6 +1098,63 @@ B2A_API int b2a_antialias_bwd(const float* color, const float* bg, int Bg, int c
         else fast = false;
     }
     if (!fast) aa_bwd_kernel<<<dim3(b2a_blocks((int64_t)H * W * Cc, 256), B), 256, 0, stream>>>(P, G, d_color, d_pos);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+/* Two keys of one render in one launch per direction (the training pair: wide key dino_pred [16+1], narrow key shaded
+ * [3+1]; composite mode with a prepared context only).  Returns B2A_ERR_UNSUPPORTED-style non-zero when the combination
+ * has no fused instantiation: the caller then issues the two single-key calls (same kernels' bodies, same results). */
+B2A_API int b2a_antialias_pair_fwd(const float* color_w, const float* bg_w, int Bg_w, int Cw, float* out_w, const float* color_n,
+                                   const float* bg_n, int Bg_n, int Cn, float* out_n, int B, int H, int W, const void* aa_ctx,
+                                   size_t aa_ctx_bytes, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(color_w && color_n && out_w && out_n && aa_ctx, "null pointer");
+    B2A_CHECK_ARG(B > 0 && H > 0 && W > 0 && (Bg_w == 1 || Bg_w == B) && (Bg_n == 1 || Bg_n == B), "shape");
+    B2A_CHECK_ARG(Cw == 17 && Cn == 4, "fused pair: only (wide 17, narrow 4) channels are instantiated");
+    AAContext ctx;
+    B2A_CHECK_ARG(aa_fast_ok(1, aa_ctx, aa_ctx_bytes, B, H, W, Cw, &ctx), "prepared context required (H*W % 32 == 0)");
+    B2A_CHECK_ARG(aligned16(color_w) && aligned16(bg_w) && aligned16(out_w) && aligned16(out_n), "16-byte alignment");
+    const unsigned tiles = (unsigned)(((int64_t)B * H * W) / 32);
+    const unsigned wide_blocks = b2a_blocks(tiles, 8);
+    const unsigned narrow_blocks = b2a_blocks((int64_t)B * H * W, 256 * AA_PPT);
+    aa_fwd_pair_kernel<17, 4><<<wide_blocks + narrow_blocks, 256, 0, stream>>>(color_w, bg_w, Bg_w, out_w, color_n, bg_n, Bg_n, out_n, ctx, B, H, W,
+                                                                               (int)wide_blocks);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+B2A_API int b2a_antialias_pair_bwd(const float* color_w, const float* bg_w, int Bg_w, int Cw, const float* d_out_w, int64_t w_sb, int64_t w_sy,
+                                   int64_t w_sx, int64_t w_sc, int Cgw, float* d_color_w, const float* color_n, const float* bg_n, int Bg_n,
+                                   int Cn, const float* d_out_n, int64_t n_sb, int64_t n_sy, int64_t n_sx, int64_t n_sc, int Cgn,
+                                   float* d_color_n, int B, int64_t V, int H, int W, float* d_pos, const void* aa_ctx, size_t aa_ctx_bytes,
+                                   b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(color_w && color_n && d_out_w && d_out_n && d_color_w && d_color_n && aa_ctx, "null pointer");
+    B2A_CHECK_ARG(B > 0 && V > 0 && H > 0 && W > 0 && (Bg_w == 1 || Bg_w == B) && (Bg_n == 1 || Bg_n == B), "shape");
+    B2A_CHECK_ARG(Cw == 17 && Cgw == 16 && Cn == 4 && (Cgn == 4 || Cgn == 3), "fused pair: only (wide 17/16, narrow 4/{3,4}) channels are instantiated");
+    AAContext ctx;
+    B2A_CHECK_ARG(aa_fast_ok(1, aa_ctx, aa_ctx_bytes, B, H, W, Cw, &ctx), "prepared context required (H*W % 32 == 0)");
+    B2A_CHECK_ARG(aligned16(d_color_w) && aligned16(d_color_n), "16-byte alignment");
+    AAParams Pw{color_w, bg_w, nullptr, nullptr, nullptr, nullptr, Bg_w, 1, B, H, W, Cw, V, 0};
+    AAParams Pn{color_n, bg_n, nullptr, nullptr, nullptr, nullptr, Bg_n, 1, B, H, W, Cn, V, 0};
+    AAGrad Gw{d_out_w, w_sb, w_sy, w_sx, w_sc, Cgw};
+    AAGrad Gn{d_out_n, n_sb, n_sy, n_sx, n_sc, Cgn};
+    const bool nhwc = w_sc == 1 && w_sx == Cgw && w_sy == (int64_t)W * Cgw && w_sb % 4 == 0 && aligned16(d_out_w);
+    const bool nchw = w_sx == 1 && W % 32 == 0;
+    B2A_CHECK_ARG(nhwc || nchw, "fused pair: the wide gradient must be NCHW- or NHWC-contiguous");
+    const int pos_blocks = d_pos ? AA_POS_BLOCKS : 0;
+    const unsigned tiles = (unsigned)(((int64_t)B * H * W) / 32);
+    const unsigned wide_blocks = b2a_blocks(tiles, 8);
+    const unsigned narrow_blocks = b2a_blocks((int64_t)B * H * W, 256 * AA_PPT);
+    const unsigned grid = 2 * pos_blocks + wide_blocks + narrow_blocks;
+#define B2A_PAIR_BWD(NCHW_, CGN_) \
+    aa_bwd_pair_kernel<17, 16, NCHW_, 4, CGN_><<<grid, 256, 0, stream>>>(Pw, Gw, d_color_w, Pn, Gn, d_color_n, ctx, d_pos, pos_blocks, (int)wide_blocks)
+    if (nhwc) { if (Cgn == 4) B2A_PAIR_BWD(false, 4); else B2A_PAIR_BWD(false, 3); }
+    else      { if (Cgn == 4) B2A_PAIR_BWD(true, 4);  else B2A_PAIR_BWD(true, 3); }
+#undef B2A_PAIR_BWD
     B2A_LAUNCH_OK();
     return 0;
 }

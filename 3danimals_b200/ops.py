@@ -55,7 +55,8 @@ KERNELS_PER_CALL = {
     "b2a_mt_count": 4, "b2a_mt_emit": 2, "b2a_mt_bwd": 1, "b2a_estimate_bones": 4, "b2a_lbs_bone_transforms": 2, "b2a_lbs_fwd": 1, "b2a_lbs_bwd": 1,
     "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1,
     "b2a_xfm_points_bwd": 1, "b2a_rasterize_fwd": 3, "b2a_rasterize_bwd": 1, "b2a_interpolate_fwd": 1, "b2a_interpolate_bwd": 1,
-    "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 2, "b2a_gbuffer_fwd": 2, "b2a_gbuffer_bwd": 2,
+    "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 2,
+    "b2a_antialias_pair_fwd": 1, "b2a_antialias_pair_bwd": 1, "b2a_gbuffer_fwd": 2, "b2a_gbuffer_bwd": 2,
 }
 
 
@@ -560,6 +561,78 @@ def composite_antialias(color, background, rast, pos, tri, opp, antialias_edges=
         acc = torch.lerp(bgt.expand(color.shape[0], -1, -1, -1), torch.cat((color, torch.ones_like(color[..., :1])), -1), alpha)
         return acc[..., :keep]
     return _Antialias.apply(color, background, rast, pos, tri, opp, True, keep, aa_ctx)
+
+
+class _AntialiasPair(torch.autograd.Function):
+    """composite + antialias of the training pair of keys - a wide one (dino_pred, 16+1 channels) and a narrow one
+    (shaded, 3+1) - in ONE launch per direction over the render's prepared context (b2a_antialias_pair_fwd/bwd).  Same
+    device code as two _Antialias nodes (bit-identical images); what it removes is a launch ramp + tail per direction,
+    one autograd node, one zero fill and the d_pos sum of the two keys."""
+
+    @staticmethod
+    def forward(ctx, color_w, color_n, bg_w, bg_n, pos, keep_w, keep_n, aa_ctx, rast, tri, opp):
+        color_w = _f32(color_w, "color"); color_n = _f32(color_n, "color"); pos = _f32(pos, "pos")
+        bg_w = _f32(bg_w, "background") if bg_w is not None else None
+        bg_n = _f32(bg_n, "background") if bg_n is not None else None
+        B, H, W = color_w.shape[0], color_w.shape[1], color_w.shape[2]
+        Cw, Cn = color_w.shape[-1] + 1, color_n.shape[-1] + 1
+        if color_n.shape[:3] != color_w.shape[:3]:
+            raise _lib.B2AError("antialias pair: the two keys must share [B,H,W]")
+        for bg, Cc in ((bg_w, Cw), (bg_n, Cn)):
+            if bg is not None and (bg.shape[1:] != (H, W, Cc) or bg.shape[0] not in (1, B)):
+                raise _lib.B2AError("antialias: background shape %s, expected [1|B,%d,%d,%d]" % (tuple(bg.shape), H, W, Cc))
+        Bgw = 1 if bg_w is None else bg_w.shape[0]
+        Bgn = 1 if bg_n is None else bg_n.shape[0]
+        out_w = torch.empty(B, H, W, Cw, device=color_w.device)
+        out_n = torch.empty(B, H, W, Cn, device=color_w.device)
+        _call("b2a_antialias_pair_fwd", (_p(color_w), _p(bg_w), Bgw, Cw, _p(out_w), _p(color_n), _p(bg_n), Bgn, Cn, _p(out_n), B, H, W,
+                                          _p(aa_ctx), aa_ctx.numel(), _stream()), tag="C%d+C%d" % (Cw, Cn))
+        ctx.save_for_backward(color_w, color_n, bg_w, bg_n, pos, aa_ctx, rast, tri, opp)
+        ctx.cfg = (Bgw, Bgn, Cw, Cn, int(keep_w), int(keep_n))
+        return (out_w[..., :keep_w] if keep_w < Cw else out_w), (out_n[..., :keep_n] if keep_n < Cn else out_n)
+
+    @staticmethod
+    def backward(ctx, g_w, g_n):
+        color_w, color_n, bg_w, bg_n, pos, aa_ctx, rast, tri, opp = ctx.saved_tensors
+        Bgw, Bgn, Cw, Cn, keep_w, keep_n = ctx.cfg
+        B, H, W = color_w.shape[0], color_w.shape[1], color_w.shape[2]
+        g_w = g_w if g_w.dtype == torch.float32 else g_w.float()
+        g_n = g_n if g_n.dtype == torch.float32 else g_n.float()
+        d_color_w = torch.empty_like(color_w)
+        d_color_n = torch.empty_like(color_n)
+        d_pos = torch.zeros_like(pos) if ctx.needs_input_grad[4] else None
+        wsb, wsy, wsx, wsc = g_w.stride()
+        nsb, nsy, nsx, nsc = g_n.stride()
+        V = pos.shape[1]
+        st = _stream()
+        nhwc = wsc == 1 and wsx == keep_w and wsy == W * keep_w and wsb % 4 == 0 and g_w.data_ptr() % 16 == 0
+        nchw = wsx == 1 and W % 32 == 0
+        if (nhwc or nchw) and keep_w == Cw - 1 and keep_n in (Cn, Cn - 1):
+            _call("b2a_antialias_pair_bwd", (_p(color_w), _p(bg_w), Bgw, Cw, _p(g_w), wsb, wsy, wsx, wsc, keep_w, _p(d_color_w), _p(color_n),
+                                              _p(bg_n), Bgn, Cn, _p(g_n), nsb, nsy, nsx, nsc, keep_n, _p(d_color_n), B, V, H, W, _p(d_pos),
+                                              _p(aa_ctx), aa_ctx.numel(), st), tag="C%d+C%d" % (Cw, Cn))
+        else:   # gradient layout without a fused instantiation: the two single-key launches, same d_pos accumulator
+            for color, bg, Bg, Cc, g, (sb, sy, sx, sc), keep, d_color in (
+                    (color_w, bg_w, Bgw, Cw, g_w, (wsb, wsy, wsx, wsc), keep_w, d_color_w),
+                    (color_n, bg_n, Bgn, Cn, g_n, (nsb, nsy, nsx, nsc), keep_n, d_color_n)):
+                _call("b2a_antialias_bwd", (_p(color), _p(bg), Bg, 1, _p(rast), _p(pos), _p(tri), _p(opp), _p(g), sb, sy, sx, sc, keep, B, V,
+                                              tri.shape[0], H, W, Cc, _p(d_color), _p(d_pos), _p(aa_ctx), aa_ctx.numel(), st), tag="C%d" % Cc,
+                      launches=1)
+        return d_color_w, d_color_n, None, None, d_pos, None, None, None, None, None, None
+
+
+def composite_antialias_pair(color_w, bg_w, keep_w, color_n, bg_n, keep_n, rast, pos, tri, opp, aa_ctx):
+    """Fused composite + antialias of a wide key (color_w [B,H,W,16]) and a narrow key (color_n [B,H,W,3]) of one render.
+    -> ([B,H,W,keep_w], [B,H,W,keep_n]).  Requires the render's prepared context (ops.antialias_prepare)."""
+    if not pair_supported(color_w, color_n, aa_ctx):
+        raise _lib.B2AError("composite_antialias_pair: unsupported key combination (use composite_antialias per key)")
+    return _AntialiasPair.apply(color_w, color_n, bg_w, bg_n, pos, int(keep_w), int(keep_n), aa_ctx, _f32(rast, "rast"), _idx32(tri, "tri"),
+                                _idx32(opp, "opp"))
+
+
+def pair_supported(color_w, color_n, aa_ctx):
+    return (aa_ctx is not None and color_w.shape[-1] == 16 and color_n.shape[-1] == 3 and color_w.shape[:3] == color_n.shape[:3]
+            and color_w.shape[0] * color_w.shape[1] * color_w.shape[2] * 17 < (1 << 31))
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -8,9 +8,14 @@ Same signature, same list-of-NCHW return (reference render.py:228-337).  What ch
     and the light (which stay PyTorch modules);
   * lerp-composite + dr.antialias per key (render.py:258-268) is one gather kernel per key, no composited image in HBM.
 """
+import os
+
 import torch
 
 from .. import ops
+
+# A/B switch for measurements: B2A_FUSE_AA_PAIR=0 renders the training pair of keys with two single-key launches
+FUSE_AA_PAIR = os.environ.get("B2A_FUSE_AA_PAIR", "1") != "0"
 
 
 def interpolate(attr, rast, attr_idx, rast_db=None):
@@ -148,10 +153,22 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
     else:
         bg_full = None
 
+    # the training pair ['shaded', 'dino_pred'] goes through ONE composite+antialias launch per direction
+    fused = {}
+    if (FUSE_AA_PAIR and spp == 1 and aa_ctx is not None and "shaded" in render_modes and "dino_pred" in render_modes and "dino_pred" in buffers
+            and buffers["shaded"].dtype == torch.float32 and buffers["dino_pred"].dtype == torch.float32
+            and ops.pair_supported(buffers["dino_pred"], buffers["shaded"], aa_ctx)):
+        dino_c = buffers["dino_pred"]
+        fused["dino_pred"], fused["shaded"] = ops.composite_antialias_pair(dino_c, None, dino_c.shape[-1], buffers["shaded"], bg_full, 4,
+                                                                           rast, v_pos_clip, tri, opp, aa_ctx)
+
     out_buffers = []
     for key in render_modes:
         if key not in buffers:
             out_buffers.append(None)
+            continue
+        if key in fused:
+            out_buffers.append(fused[key].permute(0, 3, 1, 2))
             continue
         color = _nearest_up(buffers[key].float(), shade_spp)
         bg = bg_full if key in _BG_KEYS else None

@@ -166,6 +166,20 @@ int b2a_antialias_bwd(const float* color, const float* bg, int Bg, int composite
                       const int32_t* tri, const int32_t* opp, const float* d_out, int64_t d_sb, int64_t d_sy,
                       int64_t d_sx, int64_t d_sc, int Cg, int B, int64_t V, int64_t F, int H, int W, int C,
                       float* d_color, float* d_pos, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
+/* Fused fast path of render_mesh's composite_buffer loop (model/render/render.py:311-331) for the training pair of keys:
+ * 'dino_pred' (wide, Cw = D+1 = 17 channels) and 'shaded' (narrow, Cn = 4) composited + antialiased in ONE launch per
+ * direction, sharing the render's prepared context.  Arguments as in b2a_antialias_fwd/bwd with composite = 1, one set
+ * per key (suffix _w / _n); d_pos [B,V,4] receives the SUM of both keys' position gradients (zero-init, nullable).
+ * Only (Cw, Cn) = (17, 4) with Cgw = 16, Cgn in {3, 4} is instantiated: other combinations return an error and the
+ * caller issues the two single-key calls. */
+int b2a_antialias_pair_fwd(const float* color_w, const float* bg_w, int Bg_w, int Cw, float* out_w, const float* color_n,
+                           const float* bg_n, int Bg_n, int Cn, float* out_n, int B, int H, int W, const void* aa_ctx,
+                           size_t aa_ctx_bytes, b2a_stream_t stream);
+int b2a_antialias_pair_bwd(const float* color_w, const float* bg_w, int Bg_w, int Cw, const float* d_out_w, int64_t w_sb,
+                           int64_t w_sy, int64_t w_sx, int64_t w_sc, int Cgw, float* d_color_w, const float* color_n,
+                           const float* bg_n, int Bg_n, int Cn, const float* d_out_n, int64_t n_sb, int64_t n_sy,
+                           int64_t n_sx, int64_t n_sc, int Cgn, float* d_color_n, int B, int64_t V, int H, int W,
+                           float* d_pos, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused g-buffer pass (fast path of render_layer + shade's geometry part, model/render/render.py:160-209, :72-75):

@@ -407,6 +407,55 @@ def test_composite_antialias_oracle(cuda, C, keep, with_bg, image, layout, prepa
     assert rel_err(pd.grad.cpu().numpy(), pt.grad.numpy()) < TOL
 
 
+@pytest.mark.parametrize("image,layout,keep_n", [(128, "nchw", 4), (128, "nhwc", 4), (96, "nchw", 3), (128, "strided", 4)])
+def test_composite_antialias_pair_oracle(cuda, image, layout, keep_n):
+    """The fused two-key launch (dino_pred 16+1 | shaded 3+1, b2a_antialias_pair_fwd/bwd) vs the oracle's two separate
+    composite+antialias passes: images bit-exact, colour gradients and the SUMMED position gradient <= 1e-4.
+    'strided': a wide gradient that is neither NCHW- nor NHWC-contiguous takes the two single-key launches."""
+    ops = _ops()
+    verts, faces, prior, mvp, w2c, campos, clip = _scene()
+    S = image
+    rast = R.rasterize(clip, faces, (S, S))
+    rng = np.random.RandomState(11)
+    col_w = rng.rand(3, S, S, 16).astype(np.float32)
+    col_n = rng.rand(3, S, S, 3).astype(np.float32)
+    bg_n = rng.rand(3, S, S, 4).astype(np.float32)
+    opp = R.edge_adjacency(faces, verts.shape[1])
+    pt = torch.from_numpy(clip).requires_grad_(True)
+    alpha = torch.from_numpy((rast[..., 3:] > 0).astype(np.float32))
+    refs, cts, gs = [], [], []
+    for col, bg, C, keep in ((col_w, None, 17, 16), (col_n, bg_n, 4, keep_n)):
+        ct = torch.from_numpy(col).requires_grad_(True)
+        bgt = torch.from_numpy(bg) if bg is not None else torch.zeros(1, S, S, C)
+        acc = torch.lerp(bgt.expand(3, -1, -1, -1), torch.cat((ct, torch.ones_like(ct[..., :1])), -1), alpha)
+        ref = T.antialias(acc.contiguous(), torch.from_numpy(rast), pt, torch.from_numpy(faces), torch.from_numpy(opp))[..., :keep].permute(0, 3, 1, 2)
+        g = rng.randn(*ref.shape).astype(np.float32)
+        refs.append(ref); cts.append(ct); gs.append(g)
+    torch.autograd.backward(refs, [torch.from_numpy(g) for g in gs])
+    cw, cn = dev(col_w, cuda).requires_grad_(True), dev(col_n, cuda).requires_grad_(True)
+    pd = dev(clip, cuda).requires_grad_(True)
+    rd, fd, od = dev(rast, cuda), dev(faces, cuda), dev(opp, cuda)
+    aa_ctx = ops.antialias_prepare(rd, pd.detach(), fd, od)
+    assert aa_ctx is not None and ops.pair_supported(cw, cn, aa_ctx)
+    ow, on = ops.composite_antialias_pair(cw, None, 16, cn, dev(bg_n, cuda), keep_n, rd, pd, fd, od, aa_ctx)
+    ow, on = ow.permute(0, 3, 1, 2), on.permute(0, 3, 1, 2)
+    assert np.array_equal(ow.detach().cpu().numpy(), refs[0].detach().numpy())
+    assert np.array_equal(on.detach().cpu().numpy(), refs[1].detach().numpy())
+    gw, gn = dev(gs[0], cuda), dev(gs[1], cuda)
+    if layout == "nhwc":
+        gw = gw.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        gn = gn.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    elif layout == "strided":
+        gw = torch.stack([gw, gw], -1)[..., 0]       # x stride 2: no fused instantiation
+    torch.autograd.backward([ow, on], [gw, gn])
+    assert rel_err(cw.grad.cpu().numpy(), cts[0].grad.numpy()) < TOL
+    assert rel_err(cn.grad.cpu().numpy(), cts[1].grad.numpy()) < TOL
+    assert np.abs(pt.grad.numpy()).max() > 0
+    assert rel_err(pd.grad.cpu().numpy(), pt.grad.numpy()) < TOL
+    calls = ops.stats.calls
+    assert calls.get("b2a_antialias_pair_fwd", 0) >= 1
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # fused g-buffer
 # ----------------------------------------------------------------------------------------------------------------
