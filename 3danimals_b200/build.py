@@ -10,7 +10,7 @@ Two arithmetic regimes, chosen per file:
          (interpolate.cu), antialiased images (antialias.cu), quantile selection (estimate_bones.cu).  Every fp32 op is
          individually rounded; oracle/raster_ref.c is built with -ffp-contract=off to match.
   FAST   (-use_fast_math: FMA contraction, approximate div / sqrt / exp): files whose contract is the 1e-4 relative
-         tolerance - fused g-buffer (gbuffer.cu), skinning (lbs.cu), vertex normals (normals.cu).  The IEEE division
+         tolerance - fused g-buffer (gbuffer.cu), skinning (lbs.cu), vertex normals (normals.cu), light shading (shade.cu).  The IEEE division
          subroutine alone was 25 % of the g-buffer backward's instructions (profiles/).
 """
 import concurrent.futures
@@ -28,7 +28,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 COMMON_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 EXACT_FLAGS = ["-fmad=false"]
 FAST_FLAGS = ["-use_fast_math"]
-FAST_FILES = {"gbuffer.cu", "lbs.cu", "normals.cu"}
+FAST_FILES = {"gbuffer.cu", "lbs.cu", "normals.cu", "shade.cu"}
 
 
 def sources():

@@ -56,7 +56,8 @@ KERNELS_PER_CALL = {
     "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1,
     "b2a_xfm_points_bwd": 1, "b2a_rasterize_fwd": 3, "b2a_rasterize_bwd": 1, "b2a_interpolate_fwd": 1, "b2a_interpolate_bwd": 1,
     "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 2,
-    "b2a_antialias_pair_fwd": 1, "b2a_antialias_pair_bwd": 1, "b2a_gbuffer_fwd": 2, "b2a_gbuffer_bwd": 2,
+    "b2a_antialias_pair_fwd": 1, "b2a_antialias_pair_bwd": 1, "b2a_shade_directional_fwd": 1, "b2a_shade_directional_bwd": 1,
+    "b2a_analytic_field_fwd": 1, "b2a_analytic_field_bwd": 1, "b2a_gbuffer_fwd": 2, "b2a_gbuffer_bwd": 2,
 }
 
 
@@ -88,8 +89,13 @@ class CallStats:
 stats = CallStats()
 
 
+_fn_cache = {}
+
+
 def _call(name, args, tag=None, launches=None):
-    fn = getattr(_L(), name)
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(_L(), name)
     tag = stats.tag if tag is None else tag
     if stats.timing:
         e0 = torch.cuda.Event(enable_timing=True)
@@ -109,11 +115,20 @@ def _call(name, args, tag=None, launches=None):
     _lib.check(rc)
 
 
+_size_cache = {}
+
+
 def _size(fn, *args):
-    import ctypes
-    out = ctypes.c_size_t(0)
-    _lib.check(fn(*args, ctypes.byref(out)))
-    return out.value
+    """Workspace-size query (a pure function of its integer arguments): memoised, the hot path asks the same five
+    questions every step."""
+    key = (fn.__name__,) + args
+    v = _size_cache.get(key)
+    if v is None:
+        import ctypes
+        out = ctypes.c_size_t(0)
+        _lib.check(fn(*args, ctypes.byref(out)))
+        v = _size_cache[key] = out.value
+    return v
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -708,6 +723,97 @@ def gbuffer(rast, pos_clip, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp=1, tw
     outs = _GBuffer.apply(rast.detach(), pos_clip, _idx32(tri, "tri"), v_pos, v_nrm, prior_pos, w2c, campos, int(spp), bool(two_sided),
                           tuple(want), cl, cc)
     return {k: o for k, o in zip(GB_KEYS, outs) if k in want}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Directional-light shading (reference model/render/light.py:186-193)
+# ---------------------------------------------------------------------------------------------------------------
+def _rows3(t):
+    """-> (tensor to keep alive, row stride in floats) for a [..., 3] fp32 CUDA tensor whose last dim is dense and whose
+    leading dims are uniformly strided (a channel slice of an NHWC tensor qualifies); anything else is made contiguous."""
+    if t.dtype == torch.float32 and t.stride(-1) == 1 and t.dim() >= 2:
+        rs = t.stride(-2)
+        ok = rs >= 3
+        n = t.shape[-2]
+        for d in range(t.dim() - 3, -1, -1):
+            ok = ok and (t.shape[d] == 1 or t.stride(d) == rs * n)
+            n *= t.shape[d]
+        if ok:
+            return t, rs
+    return t.float().contiguous(), 3
+
+
+class _ShadeDirectional(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kd, normal, light):
+        if not (kd.is_cuda and normal.is_cuda and light.is_cuda):
+            raise _lib.B2AError("shade_directional needs CUDA tensors (the B200 hot path has no CPU fallback)")
+        normal = _f32(normal, "normal"); light = _f32(light, "light_params")
+        kd_t, ks = _rows3(kd)
+        B = normal.shape[0]
+        HW = normal.numel() // (3 * B)
+        Bl = light.shape[0]
+        if kd.shape != normal.shape or light.shape[-1] != 5 or Bl not in (1, B):
+            raise _lib.B2AError("shade_directional: kd %s, normal %s, light %s" % (tuple(kd.shape), tuple(normal.shape), tuple(light.shape)))
+        shaded = torch.empty_like(normal)
+        shading = torch.empty(*normal.shape[:-1], 1, device=normal.device)
+        _call("b2a_shade_directional_fwd", (_p(kd_t), ks, _p(normal), _p(light), Bl, B, HW, _p(shaded), _p(shading), _stream()))
+        ctx.save_for_backward(kd_t, normal, light)
+        ctx.ks = ks
+        ctx.kd_shape = kd.shape
+        return shaded, shading
+
+    @staticmethod
+    def backward(ctx, g_shaded, g_shading):
+        kd_t, normal, light = ctx.saved_tensors
+        B = normal.shape[0]
+        HW = normal.numel() // (3 * B)
+        need = ctx.needs_input_grad
+        if g_shaded is None:
+            g_shaded = torch.zeros_like(normal)
+        g_shaded = _f32(g_shaded, "d_shaded")
+        g_shading = _f32(g_shading, "d_shading") if g_shading is not None else None
+        d_kd = torch.empty(ctx.kd_shape, device=normal.device) if need[0] else None
+        d_n = torch.empty_like(normal) if need[1] else None
+        d_l = torch.zeros_like(light) if need[2] else None
+        _call("b2a_shade_directional_bwd", (_p(kd_t), ctx.ks, _p(normal), _p(light), light.shape[0], _p(g_shaded), _p(g_shading), B, HW, _p(d_kd),
+                                             _p(d_n), _p(d_l), _stream()))
+        return d_kd, d_n, d_l
+
+
+def shade_directional(kd, normal, light_params):
+    """kd, normal [B,H,W,3] (kd may be a channel slice of the texture field's output), light_params [B|1,5] =
+    (dir.xyz, ambient, diffuse) -> (shaded [B,H,W,3], shading [B,H,W,1]); one kernel per direction."""
+    return _ShadeDirectional.apply(kd, normal, light_params)
+
+
+class _AnalyticField(torch.autograd.Function):
+    """Benchmark stand-in for the field MLPs (M1a; not a reference interface): act(x W), one kernel per
+    direction (csrc/analytic_field.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, squash):
+        x = _f32(x, "x"); weight = _f32(weight, "weight")
+        C = weight.shape[1]
+        N = x.numel() // 3
+        out = torch.empty(*x.shape[:-1], 3 * C if squash else C, device=x.device)
+        _call("b2a_analytic_field_fwd", (_p(x), _p(weight), C, int(squash), N, _p(out), _stream()))
+        ctx.save_for_backward(x, weight)
+        ctx.squash = bool(squash)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = _f32(g, "d_out")
+        d_x = torch.empty_like(x)
+        _call("b2a_analytic_field_bwd", (_p(x), _p(weight), weight.shape[1], int(ctx.squash), x.numel() // 3, _p(g), _p(d_x), _stream()))
+        return d_x, None, None
+
+
+def analytic_field(x, weight, squash):
+    """x [...,3], weight [3,C] -> sin(x W) [...,C] (squash False) or cat([sigmoid(x W)] * 3) [...,3C] (squash True)."""
+    return _AnalyticField.apply(x, weight, bool(squash))
 
 
 # ---------------------------------------------------------------------------------------------------------------

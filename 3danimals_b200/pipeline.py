@@ -50,7 +50,11 @@ class SyntheticScene:
 
 
 class AnalyticField(torch.nn.Module):
-    """Fixed smooth colour / feature field standing in for the texture and DINO CoordMLPs (M1a)."""
+    """Fixed smooth colour / feature field standing in for the texture and DINO CoordMLPs (M1a):
+    texture = cat([sigmoid(x W)] * 3) (9 channels), dino = sin(x W16) - the same function as
+    oracle.pipeline_ref.analytic_shader - as one kernel per direction (csrc/analytic_field.cu): M1a measures the hot-path
+    kernels, so the stand-in must cost as little as possible (a K=3 torch.matmul is a ~90 us SIMT sgemm plus ~25 us of
+    cuBLAS host time, and its autograd graph adds a dozen kernels per step)."""
 
     def __init__(self, weight, squash):
         super().__init__()
@@ -60,24 +64,21 @@ class AnalyticField(torch.nn.Module):
         self.dense_only = True   # three flops per pixel: gathering the covered rows would cost more than evaluating everywhere
 
     def sample(self, x, feat=None):
-        y = torch.matmul(x, self.weight)
-        if self.squash:  # texture: 9 channels (kd, ks, normal) in [0,1]
-            y = torch.sigmoid(y)
-            return torch.cat([y, y, y], -1)
-        return torch.sin(y)
+        from . import ops
+        return ops.analytic_field(x, self.weight, self.squash)
 
 
 class FixedLight(torch.nn.Module):
-    """DirectionalLight.shade arithmetic (reference model/render/light.py:186-193) with fixed light parameters."""
+    """DirectionalLight.shade (reference model/render/light.py:186-193) with fixed light parameters: the same fused
+    kernel the drop-in DirectionalLight uses (render/light.py -> ops.shade_directional)."""
 
     def __init__(self, params):
         super().__init__()
-        self.register_buffer("params", params)
+        self.register_buffer("params", params.reshape(1, 5).contiguous())
 
     def shade(self, feat, kd, normal):
-        ldir, amb, diff = self.params[:3], self.params[3], self.params[4]
-        shading = amb + diff * torch.clamp(torch.sum(ldir * normal, -1, keepdim=True), min=0.0)
-        return shading * kd, shading
+        from . import ops
+        return ops.shade_directional(kd, normal, self.params)
 
 
 class HotPath(torch.nn.Module):

@@ -182,6 +182,31 @@ int b2a_antialias_pair_bwd(const float* color_w, const float* bg_w, int Bg_w, in
                            float* d_pos, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Directional-light diffuse shading (DirectionalLight.shade, model/render/light.py:186-193):
+ *   shading = ambient + diffuse * clamp(dot(light_dir, normal), min=0);  shaded = shading * kd.
+ * kd rows are kd_stride floats apart (3 = dense [B,HW,3]; 9 = the leading channels of the texture field's [B,HW,9]
+ * output, read in place); normal [B,HW,3]; light [Bl,5] = (dir.xyz, ambient, diffuse), Bl in {1,B}.
+ * Outputs shaded [B,HW,3], shading [B,HW] (nullable).  Backward: d_shaded [B,HW,3], d_shading [B,HW] (nullable) ->
+ * d_kd [B,HW,3] dense, d_normal [B,HW,3], d_light [Bl,5] accumulated (zero-init); each nullable.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_shade_directional_fwd(const float* kd, int64_t kd_stride, const float* normal, const float* light, int Bl, int B,
+                              int64_t HW, float* shaded, float* shading, b2a_stream_t stream);
+int b2a_shade_directional_bwd(const float* kd, int64_t kd_stride, const float* normal, const float* light, int Bl,
+                              const float* d_shaded, const float* d_shading, int B, int64_t HW, float* d_kd,
+                              float* d_normal, float* d_light, b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Benchmark stand-in for the field MLPs - NOT a reference interface.  SURVEY.md §8d defines M1a with the texture and
+ * DINO CoordMLPs replaced by a fixed analytic function of the canonical position x [N,3]:  squash = 1: out [N,3C] =
+ * three copies of sigmoid(x W) (kd|ks|normal);  squash = 0: out [N,C] = sin(x W);  W [3,C], C <= 16.  One kernel per
+ * direction so the stand-in costs as little as possible on the number that measures the hot-path kernels.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_analytic_field_fwd(const float* x, const float* weight, int C, int squash, int64_t N, float* out,
+                           b2a_stream_t stream);
+int b2a_analytic_field_bwd(const float* x, const float* weight, int C, int squash, int64_t N, const float* d_out,
+                           float* d_x, b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Fused g-buffer pass (fast path of render_layer + shade's geometry part, model/render/render.py:160-209, :72-75):
  * interpolate v_pos, v_nrm, prior v_pos and the per-face normal at each covered pixel; prepare_shading_normal
  * (renderutils/ops.py:194-227 -> bsdf.py:46-51 with perturbed normal (0,0,1)); camera-space normal

@@ -44,7 +44,7 @@ def _load(name, relpath):
 
 
 def load():
-    """Returns a namespace with the reference modules: dmtet, skinning, geo_util, mesh, bsdf, rutil, mlps."""
+    """Returns a namespace with the reference modules: dmtet, skinning, geo_util, mesh, bsdf, rutil, mlps, light."""
     global _cache
     if _cache is not None:
         return _cache
@@ -78,6 +78,10 @@ def load():
         sys.modules["model.geometry"].util = ns.geo_util
         ns.skinning = _load("model.geometry.skinning", "model/geometry/skinning.py")
         ns.bsdf = _load("model.render.renderutils.bsdf", "model/render/renderutils/bsdf.py")
+        try:    # light.py only needs its imports to resolve (nvdiffrast / renderutils are stubs); DirectionalLight is pure torch
+            ns.light = _load("model.render.light", "model/render/light.py")
+        except Exception:
+            ns.light = None
     finally:
         # leave the reference modules importable under their own names only inside `ns`;
         # restore sys.modules so the product overlay (3danimals_b200.overlay) is not shadowed.

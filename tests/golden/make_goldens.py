@@ -3,7 +3,7 @@
     python tests/golden/make_goldens.py
 
 The reference ships no golden vectors or tests for the hot path, so these pin it: the reference's
-`DMTet.__call__`, `estimate_bones`, `skinning` (+ autograd grads) and `bsdf_prepare_shading_normal`, loaded by file
+`DMTet.__call__`, `estimate_bones`, `skinning` (+ autograd grads), `bsdf_prepare_shading_normal` and `DirectionalLight`, loaded by file
 path on CPU tensors (oracle/reference_loader.py), on small seeded inputs.  The fixtures travel to the GPU box; the
 reference tree does not.
 """
@@ -88,9 +88,36 @@ def shading_case():
                         d_nrm=nrm.grad.numpy(), d_geo=geo.grad.numpy())
 
 
+def light_case():
+    """The reference's DirectionalLight (light.py:168-193): light MLP -> light_params, shade(feat, kd, normal) + grads."""
+    ref = reference_loader.load()
+    torch.manual_seed(5)
+    lgt = ref.light.DirectionalLight(16, 3, 32, intensity_min_max=torch.FloatTensor([[0.0, 1.0], [0.5, 1.0]]))
+    rng = np.random.RandomState(22)
+    B, H, W = 3, 6, 10
+    feat = torch.from_numpy(rng.randn(B, 16).astype(np.float32)).requires_grad_(True)
+    tex = torch.from_numpy(rng.rand(B, H, W, 9).astype(np.float32)).requires_grad_(True)     # kd = leading 3 of 9 channels
+    nrm = rng.randn(B, H, W, 3).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    nrm[:, 0] = 0                                                                            # uncovered pixels: zero normal (dot == 0)
+    nrm = torch.from_numpy(nrm).requires_grad_(True)
+    shaded, shading = lgt.shade(feat, tex[..., :3], nrm)
+    g1 = torch.from_numpy(rng.randn(*shaded.shape).astype(np.float32))
+    g2 = torch.from_numpy(rng.randn(*shading.shape).astype(np.float32))
+    ((shaded * g1).sum() + (shading * g2).sum()).backward()
+    lp = lgt.light_params.detach()
+    sd = {k: v.detach().numpy() for k, v in lgt.state_dict().items()}
+    np.savez_compressed(os.path.join(OUT, "light_directional.npz"), feat=feat.detach().numpy(), tex=tex.detach().numpy(), nrm=nrm.detach().numpy(),
+                        light_params=lp.numpy(), shaded=shaded.detach().numpy(), shading=shading.detach().numpy(), g_shaded=g1.numpy(),
+                        g_shading=g2.numpy(), d_feat=feat.grad.numpy(), d_tex=tex.grad.numpy(), d_nrm=nrm.grad.numpy(),
+                        **{"sd:" + k: v for k, v in sd.items()})
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    mt_cases()
-    skin_cases()
-    shading_case()
+    if "--only-light" not in sys.argv:
+        mt_cases()
+        skin_cases()
+        shading_case()
+    light_case()
     print(sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))

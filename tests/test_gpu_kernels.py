@@ -514,3 +514,63 @@ def test_gbuffer_oracle(cuda, spp, Bq, two_sided, use_cov):
     sum((out[k] * dev(gs[k], cuda)).sum() for k in refs).backward()
     for name, a, b in (("v_pos", vd, vt), ("v_nrm", nd, nt), ("prior", qd, qt), ("clip", cd, ct), ("w2c", wd, wt), ("campos", pd, pt)):
         assert rel_err(a.grad.cpu().numpy(), b.grad.numpy()) < 2e-4, name
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# directional-light shading
+# ----------------------------------------------------------------------------------------------------------------
+def test_directional_light_golden(cuda):
+    """Drop-in DirectionalLight (light MLP in torch, shading in csrc/shade.cu) vs the reference's own class: outputs and the
+    gradients to the light MLP input, the 9-channel texture (kd is read in place as its leading 3 channels) and the normal."""
+    light_mod = pkg("render.light")
+    g = golden("light_directional.npz")
+    lgt = light_mod.DirectionalLight(16, 3, 32, intensity_min_max=torch.zeros(2, 2)).to(cuda)
+    lgt.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd:")}, strict=True)
+    feat, tex, nrm = (dev(g[k], cuda).requires_grad_(True) for k in ("feat", "tex", "nrm"))
+    shaded, shading = lgt.shade(feat, tex[..., :3], nrm)
+    assert tuple(shading.shape) == tuple(g["shading"].shape)
+    assert rel_err(shaded.detach().cpu().numpy(), g["shaded"]) < TOL and rel_err(shading.detach().cpu().numpy(), g["shading"]) < TOL
+    ((shaded * dev(g["g_shaded"], cuda)).sum() + (shading * dev(g["g_shading"], cuda)).sum()).backward()
+    for a, k in ((feat, "d_feat"), (tex, "d_tex"), (nrm, "d_nrm")):
+        assert rel_err(a.grad.cpu().numpy(), g[k]) < TOL, k
+
+
+@pytest.mark.parametrize("B,H,W,Bl,dense_kd", [(2, 5, 5, 2, True), (3, 16, 24, 1, True), (2, 8, 8, 2, False), (1, 7, 9, 1, False)])
+def test_shade_directional_oracle(cuda, B, H, W, Bl, dense_kd):
+    """Vector (H*W % 4 == 0) and scalar paths, shared and per-image light, dense kd and kd as a slice of 9 channels."""
+    ops = _ops()
+    rng = np.random.RandomState(31)
+    tex = rng.rand(B, H, W, 9).astype(np.float32)
+    nrm = rng.randn(B, H, W, 3).astype(np.float32)
+    nrm[:, :1] = 0
+    lp = np.concatenate([rng.randn(Bl, 3), rng.rand(Bl, 2) + 0.2], -1).astype(np.float32)
+    g1, g2 = rng.randn(B, H, W, 3).astype(np.float32), rng.randn(B, H, W, 1).astype(np.float32)
+    tt, nt, lt = (torch.from_numpy(x).requires_grad_(True) for x in (tex, nrm, lp))
+    rs, rh = T.directional_shade(lt.expand(B, 5), tt[..., :3], nt)
+    ((rs * torch.from_numpy(g1)).sum() + (rh * torch.from_numpy(g2)).sum()).backward()
+    td, nd, ld = (dev(x, cuda).requires_grad_(True) for x in (tex, nrm, lp))
+    kd = td[..., :3].contiguous() if dense_kd else td[..., :3]
+    s, h = ops.shade_directional(kd, nd, ld)
+    assert rel_err(s.detach().cpu().numpy(), rs.detach().numpy()) < TOL and rel_err(h.detach().cpu().numpy(), rh.detach().numpy()) < TOL
+    ((s * dev(g1, cuda)).sum() + (h * dev(g2, cuda)).sum()).backward()
+    for a, b, k in ((td, tt, "tex"), (nd, nt, "nrm"), (ld, lt, "light")):
+        assert rel_err(a.grad.cpu().numpy(), b.grad.numpy()) < TOL, k
+
+
+@pytest.mark.parametrize("squash,C", [(True, 3), (False, 16), (False, 5)])
+def test_analytic_field_stand_in(cuda, squash, C):
+    """The bench's stand-in pixel shader (csrc/analytic_field.cu) computes exactly the oracle twin's function."""
+    ops = _ops()
+    rng = np.random.RandomState(41)
+    x = (rng.randn(2, 9, 7, 3) * 2).astype(np.float32)
+    w = (rng.randn(3, C) * 1.5).astype(np.float32)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    z = torch.matmul(xt, torch.from_numpy(w))
+    ref = torch.cat([torch.sigmoid(z)] * 3, -1) if squash else torch.sin(z)
+    g = rng.randn(*ref.shape).astype(np.float32)
+    (ref * torch.from_numpy(g)).sum().backward()
+    xd = dev(x, cuda).requires_grad_(True)
+    out = ops.analytic_field(xd, dev(w, cuda), squash)
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < 1e-5
+    (out * dev(g, cuda)).sum().backward()
+    assert rel_err(xd.grad.cpu().numpy(), xt.grad.numpy()) < 1e-5

@@ -135,3 +135,18 @@ def test_mesh_bookkeeping_cpu():
     assert mesh.Mesh(base=m).t_pos_idx is f
     assert torch.equal(mesh.compute_edges(f), torch.tensor([[0, 1], [0, 2], [1, 2], [2, 3], [2, 4], [3, 4]]))
     assert m.tri_i32().dtype == torch.int32
+
+
+def test_directional_light_module_matches_reference_golden():
+    """The drop-in DirectionalLight keeps the reference's parameter names (checkpoints load strictly) and its light MLP
+    -> light_params arithmetic (light.py:177-184); the per-pixel shading has no CPU path."""
+    import torch
+    light_mod = pkg("render.light")
+    g = golden("light_directional.npz")
+    lgt = light_mod.DirectionalLight(16, 3, 32, intensity_min_max=torch.zeros(2, 2))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd:")}
+    lgt.load_state_dict(sd, strict=True)
+    lp = lgt(torch.from_numpy(g["feat"]))
+    assert np.abs(lp.detach().numpy() - g["light_params"]).max() < 1e-6
+    with pytest.raises(RuntimeError):
+        lgt.shade(torch.from_numpy(g["feat"]), torch.from_numpy(g["tex"])[..., :3], torch.from_numpy(g["nrm"]))

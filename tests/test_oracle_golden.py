@@ -67,3 +67,16 @@ def test_shading_normal_matches_reference():
     assert rel_err(pos.grad.numpy(), g["d_pos"]) < 1e-4
     assert rel_err(nrm.grad.numpy(), g["d_nrm"]) < 1e-4
     assert rel_err(geo.grad.numpy(), g["d_geo"]) < 1e-4
+
+
+def test_directional_shade_matches_reference():
+    """oracle.torch_ref.directional_shade vs the reference's DirectionalLight.shade (light.py:186-193) incl. gradients."""
+    g = golden("light_directional.npz")
+    tex = torch.from_numpy(g["tex"]).requires_grad_(True)
+    nrm = torch.from_numpy(g["nrm"]).requires_grad_(True)
+    lp = torch.from_numpy(g["light_params"])
+    shaded, shading = T.directional_shade(lp, tex[..., :3], nrm)
+    assert rel_err(shaded.detach().numpy(), g["shaded"]) < 1e-6 and rel_err(shading.detach().numpy(), g["shading"]) < 1e-6
+    ((shaded * torch.from_numpy(g["g_shaded"])).sum() + (shading * torch.from_numpy(g["g_shading"])).sum()).backward()
+    assert rel_err(tex.grad.numpy(), g["d_tex"]) < 1e-5
+    assert rel_err(nrm.grad.numpy(), g["d_nrm"]) < 1e-5
