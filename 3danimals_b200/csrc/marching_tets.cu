@@ -57,18 +57,21 @@ size_t mt_layout(int64_t Vg, int64_t E, int64_t T, void* base, MtWorkspace* ws)
 __device__ __forceinline__ bool occ_at(const uint32_t* __restrict__ bits, int v) { return (__ldg(bits + (v >> 5)) >> (v & 31)) & 1u; }
 
 // occupancy bitmask: occ = sdf > 0  (dmtet.py:106).  Each warp packs four 32-vertex words (four loads in flight per lane).
-__global__ void __launch_bounds__(MT_BLOCK) mt_occ_kernel(const float* __restrict__ sdf, int64_t Vg, uint32_t* __restrict__ bits)
+// Also clears the candidate-vertex bits (same word grid) and the error flag for the kernels that follow: no memsets.
+__global__ void __launch_bounds__(MT_BLOCK) mt_occ_kernel(const float* __restrict__ sdf, int64_t Vg, uint32_t* __restrict__ bits,
+                                                          uint32_t* __restrict__ cand, int* __restrict__ err)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t v0 = warp * 128 + lane;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *err = 0;
     float x[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) x[k] = v0 + k * 32 < Vg ? __ldg(sdf + v0 + k * 32) : 0.f;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         uint32_t m = __ballot_sync(0xffffffffu, x[k] > 0.f);
-        if (lane == 0 && warp * 128 + k * 32 < Vg) bits[warp * 4 + k] = m;
+        if (lane == 0 && warp * 128 + k * 32 < Vg) { bits[warp * 4 + k] = m; cand[warp * 4 + k] = 0u; }
     }
 }
 
@@ -176,8 +179,9 @@ __global__ void __launch_bounds__(MT_BLOCK) mt_tcount_kernel(const int4* __restr
 // totals; pass 2: shuffle scan per row with a running carry).  The array keeps one extra slot [n] = total so that tile
 // b's own count is data[b+1] - data[b].
 struct ScanJob { int* data; int64_t n; };
-__global__ void __launch_bounds__(1024) mt_scan_tiles_kernel(ScanJob j0, ScanJob j1, ScanJob j2, int* __restrict__ counts)
+__global__ void __launch_bounds__(1024) mt_scan_tiles_kernel(ScanJob j0, ScanJob j1, ScanJob j2, const int* __restrict__ err, int* __restrict__ counts)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[3] = *err;   // written by mt_vcount, which has completed
     __shared__ int s_warp[32];
     ScanJob j = blockIdx.x == 0 ? j0 : (blockIdx.x == 1 ? j1 : j2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -410,15 +414,12 @@ B2A_API int b2a_mt_count(const float* sdf, const int32_t* tets, const int32_t* e
     B2A_CHECK_ARG(((uintptr_t)tets & 15) == 0, "tets must be 16-byte aligned");
     MtWorkspace ws;
     B2A_CHECK_ARG(mt_layout(Vg, E, T, workspace, &ws) <= workspace_bytes, "workspace too small");
-    B2A_CUDA_OK(cudaMemsetAsync(ws.err, 0, 4, stream));
-    B2A_CUDA_OK(cudaMemsetAsync(ws.cand_bits, 0, (size_t)((Vg + 31) / 32) * 4, stream));
-    mt_occ_kernel<<<b2a_blocks(Vg, MT_BLOCK * 4), MT_BLOCK, 0, stream>>>(sdf, Vg, ws.occ_bits);
+    mt_occ_kernel<<<b2a_blocks(Vg, MT_BLOCK * 4), MT_BLOCK, 0, stream>>>(sdf, Vg, ws.occ_bits, ws.cand_bits, ws.err);
     mt_tcount_kernel<<<(unsigned)((ws.nTT + MT_TPB - 1) / MT_TPB), MT_BLOCK, 0, stream>>>((const int4*)tets, ws.occ_bits, tile_words, T, ws.nTT,
                                                                                           ws.tetidx, ws.t1tile, ws.t2tile, ws.cand_bits);
     mt_vcount_kernel<<<(unsigned)ws.nVT, MT_BLOCK, 0, stream>>>(edge_start, edge_b, ws.occ_bits, ws.cand_bits, Vg, ws.vcnt, ws.vtile, ws.err);
     ScanJob j0{ws.vtile, ws.nVT}, j1{ws.t1tile, ws.nTT}, j2{ws.t2tile, ws.nTT};
-    mt_scan_tiles_kernel<<<3, 1024, 0, stream>>>(j0, j1, j2, counts);
-    B2A_CUDA_OK(cudaMemcpyAsync(counts + 3, ws.err, 4, cudaMemcpyDeviceToDevice, stream));
+    mt_scan_tiles_kernel<<<3, 1024, 0, stream>>>(j0, j1, j2, ws.err, counts);
     B2A_LAUNCH_OK();
     return 0;
 }

@@ -304,16 +304,17 @@ class _LBS(torch.autograd.Function):
         Bb = bones.shape[0]
         dev = v_pos.device
         st = _stream()
-        d_G = torch.zeros(B, K, 12, device=dev)
-        d_v = None
-        if ctx.needs_input_grad[0]:
-            d_v = torch.zeros(Bv, V, 3, device=dev)
+        # one zero fill for the three accumulators (d_G, d_T, d_v): the step is host-bound, every launch counts
+        n, need_v = B * K * 12, ctx.needs_input_grad[0]
+        zbuf = torch.zeros(2 * n + (Bv * V * 3 if need_v else 0), device=dev)
+        d_G = zbuf[:n].view(B, K, 12)
+        d_v = zbuf[2 * n:].view(Bv, V, 3) if need_v else None
         if d_out is not None and V > 0:
             g = _f32(d_out, "d_out")
             _call("b2a_lbs_bwd", (_p(v_pos), _p(bones), _p(G), _p(g), B, Bv, Bb, K, V, ctx.inv_t, _p(d_v), _p(d_G), st))
         d_angles = None
         if ctx.needs_input_grad[2]:
-            d_T = torch.zeros(B, K, 12, device=dev)
+            d_T = zbuf[n:2 * n].view(B, K, 12)
             d_angles = torch.empty(B, K, 3, device=dev)
             gp = _f32(d_posed, "d_posed") if d_posed is not None else None
             _call("b2a_lbs_bone_transforms_bwd", (_p(bones), _p(angles), _p(chain_ptr), _p(chain_ids), _p(T_local), _p(d_G),

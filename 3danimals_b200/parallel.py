@@ -27,9 +27,12 @@ def allreduce_gradients(tensors, average=True, group=None):
     world = dist.get_world_size(group)
     if len(grads) == 1 and grads[0].is_contiguous():
         # single bucket already: reduce in place (no flatten / copy-back launches)
-        dist.all_reduce(grads[0], op=dist.ReduceOp.SUM, group=group)
-        if average:
-            grads[0].div_(world)
+        if average and dist.get_backend(group) == "nccl":
+            dist.all_reduce(grads[0], op=dist.ReduceOp.AVG, group=group)    # NCCL averages inside the collective: no div launch
+        else:
+            dist.all_reduce(grads[0], op=dist.ReduceOp.SUM, group=group)
+            if average:
+                grads[0].div_(world)
         return grads[0].numel() * grads[0].element_size()
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
