@@ -289,7 +289,18 @@ class _SkinningAux(dict):
 _chain_cache = {}
 
 
+_chain_last = [None, None, None, None]   # (tree object, K, device, tables): the same list object comes back every step
+
+
 def _chain_tables(kinematic_tree, K, device):
+    if _chain_last[0] is kinematic_tree and _chain_last[1] == K and _chain_last[2] == device:
+        return _chain_last[3]
+    tables = _chain_tables_by_value(kinematic_tree, K, device)
+    _chain_last[:] = [kinematic_tree, K, device, tables]
+    return tables
+
+
+def _chain_tables_by_value(kinematic_tree, K, device):
     key = (tuple((int(b), tuple(int(c) for c in ch)) for b, ch in kinematic_tree), K, str(device))
     if key not in _chain_cache:
         if len(_chain_cache) > 64:
