@@ -70,6 +70,34 @@ def lib():
     return handle
 
 
+_fast = False
+
+
+def fast():
+    """The generated METH_FASTCALL binding of the compute entry points (build.py build_fastcall), or None.  Same library,
+    same C-ABI: only the Python->C argument conversion differs (ctypes costs ~4 us per 30-argument call)."""
+    global _fast
+    if _fast is False:
+        _fast = None
+        lib()       # the extension links against libb2a.so ($ORIGIN rpath): make sure it exists / is built first
+        try:
+            import importlib.machinery
+            import importlib.util
+            from . import build as _build
+            path = _build.fastcall_path()
+            if not os.path.isfile(path):
+                path = _build.build_fastcall()
+            if path and os.path.isfile(path) and os.environ.get("B2A_CTYPES_ONLY", "0") != "1":
+                loader = importlib.machinery.ExtensionFileLoader(_build.FASTCALL_NAME, path)
+                spec = importlib.util.spec_from_loader(_build.FASTCALL_NAME, loader)
+                mod = importlib.util.module_from_spec(spec)
+                loader.exec_module(mod)
+                _fast = mod
+        except Exception:
+            _fast = None
+    return _fast
+
+
 def check(rc):
     if rc != 0:
         raise B2AError(lib().b2a_last_error_string().decode("utf-8", "replace") or "libb2a error %d" % rc)

@@ -95,7 +95,8 @@ _fn_cache = {}
 def _call(name, args, tag=None, launches=None):
     fn = _fn_cache.get(name)
     if fn is None:
-        fn = _fn_cache[name] = getattr(_L(), name)
+        fast = _lib.fast()
+        fn = _fn_cache[name] = getattr(fast, name, None) or getattr(_L(), name)
     tag = stats.tag if tag is None else tag
     if stats.timing:
         e0 = torch.cuda.Event(enable_timing=True)

@@ -66,3 +66,22 @@ def test_sass_is_sm100a():
     out = subprocess.run([cuobjdump, "-lelf", lib_mod.LIB_PATH], capture_output=True, text=True).stdout
     archs = {tok for line in out.splitlines() for tok in line.replace(".", " ").split() if tok.startswith("sm_")}
     assert archs == {"sm_100a"}, archs
+
+
+def test_fastcall_binding_covers_the_compute_entry_points():
+    """The generated METH_FASTCALL module (build.py build_fastcall) wraps every status-returning entry point whose
+    arguments are plain ints / floats / pointers, calls the same library instance (shared error string) and type-checks."""
+    lib_mod = pkg("_lib")
+    fast = lib_mod.fast()
+    assert fast is not None, "fastcall extension missing (needs Python.h + gcc at build time)"
+    protos = lib_mod.parse_header()
+    cold = {n for n, (rt, ps) in protos.items() if rt is not ctypes.c_int or any(p[0] in (ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_int)) for p in ps)}
+    assert {n for n in dir(fast) if n.startswith("b2a_")} == set(protos) - cold
+    n = len(protos["b2a_xfm_points_fwd"][1])
+    assert fast.b2a_xfm_points_fwd(*([None] * 2 + [1, 1, 8] + [None] * (n - 5))) != 0      # null pointers -> status, no launch
+    assert b"invalid argument" in lib_mod.lib().b2a_last_error_string()
+    try:
+        fast.b2a_xfm_points_fwd(1, 2)
+        raise AssertionError("wrong arity must raise")
+    except TypeError:
+        pass
