@@ -44,7 +44,12 @@ for name in dir(ops):
     if isinstance(obj, type) and issubclass(obj, torch.autograd.Function) and obj is not torch.autograd.Function:
         obj.forward = staticmethod(timed("node %s.forward" % name, obj.forward))
         obj.backward = staticmethod(timed("node %s.backward" % name, obj.backward))
-ops._call = timed("       C-ABI calls (ctypes)", ops._call)
+ops._call = timed("       C-ABI calls (binding + launches)", ops._call)
+torch.empty = timed("       torch.empty", torch.empty)
+torch.empty_like = timed("       torch.empty_like", torch.empty_like)
+torch.zeros = timed("       torch.zeros", torch.zeros)
+torch.zeros_like = timed("       torch.zeros_like", torch.zeros_like)
+ops._f32 = timed("       _f32 checks", ops._f32)
 ops._size = timed("       C-ABI size queries", ops._size)
 
 dev = torch.device("cuda:0")
@@ -66,6 +71,7 @@ def step():
     d[1] += 1
 
 
+torch.autograd.set_multithreading_enabled(False)      # what bench.py does by default
 for _ in range(5):
     step()
 torch.cuda.synchronize()

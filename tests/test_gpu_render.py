@@ -280,3 +280,56 @@ def test_sparse_field_evaluation_matches_dense(cuda):
         assert rel_err(x.cpu().numpy(), y.cpu().numpy()) < 1e-4
     for x, y in zip(a[4], b[4]):
         assert rel_err(x.cpu().numpy(), y.cpu().numpy()) < 1e-3      # sums over pixels in a different order / GEMM tiling
+
+
+def test_captured_render_and_finetune_match_eager(cuda):
+    """CUDA-graph replay of the fixed-topology loops (rotation frames, texture finetune; BASELINE configs[4]) gives exactly
+    the eager results: same kernels, same order, one launch."""
+    mesh_mod, render_mod, graphs = pkg("render.mesh"), pkg("render.render"), pkg("graphs")
+    pipe, sc, ref = _stage_inputs()
+    r = sc.image_res
+    faces_d = dev(ref["faces"].numpy(), cuda)
+    inst = mesh_mod.make_mesh(dev(ref["posed"][:, 0].detach().numpy(), cuda), faces_d[None], None, None, None)
+    prior = mesh_mod.make_mesh(dev(ref["verts"].detach().numpy(), cuda)[None], faces_d[None], None, None, None)
+    material = pipe.AnalyticField(dev(sc.w_kd, cuda), True)
+    light = pipe.FixedLight(dev(sc.light, cuda))
+    cams = [tuple(dev(x, cuda) for x in pkg("synthetic").cameras(sc.batch, seed=s)) for s in (3, 4, 5)]
+    modes = ("shaded", "shading", "kd")
+    cap = graphs.captured_render(inst, prior, material, light, (r, r), cams[0], spp=2, render_modes=modes)
+    for mvp, w2c, campos in cams:
+        with torch.no_grad():
+            eager = render_mod.render_mesh(None, inst, mvp, w2c, campos, material, light, (r, r), spp=2, msaa=True, bsdf="diffuse",
+                                           render_modes=list(modes), prior_mesh=prior, sparse_fields=False)
+        got = cap(mvp, w2c, campos)
+        for m, a, b in zip(modes, got, eager):
+            assert torch.equal(a, b), m
+    assert cap.replays == 3
+    # texture finetune: forward + backward to the texture field's weights, geometry fixed
+    w = dev(sc.w_kd, cuda).clone().requires_grad_(True)
+    ops = pkg("ops")
+
+    class Tex(torch.nn.Module):
+        bsdf, dense_only = None, True
+
+        def sample(self, x, feat=None):
+            return ops.analytic_field(x, w.detach(), True) * w.sum()      # differentiable in w through a PyTorch op
+
+    mvp, w2c, campos = cams[1]
+    target = torch.rand(sc.batch, 4, r, r, device=cuda)
+
+    def it(tgt):
+        out, = render_mod.render_mesh(None, inst, mvp, w2c, campos, Tex(), light, (r, r), render_modes=["shaded"], bsdf="diffuse",
+                                      prior_mesh=prior, sparse_fields=False)
+        loss = ((out - tgt) ** 2).mean()
+        g, = torch.autograd.grad(loss, [w])
+        return loss.detach(), g
+
+    loss_e, g_e = it(target)
+    step = graphs.CapturedStep(it, [target])
+    loss_c, g_c = step(target)
+    assert float(g_e.abs().max()) > 0
+    assert torch.allclose(loss_c, loss_e, rtol=1e-6) and torch.allclose(g_c, g_e, rtol=1e-5, atol=1e-9)
+    t2 = torch.rand_like(target)
+    loss_e2, g_e2 = it(t2)
+    loss_c2, g_c2 = step(t2)
+    assert torch.allclose(loss_c2, loss_e2, rtol=1e-6) and torch.allclose(g_c2, g_e2, rtol=1e-5, atol=1e-9)
