@@ -945,6 +945,173 @@ __global__ void __launch_bounds__(256, 5) aa_bwd_pair_kernel(AAParams Pw, AAGrad
     else aa_bwd_pix_body<CN, CN - 1, CGN>(Pn, Gn, ctx, d_color_n, (int64_t)nb);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// msaa / logging path (spp > 1, or keys that are composited but not antialiased: kd, normal, geo_normal).
+// render_mesh shades the g-buffer at [H/up, W/up] and the reference nearest-UPSAMPLES every shaded buffer to the raster
+// resolution before compositing it (render.py:217-219 util.scale_img_nhwc, :258-268) - at 2048^2 internal that is a
+// 64 MB copy per key forward and a 4x4 block sum per key backward, in separate PyTorch kernels.  Here the low-resolution
+// colour is read IN PLACE: hi-res pixel (y,x) takes colour row (y/up, x/up); the backward accumulates the up*up hi-res
+// contributions of a low-res pixel in registers and writes d_color at low resolution.  aa = 0: composite only.
+// Narrow keys only (C <= 4), prepared context required; same blend arithmetic and accumulation order as aa_fwd_pix.
+// ------------------------------------------------------------------------------------------------------------
+struct AAUp {
+    int up, W, HW, lw, lhw;   // hi-res width / pixels per image, low-res width / pixels per image
+};
+
+__device__ __forceinline__ size_t up_index(const AAUp& U, int b, size_t q)
+{
+    if (U.up == 1) return q;
+    const int p = (int)(q - (size_t)b * U.HW);
+    const int y = p / U.W, x = p - y * U.W;
+    return (size_t)b * U.lhw + (size_t)(y / U.up) * U.lw + (x / U.up);
+}
+
+template <int C>
+__device__ __forceinline__ float aa_comp_up(const float* __restrict__ color, const AAUp& U, const float* __restrict__ bg, int Bg,
+                                            const uint32_t* __restrict__ cover, int b, size_t q, int c)
+{
+    if (aa_bit(cover, q)) return c < C - 1 ? __ldg(color + up_index(U, b, q) * (C - 1) + c) : 1.f;
+    return bg ? __ldg(bg + (Bg == 1 ? q - (size_t)b * U.HW : q) * C + c) : 0.f;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) aa_up_fwd_kernel(const float* __restrict__ color, AAUp U, const float* __restrict__ bg, int Bg, AAContext ctx,
+                                                        int B, int aa, float* __restrict__ out)
+{
+    constexpr int CI = C - 1;
+    const int64_t n = (int64_t)B * U.HW;
+    const int64_t flat = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (flat >= n) return;
+    const int b = (int)(flat / U.HW);
+    const uint32_t cw = __ldg(ctx.cover + (flat >> 5));
+    const uint32_t aw = aa ? __ldg(ctx.act + (flat >> 5)) : 0u;
+    float v[C];
+    if ((cw >> (flat & 31)) & 1u) {
+        const float* cp = color + up_index(U, b, (size_t)flat) * CI;
+#pragma unroll
+        for (int c = 0; c < CI; c++) v[c] = __ldg(cp + c);
+        v[CI] = 1.f;
+    } else {
+        const float* bp = bg ? bg + (Bg == 1 ? flat - (int64_t)b * U.HW : flat) * C : nullptr;
+#pragma unroll
+        for (int c = 0; c < C; c++) v[c] = bp ? __ldg(bp + c) : 0.f;
+    }
+    if ((aw >> (flat & 31)) & 1u) {
+        const float4 a = __ldg(ctx.rec + flat);
+        const bool k0 = a.x < 0.f, k1 = a.y < 0.f, k2 = a.z > 0.f, k3 = a.w > 0.f;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const float own = v[c];
+            const float cu = k0 ? aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, (size_t)flat - U.W, c) : own;
+            const float cl = k1 ? aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, (size_t)flat - 1, c) : own;
+            const float cr = k2 ? aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, (size_t)flat + 1, c) : own;
+            const float cd = k3 ? aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, (size_t)flat + U.W, c) : own;
+            float acc = own;
+            if (k0) acc += a.x * (own - cu);
+            if (k1) acc += a.y * (own - cl);
+            if (k2) acc += a.z * (cr - own);
+            if (k3) acc += a.w * (cd - own);
+            v[c] = acc;
+        }
+    }
+    float* o = out + flat * C;
+    if (C == 4) reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[C - 1]);
+    else if (C == 2) reinterpret_cast<float2*>(o)[0] = make_float2(v[0], v[C - 1]);
+    else {
+#pragma unroll
+        for (int c = 0; c < C; c++) o[c] = v[c];
+    }
+}
+
+// position-gradient role with up-sampled colour (see aa_bwd_pos_role)
+template <int C>
+__device__ __forceinline__ void aa_up_pos_role(const float* __restrict__ color, const AAUp& U, const float* __restrict__ bg, int Bg, int64_t V,
+                                               const AAGrad& G, const AAContext& ctx, float* __restrict__ d_pos, int role_block)
+{
+    const int lane = threadIdx.x & 31, sub = lane & 15, d = lane >> 4;
+    const int count = ctx.count[1];
+    const int nwarp = AA_POS_BLOCKS * (blockDim.x >> 5);
+    for (int i = role_block * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += nwarp) {
+        const int flat = ctx.alist[i];
+        const int b = flat / U.HW, p = flat - b * U.HW;
+        const float4 av = __ldg(ctx.rec + flat);
+        const float a = d ? av.w : av.z;
+        const bool on = a != 0.f && fabsf(a) < 0.5f;
+        float dd = 0.f;
+        const size_t q0 = (size_t)flat, q1 = q0 + (d ? U.W : 1);
+        if (on) {
+            const int target = a > 0.f ? p : p + (d ? U.W : 1);
+            for (int c = sub; c < G.Cg; c += 16)
+                dd += grad_at(G, U.W, b, target, c) * (aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, q1, c) -
+                                                       aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, q0, c));
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
+        if (on && sub == 0 && dd != 0.f) {
+            const AAPosCoef* cp = ctx.acoef + (size_t)i * 2 + d;
+            const int4 c0 = __ldg(reinterpret_cast<const int4*>(cp));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(cp) + 1);
+            float* g1 = d_pos + ((size_t)b * V + c0.x) * 4;
+            float* g2 = d_pos + ((size_t)b * V + c0.y) * 4;
+            atomicAdd(g1, dd * __int_as_float(c0.z)); atomicAdd(g1 + 1, dd * __int_as_float(c0.w)); atomicAdd(g1 + 3, dd * c1.x);
+            atomicAdd(g2, dd * c1.y); atomicAdd(g2 + 1, dd * c1.z); atomicAdd(g2 + 3, dd * c1.w);
+        }
+    }
+}
+
+// one thread per LOW-resolution pixel: sums the colour gradient of its up*up hi-res pixels
+template <int C, int CC>
+__global__ void __launch_bounds__(256) aa_up_bwd_kernel(const float* __restrict__ color, AAUp U, const float* __restrict__ bg, int Bg, int64_t V,
+                                                        AAGrad G, AAContext ctx, int B, int aa, float* __restrict__ d_color,
+                                                        float* __restrict__ d_pos, int pos_blocks)
+{
+    if ((int)blockIdx.x < pos_blocks) {
+        aa_up_pos_role<C>(color, U, bg, Bg, V, G, ctx, d_pos, (int)blockIdx.x);
+        return;
+    }
+    const int64_t n = (int64_t)B * U.lhw;
+    const int64_t li = (int64_t)(blockIdx.x - pos_blocks) * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const int b = (int)(li / U.lhw);
+    const int lp = (int)(li - (int64_t)b * U.lhw);
+    const int yl = lp / U.lw, xl = lp - yl * U.lw;
+    float acc[CC];
+#pragma unroll
+    for (int c = 0; c < CC; c++) acc[c] = 0.f;
+    for (int dy = 0; dy < U.up; dy++) {
+        for (int dx = 0; dx < U.up; dx++) {
+            const int p = (yl * U.up + dy) * U.W + xl * U.up + dx;
+            const size_t flat = (size_t)b * U.HW + p;
+            if (!aa_bit(ctx.cover, flat)) continue;
+            float v[CC];
+#pragma unroll
+            for (int c = 0; c < CC; c++) v[c] = grad_at(G, U.W, b, p, c);
+            if (aa && aa_bit(ctx.act, flat)) {
+                const float4 a = __ldg(ctx.rec + flat);
+#pragma unroll
+                for (int c = 0; c < CC; c++) {
+                    const float own = v[c];
+                    const float gu = a.x != 0.f ? (a.x > 0.f ? grad_at(G, U.W, b, p - U.W, c) : own) : 0.f;
+                    const float gl = a.y != 0.f ? (a.y > 0.f ? grad_at(G, U.W, b, p - 1, c) : own) : 0.f;
+                    const float gr = a.z != 0.f ? (a.z > 0.f ? own : grad_at(G, U.W, b, p + 1, c)) : 0.f;
+                    const float gd = a.w != 0.f ? (a.w > 0.f ? own : grad_at(G, U.W, b, p + U.W, c)) : 0.f;
+                    float t = own;
+                    if (a.x != 0.f) t += a.x * gu;
+                    if (a.y != 0.f) t += a.y * gl;
+                    if (a.z != 0.f) t -= a.z * gr;
+                    if (a.w != 0.f) t -= a.w * gd;
+                    v[c] = t;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CC; c++) acc[c] += v[c];
+        }
+    }
+    float* o = d_color + li * CC;
+#pragma unroll
+    for (int c = 0; c < CC; c++) o[c] = acc[c];
+}
+
 int aa_check(const float* color, const float* rast, const float* pos, const int32_t* tri, const int32_t* opp, int Bg, int composite, int B,
              int64_t V, int64_t F, int H, int W, int C)
 {
@@ -1168,6 +1335,57 @@ B2A_API int b2a_antialias_pair_bwd(const float* color_w, const float* bg_w, int 
     if (nhwc) { if (Cgn == 4) B2A_PAIR_BWD(false, 4); else B2A_PAIR_BWD(false, 3); }
     else      { if (Cgn == 4) B2A_PAIR_BWD(true, 4);  else B2A_PAIR_BWD(true, 3); }
 #undef B2A_PAIR_BWD
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+namespace {
+bool up_args_ok(int up, int B, int H, int W, int C, const void* aa_ctx, size_t aa_ctx_bytes, AAContext* ctx, AAUp* U)
+{
+    if (up < 1 || H % up || W % up || C < 2 || C > 4 || !aa_fast_ok(1, aa_ctx, aa_ctx_bytes, B, H, W, C, ctx)) return false;
+    *U = AAUp{up, W, H * W, W / up, (H / up) * (W / up)};
+    return true;
+}
+}  // namespace
+
+B2A_API int b2a_composite_up_fwd(const float* color, int up, const float* bg, int Bg, int antialias, int B, int H, int W, int C,
+                                 float* out, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(color && out && aa_ctx, "null pointer");
+    B2A_CHECK_ARG(B > 0 && H > 0 && W > 0 && (Bg == 1 || Bg == B), "shape");
+    AAContext ctx;
+    AAUp U;
+    B2A_CHECK_ARG(up_args_ok(up, B, H, W, C, aa_ctx, aa_ctx_bytes, &ctx, &U), "needs C in 2..4, H and W multiples of `up`, and a prepared context");
+    B2A_CHECK_ARG(aligned16(out) || C == 3, "out must be 16-byte aligned");
+    const unsigned blocks = b2a_blocks((int64_t)B * H * W, 256);
+    switch (C) {
+        case 2: aa_up_fwd_kernel<2><<<blocks, 256, 0, stream>>>(color, U, bg, Bg, ctx, B, antialias, out); break;
+        case 3: aa_up_fwd_kernel<3><<<blocks, 256, 0, stream>>>(color, U, bg, Bg, ctx, B, antialias, out); break;
+        default: aa_up_fwd_kernel<4><<<blocks, 256, 0, stream>>>(color, U, bg, Bg, ctx, B, antialias, out); break;
+    }
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+B2A_API int b2a_composite_up_bwd(const float* color, int up, const float* bg, int Bg, int antialias, const float* d_out, int64_t d_sb,
+                                 int64_t d_sy, int64_t d_sx, int64_t d_sc, int Cg, int B, int64_t V, int H, int W, int C, float* d_color,
+                                 float* d_pos, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(color && d_out && d_color && aa_ctx, "null pointer");
+    B2A_CHECK_ARG(B > 0 && V > 0 && H > 0 && W > 0 && (Bg == 1 || Bg == B) && Cg >= 0 && Cg <= C, "shape");
+    AAContext ctx;
+    AAUp U;
+    B2A_CHECK_ARG(up_args_ok(up, B, H, W, C, aa_ctx, aa_ctx_bytes, &ctx, &U), "needs C in 2..4, H and W multiples of `up`, and a prepared context");
+    AAGrad G{d_out, d_sb, d_sy, d_sx, d_sc, Cg};
+    const int pos_blocks = (d_pos && antialias) ? AA_POS_BLOCKS : 0;
+    const unsigned grid = b2a_blocks((int64_t)B * U.lhw, 256) + pos_blocks;
+    switch (C) {
+        case 2: aa_up_bwd_kernel<2, 1><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
+        case 3: aa_up_bwd_kernel<3, 2><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
+        default: aa_up_bwd_kernel<4, 3><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
+    }
     B2A_LAUNCH_OK();
     return 0;
 }

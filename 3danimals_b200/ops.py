@@ -57,7 +57,7 @@ KERNELS_PER_CALL = {
     "b2a_xfm_points_bwd": 1, "b2a_rasterize_fwd": 3, "b2a_rasterize_bwd": 1, "b2a_interpolate_fwd": 1, "b2a_interpolate_bwd": 1,
     "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 2,
     "b2a_antialias_pair_fwd": 1, "b2a_antialias_pair_bwd": 1, "b2a_shade_directional_fwd": 1, "b2a_shade_directional_bwd": 1,
-    "b2a_analytic_field_fwd": 1, "b2a_analytic_field_bwd": 1, "b2a_gbuffer_fwd": 2, "b2a_gbuffer_bwd": 2,
+    "b2a_analytic_field_fwd": 1, "b2a_analytic_field_bwd": 1, "b2a_composite_up_fwd": 1, "b2a_composite_up_bwd": 1, "b2a_gbuffer_fwd": 2, "b2a_gbuffer_bwd": 2,
 }
 
 
@@ -650,6 +650,58 @@ def composite_antialias_pair(color_w, bg_w, keep_w, color_n, bg_n, keep_n, rast,
 def pair_supported(color_w, color_n, aa_ctx):
     return (aa_ctx is not None and color_w.shape[-1] == 16 and color_n.shape[-1] == 3 and color_w.shape[:3] == color_n.shape[:3]
             and color_w.shape[0] * color_w.shape[1] * color_w.shape[2] * 17 < (1 << 31))
+
+
+class _CompositeUp(torch.autograd.Function):
+    """Composite (+ antialias) of a narrow key whose colour lives at the g-buffer resolution [B,H/up,W/up,C-1]: the nearest
+    up-sampling of render.py:217-219 happens inside the kernel, the backward writes d_color at low resolution
+    (b2a_composite_up_fwd/bwd).  antialias=False: composite only (kd / normal / geo_normal)."""
+
+    @staticmethod
+    def forward(ctx, color, bg, pos, up, antialias, keep, aa_ctx, H, W):
+        color = _f32(color, "color"); pos = _f32(pos, "pos")
+        bg = _f32(bg, "background") if bg is not None else None
+        B = color.shape[0]
+        Cc = color.shape[-1] + 1
+        if color.shape[1] * up != H or color.shape[2] * up != W:
+            raise _lib.B2AError("composite_up: colour %s x%d does not match the raster resolution (%d,%d)" % (tuple(color.shape), up, H, W))
+        Bg = 1
+        if bg is not None:
+            if bg.shape[1:] != (H, W, Cc) or bg.shape[0] not in (1, B):
+                raise _lib.B2AError("antialias: background shape %s, expected [1|B,%d,%d,%d]" % (tuple(bg.shape), H, W, Cc))
+            Bg = bg.shape[0]
+        out = torch.empty(B, H, W, Cc, device=color.device)
+        _call("b2a_composite_up_fwd", (_p(color), up, _p(bg), Bg, int(antialias), B, H, W, Cc, _p(out), _p(aa_ctx), aa_ctx.numel(), _stream()),
+              tag="C%d" % Cc)
+        ctx.save_for_backward(color, bg, pos, aa_ctx)
+        ctx.cfg = (up, bool(antialias), Bg, Cc, int(keep), H, W)
+        return out[..., :keep] if keep < Cc else out
+
+    @staticmethod
+    def backward(ctx, g):
+        color, bg, pos, aa_ctx = ctx.saved_tensors
+        up, antialias, Bg, Cc, keep, H, W = ctx.cfg
+        if g.dtype != torch.float32:
+            g = g.float()
+        d_color = torch.empty_like(color)
+        d_pos = torch.zeros_like(pos) if (ctx.needs_input_grad[2] and antialias) else None
+        sb, sy, sx, sc = g.stride()
+        _call("b2a_composite_up_bwd", (_p(color), up, _p(bg), Bg, int(antialias), _p(g), sb, sy, sx, sc, keep, color.shape[0], pos.shape[1], H, W,
+                                        Cc, _p(d_color), _p(d_pos), _p(aa_ctx), aa_ctx.numel(), _stream()), tag="C%d" % Cc)
+        return d_color, None, d_pos, None, None, None, None, None, None
+
+
+def composite_up_supported(color, aa_ctx):
+    return aa_ctx is not None and 1 <= color.shape[-1] <= 3 and color.dtype == torch.float32
+
+
+def composite_up(color, background, pos, resolution, up=1, antialias_edges=True, keep=None, aa_ctx=None):
+    """color [B,H/up,W/up,C-1] (C <= 4) -> composited (+ antialiased) [B,H,W,keep] at the raster resolution (H,W)."""
+    if not composite_up_supported(color, aa_ctx):
+        raise _lib.B2AError("composite_up: needs a prepared context and at most 3 colour channels")
+    Cc = color.shape[-1] + 1
+    return _CompositeUp.apply(color, background, pos, int(up), bool(antialias_edges), Cc if keep is None else int(keep), aa_ctx,
+                              int(resolution[0]), int(resolution[1]))
 
 
 # ---------------------------------------------------------------------------------------------------------------

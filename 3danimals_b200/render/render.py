@@ -170,13 +170,19 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
         if key in fused:
             out_buffers.append(fused[key].permute(0, 3, 1, 2))
             continue
-        color = _nearest_up(buffers[key].float(), shade_spp)
+        color = buffers[key].float()
         bg = bg_full if key in _BG_KEYS else None
         if key == "shading" and bg is not None:
             bg = bg[..., 2:].contiguous()
         Cc = color.shape[-1] + 1
         keep = Cc if key == "shaded" else (Cc - 1 if key == "dino_pred" else _KEEP[key])
-        accum = ops.composite_antialias(color, bg, rast, v_pos_clip, tri, opp, antialias_edges=key in _AA_KEYS, keep=keep, aa_ctx=aa_ctx)
+        if (shade_spp > 1 or key not in _AA_KEYS) and ops.composite_up_supported(color, aa_ctx):
+            # msaa / logging keys: the low-resolution colour is up-sampled inside the composite kernel (no [B,H*spp,W*spp,C]
+            # copies), un-antialiased keys composite in the same kernel instead of a torch lerp sequence
+            accum = ops.composite_up(color, bg, v_pos_clip, full_res, up=shade_spp, antialias_edges=key in _AA_KEYS, keep=keep, aa_ctx=aa_ctx)
+        else:
+            accum = ops.composite_antialias(_nearest_up(color, shade_spp), bg, rast, v_pos_clip, tri, opp, antialias_edges=key in _AA_KEYS,
+                                            keep=keep, aa_ctx=aa_ctx)
         if spp > 1:
             accum = torch.nn.functional.avg_pool2d(accum.permute(0, 3, 1, 2), spp)
             out_buffers.append(accum)

@@ -181,6 +181,18 @@ int b2a_antialias_pair_bwd(const float* color_w, const float* bg_w, int Bg_w, in
                            int64_t n_sx, int64_t n_sc, int Cgn, float* d_color_n, int B, int64_t V, int H, int W,
                            float* d_pos, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
 
+/* msaa / logging fast path of the composite loop (model/render/render.py:217-219 + :258-268, :311-331): `color` is the
+ * shaded buffer at the g-buffer resolution [B,H/up,W/up,C-1] and is nearest-upsampled IN PLACE while it is composited
+ * (and, with antialias = 1, antialiased) at the raster resolution [B,H,W]; antialias = 0 composites only (kd, normal,
+ * geo_normal).  Narrow keys (C in 2..4) with a prepared context.  Backward: d_color at LOW resolution (the sum over each
+ * up x up block), d_pos [B,V,4] accumulated (zero-init, nullable; untouched when antialias = 0). */
+int b2a_composite_up_fwd(const float* color, int up, const float* bg, int Bg, int antialias, int B, int H, int W, int C,
+                         float* out, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
+int b2a_composite_up_bwd(const float* color, int up, const float* bg, int Bg, int antialias, const float* d_out,
+                         int64_t d_sb, int64_t d_sy, int64_t d_sx, int64_t d_sc, int Cg, int B, int64_t V, int H, int W,
+                         int C, float* d_color, float* d_pos, const void* aa_ctx, size_t aa_ctx_bytes,
+                         b2a_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Directional-light diffuse shading (DirectionalLight.shade, model/render/light.py:186-193):
  *   shading = ambient + diffuse * clamp(dot(light_dir, normal), min=0);  shaded = shading * kd.

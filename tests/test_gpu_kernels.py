@@ -456,6 +456,45 @@ def test_composite_antialias_pair_oracle(cuda, image, layout, keep_n):
     assert calls.get("b2a_antialias_pair_fwd", 0) >= 1
 
 
+@pytest.mark.parametrize("C,keep,up,aa,with_bg", [(4, 4, 2, True, True), (4, 4, 4, True, False), (2, 1, 2, True, True), (4, 3, 1, False, False),
+                                                  (4, 3, 2, False, True), (3, 2, 4, True, False)])
+def test_composite_up_oracle(cuda, C, keep, up, aa, with_bg):
+    """Low-resolution colour up-sampled inside the composite (+ antialias) kernel vs the reference's sequence: nearest
+    upsample (render.py:217-219) -> lerp composite -> antialias -> channel slice; backward incl. the up x up block sum."""
+    ops = _ops()
+    verts, faces, prior, mvp, w2c, campos, clip = _scene()
+    S = 128
+    s = S // up
+    rast = R.rasterize(clip, faces, (S, S))
+    rng = np.random.RandomState(13)
+    color = rng.rand(3, s, s, C - 1).astype(np.float32)
+    bg = rng.rand(3, S, S, C).astype(np.float32) if with_bg else None
+    opp = R.edge_adjacency(faces, verts.shape[1])
+    ct = torch.from_numpy(color).requires_grad_(True)
+    pt = torch.from_numpy(clip).requires_grad_(True)
+    alpha = torch.from_numpy((rast[..., 3:] > 0).astype(np.float32))
+    bgt = torch.from_numpy(bg) if with_bg else torch.zeros(1, S, S, C)
+    cu = ct.repeat_interleave(up, dim=1).repeat_interleave(up, dim=2)
+    acc = torch.lerp(bgt.expand(3, -1, -1, -1), torch.cat((cu, torch.ones_like(cu[..., :1])), -1), alpha)
+    if aa:
+        acc = T.antialias(acc.contiguous(), torch.from_numpy(rast), pt, torch.from_numpy(faces), torch.from_numpy(opp))
+    ref = acc[..., :keep].permute(0, 3, 1, 2)
+    g = rng.randn(*ref.shape).astype(np.float32)
+    (ref * torch.from_numpy(g)).sum().backward()
+    cd = dev(color, cuda).requires_grad_(True)
+    pd = dev(clip, cuda).requires_grad_(True)
+    aa_ctx = ops.antialias_prepare(dev(rast, cuda), pd.detach(), dev(faces, cuda), dev(opp, cuda))
+    out = ops.composite_up(cd, dev(bg, cuda) if with_bg else None, pd, (S, S), up=up, antialias_edges=aa, keep=keep, aa_ctx=aa_ctx).permute(0, 3, 1, 2)
+    assert np.array_equal(out.detach().cpu().numpy(), ref.detach().numpy())
+    out.backward(dev(g, cuda))
+    assert rel_err(cd.grad.cpu().numpy(), ct.grad.numpy()) < TOL
+    if aa:
+        assert np.abs(pt.grad.numpy()).max() > 0
+        assert rel_err(pd.grad.cpu().numpy(), pt.grad.numpy()) < TOL
+    else:
+        assert pd.grad is None or float(pd.grad.abs().max()) == 0
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # fused g-buffer
 # ----------------------------------------------------------------------------------------------------------------
