@@ -9,6 +9,8 @@
 // composite lerp(bg, [color,1], id>0) is folded in so the composited image never exists in HBM.  Only the vertex
 // position gradient of silhouette pairs uses atomics (a few thousand per image).
 #include "common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -594,12 +596,13 @@ constexpr int AA_POS_BLOCKS = 148 * 4;
 // geometry was folded into per-pair coefficients by aa_pairs_kernel, so this is a short gather + six atomics and costs
 // the streaming kernel no registers; it runs in the FIRST blocks of the same launch.
 template <int C>
-__device__ __forceinline__ void aa_bwd_pos_role(const AAParams& P, const AAGrad& G, const AAContext& ctx, float* __restrict__ d_pos, int role_block)
+__device__ __forceinline__ void aa_bwd_pos_role(const AAParams& P, const AAGrad& G, const AAContext& ctx, float* __restrict__ d_pos, int role_block,
+                                                int role_blocks = AA_POS_BLOCKS)
 {
     const int HW = P.H * P.W;
     const int lane = threadIdx.x & 31, sub = lane & 15, d = lane >> 4;
     const int count = ctx.count[1];
-    const int nwarp = AA_POS_BLOCKS * (blockDim.x >> 5);
+    const int nwarp = role_blocks * (blockDim.x >> 5);
     for (int i = role_block * (blockDim.x >> 5) + (threadIdx.x >> 5); i < count; i += nwarp) {
         const int flat = ctx.alist[i];
         const int b = flat / HW, p = flat - b * HW;
@@ -931,14 +934,24 @@ __global__ void __launch_bounds__(256, 5) aa_fwd_pair_kernel(const float* __rest
 template <int CW, int CGW, bool NCHW, int CN, int CGN>
 __global__ void __launch_bounds__(256, 5) aa_bwd_pair_kernel(AAParams Pw, AAGrad Gw, float* __restrict__ d_color_w, AAParams Pn, AAGrad Gn,
                                                              float* __restrict__ d_color_n, AAContext ctx, float* __restrict__ d_pos,
-                                                             int pos_blocks, int wide_blocks)
+                                                             int pos_blocks, int wide_blocks, int pos_first)
 {
     __shared__ float s_tile[8 * 32 * (CGW + 1)];
     int bx = (int)blockIdx.x;
-    if (bx < pos_blocks) { aa_bwd_pos_role<CW>(Pw, Gw, ctx, d_pos, bx); return; }
-    bx -= pos_blocks;
-    if (bx < pos_blocks) { aa_bwd_pos_role<CN>(Pn, Gn, ctx, d_pos, bx); return; }
-    bx -= pos_blocks;
+    if (pos_first < 0) {         // experiment switch (B2A_AA_POS): position-gradient roles at the END of the grid
+        const int stream_blocks = (int)gridDim.x - 2 * pos_blocks;
+        if (bx >= stream_blocks) {
+            bx -= stream_blocks;
+            if (bx < pos_blocks) aa_bwd_pos_role<CW>(Pw, Gw, ctx, d_pos, bx, pos_blocks);
+            else aa_bwd_pos_role<CN>(Pn, Gn, ctx, d_pos, bx - pos_blocks, pos_blocks);
+            return;
+        }
+    } else {
+        if (bx < pos_blocks) { aa_bwd_pos_role<CW>(Pw, Gw, ctx, d_pos, bx, pos_blocks); return; }
+        bx -= pos_blocks;
+        if (bx < pos_blocks) { aa_bwd_pos_role<CN>(Pn, Gn, ctx, d_pos, bx, pos_blocks); return; }
+        bx -= pos_blocks;
+    }
     int wb, nb;
     const bool wide = pair_role(bx, wide_blocks, wb, nb);
     if (wide) aa_bwd_tile_body<CW, CW - 1, CGW, NCHW, 1>(Pw, Gw, ctx, d_color_w, (int64_t)wb, s_tile);
@@ -1325,13 +1338,23 @@ B2A_API int b2a_antialias_pair_bwd(const float* color_w, const float* bg_w, int 
     const bool nhwc = w_sc == 1 && w_sx == Cgw && w_sy == (int64_t)W * Cgw && w_sb % 4 == 0 && aligned16(d_out_w);
     const bool nchw = w_sx == 1 && W % 32 == 0;
     B2A_CHECK_ARG(nhwc || nchw, "fused pair: the wide gradient must be NCHW- or NHWC-contiguous");
-    const int pos_blocks = d_pos ? AA_POS_BLOCKS : 0;
+    static int s_pos_blocks = 0, s_pos_first = 1;
+    if (s_pos_blocks == 0) {      // experiment switch: B2A_AA_POS="<blocks per key>[,last]" (default 592, first in the grid)
+        s_pos_blocks = AA_POS_BLOCKS;
+        const char* e = getenv("B2A_AA_POS");
+        if (e) {
+            int n = atoi(e);
+            if (n > 0 && n <= 4096) s_pos_blocks = n;
+            if (strstr(e, "last")) s_pos_first = -1;
+        }
+    }
+    const int pos_blocks = d_pos ? s_pos_blocks : 0;
     const unsigned tiles = (unsigned)(((int64_t)B * H * W) / 32);
     const unsigned wide_blocks = b2a_blocks(tiles, 8);
     const unsigned narrow_blocks = b2a_blocks((int64_t)B * H * W, 256 * AA_PPT);
     const unsigned grid = 2 * pos_blocks + wide_blocks + narrow_blocks;
 #define B2A_PAIR_BWD(NCHW_, CGN_) \
-    aa_bwd_pair_kernel<17, 16, NCHW_, 4, CGN_><<<grid, 256, 0, stream>>>(Pw, Gw, d_color_w, Pn, Gn, d_color_n, ctx, d_pos, pos_blocks, (int)wide_blocks)
+    aa_bwd_pair_kernel<17, 16, NCHW_, 4, CGN_><<<grid, 256, 0, stream>>>(Pw, Gw, d_color_w, Pn, Gn, d_color_n, ctx, d_pos, pos_blocks, (int)wide_blocks, s_pos_first)
     if (nhwc) { if (Cgn == 4) B2A_PAIR_BWD(false, 4); else B2A_PAIR_BWD(false, 3); }
     else      { if (Cgn == 4) B2A_PAIR_BWD(true, 4);  else B2A_PAIR_BWD(true, 3); }
 #undef B2A_PAIR_BWD

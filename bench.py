@@ -110,6 +110,70 @@ def cpu_arm(scene, steps, warmup, images):
     return images / dt, dt, max(cores, R.num_threads())
 
 
+def torch_ops_geometry_arm(hp, dev, reps=5):
+    """Second baseline of SURVEY.md §8d: the reference's torch-op formulation of the geometry half (R2 marching tets, R3
+    normals, R5 skinning; oracle/torch_ops_geometry.py, pinned against the reference's goldens) ON THIS GPU, next to the same
+    region through libb2a.so - forward + backward from seeded upstream gradients, CUDA events, mean of `reps`."""
+    import torch
+    from oracle import torch_ops_geometry as G
+    mesh_mod = importlib.import_module("3danimals_b200.render.mesh")
+    sk = importlib.import_module("3danimals_b200.geometry.skinning")
+    tets64 = hp.tets.long()
+    bones, chain = hp.last["bones"].detach(), hp.kinematic_chain
+    V = int(hp.last["inst"].v_pos.shape[1])
+    gen = torch.Generator(device=dev).manual_seed(11)
+    g_pos = torch.randn(hp.angles.shape[0], V, 3, device=dev, generator=gen)
+    g_nrm = torch.randn(hp.angles.shape[0], V, 3, device=dev, generator=gen)
+
+    grads = [g_pos, g_nrm]
+
+    def theirs():
+        sdf = hp.sdf.detach().clone().requires_grad_(True)
+        ang = hp.angles.detach().clone().requires_grad_(True)
+        verts, faces = G.marching_tets(hp.grid_verts, sdf, tets64)
+        G.auto_normals(verts[None], faces)
+        posed = G.skinning(verts[None, None], bones, chain, ang, temperature=0.05)[:, 0]
+        nrm = G.auto_normals(posed, faces)
+        torch.autograd.backward([posed, nrm], grads)
+        return sdf.grad, ang.grad
+
+    def ours():
+        sdf = hp.sdf.detach().clone().requires_grad_(True)
+        ang = hp.angles.detach().clone().requires_grad_(True)
+        verts, faces, uv_idx, faces32 = hp.dmtet.extract(hp.grid_verts, sdf, hp.grid)
+        prior = mesh_mod.make_mesh(verts[None], faces[None], None, uv_idx[None], None, faces_i32=faces32)
+        posed, _ = sk.skinning(prior.v_pos[:, None], bones, chain, ang, output_posed_bones=True, temperature=0.05)
+        inst = mesh_mod.make_mesh(posed[:, 0], prior.t_pos_idx, None, prior.t_tex_idx, None, faces_i32=prior.tri_i32())
+        torch.autograd.backward([inst.v_pos, inst.v_nrm], grads)
+        return sdf.grad, ang.grad
+
+    out = {}
+    for name, fn in (("torch_ops", theirs), ("libb2a", ours)):
+        for _ in range(2):
+            res = fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out["ms_" + name] = e0.elapsed_time(e1) / reps
+        out["_" + name] = res
+    out.pop("_torch_ops"), out.pop("_libb2a")
+    # agreement of the two arms on the well-conditioned part (gradient through the posed positions only: with a white-noise
+    # gradient on the vertex NORMALS both fp32 arms are 1e-2 away from an fp64 evaluation - near-degenerate vertices of the
+    # noisy SDF amplify rounding by 1/|sum of face normals|; measured: torch fp32 1.3e-2, libb2a 5e-2, see DESIGN.md §2)
+    grads[1] = torch.zeros_like(g_nrm)
+    a, b = theirs(), ours()
+    out["max_rel_diff_d_sdf_position_path"] = float((a[0] - b[0]).abs().max() / a[0].abs().max().clamp_min(1e-20))
+    out["max_rel_diff_d_angles_position_path"] = float((a[1] - b[1]).abs().max() / a[1].abs().max().clamp_min(1e-20))
+    out["speedup"] = out["ms_torch_ops"] / out["ms_libb2a"]
+    out["what"] = ("geometry half of the step (R2 extraction res-128 grid, R3 normals x2, R5 skinning 16 x %d verts x 20 bones) forward + "
+                   "backward on this GPU: the reference's torch-op formulation (oracle/torch_ops_geometry.py) vs libb2a.so" % V)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -321,6 +385,10 @@ def run_ours(args):
         ips, dt, cores = cpu_arm(scene, reps, 1, B)
         cpu = dict(value=ips, unit="images/s", cores=cores, kind="port", seconds_per_step=dt,
                    sample="full step (extraction + %d images fwd+bwd), %d steps after 1 warm-up; oracle/pipeline_ref.py" % (B, reps))
+        try:
+            cpu["gpu_torch_ops_geometry"] = torch_ops_geometry_arm(hp, dev)
+        except Exception as e:      # a baseline must never cost the bench line
+            cpu["gpu_torch_ops_geometry"] = dict(error=repr(e)[:200])
 
     if rank == 0:
         cfg = dict(WORKLOAD)

@@ -80,3 +80,35 @@ def test_directional_shade_matches_reference():
     ((shaded * torch.from_numpy(g["g_shaded"])).sum() + (shading * torch.from_numpy(g["g_shading"])).sum()).backward()
     assert rel_err(tex.grad.numpy(), g["d_tex"]) < 1e-5
     assert rel_err(nrm.grad.numpy(), g["d_nrm"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", golden_files("mt_")[:4] + golden_files("skin_"))
+def test_torch_op_geometry_baseline_matches_reference(name):
+    """oracle/torch_ops_geometry.py (the reference's torch-op formulation, timed on the GPU by bench.py as the second
+    baseline of SURVEY §8d) reproduces the reference-generated goldens on CPU."""
+    from oracle import torch_ops_geometry as G
+    g = golden(name)
+    if name.startswith("mt_"):
+        v, t = syn.kuhn_tet_grid(int(g["res"]))
+        pos = torch.from_numpy(v * np.float32(7.0))
+        sdf = torch.from_numpy(g["sdf"]).requires_grad_(True)
+        verts, faces = G.marching_tets(pos, sdf, torch.from_numpy(t).long())
+        assert np.array_equal(faces.numpy(), g["faces"])
+        assert rel_err(verts.detach().numpy(), g["verts"]) < 1e-6
+        (verts * torch.from_numpy(g["d_verts"])).sum().backward()
+        assert rel_err(sdf.grad.numpy().reshape(-1), g["d_sdf"].reshape(-1)) < 1e-4
+        n = G.auto_normals(verts.detach()[None], faces)
+        assert rel_err(n.numpy(), gnp.auto_normals(verts.detach().numpy()[None], faces.numpy())) < 1e-5
+    else:
+        ang = torch.from_numpy(g["angles"]).requires_grad_(True)
+        vp = torch.from_numpy(g["verts"])[None, None].clone().requires_grad_(True)
+        out = G.skinning(vp, torch.from_numpy(g["bones"]), _chain(g), ang, temperature=0.05)
+        assert rel_err(out.detach().numpy(), g["out"]) < 1e-5
+        (out * torch.from_numpy(g["g_out"])).sum().backward()
+        # the golden's d_angles also carries the posed-bones term; compare against the torch twin with that term removed
+        ang2 = torch.from_numpy(g["angles"]).requires_grad_(True)
+        vp2 = torch.from_numpy(g["verts"])[None, None].clone().requires_grad_(True)
+        o2, _ = T.skinning(vp2, torch.from_numpy(g["bones"]), _chain(g), ang2, temperature=0.05)
+        (o2 * torch.from_numpy(g["g_out"])).sum().backward()
+        assert rel_err(ang.grad.numpy(), ang2.grad.numpy()) < 1e-4
+        assert rel_err(vp.grad.numpy(), vp2.grad.numpy()) < 1e-4
