@@ -166,7 +166,10 @@ class TetGrid:
         self.tets = tets.to(_i32).contiguous()
         self.tile_words = self._build_tile_words()
         self.workspace = _workspace(_size(_L().b2a_mt_workspace_bytes, self.Vg, self.E, self.T), tets.device)
-        self.counts = torch.zeros(4, dtype=_i32, device=tets.device)
+        # output sizes (V, N1, N2, err): written by the count pass straight into PINNED host memory (zero-copy; under UVA the
+        # host pointer is the device pointer), so the one readback of the extraction is an event wait, not a D2H memcpy
+        self.counts = torch.zeros(4, dtype=_i32).pin_memory()
+        self.counts_ready = torch.cuda.Event()
 
     def _build_tile_words(self):
         """Static skip table of the extraction (csrc/marching_tets.cu mt_tcount): for every tile of consecutive tets the
@@ -215,7 +218,9 @@ class _MarchingTets(torch.autograd.Function):
         st = _stream()
         _call("b2a_mt_count", (_p(sdf_c), _p(grid.tets), _p(grid.edge_start), _p(grid.edge_b), _p(grid.tile_words), grid.Vg, grid.E, grid.T,
                                   _p(grid.workspace), grid.workspace.numel(), _p(grid.counts), st))
-        V, N1, N2, err = grid.counts.tolist()  # the one device->host read of the extraction (output sizes)
+        grid.counts_ready.record()
+        grid.counts_ready.synchronize()        # the one device->host hand-off of the extraction (output sizes)
+        V, N1, N2, err = grid.counts.tolist()
         if err:
             raise _lib.B2AError("marching_tets: a grid vertex has more than 255 crossing edges")
         Fn = N1 + 2 * N2
