@@ -88,6 +88,29 @@ def shading_case():
                         d_nrm=nrm.grad.numpy(), d_geo=geo.grad.numpy())
 
 
+def fauna_bones_case():
+    """3D-Fauna's estimate_bones variant (InstancePredictorFauna.py:20,84-99: bone_y_threshold = 0.4, seven masked
+    quantiles, skinning.py:163-175), single shape and a batch of per-instance shapes."""
+    ref = reference_loader.load()
+    mt = reference_loader.reference_dmtet("cpu")
+    v, t = syn.kuhn_tet_grid(20)
+    v = v * np.float32(7.0)
+    verts, _, _, _ = mt(torch.from_numpy(v), torch.from_numpy(syn.sdf_horse(v, 0.0, 0))[:, None], torch.from_numpy(t))
+    verts = verts.detach()
+    rng = np.random.RandomState(17)
+    batch = torch.stack([verts * (1 + 0.04 * i) + torch.from_numpy(rng.randn(*verts.shape).astype(np.float32)) * 0.01 for i in range(3)])[:, None]
+    out = {}
+    for tag, shape in (("single", verts[None, None]), ("batch", batch)):
+        bones, chain, aux = ref.skinning.estimate_bones(shape, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+",
+                                                        compute_kinematic_chain=True, bone_y_threshold=0.4)
+        bones2 = ref.skinning.estimate_bones(shape * 1.01, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+",
+                                             compute_kinematic_chain=False, aux=aux, bone_y_threshold=0.4)
+        out.update({tag + "_shape": shape.numpy(), tag + "_bones": bones.numpy(), tag + "_bones_rescaled": bones2.numpy(),
+                    tag + "_chain_ids": np.array([b for b, _ in chain]), tag + "_chain_dep": np.array([",".join(map(str, d)) for _, d in chain]),
+                    tag + "_attach": np.array([l["body_bone_idx"] for l in aux["legs"]])})
+    np.savez_compressed(os.path.join(OUT, "bones_fauna.npz"), **out)
+
+
 def light_case():
     """The reference's DirectionalLight (light.py:168-193): light MLP -> light_params, shade(feat, kd, normal) + grads."""
     ref = reference_loader.load()
@@ -115,9 +138,10 @@ def light_case():
 
 if __name__ == "__main__":
     torch.manual_seed(0)
-    if "--only-light" not in sys.argv:
+    if "--only-new" not in sys.argv:
         mt_cases()
         skin_cases()
         shading_case()
-    light_case()
+        light_case()
+    fauna_bones_case()
     print(sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))

@@ -142,6 +142,21 @@ def test_estimate_bones_batched_oracle(cuda, n_leg, mode):
     assert np.allclose(b3.cpu().numpy(), r3, atol=1e-5) and [(b, list(d)) for b, d in c3] == [(b, list(d)) for b, d in rc3]
 
 
+@pytest.mark.parametrize("tag", ["single", "batch"])
+def test_estimate_bones_fauna_variant_golden(cuda, tag):
+    """3D-Fauna's bone_y_threshold variant (config C3) on the device vs the reference's golden."""
+    sk = pkg("geometry.skinning")
+    g = golden("bones_fauna.npz")
+    shape = dev(g[tag + "_shape"], cuda)
+    bones, chain, aux = sk.estimate_bones(shape, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+", bone_y_threshold=0.4)
+    ref_chain = [(int(b), [int(x) for x in str(d).split(",") if x != ""]) for b, d in zip(g[tag + "_chain_ids"], g[tag + "_chain_dep"])]
+    assert [(int(b), [int(x) for x in d]) for b, d in chain] == ref_chain
+    assert np.allclose(bones.cpu().numpy(), g[tag + "_bones"], atol=1e-5)
+    bones2 = sk.estimate_bones(shape * 1.01, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+", compute_kinematic_chain=False,
+                               aux=aux, bone_y_threshold=0.4)
+    assert np.allclose(bones2.cpu().numpy(), g[tag + "_bones_rescaled"], atol=1e-5)
+
+
 def test_estimate_bones_quantile_exact(cuda):
     """The radix-select quantiles equal torch.quantile on the same device bits (x_margin exposed through the stats hook)."""
     ops = _ops()

@@ -150,3 +150,21 @@ def test_directional_light_module_matches_reference_golden():
     assert np.abs(lp.detach().numpy() - g["light_params"]).max() < 1e-6
     with pytest.raises(RuntimeError):
         lgt.shade(torch.from_numpy(g["feat"]), torch.from_numpy(g["tex"])[..., :3], torch.from_numpy(g["nrm"]))
+
+
+@pytest.mark.parametrize("tag", ["single", "batch"])
+def test_fauna_bones_variant_host_logic(tag):
+    """The drop-in estimate_bones' bone_y_threshold branch (device-side torch formulation; runs on any device) vs the
+    reference's golden: bones, kinematic chain, leg attachment, and the no-chain re-estimation of the next iteration."""
+    import torch
+    sk = pkg("geometry.skinning")
+    g = golden("bones_fauna.npz")
+    shape = torch.from_numpy(g[tag + "_shape"])
+    bones, chain, aux = sk.estimate_bones(shape, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+", bone_y_threshold=0.4)
+    ref_chain = [(int(b), [int(x) for x in str(d).split(",") if x != ""]) for b, d in zip(g[tag + "_chain_ids"], g[tag + "_chain_dep"])]
+    assert [(int(b), [int(x) for x in d]) for b, d in chain] == ref_chain
+    assert [int(l["body_bone_idx"]) for l in aux["legs"]] == list(g[tag + "_attach"])
+    assert np.allclose(bones.numpy(), g[tag + "_bones"], atol=1e-5)
+    bones2 = sk.estimate_bones(shape * 1.01, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+", compute_kinematic_chain=False,
+                               aux=aux, bone_y_threshold=0.4)
+    assert np.allclose(bones2.numpy(), g[tag + "_bones_rescaled"], atol=1e-5)

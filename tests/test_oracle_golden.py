@@ -112,3 +112,18 @@ def test_torch_op_geometry_baseline_matches_reference(name):
         (o2 * torch.from_numpy(g["g_out"])).sum().backward()
         assert rel_err(ang.grad.numpy(), ang2.grad.numpy()) < 1e-4
         assert rel_err(vp.grad.numpy(), vp2.grad.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["single", "batch"])
+def test_fauna_bones_variant_matches_reference(tag):
+    """bone_y_threshold = 0.4 (3D-Fauna, InstancePredictorFauna.py:20,84-99; skinning.py:163-175): numpy oracle vs the reference."""
+    g = golden("bones_fauna.npz")
+    shape = g[tag + "_shape"]
+    bones, chain, aux = gnp.estimate_bones(shape, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+", bone_y_threshold=0.4)
+    ref_chain = [(int(b), [int(x) for x in str(d).split(",") if x != ""]) for b, d in zip(g[tag + "_chain_ids"], g[tag + "_chain_dep"])]
+    assert chain == ref_chain
+    assert [l["body_bone_idx"] for l in aux["legs"]] == list(g[tag + "_attach"])
+    assert np.allclose(bones, g[tag + "_bones"], atol=1e-6)
+    bones2 = gnp.estimate_bones(shape * np.float32(1.01), 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+",
+                                compute_kinematic_chain=False, aux=aux, bone_y_threshold=0.4)
+    assert np.allclose(bones2, g[tag + "_bones_rescaled"], atol=1e-6)
