@@ -140,3 +140,57 @@ def test_vertex_normals_c_matches_numpy_restatement():
     for idx in [(0, 3, 0), (1, 10, 2), (0, 20, 1)]:
         fd = _fd(lambda x: R.vertex_normals(x, f)[0], v, g, idx, 1e-3)
         assert abs(fd - dp[idx]) < 2e-2 * max(1, abs(dp[idx]))
+
+
+def test_coverage_and_visibility_agree_with_an_independent_fp64_evaluation():
+    """Independent cross-check of the restated sampling rule on an extracted DMTet mesh: a brute-force numpy fp64
+    evaluation (every pixel centre against every projected triangle: signed-area containment, nearest interpolated z/w)
+    must give the same covered set and the same visible triangle as the C restatement, at every pixel that is not within
+    rounding distance of an edge or of a depth tie (where fp32 and fp64 may legitimately differ)."""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    syn = importlib.import_module("3danimals_b200.synthetic")
+    from oracle import geometry_np as gnp
+    v, t = syn.kuhn_tet_grid(20)
+    v = v * np.float32(7.0)
+    o = gnp.marching_tets(v, syn.sdf_horse(v, 0.0, 0), t, with_uvs=False)
+    verts, faces = o["verts"], o["faces"].astype(np.int32)
+    mvp, _, _ = syn.cameras(2, seed=5)
+    pos = R.xfm_points(verts[None], mvp)
+    H = W = 96
+    rast = R.rasterize(pos, faces, (H, W))
+    fy, fx = np.meshgrid((np.arange(H) + 0.5) / H * 2 - 1, (np.arange(W) + 0.5) / W * 2 - 1, indexing="ij")   # row 0 is clip y = -1
+    centre = np.stack([fx, fy], -1).reshape(-1, 1, 1, 2)                       # [P,1,1,2]
+    checked = 0
+    for b in range(2):
+        P = pos[b].astype(np.float64)
+        ndc = (P[:, :2] / P[:, 3:4])[faces]                                   # [F,3,2]
+        zw = (P[:, 2] / P[:, 3])[faces]                                       # [F,3]
+        cover = np.zeros(H * W, bool)
+        sure = np.ones(H * W, bool)
+        best = np.full(H * W, -1)
+        for p0 in range(0, H * W, 1024):                                      # chunks of pixels x all faces
+            d = ndc[None] - centre[p0:p0 + 1024]                              # [p,F,3,2]
+            e = d[:, :, [1, 2, 0]]
+            cr = d[..., 0] * e[..., 1] - d[..., 1] * e[..., 0]               # [p,F,3] signed areas
+            area = cr.sum(-1)
+            inside = ((cr >= 0).all(-1) | (cr <= 0).all(-1)) & (np.abs(area) > 1e-14)
+            edge_close = (np.abs(cr).min(-1) < 1e-6 * np.abs(area).clip(1e-14)) & (np.abs(area) > 1e-14) & \
+                         (((cr >= -1e-9).all(-1)) | ((cr <= 1e-9).all(-1)))
+            wgt = np.abs(cr[..., [1, 2, 0]]) / np.abs(area)[..., None].clip(1e-300)
+            z = np.where(inside, (wgt * zw[None]).sum(-1), np.inf)            # screen-space interpolation of z/w is exact
+            zs = np.sort(z, -1)
+            cover[p0:p0 + 1024] = inside.any(-1)
+            best[p0:p0 + 1024] = np.where(inside.any(-1), z.argmin(-1), -1)
+            with np.errstate(invalid="ignore"):
+                tie = (zs[:, 1] - zs[:, 0]) < 1e-6
+            sure[p0:p0 + 1024] = ~edge_close.any(-1) & ~tie
+        ours = rast[b, ..., 3].reshape(-1).astype(np.int64) - 1
+        m = sure
+        assert np.array_equal(ours[m] >= 0, cover[m])
+        assert np.array_equal(ours[m], best[m])
+        checked += int(m.sum())
+        assert cover[m].sum() > 800
+    assert checked > 2 * H * W * 0.9
