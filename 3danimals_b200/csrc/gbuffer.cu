@@ -190,12 +190,15 @@ __global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float*
                                                      const int* __restrict__ cov_count, const float* __restrict__ d_gb_pos,
                                                      const float* __restrict__ d_gb_geo, const float* __restrict__ d_gb_shn,
                                                      const float* __restrict__ d_gb_cam, const float* __restrict__ d_gb_tex,
-                                                     float* __restrict__ acc, float* __restrict__ d_w2c, float* __restrict__ d_campos)
+                                                     float* __restrict__ acc, float* __restrict__ d_w2c, float* __restrict__ d_campos,
+                                                     float* __restrict__ zero_buf, int64_t zero_n)
 {
     const int HW = P.H * P.W;
     const int64_t total = LIST ? (int64_t)*cov_count : (int64_t)P.B * HW;
     const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t span = (int64_t)gridDim.x * blockDim.x;
+    // zero-initialise the shared-prior gradient for the finalize pass that follows (instead of a memset in the stream)
+    for (int64_t i = first; i < zero_n; i += span) zero_buf[i] = 0.f;
     for (int64_t it = first - (threadIdx.x & 31); it < total; it += span) {   // warp-uniform trip count
         const int64_t idx = it + (threadIdx.x & 31);
         bool active = idx < total;
@@ -424,27 +427,28 @@ B2A_API int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, c
     }
     const float* pc = d_clip ? pos_clip : nullptr;
     const bool cam = d_w2c || d_campos;   // camera gradients cost registers (12 warp reductions): separate instantiation
+    float* zbuf = (d_prior_pos && Bq == 1) ? d_prior_pos : nullptr;      // zeroed by the main kernel for finalize's atomics
+    const int64_t zn = zbuf ? V * 3 : 0;
     if (cov_list) {
         // about one covered pixel per thread at typical coverage (~25 %); the grid-stride loop absorbs the rest
         unsigned lblocks = b2a_blocks(((int64_t)B * H * W + 3) / 4, 128);
         if (lblocks > 148u * 32u) lblocks = 148u * 32u;
         if (cam)
             gb_bwd_kernel<true, true><<<lblocks, 128, 0, stream>>>(P, pc, (const int4*)cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm,
-                                                                   d_gb_cam_nrm, d_gb_tex_pos, acc, d_w2c, d_campos);
+                                                                   d_gb_cam_nrm, d_gb_tex_pos, acc, d_w2c, d_campos, zbuf, zn);
         else
             gb_bwd_kernel<true, false><<<lblocks, 128, 0, stream>>>(P, pc, (const int4*)cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm,
-                                                                    d_gb_cam_nrm, d_gb_tex_pos, acc, d_w2c, d_campos);
+                                                                    d_gb_cam_nrm, d_gb_tex_pos, acc, d_w2c, d_campos, zbuf, zn);
     } else {
         unsigned blocks = b2a_blocks((int64_t)B * H * W, 128);
         if (cam)
             gb_bwd_kernel<false, true><<<blocks, 128, 0, stream>>>(P, pc, nullptr, nullptr, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
-                                                                   d_gb_tex_pos, acc, d_w2c, d_campos);
+                                                                   d_gb_tex_pos, acc, d_w2c, d_campos, zbuf, zn);
         else
             gb_bwd_kernel<false, false><<<blocks, 128, 0, stream>>>(P, pc, nullptr, nullptr, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
-                                                                    d_gb_tex_pos, acc, d_w2c, d_campos);
+                                                                    d_gb_tex_pos, acc, d_w2c, d_campos, zbuf, zn);
     }
     if (d_v_pos || d_v_nrm || d_prior_pos || d_clip || workspace_is_zero) {
-        if (d_prior_pos && Bq == 1) B2A_CUDA_OK(cudaMemsetAsync(d_prior_pos, 0, (size_t)V * 3 * sizeof(float), stream));
         gb_bwd_finalize_kernel<<<dim3(b2a_blocks(V, 256), B), 256, 0, stream>>>(acc, workspace_is_zero, B, Bq, V, d_v_pos, d_v_nrm, d_prior_pos, d_clip);
     }
     B2A_LAUNCH_OK();
