@@ -185,6 +185,8 @@ __device__ __forceinline__ void red4(float* p, float x, float y, float z, float 
 
 // LIST: threads walk the compact covered-pixel list written by the rasterizer (dense warps; DMTet renders cover ~20 %
 // of the image); otherwise one thread per pixel of the [B,H,W] grid (spp > 1 or no list).
+// launch bounds measured at C1 (B2A_GB_MINB sweep, round 1): (128,4) 123 regs, no spills 38.3 us | (128,5) 96 regs 38.3-39.1 us |
+// (128,6) 80 regs 44.8 us | (128,8) 64 regs 48.1 us - occupancy bought with spills loses
 template <bool LIST, bool CAMGRAD>
 __global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float* __restrict__ pos_clip, const int4* __restrict__ cov_list,
                                                      const int* __restrict__ cov_count, const float* __restrict__ d_gb_pos,
