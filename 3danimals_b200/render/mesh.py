@@ -1,6 +1,9 @@
 """Drop-in for the reference's model/render/mesh.py: Mesh, make_mesh, auto_normals (+ the edge utilities).
 
-`auto_normals` runs in libb2a.so (csrc/normals.cu, one launch for the whole batch, analytic backward).  Tangents are
+`auto_normals` runs in libb2a.so (csrc/normals.cu, one launch for the whole batch, analytic backward) - when somebody
+reads `mesh.v_nrm`: make_mesh / auto_normals only mark the normals as pending.  On the training path the prior shape's
+normals are never read (only the posed instances' normals reach the renderer, render.py:195), so a third of the
+reference's normal passes (mesh.py:276-304 runs three times per step) is not executed at all.  Tangents are
 numerically dead on every path of the reference (the perturbed normal is the constant (0,0,1), so the
 shading normal never depends on them) and the 4N^2-row UV atlas they are derived from is a per-grid constant; both
 are therefore materialised lazily - `mesh.v_tng` / `mesh.v_tex` have the reference's values when somebody reads them,
@@ -25,7 +28,8 @@ class Mesh:
     def __init__(self, v_pos=None, t_pos_idx=None, v_nrm=None, t_nrm_idx=None, v_tex=None, t_tex_idx=None, v_tng=None,
                  t_tng_idx=None, material=None, base=None):
         self.v_pos = v_pos
-        self.v_nrm = v_nrm
+        self._v_nrm = v_nrm
+        self._nrm_pending = False   # auto_normals: compute v_nrm from v_pos on first access
         self._v_tex = v_tex
         self._v_tng = v_tng
         self.t_pos_idx = t_pos_idx
@@ -40,6 +44,20 @@ class Mesh:
 
     # -- lazily materialised attributes --------------------------------------------------------------------------
     @property
+    def v_nrm(self):
+        if self._nrm_pending:
+            self._nrm_pending = False
+            self._v_nrm = ops.vertex_normals(self.v_pos, self.tri_i32())
+            if torch.is_anomaly_enabled():
+                assert torch.all(torch.isfinite(self._v_nrm))
+        return self._v_nrm
+
+    @v_nrm.setter
+    def v_nrm(self, v):
+        self._v_nrm = v
+        self._nrm_pending = False
+
+    @property
     def v_tex(self):
         v = self._v_tex
         if v is not None and self.v_pos is not None and v.shape[0] != self.v_pos.shape[0] and v.shape[0] == 1:
@@ -52,7 +70,7 @@ class Mesh:
 
     @property
     def v_tng(self):
-        if self._v_tng is None and self.v_nrm is not None and self._v_tex is not None and self.t_tex_idx is not None:
+        if self._v_tng is None and (self._v_nrm is not None or self._nrm_pending) and self._v_tex is not None and self.t_tex_idx is not None:
             self._v_tng = _tangents(self)
         return self._v_tng
 
@@ -83,9 +101,14 @@ class Mesh:
         return len(self.v_pos)
 
     def copy_none(self, other):
-        for name in ("v_pos", "t_pos_idx", "v_nrm", "t_nrm_idx", "_v_tex", "t_tex_idx", "_v_tng", "_t_tng_idx", "material"):
+        for name in ("v_pos", "t_pos_idx", "t_nrm_idx", "_v_tex", "t_tex_idx", "_v_tng", "_t_tng_idx", "material"):
             if getattr(self, name) is None:
                 setattr(self, name, getattr(other, name))
+        if self._v_nrm is None and not self._nrm_pending:      # normals: take the other's, computed or still pending
+            if other._nrm_pending and self.v_pos is other.v_pos and self.t_pos_idx is other.t_pos_idx:
+                self._nrm_pending = True
+            else:
+                self._v_nrm = other.v_nrm
         if self.t_pos_idx is other.t_pos_idx:
             if self.t_pos_idx_i32 is None:
                 self.t_pos_idx_i32 = other.t_pos_idx_i32
@@ -94,7 +117,9 @@ class Mesh:
 
     def clone(self):
         out = Mesh(base=self)
-        for name in ("v_pos", "t_pos_idx", "v_nrm", "t_nrm_idx", "_v_tex", "t_tex_idx", "_v_tng", "_t_tng_idx"):
+        if out._nrm_pending:          # a clone holds values, not a recipe
+            out.v_nrm = self.v_nrm
+        for name in ("v_pos", "t_pos_idx", "_v_nrm", "t_nrm_idx", "_v_tex", "t_tex_idx", "_v_tng", "_t_tng_idx"):
             v = getattr(out, name)
             if v is not None:
                 setattr(out, name, v.clone().detach())
@@ -180,10 +205,12 @@ def center_by_reference(base_mesh, ref_aabb, scale):
 
 def auto_normals(imesh):
     """Smooth area-weighted vertex normals (reference mesh.py:276-304) in one fused launch + analytic backward."""
-    v_nrm = ops.vertex_normals(imesh.v_pos, imesh.tri_i32())
-    if torch.is_anomaly_enabled():
-        assert torch.all(torch.isfinite(v_nrm))
-    return Mesh(v_nrm=v_nrm, t_nrm_idx=imesh.t_pos_idx, base=imesh)
+    if not imesh.v_pos.is_cuda:
+        raise ops._lib.B2AError("auto_normals needs CUDA tensors (the B200 hot path has no CPU fallback)")
+    out = Mesh(t_nrm_idx=imesh.t_pos_idx)
+    out._nrm_pending = True        # evaluated by the v_nrm property on first read (one fused launch + analytic backward)
+    out.copy_none(imesh)
+    return out
 
 
 def _tangents(imesh):
