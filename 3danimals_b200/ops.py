@@ -30,7 +30,15 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+_f32_t = torch.float32
+
+
 def _f32(t, name):
+    try:
+        if t.is_cuda and t.dtype is _f32_t and t.is_contiguous():      # the common case: nothing to do
+            return t
+    except AttributeError:
+        pass
     if not torch.is_tensor(t) or not t.is_cuda:
         raise _lib.B2AError("%s must be a CUDA tensor (the B200 hot path has no CPU fallback)" % name)
     if t.dtype != torch.float32:
@@ -39,6 +47,11 @@ def _f32(t, name):
 
 
 def _idx32(t, name):
+    try:
+        if t.is_cuda and t.dtype is _i32 and t.is_contiguous():
+            return t
+    except AttributeError:
+        pass
     if not torch.is_tensor(t) or not t.is_cuda:
         raise _lib.B2AError("%s must be a CUDA tensor" % name)
     if t.dtype != _i32:
@@ -914,7 +927,7 @@ class _RenderGeometry(torch.autograd.Function):
         ctx.set_materialize_grads(False)   # an unused output (rast outside 'flow' mode) must arrive as None, not as a zero tensor
         aa_out = aa_ctx if aa_ctx is not None else torch.empty(0, dtype=torch.uint8, device=dev)
         ctx.mark_non_differentiable(aa_out)
-        return (clip, rast, aa_out) + tuple(o if o is not None else torch.empty(0, device=dev) for o in outs)
+        return (clip, rast, aa_out) + tuple(o for o in outs if o is not None)     # only the requested g-buffers, in GB_KEYS order
 
     @staticmethod
     def backward(ctx, d_clip_up, d_rast, _aa, *grads):
@@ -924,9 +937,11 @@ class _RenderGeometry(torch.autograd.Function):
         B, V, F = v_pos.shape[0], v_pos.shape[1], tri.shape[0]
         st = _stream()
         need = ctx.needs_input_grad
-        gs = [(_f32(g, "d_gb") if (g is not None and p) else None) for g, p in zip(grads, present)]
+        it = iter(grads)                                                      # grads arrive for the present outputs only
+        gs = [next(it) if p else None for p in present]
+        gs = [(_f32(g, "d_gb") if g is not None else None) for g in gs]
         have_gb = any(g is not None for g in gs)
-        d_v_pos = torch.empty_like(v_pos) if (need[0] or True) else None      # also the accumulator of the clip-transform adjoint
+        d_v_pos = torch.empty_like(v_pos)                                     # also the accumulator of the clip-transform adjoint
         d_v_nrm = torch.empty_like(v_nrm) if need[1] else None
         d_prior = torch.empty_like(prior_pos) if need[2] else None
         d_mtx = torch.zeros_like(mtx) if need[3] else None
@@ -960,4 +975,4 @@ def render_geometry(v_pos, v_nrm, prior_pos, mtx, w2c, campos, tri, opp, resolut
     outs = _RenderGeometry.apply(v_pos, v_nrm, prior_pos, mtx, w2c, campos, _idx32(tri, "tri"), _idx32(opp, "opp"), int(resolution[0]),
                                  int(resolution[1]), int(spp), bool(two_sided), tuple(want), bool(need_aa))
     clip, rast, aa = outs[0], outs[1], outs[2]
-    return clip, rast, (aa if aa.numel() else None), {k: o for k, o in zip(GB_KEYS, outs[3:]) if k in want}
+    return clip, rast, (aa if aa.numel() else None), dict(zip([k for k in GB_KEYS if k in want], outs[3:]))
