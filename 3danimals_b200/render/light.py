@@ -18,28 +18,37 @@ import torch.nn.functional as F
 from .. import ops
 
 
+_ref_cache = {}
+
+
 def _reference_light():
+    """The reference's own model/render/light.py, loaded under a private name the first time one of its other names is asked
+    for (overlay mode: `model.render` is then the reference's package); None when the reference tree is not importable."""
     pkg = sys.modules.get("model.render")
     for d in getattr(pkg, "__path__", None) or []:
         f = os.path.join(d, "light.py")
+        if f in _ref_cache:
+            return _ref_cache[f]
         if os.path.isfile(f):
             try:
                 spec = importlib.util.spec_from_file_location("model.render._reference_light", f)
                 mod = importlib.util.module_from_spec(spec)
                 sys.modules[spec.name] = mod
                 spec.loader.exec_module(mod)
-                return mod
-            except Exception:           # the reference file needs its CUDA plugin / nvdiffrast textures: leave those names out
+            except Exception:           # the reference file needs something that is absent here: leave its names out
                 sys.modules.pop("model.render._reference_light", None)
-                return None
+                mod = None
+            _ref_cache[f] = mod
+            return mod
     return None
 
 
-_ref = _reference_light()
-if _ref is not None:
-    for _n in dir(_ref):
-        if not _n.startswith("_") and _n != "DirectionalLight":
-            globals()[_n] = getattr(_ref, _n)
+def __getattr__(name):      # PEP 562: every name this module does not define resolves to the reference module's
+    if not name.startswith("__"):
+        ref = _reference_light()
+        if ref is not None and hasattr(ref, name):
+            return getattr(ref, name)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))
 
 
 def _mlp_class():

@@ -115,6 +115,17 @@ def test_overlay_lets_reference_predictor_import_our_geometry():
         assert mod.DMTetGeometry.__module__ == "3danimals_b200.geometry.dmtet"
         assert importlib.import_module("model.render.render").__name__ == "3danimals_b200.render.render"
         assert importlib.import_module("model.networks.MLPs").__file__.startswith("/root/reference")
+        # model.render.light: DirectionalLight is the fused-shade drop-in (built on the reference's own MLP class), every
+        # other name of the reference module is re-exported from the reference file
+        mlps = importlib.import_module("model.networks.MLPs")
+        for sym in ("MLP", "CoordMLP"):      # what the reference's model/networks/__init__.py exports (the skeleton above skips it)
+            setattr(sys.modules["model.networks"], sym, getattr(mlps, sym))
+        light = importlib.import_module("model.render.light")
+        assert light.DirectionalLight.__module__ == "3danimals_b200.render.light"
+        assert hasattr(light, "EnvironmentLight") and light.EnvironmentLight.__module__ == "model.render._reference_light"
+        lgt = light.DirectionalLight(16, 3, 32, intensity_min_max=torch.zeros(2, 2))
+        assert type(lgt.mlp).__module__ == "model.networks.MLPs" and sorted(lgt.state_dict()) == [
+            "intensity_min_max", "mlp.network.0.weight", "mlp.network.2.weight", "mlp.network.4.weight"]
     finally:
         ov.uninstall()
         for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
