@@ -1338,17 +1338,24 @@ B2A_API int b2a_antialias_pair_bwd(const float* color_w, const float* bg_w, int 
     const bool nhwc = w_sc == 1 && w_sx == Cgw && w_sy == (int64_t)W * Cgw && w_sb % 4 == 0 && aligned16(d_out_w);
     const bool nchw = w_sx == 1 && W % 32 == 0;
     B2A_CHECK_ARG(nhwc || nchw, "fused pair: the wide gradient must be NCHW- or NHWC-contiguous");
-    static int s_pos_blocks = 0, s_pos_first = 1;
-    if (s_pos_blocks == 0) {      // experiment switch: B2A_AA_POS="<blocks per key>[,last]" (default 592, first in the grid)
-        s_pos_blocks = AA_POS_BLOCKS;
+    // Position-gradient blocks per key, leading the grid.  Measured at C1 (1 M pixels, ~5 k active pixels): 148 blocks 38.4 us,
+    // 592 41.0 us, 1184 41.1 us; at the END of the grid 592 40.7 us, 148 47.1 us, 37 80.3 us (their latency chains must overlap
+    // the streaming blocks).  Scaled with the image area so that a 2048^2 render (8x the silhouette) keeps ~600.
+    // B2A_AA_POS="<n>[,last]" overrides (tuning switch).
+    static int s_pos_override = -1, s_pos_first = 1;
+    if (s_pos_override < 0) {
+        s_pos_override = 0;
         const char* e = getenv("B2A_AA_POS");
         if (e) {
             int n = atoi(e);
-            if (n > 0 && n <= 4096) s_pos_blocks = n;
+            if (n > 0 && n <= 4096) s_pos_override = n;
             if (strstr(e, "last")) s_pos_first = -1;
         }
     }
-    const int pos_blocks = d_pos ? s_pos_blocks : 0;
+    int64_t scaled = ((int64_t)B * H * W) >> 13;
+    if (scaled < 148) scaled = 148;
+    if (scaled > 2 * AA_POS_BLOCKS) scaled = 2 * AA_POS_BLOCKS;
+    const int pos_blocks = d_pos ? (s_pos_override ? s_pos_override : (int)scaled) : 0;
     const unsigned tiles = (unsigned)(((int64_t)B * H * W) / 32);
     const unsigned wide_blocks = b2a_blocks(tiles, 8);
     const unsigned narrow_blocks = b2a_blocks((int64_t)B * H * W, 256 * AA_PPT);
