@@ -346,26 +346,41 @@ def run_ours(args):
         ev.record()
     prefetch(0)
 
+    seg = {} if os.environ.get("B2A_E2E_PROFILE", "0") == "1" else None     # host-time breakdown of the harness (stderr)
+
+    def mark(name, t0):
+        if seg is not None:
+            seg[name] = seg.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
     def e2e_step():
+        t0 = time.perf_counter()
         slot = state["i"] & 1
         state["i"] += 1
         prefetch(slot ^ 1)                                   # next step's inputs: H2D overlaps this step's compute
         main_stream.wait_event(copy_done[slot])
-        u8 = dev_bufs[slot]
-        tgt_rgba = torch.div(u8[:, :4], 255.0)              # uint8 -> fp32 / 255 in one kernel per target, contiguous results
-        tgt_dino = torch.div(u8[:, 4:], 255.0)
+        t0 = mark("prefetch + wait", t0)
+        tgt_all = torch.div(dev_bufs[slot], 255.0)          # uint8 -> fp32 / 255, one kernel for the whole record
+        tgt_rgba, tgt_dino = tgt_all[:, :4], tgt_all[:, 4:]
         consumed[slot].record()
         hp.sdf.grad = None
         hp.angles.grad = None
+        t0 = mark("convert", t0)
         shaded, dino = hp.forward()
+        t0 = mark("forward", t0)
         loss = F.mse_loss(shaded, tgt_rgba) + F.mse_loss(dino, tgt_dino)
+        t0 = mark("loss", t0)
         loss.backward()
+        t0 = mark("backward", t0)
         par.allreduce_gradients([hp.sdf.grad], average=True)
         loss_host.copy_(loss.detach(), non_blocking=True)
+        mark("allreduce + loss readback", t0)
 
     for _ in range(3):
         e2e_step()
     barrier()
+    if seg is not None:
+        seg.clear()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
@@ -375,6 +390,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms2.item()) / args.steps
+    if seg is not None and rank == 0:
+        n = args.steps
+        sys.stderr.write("e2e host segments (us/step): " + ", ".join("%s %.1f" % (k, v / n * 1e6) for k, v in seg.items()) + "\n")
     clocks = sampler.stop() if sampler else None     # sampled over the timed region, the per-kernel pass and the e2e region
     e2e = dict(value=world * B / (e2e_ms * 1e-3), unit="images/s", ms_per_step=e2e_ms,
                h2d_bytes_per_step=int(tgt.numel() * tgt.element_size()),
