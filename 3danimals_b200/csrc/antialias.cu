@@ -931,8 +931,8 @@ __global__ void __launch_bounds__(256, 5) aa_fwd_pair_kernel(const float* __rest
     else aa_fwd_pix_body<CN>(color_n, bg_n, Bg_n, ctx, B, H, W, out_n, (int64_t)nb);
 }
 
-template <int CW, int CGW, bool NCHW, int CN, int CGN, int TPW = 1, int MINB = 5>
-__global__ void __launch_bounds__(256, MINB) aa_bwd_pair_kernel(AAParams Pw, AAGrad Gw, float* __restrict__ d_color_w, AAParams Pn, AAGrad Gn,
+template <int CW, int CGW, bool NCHW, int CN, int CGN>
+__global__ void __launch_bounds__(256, 5) aa_bwd_pair_kernel(AAParams Pw, AAGrad Gw, float* __restrict__ d_color_w, AAParams Pn, AAGrad Gn,
                                                              float* __restrict__ d_color_n, AAContext ctx, float* __restrict__ d_pos,
                                                              int pos_blocks, int wide_blocks, int pos_first)
 {
@@ -954,7 +954,7 @@ __global__ void __launch_bounds__(256, MINB) aa_bwd_pair_kernel(AAParams Pw, AAG
     }
     int wb, nb;
     const bool wide = pair_role(bx, wide_blocks, wb, nb);
-    if (wide) aa_bwd_tile_body<CW, CW - 1, CGW, NCHW, TPW>(Pw, Gw, ctx, d_color_w, (int64_t)wb, s_tile);
+    if (wide) aa_bwd_tile_body<CW, CW - 1, CGW, NCHW, 1>(Pw, Gw, ctx, d_color_w, (int64_t)wb, s_tile);
     else aa_bwd_pix_body<CN, CN - 1, CGN>(Pn, Gn, ctx, d_color_n, (int64_t)nb);
 }
 
@@ -1356,20 +1356,12 @@ B2A_API int b2a_antialias_pair_bwd(const float* color_w, const float* bg_w, int 
     if (scaled < 148) scaled = 148;
     if (scaled > 2 * AA_POS_BLOCKS) scaled = 2 * AA_POS_BLOCKS;
     const int pos_blocks = d_pos ? (s_pos_override ? s_pos_override : (int)scaled) : 0;
-    static int s_var = -1;      // experiment switch B2A_AA_VAR: 0 default | 1 = (256,4) launch bounds | 2 = two tiles per wide warp
-    if (s_var < 0) { const char* e = getenv("B2A_AA_VAR"); s_var = e ? atoi(e) : 0; }
+    // Measured alternatives at C1 (B2A_AA_VAR sweep, round 1): (256,4) launch bounds / 64 registers, no spills: 42.3 us;
+    // two tiles per wide warp (32 loads in flight per lane): 41.5 us; this configuration ((256,5), one tile per warp): 38.6 us.
     const unsigned tiles = (unsigned)(((int64_t)B * H * W) / 32);
-    const unsigned wide_blocks = b2a_blocks(tiles, 8 * ((s_var == 2 && nchw && !nhwc && Cgn == 4) ? 2 : 1));
+    const unsigned wide_blocks = b2a_blocks(tiles, 8);
     const unsigned narrow_blocks = b2a_blocks((int64_t)B * H * W, 256 * AA_PPT);
     const unsigned grid = 2 * pos_blocks + wide_blocks + narrow_blocks;
-    if (s_var && nchw && !nhwc && Cgn == 4) {
-        if (s_var == 1)
-            aa_bwd_pair_kernel<17, 16, true, 4, 4, 1, 4><<<grid, 256, 0, stream>>>(Pw, Gw, d_color_w, Pn, Gn, d_color_n, ctx, d_pos, pos_blocks, (int)wide_blocks, s_pos_first);
-        else
-            aa_bwd_pair_kernel<17, 16, true, 4, 4, 2, 4><<<grid, 256, 0, stream>>>(Pw, Gw, d_color_w, Pn, Gn, d_color_n, ctx, d_pos, pos_blocks, (int)wide_blocks, s_pos_first);
-        B2A_LAUNCH_OK();
-        return 0;
-    }
 #define B2A_PAIR_BWD(NCHW_, CGN_) \
     aa_bwd_pair_kernel<17, 16, NCHW_, 4, CGN_><<<grid, 256, 0, stream>>>(Pw, Gw, d_color_w, Pn, Gn, d_color_n, ctx, d_pos, pos_blocks, (int)wide_blocks, s_pos_first)
     if (nhwc) { if (Cgn == 4) B2A_PAIR_BWD(false, 4); else B2A_PAIR_BWD(false, 3); }
