@@ -221,6 +221,12 @@ def run_ours(args):
     B, r = WORKLOAD["batch_per_gpu"], WORKLOAD["image_res"]
     scene = pipe.SyntheticScene(grid_res=WORKLOAD["grid_res"], batch=B, image_res=r, seed=rank)   # image-parallel shard
     hp = pipe.HotPath(scene, dev, mlps=args.mlps)
+    if args.mlps and args.mlp_math == "tf32":
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+    if args.mlps and args.mlp_math == "fp16":      # the reference wraps the field evaluation in autocast (bird config)
+        for net in (hp.material, hp.dino_net):
+            net.forward = torch.autocast("cuda", dtype=torch.float16)(net.forward)
     g1, g2 = scene.upstream_grads()
     d_shaded, d_dino = torch.from_numpy(g1).to(dev), torch.from_numpy(g2).to(dev)
 
@@ -415,7 +421,7 @@ def run_ours(args):
 
     if rank == 0:
         cfg = dict(WORKLOAD)
-        cfg.update(autograd_threads=args.autograd_threads, mesh_verts=st["V"], mesh_faces=st["F"], field="CoordMLP texture 8x256 + DINO 5x256 (M1b)" if args.mlps else "analytic (M1a)",
+        cfg.update(autograd_threads=args.autograd_threads, mesh_verts=st["V"], mesh_faces=st["F"], field=("CoordMLP texture 8x256 + DINO 5x256 (M1b, %s)" % args.mlp_math) if args.mlps else "analytic (M1a)",
                    parallelism="image-parallel dp%d, NCCL all-reduce on d_sdf only" % world)
         line = dict(metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -433,6 +439,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mlps", action="store_true", help="M1b: real CoordMLP texture/DINO fields instead of the analytic field")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--mlp-math", choices=["fp32", "tf32", "fp16"], default="fp32",
+                    help="with --mlps: arithmetic of the PyTorch-owned field MLPs - fp32 (the horse configs), tf32 "
+                         "(torch.backends.cuda.matmul.allow_tf32), fp16 autocast (the bird config, train_magicpony_bird.yaml:52)")
     ap.add_argument("--autograd-threads", choices=["on", "off"], default="off",
                     help="off (default): the caller runs the autograd engine on its own thread "
                          "(torch.autograd.set_multithreading_enabled(False)) - a one-line training-script setting that removes the "
