@@ -141,6 +141,8 @@ def _size(fn, *args):
         import ctypes
         out = ctypes.c_size_t(0)
         _lib.check(fn(*args, ctypes.byref(out)))
+        if len(_size_cache) >= 4096:      # in training V and F change every step: keep the memo bounded
+            _size_cache.clear()
         v = _size_cache[key] = out.value
     return v
 
