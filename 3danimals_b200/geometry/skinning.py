@@ -117,7 +117,9 @@ def estimate_bones(seq_shape, n_body_bones, resample=False, n_legs=4, n_leg_bone
     assert n_body_bones % 2 == 0
     if n_leg_bones > 0:
         assert n_legs == 4
-    if bone_y_threshold is None and body_bones_mode in _MODES and seq_shape.is_cuda:
+    if not seq_shape.is_cuda:
+        raise ops._lib.B2AError("estimate_bones needs CUDA tensors (the B200 hot path has no CPU fallback)")
+    if bone_y_threshold is None and body_bones_mode in _MODES:
         return _estimate_bones_fused(seq_shape, n_body_bones, n_leg_bones, body_bones_mode, compute_kinematic_chain, aux,
                                      attach_legs_to_body, legs_to_body_joint_indices)
     return _estimate_bones_torch(seq_shape, n_body_bones, n_leg_bones, body_bones_mode, compute_kinematic_chain, aux, attach_legs_to_body,
@@ -127,7 +129,9 @@ def estimate_bones(seq_shape, n_body_bones, resample=False, n_legs=4, n_leg_bone
 def _estimate_bones_torch(seq_shape, n_body_bones, n_leg_bones, body_bones_mode, compute_kinematic_chain, aux, attach_legs_to_body,
                           legs_to_body_joint_indices, bone_y_threshold):
     """Device-side torch formulation, used for Fauna's bone_y_threshold variant (InstancePredictorFauna.py:20,90: seven
-    masked quantiles) which the fused kernel does not cover yet."""
+    masked quantiles) which the fused kernel does not cover yet.  The public entry point only passes CUDA tensors; the
+    formulation itself is device-agnostic, which is how tests/test_host_logic.py pins it against the reference's goldens
+    without a GPU."""
     n_legs = 4
     zs_all = seq_shape[..., 2]
     if body_bones_mode == "z_minmax":

@@ -18,17 +18,20 @@ def _chain(g):
 
 @pytest.mark.parametrize("name", golden_files("skin_"))
 def test_estimate_bones_matches_reference_golden(name):
-    """estimate_bones is plain torch (device-agnostic): check it on CPU tensors against the reference's output."""
+    """The torch formulation behind estimate_bones (the path Fauna's variant takes on the device) is device-agnostic: pin it
+    on CPU tensors against the reference's output.  The public entry point itself refuses CPU tensors (no CPU fallback)."""
     sk = pkg("geometry.skinning")
     g = golden(name)
     verts = torch.from_numpy(g["verts"])[None, None]
     n_leg, mode = int(g["n_leg_bones"]), str(g["mode"])
-    bones, chain, aux = sk.estimate_bones(verts, 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode)
-    assert [(b, list(d)) for b, d in chain] == _chain(g)
-    assert np.allclose(bones.numpy(), g["bones"], atol=1e-6)
-    assert not bones.requires_grad
-    bones2 = sk.estimate_bones(verts * 1.01, 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode, compute_kinematic_chain=False, aux=aux)
-    assert np.allclose(bones2.numpy(), g["bones_rescaled"], atol=1e-6)
+    with pytest.raises(RuntimeError):
+        sk.estimate_bones(verts, 8, n_legs=4, n_leg_bones=n_leg, body_bones_mode=mode)
+    with torch.no_grad():
+        bones, chain, aux = sk._estimate_bones_torch(verts, 8, n_leg, mode, True, None, True, None, None)
+        assert [(b, list(d)) for b, d in chain] == _chain(g)
+        assert np.allclose(bones.numpy(), g["bones"], atol=1e-6)
+        bones2 = sk._estimate_bones_torch(verts * 1.01, 8, n_leg, mode, False, aux, True, None, None)
+        assert np.allclose(bones2.numpy(), g["bones_rescaled"], atol=1e-6)
 
 
 def test_estimate_bones_batched_matches_numpy_oracle():
@@ -40,7 +43,8 @@ def test_estimate_bones_batched_matches_numpy_oracle():
     shapes = np.stack([g["verts"] * np.float32(1 + 0.05 * i) + rng.randn(*g["verts"].shape).astype(np.float32) * 0.01
                        for i in range(6)]).reshape(3, 2, -1, 3)
     ref_b, ref_chain, ref_aux = gnp.estimate_bones(shapes, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+")
-    bones, chain, aux = sk.estimate_bones(torch.from_numpy(shapes), 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+")
+    with torch.no_grad():
+        bones, chain, aux = sk._estimate_bones_torch(torch.from_numpy(shapes), 8, 3, "z_minmax_y+", True, None, True, None, None)
     assert [(b, list(d)) for b, d in chain] == [(b, list(d)) for b, d in ref_chain]
     assert np.allclose(bones.numpy(), ref_b, atol=1e-6)
     assert [l["body_bone_idx"] for l in aux["legs"]] == [l["body_bone_idx"] for l in ref_aux["legs"]]
@@ -171,11 +175,11 @@ def test_fauna_bones_variant_host_logic(tag):
     sk = pkg("geometry.skinning")
     g = golden("bones_fauna.npz")
     shape = torch.from_numpy(g[tag + "_shape"])
-    bones, chain, aux = sk.estimate_bones(shape, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+", bone_y_threshold=0.4)
-    ref_chain = [(int(b), [int(x) for x in str(d).split(",") if x != ""]) for b, d in zip(g[tag + "_chain_ids"], g[tag + "_chain_dep"])]
-    assert [(int(b), [int(x) for x in d]) for b, d in chain] == ref_chain
-    assert [int(l["body_bone_idx"]) for l in aux["legs"]] == list(g[tag + "_attach"])
-    assert np.allclose(bones.numpy(), g[tag + "_bones"], atol=1e-5)
-    bones2 = sk.estimate_bones(shape * 1.01, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+", compute_kinematic_chain=False,
-                               aux=aux, bone_y_threshold=0.4)
-    assert np.allclose(bones2.numpy(), g[tag + "_bones_rescaled"], atol=1e-5)
+    with torch.no_grad():
+        bones, chain, aux = sk._estimate_bones_torch(shape, 8, 3, "z_minmax_y+", True, None, True, None, 0.4)
+        ref_chain = [(int(b), [int(x) for x in str(d).split(",") if x != ""]) for b, d in zip(g[tag + "_chain_ids"], g[tag + "_chain_dep"])]
+        assert [(int(b), [int(x) for x in d]) for b, d in chain] == ref_chain
+        assert [int(l["body_bone_idx"]) for l in aux["legs"]] == list(g[tag + "_attach"])
+        assert np.allclose(bones.numpy(), g[tag + "_bones"], atol=1e-5)
+        bones2 = sk._estimate_bones_torch(shape * 1.01, 8, 3, "z_minmax_y+", False, aux, True, None, 0.4)
+        assert np.allclose(bones2.numpy(), g[tag + "_bones_rescaled"], atol=1e-5)
