@@ -1,6 +1,9 @@
 // estimate_bones.cu - bone placement heuristic on sm_100a, no host synchronisation.
 // Replaces estimate_bones (reference model/geometry/skinning.py:49-248) for body_bones_mode in {z_minmax, z_minmax_y+},
-// bone_y_threshold=None, resample=False - the MagicPony / Ponymation configuration.
+// resample=False: the MagicPony / Ponymation configuration (bone_y_threshold=None: leg quadrants from the whole-batch x
+// quantiles, :156-161) and the 3D-Fauna one (bone_y_threshold = q: quadrants centred on the medians of the vertices below
+// the q-quantile of y, with margins from their 5 % / 95 % quantiles in x and z, :163-175 - seven quantiles, six of them
+// over a data-dependent subset).
 //
 // The reference runs ~80 torch ops per call: two full sorts (xs.quantile(0.05/0.95) over the whole batch), boolean-mask
 // gathers and a Python loop over (b,f) x 4 legs, each with host syncs.  Here:
@@ -19,9 +22,23 @@ constexpr int EB_T = 4;            // order statistics selected together
 constexpr int EB_BINS = 2048;
 constexpr int EB_HIST_THREADS = 256;
 
+constexpr int EB_SETS = 5;         // histogram sets: 0 = primary selection, 1..4 = the masked selections of the Fauna variant
+constexpr size_t EB_SET_WORDS = (size_t)3 * EB_T * EB_BINS;
+
 struct EbWorkspace {
-    unsigned* hist;   // [3][EB_T][EB_BINS]
+    unsigned* hist;   // [EB_SETS][3][EB_T][EB_BINS]
 };
+
+// one selection: two quantiles (floor / ceil rank each -> EB_T = 4 order statistics) of one coordinate
+struct EbSel {
+    int comp;         // 0 x, 1 y, 2 z
+    float q0, q1;
+};
+// the masked selections of the Fauna variant (skinning.py:167-170), sets 1..4
+__device__ __forceinline__ EbSel eb_masked_sel(int g)
+{
+    return g == 0 ? EbSel{0, 0.05f, 0.95f} : (g == 1 ? EbSel{0, 0.5f, 0.5f} : (g == 2 ? EbSel{2, 0.05f, 0.95f} : EbSel{2, 0.5f, 0.5f}));
+}
 
 __device__ __forceinline__ unsigned sortable_key(float f)
 {
@@ -33,11 +50,11 @@ __device__ __forceinline__ float key_to_float(unsigned k)
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// ranks of the four order statistics: floor/ceil of q*(n-1) for q = 0.05, 0.95 (fp32 arithmetic, as torch.quantile)
-__device__ __forceinline__ void eb_ranks(int64_t n, unsigned rank[EB_T], float w[2])
+// ranks of the four order statistics: floor/ceil of q*(n-1) for the two quantiles (fp32 arithmetic, as torch.quantile)
+__device__ __forceinline__ void eb_ranks(int64_t n, float q0, float q1, unsigned rank[EB_T], float w[2])
 {
-    const float last = (float)(n - 1);
-    const float qs[2] = {0.05f, 0.95f};
+    const float last = (float)(n > 0 ? n - 1 : 0);
+    const float qs[2] = {q0, q1};
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         float r = qs[i] * last;
@@ -46,6 +63,13 @@ __device__ __forceinline__ void eb_ranks(int64_t n, unsigned rank[EB_T], float w
         rank[2 * i + 1] = (unsigned)ceilf(r);
         w[i] = r - lo;
     }
+}
+
+// torch lerp (ATen/native/Lerp.h), fused like the CUDA build
+__device__ __forceinline__ float torch_lerp(float a, float b, float w)
+{
+    float d = b - a;
+    return fabsf(w) < 0.5f ? fmaf(w, d, a) : fmaf(-d, 1.f - w, b);
 }
 
 // One warp: smallest bin whose inclusive cumulative count exceeds k; *krem = k - (count before that bin).  Each lane owns
@@ -85,10 +109,11 @@ __device__ __forceinline__ void eb_select_bin_warp(const unsigned* __restrict__ 
 // prefix (already selected high bits) and remaining rank of every target after `passes` completed passes.  Warp t of
 // the block resolves target t (the four selections run concurrently); results are broadcast through shared memory.
 // Needs blockDim.x >= 128.  smem: 2 * EB_T unsigned.
-__device__ void eb_resolve(const EbWorkspace& ws, int passes, int64_t n, int* smem, unsigned prefix[EB_T], unsigned krem[EB_T])
+__device__ void eb_resolve(const unsigned* __restrict__ hset, int passes, int64_t n, float q0, float q1, int* smem, unsigned prefix[EB_T],
+                           unsigned krem[EB_T])
 {
     float w[2];
-    eb_ranks(n, krem, w);
+    eb_ranks(n, q0, q1, krem, w);
 #pragma unroll
     for (int t = 0; t < EB_T; t++) prefix[t] = 0u;
     const int warp = threadIdx.x >> 5;
@@ -98,7 +123,7 @@ __device__ void eb_resolve(const EbWorkspace& ws, int passes, int64_t n, int* sm
         for (int p = 0; p < passes; p++) {
             unsigned bin, k2;
             // pass 0 has one shared histogram (slot 0); later passes one per target
-            const unsigned* h = ws.hist + ((size_t)p * EB_T + (p == 0 ? 0 : t)) * EB_BINS;
+            const unsigned* h = hset + ((size_t)p * EB_T + (p == 0 ? 0 : t)) * EB_BINS;
             if (p == 2) eb_select_bin_warp<1024>(h, kr, &bin, &k2);
             else eb_select_bin_warp<EB_BINS>(h, kr, &bin, &k2);
             pf = (pf << (p == 2 ? 10 : 11)) | bin;
@@ -114,23 +139,63 @@ __device__ void eb_resolve(const EbWorkspace& ws, int passes, int64_t n, int* sm
     __syncthreads();
 }
 
-// x coordinate of flat vertex i of verts [n,3]
-template <int PASS>
-__global__ void __launch_bounds__(EB_HIST_THREADS) eb_hist_kernel(const float* __restrict__ verts, int64_t n, EbWorkspace ws)
+// number of keys a set's pass-0 histogram holds (the size of a masked subset); blockDim.x >= 32.  smem: 1 int.
+__device__ int64_t eb_set_count(const unsigned* __restrict__ hset, int* smem)
+{
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned s = 0;
+        for (int i = threadIdx.x; i < EB_BINS; i += 32) s += hset[i];
+        s = (unsigned)warp_sum_i((int)s);
+        if (threadIdx.x == 0) smem[0] = (int)s;
+    }
+    __syncthreads();
+    const int64_t c = (int64_t)(unsigned)smem[0];
+    __syncthreads();
+    return c;
+}
+
+// the two quantile values of a finished selection (three passes done): torch.quantile 'linear'
+__device__ void eb_quantiles(const unsigned* __restrict__ hset, int64_t n, float q0, float q1, int* smem, float& v0, float& v1)
+{
+    unsigned prefix[EB_T], krem[EB_T];
+    eb_resolve(hset, 3, n, q0, q1, smem, prefix, krem);
+    float w[2];
+    unsigned rk[EB_T];
+    eb_ranks(n, q0, q1, rk, w);
+    v0 = torch_lerp(key_to_float(prefix[0]), key_to_float(prefix[1]), w[0]);
+    v1 = torch_lerp(key_to_float(prefix[2]), key_to_float(prefix[3]), w[1]);
+}
+
+// Histogram pass PASS of selection `sel` into set `hset`.  MASKED: only vertices with y < y_thr take part, where y_thr is
+// the q_y quantile of y over everything (set 0, finished) and the subset size is the total of this set's pass-0 histogram;
+// blockIdx.y picks one of the four masked selections.
+template <int PASS, bool MASKED>
+__global__ void __launch_bounds__(EB_HIST_THREADS) eb_hist_kernel(const float* __restrict__ verts, int64_t n, EbWorkspace ws, EbSel sel0, float q_y)
 {
     __shared__ unsigned s_hist[(PASS == 0 ? 1 : EB_T) * EB_BINS];
     __shared__ int s_scan[34];
+    const EbSel sel = MASKED ? eb_masked_sel((int)blockIdx.y) : sel0;
+    unsigned* hset = ws.hist + (size_t)(MASKED ? 1 + blockIdx.y : 0) * EB_SET_WORDS;
+    float y_thr = 0.f;
+    int64_t n_sel = n;
+    if (MASKED) {
+        float dummy;
+        eb_quantiles(ws.hist, n, q_y, q_y, s_scan, y_thr, dummy);      // set 0 holds the finished y selection
+        if (PASS > 0) n_sel = eb_set_count(hset, s_scan);
+    }
     constexpr int NH = PASS == 0 ? 1 : EB_T;
     constexpr int SHIFT = PASS == 0 ? 21 : (PASS == 1 ? 10 : 0);       // position of this pass's digit
     constexpr unsigned MASK = PASS == 2 ? 1023u : 2047u;
     constexpr int PSHIFT = PASS == 1 ? 21 : 10;                         // key >> PSHIFT = bits selected so far
     for (int i = threadIdx.x; i < NH * EB_BINS; i += blockDim.x) s_hist[i] = 0u;
     unsigned prefix[EB_T], krem[EB_T];
-    eb_resolve(ws, PASS, n, s_scan, prefix, krem);   // includes __syncthreads
+    eb_resolve(hset, PASS, n_sel, sel.q0, sel.q1, s_scan, prefix, krem);   // includes __syncthreads
     __syncthreads();
 #pragma unroll 4
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        unsigned key = sortable_key(__ldg(verts + i * 3));
+        if (MASKED && !(__ldg(verts + i * 3 + 1) < y_thr)) continue;
+        unsigned key = sortable_key(__ldg(verts + i * 3 + sel.comp));
         unsigned digit = (key >> SHIFT) & MASK;
         if (PASS == 0) {
             atomicAdd(&s_hist[digit], 1u);
@@ -142,7 +207,7 @@ __global__ void __launch_bounds__(EB_HIST_THREADS) eb_hist_kernel(const float* _
         }
     }
     __syncthreads();
-    unsigned* g = ws.hist + (size_t)PASS * EB_T * EB_BINS;
+    unsigned* g = hset + (size_t)PASS * EB_T * EB_BINS;
     for (int i = threadIdx.x; i < NH * EB_BINS; i += blockDim.x)
         if (s_hist[i]) atomicAdd(g + i, s_hist[i]);
 }
@@ -204,17 +269,10 @@ __device__ __forceinline__ float linspace01(int i, int steps)
     return i < steps / 2 ? step * (float)i : 1.f - step * (float)(steps - 1 - i);
 }
 
-// torch lerp (ATen/native/Lerp.h), fused like the CUDA build
-__device__ __forceinline__ float torch_lerp(float a, float b, float w)
-{
-    float d = b - a;
-    return fabsf(w) < 0.5f ? fmaf(w, d, a) : fmaf(-d, 1.f - w, b);
-}
-
 constexpr int EB_MAX_JOINTS = 65;
 
 __global__ void __launch_bounds__(1024) eb_final_kernel(const float* __restrict__ verts, int N, int64_t V, int n_body, int n_leg, int mode,
-                                                        int at0, int at1, int at2, int at3, EbWorkspace ws, float* __restrict__ bones,
+                                                        int at0, int at1, int at2, int at3, EbWorkspace ws, float q_y, float* __restrict__ bones,
                                                         int* __restrict__ attach_out, float* __restrict__ stats_out)
 {
     __shared__ int s_scan[34];
@@ -226,17 +284,26 @@ __global__ void __launch_bounds__(1024) eb_final_kernel(const float* __restrict_
     const float* vp = verts + (size_t)inst * V * 3;
     const int64_t n = (int64_t)N * V;
 
-    // x_margin from the whole-batch quantiles (skinning.py:157)
-    float x_margin = 0.f;
-    if (n_leg > 0) {
-        unsigned prefix[EB_T], krem[EB_T];
-        eb_resolve(ws, 3, n, s_scan, prefix, krem);
-        float w[2];
-        unsigned rk[EB_T];
-        eb_ranks(n, rk, w);
-        float q05 = torch_lerp(key_to_float(prefix[0]), key_to_float(prefix[1]), w[0]);
-        float q95 = torch_lerp(key_to_float(prefix[2]), key_to_float(prefix[3]), w[1]);
+    // leg quadrants: x_margin from the whole-batch quantiles (skinning.py:157), or (Fauna, :163-175) centre (x0, z0) and
+    // margins (x_margin, z_margin) from the quantiles of the vertices below the y threshold
+    float x_margin = 0.f, z_margin = 0.f, x0 = 0.f, z0 = 0.f;
+    const bool fauna = q_y > 0.f;
+    if (n_leg > 0 && !fauna) {
+        float q05, q95;
+        eb_quantiles(ws.hist, n, 0.05f, 0.95f, s_scan, q05, q95);
         x_margin = (q95 - q05) * 0.2f;
+    } else if (n_leg > 0) {
+        float lo, hi, med, dummy;
+        const unsigned* h1 = ws.hist + 1 * EB_SET_WORDS;
+        const int64_t m = eb_set_count(h1, s_scan);
+        eb_quantiles(h1, m, 0.05f, 0.95f, s_scan, lo, hi);
+        x_margin = (hi - lo) * 0.2f;
+        eb_quantiles(ws.hist + 2 * EB_SET_WORDS, m, 0.5f, 0.5f, s_scan, med, dummy);
+        x0 = med;
+        eb_quantiles(ws.hist + 3 * EB_SET_WORDS, m, 0.05f, 0.95f, s_scan, lo, hi);
+        z_margin = (hi - lo) * 0.2f;
+        eb_quantiles(ws.hist + 4 * EB_SET_WORDS, m, 0.5f, 0.5f, s_scan, med, dummy);
+        z0 = med;
     }
 
     // mean (deterministic: fixed strided partial sums in double, fixed tree)
@@ -262,7 +329,8 @@ __global__ void __launch_bounds__(1024) eb_final_kernel(const float* __restrict_
         amax = arg_min2(amax, ArgVal{-zmax, (int)v});
         amin = arg_min2(amin, ArgVal{zmin, (int)v});
         if (n_leg > 0) {
-            bool q[4] = {x > x_margin && z > 0.f, x > x_margin && z < 0.f, x < -x_margin && z < 0.f, x < -x_margin && z > 0.f};
+            const float xr = x - x0, zr = z - z0;       // x0 = z0 = 0 and z_margin = 0 outside the Fauna variant
+            bool q[4] = {xr > x_margin && zr > z_margin, xr > x_margin && z < z0, xr < -x_margin && z < z0, xr < -x_margin && zr > z_margin};
 #pragma unroll
             for (int k = 0; k < 4; k++) foot[k] = arg_min2(foot[k], ArgVal{q[k] ? y : __int_as_float(0x7f800000), (int)v});
         }
@@ -284,6 +352,7 @@ __global__ void __launch_bounds__(1024) eb_final_kernel(const float* __restrict_
             float* so = stats_out + (size_t)inst * 8;
             so[0] = x_margin; so[1] = mx; so[2] = my; so[3] = mz;
             so[4] = __int_as_float(ia); so[5] = __int_as_float(ib);
+            so[6] = x0; so[7] = z0;
         }
     }
     __syncthreads();
@@ -347,7 +416,7 @@ __global__ void __launch_bounds__(1024) eb_final_kernel(const float* __restrict_
 size_t eb_layout(void* base, EbWorkspace* ws)
 {
     if (ws) ws->hist = (unsigned*)base;
-    return b2a_align((size_t)3 * EB_T * EB_BINS * sizeof(unsigned));
+    return b2a_align((size_t)EB_SETS * EB_SET_WORDS * sizeof(unsigned));
 }
 
 }  // namespace
@@ -359,9 +428,9 @@ B2A_API int b2a_estimate_bones_workspace_bytes(size_t* bytes)
     return 0;
 }
 
-B2A_API int b2a_estimate_bones(const float* verts, int N, int64_t V, int n_body_bones, int n_leg_bones, int mode, int attach0, int attach1,
-                               int attach2, int attach3, void* workspace, size_t workspace_bytes, float* bones, int32_t* attach_out,
-                               float* stats_out, b2a_stream_t stream_)
+B2A_API int b2a_estimate_bones(const float* verts, int N, int64_t V, int n_body_bones, int n_leg_bones, int mode, float bone_y_threshold,
+                               int attach0, int attach1, int attach2, int attach3, void* workspace, size_t workspace_bytes, float* bones,
+                               int32_t* attach_out, float* stats_out, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2A_CHECK_ARG(verts && bones && workspace, "null pointer");
@@ -369,19 +438,30 @@ B2A_API int b2a_estimate_bones(const float* verts, int N, int64_t V, int n_body_
     B2A_CHECK_ARG(n_body_bones >= 2 && n_body_bones % 2 == 0 && n_body_bones + 1 <= EB_MAX_JOINTS && n_leg_bones >= 0 && n_leg_bones <= 16,
                   "bone counts");
     B2A_CHECK_ARG(mode == 0 || mode == 1, "mode");
+    B2A_CHECK_ARG(bone_y_threshold >= 0.f && bone_y_threshold <= 1.f, "bone_y_threshold must be a quantile in [0,1] (0 = off)");
     B2A_CHECK_ARG(attach0 < n_body_bones && attach1 < n_body_bones && attach2 < n_body_bones && attach3 < n_body_bones, "attach index");
     EbWorkspace ws;
     B2A_CHECK_ARG(eb_layout(workspace, &ws) <= workspace_bytes, "workspace too small");
     const int64_t n = (int64_t)N * V;
+    const float q_y = n_leg_bones > 0 ? bone_y_threshold : 0.f;
     if (n_leg_bones > 0) {
-        B2A_CUDA_OK(cudaMemsetAsync(ws.hist, 0, (size_t)3 * EB_T * EB_BINS * sizeof(unsigned), stream));
+        const bool fauna = q_y > 0.f;
+        B2A_CUDA_OK(cudaMemsetAsync(ws.hist, 0, (size_t)(fauna ? EB_SETS : 1) * EB_SET_WORDS * sizeof(unsigned), stream));
         unsigned blocks = b2a_blocks(n, EB_HIST_THREADS * 2);
         if (blocks > 148u * 4u) blocks = 148u * 4u;
-        eb_hist_kernel<0><<<blocks, EB_HIST_THREADS, 0, stream>>>(verts, n, ws);
-        eb_hist_kernel<1><<<blocks, EB_HIST_THREADS, 0, stream>>>(verts, n, ws);
-        eb_hist_kernel<2><<<blocks, EB_HIST_THREADS, 0, stream>>>(verts, n, ws);
+        // primary selection: x at 5 % / 95 % (MagicPony), or y at the threshold quantile (Fauna)
+        const EbSel s0 = fauna ? EbSel{1, q_y, q_y} : EbSel{0, 0.05f, 0.95f};
+        eb_hist_kernel<0, false><<<blocks, EB_HIST_THREADS, 0, stream>>>(verts, n, ws, s0, q_y);
+        eb_hist_kernel<1, false><<<blocks, EB_HIST_THREADS, 0, stream>>>(verts, n, ws, s0, q_y);
+        eb_hist_kernel<2, false><<<blocks, EB_HIST_THREADS, 0, stream>>>(verts, n, ws, s0, q_y);
+        if (fauna) {   // four masked selections side by side (grid.y): x 5/95 %, x median, z 5/95 %, z median of {y < y_thr}
+            unsigned mb = blocks > 148u ? 148u : blocks;
+            eb_hist_kernel<0, true><<<dim3(mb, 4), EB_HIST_THREADS, 0, stream>>>(verts, n, ws, s0, q_y);
+            eb_hist_kernel<1, true><<<dim3(mb, 4), EB_HIST_THREADS, 0, stream>>>(verts, n, ws, s0, q_y);
+            eb_hist_kernel<2, true><<<dim3(mb, 4), EB_HIST_THREADS, 0, stream>>>(verts, n, ws, s0, q_y);
+        }
     }
-    eb_final_kernel<<<N, 1024, 0, stream>>>(verts, N, V, n_body_bones, n_leg_bones, mode, attach0, attach1, attach2, attach3, ws, bones,
+    eb_final_kernel<<<N, 1024, 0, stream>>>(verts, N, V, n_body_bones, n_leg_bones, mode, attach0, attach1, attach2, attach3, ws, q_y, bones,
                                             attach_out, stats_out);
     B2A_LAUNCH_OK();
     return 0;

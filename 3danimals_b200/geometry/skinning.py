@@ -10,6 +10,7 @@ arg-min instead of per-(b,f) Python loops; the only host read left is the leg at
 Python kinematic-chain lists when `compute_kinematic_chain=True` (once per epoch in MagicPony).
 """
 import math
+import os
 
 import torch
 
@@ -69,17 +70,20 @@ def _body_chain(n_body_bones):
 
 
 _MODES = {"z_minmax": 0, "z_minmax_y+": 1}
+# B2A_FUSED_FAUNA_BONES=0: 3D-Fauna's bone_y_threshold variant takes the device-side torch formulation instead of the kernel
+FUSED_FAUNA_VARIANT = os.environ.get("B2A_FUSED_FAUNA_BONES", "1") != "0"
 
 
 def _estimate_bones_fused(seq_shape, n_body_bones, n_leg_bones, body_bones_mode, compute_kinematic_chain, aux, attach_legs_to_body,
-                          legs_to_body_joint_indices):
-    """The sm_100a path (csrc/estimate_bones.cu): steady state = 1 memset + 4 launches, no host sync.  Building the
+                          legs_to_body_joint_indices, bone_y_threshold=None):
+    """The sm_100a path (csrc/estimate_bones.cu): steady state = 1 memset + 4 launches (7 for 3D-Fauna's bone_y_threshold
+    variant), no host sync.  Building the
     Python kinematic-chain lists (once per epoch in MagicPony, InstancePredictorBase.py:319-335) needs the leg attachment
     indices on the host: one 16-byte read."""
     mode = _MODES[body_bones_mode]
     if not compute_kinematic_chain:
         attach = [leg["body_bone_idx"] for leg in aux["legs"]] if n_leg_bones > 0 else (-1, -1, -1, -1)
-        return ops.estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, attach)
+        return ops.estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, attach, bone_y_threshold=bone_y_threshold)
     aux = {}
     bones_to_joints, kinematic_chain = _body_chain(n_body_bones)
     aux["bones_to_joints"] = bones_to_joints
@@ -87,7 +91,8 @@ def _estimate_bones_fused(seq_shape, n_body_bones, n_leg_bones, body_bones_mode,
         cfg = legs_to_body_joint_indices if legs_to_body_joint_indices is not None else [None, None, None, None]
         first = [-1 if cfg[i] is None else int(cfg[i]) for i in range(2)]
         if -1 in first:
-            _, att = ops.estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, first + [-1, -1], want_attach=True)
+            _, att = ops.estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, first + [-1, -1], want_attach=True,
+                                        bone_y_threshold=bone_y_threshold)
             first = att[:2].tolist()
         # legs 2 and 3 reuse the joints chosen for legs 1 and 0 (skinning.py:214-217)
         attach = [first[0], first[1], first[1], first[0]]
@@ -103,7 +108,7 @@ def _estimate_bones_fused(seq_shape, n_body_bones, n_leg_bones, body_bones_mode,
     else:
         attach = (-1, -1, -1, -1)
     aux["kinematic_chain"] = kinematic_chain
-    bones = ops.estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, attach)
+    bones = ops.estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, attach, bone_y_threshold=bone_y_threshold)
     return bones, kinematic_chain, aux
 
 
@@ -119,17 +124,19 @@ def estimate_bones(seq_shape, n_body_bones, resample=False, n_legs=4, n_leg_bone
         assert n_legs == 4
     if not seq_shape.is_cuda:
         raise ops._lib.B2AError("estimate_bones needs CUDA tensors (the B200 hot path has no CPU fallback)")
-    if bone_y_threshold is None and body_bones_mode in _MODES:
+    fused_ok = body_bones_mode in _MODES and (bone_y_threshold is None or (FUSED_FAUNA_VARIANT and 0.0 < float(bone_y_threshold) <= 1.0))
+    if fused_ok:
         return _estimate_bones_fused(seq_shape, n_body_bones, n_leg_bones, body_bones_mode, compute_kinematic_chain, aux,
-                                     attach_legs_to_body, legs_to_body_joint_indices)
+                                     attach_legs_to_body, legs_to_body_joint_indices, bone_y_threshold)
     return _estimate_bones_torch(seq_shape, n_body_bones, n_leg_bones, body_bones_mode, compute_kinematic_chain, aux, attach_legs_to_body,
                                  legs_to_body_joint_indices, bone_y_threshold)
 
 
 def _estimate_bones_torch(seq_shape, n_body_bones, n_leg_bones, body_bones_mode, compute_kinematic_chain, aux, attach_legs_to_body,
                           legs_to_body_joint_indices, bone_y_threshold):
-    """Device-side torch formulation, used for Fauna's bone_y_threshold variant (InstancePredictorFauna.py:20,90: seven
-    masked quantiles) which the fused kernel does not cover yet.  The public entry point only passes CUDA tensors; the
+    """Device-side torch formulation of both variants (Fauna's bone_y_threshold one: InstancePredictorFauna.py:20,90, seven
+    masked quantiles).  The fused kernel covers both; this formulation remains as the switchable alternative
+    (B2A_FUSED_FAUNA_BONES=0) and for body_bones_mode values outside the kernel's.  The public entry point only passes CUDA tensors; the
     formulation itself is device-agnostic, which is how tests/test_host_logic.py pins it against the reference's goldens
     without a GPU."""
     n_legs = 4

@@ -352,7 +352,7 @@ def lbs(v_pos, bones, angles, chain_ptr, chain_ids, temperature=1.0, want_weight
 _eb_ws = {}
 
 
-def estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, attach=(-1, -1, -1, -1), want_attach=False):
+def estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, attach=(-1, -1, -1, -1), want_attach=False, bone_y_threshold=None):
     """seq_shape [B,F,V,3] -> bones [B,F,K,2,3] in one memset + 4 launches, no host sync (reference skinning.py:49-248).
     attach: body-bone index per leg, -1 = auto.  want_attach: also return the device int32[4] with instance 0's choice."""
     L = _L()
@@ -365,9 +365,10 @@ def estimate_bones(seq_shape, n_body_bones, n_leg_bones, mode, attach=(-1, -1, -
         ws = _eb_ws[dev] = _workspace(_size(L.b2a_estimate_bones_workspace_bytes), dev)
     bones = torch.empty(B, Fr, K, 2, 3, device=dev)
     att = torch.empty(4, dtype=_i32, device=dev) if want_attach else None
-    _call("b2a_estimate_bones", (_p(x), B * Fr, V, int(n_body_bones), int(n_leg_bones), int(mode), int(attach[0]), int(attach[1]),
+    qy = 0.0 if bone_y_threshold is None else float(bone_y_threshold)
+    _call("b2a_estimate_bones", (_p(x), B * Fr, V, int(n_body_bones), int(n_leg_bones), int(mode), qy, int(attach[0]), int(attach[1]),
                                      int(attach[2]), int(attach[3]), _p(ws), ws.numel(), _p(bones), _p(att), None, _stream()),
-          launches=4 if n_leg_bones > 0 else 1)
+          launches=(7 if qy > 0 else 4) if n_leg_bones > 0 else 1)
     return (bones, att) if want_attach else bones
 
 

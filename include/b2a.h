@@ -79,18 +79,21 @@ int b2a_lbs_bone_transforms_bwd(const float* bones, const float* angles, const i
 
 /* ------------------------------------------------------------------------------------------------------------
  * Bone placement heuristic.  Replaces estimate_bones (model/geometry/skinning.py:49-248) for body_bones_mode
- * 'z_minmax' (mode 0) / 'z_minmax_y+' (mode 1), bone_y_threshold=None, resample=False.
+ * 'z_minmax' (mode 0) / 'z_minmax_y+' (mode 1), resample=False.  bone_y_threshold = 0: the MagicPony / Ponymation leg
+ * quadrants (bone_y_threshold=None, skinning.py:156-161); in (0,1]: the 3D-Fauna variant (InstancePredictorFauna.py:20,90;
+ * skinning.py:163-175): quadrants centred on the medians of the vertices below that quantile of y, with margins from their
+ * 5 % / 95 % quantiles in x and z - seven exact whole-batch quantiles, six of them over a data-dependent subset.
  * verts [N,V,3] (N = batch*frames) -> bones [N,K,2,3], K = n_body_bones + 4*n_leg_bones (legs only if n_leg_bones>0).
  * attach0..3: index of the body bone whose end joint each leg attaches to (aux['legs'][i]['body_bone_idx']); -1 = pick
  * the body bone closest in z to that instance's own foot (skinning.py:190-192) - attach_out [4] (nullable) receives
  * instance 0's choice, which is the one the reference then reuses for every instance.
  * The 5 %/95 % x-quantiles are taken over the WHOLE batch (skinning.py:157) by exact radix select, no sort, no sync.
- * stats_out (nullable) [N,8]: x_margin, mean xyz, bit-cast arg-max/arg-min vertex ids (test hook).
+ * stats_out (nullable) [N,8]: x_margin, mean xyz, bit-cast arg-max/arg-min vertex ids, x0, z0 (test hook).
  * ---------------------------------------------------------------------------------------------------------- */
 int b2a_estimate_bones_workspace_bytes(size_t* bytes);
-int b2a_estimate_bones(const float* verts, int N, int64_t V, int n_body_bones, int n_leg_bones, int mode, int attach0,
-                       int attach1, int attach2, int attach3, void* workspace, size_t workspace_bytes, float* bones,
-                       int32_t* attach_out, float* stats_out, b2a_stream_t stream);
+int b2a_estimate_bones(const float* verts, int N, int64_t V, int n_body_bones, int n_leg_bones, int mode,
+                       float bone_y_threshold, int attach0, int attach1, int attach2, int attach3, void* workspace,
+                       size_t workspace_bytes, float* bones, int32_t* attach_out, float* stats_out, b2a_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Smooth vertex normals.  Replaces mesh.auto_normals (model/render/mesh.py:276-304).

@@ -157,6 +157,34 @@ def test_estimate_bones_fauna_variant_golden(cuda, tag):
     assert np.allclose(bones2.cpu().numpy(), g[tag + "_bones_rescaled"], atol=1e-5)
 
 
+def test_estimate_bones_fauna_quantiles_exact_and_batched_oracle(cuda):
+    """The Fauna variant's seven radix-select quantiles (one over everything, six over the data-dependent subset y < y_thr)
+    equal torch.quantile on the same device bits (stats hook), and random batched shapes agree with the numpy oracle."""
+    ops, sk, lib = _ops(), pkg("geometry.skinning"), pkg("_lib")
+    rng = np.random.RandomState(5)
+    for n_inst, V in ((1, 1500), (3, 4099)):
+        x = dev(rng.randn(n_inst, 1, V, 3).astype(np.float32) * 2, cuda)
+        x[0, 0, :9, 1] = x[0, 0, 9, 1]          # ties around / inside the subset
+        ws = torch.empty(ops._size(lib.lib().b2a_estimate_bones_workspace_bytes), dtype=torch.uint8, device=cuda)
+        bones = torch.empty(n_inst, 20, 2, 3, device=cuda)
+        stats = torch.zeros(n_inst, 8, device=cuda)
+        ops._call("b2a_estimate_bones", (x.data_ptr(), n_inst, V, 8, 3, 1, 0.4, -1, -1, -1, -1, ws.data_ptr(), ws.numel(), bones.data_ptr(), None,
+                                         stats.data_ptr(), ops._stream()), launches=7)
+        xs, ys, zs = x[..., 0], x[..., 1], x[..., 2]
+        flags = ys < ys.quantile(0.4)
+        xm = (xs[flags].quantile(0.95) - xs[flags].quantile(0.05)) * 0.2
+        assert torch.all(stats[:, 0] == xm), (stats[:, 0], xm)
+        assert torch.all(stats[:, 6] == xs[flags].quantile(0.5)) and torch.all(stats[:, 7] == zs[flags].quantile(0.5))
+    g = golden("skin_horse.npz")
+    shapes = np.stack([g["verts"] * np.float32(1 + 0.05 * i) + rng.randn(*g["verts"].shape).astype(np.float32) * 0.01
+                       for i in range(4)]).reshape(2, 2, -1, 3)
+    ref_b, ref_chain, ref_aux = gnp.estimate_bones(shapes, 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+", bone_y_threshold=0.4)
+    bones, chain, aux = sk.estimate_bones(dev(shapes, cuda), 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+", bone_y_threshold=0.4)
+    assert [(int(b), [int(v) for v in d]) for b, d in chain] == [(int(b), [int(v) for v in d]) for b, d in ref_chain]
+    assert np.allclose(bones.cpu().numpy(), ref_b, atol=1e-5)
+    assert ops.stats.calls.get("b2a_estimate_bones", 0) > 0
+
+
 def test_estimate_bones_quantile_exact(cuda):
     """The radix-select quantiles equal torch.quantile on the same device bits (x_margin exposed through the stats hook)."""
     ops = _ops()
@@ -168,7 +196,7 @@ def test_estimate_bones_quantile_exact(cuda):
         ws = torch.empty(ops._size(lib.lib().b2a_estimate_bones_workspace_bytes), dtype=torch.uint8, device=cuda)
         bones = torch.empty(n_inst, 20, 2, 3, device=cuda)
         stats = torch.zeros(n_inst, 8, device=cuda)
-        ops._call("b2a_estimate_bones", (x.data_ptr(), n_inst, V, 8, 3, 1, -1, -1, -1, -1, ws.data_ptr(), ws.numel(), bones.data_ptr(), None,
+        ops._call("b2a_estimate_bones", (x.data_ptr(), n_inst, V, 8, 3, 1, 0.0, -1, -1, -1, -1, ws.data_ptr(), ws.numel(), bones.data_ptr(), None,
                                          stats.data_ptr(), ops._stream()), launches=4)
         xs = x[..., 0]
         ref = (xs.quantile(0.95) - xs.quantile(0.05)) * 0.2
