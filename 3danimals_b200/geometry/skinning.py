@@ -335,12 +335,25 @@ def skinning(v_pos, bones_pred, kinematic_tree, deform_params, output_posed_bone
             x = x.expand(B, Fr, *inner)
         return x.reshape(BF, *inner)
 
-    v_flat = flat(v_pos, (V, 3))
-    b_flat = flat(bones_pred.detach() if not bones_pred.requires_grad else bones_pred, (K, 2, 3))
     chain_ptr, chain_ids = _chain_tables(kinematic_tree, K, deform_params.device)
-    out, posed, _ = ops.lbs(v_flat, b_flat, deform_params.reshape(BF, K, 3), chain_ptr, chain_ids, temperature, want_weights=False)
+    bones_in = bones_pred.detach() if not bones_pred.requires_grad else bones_pred
+
+    def plain(x):       # batch/frame dims both 1, or both full: no broadcast to materialise
+        return x.shape[0] * x.shape[1] == 1 or (x.shape[0] == B and x.shape[1] == Fr)
+
+    if plain(v_pos) and plain(bones_in):
+        v_flat = b_flat = None
+        out4, posed4 = ops.lbs_bf(v_pos, bones_in, deform_params, chain_ptr, chain_ids, temperature)
+    else:
+        v_flat = flat(v_pos, (V, 3))
+        b_flat = flat(bones_in, (K, 2, 3))
+        out, posed, _ = ops.lbs(v_flat, b_flat, deform_params.reshape(BF, K, 3), chain_ptr, chain_ids, temperature, want_weights=False)
+        out4, posed4 = out.reshape(B, Fr, V, 3), posed.reshape(B, Fr, K, 2, 3)
 
     def weights():
+        nonlocal v_flat, b_flat
+        if v_flat is None:
+            v_flat, b_flat = flat(v_pos, (V, 3)), flat(bones_in, (K, 2, 3))
         with torch.no_grad():
             _, _, w = ops.lbs(v_flat.detach(), b_flat.detach(), deform_params.detach().reshape(BF, K, 3), chain_ptr, chain_ids,
                               temperature, want_weights=True)
@@ -353,5 +366,5 @@ def skinning(v_pos, bones_pred, kinematic_tree, deform_params, output_posed_bone
     aux["bones_pred"] = bones_pred
     aux["vertices_to_bones"] = _LazyWeights(weights)
     if output_posed_bones:
-        aux["posed_bones"] = posed.reshape(B, Fr, K, 2, 3)
-    return out.reshape(B, Fr, V, 3), aux
+        aux["posed_bones"] = posed4
+    return out4, aux

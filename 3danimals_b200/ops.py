@@ -292,9 +292,15 @@ def chain_tables(kinematic_tree, num_bones, device):
 
 class _LBS(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, v_pos, bones, angles, chain_ptr, chain_ids, temperature, want_weights):
+    def forward(ctx, v_pos, bones, angles, chain_ptr, chain_ids, temperature, want_weights, bf=None):
         L = _L()
         v_pos = _f32(v_pos, "v_pos"); bones = _f32(bones, "bones"); angles = _f32(angles, "angles")
+        # bf = (batch, frames): the caller's [B|1,F|1,...] tensors are flattened HERE (and the outputs / gradients un-flattened
+        # below), outside the autograd tape - four recorded view ops fewer per direction than reshaping around the node
+        ctx.shapes = (v_pos.shape, angles.shape) if bf is not None else None
+        if bf is not None:
+            v_pos = v_pos.reshape(-1, v_pos.shape[-2], 3); bones = bones.reshape(-1, bones.shape[-3], 2, 3)
+            angles = angles.reshape(-1, angles.shape[-2], 3)
         B, K = angles.shape[0], angles.shape[1]
         Bv, V = v_pos.shape[0], v_pos.shape[1]
         Bb = bones.shape[0]
@@ -314,12 +320,17 @@ class _LBS(torch.autograd.Function):
         if weights is None:
             weights = torch.empty(0, device=dev)
         ctx.mark_non_differentiable(weights)
+        if bf is not None:
+            out, posed = out.view(bf[0], bf[1], V, 3), posed.view(bf[0], bf[1], K, 2, 3)
         return out, posed, weights
 
     @staticmethod
     def backward(ctx, d_out, d_posed, _):
         L = _L()
         v_pos, bones, angles, chain_ptr, chain_ids, T_local, G = ctx.saved_tensors
+        if ctx.shapes is not None:
+            d_out = d_out.reshape(-1, d_out.shape[-2], 3) if d_out is not None else None
+            d_posed = d_posed.reshape(-1, d_posed.shape[-3], 2, 3) if d_posed is not None else None
         B, K = angles.shape[0], angles.shape[1]
         Bv, V = v_pos.shape[0], v_pos.shape[1]
         Bb = bones.shape[0]
@@ -340,12 +351,22 @@ class _LBS(torch.autograd.Function):
             gp = _f32(d_posed, "d_posed") if d_posed is not None else None
             _call("b2a_lbs_bone_transforms_bwd", (_p(bones), _p(angles), _p(chain_ptr), _p(chain_ids), _p(T_local), _p(d_G),
                                                      _p(gp), B, Bb, K, _p(d_T), _p(d_angles), st))
-        return d_v, None, d_angles, None, None, None, None
+        if ctx.shapes is not None:
+            d_v = d_v.view(ctx.shapes[0]) if d_v is not None else None
+            d_angles = d_angles.view(ctx.shapes[1]) if d_angles is not None else None
+        return d_v, None, d_angles, None, None, None, None, None
+
+
+def lbs_bf(v_pos, bones, angles, chain_ptr, chain_ids, temperature=1.0):
+    """The [batch, frames] form skinning() receives: v_pos [B|1,F|1,V,3] (both 1 or both full), bones [B|1,F|1,K,2,3],
+    angles [B,F,K,3] -> posed verts [B,F,V,3], posed bones [B,F,K,2,3]."""
+    out, posed, _ = _LBS.apply(v_pos, bones, angles, chain_ptr, chain_ids, temperature, False, (angles.shape[0], angles.shape[1]))
+    return out, posed
 
 
 def lbs(v_pos, bones, angles, chain_ptr, chain_ids, temperature=1.0, want_weights=False):
     """v_pos [Bv,V,3], bones [Bb,K,2,3], angles [B,K,3] -> posed verts [B,V,3], posed bones [B,K,2,3], weights [K,Bw,V]|None."""
-    out, posed, w = _LBS.apply(v_pos, bones, angles, chain_ptr, chain_ids, temperature, want_weights)
+    out, posed, w = _LBS.apply(v_pos, bones, angles, chain_ptr, chain_ids, temperature, want_weights, None)
     return out, posed, (w if want_weights else None)
 
 
@@ -608,7 +629,7 @@ class _AntialiasPair(torch.autograd.Function):
     one autograd node, one zero fill and the d_pos sum of the two keys."""
 
     @staticmethod
-    def forward(ctx, color_w, color_n, bg_w, bg_n, pos, keep_w, keep_n, aa_ctx, rast, tri, opp):
+    def forward(ctx, color_w, color_n, bg_w, bg_n, pos, keep_w, keep_n, aa_ctx, rast, tri, opp, nchw=False):
         color_w = _f32(color_w, "color"); color_n = _f32(color_n, "color"); pos = _f32(pos, "pos")
         bg_w = _f32(bg_w, "background") if bg_w is not None else None
         bg_n = _f32(bg_n, "background") if bg_n is not None else None
@@ -626,16 +647,22 @@ class _AntialiasPair(torch.autograd.Function):
         _call("b2a_antialias_pair_fwd", (_p(color_w), _p(bg_w), Bgw, Cw, _p(out_w), _p(color_n), _p(bg_n), Bgn, Cn, _p(out_n), B, H, W,
                                           _p(aa_ctx), aa_ctx.numel(), _stream()), tag="C%d+C%d" % (Cw, Cn))
         ctx.save_for_backward(color_w, color_n, bg_w, bg_n, pos, aa_ctx, rast, tri, opp)
-        ctx.cfg = (Bgw, Bgn, Cw, Cn, int(keep_w), int(keep_n))
-        return (out_w[..., :keep_w] if keep_w < Cw else out_w), (out_n[..., :keep_n] if keep_n < Cn else out_n)
+        ctx.cfg = (Bgw, Bgn, Cw, Cn, int(keep_w), int(keep_n), bool(nchw))
+        ow = out_w[..., :keep_w] if keep_w < Cw else out_w
+        on = out_n[..., :keep_n] if keep_n < Cn else out_n
+        if nchw:    # render.py:334 hands NCHW views of the NHWC storage to the caller: made here, outside the autograd tape
+            ow, on = ow.permute(0, 3, 1, 2), on.permute(0, 3, 1, 2)
+        return ow, on
 
     @staticmethod
     def backward(ctx, g_w, g_n):
         color_w, color_n, bg_w, bg_n, pos, aa_ctx, rast, tri, opp = ctx.saved_tensors
-        Bgw, Bgn, Cw, Cn, keep_w, keep_n = ctx.cfg
+        Bgw, Bgn, Cw, Cn, keep_w, keep_n, nchw_out = ctx.cfg
         B, H, W = color_w.shape[0], color_w.shape[1], color_w.shape[2]
         g_w = g_w if g_w.dtype == torch.float32 else g_w.float()
         g_n = g_n if g_n.dtype == torch.float32 else g_n.float()
+        if nchw_out:    # gradients arrive [B,C,H,W]-shaped: view them [B,H,W,C]-shaped (strides carry the layout)
+            g_w, g_n = g_w.permute(0, 2, 3, 1), g_n.permute(0, 2, 3, 1)
         d_color_w = torch.empty_like(color_w)
         d_color_n = torch.empty_like(color_n)
         d_pos = torch.zeros_like(pos) if ctx.needs_input_grad[4] else None
@@ -656,16 +683,17 @@ class _AntialiasPair(torch.autograd.Function):
                 _call("b2a_antialias_bwd", (_p(color), _p(bg), Bg, 1, _p(rast), _p(pos), _p(tri), _p(opp), _p(g), sb, sy, sx, sc, keep, B, V,
                                               tri.shape[0], H, W, Cc, _p(d_color), _p(d_pos), _p(aa_ctx), aa_ctx.numel(), st), tag="C%d" % Cc,
                       launches=1)
-        return d_color_w, d_color_n, None, None, d_pos, None, None, None, None, None, None
+        return d_color_w, d_color_n, None, None, d_pos, None, None, None, None, None, None, None
 
 
-def composite_antialias_pair(color_w, bg_w, keep_w, color_n, bg_n, keep_n, rast, pos, tri, opp, aa_ctx):
+def composite_antialias_pair(color_w, bg_w, keep_w, color_n, bg_n, keep_n, rast, pos, tri, opp, aa_ctx, nchw=False):
     """Fused composite + antialias of a wide key (color_w [B,H,W,16]) and a narrow key (color_n [B,H,W,3]) of one render.
-    -> ([B,H,W,keep_w], [B,H,W,keep_n]).  Requires the render's prepared context (ops.antialias_prepare)."""
+    -> ([B,H,W,keep_w], [B,H,W,keep_n]), or with nchw=True the [B,keep,H,W] views of the same storage that render_mesh returns
+    (render.py:334).  Requires the render's prepared context (ops.antialias_prepare)."""
     if not pair_supported(color_w, color_n, aa_ctx):
         raise _lib.B2AError("composite_antialias_pair: unsupported key combination (use composite_antialias per key)")
     return _AntialiasPair.apply(color_w, color_n, bg_w, bg_n, pos, int(keep_w), int(keep_n), aa_ctx, _f32(rast, "rast"), _idx32(tri, "tri"),
-                                _idx32(opp, "opp"))
+                                _idx32(opp, "opp"), bool(nchw))
 
 
 def pair_supported(color_w, color_n, aa_ctx):

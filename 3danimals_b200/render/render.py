@@ -160,7 +160,7 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
             and ops.pair_supported(buffers["dino_pred"], buffers["shaded"], aa_ctx)):
         dino_c = buffers["dino_pred"]
         fused["dino_pred"], fused["shaded"] = ops.composite_antialias_pair(dino_c, None, dino_c.shape[-1], buffers["shaded"], bg_full, 4,
-                                                                           rast, v_pos_clip, tri, opp, aa_ctx)
+                                                                           rast, v_pos_clip, tri, opp, aa_ctx, nchw=True)
 
     out_buffers = []
     for key in render_modes:
@@ -168,7 +168,7 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
             out_buffers.append(None)
             continue
         if key in fused:
-            out_buffers.append(fused[key].permute(0, 3, 1, 2))
+            out_buffers.append(fused[key])      # already the NCHW view
             continue
         color = buffers[key].float()
         bg = bg_full if key in _BG_KEYS else None
