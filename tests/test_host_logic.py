@@ -183,3 +183,14 @@ def test_fauna_bones_variant_host_logic(tag):
         assert np.allclose(bones.numpy(), g[tag + "_bones"], atol=1e-5)
         bones2 = sk._estimate_bones_torch(shape * 1.01, 8, 3, "z_minmax_y+", False, aux, True, None, 0.4)
         assert np.allclose(bones2.numpy(), g[tag + "_bones_rescaled"], atol=1e-5)
+
+
+def test_capture_helpers_refuse_cpu_tensors():
+    """CUDA-graph capture (3danimals_b200/graphs.py) is a device-only facility: CPU tensors are rejected up front."""
+    import torch
+    graphs = pkg("graphs")
+    with pytest.raises(RuntimeError):
+        graphs.CapturedStep(lambda x: x * 2, [torch.zeros(3)])
+    ops = pkg("ops")
+    assert not ops.composite_up_supported(torch.zeros(1, 4, 4, 3), None)          # no prepared context -> reference-order torch path
+    assert not ops.pair_supported(torch.zeros(1, 4, 4, 16), torch.zeros(1, 4, 4, 3), None)
