@@ -194,3 +194,42 @@ def test_coverage_and_visibility_agree_with_an_independent_fp64_evaluation():
         checked += int(m.sum())
         assert cover[m].sum() > 800
     assert checked > 2 * H * W * 0.9
+
+
+def test_rasterizer_is_invariant_to_face_order_and_vertex_rotation():
+    """Two more properties the restated fill rule must have (nothing pins it against nvdiffrast itself):
+    visibility does not depend on the order of the triangle list (away from exact depth ties), and rotating the vertex
+    order inside each triangle keeps coverage and depth and rotates the barycentrics accordingly."""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    syn = importlib.import_module("3danimals_b200.synthetic")
+    from oracle import geometry_np as gnp
+    v, t = syn.kuhn_tet_grid(16)
+    v = v * np.float32(7.0)
+    o = gnp.marching_tets(v, syn.sdf_horse(v, 0.01, 3), t, with_uvs=False)
+    verts, faces = o["verts"], o["faces"].astype(np.int32)
+    mvp, _, _ = syn.cameras(2, seed=9)
+    pos = R.xfm_points(verts[None], mvp)
+    H = W = 80
+    base = R.rasterize(pos, faces, (H, W))
+    ids = base[..., 3].astype(np.int64) - 1
+    # (1) random permutation of the triangle list
+    perm = np.random.RandomState(1).permutation(len(faces))
+    r2 = R.rasterize(pos, faces[perm], (H, W))
+    ids2 = r2[..., 3].astype(np.int64) - 1
+    back = np.where(ids2 >= 0, perm[np.clip(ids2, 0, None)], -1)
+    same = back == ids
+    assert np.array_equal(ids >= 0, ids2 >= 0)                          # identical coverage
+    assert same.mean() > 0.999                                          # identical winner except exact depth ties (id tie-break)
+    assert np.allclose(base[..., :3][same], r2[..., :3][same], atol=0)  # and then identical barycentrics / depth bits
+    # (2) rotate the vertex order of every triangle: (v0,v1,v2) -> (v1,v2,v0)
+    r3 = R.rasterize(pos, faces[:, [1, 2, 0]], (H, W))
+    assert np.array_equal(r3[..., 3], base[..., 3])
+    cov = ids >= 0
+    u, vv = base[..., 0][cov], base[..., 1][cov]
+    w = 1.0 - u - vv
+    # new weights of (new v0, new v1) = old weights of (v1, v2)
+    assert np.abs(r3[..., 0][cov] - vv).max() < 2e-5 and np.abs(r3[..., 1][cov] - w).max() < 2e-5
+    assert np.abs(r3[..., 2][cov] - base[..., 2][cov]).max() < 1e-6
