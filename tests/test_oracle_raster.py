@@ -233,3 +233,31 @@ def test_rasterizer_is_invariant_to_face_order_and_vertex_rotation():
     # new weights of (new v0, new v1) = old weights of (v1, v2)
     assert np.abs(r3[..., 0][cov] - vv).max() < 2e-5 and np.abs(r3[..., 1][cov] - w).max() < 2e-5
     assert np.abs(r3[..., 2][cov] - base[..., 2][cov]).max() < 1e-6
+
+
+def test_antialias_is_linear_in_colour_and_preserves_constants():
+    """For fixed geometry the restated antialias is a linear map of the colour image whose rows sum to one: a constant image
+    comes back unchanged and aa(a c1 + b c2) = a aa(c1) + b aa(c2)."""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    syn = importlib.import_module("3danimals_b200.synthetic")
+    from oracle import geometry_np as gnp
+    v, t = syn.kuhn_tet_grid(12)
+    v = v * np.float32(7.0)
+    o = gnp.marching_tets(v, syn.sdf_horse(v, 0.0, 0), t, with_uvs=False)
+    verts, faces = o["verts"], o["faces"].astype(np.int32)
+    mvp, _, _ = syn.cameras(2, seed=4)
+    pos = R.xfm_points(verts[None], mvp)
+    H = W = 64
+    rast = R.rasterize(pos, faces, (H, W))
+    opp = R.edge_adjacency(faces, verts.shape[0])
+    rng = np.random.RandomState(2)
+    c1, c2 = rng.rand(2, H, W, 3).astype(np.float32), rng.rand(2, H, W, 3).astype(np.float32)
+    a1, a2 = R.antialias(c1, rast, pos, faces, opp), R.antialias(c2, rast, pos, faces, opp)
+    assert np.abs(a1 - c1).max() > 0.02                                   # the scene does blend
+    const = np.full((2, H, W, 3), 0.37, np.float32)
+    assert np.abs(R.antialias(const, rast, pos, faces, opp) - const).max() < 1e-6
+    mix = R.antialias((0.25 * c1 + 1.5 * c2).astype(np.float32), rast, pos, faces, opp)
+    assert np.abs(mix - (0.25 * a1 + 1.5 * a2)).max() < 1e-5
