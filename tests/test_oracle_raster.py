@@ -261,3 +261,41 @@ def test_antialias_is_linear_in_colour_and_preserves_constants():
     assert np.abs(R.antialias(const, rast, pos, faces, opp) - const).max() < 1e-6
     mix = R.antialias((0.25 * c1 + 1.5 * c2).astype(np.float32), rast, pos, faces, opp)
     assert np.abs(mix - (0.25 * a1 + 1.5 * a2)).max() < 1e-5
+
+
+def test_barycentrics_are_perspective_correct_fp64():
+    """rast (u, v) = perspective-correct weights of triangle vertices 0 and 1: an fp64 evaluation from screen-space areas and
+    the clip-space w of each vertex (b_i = (l_i / w_i) / sum_j (l_j / w_j)) agrees with the restatement on every covered pixel,
+    and interpolating the clip-space z and w with them reproduces channel 2 (z/w)."""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    syn = importlib.import_module("3danimals_b200.synthetic")
+    from oracle import geometry_np as gnp
+    v, t = syn.kuhn_tet_grid(12)
+    v = v * np.float32(7.0)
+    o = gnp.marching_tets(v, syn.sdf_horse(v, 0.0, 0), t, with_uvs=False)
+    verts, faces = o["verts"], o["faces"].astype(np.int32)
+    mvp, _, _ = syn.cameras(1, seed=8, fov_deg=60.0, z_offset=4.0)          # strong perspective: w varies by ~2x over the mesh
+    pos = R.xfm_points(verts[None], mvp)
+    H = W = 128
+    rast = R.rasterize(pos, faces, (H, W))[0]
+    P = pos[0].astype(np.float64)
+    ys, xs = np.nonzero(rast[..., 3] > 0)
+    assert len(ys) > 500 and P[:, 3].max() / P[:, 3].min() > 1.3
+    f = faces[rast[ys, xs, 3].astype(np.int64) - 1]                          # [n,3]
+    c = np.stack([(xs + 0.5) / W * 2 - 1, (ys + 0.5) / H * 2 - 1], -1)       # pixel centres, row 0 is clip y = -1
+    p = P[f]                                                                 # [n,3,4]
+    ndc = p[..., :2] / p[..., 3:4]
+    d = ndc - c[:, None]
+    e = d[:, [1, 2, 0]]
+    cr = d[..., 0] * e[..., 1] - d[..., 1] * e[..., 0]                        # area opposite vertex (i+2)
+    lam = cr[:, [1, 2, 0]] / cr.sum(-1, keepdims=True)                       # screen-space weights of v0, v1, v2
+    b = lam / p[..., 3]
+    b = b / b.sum(-1, keepdims=True)                                         # perspective-correct weights
+    ok = np.abs(cr).min(-1) > 1e-7 * np.abs(cr.sum(-1))                      # away from edges
+    assert ok.mean() > 0.95
+    assert np.abs(rast[ys, xs, 0] - b[:, 0])[ok].max() < 2e-4 and np.abs(rast[ys, xs, 1] - b[:, 1])[ok].max() < 2e-4
+    zw = (b * p[..., 2]).sum(-1) / (b * p[..., 3]).sum(-1)
+    assert np.abs(rast[ys, xs, 2] - zw)[ok].max() < 2e-5
