@@ -3,7 +3,7 @@
     import importlib; importlib.import_module("3danimals_b200.overlay").install()
 
 After `install()`, `import model.geometry.dmtet`, `model.geometry.skinning`, `model.render.mesh`,
-`model.render.render`, `model.render.light` and `nvdiffrast(.torch)` resolve to the B200-native modules, so the reference's
+`model.render.render`, `model.render.light`, `model.render.obj` and `nvdiffrast(.torch)` resolve to the B200-native modules, so the reference's
 `model/models`, `model/predictors`, Trainer and visualization scripts run unmodified on top of libb2a.so.
 Everything else under `model.*` (networks, light, material, util, ...) keeps loading from the reference tree.
 """
@@ -20,6 +20,7 @@ ALIASES = {
     "model.render.mesh": _PKG + ".render.mesh",
     "model.render.render": _PKG + ".render.render",
     "model.render.light": _PKG + ".render.light",
+    "model.render.obj": _PKG + ".render.obj",
     "nvdiffrast": _PKG + ".nvdiffrast_shim",
     "nvdiffrast.torch": _PKG + ".nvdiffrast_shim.torch",
 }

@@ -254,6 +254,23 @@ int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, const int
                     void* workspace, size_t workspace_bytes, int workspace_is_zero, float* d_v_pos, float* d_v_nrm,
                     float* d_prior_pos, float* d_clip, float* d_w2c, float* d_campos, b2a_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Mesh export: the text of a Wavefront OBJ file.  Replaces the per-line loops of write_obj
+ * (model/render/obj.py:128-177); byte-identical output, including the reference's number format: every coordinate is
+ * '{}'.format(np.float32) = Python's repr of the value widened to double, the texcoord v is flipped in float32 first
+ * (obj.py:148).  HOST pointers (the only entry points of this library that take them; no CUDA work, no stream).
+ * Text: "mtllib <name>.mtl\ng default\n", 'v' lines, 'vt' lines (n_tex of them), 'vn' lines, "s 1 \ng pMesh1\n
+ * usemtl defaultMat\n", 'f' lines "f  a/b/c a/b/c a/b/c" with 1-based indices; the b / c columns are empty when v_tex /
+ * v_nrm is NULL (obj.py:166).  n_tex = 0 with a non-NULL v_tex is the reference's save_material=False case (:145).
+ * `out` must hold at least b2a_obj_text_bound bytes; lines are formatted by `threads` host threads (0 = all) at
+ * worst-case offsets and compacted in place; *written = size of the text.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_obj_text_bound(int64_t n_pos, int64_t n_tex, int64_t n_nrm, int64_t n_faces, int64_t name_bytes, size_t* bytes);
+int b2a_obj_format(const float* v_pos, int64_t n_pos, const float* v_tex, int64_t n_tex, const float* v_nrm,
+                   int64_t n_nrm, const int64_t* t_pos_idx, const int64_t* t_tex_idx, const int64_t* t_nrm_idx,
+                   int64_t n_faces, const char* mtl_name, int64_t name_bytes, char* out, size_t capacity,
+                   size_t* written, int threads);
+
 #ifdef __cplusplus
 }
 #endif

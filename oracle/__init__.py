@@ -15,6 +15,8 @@ Contents
   (R3), bone estimation (R4), linear blend skinning (R5).
 * ``torch_ref``         torch-CPU restatement with autograd of R3/R5/R8 and render_mesh (R6-R9) over the C ops.
 * ``pipeline_ref``      the whole hot path on host cores (parity checker and CPU baseline of bench.py).
+* ``obj_text``          line-by-line restatement of the OBJ writer (``render/obj.py:128-177``), pinned by the
+  reference's own function (``tests/golden/obj_export.npz``).
 * ``raster_ref.c``      C (OpenMP) restatement of the un-vendored nvdiffrast ops
   used by ``model/render/render.py`` (rasterize, interpolate, antialias) with
   forward and backward passes; built into ``oracle/_build/liboracle.so``.

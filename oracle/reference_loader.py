@@ -103,3 +103,28 @@ def reference_dmtet(device="cpu"):
     mt = ns.dmtet.DMTet(device=device)
     mt.device = device
     return mt
+
+
+def reference_write_obj():
+    """The reference's own `write_obj` (model/render/obj.py:128-177), loaded by path.  Its sibling modules (texture, mesh,
+    material: GPU / nvdiffrast / imageio dependent) are never touched when `mesh.material is None`, so empty stand-ins satisfy
+    the file's imports.  sys.modules is restored afterwards."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    names = ["model", "model.render", "model.render.texture", "model.render.mesh", "model.render.material", "model.render.obj"]
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        for name in names[:-1]:
+            mod = types.ModuleType(name)
+            if name in ("model", "model.render"):
+                mod.__path__ = [os.path.join(REFERENCE_ROOT, name.replace(".", "/"))]
+            sys.modules[name] = mod
+        for leaf in ("texture", "mesh", "material"):
+            setattr(sys.modules["model.render"], leaf, sys.modules["model.render." + leaf])
+        return _load("model.render.obj", "model/render/obj.py").write_obj
+    finally:
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+            else:
+                sys.modules.pop(k, None)

@@ -136,6 +136,40 @@ def light_case():
                         **{"sd:" + k: v for k, v in sd.items()})
 
 
+def obj_case():
+    """The reference's own write_obj (obj.py:128-177) on a small mesh whose coordinates cover the special values of the number
+    format, in the three layouts the callers produce: full (texcoords + normals), save_material=False (no 'vt' lines, texcoord
+    column kept) and bare (no texcoords, no normals).  material=None so no .mtl is written (obj.py:169)."""
+    import contextlib
+    import io
+    import tempfile
+    import types
+    from oracle import obj_text as oracle_obj
+    write_obj = reference_loader.reference_write_obj()
+    rng = np.random.RandomState(31)
+    sp = oracle_obj.special_float32()
+    n = (len(sp) + 2) // 3
+    v_pos = np.concatenate([sp, rng.randn(3 * n - len(sp)).astype(np.float32)]).reshape(n, 3)
+    bits = rng.randint(0, 2 ** 32, size=(200, 3), dtype=np.uint64).astype(np.uint32).view(np.float32)      # any bit pattern
+    v_pos = np.concatenate([v_pos, bits, (rng.randn(100, 3) * 3).astype(np.float32)])
+    V = len(v_pos)
+    v_nrm = rng.randn(V, 3).astype(np.float32)
+    v_nrm /= np.linalg.norm(v_nrm, axis=-1, keepdims=True)
+    v_tex = np.concatenate([rng.rand(150, 2), sp[:60].reshape(30, 2)]).astype(np.float32)
+    F = 400
+    t_pos = rng.randint(0, V, size=(F, 3)).astype(np.int64)
+    t_tex = rng.randint(0, len(v_tex), size=(F, 3)).astype(np.int64)
+    out = dict(v_pos=v_pos, v_nrm=v_nrm, v_tex=v_tex, t_pos=t_pos, t_tex=t_tex)
+    T = lambda a: None if a is None else torch.from_numpy(a)[None]
+    with tempfile.TemporaryDirectory() as d, contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        for key, (nrm, tex, save_material) in dict(full=(v_nrm, v_tex, True), nomat=(v_nrm, v_tex, False), bare=(None, None, True)).items():
+            m = types.SimpleNamespace(v_pos=T(v_pos), v_nrm=T(nrm), v_tex=T(tex), t_pos_idx=T(t_pos), t_nrm_idx=T(t_pos) if nrm is not None else None,
+                                      t_tex_idx=T(t_tex) if tex is not None else None, material=None)
+            write_obj(d, "golden_" + key, m, 0, save_material=save_material)
+            out["text_" + key] = np.frombuffer(open(os.path.join(d, "golden_" + key + ".obj"), "rb").read(), np.uint8)
+    np.savez_compressed(os.path.join(OUT, "obj_export.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     if "--only-new" not in sys.argv:
@@ -143,5 +177,6 @@ if __name__ == "__main__":
         skin_cases()
         shading_case()
         light_case()
-    fauna_bones_case()
+        fauna_bones_case()
+    obj_case()
     print(sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))

@@ -127,6 +127,8 @@ def test_overlay_lets_reference_predictor_import_our_geometry():
         light = importlib.import_module("model.render.light")
         assert light.DirectionalLight.__module__ == "3danimals_b200.render.light"
         assert hasattr(light, "EnvironmentLight") and light.EnvironmentLight.__module__ == "model.render._reference_light"
+        # model.render.obj: write_obj is the libb2a.so writer (what model/utils/misc.py:12 imports)
+        assert importlib.import_module("model.render.obj").write_obj.__module__ == "3danimals_b200.render.obj"
         lgt = light.DirectionalLight(16, 3, 32, intensity_min_max=torch.zeros(2, 2))
         assert type(lgt.mlp).__module__ == "model.networks.MLPs" and sorted(lgt.state_dict()) == [
             "intensity_min_max", "mlp.network.0.weight", "mlp.network.2.weight", "mlp.network.4.weight"]
