@@ -161,6 +161,15 @@ class Mesh:
         return self.get_m_to_n(n, n + 1)
 
 
+def load_mesh(filename, mtl_override=None):
+    """mesh.py:181-185.  `load_obj` is the reference's own reader, reachable in overlay mode (render/obj.py re-exports it)."""
+    import os
+    from . import obj
+    if os.path.splitext(filename)[1] == ".obj":
+        return obj.load_obj(filename, clear_ks=True, mtl_override=mtl_override)
+    assert False, "Invalid mesh file extension"
+
+
 def aabb(mesh):
     return torch.min(mesh.v_pos, dim=0).values, torch.max(mesh.v_pos, dim=0).values
 

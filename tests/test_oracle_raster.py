@@ -299,3 +299,37 @@ def test_barycentrics_are_perspective_correct_fp64():
     assert np.abs(rast[ys, xs, 0] - b[:, 0])[ok].max() < 2e-4 and np.abs(rast[ys, xs, 1] - b[:, 1])[ok].max() < 2e-4
     zw = (b * p[..., 2]).sum(-1) / (b * p[..., 3]).sum(-1)
     assert np.abs(rast[ys, xs, 2] - zw)[ok].max() < 2e-5
+
+
+def test_antialias_of_axis_aligned_edges_is_the_exact_area_coverage():
+    """An analytic consequence of the published antialiasing rule that nothing in the restatement hard-codes: for a straight
+    axis-aligned silhouette edge crossing between two pixel centres at fraction d from the inside pixel, the pair blend
+    (weight |d - 0.5| on the pixel the edge does NOT cut through the centre side of) turns a 0/1 mask into the exact box-filter
+    area of each pixel.  Checked on all four sides of a rectangle (two triangles: the diagonal is an interior edge and must
+    stay untouched), away from the corners, at w = 1 and at w = 3 (the rule works on post-divide positions)."""
+    H, W = 32, 40
+    x0, x1, y0, y1 = 7.3, 29.85, 5.62, 24.41                                   # rectangle in pixel units
+    cx = lambda p: p / W * 2 - 1
+    cy = lambda p: p / H * 2 - 1
+    tri = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    ax = np.clip(np.minimum(np.arange(W) + 1, x1) - np.maximum(np.arange(W), x0), 0, 1)     # exact 1-D coverages
+    ay = np.clip(np.minimum(np.arange(H) + 1, y1) - np.maximum(np.arange(H), y0), 0, 1)
+    area = ay[:, None] * ax[None, :]
+    for w in (1.0, 3.0):
+        pos = np.array([[[cx(x0), cy(y0), 0.2, 1], [cx(x1), cy(y0), 0.2, 1], [cx(x1), cy(y1), 0.2, 1], [cx(x0), cy(y1), 0.2, 1]]], np.float32) * np.float32(w)
+        rast = R.rasterize(pos, tri, (H, W))
+        mask = (rast[..., 3:4] > 0).astype(np.float32)
+        inside = mask[0, ..., 0] > 0
+        want_inside = (np.abs(np.arange(H) + 0.5 - (y0 + y1) / 2)[:, None] < (y1 - y0) / 2) & (np.abs(np.arange(W) + 0.5 - (x0 + x1) / 2)[None, :] < (x1 - x0) / 2)
+        assert np.array_equal(inside, want_inside)
+        aa = R.antialias(mask, rast, pos, tri)[0, ..., 0]
+        # away from the corners (pixels whose row AND column are both cut by an edge see two blends)
+        cut_x = (ax > 0) & (ax < 1)
+        cut_y = (ay > 0) & (ay < 1)
+        near_x = cut_x | np.roll(cut_x, 1) | np.roll(cut_x, -1)
+        near_y = cut_y | np.roll(cut_y, 1) | np.roll(cut_y, -1)
+        straight = ~(near_y[:, None] & near_x[None, :])
+        assert np.abs(aa - area)[straight].max() < 2e-5, np.abs(aa - area)[straight].max()
+        touched = np.abs(aa - mask[0, ..., 0]) > 1e-7
+        assert touched.sum() >= 2 * (18 + 22) - 8                               # one pixel of every straddling pair along the four sides
+        assert not touched[8:22, 10:27].any()                                   # the interior (incl. the diagonal) is untouched
