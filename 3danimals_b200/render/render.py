@@ -41,18 +41,63 @@ def _covered_rows(rast_s):
     return idx, torch.div(idx, h * w, rounding_mode="floor"), (B, h, w)
 
 
+# A/B switch for measurements: B2A_SPLIT_FIELD_FEAT=0 feeds the per-image feature to the field MLP as [N,C] rows (the
+# reference's concat) instead of as a per-image bias of its first hidden layer
+SPLIT_FIELD_FEAT = os.environ.get("B2A_SPLIT_FIELD_FEAT", "1") != "0"
+
+
+def _splits_feat(net, feat):
+    """True for a `CoordMLP` (MLPs.py:34-101, the reference's class or this package's twin) that takes a per-image feature."""
+    if not SPLIT_FIELD_FEAT or feat is None or type(net).__name__ != "CoordMLP":
+        return False
+    layers = getattr(getattr(net, "mlp", None), "network", None)
+    if layers is None or len(layers) == 0 or not hasattr(net, "in_layer"):
+        return False
+    first = layers[0]
+    return (isinstance(first, torch.nn.Linear) and first.bias is None and getattr(net, "extra_feat_dim", 0) > 0
+            and first.in_features == net.in_layer.out_features + net.extra_feat_dim and feat.shape[-1] == net.extra_feat_dim)
+
+
+def _coord_mlp_rows(net, x, feat, img):
+    """CoordMLP.forward (MLPs.py:72-98) on rows x [N,3] whose feature is feat[img[n]] ([B,C] per-image rows): the first
+    hidden layer `Linear(nf + C -> nf)` of `relu(cat(h, feat))` (:90-94) is evaluated as W[:, :nf] . relu(h) + a PER-IMAGE
+    bias W[:, nf:] . relu(feat_b) - the feature half of that layer (half of its FLOPs, 1 of the texture field's 8.3
+    256x256-layer equivalents) runs on B rows instead of N, and neither the [N,C] feature rows nor the [N, nf+C] concat are
+    ever materialised.  Same arithmetic up to the fp32 summation order of that one layer; autograd supplies the backward."""
+    if net.symmetrize:
+        x = torch.cat([x[..., :1].abs(), x[..., 1:]], -1)
+    h = x
+    if net.embedder is not None:
+        h = net.embedder(x)
+        if net.embed_concat_pts:
+            h = torch.cat([x, h], -1)
+    h = net.in_layer(h)
+    layers = net.mlp.network
+    w = layers[0].weight
+    nf = net.in_layer.out_features
+    bias = torch.nn.functional.linear(torch.relu(feat), w[:, nf:])             # [B, nf]
+    z = torch.addmm(bias.index_select(0, img), torch.relu(h), w[:, :nf].t())    # `in_layer_relu` is idempotent under this relu
+    out = layers[1:](z)
+    if net.min_max is not None:
+        out = out * (net.min_max[:, 1] - net.min_max[:, 0]) + net.min_max[:, 0]
+    return out
+
+
 def _sample_field(net, gb_tex_pos, feat, sparse):
     """net.sample on every pixel (sparse=None: the reference's evaluation) or on the covered rows only, scattered back
-    into a zero image.  Identical on covered pixels; uncovered pixels never reach an output (alpha = 0 in the composite,
-    render.py:258-262)."""
+    into a zero image.  Same values on covered pixels (a per-image feature enters as a per-image bias, _coord_mlp_rows);
+    uncovered pixels never reach an output (alpha = 0 in the composite, render.py:258-262)."""
     if sparse is None or getattr(net, "dense_only", False):
         return net.sample(gb_tex_pos, feat=feat)
     idx, img, (B, h, w) = sparse
     x = gb_tex_pos.reshape(-1, gb_tex_pos.shape[-1]).index_select(0, idx)
-    f = None
-    if feat is not None:
-        f = feat.index_select(0, img) if feat.shape[0] == B else feat.expand(B, -1).index_select(0, img)
-    y = net.sample(x, feat=f)
+    if _splits_feat(net, feat):
+        y = _coord_mlp_rows(net, x, feat if feat.shape[0] == B else feat.expand(B, -1), img)
+    else:
+        f = None
+        if feat is not None:
+            f = feat.index_select(0, img) if feat.shape[0] == B else feat.expand(B, -1).index_select(0, img)
+        y = net.sample(x, feat=f)
     out = y.new_zeros(B * h * w, y.shape[-1]).index_copy(0, idx, y)
     return out.view(B, h, w, y.shape[-1])
 

@@ -196,3 +196,59 @@ def test_capture_helpers_refuse_cpu_tensors():
     ops = pkg("ops")
     assert not ops.composite_up_supported(torch.zeros(1, 4, 4, 3), None)          # no prepared context -> reference-order torch path
     assert not ops.pair_supported(torch.zeros(1, 4, 4, 16), torch.zeros(1, 4, 4, 3), None)
+
+
+@pytest.mark.parametrize("which", ["twin", "reference"])
+def test_field_feature_enters_as_per_image_bias(which):
+    """Sparse field evaluation (§8f-1): the per-image feature half of CoordMLP's first hidden layer (MLPs.py:90-94) is applied as
+    a per-image bias (`render._coord_mlp_rows`).  Against the module's own every-pixel forward - this package's twin and, when
+    the tree is present, the reference's own class - outputs on covered pixels and every gradient (positions, feature,
+    parameters) agree to fp32 summation order; pure PyTorch, so the CPU run covers the arithmetic of the device path."""
+    from oracle import reference_loader
+    R = pkg("render.render")
+    if which == "reference":
+        if not reference_loader.available():
+            pytest.skip("reference tree only exists in the build container")
+        cls = reference_loader.load().mlps.CoordMLP
+    else:
+        cls = pkg("networks").CoordMLP
+    torch.manual_seed(3)
+    cases = (dict(cin=3, cout=9, num_layers=8, nf=64, activation="sigmoid", min_max=torch.tensor([[0.0, 1.0]] * 6 + [[-1.0, 1.0]] * 3), extra_feat_dim=32, symmetrize=True),
+             dict(cin=3, cout=16, num_layers=5, nf=48, activation="sigmoid", extra_feat_dim=24, in_layer_relu=True, n_harmonic_functions=0),
+             dict(cin=3, cout=4, num_layers=2, nf=32, extra_feat_dim=8, embed_concat_pts=False))
+    for kw in cases:
+        net = cls(**kw)
+        assert type(net).__name__ == "CoordMLP"
+        B, h, w, C = 3, 9, 11, kw["extra_feat_dim"]
+        gb = torch.randn(B, h, w, 3)
+        feat = torch.randn(B, C, requires_grad=True)
+        rast = torch.zeros(B, h, w, 4)
+        rast[..., 3] = (torch.rand(B, h, w) > 0.4).float()
+        rast[1, ..., 3] = 0                                     # an image without coverage
+        sparse = R._covered_rows(rast)
+        assert R._splits_feat(net, feat) and not R._splits_feat(net, None) and not R._splits_feat(torch.nn.Linear(3, 3), feat)
+        up = torch.randn(B, h, w, kw["cout"])
+        res = []
+        for split in (True, False, None):                       # per-image bias / [N,C] feature rows / the reference's dense call
+            net.zero_grad()
+            feat.grad = None
+            x = gb.clone().requires_grad_(True)
+            saved = R.SPLIT_FIELD_FEAT
+            try:
+                R.SPLIT_FIELD_FEAT = bool(split)
+                y = R._sample_field(net, x, feat, sparse if split is not None else None)
+            finally:
+                R.SPLIT_FIELD_FEAT = saved
+            y = y * (rast[..., 3:] > 0)
+            (y * up).sum().backward()
+            res.append([y.detach(), x.grad.clone(), feat.grad.clone()] + [p.grad.clone() for p in net.parameters()])
+        for other in res[1:]:
+            for a, b in zip(res[0], other):
+                assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(b.abs().max()))
+    # a feature shared by the batch ([1,C]) and a module without features keep working
+    net = cls(cin=3, cout=4, num_layers=3, nf=32, extra_feat_dim=8)
+    y1 = R._sample_field(net, gb, feat[:1, :8].detach(), sparse)
+    y2 = net.sample(gb, feat=feat[:1, :8].detach().expand(B, -1)) * (rast[..., 3:] > 0)
+    assert float((y1 - y2).detach().abs().max()) < 1e-5
+    net = cls(cin=3, cout=4, num_layers=3, nf=32)
+    assert float((R._sample_field(net, gb, None, sparse) - net.sample(gb) * (rast[..., 3:] > 0)).detach().abs().max()) < 1e-6
