@@ -359,7 +359,8 @@ B2A_API int b2a_obj_format(const float* v_pos, int64_t n_pos, const float* v_tex
 
     char* p = out;                                                        // obj.py:132-133
     memcpy(p, "mtllib ", 7); p += 7;
-    memcpy(p, mtl_name, (size_t)name_bytes); p += name_bytes;
+    if (name_bytes) memcpy(p, mtl_name, (size_t)name_bytes);
+    p += name_bytes;
     memcpy(p, ".mtl\ng default\n", 15); p += 15;
     const size_t head = (size_t)(p - out);
 
@@ -393,7 +394,11 @@ B2A_API int b2a_obj_format(const float* v_pos, int64_t n_pos, const float* v_tex
         work();
     } else {
         std::vector<std::thread> pool;
-        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+        try {
+            for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+        } catch (...) {
+            // thread creation refused (resource limits): the threads that did start and this one finish the chunks
+        }
         work();
         for (auto& th : pool) th.join();
     }
