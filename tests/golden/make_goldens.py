@@ -170,6 +170,41 @@ def obj_case():
     np.savez_compressed(os.path.join(OUT, "obj_export.npz"), **out)
 
 
+def raster_case():
+    """REGRESSION PINS of the rasterizer restatement (oracle/raster_ref.c), not reference outputs: nvdiffrast is absent, so
+    nothing upstream can be run (DESIGN.md §2 "parity unpinned").  They freeze today's ids / barycentrics / interpolation /
+    antialiasing / gradients on the analytic scenes (tests/raster_scenes.py) and one extracted mesh, so that a later edit of the
+    restatement (the yardstick of every GPU parity test) cannot drift silently."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from raster_scenes import ANALYTIC, RESOLUTIONS
+    from oracle import geometry_np as gnp
+    from oracle import raster as R
+    out = {}
+    scenes = {k: v for k, v in ANALYTIC.items()}
+    v, t = syn.kuhn_tet_grid(16)
+    v = v * np.float32(7.0)
+    o = gnp.marching_tets(v, syn.sdf_horse(v, 0.01, 3), t, with_uvs=False)
+    mvp, _, _ = syn.cameras(2, seed=9)
+    scenes["horse_mesh"] = (R.xfm_points(o["verts"][None], mvp), o["faces"].astype(np.int32))
+    for name, (pos, tri) in sorted(scenes.items()):
+        for res in (RESOLUTIONS if name != "horse_mesh" else [(64, 64)]):
+            key = "%s:%dx%d:" % (name, res[0], res[1])
+            rng = np.random.RandomState(len(key) * 7 + res[0])
+            rast = R.rasterize(pos, tri, res)
+            attr = rng.randn(pos.shape[0], pos.shape[1], 5).astype(np.float32)
+            col = R.interpolate(attr, rast, tri)
+            aa = R.antialias(col, rast, pos, tri)
+            g = rng.randn(*col.shape).astype(np.float32)
+            d_attr, d_rast = R.interpolate_bwd(attr, rast, tri, g)
+            d_col, d_pos_aa = R.antialias_bwd(col, rast, pos, tri, g)
+            d_pos_r = R.rasterize_bwd(pos, tri, rast, d_rast)
+            if name == "horse_mesh":
+                out[key + "pos"], out[key + "tri"] = pos, tri
+            for k, a in dict(rast=rast, attr=attr, col=col, aa=aa, g=g, d_attr=d_attr, d_rast=d_rast, d_col=d_col, d_pos_aa=d_pos_aa, d_pos_r=d_pos_r).items():
+                out[key + k] = a
+    np.savez_compressed(os.path.join(OUT, "raster_scenes.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     if "--only-new" not in sys.argv:
@@ -179,4 +214,5 @@ if __name__ == "__main__":
         light_case()
         fauna_bones_case()
     obj_case()
+    raster_case()
     print(sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))

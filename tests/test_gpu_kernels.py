@@ -320,20 +320,7 @@ def _scene(res=24, batch=3, image=96, seed=0):
     return verts, faces, prior, mvp, w2c, campos, clip
 
 
-ANALYTIC = {
-    "single_triangle": (np.array([[[-0.6, -0.5, 0.1, 1], [0.7, -0.4, 0.2, 1], [0.0, 0.8, 0.3, 1]]], np.float32), np.array([[0, 1, 2]], np.int32)),
-    "overlapping_quads": (np.array([[[-0.8, -0.8, 0.5, 1], [0.4, -0.8, 0.5, 1], [0.4, 0.4, 0.5, 1], [-0.8, 0.4, 0.5, 1],
-                                     [-0.3, -0.3, 0.2, 1], [0.9, -0.3, 0.2, 1], [0.9, 0.9, 0.2, 1], [-0.3, 0.9, 0.2, 1]]], np.float32),
-                          np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7]], np.int32)),
-    "shared_edge_fan": (np.array([[[0, 0, 0.3, 1], [0.9, 0, 0.3, 1], [0.6, 0.7, 0.3, 1], [-0.2, 0.9, 0.3, 1], [-0.8, 0.3, 0.3, 1],
-                                   [-0.7, -0.6, 0.3, 1], [0.2, -0.9, 0.3, 1]]], np.float32),
-                        np.array([[0, 1, 2], [0, 2, 3], [0, 3, 4], [0, 4, 5], [0, 5, 6], [0, 6, 1]], np.int32)),
-    "slivers": (np.array([[[-0.9, -0.9, 0.1, 1], [0.9, -0.89, 0.1, 1], [0.9, -0.88, 0.1, 1], [-0.5, 0.1, 0.4, 1], [-0.49, 0.9, 0.4, 1],
-                           [-0.48, 0.1, 0.4, 1]]], np.float32), np.array([[0, 1, 2], [3, 4, 5]], np.int32)),
-    "behind_camera": (np.array([[[-0.5, -0.5, 0.2, 1.0], [0.5, -0.5, 0.2, 1.0], [0.0, 0.5, -0.8, -0.5], [0.3, 0.3, 1.5, 1.0],
-                                 [0.8, 0.3, 0.5, 1.0], [0.5, 0.9, 0.5, 1.0]]], np.float32), np.array([[0, 1, 2], [3, 4, 5]], np.int32)),
-    "perspective_w": (np.array([[[-1.2, -1.0, 0.4, 2.0], [1.5, -0.8, 1.0, 3.0], [0.1, 0.9, 0.2, 1.0]]], np.float32), np.array([[0, 1, 2]], np.int32)),
-}
+from raster_scenes import ANALYTIC  # noqa: E402
 
 
 @pytest.mark.parametrize("name", sorted(ANALYTIC))

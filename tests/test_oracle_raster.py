@@ -333,3 +333,34 @@ def test_antialias_of_axis_aligned_edges_is_the_exact_area_coverage():
         touched = np.abs(aa - mask[0, ..., 0]) > 1e-7
         assert touched.sum() >= 2 * (18 + 22) - 8                               # one pixel of every straddling pair along the four sides
         assert not touched[8:22, 10:27].any()                                   # the interior (incl. the diagonal) is untouched
+
+
+def test_restatement_regression_pins():
+    """tests/golden/raster_scenes.npz freezes the restatement's outputs (ids, barycentrics, interpolation, antialiasing, all
+    gradients) on the analytic scenes and one extracted mesh - regression pins of the yardstick, NOT reference outputs (DESIGN.md
+    §2).  Forward results are bit-identical (the C file is built with -ffp-contract=off); gradients accumulate in thread order
+    under OpenMP, hence a 1e-6 band."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from conftest import golden
+    from raster_scenes import ANALYTIC, RESOLUTIONS
+    g = golden("raster_scenes.npz")
+    cases = [(name, res, pos, tri) for name, (pos, tri) in sorted(ANALYTIC.items()) for res in RESOLUTIONS]
+    cases.append(("horse_mesh", (64, 64), g["horse_mesh:64x64:pos"], g["horse_mesh:64x64:tri"]))
+    covered = 0
+    for name, res, pos, tri in cases:
+        k = "%s:%dx%d:" % (name, res[0], res[1])
+        rast = R.rasterize(pos, tri, res)
+        assert np.array_equal(rast, g[k + "rast"]), k
+        covered += int((rast[..., 3] > 0).sum())
+        col = R.interpolate(g[k + "attr"], rast, tri)
+        assert np.array_equal(col, g[k + "col"]), k
+        assert np.array_equal(R.antialias(col, rast, pos, tri), g[k + "aa"]), k
+        d_attr, d_rast = R.interpolate_bwd(g[k + "attr"], rast, tri, g[k + "g"])
+        d_col, d_pos_aa = R.antialias_bwd(col, rast, pos, tri, g[k + "g"])
+        d_pos_r = R.rasterize_bwd(pos, tri, rast, g[k + "d_rast"])
+        for got, key in ((d_attr, "d_attr"), (d_rast, "d_rast"), (d_col, "d_col"), (d_pos_aa, "d_pos_aa"), (d_pos_r, "d_pos_r")):
+            want = g[k + key]
+            assert np.abs(got - want).max() <= 1e-6 * max(1.0, np.abs(want).max()), k + key
+    assert covered > 4000
