@@ -32,3 +32,14 @@ def test_reference_arm_line():
 def test_reference_arm_other_ranks_exit_quietly():
     res = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+def test_our_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: without a CUDA device the product arm fails loudly instead of timing something else."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu"],
+                         capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert res.returncode != 0 and "no CPU fallback" in res.stderr and res.stdout.strip() == ""
