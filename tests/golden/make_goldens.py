@@ -170,6 +170,62 @@ def obj_case():
     np.savez_compressed(os.path.join(OUT, "obj_export.npz"), **out)
 
 
+def geometry_module_case():
+    """The torch side of R1 (DMTetGeometry, dmtet.py:161-281): the reference class itself on CPU - its CUDA-only grid load is
+    replaced by an in-memory Kuhn grid - with a seeded SDF MLP: get_sdf for every init_sdf mode (+ symmetrize), the BCE edge
+    regulariser on the unique sorted edge list, the eikonal sample gradients and both regulariser values under a fixed RNG seed."""
+    ref = reference_loader.load()
+    D = ref.dmtet
+    v, t = syn.kuhn_tet_grid(6)
+    out = dict(verts=v, tets=t.astype(np.int64))
+    orig_load, orig_dmtet = D.DMTetGeometry.load_tets, D.DMTet
+
+    def load_tets(self, grid_res=None, scale=None):
+        self.verts = torch.from_numpy(v) * self.grid_scale
+        self.indices = torch.from_numpy(t.astype(np.int64))
+        e = self.indices[:, torch.tensor([0, 1, 0, 2, 0, 3, 1, 2, 1, 3, 2, 3])].reshape(-1, 2)      # generate_edges (:283-288) on CPU
+        self.all_edges = torch.unique(torch.sort(e, dim=1)[0], dim=0)
+
+    D.DMTetGeometry.load_tets, D.DMTet = load_tets, (lambda device=None: orig_dmtet(device="cpu"))
+    try:
+        torch.manual_seed(41)
+        geo = D.DMTetGeometry(6, 7.0, num_layers=5, hidden_size=32, embedder_freq=8, embed_concat_pts=True, init_sdf="ellipsoid",
+                              jitter_grid=0.05, symmetrize=True)
+    finally:
+        D.DMTetGeometry.load_tets, D.DMTet = orig_load, orig_dmtet
+    with torch.no_grad():
+        for p_ in geo.mlp.parameters():
+            p_.mul_(3.0)                                    # away from the near-zero default init
+    for k, w in geo.mlp.state_dict().items():
+        out["sd:" + k] = w.numpy()
+    out["all_edges"] = geo.all_edges.numpy()
+    pts = (torch.rand(300, 3) - 0.5) * 7.0
+    out["pts"] = pts.numpy()
+    for mode in ("ellipsoid", "sphere", 0.25, None):
+        geo.init_sdf = mode
+        out["sdf_%s" % mode] = geo.get_sdf(pts).detach().numpy()
+        out["sdf_grid_%s" % mode] = geo.get_sdf().detach().numpy()
+    geo.init_sdf = "ellipsoid"
+    geo.symmetrize = False
+    out["sdf_nosym"] = geo.get_sdf(pts).detach().numpy()
+    geo.symmetrize = True
+    geo.current_sdf = geo.get_sdf()
+    out["bce"] = D.sdf_bce_reg_loss(geo.current_sdf, geo.all_edges).detach().numpy()
+    geo.mesh_verts = (torch.rand(6000, 3) - 0.5) * 2.0
+    out["mesh_verts"] = geo.mesh_verts.numpy()
+    torch.manual_seed(43)
+    out["eikonal_grad"] = geo.get_sdf_gradient().detach().numpy()
+    torch.manual_seed(43)
+    reg = geo.get_sdf_reg_loss()
+    out["reg_bce"], out["reg_grad"] = reg["sdf_bce_reg_loss"].detach().numpy(), reg["sdf_gradient_reg_loss"].detach().numpy()
+    (reg["sdf_bce_reg_loss"] + reg["sdf_gradient_reg_loss"]).backward()         # double backward through the eikonal term
+    for k, p_ in geo.mlp.named_parameters():
+        out["grad:" + k] = p_.grad.numpy()
+    lo, hi = geo.getAABB()
+    out["aabb"] = torch.stack([lo, hi]).numpy()
+    np.savez_compressed(os.path.join(OUT, "dmtet_geometry.npz"), **out)
+
+
 def raster_case():
     """REGRESSION PINS of the rasterizer restatement (oracle/raster_ref.c), not reference outputs: nvdiffrast is absent, so
     nothing upstream can be run (DESIGN.md §2 "parity unpinned").  They freeze today's ids / barycentrics / interpolation /
@@ -215,4 +271,5 @@ if __name__ == "__main__":
         fauna_bones_case()
     obj_case()
     raster_case()
+    geometry_module_case()
     print(sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))

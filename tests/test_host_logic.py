@@ -252,3 +252,61 @@ def test_field_feature_enters_as_per_image_bias(which):
     assert float((y1 - y2).detach().abs().max()) < 1e-5
     net = cls(cin=3, cout=4, num_layers=3, nf=32)
     assert float((R._sample_field(net, gb, None, sparse) - net.sample(gb) * (rast[..., 3:] > 0)).detach().abs().max()) < 1e-6
+
+
+def test_dmtet_geometry_torch_side_matches_reference_golden():
+    """R1's PyTorch half (DMTetGeometry: get_sdf for every init mode, the BCE edge regulariser, the eikonal sample gradients,
+    both regulariser values and their parameter gradients incl. the double backward, getAABB) against the reference class's
+    own outputs (tests/golden/dmtet_geometry.npz).  The grid load / extraction (CUDA) is bypassed: only device-agnostic code runs."""
+    g = golden("dmtet_geometry.npz")
+    D = pkg("geometry.dmtet")
+    orig = D.DMTetGeometry.load_tets
+
+    def load_tets(self, grid_res=None, scale=None):
+        self.verts = torch.from_numpy(g["verts"]) * self.grid_scale
+        self.indices = torch.from_numpy(g["tets"])
+        self.grid, self._all_edges = None, torch.from_numpy(g["all_edges"])
+
+    D.DMTetGeometry.load_tets = load_tets
+    try:
+        geo = D.DMTetGeometry(6, 7.0, num_layers=5, hidden_size=32, embedder_freq=8, embed_concat_pts=True, init_sdf="ellipsoid",
+                              jitter_grid=0.05, symmetrize=True)
+    finally:
+        D.DMTetGeometry.load_tets = orig
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd:")}
+    assert set(sd) == set(geo.mlp.state_dict())                       # checkpoint-compatible parameter names
+    geo.mlp.load_state_dict(sd)
+    pts = torch.from_numpy(g["pts"])
+    for mode in ("ellipsoid", "sphere", 0.25, None):
+        geo.init_sdf = mode
+        assert np.allclose(geo.get_sdf(pts).detach().numpy(), g["sdf_%s" % mode], atol=2e-6)
+        assert np.allclose(geo.get_sdf().detach().numpy(), g["sdf_grid_%s" % mode], atol=2e-6)
+    geo.init_sdf = "bogus"
+    with pytest.raises(NotImplementedError):
+        geo.get_sdf(pts)
+    geo.init_sdf = "ellipsoid"
+    geo.symmetrize = False
+    assert np.allclose(geo.get_sdf(pts).detach().numpy(), g["sdf_nosym"], atol=2e-6)
+    geo.symmetrize = True
+    geo.current_sdf = geo.get_sdf()
+    assert np.allclose(D.sdf_bce_reg_loss(geo.current_sdf, geo.all_edges).detach().numpy(), g["bce"], rtol=1e-5)
+    geo.mesh_verts = torch.from_numpy(g["mesh_verts"])
+    torch.manual_seed(43)
+    grad = geo.get_sdf_gradient()
+    assert grad.shape == (10000, 3) and np.allclose(grad.detach().numpy(), g["eikonal_grad"], atol=5e-5)
+    torch.manual_seed(43)
+    reg = geo.get_sdf_reg_loss()
+    assert np.allclose(reg["sdf_bce_reg_loss"].detach().numpy(), g["reg_bce"], rtol=1e-5)
+    assert np.allclose(reg["sdf_gradient_reg_loss"].detach().numpy(), g["reg_grad"], rtol=1e-4)
+    (reg["sdf_bce_reg_loss"] + reg["sdf_gradient_reg_loss"]).backward()
+    for k, p in geo.mlp.named_parameters():
+        want = g["grad:" + k]
+        assert np.abs(p.grad.numpy() - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), k
+    with torch.no_grad():                                              # validation mode: zeros instead of an autograd error (:277-278)
+        assert float(geo.get_sdf_gradient().abs().max()) == 0.0
+    lo, hi = geo.getAABB()
+    assert np.array_equal(torch.stack([lo, hi]).numpy(), g["aabb"])
+    # the per-grid UV atlas of map_uv (dmtet.py:69-84), built once: 4 N^2 rows, N = ceil(sqrt(T))
+    m = golden("mt_ellipsoid_12.npz")
+    uv = D.DMTet(device="cpu").uv_table(6 * 12 ** 3, torch.device("cpu")).numpy()
+    assert tuple(uv.shape) == tuple(m["uvs_shape"]) and np.allclose(uv[:64], m["uvs_head"], atol=1e-7)
