@@ -226,7 +226,7 @@ def _tangents(imesh):
     """Reference mesh.py:310-350 (MikkTSpace-style), evaluated only when a caller actually reads `v_tng`."""
     B = imesh.v_pos.shape[0]
     pos = [imesh.v_pos[:, imesh.t_pos_idx[0, :, i]] for i in range(3)]
-    uv = imesh._v_tex[:1]
+    uv = imesh._v_tex            # [B,Nuv,2] per-image texcoords, or the shared [1,Nuv,2] atlas (broadcasts below)
     tex = [uv[:, imesh.t_tex_idx[0, :, i]] for i in range(3)]
     uve1, uve2 = tex[1] - tex[0], tex[2] - tex[0]
     pe1, pe2 = pos[1] - pos[0], pos[2] - pos[0]

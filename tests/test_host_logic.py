@@ -310,3 +310,50 @@ def test_dmtet_geometry_torch_side_matches_reference_golden():
     m = golden("mt_ellipsoid_12.npz")
     uv = D.DMTet(device="cpu").uv_table(6 * 12 ** 3, torch.device("cpu")).numpy()
     assert tuple(uv.shape) == tuple(m["uvs_shape"]) and np.allclose(uv[:64], m["uvs_head"], atol=1e-7)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference tree only exists in the build container")
+def test_mesh_utilities_match_reference_side_by_side():
+    """The device-agnostic helpers of model/render/mesh.py run from the reference's own file next to this package's on the same
+    CPU tensors: aabb, compute_edges (+inverse), unit_size, center_by_reference, compute_tangents (mesh.py:190-350).
+    compute_edge_to_face_mapping hard-codes .cuda() upstream (:237-239), so its table is checked against its definition."""
+    from oracle import reference_loader
+    ref = reference_loader.load().mesh
+    ours = pkg("render.mesh")
+    rng = np.random.RandomState(12)
+    B, V, F, Vt = 3, 40, 70, 55
+    v_pos = torch.from_numpy(rng.randn(B, V, 3).astype(np.float32))
+    v_nrm = torch.nn.functional.normalize(torch.from_numpy(rng.randn(B, V, 3).astype(np.float32)), dim=-1)
+    v_tex = torch.from_numpy(rng.rand(B, Vt, 2).astype(np.float32))
+    t_pos = torch.from_numpy(np.stack([rng.permutation(V)[:3] for _ in range(F)]).astype(np.int64))[None]
+    t_pos[0, :V // 3 + 1] = torch.arange(3 * (V // 3 + 1)).remainder(V).view(-1, 3)      # every vertex is used
+    t_tex = torch.from_numpy(rng.randint(0, Vt, (1, F, 3)).astype(np.int64))
+    mk = lambda mod: mod.Mesh(v_pos.clone(), t_pos, v_nrm=v_nrm.clone(), t_nrm_idx=t_pos, v_tex=v_tex.clone(), t_tex_idx=t_tex)
+    a, b = mk(ours), mk(ref)
+    for x, y in zip(ours.aabb(a), ref.aabb(b)):
+        assert torch.equal(x, y)
+    assert torch.equal(ours.compute_edges(t_pos), ref.compute_edges(t_pos))
+    for x, y in zip(ours.compute_edges(t_pos, return_inverse=True), ref.compute_edges(t_pos, return_inverse=True)):
+        assert torch.equal(x, y)
+    assert torch.equal(ours.unit_size(a).v_pos, ref.unit_size(b).v_pos)
+    box = (torch.tensor([-1.0, -2.0, -0.5]), torch.tensor([2.0, 1.0, 0.5]))
+    assert torch.equal(ours.center_by_reference(a, box, 1.7).v_pos, ref.center_by_reference(b, box, 1.7).v_pos)
+    ta, tb = ours.compute_tangents(a), ref.compute_tangents(b)
+    assert torch.allclose(ta.v_tng, tb.v_tng, atol=1e-6) and torch.equal(ta.t_tng_idx, tb.t_tng_idx)
+    assert torch.allclose(a.v_tng, tb.v_tng, atol=1e-6)                 # and the lazily materialised attribute is the same thing
+    # edge -> (triangle seeing it ascending, triangle seeing it descending); last writer wins exactly as upstream's indexing
+    table = ours.compute_edge_to_face_mapping(t_pos)
+    edges = ours.compute_edges(t_pos)
+    want = np.zeros((edges.shape[0], 2), np.int64)
+    lut = {tuple(e): i for i, e in enumerate(edges.tolist())}
+    for f, tri in enumerate(t_pos[0].tolist()):
+        for k in range(3):
+            p, q = tri[k], tri[(k + 1) % 3]
+            want[lut[(min(p, q), max(p, q))], int(p > q)] = f
+    multi = np.zeros_like(want)
+    for f, tri in enumerate(t_pos[0].tolist()):
+        for k in range(3):
+            p, q = tri[k], tri[(k + 1) % 3]
+            multi[lut[(min(p, q), max(p, q))], int(p > q)] += 1
+    once = multi <= 1                                                    # slots written by several triangles are order-dependent upstream too
+    assert np.array_equal(table.numpy()[once], want[once]) and once.mean() > 0.9
