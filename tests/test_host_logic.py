@@ -357,3 +357,49 @@ def test_mesh_utilities_match_reference_side_by_side():
             multi[lut[(min(p, q), max(p, q))], int(p > q)] += 1
     once = multi <= 1                                                    # slots written by several triangles are order-dependent upstream too
     assert np.array_equal(table.numpy()[once], want[once]) and once.mean() > 0.9
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference tree only exists in the build container")
+def test_skinning_helpers_match_reference_side_by_side():
+    """The host helpers of model/geometry/skinning.py next to the reference's own functions on the same inputs: kinematic-chain
+    builders (:25-46), children_to_parents (:273-282), _joints_to_bones (:8-13), Euler conventions and argument errors (:285-340)."""
+    import copy
+    import itertools
+    from oracle import reference_loader
+    ref = reference_loader.load().skinning
+    ours = pkg("geometry.skinning")
+    for n, start in ((8, 0), (7, 3), (2, 0), (1, 5)):
+        assert ours.build_kinematic_chain(n, start) == ref.build_kinematic_chain(n, start)
+    for n_body, n_leg, attach in ((8, 3, True), (8, 3, False), (4, 2, True), (6, 1, True)):
+        half = n_body // 2
+        chains = []
+        for mod in (ours, ref):
+            kc = mod.build_kinematic_chain(half, half)[1] + mod.build_kinematic_chain(half, 0)[1]
+            legs = []
+            for i in range(4):
+                b2j, leg, dep = mod.build_kinematic_chain(n_leg, n_body + i * n_leg)
+                kc = mod.update_body_kinematic_chain(copy.deepcopy(kc), leg, i % n_body, dep, attach_legs_to_body=attach)
+                legs.append((b2j, leg, dep))
+            chains.append((kc, legs, mod.children_to_parents(kc)))
+        assert chains[0] == chains[1]
+    joints = torch.arange(2 * 2 * 9 * 3, dtype=torch.float32).view(2, 2, 9, 3)
+    idx = [(0, 1), (1, 2), (4, 3), (8, 0)]
+    assert torch.equal(ours._joints_to_bones(joints, idx), ref._joints_to_bones(joints, idx))
+    ang = torch.from_numpy(np.random.RandomState(4).uniform(-3, 3, (5, 2, 3)).astype(np.float32))
+    for conv in ("".join(p) for p in itertools.product("XYZ", repeat=3)):
+        try:
+            want = ref.euler_angles_to_matrix(ang, conv)
+        except ValueError as e:
+            with pytest.raises(ValueError) as got:
+                ours.euler_angles_to_matrix(ang, conv)
+            assert str(got.value) == str(e)
+            continue
+        assert torch.allclose(ours.euler_angles_to_matrix(ang, conv), want, atol=1e-6), conv
+    for bad_angles, conv in ((ang[..., :2], "XYZ"), (ang, "XY"), (ang, "XYW")):
+        with pytest.raises(ValueError) as e1:
+            ref.euler_angles_to_matrix(bad_angles, conv)
+        with pytest.raises(ValueError) as e2:
+            ours.euler_angles_to_matrix(bad_angles, conv)
+        assert str(e1.value) == str(e2.value)
+    for axis in "XYZ":
+        assert torch.allclose(ours._axis_angle_rotation(axis, ang[..., 0]), ref._axis_angle_rotation(axis, ang[..., 0]), atol=1e-7)
