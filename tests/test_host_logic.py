@@ -403,3 +403,32 @@ def test_skinning_helpers_match_reference_side_by_side():
         assert str(e1.value) == str(e2.value)
     for axis in "XYZ":
         assert torch.allclose(ours._axis_angle_rotation(axis, ang[..., 0]), ref._axis_angle_rotation(axis, ang[..., 0]), atol=1e-7)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference tree only exists in the build container")
+def test_network_twins_match_reference_classes():
+    """The standalone twins in networks.py (used by bench.py --mlps and the tests when the reference tree is absent) are the
+    reference's modules: same state-dict names and shapes, and with the same weights the same outputs (MLPs.py:9-101,
+    HarmonicEmbedding.py) - so an M1b number measured on the twins is a number for the reference's field networks."""
+    from oracle import reference_loader
+    ref = reference_loader.load().mlps
+    ours = pkg("networks")
+    torch.manual_seed(9)
+    x = torch.randn(4, 7, 3)
+    mm = torch.tensor([[0.0, 1.0], [-1.0, 1.0], [0.2, 0.4]])
+    cases = [("MLP", dict(cin=16, cout=4, num_layers=3, nf=32, activation="sigmoid"), torch.randn(5, 16), None),
+             ("MLP", dict(cin=16, cout=4, num_layers=1), torch.randn(5, 16), None),
+             ("CoordMLP", dict(cin=3, cout=3, num_layers=5, nf=32, activation="sigmoid", min_max=mm, n_harmonic_functions=6, embedder_scalar=0.8,
+                               extra_feat_dim=8, symmetrize=True), x, torch.randn(4, 8)),
+             ("CoordMLP", dict(cin=3, cout=1, num_layers=5, nf=32, n_harmonic_functions=8, embedder_scalar=0.8, embed_concat_pts=False), x, None),
+             ("CoordMLP", dict(cin=3, cout=2, num_layers=2, nf=16, n_harmonic_functions=0, in_layer_relu=True, activation="tanh"), x, None)]
+    for name, kw, inp, feat in cases:
+        a, b = getattr(ours, name)(**kw), getattr(ref, name)(**kw)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb) and all(sa[k].shape == sb[k].shape for k in sa), name
+        a.load_state_dict(sb)
+        ya = a(inp) if feat is None else a(inp, feat=feat)
+        yb = b(inp) if feat is None else b(inp, feat=feat)
+        assert torch.allclose(ya, yb, atol=1e-6), (name, kw)
+    with pytest.raises(NotImplementedError):
+        ours.CoordMLP_Mod(3, 1, 5)
