@@ -432,3 +432,18 @@ def test_network_twins_match_reference_classes():
         assert torch.allclose(ya, yb, atol=1e-6), (name, kw)
     with pytest.raises(NotImplementedError):
         ours.CoordMLP_Mod(3, 1, 5)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference tree only exists in the build container")
+def test_synthetic_projection_is_the_references():
+    """The synthetic cameras use the reference's projection (render/util.py:189-194, negated y row: image row 0 is clip y = -1)
+    and its safe_normalize / dot helpers agree with this package's mesh helpers."""
+    from oracle import reference_loader
+    ru = reference_loader.load().rutil
+    syn = pkg("synthetic")
+    for fov, asp, n, f in ((25 / 180 * np.pi, 1.0, 0.1, 1000.0), (0.7854, 1.5, 0.5, 50.0)):
+        assert np.allclose(syn.perspective(fov, asp, n, f), ru.perspective(fov, asp, n, f).numpy(), rtol=1e-7, atol=0)
+    m = pkg("render.mesh")
+    x = torch.randn(5, 3)
+    x[0] = 0
+    assert torch.equal(m._safe_normalize(x), ru.safe_normalize(x)) and torch.equal(m._dot(x, x.flip(0)), ru.dot(x, x.flip(0)))
