@@ -333,3 +333,36 @@ def test_captured_render_and_finetune_match_eager(cuda):
     loss_e2, g_e2 = it(t2)
     loss_c2, g_c2 = step(t2)
     assert torch.allclose(loss_c2, loss_e2, rtol=1e-6) and torch.allclose(g_c2, g_e2, rtol=1e-5, atol=1e-9)
+
+
+def test_dmtet_geometry_getmesh_end_to_end(cuda, tmp_path):
+    """R1 through the drop-in class itself (reference dmtet.py:175-310): load_tets on a grid file in the reference's npz schema ->
+    get_sdf (CoordMLP + ellipsoid init, symmetrised) -> extraction -> make_mesh.  The mesh is the oracle's extraction of the very
+    SDF values the module produced; both regularisers run and gradients reach the SDF network through the extraction, the
+    normals and the eikonal double backward."""
+    import math
+    from oracle import geometry_np as gnp
+    D = pkg("geometry.dmtet")
+    torch.manual_seed(0)
+    geo = D.DMTetGeometry(16, 7.0, num_layers=5, hidden_size=32, embedder_freq=8, embed_concat_pts=True, init_sdf="ellipsoid",
+                          jitter_grid=0.0, symmetrize=True, tets_root=str(tmp_path)).to(cuda)
+    assert geo.verts.is_cuda and geo.indices.dtype == torch.int64 and tuple(geo.indices.shape) == (6 * 16 ** 3, 4)
+    mesh = geo.getMesh(material=None, jitter_grid=False)
+    sdf = geo.current_sdf.detach().cpu().numpy().reshape(-1)
+    o = gnp.marching_tets(geo.verts.cpu().numpy(), sdf, geo.indices.cpu().numpy(), with_uvs=False)
+    assert o["faces"].shape[0] > 100
+    assert np.array_equal(mesh.t_pos_idx[0].cpu().numpy(), o["faces"])
+    assert np.array_equal(mesh.t_tex_idx[0].cpu().numpy(), o["uv_idx"])
+    assert rel_err(mesh.v_pos[0].detach().cpu().numpy(), o["verts"]) < 1e-6
+    N = math.ceil(math.sqrt(geo.indices.shape[0]))
+    assert tuple(mesh.v_pos.shape) == (1, o["verts"].shape[0], 3) and tuple(mesh.v_tex.shape) == (1, 4 * N * N, 2)
+    assert geo.mesh_verts.shape == mesh.v_pos.shape[1:]
+    reg = geo.get_sdf_reg_loss()
+    loss = mesh.v_pos.square().sum() + mesh.v_nrm[..., 2].sum() + reg["sdf_bce_reg_loss"] + reg["sdf_gradient_reg_loss"]
+    loss.backward()
+    grads = [p.grad for p in geo.mlp.parameters()]
+    assert all(g is not None and bool(torch.isfinite(g).all()) for g in grads) and any(float(g.abs().max()) > 0 for g in grads)
+    lo, hi = geo.getAABB()
+    assert torch.allclose(lo, torch.full((3,), -3.5, device=cuda)) and torch.allclose(hi, torch.full((3,), 3.5, device=cuda))
+    geo.jitter_grid = 0.05                      # one scalar shift of the whole grid per call (dmtet.py:302-304)
+    assert geo.getMesh(jitter_grid=True).v_pos.shape[1] > 100
