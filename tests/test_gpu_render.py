@@ -366,3 +366,100 @@ def test_dmtet_geometry_getmesh_end_to_end(cuda, tmp_path):
     assert torch.allclose(lo, torch.full((3,), -3.5, device=cuda)) and torch.allclose(hi, torch.full((3,), 3.5, device=cuda))
     geo.jitter_grid = 0.05                      # one scalar shift of the whole grid per call (dmtet.py:302-304)
     assert geo.getMesh(jitter_grid=True).v_pos.shape[1] > 100
+
+
+def _extracted(cuda, res=12):
+    """A DMTet extraction through the reference call signature `DMTet()(pos, sdf, tets) -> (verts, faces, uvs, uv_idx)`."""
+    syn = pkg("synthetic")
+    v, t = syn.kuhn_tet_grid(res)
+    v = v * np.float32(7.0)
+    sdf = syn.sdf_horse(v, 0.0, 0)
+    verts, faces, uvs, uv_idx = pkg("geometry.dmtet").DMTet()(dev(v, cuda), dev(sdf, cuda)[:, None], dev(t, cuda))
+    return v, t, sdf, verts, faces, uvs, uv_idx
+
+
+def test_nvdiffrast_shim_surface(cuda):
+    """The `nvdiffrast.torch` names the unmodified reference files import (AnimalModel.py:9,236; material.py:13,116): contexts,
+    rasterize (+ the dead db buffer), DepthPeeler's first layer, interpolate, antialias - same bits as the restated ops."""
+    from oracle import raster as R
+    dr = pkg("nvdiffrast_shim.torch")
+    syn = pkg("synthetic")
+    _, _, _, verts, faces, _, _ = _extracted(cuda)
+    V = verts.shape[0]
+    vb = torch.stack([verts, verts * 0.9]).detach()
+    mvp, _, _ = syn.cameras(2, seed=3)
+    clip = R.xfm_points(vb.cpu().numpy(), mvp)
+    tri = faces.cpu().numpy().astype(np.int32)
+    H, W = 96, 80
+    ref = R.rasterize(clip, tri, (H, W))
+    assert (ref[..., 3] > 0).mean() > 0.02
+    ctx = dr.RasterizeGLContext()
+    assert isinstance(ctx, dr.RasterizeCudaContext)
+    pd, td = dev(clip, cuda), dev(tri, cuda)
+    rast, db = dr.rasterize(ctx, pd, td, (H, W))
+    assert np.array_equal(rast.cpu().numpy(), ref) and tuple(db.shape) == tuple(rast.shape) and float(db.abs().max()) == 0.0
+    with dr.DepthPeeler(ctx, pd, td, (H, W)) as peeler:
+        first, _ = peeler.rasterize_next_layer()
+        assert torch.equal(first, rast)
+        with pytest.raises(NotImplementedError):
+            peeler.rasterize_next_layer()
+    attr = np.random.RandomState(2).randn(2, V, 5).astype(np.float32)
+    out, out_da = dr.interpolate(dev(attr, cuda), rast, td)
+    assert out_da is None and np.array_equal(out.cpu().numpy(), R.interpolate(attr, ref, tri))
+    color = np.random.RandomState(3).rand(2, H, W, 4).astype(np.float32)
+    color[..., -1] = ref[..., 3] > 0
+    aa = dr.antialias(dev(color, cuda), rast, pd, td)
+    want = R.antialias(color, ref, clip, tri)
+    assert np.abs(want - color).max() > 0.05 and np.array_equal(aa.cpu().numpy(), want)
+    with pytest.raises(NotImplementedError):
+        dr.texture()
+
+
+class _LinearField(torch.nn.Module):
+    """9-channel stand-in for `material['kd_ks_normal']` with the `sample(x, feat=None)` interface (material.py:116-117)."""
+
+    def __init__(self, w):
+        super().__init__()
+        self.w = w
+
+    def sample(self, x, feat=None):
+        return torch.tanh((x[..., None, :] * self.w.t()).sum(-1))
+
+
+def test_mesh_methods_and_render_uv(cuda):
+    """Mesh bookkeeping the predictors call on device (extend / deform / get_m_to_n / first_n / get_n / clone, mesh.py:47-175) with
+    normals recomputed by the normals kernel, and render_uv (render.py:342-360, the texture bake of save_mtl) against the
+    restated rasterize + interpolate of the UV atlas."""
+    from oracle import raster as R
+    mesh_mod, render_mod = pkg("render.mesh"), pkg("render.render")
+    _, t, _, verts, faces, uvs, uv_idx = _extracted(cuda)
+    V = verts.shape[0]
+    m = mesh_mod.make_mesh(verts[None], faces[None], uvs[None], uv_idx[None], None)
+    ext = m.extend(3)
+    assert tuple(ext.v_pos.shape) == (3, V, 3) and torch.equal(ext.v_pos[2], m.v_pos[0]) and len(ext) == 3
+    delta = torch.from_numpy(np.random.RandomState(4).randn(3, V, 3).astype(np.float32) * 0.01).to(cuda)
+    d = ext.deform(delta)
+    assert torch.equal(d.v_pos, ext.v_pos + delta) and torch.equal(d.t_pos_idx, m.t_pos_idx)
+    nrm_ref = T.auto_normals(d.v_pos.detach().cpu(), faces.cpu().long())
+    assert rel_err(d.v_nrm.detach().cpu().numpy(), nrm_ref.numpy()) < 1e-3      # bookkeeping check: a stale or mis-indexed mesh is O(1) off
+    sub = d.get_m_to_n(1, 3)
+    assert len(sub) == 2 and torch.equal(sub.v_pos, d.v_pos[1:3]) and tuple(sub.v_tex.shape) == (2, uvs.shape[0], 2)
+    assert rel_err(sub.v_nrm.detach().cpu().numpy(), nrm_ref[1:3].numpy()) < 1e-3
+    assert torch.equal(d.first_n(2).v_pos, d.v_pos[:2]) and torch.equal(d.get_n(1).v_pos, d.v_pos[1:2])
+    c = d.clone()
+    assert c.v_pos is not d.v_pos and torch.equal(c.v_pos, d.v_pos) and torch.equal(c.v_nrm, d.v_nrm)
+    # render_uv on the un-batched prior mesh
+    res = (192, 192)
+    w = np.random.RandomState(5).randn(3, 9).astype(np.float32) * 0.5
+    mask, kd, ks, nrm = render_mod.render_uv(None, m, res, _LinearField(dev(w, cuda)))
+    uv = uvs.cpu().numpy()
+    uv4 = np.concatenate([uv * 2 - 1, np.zeros_like(uv[:, :1]), np.ones_like(uv[:, :1])], -1)[None].astype(np.float32)
+    rast = R.rasterize(uv4, uv_idx.cpu().numpy().astype(np.int32), res)
+    assert (rast[..., 3] > 0).sum() > 150            # ~2-pixel atlas cells: a few hundred covered texels
+    assert np.array_equal(mask.cpu().numpy(), (rast[..., 3:] > 0).astype(np.float32))
+    gb = R.interpolate(verts.detach().cpu().numpy()[None], rast, faces.cpu().numpy().astype(np.int32))
+    tex = _LinearField(torch.from_numpy(w)).sample(torch.from_numpy(gb))
+    n3 = tex[..., -3:]
+    n3 = n3 / torch.sqrt(torch.clamp((n3 * n3).sum(-1, keepdim=True), min=1e-20))
+    for got, want in ((kd, tex[..., :3]), (ks, tex[..., 3:6]), (nrm, n3)):
+        assert tuple(got.shape) == tuple(want.shape) and float((got.cpu() - want).abs().max()) < 2e-5
