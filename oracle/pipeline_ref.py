@@ -5,7 +5,6 @@ Runs the same hot path on host cores from the same SyntheticScene bytes: the res
 nvdiffrast ops (oracle/raster_ref.c).  Used by tests/ and smoke() as the parity checker and by bench.py as the
 `cpu_baseline` / `--impl reference` arm.  Never imported by the product.
 """
-import numpy as np
 import torch
 
 from . import geometry_np as gnp

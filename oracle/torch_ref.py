@@ -6,7 +6,6 @@ nvdiffrast ops (oracle/raster_ref.c) wrapped as autograd Functions.  It is the p
 product and the CPU baseline that bench.py times; it is never imported by the product.
 Each function cites the reference file:line it follows (relative to /root/reference).
 """
-import numpy as np
 import torch
 
 from . import geometry_np as gnp

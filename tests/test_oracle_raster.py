@@ -2,7 +2,6 @@
 this boundary (parity unpinned), so the restatement is held to analytic answers and to finite differences
 of its own forward passes."""
 import numpy as np
-import pytest
 
 from oracle import raster as R
 
