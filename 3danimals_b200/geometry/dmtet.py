@@ -22,6 +22,7 @@ class DMTet:
         self.device = device
         self._grid = None
         self._grid_key = None
+        self._grid_src = None
         self._uv_cache = {}
 
     def to(self, device):
@@ -30,10 +31,12 @@ class DMTet:
 
     def grid_for(self, tet_fx4, num_verts):
         """Static edge tables for a tet index tensor; cached, so `load_tets` pays the table build once per grid."""
-        key = (tet_fx4.data_ptr(), tuple(tet_fx4.shape), int(num_verts), tet_fx4._version)
-        if self._grid_key != key:
+        key = (tuple(tet_fx4.shape), int(num_verts), tet_fx4._version)
+        # the keyed tensor itself is held (compared with `is`): its address cannot be recycled for another grid while cached
+        if self._grid_src is not tet_fx4 or self._grid_key != key:
             self._grid = ops.TetGrid(tet_fx4, num_verts)
             self._grid_key = key
+            self._grid_src = tet_fx4
         return self._grid
 
     def uv_table(self, num_tets, device):
@@ -94,6 +97,7 @@ class DMTetGeometry(torch.nn.Module):
         self.jitter_grid = jitter_grid
         self.symmetrize = symmetrize
         self.tets_root = kwargs.get("tets_root", "data/tets")
+        self.synthetic_tets = bool(kwargs.get("synthetic_tets", False))
         self.load_tets(self.grid_res, self.grid_scale)
         CoordMLP, CoordMLP_Mod = _field_networks()
         embedder_scalar = 2 * np.pi / self.grid_scale * 0.9
@@ -115,7 +119,12 @@ class DMTetGeometry(torch.nn.Module):
             self.grid_scale = scale
         path = os.path.join(self.tets_root, "{}_tets.npz".format(grid_res))
         if not os.path.isfile(path):
-            # the reference downloads its grids (data/tets/download_tets.sh); offline we synthesise one in its schema
+            # The reference raises here (np.load, dmtet.py:223): a different grid would silently extract a different mesh from
+            # a reference checkpoint.  Offline benches / tests opt in to a synthetic Kuhn grid in the reference's schema
+            # (`synthetic_tets=True` or B2A_SYNTHETIC_TETS=1); it is written atomically so concurrent ranks never read a torn file.
+            if not (self.synthetic_tets or os.environ.get("B2A_SYNTHETIC_TETS", "0") == "1"):
+                raise FileNotFoundError("tet grid %s not found (run data/tets/download_tets.sh; or pass synthetic_tets=True / "
+                                        "B2A_SYNTHETIC_TETS=1 for a synthetic Kuhn grid)" % path)
             from ..synthetic import write_tet_npz
             path = write_tet_npz(grid_res, self.tets_root)
         tets = np.load(path)

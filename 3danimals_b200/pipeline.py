@@ -109,6 +109,7 @@ class HotPath(torch.nn.Module):
             self.dino_net = AnalyticField(torch.from_numpy(s.w_dino).to(dev), False)
         self.mlps = mlps
         self.sparse_fields = True
+        self.spp = 1
         self.bone_aux = None
         self.kinematic_chain = None
 
@@ -133,7 +134,7 @@ class HotPath(torch.nn.Module):
         inst._opp = prior._opp
         res = (s.image_res, s.image_res)
         feat = self.feat if self.mlps else None
-        out = render_mod.render_mesh(None, inst, self.mvp, self.w2c, self.campos, self.material, self.light, res, spp=1,
+        out = render_mod.render_mesh(None, inst, self.mvp, self.w2c, self.campos, self.material, self.light, res, spp=self.spp,
                                      num_layers=1, msaa=True, background=None, bsdf="diffuse", feat=feat,
                                      render_modes=list(render_modes), prior_mesh=prior, dino_net=self.dino_net,
                                      sparse_fields=self.sparse_fields)

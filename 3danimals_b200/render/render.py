@@ -33,11 +33,17 @@ def _as_b3(x, B, device):
     return x.expand(B, 3) if x.shape[0] == 1 and B > 1 else x
 
 
-def _covered_rows(rast_s):
-    """Flat indices (into [B*h*w]) of the pixels where a triangle is visible, image index of each, and the grid shape.
-    One device->host read (the row count) per render."""
+def _covered_rows(rast_s, rast_full=None, spp=1):
+    """Flat indices (into [B*h*w]) of the shaded pixels that can reach an output, image index of each, and the grid shape.
+    One device->host read (the row count) per render.  spp == 1: the pixels where a triangle is visible.  msaa (spp > 1,
+    render.py:170-172,217-219): the shaded value of a low-resolution pixel is up-sampled to its spp x spp block and composited
+    with the FULL-resolution alpha, so it is needed whenever ANY sub-pixel of the block is covered - also when the block's own
+    nearest sample is not (the reference then shades material.sample(gb_tex_pos = 0), and that value carries gradient)."""
     B, h, w = rast_s.shape[:3]
-    idx = torch.nonzero(rast_s[..., 3].reshape(-1) > 0).squeeze(1)
+    cov = rast_s[..., 3] > 0
+    if rast_full is not None and spp > 1:
+        cov = (rast_full[..., 3] > 0).view(B, h, spp, w, spp).any(4).any(2)
+    idx = torch.nonzero(cov.reshape(-1)).squeeze(1)
     return idx, torch.div(idx, h * w, rounding_mode="floor"), (B, h, w)
 
 
@@ -85,8 +91,9 @@ def _coord_mlp_rows(net, x, feat, img):
 
 def _sample_field(net, gb_tex_pos, feat, sparse):
     """net.sample on every pixel (sparse=None: the reference's evaluation) or on the covered rows only, scattered back
-    into a zero image.  Same values on covered pixels (a per-image feature enters as a per-image bias, _coord_mlp_rows);
-    uncovered pixels never reach an output (alpha = 0 in the composite, render.py:258-262)."""
+    into a zero image.  Same values on those rows (a per-image feature enters as a per-image bias, _coord_mlp_rows);
+    the pixels left out never reach an output (alpha = 0 at every full-resolution sub-pixel of theirs in the composite,
+    render.py:258-262)."""
     if sparse is None or getattr(net, "dense_only", False):
         return net.sample(gb_tex_pos, feat=feat)
     idx, img, (B, h, w) = sparse
@@ -151,7 +158,7 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
     # (SURVEY.md §8f-1): the reference runs both MLPs (1.6 MFLOP/pixel) on every pixel of the frame although the
     # composite discards everything where no triangle is visible - ~80 % of a 256^2 training view.
     nets = [n for n in (material, dino_net) if n is not None and not getattr(n, "dense_only", False)]
-    sparse = _covered_rows(rast_s) if (sparse_fields and nets) else None
+    sparse = _covered_rows(rast_s, rast, shade_spp) if (sparse_fields and nets) else None
     if material is not None:
         all_tex = _sample_field(material, gb_tex_pos, feat, sparse)
     else:

@@ -75,7 +75,9 @@ def write_tet_npz(res, root="data/tets"):
     os.makedirs(root, exist_ok=True)
     v, t = kuhn_tet_grid(res)
     path = os.path.join(root, "%d_tets.npz" % res)
-    np.savez(path, vertices=v, indices=t)
+    tmp = os.path.join(root, ".%d_tets.%d.tmp.npz" % (res, os.getpid()))
+    np.savez(tmp, vertices=v, indices=t)
+    os.replace(tmp, path)          # atomic: concurrent ranks see either no file or a complete one
     return path
 
 

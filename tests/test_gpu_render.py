@@ -257,13 +257,17 @@ def test_full_size_properties(cuda):
     assert float(d_sdf[~touched].abs().max()) == 0
 
 
-def test_sparse_field_evaluation_matches_dense(cuda):
+@pytest.mark.parametrize("spp", [1, 2, 4])
+def test_sparse_field_evaluation_matches_dense(cuda, spp):
     """M1b path: the texture / DINO CoordMLPs evaluated on covered pixels only give the images and the
-    parameter gradients of the reference's every-pixel evaluation."""
+    parameter gradients of the reference's every-pixel evaluation - also on the msaa path (spp 2 / 4 with msaa=True, as
+    AnimalModel.render always passes and train_ponymation_horse_stage1.yaml:29 sets), where a low-resolution pixel is needed as
+    soon as any of its full-resolution sub-pixels is covered."""
     pipe = pkg("pipeline")
     torch.manual_seed(0)
     sc = pipe.SyntheticScene(grid_res=32, batch=2, image_res=64, sdf_noise=0.0)
     hp = pipe.HotPath(sc, cuda, mlps=True)
+    hp.spp = spp
     g1, g2 = sc.upstream_grads()
     d1, d2 = dev(g1, cuda) * 1e3, dev(g2, cuda) * 1e3
     res = {}
@@ -345,8 +349,10 @@ def test_dmtet_geometry_getmesh_end_to_end(cuda, tmp_path):
     D = pkg("geometry.dmtet")
     torch.manual_seed(0)
     geo = D.DMTetGeometry(16, 7.0, num_layers=5, hidden_size=32, embedder_freq=8, embed_concat_pts=True, init_sdf="ellipsoid",
-                          jitter_grid=0.0, symmetrize=True, tets_root=str(tmp_path)).to(cuda)
+                          jitter_grid=0.0, symmetrize=True, tets_root=str(tmp_path), synthetic_tets=True).to(cuda)
     assert geo.verts.is_cuda and geo.indices.dtype == torch.int64 and tuple(geo.indices.shape) == (6 * 16 ** 3, 4)
+    with pytest.raises(FileNotFoundError):      # like the reference (np.load, dmtet.py:223): no silent substitute grid
+        D.DMTetGeometry(8, 7.0, num_layers=2, hidden_size=8, embedder_freq=2, tets_root=str(tmp_path))
     mesh = geo.getMesh(material=None, jitter_grid=False)
     sdf = geo.current_sdf.detach().cpu().numpy().reshape(-1)
     o = gnp.marching_tets(geo.verts.cpu().numpy(), sdf, geo.indices.cpu().numpy(), with_uvs=False)
@@ -368,10 +374,6 @@ def test_dmtet_geometry_getmesh_end_to_end(cuda, tmp_path):
     assert geo.getMesh(jitter_grid=True).v_pos.shape[1] > 100
 
 
-_FIRST_DEVICE_RUN = pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent: the first run on a device is the "
-                                     "round-end one (an XPASS promotes it to a plain test next round; the oracle half was exercised on the host)")
-
-
 def _extracted(cuda, res=12):
     """A DMTet extraction through the reference call signature `DMTet()(pos, sdf, tets) -> (verts, faces, uvs, uv_idx)`."""
     syn = pkg("synthetic")
@@ -382,7 +384,6 @@ def _extracted(cuda, res=12):
     return v, t, sdf, verts, faces, uvs, uv_idx
 
 
-@_FIRST_DEVICE_RUN
 def test_nvdiffrast_shim_surface(cuda):
     """The `nvdiffrast.torch` names the unmodified reference files import (AnimalModel.py:9,236; material.py:13,116): contexts,
     rasterize (+ the dead db buffer), DepthPeeler's first layer, interpolate, antialias - same bits as the restated ops."""
@@ -431,7 +432,6 @@ class _LinearField(torch.nn.Module):
         return torch.tanh((x[..., None, :] * self.w.t()).sum(-1))
 
 
-@_FIRST_DEVICE_RUN
 def test_mesh_methods_and_render_uv(cuda):
     """Mesh bookkeeping the predictors call on device (extend / deform / get_m_to_n / first_n / get_n / clone, mesh.py:47-175) with
     normals recomputed by the normals kernel, and render_uv (render.py:342-360, the texture bake of save_mtl) against the
