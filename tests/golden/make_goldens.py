@@ -226,6 +226,45 @@ def geometry_module_case():
     np.savez_compressed(os.path.join(OUT, "dmtet_geometry.npz"), **out)
 
 
+def normals_case():
+    """R3: the reference's own `auto_normals` (model/render/mesh.py:276-304) on CPU tensors.  The function hard-codes
+    device='cuda' for its fallback constant (:297-298); the file is executed unmodified and `torch.tensor` is intercepted for
+    the duration of the call so that literal lands on the CPU.  Cases: an extracted DMTet mesh (batch 2, second instance
+    perturbed), plus a mesh with a vertex no face uses and a vertex touched only by zero-area faces (fallback (0,0,1))."""
+    ref = reference_loader.load()
+    mt = reference_loader.reference_dmtet("cpu")
+    v, t = syn.kuhn_tet_grid(12)
+    v = v * np.float32(7.0)
+    verts, faces, _, _ = mt(torch.from_numpy(v), torch.from_numpy(syn.sdf_horse(v, 0.01, 0))[:, None], torch.from_numpy(t))
+    verts = verts.detach()
+    rng = np.random.RandomState(21)
+    real_tensor = torch.tensor
+
+    def cpu_tensor(*a, **k):
+        if k.get("device") == "cuda":
+            k["device"] = "cpu"
+        return real_tensor(*a, **k)
+
+    out = {}
+    deg_v = torch.tensor([[0, 0, 0], [1, 0, 0], [0, 1, 1], [2, 0, 0], [5, 5, 5], [3, 0, 0]], dtype=torch.float32)   # 4: unused; 5: only in a collinear face
+    deg_f = torch.tensor([[0, 1, 2], [1, 3, 5]], dtype=torch.long)
+    for name, vp, fc in (("mesh", torch.stack([verts, verts + torch.from_numpy(rng.randn(*verts.shape).astype(np.float32)) * 0.02]), faces),
+                         ("degenerate", deg_v[None], deg_f)):
+        vp = vp.clone().requires_grad_(True)
+        m = ref.mesh.Mesh(vp, fc[None])
+        torch.tensor = cpu_tensor
+        try:
+            nm = ref.mesh.auto_normals(m)
+        finally:
+            torch.tensor = real_tensor
+        g = torch.from_numpy(rng.randn(*nm.v_nrm.shape).astype(np.float32))
+        (nm.v_nrm * g).sum().backward()
+        assert nm.t_nrm_idx is m.t_pos_idx or torch.equal(nm.t_nrm_idx, m.t_pos_idx)
+        out.update({name + "_v_pos": vp.detach().numpy(), name + "_faces": fc.numpy().astype(np.int32), name + "_v_nrm": nm.v_nrm.detach().numpy(),
+                    name + "_g": g.numpy(), name + "_d_v_pos": vp.grad.numpy()})
+    np.savez_compressed(os.path.join(OUT, "normals.npz"), **out)
+
+
 def raster_case():
     """REGRESSION PINS of the rasterizer restatement (oracle/raster_ref.c), not reference outputs: nvdiffrast is absent, so
     nothing upstream can be run (DESIGN.md §2 "parity unpinned").  They freeze today's ids / barycentrics / interpolation /
@@ -270,6 +309,7 @@ if __name__ == "__main__":
         light_case()
         fauna_bones_case()
     obj_case()
+    normals_case()
     raster_case()
     geometry_module_case()
     print(sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))

@@ -262,6 +262,21 @@ def test_vertex_normals_oracle(cuda):
     assert np.array_equal(n2[:, -1], np.array([[0, 0, 1], [0, 0, 1]], np.float32))
 
 
+@pytest.mark.parametrize("case", ["mesh", "degenerate"])
+def test_vertex_normals_golden(cuda, case):
+    """R3 against the reference's own `auto_normals` (committed fixture tests/golden/normals.npz, generated by running
+    model/render/mesh.py:276-304 unmodified): values, gradient, degenerate-vertex fallback."""
+    ops = _ops()
+    g = golden("normals.npz")
+    v = dev(g[case + "_v_pos"], cuda).requires_grad_(True)
+    nrm = ops.vertex_normals(v, dev(g[case + "_faces"], cuda))
+    assert rel_err(nrm.detach().cpu().numpy(), g[case + "_v_nrm"]) < TOL
+    (nrm * dev(g[case + "_g"], cuda)).sum().backward()
+    assert rel_err(v.grad.cpu().numpy(), g[case + "_d_v_pos"]) < TOL
+    if case == "degenerate":
+        assert np.array_equal(nrm.detach().cpu().numpy()[0, 3:], np.array([[0, 0, 1]] * 3, np.float32))
+
+
 @pytest.mark.parametrize("Bp", [1, 3])
 def test_xfm_points_oracle(cuda, Bp):
     ops = _ops()

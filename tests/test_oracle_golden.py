@@ -69,6 +69,23 @@ def test_shading_normal_matches_reference():
     assert rel_err(geo.grad.numpy(), g["d_geo"]) < 1e-4
 
 
+@pytest.mark.parametrize("case", ["mesh", "degenerate"])
+def test_vertex_normals_match_reference(case):
+    """R3: every restatement of `auto_normals` (torch ops, the C twin used by the CPU baseline, numpy) against the output and the
+    gradient of the reference's own function (model/render/mesh.py:276-304; tests/golden/normals.npz), incl. the (0,0,1)
+    fallback of a vertex no face uses and of one touched by zero-area faces only."""
+    g = golden("normals.npz")
+    faces = torch.from_numpy(g[case + "_faces"]).long()
+    for fn in (T.auto_normals, T.auto_normals_c):
+        v = torch.from_numpy(g[case + "_v_pos"]).requires_grad_(True)
+        nrm = fn(v, faces)
+        assert rel_err(nrm.detach().numpy(), g[case + "_v_nrm"]) < 1e-6, fn.__name__
+        (nrm * torch.from_numpy(g[case + "_g"])).sum().backward()
+        assert rel_err(v.grad.numpy(), g[case + "_d_v_pos"]) < 1e-5, fn.__name__
+    nn = gnp.auto_normals(g[case + "_v_pos"], g[case + "_faces"])
+    assert rel_err(nn, g[case + "_v_nrm"]) < 1e-6
+
+
 def test_directional_shade_matches_reference():
     """oracle.torch_ref.directional_shade vs the reference's DirectionalLight.shade (light.py:186-193) incl. gradients."""
     g = golden("light_directional.npz")
