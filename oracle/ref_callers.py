@@ -123,8 +123,10 @@ def unload():
 
 
 def bare(cls):
-    """An instance of a reference nn.Module class whose constructor is NOT run (it would download a ViT): nn.Module state only."""
+    """An instance of a reference class whose constructor is NOT run (it would download a ViT): nn.Module state only (the model
+    classes - AnimalModel, FaunaModel - are plain Python classes, the predictors are nn.Modules)."""
     import torch
     obj = cls.__new__(cls)
-    torch.nn.Module.__init__(obj)
+    if isinstance(obj, torch.nn.Module):
+        torch.nn.Module.__init__(obj)
     return obj
