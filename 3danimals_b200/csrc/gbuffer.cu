@@ -25,6 +25,8 @@ struct GbParams {
     int64_t V, F;
     const float4* pn;   // packed (P.xyz, N.x | N.y, N.z, -, -) [B,V,2] or NULL: vertex attributes as 16-byte gathers
     const float4* q4;   // packed prior positions [Bq,V] (xyz, -) or NULL
+    const float* mtx;   // [B,4,4] clip transform or NULL: when set the backward recomputes the clip-space positions of the pixel's
+                        // three vertices from P (12 FMAs each) instead of gathering them from pos_clip (3 scattered 16-byte loads)
 };
 
 struct V3 { float x, y, z; };
@@ -81,7 +83,20 @@ struct GbPixel {  // forward intermediates of one covered pixel
     bool front;
 };
 
+// One 32-byte vertex record (P.xyz, N.xyz, -, -) with ONE 256-bit load (LDG.E.256, sm_100+): the per-pixel gathers are bound
+// by L1 sector lookups per instruction, and a 32-byte aligned record is exactly one sector.
+struct PN8 { float px, py, pz, nx, ny, nz, s0, s1; };
+__device__ __forceinline__ PN8 ldg_pn8(const float4* p)
+{
+    PN8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.px), "=f"(r.py), "=f"(r.pz), "=f"(r.nx), "=f"(r.ny), "=f"(r.nz), "=f"(r.s0), "=f"(r.s1)
+                 : "l"(p));
+    return r;
+}
+
 // f >= 0: vertex ids come from the triangle table; f < 0: the caller already set g.i0..i2 (covered-pixel list entry)
+template <bool PACKED = false>
 __device__ __forceinline__ void gb_forward(const GbParams& P, int b, int f, float u, float v, GbPixel& g)
 {
     g.u = u; g.v = v; g.w = 1.f - u - v;
@@ -89,16 +104,15 @@ __device__ __forceinline__ void gb_forward(const GbParams& P, int b, int f, floa
     const float* vp = P.v_pos + (size_t)b * P.V * 3;
     const float* vn = P.v_nrm + (size_t)b * P.V * 3;
     const float* vq = P.prior + (size_t)(P.Bq == 1 ? 0 : b) * P.V * 3;
-    if (P.pn) {
+    if (PACKED || P.pn) {
         // the gather is bound by L1 wavefronts per instruction, not bytes: 9 x 16-byte loads instead of 27 scalar ones
         const float4* pn = P.pn + (size_t)b * P.V * 2;
         const float4* q4 = P.q4 + (size_t)(P.Bq == 1 ? 0 : b) * P.V;
-        float4 a0 = __ldg(pn + (size_t)g.i0 * 2), b0 = __ldg(pn + (size_t)g.i0 * 2 + 1), c0 = __ldg(q4 + g.i0);
-        float4 a1 = __ldg(pn + (size_t)g.i1 * 2), b1 = __ldg(pn + (size_t)g.i1 * 2 + 1), c1 = __ldg(q4 + g.i1);
-        float4 a2 = __ldg(pn + (size_t)g.i2 * 2), b2 = __ldg(pn + (size_t)g.i2 * 2 + 1), c2 = __ldg(q4 + g.i2);
-        g.P0 = V3{a0.x, a0.y, a0.z}; g.N0 = V3{a0.w, b0.x, b0.y}; g.Q0 = V3{c0.x, c0.y, c0.z};
-        g.P1 = V3{a1.x, a1.y, a1.z}; g.N1 = V3{a1.w, b1.x, b1.y}; g.Q1 = V3{c1.x, c1.y, c1.z};
-        g.P2 = V3{a2.x, a2.y, a2.z}; g.N2 = V3{a2.w, b2.x, b2.y}; g.Q2 = V3{c2.x, c2.y, c2.z};
+        const PN8 a0 = ldg_pn8(pn + (size_t)g.i0 * 2), a1 = ldg_pn8(pn + (size_t)g.i1 * 2), a2 = ldg_pn8(pn + (size_t)g.i2 * 2);
+        const float4 c0 = __ldg(q4 + g.i0), c1 = __ldg(q4 + g.i1), c2 = __ldg(q4 + g.i2);
+        g.P0 = V3{a0.px, a0.py, a0.pz}; g.N0 = V3{a0.nx, a0.ny, a0.nz}; g.Q0 = V3{c0.x, c0.y, c0.z};
+        g.P1 = V3{a1.px, a1.py, a1.pz}; g.N1 = V3{a1.nx, a1.ny, a1.nz}; g.Q1 = V3{c1.x, c1.y, c1.z};
+        g.P2 = V3{a2.px, a2.py, a2.pz}; g.N2 = V3{a2.nx, a2.ny, a2.nz}; g.Q2 = V3{c2.x, c2.y, c2.z};
     } else {
         g.P0 = ld3(vp + (size_t)g.i0 * 3); g.P1 = ld3(vp + (size_t)g.i1 * 3); g.P2 = ld3(vp + (size_t)g.i2 * 3);
         g.N0 = ld3(vn + (size_t)g.i0 * 3); g.N1 = ld3(vn + (size_t)g.i1 * 3); g.N2 = ld3(vn + (size_t)g.i2 * 3);
@@ -138,7 +152,7 @@ __global__ void __launch_bounds__(256) gb_pack_kernel(const float* __restrict__ 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * V) return;
     V3 p = ld3(v_pos + i * 3), n = ld3(v_nrm + i * 3);
-    pn[i * 2] = make_float4(p.x, p.y, p.z, n.x);
+    pn[i * 2] = make_float4(p.x, p.y, p.z, n.x);       // record = (P.xyz, N.xyz, 0, 0): 32 bytes, 32-byte aligned
     pn[i * 2 + 1] = make_float4(n.y, n.z, 0.f, 0.f);
     if (i < (int64_t)Bq * V) {
         V3 q = ld3(prior + i * 3);
@@ -187,7 +201,8 @@ __device__ __forceinline__ void red4(float* p, float x, float y, float z, float 
 // of the image); otherwise one thread per pixel of the [B,H,W] grid (spp > 1 or no list).
 // launch bounds measured at C1 (B2A_GB_MINB sweep, round 1): (128,4) 123 regs, no spills 38.3 us | (128,5) 96 regs 38.3-39.1 us |
 // (128,6) 80 regs 44.8 us | (128,8) 64 regs 48.1 us - occupancy bought with spills loses
-template <bool LIST, bool CAMGRAD>
+// MTX: the fused render-geometry path - packed vertex records are present (P.pn) and clip positions are recomputed from P.mtx
+template <bool LIST, bool CAMGRAD, bool MTX>
 __global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float* __restrict__ pos_clip, const int4* __restrict__ cov_list,
                                                      const int* __restrict__ cov_count, const float* __restrict__ d_gb_pos,
                                                      const float* __restrict__ d_gb_geo, const float* __restrict__ d_gb_shn,
@@ -232,11 +247,11 @@ __global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float*
             V3 g_tex = d_gb_tex ? ld3(d_gb_tex + po) : zero;
             // clip-space positions: fetched up front with the other vertex attributes (one latency level, not a second)
             float4 p0 = make_float4(0.f, 0.f, 0.f, 1.f), p1 = p0, p2 = p0;
-            if (LIST && pos_clip) {
+            if (!MTX && LIST && pos_clip) {
                 const float* pb = pos_clip + (size_t)b * P.V * 4;
                 p0 = ldg4(pb + (size_t)g.i0 * 4); p1 = ldg4(pb + (size_t)g.i1 * 4); p2 = ldg4(pb + (size_t)g.i2 * 4);
             }
-            gb_forward(P, b, LIST ? -1 : f, r.x, r.y, g);
+            gb_forward<MTX>(P, b, LIST ? -1 : f, r.x, r.y, g);
             // camera-space normal
             d_cam = snormalize_bwd(g.cam, g.cn, g.lc, g_cn);
             const float* m = P.w2c + (size_t)b * 16;
@@ -268,8 +283,19 @@ __global__ void __launch_bounds__(128, 5) gb_bwd_kernel(GbParams P, const float*
             float c0x = 0.f, c0y = 0.f, c0w = 0.f, c1x = 0.f, c1y = 0.f, c1w = 0.f, c2x = 0.f, c2y = 0.f, c2w = 0.f;
             float du = (dot3(d_gpos, g.P0 - g.P2) + dot3(d_gnrm, g.N0 - g.N2)) + dot3(g_tex, g.Q0 - g.Q2);
             float dv = (dot3(d_gpos, g.P1 - g.P2) + dot3(d_gnrm, g.N1 - g.N2)) + dot3(g_tex, g.Q1 - g.Q2);
-            if (pos_clip && (du != 0.f || dv != 0.f)) {
-                if (!LIST) {
+            if ((MTX || pos_clip) && (du != 0.f || dv != 0.f)) {
+                if (MTX) {          // clip = [P,1] . M^T (xfm_fwd_kernel): x, y, w rows; z is not needed
+                    const float* M = P.mtx + (size_t)b * 16;
+                    const float m0 = __ldg(M), m1 = __ldg(M + 1), m2 = __ldg(M + 2), m3 = __ldg(M + 3);
+                    const float m4 = __ldg(M + 4), m5 = __ldg(M + 5), m6 = __ldg(M + 6), m7 = __ldg(M + 7);
+                    const float mc = __ldg(M + 12), md = __ldg(M + 13), me = __ldg(M + 14), mf = __ldg(M + 15);
+                    p0.x = ((m0 * g.P0.x + m1 * g.P0.y) + m2 * g.P0.z) + m3; p0.y = ((m4 * g.P0.x + m5 * g.P0.y) + m6 * g.P0.z) + m7;
+                    p0.w = ((mc * g.P0.x + md * g.P0.y) + me * g.P0.z) + mf;
+                    p1.x = ((m0 * g.P1.x + m1 * g.P1.y) + m2 * g.P1.z) + m3; p1.y = ((m4 * g.P1.x + m5 * g.P1.y) + m6 * g.P1.z) + m7;
+                    p1.w = ((mc * g.P1.x + md * g.P1.y) + me * g.P1.z) + mf;
+                    p2.x = ((m0 * g.P2.x + m1 * g.P2.y) + m2 * g.P2.z) + m3; p2.y = ((m4 * g.P2.x + m5 * g.P2.y) + m6 * g.P2.z) + m7;
+                    p2.w = ((mc * g.P2.x + md * g.P2.y) + me * g.P2.z) + mf;
+                } else if (!LIST) {
                     const float* pb = pos_clip + (size_t)b * P.V * 4;
                     p0 = ldg4(pb + (size_t)g.i0 * 4); p1 = ldg4(pb + (size_t)g.i1 * 4); p2 = ldg4(pb + (size_t)g.i2 * 4);
                 }
@@ -385,11 +411,11 @@ B2A_API int b2a_gbuffer_fwd(const float* rast, int spp, const int32_t* tri, cons
     cudaStream_t stream = (cudaStream_t)stream_;
     int rc = gb_check(rast, spp, tri, v_pos, v_nrm, prior_pos, Bq, w2c, campos, B, V, F, H, W);
     if (rc) return rc;
-    GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F, nullptr, nullptr};
+    GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F, nullptr, nullptr, nullptr};
     if (packed) {
         size_t need;
         b2a_gbuffer_pack_bytes(B, Bq, V, &need);
-        B2A_CHECK_ARG(packed_bytes >= need && ((uintptr_t)packed & 15) == 0, "packed buffer");
+        B2A_CHECK_ARG(packed_bytes >= need && ((uintptr_t)packed & 31) == 0, "packed buffer (32-byte aligned)");
         gb_packed(packed, B, Bq, V, &P);
         gb_pack_kernel<<<b2a_blocks((int64_t)B * V, 256), 256, 0, stream>>>(v_pos, v_nrm, prior_pos, B, Bq, V, (float4*)P.pn, (float4*)P.q4);
     }
@@ -405,6 +431,137 @@ B2A_API int b2a_gbuffer_bwd_workspace_bytes(int B, int64_t V, size_t* bytes)
     return 0;
 }
 
+namespace {
+
+// Fused tail of the geometry backward (b2a_render_geometry_bwd): accumulator rows -> gradient tensors AND the adjoint of the
+// clip transform in the same pass.  One thread per (image, vertex):
+//   d_clip = (A1.w, A2.w, 0, A0.w) [g-buffer / rasterize part] + d_clip_up [antialias part, nullable]
+//   d_v_pos = A0.xyz + M^T d_clip        d_v_nrm = A1.xyz        d_prior = A2.xyz (summed over the batch when the prior is shared)
+//   d_mtx[r][c] += sum_v d_clip[r] * [v,1][c]   (nullable; block-reduced, 16 atomics per block)
+// and the row is handed back zeroed.  Replaces gb_bwd_finalize_kernel + xfm_bwd_kernel (one grid-wide pass, no d_clip round trip).
+__global__ void __launch_bounds__(256) gb_bwd_finalize_xfm_kernel(float* __restrict__ acc, int rezero, int B, int Bq, int64_t V,
+                                                                  const float* __restrict__ mtx, const float* __restrict__ v_pos,
+                                                                  const float* __restrict__ d_clip_up, float* __restrict__ d_v_pos,
+                                                                  float* __restrict__ d_v_nrm, float* __restrict__ d_prior, float* __restrict__ d_mtx)
+{
+    __shared__ float m[16];
+    __shared__ float macc[16];
+    const int b = blockIdx.y;
+    if (threadIdx.x < 16) { m[threadIdx.x] = mtx[(size_t)b * 16 + threadIdx.x]; macc[threadIdx.x] = 0.f; }
+    __syncthreads();
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    float x = 0.f, y = 0.f, z = 0.f, one = 0.f;
+    if (v < V) {
+        float4* a = reinterpret_cast<float4*>(acc + ((size_t)b * V + v) * 12);
+        const float4 a0 = a[0], a1 = a[1], a2 = a[2];
+        g = make_float4(a1.w, a2.w, 0.f, a0.w);
+        if (d_clip_up) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(d_clip_up) + (size_t)b * V + v);
+            g.x += u.x; g.y += u.y; g.z += u.z; g.w += u.w;
+        }
+        const size_t o = ((size_t)b * V + v) * 3;
+        if (d_v_pos) {
+            d_v_pos[o] = a0.x + (((m[0] * g.x + m[4] * g.y) + m[8] * g.z) + m[12] * g.w);
+            d_v_pos[o + 1] = a0.y + (((m[1] * g.x + m[5] * g.y) + m[9] * g.z) + m[13] * g.w);
+            d_v_pos[o + 2] = a0.z + (((m[2] * g.x + m[6] * g.y) + m[10] * g.z) + m[14] * g.w);
+        }
+        if (d_v_nrm) { d_v_nrm[o] = a1.x; d_v_nrm[o + 1] = a1.y; d_v_nrm[o + 2] = a1.z; }
+        if (d_prior) {
+            if (Bq == 1) {
+                float* q = d_prior + (size_t)v * 3;
+                if (a2.x != 0.f) atomicAdd(q, a2.x);
+                if (a2.y != 0.f) atomicAdd(q + 1, a2.y);
+                if (a2.z != 0.f) atomicAdd(q + 2, a2.z);
+            } else {
+                d_prior[o] = a2.x; d_prior[o + 1] = a2.y; d_prior[o + 2] = a2.z;
+            }
+        }
+        if (rezero) a[0] = a[1] = a[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d_mtx) { x = v_pos[o]; y = v_pos[o + 1]; z = v_pos[o + 2]; one = 1.f; }
+    }
+    if (d_mtx) {
+        if (__ballot_sync(0xffffffffu, g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f)) {
+            const float gr[4] = {g.x, g.y, g.z, g.w}, h[4] = {x, y, z, one};
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float s = warp_sum(gr[r] * h[c]);
+                    if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(&macc[r * 4 + c], s);
+                }
+        }
+        __syncthreads();
+        if (threadIdx.x < 16 && macc[threadIdx.x] != 0.f) atomicAdd(&d_mtx[(size_t)b * 16 + threadIdx.x], macc[threadIdx.x]);
+    }
+}
+
+// shared body of b2a_gbuffer_bwd (mtx == NULL: clip positions gathered, d_clip written, separate clip-transform adjoint) and
+// b2a_render_geometry_bwd (mtx != NULL: clip positions recomputed, clip-transform adjoint fused into the finalize pass)
+int gb_bwd_impl(const char* who, const float* rast, int spp, const float* pos_clip, const float* mtx, const int32_t* tri, const float* v_pos,
+                const float* v_nrm, const float* prior_pos, int Bq, const float* w2c, const float* campos, int two_sided, int B, int64_t V,
+                int64_t F, int H, int W, const void* packed, size_t packed_bytes, const int32_t* cov_list, const int32_t* cov_count,
+                const float* d_gb_pos, const float* d_gb_geo_nrm, const float* d_gb_shading_nrm, const float* d_gb_cam_nrm,
+                const float* d_gb_tex_pos, const float* d_clip_up, void* workspace, size_t workspace_bytes, int workspace_is_zero,
+                float* d_v_pos, float* d_v_nrm, float* d_prior_pos, float* d_clip, float* d_mtx, float* d_w2c, float* d_campos,
+                cudaStream_t stream)
+{
+    int rc = gb_check(rast, spp, tri, v_pos, v_nrm, prior_pos, Bq, w2c, campos, B, V, F, H, W);
+    if (rc) return rc;
+    B2A_CHECK_ARG(!d_clip || (pos_clip && ((uintptr_t)pos_clip & 15) == 0 && ((uintptr_t)d_clip & 15) == 0), "pos_clip / d_clip");
+    B2A_CHECK_ARG(((uintptr_t)d_clip_up & 15) == 0, "d_clip_up must be 16-byte aligned");
+    B2A_CHECK_ARG(workspace && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= (size_t)B * V * 12 * sizeof(float), "workspace");
+    B2A_CHECK_ARG((cov_list == nullptr) == (cov_count == nullptr) && (!cov_list || spp == 1), "covered-pixel list");
+    float* acc = (float*)workspace;
+    if (!workspace_is_zero) B2A_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)B * V * 12 * sizeof(float), stream));
+    GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F, nullptr, nullptr, mtx};
+    if (packed) {
+        size_t need;
+        b2a_gbuffer_pack_bytes(B, Bq, V, &need);
+        B2A_CHECK_ARG(packed_bytes >= need && ((uintptr_t)packed & 31) == 0, "packed buffer");
+        gb_packed(const_cast<void*>(packed), B, Bq, V, &P);
+    }
+    const float* pcl = d_clip ? pos_clip : nullptr;     // legacy path: clip positions gathered when d_clip is wanted; with mtx they are recomputed
+    const bool cam = d_w2c || d_campos;   // camera gradients cost registers (12 warp reductions): separate instantiation
+    float* zbuf = (d_prior_pos && Bq == 1) ? d_prior_pos : nullptr;      // zeroed by the main kernel for finalize's atomics
+    const int64_t zn = zbuf ? V * 3 : 0;
+    const bool have_gb = d_gb_pos || d_gb_geo_nrm || d_gb_shading_nrm || d_gb_cam_nrm || d_gb_tex_pos;
+    if (!have_gb) {
+        if (zbuf) B2A_CUDA_OK(cudaMemsetAsync(zbuf, 0, (size_t)zn * sizeof(float), stream));
+    } else if (cov_list) {
+        // about one covered pixel per thread at typical coverage (~25 %); the grid-stride loop absorbs the rest
+        unsigned lblocks = b2a_blocks(((int64_t)B * H * W + 3) / 4, 128);
+        if (lblocks > 148u * 32u) lblocks = 148u * 32u;
+#define GB_LAUNCH_LIST(CAM, MTX)                                                                                                          \
+    gb_bwd_kernel<true, CAM, MTX><<<lblocks, 128, 0, stream>>>(P, pcl, (const int4*)cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, \
+                                                               d_gb_cam_nrm, d_gb_tex_pos, acc, d_w2c, d_campos, zbuf, zn)
+        const bool fused = mtx && P.pn;
+        if (cam) { if (fused) GB_LAUNCH_LIST(true, true); else GB_LAUNCH_LIST(true, false); }
+        else { if (fused) GB_LAUNCH_LIST(false, true); else GB_LAUNCH_LIST(false, false); }
+#undef GB_LAUNCH_LIST
+    } else {
+        unsigned blocks = b2a_blocks((int64_t)B * H * W, 128);
+#define GB_LAUNCH_GRID(CAM, MTX)                                                                                                       \
+    gb_bwd_kernel<false, CAM, MTX><<<blocks, 128, 0, stream>>>(P, pcl, nullptr, nullptr, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm, \
+                                                               d_gb_tex_pos, acc, d_w2c, d_campos, zbuf, zn)
+        const bool fused = mtx && P.pn;
+        if (cam) { if (fused) GB_LAUNCH_GRID(true, true); else GB_LAUNCH_GRID(true, false); }
+        else { if (fused) GB_LAUNCH_GRID(false, true); else GB_LAUNCH_GRID(false, false); }
+#undef GB_LAUNCH_GRID
+    }
+    if (mtx) {
+        gb_bwd_finalize_xfm_kernel<<<dim3(b2a_blocks(V, 256), B), 256, 0, stream>>>(acc, workspace_is_zero, B, Bq, V, mtx, v_pos, d_clip_up, d_v_pos, d_v_nrm,
+                                                                                     d_prior_pos, d_mtx);
+    } else if (d_v_pos || d_v_nrm || d_prior_pos || d_clip || workspace_is_zero) {
+        gb_bwd_finalize_kernel<<<dim3(b2a_blocks(V, 256), B), 256, 0, stream>>>(acc, workspace_is_zero, B, Bq, V, d_v_pos, d_v_nrm, d_prior_pos, d_clip);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { b2a_set_error("%s: CUDA error %s", who, cudaGetErrorName(e)); return 1; }
+    return 0;
+}
+
+}  // namespace
+
 B2A_API int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, const int32_t* tri, const float* v_pos,
                             const float* v_nrm, const float* prior_pos, int Bq, const float* w2c, const float* campos, int two_sided,
                             int B, int64_t V, int64_t F, int H, int W, const void* packed, size_t packed_bytes, const int32_t* cov_list,
@@ -412,47 +569,48 @@ B2A_API int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, c
                             const float* d_gb_tex_pos, void* workspace, size_t workspace_bytes, int workspace_is_zero, float* d_v_pos,
                             float* d_v_nrm, float* d_prior_pos, float* d_clip, float* d_w2c, float* d_campos, b2a_stream_t stream_)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    int rc = gb_check(rast, spp, tri, v_pos, v_nrm, prior_pos, Bq, w2c, campos, B, V, F, H, W);
+    return gb_bwd_impl(__func__, rast, spp, pos_clip, nullptr, tri, v_pos, v_nrm, prior_pos, Bq, w2c, campos, two_sided, B, V, F, H, W, packed, packed_bytes,
+                       cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm, d_gb_tex_pos, nullptr, workspace, workspace_bytes,
+                       workspace_is_zero, d_v_pos, d_v_nrm, d_prior_pos, d_clip, nullptr, d_w2c, d_campos, (cudaStream_t)stream_);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Fused geometry half of render_mesh (reference model/render/render.py:270-296 head + :160-209 render_layer + :72-75):
+// clip transform -> rasterize -> g-buffer -> antialias analysis, and its adjoint, as ONE C-ABI call per direction.
+// ------------------------------------------------------------------------------------------------------------------------
+B2A_API int b2a_render_geometry_fwd(const float* v_pos, const float* v_nrm, const float* prior_pos, int Bq, const float* mtx, const float* w2c,
+                                    const float* campos, const int32_t* tri, const int32_t* opp, int two_sided, int B, int64_t V, int64_t F,
+                                    int H, int W, int spp, void* raster_ws, size_t raster_ws_bytes, void* packed, size_t packed_bytes,
+                                    float* clip, float* rast, int32_t* cov_list, int32_t* cov_count, float* gb_pos, float* gb_geo_nrm,
+                                    float* gb_shading_nrm, float* gb_cam_nrm, float* gb_tex_pos, void* aa_ctx, size_t aa_ctx_bytes,
+                                    b2a_stream_t stream)
+{
+    B2A_CHECK_ARG(v_pos && v_nrm && prior_pos && mtx && w2c && campos && tri && clip && rast, "null pointer");
+    B2A_CHECK_ARG(spp >= 1 && H > 0 && W > 0, "shape");
+    int rc = b2a_xfm_points_fwd(v_pos, mtx, B, B, V, clip, stream);
     if (rc) return rc;
-    B2A_CHECK_ARG(!d_clip || (pos_clip && ((uintptr_t)pos_clip & 15) == 0 && ((uintptr_t)d_clip & 15) == 0), "pos_clip / d_clip");
-    B2A_CHECK_ARG(workspace && ((uintptr_t)workspace & 15) == 0 && workspace_bytes >= (size_t)B * V * 12 * sizeof(float), "workspace");
-    B2A_CHECK_ARG((cov_list == nullptr) == (cov_count == nullptr) && (!cov_list || spp == 1), "covered-pixel list");
-    float* acc = (float*)workspace;
-    if (!workspace_is_zero) B2A_CUDA_OK(cudaMemsetAsync(acc, 0, (size_t)B * V * 12 * sizeof(float), stream));
-    GbParams P{rast, tri, v_pos, v_nrm, prior_pos, w2c, campos, spp, Bq, two_sided, B, H, W, V, F, nullptr, nullptr};
-    if (packed) {
-        size_t need;
-        b2a_gbuffer_pack_bytes(B, Bq, V, &need);
-        B2A_CHECK_ARG(packed_bytes >= need && ((uintptr_t)packed & 15) == 0, "packed buffer");
-        gb_packed(const_cast<void*>(packed), B, Bq, V, &P);
+    rc = b2a_rasterize_fwd(clip, tri, B, V, F, H * spp, W * spp, raster_ws, raster_ws_bytes, rast, cov_list, cov_count, stream);
+    if (rc) return rc;
+    rc = b2a_gbuffer_fwd(rast, spp, tri, v_pos, v_nrm, prior_pos, Bq, w2c, campos, two_sided, B, V, F, H, W, packed, packed_bytes, gb_pos, gb_geo_nrm,
+                         gb_shading_nrm, gb_cam_nrm, gb_tex_pos, stream);
+    if (rc) return rc;
+    if (aa_ctx) {
+        B2A_CHECK_ARG(opp, "antialias analysis needs the edge adjacency table");
+        rc = b2a_antialias_prepare(rast, clip, tri, opp, B, V, F, H * spp, W * spp, aa_ctx, aa_ctx_bytes, stream);
     }
-    const float* pc = d_clip ? pos_clip : nullptr;
-    const bool cam = d_w2c || d_campos;   // camera gradients cost registers (12 warp reductions): separate instantiation
-    float* zbuf = (d_prior_pos && Bq == 1) ? d_prior_pos : nullptr;      // zeroed by the main kernel for finalize's atomics
-    const int64_t zn = zbuf ? V * 3 : 0;
-    if (cov_list) {
-        // about one covered pixel per thread at typical coverage (~25 %); the grid-stride loop absorbs the rest
-        unsigned lblocks = b2a_blocks(((int64_t)B * H * W + 3) / 4, 128);
-        if (lblocks > 148u * 32u) lblocks = 148u * 32u;
-        if (cam)
-            gb_bwd_kernel<true, true><<<lblocks, 128, 0, stream>>>(P, pc, (const int4*)cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm,
-                                                                   d_gb_cam_nrm, d_gb_tex_pos, acc, d_w2c, d_campos, zbuf, zn);
-        else
-            gb_bwd_kernel<true, false><<<lblocks, 128, 0, stream>>>(P, pc, (const int4*)cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm,
-                                                                    d_gb_cam_nrm, d_gb_tex_pos, acc, d_w2c, d_campos, zbuf, zn);
-    } else {
-        unsigned blocks = b2a_blocks((int64_t)B * H * W, 128);
-        if (cam)
-            gb_bwd_kernel<false, true><<<blocks, 128, 0, stream>>>(P, pc, nullptr, nullptr, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
-                                                                   d_gb_tex_pos, acc, d_w2c, d_campos, zbuf, zn);
-        else
-            gb_bwd_kernel<false, false><<<blocks, 128, 0, stream>>>(P, pc, nullptr, nullptr, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm,
-                                                                    d_gb_tex_pos, acc, d_w2c, d_campos, zbuf, zn);
-    }
-    if (d_v_pos || d_v_nrm || d_prior_pos || d_clip || workspace_is_zero) {
-        gb_bwd_finalize_kernel<<<dim3(b2a_blocks(V, 256), B), 256, 0, stream>>>(acc, workspace_is_zero, B, Bq, V, d_v_pos, d_v_nrm, d_prior_pos, d_clip);
-    }
-    B2A_LAUNCH_OK();
-    return 0;
+    return rc;
+}
+
+B2A_API int b2a_render_geometry_bwd(const float* rast, int spp, const float* mtx, const int32_t* tri, const float* v_pos, const float* v_nrm,
+                                    const float* prior_pos, int Bq, const float* w2c, const float* campos, int two_sided, int B, int64_t V,
+                                    int64_t F, int H, int W, const void* packed, size_t packed_bytes, const int32_t* cov_list,
+                                    const int32_t* cov_count, const float* d_gb_pos, const float* d_gb_geo_nrm, const float* d_gb_shading_nrm,
+                                    const float* d_gb_cam_nrm, const float* d_gb_tex_pos, const float* d_clip_up, void* workspace,
+                                    size_t workspace_bytes, int workspace_is_zero, float* d_v_pos, float* d_v_nrm, float* d_prior_pos,
+                                    float* d_mtx, float* d_w2c, float* d_campos, b2a_stream_t stream_)
+{
+    B2A_CHECK_ARG(mtx && packed, "mtx and the packed vertex records of the forward are required");
+    return gb_bwd_impl(__func__, rast, spp, nullptr, mtx, tri, v_pos, v_nrm, prior_pos, Bq, w2c, campos, two_sided, B, V, F, H, W, packed, packed_bytes,
+                       cov_list, cov_count, d_gb_pos, d_gb_geo_nrm, d_gb_shading_nrm, d_gb_cam_nrm, d_gb_tex_pos, d_clip_up, workspace, workspace_bytes,
+                       workspace_is_zero, d_v_pos, d_v_nrm, d_prior_pos, nullptr, d_mtx, d_w2c, d_campos, (cudaStream_t)stream_);
 }

@@ -71,6 +71,7 @@ KERNELS_PER_CALL = {
     "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 2,
     "b2a_antialias_pair_fwd": 1, "b2a_antialias_pair_bwd": 1, "b2a_shade_directional_fwd": 1, "b2a_shade_directional_bwd": 1,
     "b2a_analytic_field_fwd": 1, "b2a_analytic_field_bwd": 1, "b2a_composite_up_fwd": 1, "b2a_composite_up_bwd": 1, "b2a_gbuffer_fwd": 2, "b2a_gbuffer_bwd": 2,
+    "b2a_render_geometry_fwd": 8, "b2a_render_geometry_bwd": 2,
 }
 
 
@@ -938,21 +939,21 @@ class _RenderGeometry(torch.autograd.Function):
         st = _stream()
         fH, fW = H * spp, W * spp
         clip = torch.empty(B, V, 4, device=dev)
-        _call("b2a_xfm_points_fwd", (_p(v_pos), _p(mtx), B, Bp, V, _p(clip), st))
         ws = _workspace(_size(L.b2a_rasterize_workspace_bytes, B, F, fH, fW), dev)
         rast = torch.empty(B, fH, fW, 4, device=dev)
         use_cov = spp == 1
         cov_list = torch.empty((B * fH * fW, 4), dtype=_i32, device=dev) if use_cov else None
         cov_count = torch.empty(1, dtype=_i32, device=dev) if use_cov else None
-        _call("b2a_rasterize_fwd", (_p(clip), _p(tri), B, V, F, fH, fW, _p(ws), ws.numel(), _p(rast), _p(cov_list), _p(cov_count), st))
         outs = [torch.empty(B, H, W, 3, device=dev) if k in want else None for k in GB_KEYS]
         packed = _workspace(_size(L.b2a_gbuffer_pack_bytes, B, Bq, V), dev)
-        _call("b2a_gbuffer_fwd", (_p(rast), spp, _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), Bq, _p(w2c), _p(campos), int(two_sided), B, V, F,
-                                        H, W, _p(packed), packed.numel(), *[_p(o) for o in outs], st))
         aa_ctx = None
         if need_aa and (fH * fW) % 32 == 0 and F < (1 << 28):
             aa_ctx = _workspace(_size(L.b2a_antialias_workspace_bytes, B, fH, fW), dev)
-            _call("b2a_antialias_prepare", (_p(rast), _p(clip), _p(tri), _p(opp), B, V, F, fH, fW, _p(aa_ctx), aa_ctx.numel(), st))
+        # clip transform -> rasterize -> g-buffer -> antialias analysis: ONE C-ABI call (b2a_render_geometry_fwd)
+        _call("b2a_render_geometry_fwd", (_p(v_pos), _p(v_nrm), _p(prior_pos), Bq, _p(mtx), _p(w2c), _p(campos), _p(tri), _p(opp), int(two_sided), B, V, F,
+                                          H, W, spp, _p(ws), ws.numel(), _p(packed), packed.numel(), _p(clip), _p(rast), _p(cov_list), _p(cov_count),
+                                          *[_p(o) for o in outs], _p(aa_ctx), 0 if aa_ctx is None else aa_ctx.numel(), st),
+              launches=8 if aa_ctx is not None else 6)
         ctx.save_for_backward(rast, clip, tri, v_pos, v_nrm, prior_pos, mtx, w2c, campos, cov_list, cov_count, packed)
         ctx.cfg = (spp, int(two_sided), H, W, tuple(o is not None for o in outs))
         ctx.set_materialize_grads(False)   # an unused output (rast outside 'flow' mode) must arrive as None, not as a zero tensor
@@ -972,30 +973,25 @@ class _RenderGeometry(torch.autograd.Function):
         gs = [next(it) if p else None for p in present]
         gs = [(_f32(g, "d_gb") if g is not None else None) for g in gs]
         have_gb = any(g is not None for g in gs)
-        d_v_pos = torch.empty_like(v_pos)                                     # also the accumulator of the clip-transform adjoint
+        d_v_pos = torch.empty_like(v_pos)
         d_v_nrm = torch.empty_like(v_nrm) if need[1] else None
         d_prior = torch.empty_like(prior_pos) if need[2] else None
         d_mtx = torch.zeros_like(mtx) if need[3] else None
         d_w2c = torch.zeros_like(w2c) if need[4] else None
         d_campos = torch.zeros_like(campos) if need[5] else None
-        d_clip = torch.empty_like(clip)
-        if have_gb:
-            acc = _gb_accumulator(_size(L.b2a_gbuffer_bwd_workspace_bytes, B, V), rast.device)
-            _call("b2a_gbuffer_bwd", (_p(rast), spp, _p(clip), _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0], _p(w2c),
-                                            _p(campos), two_sided, B, V, F, H, W, _p(packed), packed.numel(), _p(cov_list), _p(cov_count),
-                                            *[_p(g) for g in gs], _p(acc), acc.numel(), 1, _p(d_v_pos), _p(d_v_nrm), _p(d_prior), _p(d_clip),
-                                            _p(d_w2c), _p(d_campos), st))
-        else:
-            d_v_pos.zero_(); d_clip.zero_()
-            for t in (d_v_nrm, d_prior):
-                if t is not None:
-                    t.zero_()
+        up = _f32(d_clip_up, "d_clip") if d_clip_up is not None else None
         if d_rast is not None:      # only the 'flow' mode interpolates with a differentiable rast (render.py:281-288)
+            d_clip = torch.zeros_like(clip)
             _call("b2a_rasterize_bwd", (_p(clip), _p(tri), _p(rast), _p(_f32(d_rast, "d_rast")), B, V, F, rast.shape[1], rast.shape[2],
                                               _p(d_clip), st))
-        up = _f32(d_clip_up, "d_clip") if d_clip_up is not None else None
-        # clip-transform adjoint of (g-buffer/raster contribution + antialias contribution), accumulated into d_v_pos
-        _call("b2a_xfm_points_bwd", (_p(v_pos), _p(mtx), _p(d_clip), _p(up), 1, B, B, V, _p(d_v_pos), _p(d_mtx), st))
+            up = d_clip if up is None else up + d_clip
+        # g-buffer / rasterize adjoint over the covered-pixel list, then ONE per-vertex pass: accumulator rows + antialias clip
+        # gradient -> clip-transform adjoint -> d_v_pos / d_v_nrm / d_prior (b2a_render_geometry_bwd)
+        acc = _gb_accumulator(_size(L.b2a_gbuffer_bwd_workspace_bytes, B, V), rast.device)
+        _call("b2a_render_geometry_bwd", (_p(rast), spp, _p(mtx), _p(tri), _p(v_pos), _p(v_nrm), _p(prior_pos), prior_pos.shape[0], _p(w2c), _p(campos),
+                                          two_sided, B, V, F, H, W, _p(packed), packed.numel(), _p(cov_list), _p(cov_count), *[_p(g) for g in gs], _p(up),
+                                          _p(acc), acc.numel(), 1, _p(d_v_pos), _p(d_v_nrm), _p(d_prior), _p(d_mtx), _p(d_w2c), _p(d_campos), st),
+              launches=2 if have_gb else 1)
         return (d_v_pos if need[0] else None, d_v_nrm, d_prior, d_mtx, d_w2c, d_campos, None, None, None, None, None, None, None, None)
 
 

@@ -44,3 +44,51 @@ def allreduce_gradients(tensors, average=True, group=None):
         g.copy_(flat[off:off + n].view_as(g))
         off += n
     return flat.numel() * flat.element_size()
+
+
+class GradientBuckets:
+    """DDP-style bucketed gradient all-reduce, overlapped with the backward pass (reference: accelerate / DistributedDataParallel,
+    Trainer.py:170-180; SURVEY.md §2.2 sizes the MagicPony message at ~68 MB of fp32 parameter gradients per step).
+
+    Flat fp32 buckets of at most `bucket_bytes`; `launch(i)` enqueues bucket i's all-reduce (NCCL AVG) on a SIDE stream behind an
+    event recorded on the compute stream, so the collective runs under whatever backward work is still queued; `wait()` makes the
+    compute stream wait for every launched bucket - call it where the optimiser would read the gradients.  Outside a process
+    group (N = 1) every method is a no-op.  Nothing here touches libb2a.so: the path itself has no exchange step (§8e)."""
+
+    def __init__(self, total_bytes, device, bucket_bytes=25 << 20, group=None):
+        self.group = group
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        n = max(int(total_bytes) // 4, 1)
+        per = max(int(bucket_bytes) // 4, 1)
+        self.flat = torch.zeros(n, device=device)
+        self.buckets = [self.flat[i:i + per] for i in range(0, n, per)]
+        self.stream = torch.cuda.Stream(device=device) if (self.active and torch.device(device).type == "cuda") else None
+        self.ready = [torch.cuda.Event() for _ in self.buckets] if self.stream is not None else []
+        self.launched = []
+        self.bytes_reduced = 0
+
+    def view(self, bucket, numel, offset=0):
+        """A [numel] slice of a bucket: point a gradient at it so that the kernel writes straight into the bucket (no copy)."""
+        return self.buckets[bucket][offset:offset + numel]
+
+    def launch(self, i):
+        if not self.active:
+            return
+        b = self.buckets[i]
+        op = dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM
+        if self.stream is None:       # gloo / CPU: synchronous
+            dist.all_reduce(b, op=op, group=self.group)
+            if op == dist.ReduceOp.SUM:
+                b.div_(dist.get_world_size(self.group))
+        else:
+            self.ready[i].record()                    # the bucket's gradients are final at this point of the compute stream
+            self.stream.wait_event(self.ready[i])
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(b, op=op, group=self.group)
+        self.launched.append(i)
+        self.bytes_reduced += b.numel() * 4
+
+    def wait(self):
+        if self.stream is not None and self.launched:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.launched = []

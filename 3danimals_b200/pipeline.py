@@ -24,17 +24,29 @@ class SyntheticScene:
     """Seeded numpy inputs shared by the CUDA path and the CPU oracle (same bytes on both sides)."""
 
     def __init__(self, grid_res=128, batch=16, image_res=256, n_body_bones=8, n_leg_bones=3, dino_dim=16, spatial_scale=7.0,
-                 sdf_noise=0.01, seed=0):
+                 sdf_noise=0.01, seed=0, body_bones_mode="z_minmax_y+", bone_y_threshold=None, chain_every_step=False, static_root_bones=False,
+                 second_render=False, class_dim=0):
         self.grid_res, self.batch, self.image_res = grid_res, batch, image_res
         self.n_body_bones, self.n_leg_bones, self.dino_dim = n_body_bones, n_leg_bones, dino_dim
         self.num_bones = n_body_bones + 4 * n_leg_bones
+        # config switches of the other shipped workloads (BASELINE configs[2], [3]):
+        #   body_bones_mode / n_leg_bones = 0 / static_root_bones: train_magicpony_bird.yaml:29-36
+        #   bone_y_threshold + kinematic chain every iteration: 3D-Fauna (InstancePredictorFauna.py:20,82-93)
+        #   second_render: Fauna's texture-less / light-less ['shaded'] render from a random view (Fauna.py:145-163,454)
+        #   class_dim: the class vector fed to the DINO field (Fauna.py:388; CoordMLP extra_feat_dim)
+        self.body_bones_mode, self.bone_y_threshold, self.chain_every_step = body_bones_mode, bone_y_threshold, chain_every_step
+        self.static_root_bones, self.second_render, self.class_dim = static_root_bones, second_render, class_dim
         v, t = synthetic.kuhn_tet_grid(grid_res)
         self.grid_verts = (v * np.float32(spatial_scale)).astype(np.float32)
         self.tets = t
         self.sdf = synthetic.sdf_horse(self.grid_verts, sigma=sdf_noise, seed=seed)
         rng = np.random.RandomState(seed + 1)
         self.angles = rng.uniform(-0.3, 0.3, size=(batch, 1, self.num_bones, 3)).astype(np.float32)
+        if static_root_bones:       # apply_articulation_constraints (InstancePredictorBase.py:437-441): the two root bones do not move
+            self.angles[:, :, [n_body_bones // 2 - 1, n_body_bones - 1]] = 0
         self.mvp, self.w2c, self.campos = synthetic.cameras(batch, seed=seed + 3)
+        self.mvp2, self.w2c2, self.campos2 = synthetic.cameras(batch, seed=seed + 17) if second_render else (None, None, None)
+        self.class_vector = np.random.RandomState(seed + 5).randn(batch, class_dim).astype(np.float32) if class_dim else None
         rng = np.random.RandomState(seed + 2)
         self.feat = rng.randn(batch, 256).astype(np.float32)
         self.light = np.array([0.3, 0.5, 0.8, 0.4, 0.6], np.float32)   # dir(3, normalised below), ambient, diffuse
@@ -47,6 +59,10 @@ class SyntheticScene:
         r = self.image_res
         return ((rng.randn(self.batch, 4, r, r) * 1e-3).astype(np.float32),
                 (rng.randn(self.batch, self.dino_dim, r, r) * 1e-3).astype(np.float32))
+
+    def upstream_grad_mask(self, seed=9):
+        """Upstream gradient of the second render's mask (Fauna's mask discriminator loss), [B,1,256,256]."""
+        return (np.random.RandomState(seed).randn(self.batch, 1, 256, 256) * 1e-3).astype(np.float32)
 
 
 class AnalyticField(torch.nn.Module):
@@ -97,13 +113,16 @@ class HotPath(torch.nn.Module):
         self.campos = torch.from_numpy(s.campos).to(dev)
         self.feat = torch.from_numpy(s.feat).to(dev)
         self.light = FixedLight(torch.from_numpy(s.light).to(dev))
+        self.class_vector = torch.from_numpy(s.class_vector).to(dev) if s.class_vector is not None else None
+        if s.second_render:
+            self.mvp2, self.w2c2, self.campos2 = (torch.from_numpy(x).to(dev) for x in (s.mvp2, s.w2c2, s.campos2))
         if mlps:
             from .networks import CoordMLP
             mm = torch.tensor([[0., 1.]] * 9, device=dev)
             self.material = CoordMLP(3, 9, 8, nf=256, activation="sigmoid", min_max=mm, n_harmonic_functions=10,
                                      embedder_scalar=2 * np.pi / 7.0 * 0.9, extra_feat_dim=256, symmetrize=True).to(dev)
             self.dino_net = CoordMLP(3, s.dino_dim, 5, nf=256, activation="sigmoid", n_harmonic_functions=8,
-                                     embedder_scalar=2 * np.pi / 7.0 * 0.9, symmetrize=True).to(dev)
+                                     embedder_scalar=2 * np.pi / 7.0 * 0.9, extra_feat_dim=s.class_dim, symmetrize=True).to(dev)
         else:
             self.material = AnalyticField(torch.from_numpy(s.w_kd).to(dev), True)
             self.dino_net = AnalyticField(torch.from_numpy(s.w_dino).to(dev), False)
@@ -120,13 +139,15 @@ class HotPath(torch.nn.Module):
         verts, faces, uv_idx, faces32 = self.dmtet.extract(self.grid_verts, sdf, self.grid)
         prior = mesh_mod.make_mesh(verts[None], faces[None], None, uv_idx[None], None, faces_i32=faces32)
         # bones from the prior shape (InstancePredictorBase.py:319-335); chain lists only the first time
-        if self.bone_aux is None:
+        ekw = dict(n_legs=4, n_leg_bones=s.n_leg_bones, body_bones_mode=s.body_bones_mode)
+        if s.bone_y_threshold is not None:
+            ekw["bone_y_threshold"] = s.bone_y_threshold
+        if self.bone_aux is None or s.chain_every_step:     # 3D-Fauna recomputes the chain every iteration (InstancePredictorFauna.py:82-93)
             bones, self.kinematic_chain, self.bone_aux = skinning_mod.estimate_bones(
-                prior.v_pos[:, None].detach(), s.n_body_bones, n_legs=4, n_leg_bones=s.n_leg_bones, body_bones_mode="z_minmax_y+",
-                compute_kinematic_chain=True)
+                prior.v_pos[:, None].detach(), s.n_body_bones, compute_kinematic_chain=True, **ekw)
         else:
-            bones = skinning_mod.estimate_bones(prior.v_pos[:, None].detach(), s.n_body_bones, n_legs=4, n_leg_bones=s.n_leg_bones,
-                                                body_bones_mode="z_minmax_y+", compute_kinematic_chain=False, aux=self.bone_aux)
+            bones = skinning_mod.estimate_bones(prior.v_pos[:, None].detach(), s.n_body_bones, compute_kinematic_chain=False,
+                                                aux=self.bone_aux, **ekw)
         # articulation (InstancePredictorBase.py:578-586)
         posed, aux = skinning_mod.skinning(prior.v_pos[:, None], bones, self.kinematic_chain, self.angles, output_posed_bones=True,
                                            temperature=0.05)
@@ -137,14 +158,18 @@ class HotPath(torch.nn.Module):
         out = render_mod.render_mesh(None, inst, self.mvp, self.w2c, self.campos, self.material, self.light, res, spp=self.spp,
                                      num_layers=1, msaa=True, background=None, bsdf="diffuse", feat=feat,
                                      render_modes=list(render_modes), prior_mesh=prior, dino_net=self.dino_net,
-                                     sparse_fields=self.sparse_fields)
+                                     class_vector=self.class_vector if self.mlps else None, sparse_fields=self.sparse_fields)
+        if s.second_render:     # FaunaModel.get_random_view_mask (Fauna.py:145-163): no texture, no light, one-sided, 256^2
+            out = list(out) + [render_mod.render_mesh(None, inst, self.mvp2, self.w2c2, self.campos2, None, None, (256, 256), spp=1, num_layers=1,
+                                                      msaa=True, background=None, bsdf="diffuse", feat=None, render_modes=["shaded"],
+                                                      prior_mesh=prior, two_sided_shading=False, dino_net=None)[0][:, 3:]]
         self.last = dict(prior=prior, inst=inst, bones=bones, posed_bones=aux["posed_bones"])
         return out
 
-    def step(self, d_shaded, d_dino):
-        """One fwd+bwd pass; returns (d_sdf [Vg,1], d_angles [B,1,K,3])."""
+    def step(self, d_shaded, d_dino, d_mask=None):
+        """One fwd+bwd pass; returns (d_sdf [Vg,1], d_angles [B,1,K,3]).  d_mask: upstream gradient of the second render's mask."""
         self.sdf.grad = None
         self.angles.grad = None
-        shaded, dino = self.forward()
-        torch.autograd.backward([shaded, dino], [d_shaded, d_dino])
+        outs = self.forward()
+        torch.autograd.backward(list(outs), [d_shaded, d_dino] + ([d_mask] if len(outs) > 2 else []))
         return self.sdf.grad, self.angles.grad

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - rendered-images/sec (fwd+bwd) of the 3DAnimals reconstruction hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mlps]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c4] [--mlps]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 One "step" = one pass of the hot path over one batch of synthetic input:
@@ -29,10 +29,42 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "rendered-images/sec (fwd+bwd) 256^2 horse batch"
-WORKLOAD = dict(workload="train_magicpony_horse: batch 16/GPU, 256x256, DMTet res 128 (Kuhn grid 2.15M verts / 12.6M tets), 20 bones, "
-                         "modes shaded+dino_pred(16ch), fwd+bwd, analytic colour field (M1a)",
-                grid_res=128, batch_per_gpu=16, image_res=256, bones=20, dino_dim=16,
-                l2="inputs larger than L2: every step streams the 201 MB tet index buffer (+8.6 MB sdf, 60 MB edge CSR)")
+
+# BASELINE.json configs[1..4] as bench workloads (configs[0] is the CPU-runnable parity case).  `--config c1` (default) is the
+# configuration the metric is quoted on; the others are extra lines recorded under profiles/.
+CONFIGS = {
+    "c1": dict(workload="train_magicpony_horse: batch 16/GPU, 256x256, DMTet res 128 (Kuhn grid 2.15M verts / 12.6M tets), 20 bones, "
+                        "modes shaded+dino_pred(16ch), fwd+bwd, analytic colour field (M1a)",
+               grid_res=128, batch_per_gpu=16, image_res=256, bones=20, dino_dim=16,
+               l2="inputs larger than L2: every step streams the 201 MB tet index buffer (+8.6 MB sdf, 60 MB edge CSR)"),
+    "c2": dict(workload="train_magicpony_bird: batch 32/GPU, 256x256, DMTet res 64, 8 body bones / no legs (z_minmax), static root bones, "
+                        "modes shaded+dino_pred(16ch), fwd+bwd; fields under fp16 autocast with --mlps (train_magicpony_bird.yaml:52)",
+               grid_res=64, batch_per_gpu=32, image_res=256, bones=8, dino_dim=16,
+               l2="working set per step (16-channel gradients + g-buffers of 32 images, 270 MB) exceeds L2"),
+    "c3": dict(workload="train_fauna: batch 8/GPU, 256x256, DMTet res 128, 20 bones with bone_y_threshold 0.4 and the kinematic chain "
+                        "re-derived every iteration, modes shaded+dino_pred(16ch) + second texture-less ['shaded'] random-view render, fwd+bwd",
+               grid_res=128, batch_per_gpu=8, image_res=256, bones=20, dino_dim=16,
+               l2="inputs larger than L2: every step streams the 201 MB tet index buffer"),
+    "c4": dict(workload="visualize rotation / texture finetune: batch 1, 512x512 at spp 4 (2048^2 internal), DMTet res 256 (17M verts / 100M tets), "
+                        "one step = one texture-finetune iteration ['shaded'] fwd+bwd on the fixed mesh, CUDA-graph replay",
+               grid_res=256, batch_per_gpu=1, image_res=512, bones=20, dino_dim=16, spp=4,
+               l2="2048^2 internal buffers (67 MB rast + 134 MB of colour / gradient) exceed L2"),
+}
+SCENE_KW = {
+    "c1": dict(),
+    "c2": dict(n_leg_bones=0, body_bones_mode="z_minmax", static_root_bones=True),
+    "c3": dict(bone_y_threshold=0.4, chain_every_step=True, second_render=True),
+}
+WORKLOAD = CONFIGS["c1"]
+
+
+def make_scene(cfg, seed=0, mlps=False):
+    pipe = importlib.import_module("3danimals_b200.pipeline")
+    w = CONFIGS[cfg]
+    kw = dict(SCENE_KW[cfg])
+    if cfg == "c3" and mlps:
+        kw["class_dim"] = 128
+    return pipe.SyntheticScene(grid_res=w["grid_res"], batch=w["batch_per_gpu"], image_res=w["image_res"], seed=seed, **kw)
 
 
 def peaks():
@@ -101,11 +133,12 @@ def cpu_arm(scene, steps, warmup, images):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     g1, g2 = scene.upstream_grads()
+    g3 = scene.upstream_grad_mask() if scene.second_render else None
     for _ in range(warmup):
-        P.step(scene, g1, g2, images=images)
+        P.step(scene, g1, g2, images=images, d_mask=g3)
     t0 = time.perf_counter()
     for _ in range(steps):
-        P.step(scene, g1, g2, images=images)
+        P.step(scene, g1, g2, images=images, d_mask=g3)
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return images / dt, dt, max(cores, R.num_threads())
 
@@ -175,33 +208,82 @@ def torch_ops_geometry_arm(hp, dev, reps=5):
 
 
 def run_reference(args):
+    """The CPU arm: the reference's path has no other runnable form here (nvdiffrast is absent).  Under torchrun
+    rank 0 alone works: ONE host process, `batch_per_gpu` images per step whatever N - only the N=1 ratio compares like with like
+    (`run.normalisation` says so in the line)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pipe = importlib.import_module("3danimals_b200.pipeline")
-    scene = pipe.SyntheticScene(grid_res=WORKLOAD["grid_res"], batch=WORKLOAD["batch_per_gpu"], image_res=WORKLOAD["image_res"])
-    images = WORKLOAD["batch_per_gpu"]
-    ips, dt, cores = cpu_arm(scene, args.steps, min(args.warmup, 1), images)
+    cfg = args.config
+    if cfg == "c4":
+        raise SystemExit("--impl reference --config c4: the CPU leg of c4 is part of the c4 line itself (it needs the device-extracted mesh)")
+    scene = make_scene(cfg)
+    images = CONFIGS[cfg]["batch_per_gpu"]
+    ips, dt, cores = cpu_arm(scene, args.steps, args.warmup, images)
     sample = "full step: extraction + %d images fwd+bwd per step, %d steps" % (images, args.steps)
-    line = dict(metric=METRIC, value=ips, unit="images/s", n_gpus=args.gpus, steps=args.steps, warmup=min(args.warmup, 1),
+    line = dict(metric=METRIC, value=ips, unit="images/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=WORKLOAD, impl="reference",
+                config=CONFIGS[cfg], impl="reference",
                 cpu_baseline=dict(value=ips, unit="images/s", cores=cores, kind="port", sample=sample),
-                e2e=dict(value=ips, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+                e2e=dict(value=ips, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                run=dict(images_per_step=images, normalisation="one host process, %d images per step for every --gpus N: compare with the N=1 line of "
+                                                               "the product arm (or per-GPU values)" % images))
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # ours
 # ----------------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(scene_stats):
-    """Algorithmic bytes per launch of the raster-backward kernels (DESIGN.md 'Kernels and rooflines'): every tensor that
-    must cross the kernel boundary counted once; silhouette-pair reads are O(perimeter) and counted as 0."""
-    B, HW, V, F, D = scene_stats["B"], scene_stats["HW"], scene_stats["V"], scene_stats["F"], scene_stats["D"]
-    aa_shaded = B * HW * (4 * 4 + 3 * 4) + B * HW // 8        # read d_out RGBA + coverage bit, write d_color RGB
-    aa_dino = B * HW * (D * 4 + D * 4) + B * HW // 8          # read d_out D ch + coverage bit, write d_color D ch
-    gb = B * HW * (16 + 12 + 12) + B * V * ((12 + 12 + 16) * 2 + (12 + 12 + 16)) + V * (12 * 2 + 12) + F * 12
-    return {"aa_bwd_shaded": aa_shaded, "aa_bwd_dino": aa_dino, "gb_bwd": gb}
+GRAD_SET_BYTES = 68 << 20       # fp32 parameter gradients all-reduced per step by the reference under DDP (SURVEY.md §2.2: MagicPony ~68 MB)
+RASTER_BWD_CALLS = ("b2a_antialias_pair_bwd", "b2a_antialias_bwd", "b2a_composite_up_bwd", "b2a_render_geometry_bwd", "b2a_gbuffer_bwd")
+
+
+def algorithmic_bytes(name, tag, st):
+    """Algorithmic bytes of ONE call of a raster-backward entry point: every tensor that must cross the kernel
+    boundary counted once; silhouette-pair reads are O(perimeter) and counted as 0.  st: B, HW (raster pixels per image), gHW
+    (g-buffer pixels per image), V, F, D, n_cov (covered pixels), n_gb (g-buffer gradients consumed), Bq."""
+    B, HW, V, D = st["B"], st["HW"], st["V"], st["D"]
+    bits = B * HW // 8
+    if name == "b2a_antialias_pair_bwd":          # wide key: read d_out D ch, write d_color D ch; narrow: read RGBA, write RGB
+        return B * HW * (4 * D + 4 * D) + B * HW * (4 * 4 + 4 * 3) + 2 * bits
+    if name in ("b2a_antialias_bwd", "b2a_composite_up_bwd"):
+        C = int(tag[1:]) if tag.startswith("C") and tag[1:].isdigit() else 4
+        keep = C if C == 4 else C - 1            # shaded keeps alpha, dino / kd / ... drop it
+        return B * HW * 4 * keep + B * st["gHW"] * 4 * (C - 1) + bits
+    # g-buffer / rasterize adjoint + per-vertex finalize + clip-transform adjoint (SURVEY.md §8d phase B, restated for this design):
+    # per g-buffer pixel rast 16 B + 12 B per consumed gradient, a 16-byte list entry per covered pixel; per (image, vertex) the
+    # read-modify-write of the four gradient rows d_v_pos, d_v_nrm, d_prior, d_clip (2 x (12 + 12 + 12 + 16) = 104 B, SURVEY's own term),
+    # the position + normal attributes read (24) and the antialias clip gradient read (16); per vertex the shared prior position (12)
+    # and d_prior (12).  (The accumulator's 48-byte rows / 32-byte packed records are layout choices and are not counted.)
+    return (B * st["gHW"] * (16 + 12 * st["n_gb"]) + st["n_cov"] * 16 + B * V * (104 + 24 + 16) + st["Bq"] * V * (12 + 12))
+
+
+def build_roofline(durs, st, peak, peak_src):
+    """The roofline object describes the raster backward AS A GROUP (every launch between the upstream image gradients and the
+    per-vertex gradients): algorithmic bytes of all its calls / sum of their CUDA-event durations.  Per-kernel figures beside it."""
+    mean = lambda xs: sum(xs) / len(xs)
+    kern = {}
+    for (name, tag), xs in sorted(durs.items()):
+        if name in RASTER_BWD_CALLS and xs:
+            k = name.replace("b2a_", "") + (":" + tag if tag else "")
+            n_per_step = max(1, round(len(xs) / st["timed_steps"]))
+            ms = mean(xs) * n_per_step
+            nbytes = algorithmic_bytes(name, tag, st) * n_per_step
+            kern[k] = dict(ms=ms, bytes=nbytes, gbs=nbytes / (ms * 1e-3) / 1e9, frac=nbytes / (ms * 1e-3) / 1e9 / peak, calls_per_step=n_per_step)
+    gbytes = sum(k["bytes"] for k in kern.values())
+    gms = sum(k["ms"] for k in kern.values())
+    slowest = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
+    traffic = ncu_us = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r2.json")      # dram bytes + ncu durations per launch from the committed ncu capture (c1)
+    if os.path.isfile(tpath) and st.get("cfg") == "c1":
+        t = json.load(open(tpath))
+        traffic = sum(v.get("dram_read_bytes", 0) + v.get("dram_write_bytes", 0) for v in t.values() if isinstance(v, dict))
+        ncu_us = {k: v.get("ncu_us") for k, v in t.items() if isinstance(v, dict)}
+    return dict(bound="hbm", kernel="raster backward group: " + " + ".join(kern), achieved=gbytes / (gms * 1e-3) / 1e9 if gms else None, peak=peak, unit="GB/s",
+                frac=gbytes / (gms * 1e-3) / 1e9 / peak if gms else None, traffic=traffic, peak_source=peak_src, us_per_launch=gms * 1e3,
+                bytes_per_launch=gbytes, selection="the whole raster-backward group (all launches, event-timed live inside the step)",
+                slowest_kernel=slowest, kernels=kern, ncu_us_per_kernel=ncu_us,
+                per_call_ms={(n + ":" + t if t else n): sum(v) / len(v) for (n, t), v in sorted(durs.items())})
 
 
 def run_ours(args):
@@ -216,38 +298,64 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.config == "c4":
+        return run_c4(args, dev, rank, world)
+    cfg = args.config
+    W = CONFIGS[cfg]
     pipe = importlib.import_module("3danimals_b200.pipeline")
     ops = importlib.import_module("3danimals_b200.ops")
-    B, r = WORKLOAD["batch_per_gpu"], WORKLOAD["image_res"]
-    scene = pipe.SyntheticScene(grid_res=WORKLOAD["grid_res"], batch=B, image_res=r, seed=rank)   # image-parallel shard
+    par = importlib.import_module("3danimals_b200.parallel")
+    B, r = W["batch_per_gpu"], W["image_res"]
+    scene = make_scene(cfg, seed=rank, mlps=args.mlps)          # image-parallel shard
     hp = pipe.HotPath(scene, dev, mlps=args.mlps)
-    if args.mlps and args.mlp_math == "tf32":
+    mlp_math = args.mlp_math or ("fp16" if cfg == "c2" else "fp32")
+    if args.mlps and mlp_math == "tf32":
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
-    if args.mlps and args.mlp_math == "fp16":      # the reference wraps the field evaluation in autocast (bird config)
+    if args.mlps and mlp_math == "fp16":      # the reference wraps the field evaluation in autocast (bird config)
         for net in (hp.material, hp.dino_net):
             net.forward = torch.autocast("cuda", dtype=torch.float16)(net.forward)
     g1, g2 = scene.upstream_grads()
-    d_shaded, d_dino = torch.from_numpy(g1).to(dev), torch.from_numpy(g2).to(dev)
+    ups = [torch.from_numpy(g1).to(dev), torch.from_numpy(g2).to(dev)]
+    if scene.second_render:
+        ups.append(torch.from_numpy(scene.upstream_grad_mask()).to(dev))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    par = importlib.import_module("3danimals_b200.parallel")
+    # DDP stand-in: the reference all-reduces ~68 MB of fp32 parameter gradients per step in 25 MB buckets, overlapped with the
+    # backward.  The gradients this path produces for replicated parameters (d_sdf) ride in the LAST bucket, launched when the
+    # backward has finished; the other buckets stand for parameter gradients produced elsewhere in the step (field / light / pose /
+    # encoder networks) and are launched when the backward starts.  Everything is waited for where the optimiser would read.
+    buckets = par.GradientBuckets(GRAD_SET_BYTES, dev)
+    last = len(buckets.buckets) - 1
+    n_sdf = hp.sdf.numel()
+
+    def reduce_and_wait(d_sdf):
+        if buckets.active:
+            buckets.view(last, n_sdf).copy_(d_sdf.reshape(-1))
+            buckets.launch(last)
+            buckets.wait()
 
     def step():
-        d_sdf, d_ang = hp.step(d_shaded, d_dino)
-        # DDP semantics: all-reduce on (the stand-in for) parameter gradients only; no-op at N=1
-        par.allreduce_gradients([d_sdf], average=True)
-        return d_sdf, d_ang
+        hp.sdf.grad = None
+        hp.angles.grad = None
+        outs = hp.forward()
+        for i in range(last):
+            buckets.launch(i)
+        torch.autograd.backward(list(outs), ups)
+        reduce_and_wait(hp.sdf.grad)
+        return hp.sdf.grad, hp.angles.grad
 
-    for _ in range(max(args.warmup, 3)):
+    nwarm = max(args.warmup, 3)
+    for _ in range(nwarm):
         step()
     barrier()
     # ---- timed region: exactly K steps, device-timed, max over ranks ------------------------------------------
     ops.stats.reset()
+    buckets.bytes_reduced = 0
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -265,6 +373,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = ops.stats.launches
+    reduced_per_step = buckets.bytes_reduced // max(args.steps, 1)
     ms_per_step = float(ms.item()) / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
@@ -272,53 +381,19 @@ def run_ours(args):
     ops.stats.reset()
     ops.stats.timing = True
     ops.stats.spin_cycles = 300000    # ~150 us of device spin before each start event: launches are queued when it fires
-    for _ in range(min(args.steps, 5)):
+    timed_steps = min(args.steps, 5)
+    for _ in range(timed_steps):
         step()
     torch.cuda.synchronize()
     ops.stats.timing = False
     durs = ops.stats.durations_ms()
     prior, inst = hp.last["prior"], hp.last["inst"]
-    st = dict(B=B, HW=r * r, V=int(inst.v_pos.shape[1]), F=int(inst.t_pos_idx.shape[1]), D=scene.dino_dim)
-    ab = algorithmic_bytes(st)
-    mean = lambda xs: sum(xs) / len(xs) if xs else float("nan")
-    t_gb = mean(durs.get(("b2a_gbuffer_bwd", ""), []))
+    with torch.no_grad():
+        n_cov = int((hp.forward()[0][:, 3] > 0).sum().item())      # ~ covered pixels (antialiased alpha > 0), for the list term only
+    st = dict(cfg=cfg, B=B, HW=r * r, gHW=r * r, V=int(inst.v_pos.shape[1]), F=int(inst.t_pos_idx.shape[1]), D=scene.dino_dim, n_cov=n_cov, n_gb=2, Bq=1,
+              timed_steps=timed_steps)
     peak, peak_src = peaks()
-    pair_tag = "C%d+C4" % (scene.dino_dim + 1)
-    if ("b2a_antialias_pair_bwd", pair_tag) in durs:
-        # both keys' composite+antialias backward is ONE launch (aa_bwd_pair_kernel): its bytes are the two keys' bytes
-        kern = {
-            "aa_bwd_pair": dict(ms=mean(durs[("b2a_antialias_pair_bwd", pair_tag)]), bytes=ab["aa_bwd_dino"] + ab["aa_bwd_shaded"]),
-            "gb_bwd": dict(ms=t_gb, bytes=ab["gb_bwd"]),
-        }
-    else:
-        kern = {
-            "aa_bwd_dino": dict(ms=mean(durs.get(("b2a_antialias_bwd", "C%d" % (scene.dino_dim + 1)), [])), bytes=ab["aa_bwd_dino"]),
-            "aa_bwd_shaded": dict(ms=mean(durs.get(("b2a_antialias_bwd", "C4"), [])), bytes=ab["aa_bwd_shaded"]),
-            "gb_bwd": dict(ms=t_gb, bytes=ab["gb_bwd"]),
-        }
-    for k in kern.values():
-        k["gbs"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9
-        k["frac"] = k["gbs"] / peak
-    # The roofline object describes the HBM stream of the raster backward: the kernel that moves the most algorithmic bytes
-    # (aa_bwd_dino, 54 % of the group).  gb_bwd can be a few microseconds slower but is a vertex gather / vector-reduction
-    # kernel bound by LSU sector requests and L2 atomics, not by HBM; every kernel and the group total are
-    # reported beside it in raster_backward_group.
-    dom = max(kern, key=lambda k: kern[k]["bytes"])
-    slowest = max(kern, key=lambda k: kern[k]["ms"])
-    group_bytes = sum(k["bytes"] for k in kern.values())
-    group_ms = sum(k["ms"] for k in kern.values())
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")      # dram__bytes_read+write per launch from the committed ncu capture
-    if os.path.isfile(tpath):
-        t = json.load(open(tpath)).get(dom)
-        if t:
-            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
-    roofline = dict(bound="hbm", kernel=dom, achieved=kern[dom]["gbs"], peak=peak, unit="GB/s", frac=kern[dom]["frac"], traffic=traffic,
-                    peak_source=peak_src, us_per_launch=kern[dom]["ms"] * 1e3,
-                    selection="largest algorithmic byte count among the raster-backward kernels", slowest_kernel=slowest,
-                    raster_backward_group=dict(kernels=kern, bytes=group_bytes, ms=group_ms, achieved=group_bytes / (group_ms * 1e-3) / 1e9,
-                                               frac=group_bytes / (group_ms * 1e-3) / 1e9 / peak),
-                    per_call_ms={(n + ":" + t if t else n): sum(v) / len(v) for (n, t), v in sorted(durs.items())})
+    roofline = build_roofline(durs, st, peak, peak_src)
 
     # ---- end to end through the public API from pinned host buffers -------------------------------------------
     import torch.nn.functional as F
@@ -372,13 +447,17 @@ def run_ours(args):
         hp.sdf.grad = None
         hp.angles.grad = None
         t0 = mark("convert", t0)
-        shaded, dino = hp.forward()
+        outs = hp.forward()
         t0 = mark("forward", t0)
-        loss = F.mse_loss(shaded, tgt_rgba) + F.mse_loss(dino, tgt_dino)
+        loss = F.mse_loss(outs[0], tgt_rgba) + F.mse_loss(outs[1], tgt_dino)
+        if len(outs) > 2:
+            loss = loss + outs[2].mean()
         t0 = mark("loss", t0)
+        for i in range(last):
+            buckets.launch(i)
         loss.backward()
         t0 = mark("backward", t0)
-        par.allreduce_gradients([hp.sdf.grad], average=True)
+        reduce_and_wait(hp.sdf.grad)
         loss_host.copy_(loss.detach(), non_blocking=True)
         mark("allreduce + loss readback", t0)
 
@@ -414,21 +493,173 @@ def run_ours(args):
         ips, dt, cores = cpu_arm(scene, reps, 1, B)
         cpu = dict(value=ips, unit="images/s", cores=cores, kind="port", seconds_per_step=dt,
                    sample="full step (extraction + %d images fwd+bwd), %d steps after 1 warm-up; oracle/pipeline_ref.py" % (B, reps))
-        try:
-            cpu["gpu_torch_ops_geometry"] = torch_ops_geometry_arm(hp, dev)
-        except Exception as e:      # a baseline must never cost the bench line
-            cpu["gpu_torch_ops_geometry"] = dict(error=repr(e)[:200])
+        if cfg == "c1":
+            try:
+                cpu["gpu_torch_ops_geometry"] = torch_ops_geometry_arm(hp, dev)
+            except Exception as e:      # a baseline must never cost the bench line
+                cpu["gpu_torch_ops_geometry"] = dict(error=repr(e)[:200])
 
     if rank == 0:
-        cfg = dict(WORKLOAD)
-        cfg.update(autograd_threads=args.autograd_threads, mesh_verts=st["V"], mesh_faces=st["F"], field=("CoordMLP texture 8x256 + DINO 5x256 (M1b, %s)" % args.mlp_math) if args.mlps else "analytic (M1a)",
-                   parallelism="image-parallel dp%d, NCCL all-reduce on d_sdf only" % world)
-        line = dict(metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        run = dict(autograd_threads=args.autograd_threads, mesh_verts=st["V"], mesh_faces=st["F"], covered_pixels=n_cov, warmup_done=nwarm,
+                   field=("CoordMLP texture 8x256 + DINO 5x256 (M1b, %s)" % mlp_math) if args.mlps else "analytic (M1a)",
+                   parallelism="image-parallel dp%d; DDP stand-in: %d B of fp32 gradients all-reduced per step in %d buckets (NCCL AVG, side stream, "
+                               "overlapped with the backward; d_sdf in the last bucket)" % (world, reduced_per_step, len(buckets.buckets)),
+                   allreduce_bytes_per_step=reduced_per_step)
+        line = dict(metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=args.warmup if args.warmup >= 3 else nwarm,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=cfg, clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, impl="ours")
+                    config=W, run=run, clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, impl="ours")
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_c4(args, dev, rank, world):
+    """BASELINE configs[4]: visualize rotation / texture finetune on a fixed res-256 mesh, 512^2 at spp 4.  One step = one texture-
+    finetune iteration (render ['shaded'] at 2048^2 internal, MSE against a target image, backward to the texture weights), replayed
+    from a CUDA graph (3danimals_b200/graphs.py: the loop keeps its shapes).  Also reported: one rotation frame ['shaded','shading','kd']."""
+    import torch
+    import numpy as np
+    W = CONFIGS["c4"]
+    pipe = importlib.import_module("3danimals_b200.pipeline")
+    ops = importlib.import_module("3danimals_b200.ops")
+    syn = importlib.import_module("3danimals_b200.synthetic")
+    mesh_mod = importlib.import_module("3danimals_b200.render.mesh")
+    render_mod = importlib.import_module("3danimals_b200.render.render")
+    sk = importlib.import_module("3danimals_b200.geometry.skinning")
+    dm = importlib.import_module("3danimals_b200.geometry.dmtet")
+    graphs = importlib.import_module("3danimals_b200.graphs")
+    RES, IMG, SPP = W["grid_res"], W["image_res"], W["spp"]
+    v, t = syn.kuhn_tet_grid_torch(RES, dev)
+    v = (v * 7.0).contiguous()
+    sdf = torch.from_numpy(syn.sdf_horse(v.cpu().numpy(), sigma=0.0)).to(dev)[:, None].contiguous()
+    mt = dm.DMTet()
+    grid = mt.grid_for(t, v.shape[0])
+    del t
+    mvp, w2c, campos = (torch.from_numpy(x).to(dev) for x in syn.cameras(1, seed=3 + rank))
+    rng = np.random.RandomState(0)
+    w_kd = torch.from_numpy((rng.randn(3, 3) * 1.5).astype(np.float32)).to(dev)
+    light = pipe.FixedLight(torch.tensor([0.3, 0.5, 0.8, 0.4, 0.6], device=dev))
+    angles = torch.from_numpy(rng.uniform(-0.3, 0.3, size=(1, 1, 20, 3)).astype(np.float32)).to(dev)
+    with torch.no_grad():
+        verts, faces, uv_idx, faces32 = mt.extract(v, sdf, grid)
+        prior = mesh_mod.make_mesh(verts[None], faces[None], None, uv_idx[None], None, faces_i32=faces32)
+        bones, chain, _ = sk.estimate_bones(prior.v_pos[:, None].detach(), 8, n_legs=4, n_leg_bones=3, body_bones_mode="z_minmax_y+",
+                                            compute_kinematic_chain=True)
+        posed, _ = sk.skinning(prior.v_pos[:, None], bones, chain, angles, output_posed_bones=True, temperature=0.05)
+        inst = mesh_mod.make_mesh(posed[:, 0], prior.t_pos_idx, None, prior.t_tex_idx, None, faces_i32=prior.tri_i32())
+        inst.v_nrm
+    param = w_kd.clone().requires_grad_(True)
+
+    class TexField(torch.nn.Module):
+        bsdf = None
+        dense_only = True
+
+        def sample(self, x, feat=None):       # a PyTorch-owned texture field (as the reference's texture MLP is), trainable weights
+            y = torch.sigmoid(x @ param)
+            return torch.cat([y, y, y], -1)
+
+    material = TexField()
+
+    def frame(modes, mat):
+        return render_mod.render_mesh(None, inst, mvp, w2c, campos, mat, light, (IMG, IMG), spp=SPP, num_layers=1, msaa=True, background=None,
+                                      bsdf="diffuse", render_modes=list(modes), prior_mesh=prior, sparse_fields=False)
+
+    def finetune_it(tgt_u8):
+        tgt = torch.div(tgt_u8, 255.0)
+        loss = ((frame(("shaded",), material)[0] - tgt) ** 2).mean()
+        g, = torch.autograd.grad(loss, [param])
+        return loss.detach(), g
+
+    tgt_host = (torch.rand(1, 4, IMG, IMG) * 255).to(torch.uint8).pin_memory()
+    tgt_dev = tgt_host.to(dev)
+    cap = graphs.CapturedStep(finetune_it, [tgt_dev])
+    for _ in range(max(args.warmup, 3)):
+        cap(tgt_dev)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        cap(tgt_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_per_step = e0.elapsed_time(e1) / args.steps
+    # e2e: the target image crosses PCIe every iteration, the loss comes back
+    loss_host = torch.zeros(()).pin_memory()
+
+    def e2e_step():
+        out = cap(tgt_host.to(dev, non_blocking=True))
+        loss_host.copy_(out[0], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+    # eager per-call timing of the same iteration -> raster-backward group
+    ops.stats.reset(); ops.stats.timing = True; ops.stats.spin_cycles = 300000
+    timed_steps = 3
+    for _ in range(timed_steps):
+        finetune_it(tgt_dev)
+    torch.cuda.synchronize()
+    ops.stats.timing = False
+    durs = ops.stats.durations_ms()
+    launches_per_iter = ops.stats.launches // timed_steps     # the graph replays exactly the kernels of one eager iteration
+    with torch.no_grad():
+        rot = graphs.captured_render(inst, prior, pipe.AnalyticField(w_kd, True), light, (IMG, IMG), (mvp, w2c, campos), spp=SPP,
+                                     render_modes=("shaded", "shading", "kd"))
+        rot(mvp, w2c, campos)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            rot(mvp, w2c, campos)
+        e1.record()
+        torch.cuda.synchronize()
+        frame_ms = e0.elapsed_time(e1) / 20
+        n_cov = int((frame(("shaded",), material)[0][:, 3] > 0).sum().item()) * SPP * SPP
+    clocks = sampler.stop() if sampler else None
+    V, F = int(inst.v_pos.shape[1]), int(inst.t_pos_idx.shape[1])
+    st = dict(cfg="c4", B=1, HW=IMG * IMG * SPP * SPP, gHW=IMG * IMG, V=V, F=F, D=16, n_cov=n_cov, n_gb=2, Bq=1, timed_steps=timed_steps)
+    peak, peak_src = peaks()
+    roofline = build_roofline(durs, st, peak, peak_src)
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        # bounded CPU sample: the same finetune iteration through the oracle renderer on the device-extracted mesh (the res-256
+        # extraction itself - 100 M tets - is outside the loop in the reference too, visualize_results.py:353-396)
+        from oracle import torch_ref as T
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        pv, fc, pr = inst.v_pos.detach().cpu(), prior.t_pos_idx[0].cpu(), prior.v_pos.detach().cpu()
+        nrm = inst.v_nrm.detach().cpu()
+        wk = w_kd.cpu().clone().requires_grad_(True)
+        lt = light.params.cpu()
+        tg = torch.div(tgt_host, 255.0)
+
+        def shade(gb_tex, cam_normal, gbuf):
+            kd = torch.sigmoid(gb_tex @ wk)
+            a, b = T.directional_shade(lt, kd, cam_normal)
+            return {"shaded": a, "kd": kd, "shading": b}
+
+        t0 = time.perf_counter()
+        out = T.render_mesh(pv, nrm, fc, mvp.cpu(), w2c.cpu(), campos.cpu(), shade, (IMG, IMG), spp=SPP, render_modes=("shaded",), prior_v_pos=pr)
+        ((out["shaded"] - tg) ** 2).mean().backward()
+        dt = time.perf_counter() - t0
+        cpu = dict(value=1.0 / dt, unit="images/s", cores=cores, kind="port", seconds_per_step=dt,
+                   sample="one texture-finetune iteration (render ['shaded'] 512^2 x spp4 + backward to the texture weights) through the oracle "
+                          "renderer on the device-extracted mesh; extraction excluded on both sides")
+    if rank == 0:
+        run = dict(mesh_verts=V, mesh_faces=F, covered_pixels_internal=n_cov, rotation_frame_ms=frame_ms, field="analytic (M1a)",
+                   parallelism="replicas only (a single mesh is visualised)")
+        line = dict(metric=METRIC, value=world * 1.0 / (ms_per_step * 1e-3), unit="images/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=W, run=run,
+                    clocks=clocks, e2e=dict(value=world * 1.0 / (e2e_ms * 1e-3), unit="images/s", ms_per_step=e2e_ms, h2d_bytes_per_step=int(tgt_host.numel()),
+                                            d2h_bytes_per_step=4, what="pinned uint8 target image -> H2D -> /255 -> captured finetune iteration -> D2H loss"),
+                    gpu_launches=launches_per_iter * args.steps, roofline=roofline, cpu_baseline=cpu, impl="ours")
+        print(json.dumps(line))
 
 
 def main():
@@ -439,7 +670,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mlps", action="store_true", help="M1b: real CoordMLP texture/DINO fields instead of the analytic field")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--mlp-math", choices=["fp32", "tf32", "fp16"], default="fp32",
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="c1", help="BASELINE.json workload: c1 train_magicpony_horse (the metric's "
+                    "configuration, default), c2 train_magicpony_bird, c3 train_fauna, c4 visualize rotation / texture finetune")
+    ap.add_argument("--mlp-math", choices=["fp32", "tf32", "fp16"], default=None,
                     help="with --mlps: arithmetic of the PyTorch-owned field MLPs - fp32 (the horse configs), tf32 "
                          "(torch.backends.cuda.matmul.allow_tf32), fp16 autocast (the bird config, train_magicpony_bird.yaml:52)")
     ap.add_argument("--autograd-threads", choices=["on", "off"], default="off",

@@ -254,6 +254,33 @@ int b2a_gbuffer_bwd(const float* rast, int spp, const float* pos_clip, const int
                     void* workspace, size_t workspace_bytes, int workspace_is_zero, float* d_v_pos, float* d_v_nrm,
                     float* d_prior_pos, float* d_clip, float* d_w2c, float* d_campos, b2a_stream_t stream);
 
+/* Fused geometry half of render_mesh, one call per direction (the head of render_mesh, model/render/render.py:270-296:
+ * ru.xfm_points + dr.DepthPeeler(...).rasterize_next_layer(); render_layer's interpolations :160-209 + the shading / camera
+ * normal of shade :72-75; and the discontinuity analysis nvdiffrast's antialias re-runs inside every call, :264).
+ * fwd = b2a_xfm_points_fwd -> b2a_rasterize_fwd at [H*spp, W*spp] -> b2a_gbuffer_fwd at [H,W] -> b2a_antialias_prepare
+ * (skipped when aa_ctx is NULL); every buffer is the caller's: raster_ws (b2a_rasterize_workspace_bytes(B,F,H*spp,W*spp)),
+ * packed (b2a_gbuffer_pack_bytes), clip [B,V,4], rast [B,H*spp,W*spp,4], cov_list / cov_count (nullable, spp == 1),
+ * the nullable g-buffers [B,H,W,3], aa_ctx (b2a_antialias_workspace_bytes(B,H*spp,W*spp)).
+ * bwd = the g-buffer / rasterize adjoint over the covered-pixel list with the clip-space positions RECOMPUTED from v_pos and mtx
+ * (no pos_clip gather), then ONE per-vertex pass that adds the upstream clip gradient d_clip_up [B,V,4] (nullable: the
+ * antialias position gradient), applies the clip-transform adjoint and writes d_v_pos, d_v_nrm [B,V,3], d_prior_pos [Bq,V,3]
+ * (each nullable, WRITTEN) and accumulates d_mtx [B,16], d_w2c [B,16], d_campos [B,3] (nullable, zero-initialised by the
+ * caller).  workspace / workspace_is_zero as in b2a_gbuffer_bwd.  With every d_gb_* NULL only the clip-transform adjoint runs. */
+int b2a_render_geometry_fwd(const float* v_pos, const float* v_nrm, const float* prior_pos, int Bq, const float* mtx,
+                            const float* w2c, const float* campos, const int32_t* tri, const int32_t* opp, int two_sided,
+                            int B, int64_t V, int64_t F, int H, int W, int spp, void* raster_ws, size_t raster_ws_bytes,
+                            void* packed, size_t packed_bytes, float* clip, float* rast, int32_t* cov_list,
+                            int32_t* cov_count, float* gb_pos, float* gb_geo_nrm, float* gb_shading_nrm, float* gb_cam_nrm,
+                            float* gb_tex_pos, void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
+int b2a_render_geometry_bwd(const float* rast, int spp, const float* mtx, const int32_t* tri, const float* v_pos,
+                            const float* v_nrm, const float* prior_pos, int Bq, const float* w2c, const float* campos,
+                            int two_sided, int B, int64_t V, int64_t F, int H, int W, const void* packed, size_t packed_bytes,
+                            const int32_t* cov_list, const int32_t* cov_count, const float* d_gb_pos,
+                            const float* d_gb_geo_nrm, const float* d_gb_shading_nrm, const float* d_gb_cam_nrm,
+                            const float* d_gb_tex_pos, const float* d_clip_up, void* workspace, size_t workspace_bytes,
+                            int workspace_is_zero, float* d_v_pos, float* d_v_nrm, float* d_prior_pos, float* d_mtx,
+                            float* d_w2c, float* d_campos, b2a_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Mesh export: the text of a Wavefront OBJ file.  Replaces the per-line loops of write_obj
  * (model/render/obj.py:128-177); byte-identical output, including the reference's number format: every coordinate is

@@ -35,7 +35,8 @@ def forward(scene, images=None, sdf=None, angles=None, render_modes=("shaded", "
     normals = T.auto_normals_c if fast_normals else T.auto_normals
     verts, faces, uv_idx = T.marching_tets(pos, sdf, tets)
     bones, chain, aux = gnp.estimate_bones(verts.detach().numpy()[None, None], scene.n_body_bones, n_legs=4,
-                                           n_leg_bones=scene.n_leg_bones, body_bones_mode="z_minmax_y+")
+                                           n_leg_bones=scene.n_leg_bones, body_bones_mode=getattr(scene, "body_bones_mode", "z_minmax_y+"),
+                                           bone_y_threshold=getattr(scene, "bone_y_threshold", None))
     bones_t = torch.from_numpy(bones)
     posed, saux = T.skinning(verts[None, None], bones_t, chain, angles, temperature=0.05)
     v_nrm = normals(posed[:, 0], faces)
@@ -43,15 +44,25 @@ def forward(scene, images=None, sdf=None, angles=None, render_modes=("shaded", "
     out = T.render_mesh(posed[:, 0], v_nrm, faces, torch.from_numpy(scene.mvp[:B]), torch.from_numpy(scene.w2c[:B]),
                         torch.from_numpy(scene.campos[:B]), analytic_shader(scene, B), (r, r), spp=spp, background=background,
                         render_modes=render_modes, prior_v_pos=verts[None])
+    if getattr(scene, "second_render", False):      # FaunaModel.get_random_view_mask (Fauna.py:145-163)
+        def plain(gb_tex, cam_normal, gbuf):
+            kd = torch.ones(*gb_tex.shape[:-1], 3)
+            return {"shaded": kd, "kd": kd}
+        o2 = T.render_mesh(posed[:, 0], v_nrm, faces, torch.from_numpy(scene.mvp2[:B]), torch.from_numpy(scene.w2c2[:B]),
+                           torch.from_numpy(scene.campos2[:B]), plain, (256, 256), spp=1, background=None, render_modes=("shaded",),
+                           prior_v_pos=verts[None], two_sided_shading=False)
+        out["mask2"] = o2["shaded"][:, 3:]
     out.update(sdf=sdf, angles=angles, verts=verts, faces=faces, uv_idx=uv_idx, bones=bones_t, kinematic_chain=chain,
                posed=posed, posed_bones=saux["posed_bones"], v_nrm=v_nrm)
     return out
 
 
-def step(scene, d_shaded, d_dino, images=None):
+def step(scene, d_shaded, d_dino, images=None, d_mask=None):
     """One fwd+bwd pass on the CPU; returns (d_sdf, d_angles, outputs)."""
     B = scene.batch if images is None else images
     out = forward(scene, images=B)
-    torch.autograd.backward([out["shaded"], out["dino_pred"]],
-                            [torch.from_numpy(d_shaded[:B]), torch.from_numpy(d_dino[:B])])
+    outs, grads = [out["shaded"], out["dino_pred"]], [torch.from_numpy(d_shaded[:B]), torch.from_numpy(d_dino[:B])]
+    if "mask2" in out and d_mask is not None:
+        outs.append(out["mask2"]); grads.append(torch.from_numpy(d_mask[:B]))
+    torch.autograd.backward(outs, grads)
     return out["sdf"].grad, out["angles"].grad, out

@@ -13,6 +13,7 @@ EXPECTED = {
     "b2a_vertex_normals_bwd", "b2a_xfm_points_fwd", "b2a_xfm_points_bwd", "b2a_rasterize_workspace_bytes", "b2a_rasterize_fwd",
     "b2a_rasterize_bwd", "b2a_interpolate_fwd", "b2a_interpolate_bwd", "b2a_edge_adjacency_workspace_bytes", "b2a_edge_adjacency",
     "b2a_antialias_workspace_bytes", "b2a_antialias_prepare", "b2a_antialias_fwd", "b2a_antialias_bwd", "b2a_antialias_pair_fwd", "b2a_antialias_pair_bwd", "b2a_composite_up_fwd", "b2a_composite_up_bwd", "b2a_gbuffer_pack_bytes", "b2a_gbuffer_fwd", "b2a_gbuffer_bwd_workspace_bytes", "b2a_gbuffer_bwd",
+    "b2a_render_geometry_fwd", "b2a_render_geometry_bwd",
     "b2a_shade_directional_fwd", "b2a_shade_directional_bwd", "b2a_analytic_field_fwd", "b2a_analytic_field_bwd", "b2a_obj_text_bound", "b2a_obj_format",
 }
 

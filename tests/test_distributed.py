@@ -48,6 +48,16 @@ def _worker(rank, world, port, out_dir):
         nbytes = par.allreduce_gradients([d_sdf, None, d_bias], average=True)
         assert nbytes == (50 + 3) * 4
         np.save(os.path.join(out_dir, "r%d.npy" % rank), np.concatenate([d_sdf.numpy(), d_bias.numpy()]))
+        # bucketed form (bench.py's DDP stand-in): 3 buckets of <= 40 bytes over a 100-byte gradient set, launched one by one
+        gb = par.GradientBuckets(100, "cpu", bucket_bytes=40)
+        assert gb.active and [b.numel() for b in gb.buckets] == [10, 10, 5]
+        gb.view(2, 5).copy_(torch.arange(5.0) * (rank + 1))
+        gb.buckets[0].fill_(float(rank))
+        for i in (0, 2):
+            gb.launch(i)
+        gb.wait()
+        assert gb.bytes_reduced == 60 and gb.launched == []
+        np.save(os.path.join(out_dir, "b%d.npy" % rank), gb.flat.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -60,9 +70,14 @@ def test_gradient_allreduce_world2(tmp_path):
     per_image = np.random.RandomState(0).randn(6, 50).astype(np.float32)
     assert np.allclose(r0[:50], per_image.sum(0) / world, atol=1e-6)   # = DDP mean over ranks of the per-shard sums
     assert np.allclose(r0[50:], 1.5)
+    b0, b1 = np.load(tmp_path / "b0.npy"), np.load(tmp_path / "b1.npy")
+    assert np.array_equal(b0, b1) and np.allclose(b0[:10], 0.5) and np.allclose(b0[10:20], 0) and np.allclose(b0[20:], np.arange(5.0) * 1.5)
 
 
 def test_allreduce_is_noop_without_group():
     par = pkg("parallel")
     g = torch.ones(4)
     assert par.allreduce_gradients([g]) == 0 and torch.equal(g, torch.ones(4))
+    gb = par.GradientBuckets(64, "cpu", bucket_bytes=32)
+    gb.launch(0); gb.wait()
+    assert not gb.active and gb.bytes_reduced == 0 and len(gb.buckets) == 2
