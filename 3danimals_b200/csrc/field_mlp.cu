@@ -1,0 +1,681 @@
+// field_mlp.cu - the field MLPs of the pixel shader (reference model/networks/MLPs.py:34-101 CoordMLP, evaluated by
+// material.sample / dino_net.sample, model/render/render.py:54,61) on the 5th-generation tensor cores of sm_100a.
+//
+// This is the one dense contraction on the hot path: per covered pixel a harmonic embedding (63 / 51 wide) followed by
+// 8 (texture) or 5 (DINO) layers of 256 x 256, ~1.6 MFLOP per pixel forward.  The reference runs it as fp32 SIMT GEMMs; the horse
+// configs' contract is fp32 (1e-4), which single-pass bf16 / tf32 operands cannot hold once pre-activations grow
+// (profiles/mlp_precision_study_r1.txt).  Here every fp32 operand is split on the fly into two bf16 terms (x = hi + lo) and
+// each product is three tcgen05 MMAs with fp32 accumulation in tensor memory:   a.b ~ a_hi.b_hi + a_hi.b_lo + a_lo.b_hi
+// (the dropped lo.lo term is 2^-18 relative) - fp32-grade results at the bf16 rate / 3.  `passes = 1` keeps only hi.hi: the
+// arithmetic of the bird config's fp16/bf16 autocast (train_magicpony_bird.yaml:52).
+//
+// Kernels
+//   mlp_pack_weights   W [N,K] fp32 (optionally transposed) -> bf16 hi | lo images of the canonical K-major no-swizzle shared-
+//                      memory layout, one 32-wide K chunk after the other: the GEMM CTAs fetch them with ONE bulk async copy
+//                      (cp.async.bulk, TMA engine) per chunk and mbarrier transaction counts.
+//   mlp_rows_gemm      OUT[rows, N] = epilogue(A[rows, K] . W^T): A is fp32 in global memory (activations / gradients), staged
+//                      by the CTA's threads (optional ReLU on load, hi/lo split, 16-byte shared stores in the canonical layout),
+//                      128 rows per CTA, all N (<= 256) columns in one 128 x N accumulator of tensor memory; the MMAs of chunk i
+//                      overlap the staging of chunk i+1 (two stages, tcgen05.commit -> mbarrier); epilogue: tcgen05.ld 32 columns
+//                      per thread, + bias (vector or per-image row), ReLU-derivative mask, or sigmoid, 16-byte global stores.
+//   mlp_wgrad          dW[M, N] += P^T Q over a range of rows (both operands MN-major: row-major activations / gradients with
+//                      the reduction index slow), persistent over its K range, accumulator 128 x N in tensor memory, one
+//                      vector reduction per element at the end.
+//   mlp_embed fwd/bwd  harmonic embedding (HarmonicEmbedding.py: [x, sin(x f), cos(x f)], x mirrored to |x| first when the field
+//                      is symmetric) and its adjoint.
+//   mlp_colsum_segments  per-image column sums of a gradient (adjoint of the per-image bias of the first hidden layer).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int KC = 32;            // K chunk staged per pipeline step (two stages of 48 KB at N = 256: two CTAs per SM)
+constexpr int TILE_M = 128;       // rows per CTA = MMA M
+constexpr int GEMM_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// bulk async copy global -> shared (TMA engine, no tensor map), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// shared-memory matrix descriptor, no swizzle (layout type 0), version 1 (sm_100): start address, leading-dimension and
+// stride-dimension byte offsets in 16-byte units (cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
+           (1ull << 46);
+}
+// instruction descriptor, kind::f16: D fp32, A/B bf16, M x N, operand majors (0 = K-major, 1 = MN-major)
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 columns of fp32 accumulators: thread t of the warp receives row (lane base + t), columns [col, col + 32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+        "%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// x = hi + lo with both terms bf16 (round to nearest even); packs two consecutive elements
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo)
+{
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
+    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight packing.  Canonical K-major no-swizzle image of a [Npad rows, KC k] chunk: byte(n, k) = (k/8) * Npad*16 + n*16 + (k%8)*2
+// (core matrices of 8 rows x 16 bytes; consecutive row groups 128 bytes apart = SBO, the two K halves of an MMA Npad*16 bytes
+// apart = LBO).  packed = for every chunk c: [hi image | lo image], each Npad*64*2 bytes.
+// W is [N, K] row-major (transpose = 0: B[n][k] = W[n*ldw + k]) or its transpose (transpose = 1: B[n][k] = W[k*ldw + n]).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mlp_pack_weights_kernel(const float* __restrict__ W, int ldw, int N, int K, int transpose, int Npad, int Kpad,
+                                                               uint16_t* __restrict__ packed)
+{
+    const int64_t total = (int64_t)Npad * Kpad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Kpad), n = (int)(i / Kpad);
+        float w = 0.f;
+        if (n < N && k < K) w = transpose ? __ldg(W + (size_t)k * ldw + n) : __ldg(W + (size_t)n * ldw + k);
+        const __nv_bfloat16 h = __float2bfloat16_rn(w);
+        const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+        const int c = k / KC, kk = k % KC;
+        const size_t img = (size_t)Npad * KC;                                 // elements per hi (or lo) image
+        const size_t off = (size_t)c * 2 * img + (size_t)(kk / 8) * Npad * 8 + (size_t)n * 8 + (kk % 8);
+        packed[off] = __bfloat16_as_ushort(h);
+        packed[off + img] = __bfloat16_as_ushort(l);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Rows GEMM
+// ---------------------------------------------------------------------------------------------------------------------
+enum { EPI_BIAS = 0, EPI_MASK = 1, EPI_SIGMOID = 2 };
+
+struct GemmParams {
+    const float* A;            // [rows, lda] fp32
+    int64_t lda;
+    int64_t rows;
+    int K;                     // valid K (<= Kpad)
+    int Kpad;                  // multiple of KC
+    int N;                     // valid output columns
+    int Npad;                  // MMA N: multiple of 16, <= 256
+    const uint16_t* packed;    // mlp_pack_weights image
+    int relu_on_load;          // A := max(A, 0) while staging (the stored tensor is the pre-activation)
+    int passes;                // 3: hi.hi + hi.lo + lo.hi   1: hi.hi only
+    float* out;                // [rows, ldo]
+    int64_t ldo;
+    const float* bias;         // EPI_BIAS / EPI_SIGMOID: [N] (bias_rows == NULL) or [n_img, N] gathered through bias_rows; nullable
+    const int* bias_rows;      // [rows] image index of each row (nullable)
+    const float* mask_src;     // EPI_MASK: [rows, ldm] pre-activation whose sign gates the output
+    int64_t ldm;
+};
+
+constexpr int A_ITEMS = TILE_M * (KC / 8) / GEMM_THREADS;   // (row, 8-wide k group) items per thread and chunk
+
+// global -> registers: the fp32 values of this thread's items of chunk c (issued one chunk ahead of their use)
+__device__ __forceinline__ void a_load(const GemmParams& P, int64_t row0, int c, int tid, float (&v)[A_ITEMS][8])
+{
+#pragma unroll
+    for (int it = 0; it < A_ITEMS; it++) {
+        const int item = it * GEMM_THREADS + tid;
+        const int kg = item % (KC / 8), r = item / (KC / 8);
+        const int64_t row = row0 + r;
+        const int k0 = c * KC + kg * 8;
+        if (row < P.rows && k0 + 8 <= P.K) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(P.A + row * P.lda + k0));
+            const float4 y = __ldg(reinterpret_cast<const float4*>(P.A + row * P.lda + k0) + 1);
+            v[it][0] = x.x; v[it][1] = x.y; v[it][2] = x.z; v[it][3] = x.w; v[it][4] = y.x; v[it][5] = y.y; v[it][6] = y.z; v[it][7] = y.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[it][j] = (row < P.rows && k0 + j < P.K) ? __ldg(P.A + row * P.lda + k0 + j) : 0.f;
+        }
+    }
+}
+// registers -> hi / lo images of the stage (canonical K-major layout: byte(r, k) = (k/8) * TILE_M*16 + r*16 + (k%8)*2)
+__device__ __forceinline__ void a_store(const GemmParams& P, uint8_t* st, uint32_t a_bytes, int tid, float (&v)[A_ITEMS][8])
+{
+#pragma unroll
+    for (int it = 0; it < A_ITEMS; it++) {
+        const int item = it * GEMM_THREADS + tid;
+        const int kg = item % (KC / 8), r = item / (KC / 8);
+        if (P.relu_on_load) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[it][j] = fmaxf(v[it][j], 0.f);
+        }
+        uint4 hi, lo;
+        split2(v[it][0], v[it][1], hi.x, lo.x); split2(v[it][2], v[it][3], hi.y, lo.y);
+        split2(v[it][4], v[it][5], hi.z, lo.z); split2(v[it][6], v[it][7], hi.w, lo.w);
+        const uint32_t off = (uint32_t)kg * (TILE_M * 16) + (uint32_t)r * 16;
+        *reinterpret_cast<uint4*>(st + off) = hi;
+        *reinterpret_cast<uint4*>(st + a_bytes + off) = lo;
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmParams P)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // stage s: [A_hi 8 KB | A_lo 8 KB | B_hi Npad*64 B | B_lo Npad*64 B]
+    const uint32_t a_bytes = TILE_M * KC * 2, b_bytes = (uint32_t)P.Npad * KC * 2;
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    __shared__ __align__(8) uint64_t full_b[2], mma_done[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
+    const uint32_t tmem_cols = P.Npad <= 32 ? 32u : (P.Npad <= 64 ? 64u : (P.Npad <= 128 ? 128u : 256u));
+    const int nchunks = P.Kpad / KC;
+
+    float va[A_ITEMS][8];
+    a_load(P, row0, 0, tid, va);           // chunk 0 is on its way while the barriers / tensor memory are set up
+    if (tid == 0) {
+        mbar_init(&full_b[0], 1); mbar_init(&full_b[1], 1);
+        mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t idesc = instr_desc(TILE_M, P.Npad, 0, 0);
+
+    for (int c = 0; c < nchunks; c++) {
+        const int s = c & 1;
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        if (c >= 2) mbar_wait(&mma_done[s], ((c >> 1) - 1) & 1);        // the MMAs that read this stage (chunk c-2) have completed
+        if (tid == 0) {                                                  // weights of this chunk: one bulk copy (hi | lo are adjacent)
+            mbar_expect_tx(&full_b[s], 2 * b_bytes);
+            bulk_g2s(st + 2 * a_bytes, P.packed + (size_t)c * P.Npad * KC * 2, 2 * b_bytes, &full_b[s]);
+        }
+        a_store(P, st, a_bytes, tid, va);                                // activations of chunk c: registers -> hi / lo images
+        if (c + 1 < nchunks) a_load(P, row0, c + 1, tid, va);            // chunk c+1: loads in flight across the sync and the MMA issue
+        fence_proxy_async();            // generic-proxy shared stores -> visible to the tensor core's async proxy
+        __syncthreads();
+        if (tid == 0) {
+            mbar_wait(&full_b[s], (c >> 1) & 1);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(st), a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
+            const uint32_t a_lbo = TILE_M * 16, b_lbo = (uint32_t)P.Npad * 16;
+#pragma unroll
+            for (int ks = 0; ks < KC / 16; ks++) {
+                const uint64_t dah = smem_desc(a_hi + ks * 2 * a_lbo, a_lbo, 128), dal = smem_desc(a_lo + ks * 2 * a_lbo, a_lbo, 128);
+                const uint64_t dbh = smem_desc(b_hi + ks * 2 * b_lbo, b_lbo, 128), dbl = smem_desc(b_lo + ks * 2 * b_lbo, b_lbo, 128);
+                umma(tmem_d, dah, dbh, idesc, (c | ks) != 0);
+                if (P.passes == 3) {
+                    umma(tmem_d, dah, dbl, idesc, 1);
+                    umma(tmem_d, dal, dbh, idesc, 1);
+                }
+            }
+            umma_commit(&mma_done[s]);      // arrives when every MMA issued so far has completed (implies fence::before_thread_sync)
+        }
+    }
+    // all MMAs done: the last commit covers every earlier one
+    mbar_wait(&mma_done[(nchunks - 1) & 1], ((nchunks - 1) >> 1) & 1);
+    tc_fence_after();
+
+    // Epilogue.  Warp w reads the 32 accumulator lanes of its quadrant (w % 4): thread t holds 32 consecutive columns of row
+    // 32*(w%4) + t.  The 32 x 32 block goes through a padded shared-memory tile (the pipeline stages are free now) so that global
+    // memory sees whole 128-byte row segments: lane j handles column c0 + j of one row per instruction (4 fully-written sectors
+    // instead of 32 half-written ones); the ReLU-derivative mask is read the same way.  Warps 0-3 take the even column groups, 4-7 the odd.
+    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+    const int quad = warp & 3;
+    const int64_t wrow0 = row0 + quad * 32;
+    const int ngroups = (P.Npad + 31) / 32;
+    for (int g = warp >> 2; g < ngroups; g += 2) {
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 32), v);
+        const int c0 = g * 32;
+        if (EPI == EPI_BIAS || EPI == EPI_SIGMOID) {
+            const int64_t row = wrow0 + lane;
+            if (P.bias && row < P.rows) {
+                const float* b = P.bias + (P.bias_rows ? (size_t)__ldg(P.bias_rows + row) * P.N : 0);
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (c0 + j < P.N) v[j] += __ldg(b + c0 + j);
+            }
+            if (EPI == EPI_SIGMOID) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = 1.f / (1.f + expf(-v[j]));
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j++) tile[lane * 33 + j] = v[j];
+        __syncwarp();
+        const int col = c0 + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+            const int64_t row = wrow0 + r;
+            if (row < P.rows && col < P.N) {
+                float x = tile[r * 33 + lane];
+                if (EPI == EPI_MASK && !(__ldg(P.mask_src + row * P.ldm + col) > 0.f)) x = 0.f;
+                P.out[row * P.ldo + col] = x;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+int gemm_smem_bytes(int Npad) { return 2 * (2 * TILE_M * KC * 2 + 2 * Npad * KC * 2); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient: C[M, N] += sum over rows r of P[r, m] * Q[r, n]   (dW = dz^T . a)
+// Both operands are row-major with the reduction index (the row) slow, i.e. MN-major for the tensor core.  Canonical MN-major
+// no-swizzle image of a [KC rows, MN columns] chunk: byte(mn, k) = (k/8) * MN*16 + (mn/8) * 128 + (k%8) * 16 + (mn%8) * 2
+// (core matrix = 8 k-rows of 16 bytes = 8 consecutive mn elements; mn groups 128 bytes apart = SBO, k groups MN*16 bytes apart = LBO).
+// A warp stages (8 k-rows) x (32 mn columns) per item: lane = kq + 8*mg reads 32 bytes of row kq (128 contiguous bytes per row
+// over the four mg lanes) and stores 16 bytes per image; the warp's stores cover 512 contiguous bytes (conflict-free).
+// One CTA = one 128-wide M tile x all N columns over a contiguous range of rows; accumulator in tensor memory for the whole range.
+// ---------------------------------------------------------------------------------------------------------------------
+struct WgradParams {
+    const float* Pm;  int64_t ldp;  int relu_p;      // [rows, >= M]
+    const float* Qm;  int64_t ldq;  int relu_q;      // [rows, >= N]
+    int64_t rows;
+    int M, N, Npad;                                   // M: valid columns of P (tiles of 128), N: valid columns of Q
+    int passes;
+    float* out;  int64_t ldo;  int transpose_out;     // out[m*ldo + n] += C[m][n]   (transpose_out: out[n*ldo + m])
+    int64_t rows_per_cta;                             // multiple of KC
+};
+
+template <int ITEMS>
+__device__ __forceinline__ void mn_load(const float* __restrict__ X, int64_t ldx, int64_t rows, int ncols, int64_t r0, int col0, int warp, int lane,
+                                        float (&v)[ITEMS][8])
+{
+    const int kq = lane & 7, mg = lane >> 3;
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        const int witem = it * (GEMM_THREADS / 32) + warp;        // (k group, quad of mn groups)
+        const int kg = witem & (KC / 8 - 1), mq = witem / (KC / 8);
+        const int64_t row = r0 + kg * 8 + kq;
+        const int col = col0 + mq * 32 + mg * 8;
+        if (row < rows && col + 8 <= ncols) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(X + row * ldx + col));
+            const float4 y = __ldg(reinterpret_cast<const float4*>(X + row * ldx + col) + 1);
+            v[it][0] = x.x; v[it][1] = x.y; v[it][2] = x.z; v[it][3] = x.w; v[it][4] = y.x; v[it][5] = y.y; v[it][6] = y.z; v[it][7] = y.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[it][j] = (row < rows && col + j < ncols) ? __ldg(X + row * ldx + col + j) : 0.f;
+        }
+    }
+}
+template <int ITEMS>
+__device__ __forceinline__ void mn_store(uint8_t* hi_img, uint8_t* lo_img, int MN, int relu, int warp, int lane, float (&v)[ITEMS][8])
+{
+    const int kq = lane & 7, mg = lane >> 3;
+#pragma unroll
+    for (int it = 0; it < ITEMS; it++) {
+        const int witem = it * (GEMM_THREADS / 32) + warp;
+        const int kg = witem & (KC / 8 - 1), mq = witem / (KC / 8);
+        if (mq * 32 >= MN) continue;                               // narrow operands: fewer warp items than warps
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[it][j] = fmaxf(v[it][j], 0.f);
+        }
+        uint4 hi, lo;
+        split2(v[it][0], v[it][1], hi.x, lo.x); split2(v[it][2], v[it][3], hi.y, lo.y);
+        split2(v[it][4], v[it][5], hi.z, lo.z); split2(v[it][6], v[it][7], hi.w, lo.w);
+        const uint32_t off = (uint32_t)kg * (MN * 16) + (uint32_t)(mq * 4 + mg) * 128 + (uint32_t)kq * 16;
+        *reinterpret_cast<uint4*>(hi_img + off) = hi;
+        *reinterpret_cast<uint4*>(lo_img + off) = lo;
+    }
+}
+
+// QI = Q items per thread = (KC/8) * (Npad/32) / 8 warps: 4 for Npad 256, 2 for 128, 1 for 64; Npad <= 32 -> 1 (half the warps idle)
+template <int QI>
+__global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_wgrad_kernel(WgradParams W)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int PI = (KC / 8) * (TILE_M / 32) / (GEMM_THREADS / 32);     // P items per thread (2)
+    const uint32_t p_bytes = KC * TILE_M * 2, q_bytes = (uint32_t)KC * W.Npad * 2;
+    const uint32_t stage_bytes = 2 * p_bytes + 2 * q_bytes;
+    __shared__ __align__(8) uint64_t mma_done[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * TILE_M;
+    const int64_t r_begin = (int64_t)blockIdx.x * W.rows_per_cta;
+    int64_t r_end = r_begin + W.rows_per_cta;
+    if (r_end > W.rows) r_end = W.rows;
+    if (r_begin >= r_end) return;
+    const int nchunks = (int)((r_end - r_begin + KC - 1) / KC);
+    const uint32_t tmem_cols = W.Npad <= 32 ? 32u : (W.Npad <= 64 ? 64u : (W.Npad <= 128 ? 128u : 256u));
+
+    float vp[PI][8], vq[QI][8];
+    mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r_begin, m0, warp, lane, vp);
+    mn_load<QI>(W.Qm, W.ldq, r_end, W.N, r_begin, 0, warp, lane, vq);
+    if (tid == 0) {
+        mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (warp == 0) tmem_alloc(&tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+    const uint32_t idesc = instr_desc(TILE_M, W.Npad, 1, 1);
+
+    for (int c = 0; c < nchunks; c++) {
+        const int s = c & 1;
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        if (c >= 2) mbar_wait(&mma_done[s], ((c >> 1) - 1) & 1);
+        mn_store<PI>(st, st + p_bytes, TILE_M, W.relu_p, warp, lane, vp);
+        mn_store<QI>(st + 2 * p_bytes, st + 2 * p_bytes + q_bytes, W.Npad, W.relu_q, warp, lane, vq);
+        if (c + 1 < nchunks) {
+            const int64_t r0 = r_begin + (int64_t)(c + 1) * KC;
+            mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r0, m0, warp, lane, vp);
+            mn_load<QI>(W.Qm, W.ldq, r_end, W.N, r0, 0, warp, lane, vq);
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t p_hi = smem_u32(st), p_lo = p_hi + p_bytes, q_hi = p_hi + 2 * p_bytes, q_lo = q_hi + q_bytes;
+            const uint32_t p_lbo = TILE_M * 16, q_lbo = (uint32_t)W.Npad * 16;
+#pragma unroll
+            for (int ks = 0; ks < KC / 16; ks++) {
+                const uint64_t dph = smem_desc(p_hi + ks * 2 * p_lbo, p_lbo, 128), dpl = smem_desc(p_lo + ks * 2 * p_lbo, p_lbo, 128);
+                const uint64_t dqh = smem_desc(q_hi + ks * 2 * q_lbo, q_lbo, 128), dql = smem_desc(q_lo + ks * 2 * q_lbo, q_lbo, 128);
+                umma(tmem_d, dph, dqh, idesc, (c | ks) != 0);
+                if (W.passes == 3) {
+                    umma(tmem_d, dph, dql, idesc, 1);
+                    umma(tmem_d, dpl, dqh, idesc, 1);
+                }
+            }
+            umma_commit(&mma_done[s]);
+        }
+    }
+    mbar_wait(&mma_done[(nchunks - 1) & 1], ((nchunks - 1) >> 1) & 1);
+    tc_fence_after();
+    // epilogue: thread t of quadrant q holds row m0 + 32q + t, 32 consecutive n: one reduction per element into the shared result
+    const int quad = warp & 3;
+    const int m = m0 + quad * 32 + lane;
+    const int ngroups = (W.Npad + 31) / 32;
+    for (int g = warp >> 2; g < ngroups; g += 2) {
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 32), v);
+        if (m < W.M) {
+            const int n0 = g * 32;
+            if (!W.transpose_out && n0 + 32 <= W.N && (W.ldo & 3) == 0) {
+                float* o = W.out + (size_t)m * W.ldo + n0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(o + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (n0 + j < W.N) atomicAdd(W.transpose_out ? W.out + (size_t)(n0 + j) * W.ldo + m : W.out + (size_t)m * W.ldo + n0 + j, v[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Harmonic embedding (model/networks/HarmonicEmbedding.py; CoordMLP.forward :75-84): E = [x', sin(x' f_0..f_{n-1}), cos(...)],
+// x' = (|x|, y, z) when the field is symmetric; freq f_i = scalar * 2^i; layout of the reference: for the sin block the index is
+// d * n + i (d = coordinate), then the cos block.  E rows are padded to ldE floats (zeros).  Accurate sinf / cosf: arguments reach
+// ~1e3 rad at the top octave.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mlp_embed_fwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int n_harm, float scalar, int symmetrize,
+                                                            int concat_pts, float* __restrict__ E, int64_t ldE)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float p[3] = {__ldg(x + r * ldx), __ldg(x + r * ldx + 1), __ldg(x + r * ldx + 2)};
+    if (symmetrize) p[0] = fabsf(p[0]);
+    float* e = E + r * ldE;
+    int o = 0;
+    if (concat_pts) { e[0] = p[0]; e[1] = p[1]; e[2] = p[2]; o = 3; }
+    const int nh3 = 3 * n_harm;
+    for (int d = 0; d < 3; d++) {
+        float f = scalar;
+        for (int i = 0; i < n_harm; i++) {
+            const float a = p[d] * f;
+            e[o + d * n_harm + i] = sinf(a);
+            e[o + nh3 + d * n_harm + i] = cosf(a);
+            f *= 2.f;
+        }
+    }
+    for (int k = o + 2 * nh3; k < ldE; k++) e[k] = 0.f;
+}
+
+// d_x[d] = dE[x'_d] + sum_i f_i (dE[sin] cos(a) - dE[cos] sin(a)); symmetric fields: d_x[0] *= sign(x[0]) (torch.abs: 0 at 0)
+__global__ void __launch_bounds__(256) mlp_embed_bwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int n_harm, float scalar, int symmetrize,
+                                                            int concat_pts, const float* __restrict__ dE, int64_t ldE, float* __restrict__ d_x, int64_t lddx)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float x0 = __ldg(x + r * ldx);
+    float p[3] = {x0, __ldg(x + r * ldx + 1), __ldg(x + r * ldx + 2)};
+    if (symmetrize) p[0] = fabsf(p[0]);
+    const float* g = dE + r * ldE;
+    const int o = concat_pts ? 3 : 0, nh3 = 3 * n_harm;
+    for (int d = 0; d < 3; d++) {
+        float acc = concat_pts ? __ldg(g + d) : 0.f;
+        float f = scalar;
+        for (int i = 0; i < n_harm; i++) {
+            const float a = p[d] * f;
+            acc += f * (__ldg(g + o + d * n_harm + i) * cosf(a) - __ldg(g + o + nh3 + d * n_harm + i) * sinf(a));
+            f *= 2.f;
+        }
+        if (d == 0 && symmetrize) acc = x0 > 0.f ? acc : (x0 < 0.f ? -acc : 0.f);
+        d_x[r * lddx + d] = acc;
+    }
+}
+
+// out[s, n] = sum of G[r, n] over the rows r of segment s = [seg_start[s], seg_start[s+1]) - the adjoint of a per-image bias when
+// the rows are grouped by image.  grid (segments, ceil(N/32)); 8 warps stride the segment's rows, lanes take 32 columns.
+__global__ void __launch_bounds__(256) mlp_colsum_segments_kernel(const float* __restrict__ G, int64_t ldg, const int64_t* __restrict__ seg_start, int N,
+                                                                  float* __restrict__ out)
+{
+    __shared__ float part[8][32];
+    const int sgm = blockIdx.x, n = blockIdx.y * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5;
+    const int64_t a = seg_start[sgm], b = seg_start[sgm + 1];
+    float acc = 0.f;
+    if (n < N)
+        for (int64_t r = a + warp; r < b; r += 8) acc += __ldg(G + r * ldg + n);
+    part[warp][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (warp == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += part[w][threadIdx.x];
+        out[(size_t)sgm * N + n] = t;
+    }
+}
+
+}  // namespace
+
+B2A_API int b2a_mlp_packed_bytes(int N, int K, size_t* bytes)
+{
+    B2A_CHECK_ARG(bytes && N > 0 && N <= 256 && K > 0, "shape");
+    const int Npad = (N + 15) / 16 * 16, Kpad = (K + KC - 1) / KC * KC;
+    *bytes = (size_t)Npad * Kpad * 2 * sizeof(uint16_t);
+    return 0;
+}
+
+B2A_API int b2a_mlp_pack_weights(const float* W, int64_t ldw, int N, int K, int transpose, void* packed, size_t packed_bytes, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    size_t need;
+    int rc = b2a_mlp_packed_bytes(N, K, &need);
+    if (rc) return rc;
+    B2A_CHECK_ARG(W && packed && packed_bytes >= need && ((uintptr_t)packed & 15) == 0, "packed buffer");
+    const int Npad = (N + 15) / 16 * 16, Kpad = (K + KC - 1) / KC * KC;
+    mlp_pack_weights_kernel<<<b2a_blocks((int64_t)Npad * Kpad, 256), 256, 0, stream>>>(W, (int)ldw, N, K, transpose, Npad, Kpad, (uint16_t*)packed);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+// out[rows, N] = epilogue(op(A)[rows, K] . Wpacked^T).  epilogue 0: + bias (vector [N], or row bias_rows[r] of a [n_img, N] table;
+// nullable); 1: zero where mask_src[r, n] <= 0 (the ReLU derivative of the stored pre-activation); 2: sigmoid(. + bias).
+// relu_on_load: op(A) = max(A, 0).  passes: 3 (fp32-grade split products) or 1 (single bf16 product).
+B2A_API int b2a_mlp_rows_gemm(const float* A, int64_t lda, int64_t rows, int K, const void* packed, int N, int relu_on_load, int passes, int epilogue,
+                              const float* bias, const int32_t* bias_rows, const float* mask_src, int64_t ldm, float* out, int64_t ldo,
+                              b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(A && packed && out, "null pointer");
+    B2A_CHECK_ARG(rows >= 0 && K > 0 && N > 0 && N <= 256 && lda >= K && ldo >= N && (passes == 1 || passes == 3), "shape");
+    B2A_CHECK_ARG(epilogue >= 0 && epilogue <= 2 && (epilogue != EPI_MASK || (mask_src && ldm >= N)), "epilogue");
+    B2A_CHECK_ARG(((uintptr_t)A & 15) == 0 && (lda & 3) == 0 && ((uintptr_t)packed & 15) == 0 && ((uintptr_t)out & 15) == 0, "alignment (16 bytes, lda % 4 == 0)");
+    if (rows == 0) return 0;
+    GemmParams P;
+    P.A = A; P.lda = lda; P.rows = rows; P.K = K; P.Kpad = (K + KC - 1) / KC * KC; P.N = N; P.Npad = (N + 15) / 16 * 16;
+    P.packed = (const uint16_t*)packed; P.relu_on_load = relu_on_load; P.passes = passes; P.out = out; P.ldo = ldo; P.bias = bias;
+    P.bias_rows = bias_rows; P.mask_src = mask_src; P.ldm = ldm;
+    const int smem = gemm_smem_bytes(P.Npad);
+    const unsigned grid = b2a_blocks(rows, TILE_M);
+#define MLP_LAUNCH(E)                                                                                                     \
+    do {                                                                                                                  \
+        B2A_CUDA_OK(cudaFuncSetAttribute(mlp_rows_gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
+        mlp_rows_gemm_kernel<E><<<grid, GEMM_THREADS, smem, stream>>>(P);                                                 \
+    } while (0)
+    if (epilogue == EPI_BIAS) MLP_LAUNCH(EPI_BIAS);
+    else if (epilogue == EPI_MASK) MLP_LAUNCH(EPI_MASK);
+    else MLP_LAUNCH(EPI_SIGMOID);
+#undef MLP_LAUNCH
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+// C[M, N] += P^T Q over all rows: out[m*ldo + n] (or out[n*ldo + m] with transpose_out) is ACCUMULATED with reductions - the caller
+// zero-initialises it.  relu_p / relu_q: the operand is max(., 0) of the stored tensor.  M, N <= 256.
+B2A_API int b2a_mlp_wgrad(const float* P, int64_t ldp, int relu_p, const float* Q, int64_t ldq, int relu_q, int64_t rows, int M, int N, int passes,
+                          float* out, int64_t ldo, int transpose_out, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(P && Q && out, "null pointer");
+    B2A_CHECK_ARG(rows >= 0 && M > 0 && M <= 256 && N > 0 && N <= 256 && ldp >= M && ldq >= N && (passes == 1 || passes == 3), "shape");
+    B2A_CHECK_ARG(((uintptr_t)P & 15) == 0 && ((uintptr_t)Q & 15) == 0 && (ldp & 3) == 0 && (ldq & 3) == 0 && ((uintptr_t)out & 15) == 0, "alignment");
+    if (rows == 0) return 0;
+    WgradParams W;
+    W.Pm = P; W.ldp = ldp; W.relu_p = relu_p; W.Qm = Q; W.ldq = ldq; W.relu_q = relu_q; W.rows = rows; W.M = M; W.N = N;
+    W.Npad = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));      // whole warp items of 32 columns
+    W.passes = passes; W.out = out; W.ldo = ldo; W.transpose_out = transpose_out;
+    const int mtiles = (M + TILE_M - 1) / TILE_M;
+    int64_t nsplit = (2 * 148) / mtiles;                                   // two CTAs per SM
+    int64_t per = (rows + nsplit - 1) / nsplit;
+    per = (per + KC - 1) / KC * KC;
+    if (per < 8 * KC) per = 8 * KC;
+    W.rows_per_cta = per;
+    nsplit = (rows + per - 1) / per;
+    const int smem = 2 * (2 * KC * TILE_M * 2 + 2 * KC * W.Npad * 2);
+    const dim3 grid((unsigned)nsplit, (unsigned)mtiles);
+#define WG_LAUNCH(QI)                                                                                                \
+    do {                                                                                                             \
+        B2A_CUDA_OK(cudaFuncSetAttribute(mlp_wgrad_kernel<QI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        mlp_wgrad_kernel<QI><<<grid, GEMM_THREADS, smem, stream>>>(W);                                               \
+    } while (0)
+    if (W.Npad == 256) WG_LAUNCH(4);
+    else if (W.Npad == 128) WG_LAUNCH(2);
+    else WG_LAUNCH(1);
+#undef WG_LAUNCH
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+B2A_API int b2a_mlp_embed_fwd(const float* x, int64_t ldx, int64_t rows, int n_harmonic, float scalar, int symmetrize, int concat_pts, float* E,
+                              int64_t ldE, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(x && E && rows >= 0 && n_harmonic >= 0 && ldx >= 3 && ldE >= 6 * n_harmonic + (concat_pts ? 3 : 0), "shape");
+    if (rows) mlp_embed_fwd_kernel<<<b2a_blocks(rows, 256), 256, 0, stream>>>(x, ldx, rows, n_harmonic, scalar, symmetrize, concat_pts, E, ldE);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+B2A_API int b2a_mlp_embed_bwd(const float* x, int64_t ldx, int64_t rows, int n_harmonic, float scalar, int symmetrize, int concat_pts, const float* dE,
+                              int64_t ldE, float* d_x, int64_t lddx, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(x && dE && d_x && rows >= 0 && n_harmonic >= 0 && ldx >= 3 && lddx >= 3 && ldE >= 6 * n_harmonic + (concat_pts ? 3 : 0), "shape");
+    if (rows) mlp_embed_bwd_kernel<<<b2a_blocks(rows, 256), 256, 0, stream>>>(x, ldx, rows, n_harmonic, scalar, symmetrize, concat_pts, dE, ldE, d_x, lddx);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+// out[s, n] (WRITTEN) = sum over rows seg_start[s] <= r < seg_start[s+1] of G[r, n]; seg_start: device int64 [n_seg + 1]
+B2A_API int b2a_mlp_colsum_segments(const float* G, int64_t ldg, const int64_t* seg_start, int n_seg, int N, float* out, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(G && seg_start && out && n_seg > 0 && N > 0 && ldg >= N, "shape");
+    mlp_colsum_segments_kernel<<<dim3(n_seg, (N + 31) / 32), 256, 0, stream>>>(G, ldg, seg_start, N, out);
+    B2A_LAUNCH_OK();
+    return 0;
+}

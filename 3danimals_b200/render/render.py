@@ -12,6 +12,7 @@ import os
 
 import torch
 
+from .. import field_mlp
 from .. import ops
 
 # A/B switch for measurements: B2A_FUSE_AA_PAIR=0 renders the training pair of keys with two single-key launches
@@ -98,7 +99,10 @@ def _sample_field(net, gb_tex_pos, feat, sparse):
         return net.sample(gb_tex_pos, feat=feat)
     idx, img, (B, h, w) = sparse
     x = gb_tex_pos.reshape(-1, gb_tex_pos.shape[-1]).index_select(0, idx)
-    if _splits_feat(net, feat):
+    if field_mlp.supported(net, x, feat):
+        # CoordMLP on the tensor cores (csrc/field_mlp.cu): tcgen05 GEMMs over the covered rows, forward and backward
+        y = field_mlp.coord_mlp_rows(net, x, None if feat is None else (feat if feat.shape[0] == B else feat.expand(B, -1)), img, B)
+    elif _splits_feat(net, feat):
         y = _coord_mlp_rows(net, x, feat if feat.shape[0] == B else feat.expand(B, -1), img)
     else:
         f = None

@@ -282,6 +282,37 @@ int b2a_render_geometry_bwd(const float* rast, int spp, const float* mtx, const 
                             float* d_w2c, float* d_campos, b2a_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Field MLPs on the tensor cores (tcgen05 + tensor memory).  Replaces the fp32 GEMMs of CoordMLP.forward
+ * (model/networks/MLPs.py:34-101) behind material.sample / dino_net.sample (model/render/render.py:54,61) on the covered
+ * rows.  Every fp32 operand is split into two bf16 terms and each product is three MMAs with fp32 accumulation
+ * (passes = 3; fp32-grade) or one (passes = 1; the arithmetic of the reference's autocast configs).
+ * pack_weights: W [N,K] fp32 row-major with row stride ldw (transpose = 1: W is [K,N] and its transpose is packed) ->
+ * `packed` (b2a_mlp_packed_bytes), the shared-memory image the GEMM fetches with bulk async copies; N <= 256.
+ * rows_gemm: out[rows,N] (row stride ldo) = epilogue(op(A)[rows,K] . W^T) with A fp32 (row stride lda, lda % 4 == 0);
+ * relu_on_load: op = max(., 0).  epilogue 0: + bias (nullable; [N], or row bias_rows[r] of a [*,N] table when bias_rows is
+ * given); 1: zero where mask_src[r,n] <= 0 (row stride ldm); 2: sigmoid(. + bias).
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_mlp_packed_bytes(int N, int K, size_t* bytes);
+int b2a_mlp_pack_weights(const float* W, int64_t ldw, int N, int K, int transpose, void* packed, size_t packed_bytes,
+                         b2a_stream_t stream);
+int b2a_mlp_rows_gemm(const float* A, int64_t lda, int64_t rows, int K, const void* packed, int N, int relu_on_load,
+                      int passes, int epilogue, const float* bias, const int32_t* bias_rows, const float* mask_src,
+                      int64_t ldm, float* out, int64_t ldo, b2a_stream_t stream);
+/* wgrad: out[m*ldo + n] (transpose_out: out[n*ldo + m]) += sum_r op(P)[r,m] * op(Q)[r,n] over all rows (the weight gradient
+ * dz^T . a of a Linear layer); out is ACCUMULATED with reductions and must be zero-initialised by the caller; M, N <= 256.
+ * embed fwd / bwd: the harmonic embedding in front of CoordMLP.in_layer (model/networks/HarmonicEmbedding.py; MLPs.py:75-84):
+ * E[r] = [x', sin(x' f), cos(x' f)] padded with zeros to ldE floats, x' = (|x|, y, z) when symmetrize; and its adjoint.
+ * colsum_segments: out[s,n] = sum of G[r,n] over seg_start[s] <= r < seg_start[s+1] (adjoint of a per-image bias). */
+int b2a_mlp_wgrad(const float* P, int64_t ldp, int relu_p, const float* Q, int64_t ldq, int relu_q, int64_t rows, int M,
+                  int N, int passes, float* out, int64_t ldo, int transpose_out, b2a_stream_t stream);
+int b2a_mlp_embed_fwd(const float* x, int64_t ldx, int64_t rows, int n_harmonic, float scalar, int symmetrize,
+                      int concat_pts, float* E, int64_t ldE, b2a_stream_t stream);
+int b2a_mlp_embed_bwd(const float* x, int64_t ldx, int64_t rows, int n_harmonic, float scalar, int symmetrize,
+                      int concat_pts, const float* dE, int64_t ldE, float* d_x, int64_t lddx, b2a_stream_t stream);
+int b2a_mlp_colsum_segments(const float* G, int64_t ldg, const int64_t* seg_start, int n_seg, int N, float* out,
+                            b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Mesh export: the text of a Wavefront OBJ file.  Replaces the per-line loops of write_obj
  * (model/render/obj.py:128-177); byte-identical output, including the reference's number format: every coordinate is
  * '{}'.format(np.float32) = Python's repr of the value widened to double, the texcoord v is flipped in float32 first
