@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmPara
     }
     // all MMAs done: the last commit covers every earlier one
     mbar_wait(&mma_done[(nchunks - 1) & 1], ((nchunks - 1) >> 1) & 1);
+    __syncwarp();                   // tcgen05.ld is .sync.aligned: the K-tail path of the staging and the spin loop can leave lanes diverged
     tc_fence_after();
 
     // Epilogue.  Warp w reads the 32 accumulator lanes of its quadrant (w % 4): thread t holds 32 consecutive columns of row
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmPara
     const int ngroups = (P.Npad + 31) / 32;
     for (int g = warp >> 2; g < ngroups; g += 2) {
         float v[32];
+        __syncwarp();
         tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 32), v);
         const int c0 = g * 32;
         if (EPI == EPI_BIAS || EPI == EPI_SIGMOID) {
@@ -459,6 +461,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_wgrad_kernel(WgradParams 
         }
     }
     mbar_wait(&mma_done[(nchunks - 1) & 1], ((nchunks - 1) >> 1) & 1);
+    __syncwarp();
     tc_fence_after();
     // epilogue: thread t of quadrant q holds row m0 + 32q + t, 32 consecutive n: one reduction per element into the shared result
     const int quad = warp & 3;
@@ -466,6 +469,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_wgrad_kernel(WgradParams 
     const int ngroups = (W.Npad + 31) / 32;
     for (int g = warp >> 2; g < ngroups; g += 2) {
         float v[32];
+        __syncwarp();
         tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 32), v);
         if (m < W.M) {
             const int n0 = g * 32;
@@ -494,24 +498,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_wgrad_kernel(WgradParams 
 __global__ void __launch_bounds__(256) mlp_embed_fwd_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int n_harm, float scalar, int symmetrize,
                                                             int concat_pts, float* __restrict__ E, int64_t ldE)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // 32 lanes per row: lane j < 3 * n_harm owns (coordinate d, octave i) = (j / n_harm, j % n_harm) -> one sin and one cos; the
+    // remaining lanes write the raw coordinates and the zero padding.  A warp writes one row: contiguous segments.
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (r >= rows) return;
     float p[3] = {__ldg(x + r * ldx), __ldg(x + r * ldx + 1), __ldg(x + r * ldx + 2)};
     if (symmetrize) p[0] = fabsf(p[0]);
     float* e = E + r * ldE;
-    int o = 0;
-    if (concat_pts) { e[0] = p[0]; e[1] = p[1]; e[2] = p[2]; o = 3; }
-    const int nh3 = 3 * n_harm;
-    for (int d = 0; d < 3; d++) {
-        float f = scalar;
-        for (int i = 0; i < n_harm; i++) {
-            const float a = p[d] * f;
-            e[o + d * n_harm + i] = sinf(a);
-            e[o + nh3 + d * n_harm + i] = cosf(a);
-            f *= 2.f;
-        }
+    const int o = concat_pts ? 3 : 0, nh3 = 3 * n_harm;
+    for (int j = lane; j < nh3; j += 32) {
+        const int d = j / n_harm, i = j - d * n_harm;
+        const float a = p[d] * (scalar * (float)(1u << i));
+        e[o + j] = sinf(a);
+        e[o + nh3 + j] = cosf(a);
     }
-    for (int k = o + 2 * nh3; k < ldE; k++) e[k] = 0.f;
+    if (concat_pts && lane < 3) e[lane] = p[lane];
+    for (int k = o + 2 * nh3 + lane; k < ldE; k += 32) e[k] = 0.f;
 }
 
 // d_x[d] = dE[x'_d] + sum_i f_i (dE[sin] cos(a) - dE[cos] sin(a)); symmetric fields: d_x[0] *= sign(x[0]) (torch.abs: 0 at 0)
@@ -538,14 +541,17 @@ __global__ void __launch_bounds__(256) mlp_embed_bwd_kernel(const float* __restr
     }
 }
 
-// out[s, n] = sum of G[r, n] over the rows r of segment s = [seg_start[s], seg_start[s+1]) - the adjoint of a per-image bias when
-// the rows are grouped by image.  grid (segments, ceil(N/32)); 8 warps stride the segment's rows, lanes take 32 columns.
+// out[s, n] += sum of G[r, n] over the rows r of segment s = [seg_start[s], seg_start[s+1]) - the adjoint of a per-image bias when
+// the rows are grouped by image.  grid (segments, ceil(N/32), row splits); 8 warps stride the block's share of the rows, lanes take
+// 32 columns; one atomic per (block, column) into the zero-initialised result.
 __global__ void __launch_bounds__(256) mlp_colsum_segments_kernel(const float* __restrict__ G, int64_t ldg, const int64_t* __restrict__ seg_start, int N,
                                                                   float* __restrict__ out)
 {
     __shared__ float part[8][32];
     const int sgm = blockIdx.x, n = blockIdx.y * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5;
-    const int64_t a = seg_start[sgm], b = seg_start[sgm + 1];
+    const int64_t a0 = seg_start[sgm], b0 = seg_start[sgm + 1];
+    const int64_t share = (b0 - a0 + gridDim.z - 1) / gridDim.z;
+    const int64_t a = a0 + share * blockIdx.z, b = a + share < b0 ? a + share : b0;
     float acc = 0.f;
     if (n < N)
         for (int64_t r = a + warp; r < b; r += 8) acc += __ldg(G + r * ldg + n);
@@ -555,7 +561,7 @@ __global__ void __launch_bounds__(256) mlp_colsum_segments_kernel(const float* _
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; w++) t += part[w][threadIdx.x];
-        out[(size_t)sgm * N + n] = t;
+        if (t != 0.f) atomicAdd(out + (size_t)sgm * N + n, t);
     }
 }
 
@@ -655,7 +661,8 @@ B2A_API int b2a_mlp_embed_fwd(const float* x, int64_t ldx, int64_t rows, int n_h
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2A_CHECK_ARG(x && E && rows >= 0 && n_harmonic >= 0 && ldx >= 3 && ldE >= 6 * n_harmonic + (concat_pts ? 3 : 0), "shape");
-    if (rows) mlp_embed_fwd_kernel<<<b2a_blocks(rows, 256), 256, 0, stream>>>(x, ldx, rows, n_harmonic, scalar, symmetrize, concat_pts, E, ldE);
+    B2A_CHECK_ARG(n_harmonic <= 24, "at most 24 octaves");
+    if (rows) mlp_embed_fwd_kernel<<<b2a_blocks(rows * 32, 256), 256, 0, stream>>>(x, ldx, rows, n_harmonic, scalar, symmetrize, concat_pts, E, ldE);
     B2A_LAUNCH_OK();
     return 0;
 }
@@ -670,12 +677,16 @@ B2A_API int b2a_mlp_embed_bwd(const float* x, int64_t ldx, int64_t rows, int n_h
     return 0;
 }
 
-// out[s, n] (WRITTEN) = sum over rows seg_start[s] <= r < seg_start[s+1] of G[r, n]; seg_start: device int64 [n_seg + 1]
+// out[s, n] (zeroed here, then accumulated) = sum over rows seg_start[s] <= r < seg_start[s+1] of G[r, n]; seg_start: device int64 [n_seg + 1]
 B2A_API int b2a_mlp_colsum_segments(const float* G, int64_t ldg, const int64_t* seg_start, int n_seg, int N, float* out, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2A_CHECK_ARG(G && seg_start && out && n_seg > 0 && N > 0 && ldg >= N, "shape");
-    mlp_colsum_segments_kernel<<<dim3(n_seg, (N + 31) / 32), 256, 0, stream>>>(G, ldg, seg_start, N, out);
+    B2A_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)n_seg * N * sizeof(float), stream));
+    int splits = (4 * 148) / (n_seg * ((N + 31) / 32));
+    if (splits < 1) splits = 1;
+    if (splits > 64) splits = 64;
+    mlp_colsum_segments_kernel<<<dim3(n_seg, (N + 31) / 32, splits), 256, 0, stream>>>(G, ldg, seg_start, N, out);
     B2A_LAUNCH_OK();
     return 0;
 }

@@ -104,6 +104,7 @@ stats = CallStats()
 
 
 _fn_cache = {}
+_SYNC_CALLS = __import__("os").environ.get("B2A_SYNC_CALLS", "0") == "1"
 
 
 def _call(name, args, tag=None, launches=None):
@@ -128,6 +129,11 @@ def _call(name, args, tag=None, launches=None):
     stats.launches += KERNELS_PER_CALL[name] if launches is None else launches
     stats.calls[name] = stats.calls.get(name, 0) + 1
     _lib.check(rc)
+    if _SYNC_CALLS:      # debugging aid (B2A_SYNC_CALLS=1): surface an asynchronous kernel fault at the call that caused it
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:
+            raise _lib.B2AError("%s%s faulted: %s" % (name, args, e)) from e
 
 
 _size_cache = {}
