@@ -168,59 +168,37 @@ class TetGrid:
     def __init__(self, tets, num_verts):
         if not tets.is_cuda:
             raise _lib.B2AError("TetGrid needs CUDA tensors")
-        tets = tets.long()
+        L = _L()
+        import ctypes
+        dev = tets.device
         self.Vg = int(num_verts)
         self.T = int(tets.shape[0])
-        n = self.Vg + 1
-        be = torch.tensor(_BASE_EDGES, device=tets.device)
-        keys = None
-        step = 1 << 24  # bound the transient memory of the one-off table build on very large grids
-        for s in range(0, self.T, step):
-            e = tets[s:s + step][:, be].reshape(-1, 2)
-            k = torch.unique(e.min(1).values * n + e.max(1).values)
-            keys = k if keys is None else torch.unique(torch.cat([keys, k]))
-        a = keys // n
-        self.E = int(keys.numel())
-        self.edge_b = (keys % n).to(_i32).contiguous()
-        start = torch.zeros(self.Vg + 1, dtype=torch.int64, device=tets.device)
-        start[1:] = torch.cumsum(torch.bincount(a, minlength=self.Vg), 0)
-        self.edge_start = start.to(_i32).contiguous()
-        self.tets = tets.to(_i32).contiguous()
-        self.tile_words = self._build_tile_words()
-        self.workspace = _workspace(_size(_L().b2a_mt_workspace_bytes, self.Vg, self.E, self.T), tets.device)
+        st = _stream()
+        # unique sorted (min,max) edges -> CSR by the smaller endpoint, built by the library (b2a_mt_build_edges / b2a_mt_emit_edges:
+        # device radix sort + unique + scan; the reference's generate_edges is torch.unique(dim=0) over 6 T index pairs)
+        src = tets.contiguous()
+        if src.dtype not in (torch.int32, torch.int64):
+            src = src.long()
+        ws = _workspace(_size(L.b2a_mt_tables_workspace_bytes, self.Vg, self.T), dev)
+        start = torch.empty(self.Vg + 1, dtype=_i32, device=dev)
+        n_edges = torch.zeros(1, dtype=torch.int64).pin_memory()
+        _lib.check(L.b2a_mt_build_edges(_p(src), int(src.dtype == torch.int64), self.Vg, self.T, _p(ws), ws.numel(), _p(start), _p(n_edges), st))
+        torch.cuda.current_stream().synchronize()
+        self.E = int(n_edges.item())
+        self.edge_b = torch.empty(self.E, dtype=_i32, device=dev)
+        _lib.check(L.b2a_mt_emit_edges(_p(ws), ws.numel(), self.Vg, self.T, self.E, _p(self.edge_b), st))
+        self.edge_start = start
+        self.tets = src.to(_i32).contiguous()
+        tt, tw = ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(L.b2a_mt_tile_shape(ctypes.byref(tt), ctypes.byref(tw)))
+        self.tile_words = torch.empty((self.T + tt.value - 1) // tt.value, tw.value, dtype=_i32, device=dev)
+        _lib.check(L.b2a_mt_build_tile_words(_p(self.tets), self.T, _p(self.tile_words), st))
+        del ws
+        self.workspace = _workspace(_size(L.b2a_mt_workspace_bytes, self.Vg, self.E, self.T), dev)
         # output sizes (V, N1, N2, err): written by the count pass straight into PINNED host memory (zero-copy; under UVA the
         # host pointer is the device pointer), so the one readback of the extraction is an event wait, not a D2H memcpy
         self.counts = torch.zeros(4, dtype=_i32).pin_memory()
         self.counts_ready = torch.cuda.Event()
-
-    def _build_tile_words(self):
-        """Static skip table of the extraction (csrc/marching_tets.cu mt_tcount): for every tile of consecutive tets the
-        (<= 32) occupancy words its vertices live in.  One-off, chunked to bound the transient memory."""
-        import ctypes
-        tt, tw = ctypes.c_int(0), ctypes.c_int(0)
-        _lib.check(_L().b2a_mt_tile_shape(ctypes.byref(tt), ctypes.byref(tw)))
-        tile, Wn = tt.value, tw.value
-        dev = self.tets.device
-        nTT = (self.T + tile - 1) // tile
-        out = torch.empty(nTT, Wn, dtype=_i32, device=dev)
-        step = 2048                                   # tiles per chunk: 2048 x 2048 entries
-        for t0 in range(0, nTT, step):
-            t1 = min(t0 + step, nTT)
-            w = (self.tets[t0 * tile:min(t1 * tile, self.T)] >> 5).reshape(-1)
-            need = (t1 - t0) * tile * 4
-            if w.numel() < need:                      # last tile: pad by repeating the final tet's words
-                w = torch.cat([w, w[-4:].repeat((need - w.numel()) // 4)])
-            ws = torch.sort(w.view(t1 - t0, tile * 4), dim=1).values
-            first = torch.ones_like(ws, dtype=torch.bool)
-            first[:, 1:] = ws[:, 1:] != ws[:, :-1]
-            rank = torch.cumsum(first, 1) - 1
-            chunk = ws[:, :1].expand(-1, Wn).clone()
-            sel = first & (rank < Wn)
-            rows = torch.arange(t1 - t0, device=dev)[:, None].expand_as(ws)[sel]
-            chunk[rows, rank[sel]] = ws[sel]
-            chunk[rank[:, -1] >= Wn, 0] = -1          # touches more words than the table holds: never skipped
-            out[t0:t1] = chunk
-        return out.contiguous()
 
     def all_edges(self):
         """[E,2] int64, identical to the reference's DMTetGeometry.all_edges."""

@@ -4,6 +4,8 @@ Every rank extracts the (replicated) prior shape and renders its own contiguous 
 what the reference gets from accelerate/DDP (Trainer.py:170-180).  The only exchange is the all-reduce of parameter
 gradients after the backward; nothing in libb2a.so communicates.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -55,13 +57,16 @@ class GradientBuckets:
     compute stream wait for every launched bucket - call it where the optimiser would read the gradients.  Outside a process
     group (N = 1) every method is a no-op.  Nothing here touches libb2a.so: the path itself has no exchange step (§8e)."""
 
-    def __init__(self, total_bytes, device, bucket_bytes=25 << 20, group=None):
+    def __init__(self, total_bytes, device, bucket_bytes=25 << 20, group=None, tail_bytes=0):
+        """tail_bytes > 0: the LAST bucket holds exactly that many bytes (the gradients that become final last, e.g. d_sdf) and
+        the rest of the set is cut into `bucket_bytes` buckets in front of it - the exposed collective is as small as possible."""
         self.group = group
         self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         n = max(int(total_bytes) // 4, 1)
         per = max(int(bucket_bytes) // 4, 1)
+        tail = min(max(int(tail_bytes) // 4, 0), n)
         self.flat = torch.zeros(n, device=device)
-        self.buckets = [self.flat[i:i + per] for i in range(0, n, per)]
+        self.buckets = [self.flat[i:min(i + per, n - tail)] for i in range(0, n - tail, per)] + ([self.flat[n - tail:]] if tail else [])
         self.stream = torch.cuda.Stream(device=device) if (self.active and torch.device(device).type == "cuda") else None
         self.ready = [torch.cuda.Event() for _ in self.buckets] if self.stream is not None else []
         self.launched = []
@@ -87,6 +92,30 @@ class GradientBuckets:
                 dist.all_reduce(b, op=op, group=self.group)
         self.launched.append(i)
         self.bytes_reduced += b.numel() * 4
+
+    def launch_many(self, indices):
+        """Buckets `indices` in ONE enqueue: the collectives are issued inside one NCCL group (c10d coalescing manager), i.e. one
+        launch on the side stream instead of one c10d call + launch per bucket - what matters on a host-bound rank.  (Capturing the
+        collectives into a CUDA graph was tried and deadlocked on the 2-GPU box; not used.)  Falls back to launch() per bucket."""
+        indices = tuple(indices)
+        if not self.active or not indices:
+            return
+        if self.stream is None or len(indices) == 1 or os.environ.get("B2A_ALLREDUCE_COALESCE", "1") == "0":
+            for i in indices:
+                self.launch(i)
+            return
+        self.ready[indices[0]].record()
+        self.stream.wait_event(self.ready[indices[0]])
+        with torch.cuda.stream(self.stream):
+            try:
+                with dist._coalescing_manager(group=self.group, device=self.flat.device, async_ops=False):
+                    for i in indices:
+                        dist.all_reduce(self.buckets[i], op=dist.ReduceOp.AVG, group=self.group)
+            except (AttributeError, TypeError):
+                for i in indices:
+                    dist.all_reduce(self.buckets[i], op=dist.ReduceOp.AVG, group=self.group)
+        self.launched.extend(indices)
+        self.bytes_reduced += sum(self.buckets[i].numel() * 4 for i in indices)
 
     def wait(self):
         if self.stream is not None and self.launched:

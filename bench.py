@@ -160,9 +160,29 @@ def torch_ops_geometry_arm(hp, dev, reps=5):
 
     grads = [g_pos, g_nrm]
 
+    # the reference's OWN files (model/geometry/dmtet.py, skinning.py, model/render/mesh.py) executed on this GPU when the staged
+    # tree travelled with the snapshot (oracle/stage_ref.py); else the restatement of the same torch ops (oracle/torch_ops_geometry.py)
+    ref_ns, kind = None, "restatement (oracle/torch_ops_geometry.py)"
+    try:
+        from oracle import reference_loader
+        if reference_loader.available():
+            ref_ns = reference_loader.load()
+            ref_mt = ref_ns.dmtet.DMTet(device=str(dev))
+            ref_mt.device = str(dev)
+            kind = "reference files (model/geometry/dmtet.py, skinning.py, model/render/mesh.py) from " + os.path.relpath(reference_loader.REFERENCE_ROOT, ROOT)
+    except Exception:
+        ref_ns = None
+
     def theirs():
         sdf = hp.sdf.detach().clone().requires_grad_(True)
         ang = hp.angles.detach().clone().requires_grad_(True)
+        if ref_ns is not None:
+            verts, faces, uvs, uv_idx = ref_mt(hp.grid_verts, sdf, tets64)
+            prior = ref_ns.mesh.make_mesh(verts[None], faces[None], uvs[None], uv_idx[None], None)
+            posed, _ = ref_ns.skinning.skinning(prior.v_pos[:, None], bones, chain, ang, output_posed_bones=True, temperature=0.05)
+            inst = ref_ns.mesh.make_mesh(posed[:, 0], prior.t_pos_idx, prior.v_tex.repeat(posed.shape[0], 1, 1), prior.t_tex_idx, None)
+            torch.autograd.backward([inst.v_pos, inst.v_nrm], grads)
+            return sdf.grad, ang.grad
         verts, faces = G.marching_tets(hp.grid_verts, sdf, tets64)
         G.auto_normals(verts[None], faces)
         posed = G.skinning(verts[None, None], bones, chain, ang, temperature=0.05)[:, 0]
@@ -202,6 +222,7 @@ def torch_ops_geometry_arm(hp, dev, reps=5):
     out["max_rel_diff_d_sdf_position_path"] = float((a[0] - b[0]).abs().max() / a[0].abs().max().clamp_min(1e-20))
     out["max_rel_diff_d_angles_position_path"] = float((a[1] - b[1]).abs().max() / a[1].abs().max().clamp_min(1e-20))
     out["speedup"] = out["ms_torch_ops"] / out["ms_libb2a"]
+    out["torch_ops_arm"] = kind
     out["what"] = ("geometry half of the step (R2 extraction res-128 grid, R3 normals x2, R5 skinning 16 x %d verts x 20 bones) forward + "
                    "backward on this GPU: the reference's torch-op formulation (oracle/torch_ops_geometry.py) vs libb2a.so" % V)
     return out
@@ -329,22 +350,22 @@ def run_ours(args):
     # backward.  The gradients this path produces for replicated parameters (d_sdf) ride in the LAST bucket, launched when the
     # backward has finished; the other buckets stand for parameter gradients produced elsewhere in the step (field / light / pose /
     # encoder networks) and are launched when the backward starts.  Everything is waited for where the optimiser would read.
-    buckets = par.GradientBuckets(GRAD_SET_BYTES, dev)
-    last = len(buckets.buckets) - 1
     n_sdf = hp.sdf.numel()
+    buckets = par.GradientBuckets(GRAD_SET_BYTES, dev, tail_bytes=4 * n_sdf)
+    last = len(buckets.buckets) - 1
+    standins = tuple(range(last))
 
     def reduce_and_wait(d_sdf):
         if buckets.active:
             buckets.view(last, n_sdf).copy_(d_sdf.reshape(-1))
-            buckets.launch(last)
+            buckets.launch_many((last,))
             buckets.wait()
 
     def step():
         hp.sdf.grad = None
         hp.angles.grad = None
         outs = hp.forward()
-        for i in range(last):
-            buckets.launch(i)
+        buckets.launch_many(standins)
         torch.autograd.backward(list(outs), ups)
         reduce_and_wait(hp.sdf.grad)
         return hp.sdf.grad, hp.angles.grad
@@ -453,8 +474,7 @@ def run_ours(args):
         if len(outs) > 2:
             loss = loss + outs[2].mean()
         t0 = mark("loss", t0)
-        for i in range(last):
-            buckets.launch(i)
+        buckets.launch_many(standins)
         loss.backward()
         t0 = mark("backward", t0)
         reduce_and_wait(hp.sdf.grad)

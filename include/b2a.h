@@ -50,6 +50,16 @@ int b2a_mt_emit(const float* pos, const float* sdf, const int32_t* tets, const i
                 int64_t V, int64_t N1, int64_t N2,
                 float* verts, int32_t* vert_edge, int32_t* faces_i32, int64_t* faces_i64, int64_t* uv_idx_i64,
                 b2a_stream_t stream);
+/* Static per-grid tables, once per loaded grid (DMTetGeometry.generate_edges, dmtet.py:283-288, + the tile skip table).
+ * build_edges: the unique sorted (min,max) edges of the 6 T tet edges inside `workspace` (b2a_mt_tables_workspace_bytes),
+ * edge_start [Vg+1] written, *num_edges (device or pinned-host int64) = E; then the caller allocates edge_b [E] and calls
+ * emit_edges with the same workspace.  tets: int32 or int64 [T,4].  build_tile_words: int32 tets -> [ceil(T/tile), words]. */
+int b2a_mt_tables_workspace_bytes(int64_t Vg, int64_t T, size_t* bytes);
+int b2a_mt_build_edges(const void* tets, int tets_are_i64, int64_t Vg, int64_t T, void* workspace, size_t workspace_bytes,
+                       int32_t* edge_start, int64_t* num_edges, b2a_stream_t stream);
+int b2a_mt_emit_edges(const void* workspace, size_t workspace_bytes, int64_t Vg, int64_t T, int64_t E, int32_t* edge_b,
+                      b2a_stream_t stream);
+int b2a_mt_build_tile_words(const int32_t* tets, int64_t T, int32_t* tile_words, b2a_stream_t stream);
 /* d_sdf [Vg] and d_pos [Vg,3] (nullable) must be zero-initialised by the caller; gradients are accumulated. */
 int b2a_mt_bwd(const float* pos, const float* sdf, const int32_t* vert_edge, const float* d_verts, int64_t V,
                float* d_sdf, float* d_pos, b2a_stream_t stream);

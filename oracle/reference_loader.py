@@ -14,6 +14,11 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("B2A_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "geometry", "dmtet.py")):
+    # GPU box: the byte-identical staged copy (oracle/stage_ref.py -> git-ignored oracle/_ref, travels with the snapshot)
+    _staged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    if os.path.isfile(os.path.join(_staged, "model", "geometry", "dmtet.py")):
+        REFERENCE_ROOT = _staged
 
 _STUBS = [
     "nvdiffrast", "nvdiffrast.torch", "imageio", "matplotlib", "matplotlib.pyplot",

@@ -103,3 +103,32 @@ def skinning(v_pos, bones, kinematic_tree, angles, temperature=1.0):
         xk = (v4 @ M.transpose(-1, -2))[..., :3]                              # :420-424, one matmul per bone
         out = out + w[:, :, k, :, None] * xk                                  # :428-431
     return out
+
+
+def static_tables(tets, num_verts, tile, words):
+    """The static per-grid tables in torch ops (TEST INFRASTRUCTURE: the checker of b2a_mt_build_edges / b2a_mt_build_tile_words):
+    unique sorted (min,max) edges = the reference's generate_edges (dmtet.py:283-288) as a CSR by the smaller endpoint, and the
+    tile skip table (distinct `vertex >> 5` words per tile of `tile` consecutive tets, ascending, padded with the smallest; slot 0
+    = -1 when more than `words`).  -> edge_start [Vg+1] i32, edge_b [E] i32, tile_words [ceil(T/tile), words] i32."""
+    tets = tets.long()
+    T, n = tets.shape[0], int(num_verts) + 1
+    be = torch.tensor([0, 1, 0, 2, 0, 3, 1, 2, 1, 3, 2, 3], device=tets.device)
+    e = tets[:, be].reshape(-1, 2)
+    keys = torch.unique(e.min(1).values * n + e.max(1).values)
+    start = torch.zeros(n, dtype=torch.int64, device=tets.device)
+    start[1:] = torch.cumsum(torch.bincount(keys // n, minlength=n - 1), 0)
+    nTT = (T + tile - 1) // tile
+    w = (tets >> 5).reshape(-1)
+    need = nTT * tile * 4
+    if w.numel() < need:
+        w = torch.cat([w, w[-4:].repeat((need - w.numel()) // 4)])
+    ws = torch.sort(w.view(nTT, tile * 4), dim=1).values
+    first = torch.ones_like(ws, dtype=torch.bool)
+    first[:, 1:] = ws[:, 1:] != ws[:, :-1]
+    rank = torch.cumsum(first, 1) - 1
+    table = ws[:, :1].expand(-1, words).clone()
+    sel = first & (rank < words)
+    rows = torch.arange(nTT, device=tets.device)[:, None].expand_as(ws)[sel]
+    table[rows, rank[sel]] = ws[sel]
+    table[rank[:, -1] >= words, 0] = -1
+    return start.int(), (keys % n).int(), table.int()

@@ -14,6 +14,7 @@ EXPECTED = {
     "b2a_rasterize_bwd", "b2a_interpolate_fwd", "b2a_interpolate_bwd", "b2a_edge_adjacency_workspace_bytes", "b2a_edge_adjacency",
     "b2a_antialias_workspace_bytes", "b2a_antialias_prepare", "b2a_antialias_fwd", "b2a_antialias_bwd", "b2a_antialias_pair_fwd", "b2a_antialias_pair_bwd", "b2a_composite_up_fwd", "b2a_composite_up_bwd", "b2a_gbuffer_pack_bytes", "b2a_gbuffer_fwd", "b2a_gbuffer_bwd_workspace_bytes", "b2a_gbuffer_bwd",
     "b2a_render_geometry_fwd", "b2a_render_geometry_bwd",
+    "b2a_mt_tables_workspace_bytes", "b2a_mt_build_edges", "b2a_mt_emit_edges", "b2a_mt_build_tile_words",
     "b2a_mlp_packed_bytes", "b2a_mlp_pack_weights", "b2a_mlp_rows_gemm", "b2a_mlp_wgrad", "b2a_mlp_embed_fwd", "b2a_mlp_embed_bwd", "b2a_mlp_colsum_segments",
     "b2a_shade_directional_fwd", "b2a_shade_directional_bwd", "b2a_analytic_field_fwd", "b2a_analytic_field_bwd", "b2a_obj_text_bound", "b2a_obj_format",
 }

@@ -232,6 +232,28 @@ def test_lbs_batched_oracle(cuda, Bv, Bb):
     assert rel_err(vd.grad.cpu().numpy(), vt.grad.numpy()[:, 0]) < TOL
 
 
+@pytest.mark.parametrize("res,dtype", [(12, torch.int64), (20, torch.int32), (33, torch.int64)])
+def test_static_grid_tables(cuda, res, dtype):
+    """b2a_mt_build_edges / b2a_mt_emit_edges / b2a_mt_build_tile_words (the library's replacement of generate_edges, dmtet.py:283-288,
+    + the tile skip table) bit-equal to the torch.unique formulation; all_edges equals the reference's own edge list."""
+    from oracle import torch_ops_geometry as G
+    import ctypes
+    ops, lib = _ops(), pkg("_lib")
+    v, t = syn.kuhn_tet_grid(res)
+    tets = dev(t, cuda).to(dtype)
+    grid = ops.TetGrid(tets, v.shape[0])
+    tt, tw = ctypes.c_int(0), ctypes.c_int(0)
+    lib.check(lib.lib().b2a_mt_tile_shape(ctypes.byref(tt), ctypes.byref(tw)))
+    start, edge_b, table = G.static_tables(tets, v.shape[0], tt.value, tw.value)
+    assert grid.E == edge_b.numel() and torch.equal(grid.edge_start, start) and torch.equal(grid.edge_b, edge_b)
+    assert torch.equal(grid.tile_words, table)
+    # the reference's formulation verbatim (dmtet.py:283-288)
+    be = torch.tensor([0, 1, 0, 2, 0, 3, 1, 2, 1, 3, 2, 3], device=cuda)
+    all_edges = tets.long()[:, be].reshape(-1, 2)
+    all_edges = torch.unique(torch.sort(all_edges, dim=1)[0], dim=0)
+    assert torch.equal(grid.all_edges(), all_edges)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # normals, clip transform
 # ----------------------------------------------------------------------------------------------------------------

@@ -263,7 +263,7 @@ def test_sparse_field_evaluation_matches_dense(cuda, spp):
     parameter gradients of the reference's every-pixel evaluation - also on the msaa path (spp 2 / 4 with msaa=True, as
     AnimalModel.render always passes and train_ponymation_horse_stage1.yaml:29 sets), where a low-resolution pixel is needed as
     soon as any of its full-resolution sub-pixels is covered."""
-    pipe = pkg("pipeline")
+    pipe, fm = pkg("pipeline"), pkg("field_mlp")
     torch.manual_seed(0)
     sc = pipe.SyntheticScene(grid_res=32, batch=2, image_res=64, sdf_noise=0.0)
     hp = pipe.HotPath(sc, cuda, mlps=True)
@@ -271,13 +271,17 @@ def test_sparse_field_evaluation_matches_dense(cuda, spp):
     g1, g2 = sc.upstream_grads()
     d1, d2 = dev(g1, cuda) * 1e3, dev(g2, cuda) * 1e3
     res = {}
-    for sparse in (True, False):
-        hp.sparse_fields = sparse
-        hp.zero_grad()
-        d_sdf, d_ang = hp.step(d1, d2)
-        shaded, dino = hp.forward()
-        res[sparse] = (shaded.detach().clone(), dino.detach().clone(), d_sdf.clone(), d_ang.clone(),
-                       [p.grad.clone() for p in hp.material.parameters()] + [p.grad.clone() for p in hp.dino_net.parameters()])
+    fm.ENABLED = False      # this test is about WHICH rows are evaluated: both sides on PyTorch's fp32 GEMMs (the tensor-core fields have
+    try:                    # their own parity tests, tests/test_gpu_field_mlp.py)
+        for sparse in (True, False):
+            hp.sparse_fields = sparse
+            hp.zero_grad()
+            d_sdf, d_ang = hp.step(d1, d2)
+            shaded, dino = hp.forward()
+            res[sparse] = (shaded.detach().clone(), dino.detach().clone(), d_sdf.clone(), d_ang.clone(),
+                           [p.grad.clone() for p in hp.material.parameters()] + [p.grad.clone() for p in hp.dino_net.parameters()])
+    finally:
+        fm.ENABLED = True
     a, b = res[True], res[False]
     assert float(a[0].abs().max()) > 0.1 and float(a[1].abs().max()) > 0.1
     for x, y in zip(a[:4], b[:4]):
