@@ -132,6 +132,15 @@ __device__ __forceinline__ bool same_sign(float a, float b) { return (__float_as
 
 #define B2A_F32_MAX 3.402823466e+38f
 
+// PROVENANCE.  The reference calls nvdiffrast.torch.antialias (NVlabs nvdiffrast, NVIDIA Source Code License; an un-pinned git
+// dependency that is NOT part of the reference tree, INSTALL.md:22).  Results identical to it require its pair analysis: which
+// surface of a pixel pair is nearer, which of that triangle's edges are silhouette edges (no neighbour, or the neighbour's
+// opposite vertex on the same screen side), where the edge crosses the segment between the pixel centres, the 1/16 guard on
+// near-parallel edges, the blend weight 0.5 - distance.  aa_analyze restates that published algorithm (AntialiasFwdAnalysisKernel
+// in nvdiffrast/common/antialias.cu) from memory - no nvdiffrast source is present in this container or this repository -
+// so its structure and several local names follow the original; everything around it (analyse once per render, gather-based
+// streaming kernels, pair fusion, coefficient folding for the position gradient) is this repository's own design.  Whether the
+// restatement matches nvdiffrast bit for bit cannot be checked here: PARITY UNPINNED.
 // (px,py) = first pixel of the pair, d = 0: neighbour to the right, 1: neighbour below.  r0/r1 = rast of the two pixels.
 __device__ bool aa_analyze(const AAParams& P, const float* __restrict__ pos_b, float4 r0, float4 r1, int px, int py, int d, AAPair& r)
 {

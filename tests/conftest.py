@@ -36,6 +36,24 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
 
 
+def elem_err(a, b, rtol=1e-4, floor=1e-6):
+    """Per-ELEMENT check |a - b| <= rtol * |b| + floor * max|b| (north_star: "1e-4 relative on float buffers"; the floor keeps
+    entries that are zero up to rounding from demanding infinite relative accuracy).  -> (ok, worst ratio, index of the worst
+    element): ratio = |a - b| / (rtol |b| + floor max|b|), so <= 1 passes."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    bound = rtol * np.abs(b) + floor * max(float(np.abs(b).max()), 1e-30)
+    ratio = np.abs(a - b) / bound
+    i = int(np.argmax(ratio)) if ratio.size else 0
+    worst = float(ratio.reshape(-1)[i]) if ratio.size else 0.0
+    return worst <= 1.0, worst, np.unravel_index(i, ratio.shape) if ratio.size else ()
+
+
+def assert_elem(a, b, rtol=1e-4, floor=1e-6, what=""):
+    ok, worst, idx = elem_err(a, b, rtol, floor)
+    assert ok, "%s: worst element %s is %.2f x the per-element bound (rtol %g, floor %g of max)" % (what, idx, worst, rtol, floor)
+
+
 @pytest.fixture(scope="session")
 def cuda():
     import torch

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden, golden_files, pkg, rel_err
+from conftest import assert_elem, golden, golden_files, pkg, rel_err
 from oracle import geometry_np as gnp
 from oracle import raster as R
 from oracle import torch_ref as T
@@ -97,6 +97,9 @@ def test_skinning_golden(cuda, name):
     assert rel_err(out.detach().cpu().numpy(), g["out"]) < TOL
     assert rel_err(aux["posed_bones"].detach().cpu().numpy(), g["posed_bones"]) < TOL
     assert np.abs(aux["vertices_to_bones"].cpu().numpy() - g["weights"]).max() < TOL
+    # per ELEMENT: |a - b| <= 1e-4 |b| + 1e-6 max|b| (the worst element is reported on failure)
+    assert_elem(out.detach().cpu().numpy(), g["out"], what="posed vertices")
+    assert_elem(aux["posed_bones"].detach().cpu().numpy(), g["posed_bones"], what="posed bones")
     ((out * dev(g["g_out"], cuda)).sum() + (aux["posed_bones"] * dev(g["g_posed"], cuda)).sum()).backward()
     assert rel_err(ang.grad.cpu().numpy(), g["d_angles"]) < TOL
     assert rel_err(vp.grad.cpu().numpy(), g["d_verts"]) < TOL
@@ -293,6 +296,7 @@ def test_vertex_normals_golden(cuda, case):
     v = dev(g[case + "_v_pos"], cuda).requires_grad_(True)
     nrm = ops.vertex_normals(v, dev(g[case + "_faces"], cuda))
     assert rel_err(nrm.detach().cpu().numpy(), g[case + "_v_nrm"]) < TOL
+    assert_elem(nrm.detach().cpu().numpy(), g[case + "_v_nrm"], floor=1e-5, what="vertex normals")
     (nrm * dev(g[case + "_g"], cuda)).sum().backward()
     assert rel_err(v.grad.cpu().numpy(), g[case + "_d_v_pos"]) < TOL
     if case == "degenerate":
@@ -369,6 +373,19 @@ def test_rasterize_analytic(cuda, name, res):
     out = ops.rasterize(dev(pos, cuda), dev(tri, cuda), res).cpu().numpy()
     assert np.array_equal(out[..., 3], ref[..., 3])            # bit-exact triangle ids
     assert np.array_equal(out, ref)                            # and identical barycentrics / depth bits
+
+
+def test_rasterize_edge_and_depth_ties(cuda):
+    """Pixel centres exactly on edges / on a shared diagonal / equal depth: the kernel breaks every tie like the restatement
+    (inclusive edges, lowest triangle index) - tests/test_oracle_raster.py documents where that differs from nvdiffrast-GL."""
+    from test_oracle_raster import edge_tie_scene
+    ops = _ops()
+    for res in (8, 16, 64):
+        pos, tri = edge_tie_scene(res)
+        ref = R.rasterize(pos, tri, (res, res))
+        out = ops.rasterize(dev(pos, cuda), dev(tri, cuda), (res, res)).cpu().numpy()
+        assert np.array_equal(out, ref)
+        assert (out[0, ..., 3] > 0).sum() == (res - 2) ** 2 and not np.isin(out[0, ..., 3], [3.0, 4.0]).any()
 
 
 @pytest.mark.parametrize("image", [64, 256])

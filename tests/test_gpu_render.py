@@ -186,6 +186,45 @@ def test_hot_path_matches_oracle(cuda, grid_res, batch, image, n_leg):
     assert rel_err(d_sdf.cpu().numpy(), d_sdf_ref.numpy()) < 5e-2
 
 
+def test_full_size_values_on_a_subsample(cuda):
+    """BASELINE configs[1] at FULL size (res-128 grid, 16 x 256^2, 20 bones): values, not only properties - the CPU oracle renders the
+    first 2 of the 16 images (what it can afford in a test) from the same seeded inputs; topology bit-exact, posed vertices and
+    images held to the same bars as the small cases."""
+    pipe = pkg("pipeline")
+    sc = pipe.SyntheticScene(grid_res=128, batch=16, image_res=256)
+    hp = pipe.HotPath(sc, cuda)
+    shaded, dino = hp.forward()
+    ref = P.forward(sc, images=2)
+    prior = hp.last["prior"]
+    assert np.array_equal(prior.t_pos_idx[0].cpu().numpy(), ref["faces"].numpy())
+    assert np.array_equal(prior.v_pos[0].detach().cpu().numpy(), ref["verts"].detach().numpy())
+    assert rel_err(hp.last["inst"].v_pos[:2].detach().cpu().numpy(), ref["posed"][:, 0].detach().numpy()) < TOL
+    for o, k in ((shaded, "shaded"), (dino, "dino_pred")):
+        a, b = o[:2].detach().cpu().numpy(), ref[k].detach().numpy()
+        bad = (np.abs(a - b).max(axis=1) > TOL * max(np.abs(b).max(), 1e-12))
+        assert bad.mean() < 2e-3, (k, bad.mean())
+
+
+def test_hot_path_gradients_under_smooth_upstream(cuda):
+    """Whole path with SMOOTH (low-pass) upstream image gradients: the antialias position gradient is well conditioned then, and
+    the end-to-end gradients are held to 1e-4 (relative to the largest entry; measured 4e-6 / 1e-5) instead of the 5e-2 the white-noise case needs."""
+    pipe = pkg("pipeline")
+    sc = pipe.SyntheticScene(grid_res=32, batch=2, image_res=64, sdf_noise=0.0)
+    rng = np.random.RandomState(3)
+
+    def smooth(c):
+        g = torch.from_numpy(rng.randn(2, c, 8, 8).astype(np.float32))
+        return torch.nn.functional.interpolate(g, size=(64, 64), mode="bicubic", align_corners=False).numpy() * 1e-2
+
+    g1, g2 = smooth(4), smooth(sc.dino_dim)
+    d_sdf_ref, d_ang_ref, ref = P.step(sc, g1, g2)
+    hp = pipe.HotPath(sc, cuda)
+    d_sdf, d_ang = hp.step(dev(g1, cuda), dev(g2, cuda))
+    e_ang, e_sdf = rel_err(d_ang.cpu().numpy(), d_ang_ref.numpy()), rel_err(d_sdf.cpu().numpy(), d_sdf_ref.numpy())
+    print("smooth upstream gradients: d_angles %.2e, d_sdf %.2e" % (e_ang, e_sdf))
+    assert e_ang < 1e-4 and e_sdf < 1e-4
+
+
 def test_full_size_properties(cuda):
     """BASELINE configs[1] at full size (res-128 grid, 16 x 256^2, 20 bones), where the CPU oracle is too slow to be the
     checker: size-independent properties of every stage."""

@@ -46,6 +46,35 @@ def test_depth_order_tie_break_and_clipping():
     assert np.allclose(clip[:, 2] / clip[:, 3], r[0, ..., 2][m], atol=2e-5)
 
 
+def edge_tie_scene(res=8):
+    """Two coplanar triangles (a quad split along its diagonal) whose shared edge and outer edges pass EXACTLY through pixel
+    centres, drawn twice at the same depth: every tie the fill rule has to break."""
+    s = 2.0 / res                                   # one pixel in NDC; pixel centres at -1 + (i + .5) s
+    lo, hi = -1 + 1.5 * s, -1 + (res - 1.5) * s     # the quad's corners sit ON pixel centres
+    quad = [[lo, lo, 0.25, 1], [hi, lo, 0.25, 1], [hi, hi, 0.25, 1], [lo, hi, 0.25, 1]]
+    pos = np.array([quad + quad], np.float32)
+    tri = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7]], np.int32)
+    return pos, tri
+
+
+def test_fill_rule_on_exact_edge_and_depth_ties():
+    """Documents where this restatement's fill rule can differ from nvdiffrast's OpenGL rasterizer (top-left rule, draw order):
+    a pixel centre exactly on an edge is INSIDE (inclusive edges), a centre on the shared diagonal is claimed by both triangles and
+    goes to the lower triangle index, equal depth goes to the lower index.  GL's top-left rule would drop the centres on the
+    right / bottom outer edges; on meshes in general position (every test outside this one) no centre lies exactly on an edge."""
+    res = 8
+    pos, tri = edge_tie_scene(res)
+    ids = R.rasterize(pos, tri, (res, res))[0, ..., 3]
+    inside = np.zeros((res, res), bool)
+    inside[1:res - 1, 1:res - 1] = True              # centres 1..res-2 in x and y: the closed quad, outer edges included
+    assert np.array_equal(ids > 0, inside)
+    ys, xs = np.nonzero(inside)
+    # triangle 0 = (lo,lo),(hi,lo),(hi,hi): the half with x >= y; the diagonal x == y is shared -> lowest index (0 -> id 1)
+    want = np.where(xs >= ys, 1.0, 2.0)
+    assert np.array_equal(ids[inside], want)
+    assert not np.isin(ids, [3.0, 4.0]).any()        # the second copy at equal depth never wins
+
+
 def _fd(f, x, g, idx, eps):
     """directional finite difference of sum(f(x) * g) along coordinate idx (float64 accumulation)"""
     xp, xm = x.copy(), x.copy()
