@@ -10,6 +10,7 @@ import os
 import numpy as np
 import torch
 
+from .. import field_mlp
 from .. import ops
 from ..render import mesh
 
@@ -98,6 +99,13 @@ class DMTetGeometry(torch.nn.Module):
         self.symmetrize = symmetrize
         self.tets_root = kwargs.get("tets_root", "data/tets")
         self.synthetic_tets = bool(kwargs.get("synthetic_tets", False))
+        # Narrow-band SDF evaluation (off by default = the reference's full-grid evaluation): `narrow_band = (k, M)`
+        # evaluates the SDF network only on grid vertices within k grid edges of the surface found by the last FULL evaluation, and
+        # refreshes the full grid every M calls (and whenever the surface reaches the rim of the band).  Extraction, the BCE
+        # regulariser and every gradient only involve vertices on sign-changing edges, so inside the band the results are those
+        # of the full evaluation.
+        self.narrow_band = kwargs.get("narrow_band", None)
+        self._band = None
         self.load_tets(self.grid_res, self.grid_scale)
         CoordMLP, CoordMLP_Mod = _field_networks()
         embedder_scalar = 2 * np.pi / self.grid_scale * 0.9
@@ -151,7 +159,12 @@ class DMTetGeometry(torch.nn.Module):
             pts = torch.stack([xs.abs(), ys, zs], -1)
         if feats is not None:
             feats = feats.unsqueeze(0).repeat(pts.shape[0], 1)
-        sdf = self.mlp(pts, feat=feats)
+        if feats is None and pts.dim() == 2 and pts.is_cuda and field_mlp.supported(self.mlp, pts, None):
+            # the SDF network is a CoordMLP too: the same tcgen05 GEMMs as the texture / DINO fields (csrc/field_mlp.cu); a
+            # double backward (the eikonal regulariser differentiates get_sdf's gradient) stays on PyTorch's ops
+            sdf = field_mlp.coord_mlp_rows(self.mlp, pts, None, None, 1) if not torch.is_grad_enabled() or not pts.requires_grad else self.mlp(pts, feat=feats)
+        else:
+            sdf = self.mlp(pts, feat=feats)
         if self.init_sdf is None:
             pass
         elif type(self.init_sdf) in [float, int]:
@@ -187,12 +200,66 @@ class DMTetGeometry(torch.nn.Module):
     def getAABB(self):
         return torch.min(self.verts, dim=0).values, torch.max(self.verts, dim=0).values
 
+    def _sdf_full_and_band(self, v_deformed, total_iter, feats, k):
+        """Full-grid evaluation + the band for the next calls: vertices within k grid edges of a sign-changing edge (dilation over
+        the static edge list), and its outermost ring (the guard: a sign change there means the surface has reached the rim)."""
+        sdf = self.get_sdf(v_deformed, total_iter=total_iter, feats=feats)
+        with torch.no_grad():
+            e = self.all_edges
+            a, b = e[:, 0], e[:, 1]
+            occ = sdf.detach().reshape(-1) > 0
+            band = torch.zeros_like(occ)
+            cross = occ[a] != occ[b]
+            band[a[cross]] = True
+            band[b[cross]] = True
+            ring = band
+            for _ in range(int(k)):
+                grow = band[a] | band[b]
+                nxt = band.clone()
+                nxt[a[grow]] = True
+                nxt[b[grow]] = True
+                ring = nxt & ~band
+                band = nxt
+            idx = torch.nonzero(band).squeeze(1)
+            self._band = dict(idx=idx, ring=ring[idx], sdf=sdf.detach().clone(), occ_ring=occ[idx][ring[idx]], age=0,
+                              flag=torch.zeros(1, dtype=torch.int32).pin_memory(), rows=int(idx.numel()))
+        return sdf
+
+    def _sdf_narrow_band(self, v_deformed, total_iter, feats):
+        """SDF values for the extraction with the network evaluated on the band only; everything else keeps the values (hence the
+        signs) of the last full evaluation.  Returns None when the band must be refreshed."""
+        k, every = self.narrow_band
+        bd = self._band
+        if bd is None or bd["age"] + 1 >= int(every) or bd["sdf"].shape[0] != v_deformed.shape[0]:
+            return None
+        idx = bd["idx"]
+        sdf_band = self.get_sdf(v_deformed.index_select(0, idx), total_iter=total_iter, feats=feats)
+        # guard: the sign pattern on the band's outermost ring must be unchanged (device-side count into pinned memory, read
+        # together with the extraction's own size hand-off - no extra synchronisation)
+        moved = ((sdf_band.detach().reshape(-1)[bd["ring"]] > 0) != bd["occ_ring"]).sum().to(torch.int32)
+        bd["flag"].copy_(moved.reshape(1), non_blocking=True)
+        bd["age"] += 1
+        return bd["sdf"].index_copy(0, idx, sdf_band)
+
     def getMesh(self, material=None, total_iter=0, jitter_grid=True, feats=None):
         v_deformed = self.verts
         if jitter_grid and self.jitter_grid > 0:
             jitter = (torch.rand(1, device=v_deformed.device) * 2 - 1) * self.jitter_grid * self.grid_scale
             v_deformed = v_deformed + jitter
-        self.current_sdf = self.get_sdf(v_deformed, total_iter=total_iter, feats=feats)
+        self.sdf_rows_evaluated = v_deformed.shape[0]
+        if self.narrow_band:
+            sdf = self._sdf_narrow_band(v_deformed, total_iter, feats)
+            if sdf is not None:
+                self.current_sdf = sdf
+                verts, faces, uv_idx, faces32 = self.marching_tets.extract(v_deformed, self.current_sdf, self.grid)
+                if int(self._band["flag"].item()) == 0:         # (the extraction has synchronised: the flag is final)
+                    self.sdf_rows_evaluated = self._band["rows"]
+                    self.mesh_verts = verts
+                    uvs = self.marching_tets.uv_table(self.grid.T, verts.device)
+                    return mesh.make_mesh(verts[None], faces[None], uvs[None], uv_idx[None], material, faces_i32=faces32)
+            self.current_sdf = self._sdf_full_and_band(v_deformed, total_iter, feats, self.narrow_band[0])
+        else:
+            self.current_sdf = self.get_sdf(v_deformed, total_iter=total_iter, feats=feats)
         verts, faces, uv_idx, faces32 = self.marching_tets.extract(v_deformed, self.current_sdf, self.grid)
         self.mesh_verts = verts
         uvs = self.marching_tets.uv_table(self.grid.T, verts.device)

@@ -423,6 +423,47 @@ def test_dmtet_geometry_getmesh_end_to_end(cuda, tmp_path):
     assert geo.getMesh(jitter_grid=True).v_pos.shape[1] > 100
 
 
+def test_narrow_band_sdf_evaluation(cuda, tmp_path):
+    """with `narrow_band = (k, M)` the SDF network runs on the grid vertices within k edges of the last fully
+    evaluated surface only; the extraction (faces bit-exact, vertices to rounding of the network's own output) and the gradients to
+    the network are those of the reference's full-grid evaluation; a surface that reaches the rim of the band, and every M-th call,
+    fall back to the full grid."""
+    import copy
+    D = pkg("geometry.dmtet")
+    torch.manual_seed(0)
+    kw = dict(num_layers=5, hidden_size=64, embedder_freq=8, embed_concat_pts=True, init_sdf="ellipsoid", jitter_grid=0.0, symmetrize=True,
+              tets_root=str(tmp_path), synthetic_tets=True)
+    full = D.DMTetGeometry(32, 7.0, **kw).to(cuda)
+    band = D.DMTetGeometry(32, 7.0, narrow_band=(2, 4), **kw).to(cuda)
+    band.mlp.load_state_dict(full.mlp.state_dict())
+    Vg = full.verts.shape[0]
+    rows = []
+    for it in range(6):
+        with torch.no_grad():                      # a slowly moving surface: the output layer drifts a little every step
+            for geo in (full, band):
+                list(geo.mlp.parameters())[-1].add_(0.002 * (it + 1))
+        outs = []
+        for geo in (full, band):
+            geo.mlp.zero_grad()
+            m = geo.getMesh(jitter_grid=False)
+            (m.v_pos.square().sum() + geo.get_sdf_reg_loss()["sdf_bce_reg_loss"]).backward()
+            outs.append((m, [p.grad.clone() for p in geo.mlp.parameters()]))
+        (mf, gf), (mb, gb) = outs
+        assert torch.equal(mf.t_pos_idx, mb.t_pos_idx), it
+        assert rel_err(mb.v_pos.detach().cpu().numpy(), mf.v_pos.detach().cpu().numpy()) < 1e-5
+        for a, b in zip(gb, gf):
+            assert float((a - b).norm() / b.norm().clamp_min(1e-30)) < 1e-3
+        rows.append(band.sdf_rows_evaluated)
+    assert rows[0] == Vg and rows[4] == Vg                 # call 0 and every 4th call evaluate the full grid
+    assert max(rows[1:4]) < 0.35 * Vg and rows[5] < 0.35 * Vg, rows
+    # a jump of the surface beyond the band: the guard notices and the call falls back to the full grid (same result as `full`)
+    with torch.no_grad():
+        for geo in (full, band):
+            list(geo.mlp.parameters())[-1].add_(0.5)
+    mf, mb = full.getMesh(jitter_grid=False), band.getMesh(jitter_grid=False)
+    assert band.sdf_rows_evaluated == Vg and torch.equal(mf.t_pos_idx, mb.t_pos_idx)
+
+
 def _extracted(cuda, res=12):
     """A DMTet extraction through the reference call signature `DMTet()(pos, sdf, tets) -> (verts, faces, uvs, uv_idx)`."""
     syn = pkg("synthetic")
