@@ -177,8 +177,10 @@ struct GemmParams {
     int64_t ldo;
     const float* bias;         // EPI_BIAS / EPI_SIGMOID: [N] (bias_rows == NULL) or [n_img, N] gathered through bias_rows; nullable
     const int* bias_rows;      // [rows] image index of each row (nullable)
-    const float* mask_src;     // EPI_MASK: [rows, ldm] pre-activation whose sign gates the output
+    const float* mask_src;     // EPI_MASK: [rows, ldm] pre-activation whose sign gates the output (when mask_bits is NULL)
     int64_t ldm;
+    const uint32_t* mask_bits; // EPI_MASK: [rows, Npad/32] sign bits (bit j of word g = pre-activation[row, 32 g + j] > 0): 1/32 of the bytes
+    uint32_t* bits_out;        // EPI_BIAS: (nullable) writes those sign bits of the OUTPUT for the backward pass
 };
 
 constexpr int A_ITEMS = TILE_M * (KC / 8) / GEMM_THREADS;   // (row, 8-wide k group) items per thread and chunk
@@ -311,6 +313,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmPara
 #pragma unroll
                 for (int j = 0; j < 32; j++) v[j] = 1.f / (1.f + expf(-v[j]));
             }
+            if (EPI == EPI_BIAS && P.bits_out && row < P.rows) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int j = 0; j < 32; j++) w |= (v[j] > 0.f ? 1u : 0u) << j;
+                P.bits_out[row * ngroups + g] = w;
+            }
+        }
+        if (EPI == EPI_MASK && P.mask_bits) {
+            const int64_t row = wrow0 + lane;
+            const uint32_t w = row < P.rows ? __ldg(P.mask_bits + row * ngroups + g) : 0u;
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
         }
         __syncwarp();
 #pragma unroll
@@ -322,7 +336,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmPara
             const int64_t row = wrow0 + r;
             if (row < P.rows && col < P.N) {
                 float x = tile[r * 33 + lane];
-                if (EPI == EPI_MASK && !(__ldg(P.mask_src + row * P.ldm + col) > 0.f)) x = 0.f;
+                if (EPI == EPI_MASK && !P.mask_bits && !(__ldg(P.mask_src + row * P.ldm + col) > 0.f)) x = 0.f;
                 P.out[row * P.ldo + col] = x;
             }
         }
@@ -592,19 +606,19 @@ B2A_API int b2a_mlp_pack_weights(const float* W, int64_t ldw, int N, int K, int 
 // nullable); 1: zero where mask_src[r, n] <= 0 (the ReLU derivative of the stored pre-activation); 2: sigmoid(. + bias).
 // relu_on_load: op(A) = max(A, 0).  passes: 3 (fp32-grade split products) or 1 (single bf16 product).
 B2A_API int b2a_mlp_rows_gemm(const float* A, int64_t lda, int64_t rows, int K, const void* packed, int N, int relu_on_load, int passes, int epilogue,
-                              const float* bias, const int32_t* bias_rows, const float* mask_src, int64_t ldm, float* out, int64_t ldo,
-                              b2a_stream_t stream_)
+                              const float* bias, const int32_t* bias_rows, const float* mask_src, int64_t ldm, const uint32_t* mask_bits,
+                              uint32_t* bits_out, float* out, int64_t ldo, b2a_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2A_CHECK_ARG(A && packed && out, "null pointer");
     B2A_CHECK_ARG(rows >= 0 && K > 0 && N > 0 && N <= 256 && lda >= K && ldo >= N && (passes == 1 || passes == 3), "shape");
-    B2A_CHECK_ARG(epilogue >= 0 && epilogue <= 2 && (epilogue != EPI_MASK || (mask_src && ldm >= N)), "epilogue");
+    B2A_CHECK_ARG(epilogue >= 0 && epilogue <= 2 && (epilogue != EPI_MASK || mask_bits || (mask_src && ldm >= N)), "epilogue");
     B2A_CHECK_ARG(((uintptr_t)A & 15) == 0 && (lda & 3) == 0 && ((uintptr_t)packed & 15) == 0 && ((uintptr_t)out & 15) == 0, "alignment (16 bytes, lda % 4 == 0)");
     if (rows == 0) return 0;
     GemmParams P;
     P.A = A; P.lda = lda; P.rows = rows; P.K = K; P.Kpad = (K + KC - 1) / KC * KC; P.N = N; P.Npad = (N + 15) / 16 * 16;
     P.packed = (const uint16_t*)packed; P.relu_on_load = relu_on_load; P.passes = passes; P.out = out; P.ldo = ldo; P.bias = bias;
-    P.bias_rows = bias_rows; P.mask_src = mask_src; P.ldm = ldm;
+    P.bias_rows = bias_rows; P.mask_src = mask_src; P.ldm = ldm; P.mask_bits = mask_bits; P.bits_out = bits_out;
     const int smem = gemm_smem_bytes(P.Npad);
     const unsigned grid = b2a_blocks(rows, TILE_M);
 #define MLP_LAUNCH(E)                                                                                                     \

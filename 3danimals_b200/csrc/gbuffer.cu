@@ -449,6 +449,9 @@ __global__ void __launch_bounds__(256) gb_bwd_finalize_xfm_kernel(float* __restr
     const int b = blockIdx.y;
     if (threadIdx.x < 16) { m[threadIdx.x] = mtx[(size_t)b * 16 + threadIdx.x]; macc[threadIdx.x] = 0.f; }
     __syncthreads();
+    // launched with programmatic stream serialization right behind the scatter kernel: everything above overlaps that kernel's
+    // tail; the accumulator is only read once the whole preceding grid has completed and flushed
+    cudaGridDependencySynchronize();
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     float x = 0.f, y = 0.f, z = 0.f, one = 0.f;
@@ -550,8 +553,21 @@ int gb_bwd_impl(const char* who, const float* rast, int spp, const float* pos_cl
 #undef GB_LAUNCH_GRID
     }
     if (mtx) {
-        gb_bwd_finalize_xfm_kernel<<<dim3(b2a_blocks(V, 256), B), 256, 0, stream>>>(acc, workspace_is_zero, B, Bq, V, mtx, v_pos, d_clip_up, d_v_pos, d_v_nrm,
-                                                                                     d_prior_pos, d_mtx);
+        // programmatic dependent launch: the per-vertex pass is queued while the scatter kernel drains (its blocks start as SMs
+        // free up and wait in cudaGridDependencySynchronize) - removes the launch gap between the two kernels of the call
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(b2a_blocks(V, 256), B);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = have_gb ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const int rz = workspace_is_zero, iB = B, iBq = Bq;
+        const int64_t iV = V;
+        B2A_CUDA_OK(cudaLaunchKernelEx(&cfg, gb_bwd_finalize_xfm_kernel, acc, rz, iB, iBq, iV, mtx, v_pos, d_clip_up, d_v_pos, d_v_nrm, d_prior_pos, d_mtx));
     } else if (d_v_pos || d_v_nrm || d_prior_pos || d_clip || workspace_is_zero) {
         gb_bwd_finalize_kernel<<<dim3(b2a_blocks(V, 256), B), 256, 0, stream>>>(acc, workspace_is_zero, B, Bq, V, d_v_pos, d_v_nrm, d_prior_pos, d_clip);
     }

@@ -33,13 +33,15 @@ def _pack(w, n, k, transpose):
     return buf
 
 
-def _gemm(a, k, packed, n, relu, passes, epi, bias=None, bias_rows=None, mask=None, out=None, ldo=None):
+def _gemm(a, k, packed, n, relu, passes, epi, bias=None, bias_rows=None, mask=None, out=None, ldo=None, mask_bits=None, want_bits=False):
+    """-> out, or (out, sign bits of out [rows, ceil16(n)/32 words... one uint32 per 32 columns]) with want_bits."""
     rows = a.shape[0]
     if out is None:
         out = torch.empty(rows, n if ldo is None else ldo, device=a.device)
+    bits = torch.empty(rows, ((n + 15) // 16 * 16 + 31) // 32, dtype=torch.int32, device=a.device) if want_bits else None
     _call("b2a_mlp_rows_gemm", (_p(a), a.stride(0), rows, k, _p(packed), n, int(relu), passes, epi, _p(bias), _p(bias_rows), _p(mask),
-                                0 if mask is None else mask.stride(0), _p(out), out.stride(0), _stream()))
-    return out
+                                0 if mask is None else mask.stride(0), _p(mask_bits), _p(bits), _p(out), out.stride(0), _stream()))
+    return (out, bits) if want_bits else out
 
 
 def _wgrad(p, relu_p, q, relu_q, m, n, passes, out, transpose_out=False):
@@ -84,13 +86,19 @@ class _FieldMLP(torch.autograd.Function):
         ldE = (kin + 31) // 32 * 32
         E = torch.empty(N, ldE, device=dev)
         _call("b2a_mlp_embed_fwd", (_p(x), x.stride(0), N, n_harm, float(scalar), int(symmetrize), int(concat), _p(E), ldE, st))
-        zs = [_gemm(E, kin, _pack(w_in, nf, kin, False), nf, False, passes, 0, bias=b_in)]
-        zs.append(_gemm(zs[-1], nf, _pack(ws[0], nf, nf, False), nf, True, passes, 0, bias=bias_img, bias_rows=img if bias_img is not None else None))
+        # every pre-activation is kept in fp32 (the weight gradients need relu(z)); its SIGN BITS are written by the same epilogue so
+        # that the backward's ReLU-derivative mask reads 32 bytes per row instead of 1 KB
+        z, b = _gemm(E, kin, _pack(w_in, nf, kin, False), nf, False, passes, 0, bias=b_in, want_bits=True)
+        zs, bits = [z], [b]
+        z, b = _gemm(zs[-1], nf, _pack(ws[0], nf, nf, False), nf, True, passes, 0, bias=bias_img, bias_rows=img if bias_img is not None else None,
+                     want_bits=True)
+        zs.append(z); bits.append(b)
         for w in ws[1:-1]:
-            zs.append(_gemm(zs[-1], nf, _pack(w, nf, nf, False), nf, True, passes, 0))
+            z, b = _gemm(zs[-1], nf, _pack(w, nf, nf, False), nf, True, passes, 0, want_bits=True)
+            zs.append(z); bits.append(b)
         cout = ws[-1].shape[0]
         out = _gemm(zs[-1], nf, _pack(ws[-1], cout, nf, False), cout, True, passes, 2 if sigmoid else 0)
-        ctx.save_for_backward(x, E, out, seg_start, w_in, *ws, *zs)
+        ctx.save_for_backward(x, E, out, seg_start, w_in, *ws, *zs, *bits)
         ctx.cfg = cfg
         ctx.n_w = len(ws)
         ctx.has_bias = bias_img is not None
@@ -103,7 +111,8 @@ class _FieldMLP(torch.autograd.Function):
         saved = ctx.saved_tensors
         x, E, out, seg_start, w_in = saved[:5]
         ws = saved[5:5 + ctx.n_w]
-        zs = saved[5 + ctx.n_w:]
+        zs = saved[5 + ctx.n_w:5 + 2 * ctx.n_w]
+        bits = saved[5 + 2 * ctx.n_w:]
         N = x.shape[0]
         nf, kin = w_in.shape
         cout = ws[-1].shape[0]
@@ -118,11 +127,11 @@ class _FieldMLP(torch.autograd.Function):
         d_ws = [None] * ctx.n_w
         d_ws[-1] = torch.zeros_like(ws[-1])
         _wgrad(zs[-1], True, dz, False, nf, cout, passes, d_ws[-1], transpose_out=True)          # d_W_out[c, j] = sum_r dz[r, c] relu(z)[r, j]
-        dzl = _gemm(dz, cout, _pack(ws[-1], nf, cout, True), nf, False, passes, 1, mask=zs[-1])   # (dz . W_out) * [z_last > 0]
+        dzl = _gemm(dz, cout, _pack(ws[-1], nf, cout, True), nf, False, passes, 1, mask_bits=bits[-1])   # (dz . W_out) * [z_last > 0]
         for i in range(ctx.n_w - 2, 0, -1):                                                    # hidden layers W_i: z_{i+1} = W_i relu(z_i)
             d_ws[i] = torch.zeros_like(ws[i])
             _wgrad(dzl, False, zs[i], True, nf, nf, passes, d_ws[i])
-            dzl = _gemm(dzl, nf, _pack(ws[i], nf, nf, True), nf, False, passes, 1, mask=zs[i])
+            dzl = _gemm(dzl, nf, _pack(ws[i], nf, nf, True), nf, False, passes, 1, mask_bits=bits[i])
         # first hidden layer: only its h half [nf, :nf] is a GEMM here; the feature half is the per-image bias (PyTorch side)
         d_ws[0] = torch.zeros_like(ws[0])
         _wgrad(dzl, False, zs[0], True, nf, nf, passes, d_ws[0])
@@ -130,10 +139,13 @@ class _FieldMLP(torch.autograd.Function):
         if ctx.has_bias and need[4]:
             d_bias = torch.empty(ctx.n_img, nf, device=dev)
             _call("b2a_mlp_colsum_segments", (_p(dzl), dzl.stride(0), _p(seg_start), ctx.n_img, nf, _p(d_bias), st))
-        dz0 = _gemm(dzl, nf, _pack(ws[0], nf, nf, True), nf, False, passes, 1, mask=zs[0])
+        dz0 = _gemm(dzl, nf, _pack(ws[0], nf, nf, True), nf, False, passes, 1, mask_bits=bits[0])
         d_w_in = torch.zeros_like(w_in)
         _wgrad(dz0, False, E, False, nf, kin, passes, d_w_in)
-        d_b_in = dz0.sum(0)
+        d_b_in = torch.empty(1, nf, device=dev)                  # column sums of dz0 = one segment [0, N)
+        whole = torch.tensor([0, N], dtype=torch.int64, device=dev) if seg_start is None else torch.stack([seg_start[0], seg_start[-1]])
+        _call("b2a_mlp_colsum_segments", (_p(dz0), dz0.stride(0), _p(whole), 1, nf, _p(d_b_in), st))
+        d_b_in = d_b_in.view(nf)
         d_x = None
         if need[0]:
             dE = _gemm(dz0, nf, _pack(w_in, kin, nf, True), kin, False, passes, 0, ldo=E.shape[1])

@@ -300,14 +300,16 @@ int b2a_render_geometry_bwd(const float* rast, int spp, const float* mtx, const 
  * `packed` (b2a_mlp_packed_bytes), the shared-memory image the GEMM fetches with bulk async copies; N <= 256.
  * rows_gemm: out[rows,N] (row stride ldo) = epilogue(op(A)[rows,K] . W^T) with A fp32 (row stride lda, lda % 4 == 0);
  * relu_on_load: op = max(., 0).  epilogue 0: + bias (nullable; [N], or row bias_rows[r] of a [*,N] table when bias_rows is
- * given); 1: zero where mask_src[r,n] <= 0 (row stride ldm); 2: sigmoid(. + bias).
+ * given); 1: zero where mask_src[r,n] <= 0 (row stride ldm) - or, when mask_bits [rows, ceil16(N)/32 words] is given, where its
+ * bit n is clear (the sign bits an epilogue-0 call wrote through bits_out: 1/32 of the mask bytes); 2: sigmoid(. + bias).
  * ---------------------------------------------------------------------------------------------------------- */
 int b2a_mlp_packed_bytes(int N, int K, size_t* bytes);
 int b2a_mlp_pack_weights(const float* W, int64_t ldw, int N, int K, int transpose, void* packed, size_t packed_bytes,
                          b2a_stream_t stream);
 int b2a_mlp_rows_gemm(const float* A, int64_t lda, int64_t rows, int K, const void* packed, int N, int relu_on_load,
                       int passes, int epilogue, const float* bias, const int32_t* bias_rows, const float* mask_src,
-                      int64_t ldm, float* out, int64_t ldo, b2a_stream_t stream);
+                      int64_t ldm, const uint32_t* mask_bits, uint32_t* bits_out, float* out, int64_t ldo,
+                      b2a_stream_t stream);
 /* wgrad: out[m*ldo + n] (transpose_out: out[n*ldo + m]) += sum_r op(P)[r,m] * op(Q)[r,n] over all rows (the weight gradient
  * dz^T . a of a Linear layer); out is ACCUMULATED with reductions and must be zero-initialised by the caller; M, N <= 256.
  * embed fwd / bwd: the harmonic embedding in front of CoordMLP.in_layer (model/networks/HarmonicEmbedding.py; MLPs.py:75-84):

@@ -20,7 +20,7 @@ def gemm(A, Wp, N, relu=False, passes=3, epi=0, bias=None, bias_rows=None, mask=
     out = torch.full((rows, N), float("nan"), device=dev)
     L.check(lib.b2a_mlp_rows_gemm(A.data_ptr(), A.stride(0), rows, K, Wp.data_ptr(), N, int(relu), passes, epi,
                                   None if bias is None else bias.data_ptr(), None if bias_rows is None else bias_rows.data_ptr(),
-                                  None if mask is None else mask.data_ptr(), 0 if mask is None else mask.stride(0), out.data_ptr(), out.stride(0), st))
+                                  None if mask is None else mask.data_ptr(), 0 if mask is None else mask.stride(0), None, None, out.data_ptr(), out.stride(0), st))
     torch.cuda.synchronize()
     return out
 
@@ -58,11 +58,11 @@ A = torch.randn(rows, 256, device=dev); W = torch.randn(256, 256, device=dev) / 
 out = torch.empty(rows, 256, device=dev)
 for passes in (3, 1):
     for _ in range(3):
-        lib.b2a_mlp_rows_gemm(A.data_ptr(), 256, rows, 256, Wp.data_ptr(), 256, 1, passes, 0, None, None, None, 0, out.data_ptr(), 256, st)
+        lib.b2a_mlp_rows_gemm(A.data_ptr(), 256, rows, 256, Wp.data_ptr(), 256, 1, passes, 0, None, None, None, 0, None, None, out.data_ptr(), 256, st)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20):
-        lib.b2a_mlp_rows_gemm(A.data_ptr(), 256, rows, 256, Wp.data_ptr(), 256, 1, passes, 0, None, None, None, 0, out.data_ptr(), 256, st)
+        lib.b2a_mlp_rows_gemm(A.data_ptr(), 256, rows, 256, Wp.data_ptr(), 256, 1, passes, 0, None, None, None, 0, None, None, out.data_ptr(), 256, st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
     print("passes %d: %.1f us per layer of %d rows: %.1f TFLOP/s (fp32-equivalent), %.1f TFLOP/s of bf16 MMAs, %.0f GB/s" %

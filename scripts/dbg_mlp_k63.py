@@ -10,7 +10,7 @@ nb = ctypes.c_size_t(0); lib.b2a_mlp_packed_bytes(N, K, ctypes.byref(nb))
 Wp = torch.empty(nb.value, dtype=torch.uint8, device=dev)
 L.check(lib.b2a_mlp_pack_weights(W.data_ptr(), K, N, K, 0, Wp.data_ptr(), Wp.numel(), st))
 out = torch.empty(rows, N, device=dev)
-L.check(lib.b2a_mlp_rows_gemm(A.data_ptr(), lda, rows, K, Wp.data_ptr(), N, 0, 3, 0, bias.data_ptr(), None, None, 0, out.data_ptr(), N, st))
+L.check(lib.b2a_mlp_rows_gemm(A.data_ptr(), lda, rows, K, Wp.data_ptr(), N, 0, 3, 0, bias.data_ptr(), None, None, 0, None, None, out.data_ptr(), N, st))
 torch.cuda.synchronize()
 ref = A[:, :K].double() @ W.double().t() + bias.double()
 print("rel err %.2e" % ((out.double() - ref).abs().max() / ref.abs().max()).item())

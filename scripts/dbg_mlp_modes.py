@@ -12,10 +12,10 @@ out = torch.empty(rows, 256, device=dev)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for passes, what in ((3, "full"), (1, "1 pass"), (0, "no MMA"), (-1, "no MMA, no A loads"), (-2, "3 pass, no output stores")):
     for _ in range(3):
-        lib.b2a_mlp_rows_gemm(A.data_ptr(), 256, rows, 256, Wp.data_ptr(), 256, 1, passes, 0, None, None, None, 0, out.data_ptr(), 256, st)
+        lib.b2a_mlp_rows_gemm(A.data_ptr(), 256, rows, 256, Wp.data_ptr(), 256, 1, passes, 0, None, None, None, 0, None, None, out.data_ptr(), 256, st)
     e0.record()
     for _ in range(20):
-        lib.b2a_mlp_rows_gemm(A.data_ptr(), 256, rows, 256, Wp.data_ptr(), 256, 1, passes, 0, None, None, None, 0, out.data_ptr(), 256, st)
+        lib.b2a_mlp_rows_gemm(A.data_ptr(), 256, rows, 256, Wp.data_ptr(), 256, 1, passes, 0, None, None, None, 0, None, None, out.data_ptr(), 256, st)
     e1.record(); torch.cuda.synchronize()
     print("%-28s %.1f us" % (what, e0.elapsed_time(e1) / 20 * 1e3))
 # reference points: plain copy of the same bytes
