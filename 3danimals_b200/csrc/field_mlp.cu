@@ -410,27 +410,30 @@ __device__ __forceinline__ void mn_store(uint8_t* hi_img, uint8_t* lo_img, int M
     }
 }
 
-// QI = Q items per thread = (KC/8) * (Npad/32) / 8 warps: 4 for Npad 256, 2 for 128, 1 for 64; Npad <= 32 -> 1 (half the warps idle)
-template <int QI>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_wgrad_kernel(WgradParams W)
+// PI / QI = P / Q items per thread = (KC/8) * (width/32) / 8 warps: 4 for width 256, 2 for 128, 1 for 64; <= 32 -> 1 (half the warps idle).
+// One CTA covers every 128-row M tile of the result (P is staged Mpad wide, one tensor-memory accumulator per M tile), so each operand
+// is read from HBM exactly once.
+template <int PI, int QI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) mlp_wgrad_kernel(WgradParams W)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int PI = (KC / 8) * (TILE_M / 32) / (GEMM_THREADS / 32);     // P items per thread (2)
-    const uint32_t p_bytes = KC * TILE_M * 2, q_bytes = (uint32_t)KC * W.Npad * 2;
+    const int Mpad = PI * 64;                                              // 128 or 256
+    const int mtiles = Mpad / TILE_M;
+    const uint32_t p_bytes = (uint32_t)KC * Mpad * 2, q_bytes = (uint32_t)KC * W.Npad * 2;
     const uint32_t stage_bytes = 2 * p_bytes + 2 * q_bytes;
     __shared__ __align__(8) uint64_t mma_done[2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.y * TILE_M;
     const int64_t r_begin = (int64_t)blockIdx.x * W.rows_per_cta;
     int64_t r_end = r_begin + W.rows_per_cta;
     if (r_end > W.rows) r_end = W.rows;
     if (r_begin >= r_end) return;
     const int nchunks = (int)((r_end - r_begin + KC - 1) / KC);
-    const uint32_t tmem_cols = W.Npad <= 32 ? 32u : (W.Npad <= 64 ? 64u : (W.Npad <= 128 ? 128u : 256u));
+    const uint32_t acc_cols = W.Npad < 32 ? 32u : (uint32_t)W.Npad;       // columns of one accumulator (a power of two >= 32)
+    const uint32_t tmem_cols = acc_cols * mtiles;
 
     float vp[PI][8], vq[QI][8];
-    mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r_begin, m0, warp, lane, vp);
+    mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r_begin, 0, warp, lane, vp);
     mn_load<QI>(W.Qm, W.ldq, r_end, W.N, r_begin, 0, warp, lane, vq);
     if (tid == 0) {
         mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
@@ -448,11 +451,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_wgrad_kernel(WgradParams 
         const int s = c & 1;
         uint8_t* st = smem + (size_t)s * stage_bytes;
         if (c >= 2) mbar_wait(&mma_done[s], ((c >> 1) - 1) & 1);
-        mn_store<PI>(st, st + p_bytes, TILE_M, W.relu_p, warp, lane, vp);
+        mn_store<PI>(st, st + p_bytes, Mpad, W.relu_p, warp, lane, vp);
         mn_store<QI>(st + 2 * p_bytes, st + 2 * p_bytes + q_bytes, W.Npad, W.relu_q, warp, lane, vq);
         if (c + 1 < nchunks) {
             const int64_t r0 = r_begin + (int64_t)(c + 1) * KC;
-            mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r0, m0, warp, lane, vp);
+            mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r0, 0, warp, lane, vp);
             mn_load<QI>(W.Qm, W.ldq, r_end, W.N, r0, 0, warp, lane, vq);
         }
         fence_proxy_async();
@@ -460,15 +463,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_wgrad_kernel(WgradParams 
         if (tid == 0) {
             tc_fence_after();
             const uint32_t p_hi = smem_u32(st), p_lo = p_hi + p_bytes, q_hi = p_hi + 2 * p_bytes, q_lo = q_hi + q_bytes;
-            const uint32_t p_lbo = TILE_M * 16, q_lbo = (uint32_t)W.Npad * 16;
+            const uint32_t p_lbo = (uint32_t)Mpad * 16, q_lbo = (uint32_t)W.Npad * 16;
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ks++) {
-                const uint64_t dph = smem_desc(p_hi + ks * 2 * p_lbo, p_lbo, 128), dpl = smem_desc(p_lo + ks * 2 * p_lbo, p_lbo, 128);
                 const uint64_t dqh = smem_desc(q_hi + ks * 2 * q_lbo, q_lbo, 128), dql = smem_desc(q_lo + ks * 2 * q_lbo, q_lbo, 128);
-                umma(tmem_d, dph, dqh, idesc, (c | ks) != 0);
-                if (W.passes == 3) {
-                    umma(tmem_d, dph, dql, idesc, 1);
-                    umma(tmem_d, dpl, dqh, idesc, 1);
+                for (int mt = 0; mt < mtiles; mt++) {                      // M tile mt = mn groups [16 mt, 16 mt + 16) of the P image
+                    const uint32_t po = ks * 2 * p_lbo + mt * (TILE_M / 8) * 128;
+                    const uint64_t dph = smem_desc(p_hi + po, p_lbo, 128), dpl = smem_desc(p_lo + po, p_lbo, 128);
+                    const uint32_t td = tmem_d + mt * acc_cols;
+                    umma(td, dph, dqh, idesc, (c | ks) != 0);
+                    if (W.passes == 3) {
+                        umma(td, dph, dql, idesc, 1);
+                        umma(td, dpl, dqh, idesc, 1);
+                    }
                 }
             }
             umma_commit(&mma_done[s]);
@@ -479,12 +486,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_wgrad_kernel(WgradParams 
     tc_fence_after();
     // epilogue: thread t of quadrant q holds row m0 + 32q + t, 32 consecutive n: one reduction per element into the shared result
     const int quad = warp & 3;
-    const int m = m0 + quad * 32 + lane;
     const int ngroups = (W.Npad + 31) / 32;
-    for (int g = warp >> 2; g < ngroups; g += 2) {
+    for (int gi = warp >> 2; gi < ngroups * mtiles; gi += 2) {
+        const int mt = gi / ngroups, g = gi - mt * ngroups;
+        const int m = mt * TILE_M + quad * 32 + lane;
         float v[32];
         __syncwarp();
-        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 32), v);
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * acc_cols + g * 32), v);
         if (m < W.M) {
             const int n0 = g * 32;
             if (!W.transpose_out && n0 + 32 <= W.N && (W.ldo & 3) == 0) {
@@ -649,22 +657,28 @@ B2A_API int b2a_mlp_wgrad(const float* P, int64_t ldp, int relu_p, const float* 
     W.Npad = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));      // whole warp items of 32 columns
     W.passes = passes; W.out = out; W.ldo = ldo; W.transpose_out = transpose_out;
     const int mtiles = (M + TILE_M - 1) / TILE_M;
-    int64_t nsplit = (2 * 148) / mtiles;                                   // two CTAs per SM
+    int64_t nsplit = 148;                                                  // one persistent CTA per SM
     int64_t per = (rows + nsplit - 1) / nsplit;
     per = (per + KC - 1) / KC * KC;
     if (per < 8 * KC) per = 8 * KC;
     W.rows_per_cta = per;
     nsplit = (rows + per - 1) / per;
-    const int smem = 2 * (2 * KC * TILE_M * 2 + 2 * KC * W.Npad * 2);
-    const dim3 grid((unsigned)nsplit, (unsigned)mtiles);
-#define WG_LAUNCH(QI)                                                                                                \
-    do {                                                                                                             \
-        B2A_CUDA_OK(cudaFuncSetAttribute(mlp_wgrad_kernel<QI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        mlp_wgrad_kernel<QI><<<grid, GEMM_THREADS, smem, stream>>>(W);                                               \
+    const int smem = 2 * (2 * KC * mtiles * TILE_M * 2 + 2 * KC * W.Npad * 2);
+    const dim3 grid((unsigned)nsplit);
+#define WG_LAUNCH(PI, QI)                                                                                                \
+    do {                                                                                                                 \
+        B2A_CUDA_OK(cudaFuncSetAttribute(mlp_wgrad_kernel<PI, QI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        mlp_wgrad_kernel<PI, QI><<<grid, GEMM_THREADS, smem, stream>>>(W);                                               \
     } while (0)
-    if (W.Npad == 256) WG_LAUNCH(4);
-    else if (W.Npad == 128) WG_LAUNCH(2);
-    else WG_LAUNCH(1);
+    if (mtiles == 2) {
+        if (W.Npad == 256) WG_LAUNCH(4, 4);
+        else if (W.Npad == 128) WG_LAUNCH(4, 2);
+        else WG_LAUNCH(4, 1);
+    } else {
+        if (W.Npad == 256) WG_LAUNCH(2, 4);
+        else if (W.Npad == 128) WG_LAUNCH(2, 2);
+        else WG_LAUNCH(2, 1);
+    }
 #undef WG_LAUNCH
     B2A_LAUNCH_OK();
     return 0;
