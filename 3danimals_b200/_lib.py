@@ -98,6 +98,36 @@ def fast():
     return _fast
 
 
+_cpp = False
+
+
+def cpp_nodes():
+    """The C++ autograd layer (csrc/autograd_nodes.cpp, build.py build_autograd), or None: same C-ABI underneath, the nodes' host
+    work (allocation, bookkeeping, autograd engine hand-off) in C++ instead of Python.  B2A_CPP_NODES=0 disables it."""
+    global _cpp
+    if _cpp is False:
+        _cpp = None
+        if os.environ.get("B2A_CPP_NODES", "1") != "0":
+            lib()
+            try:
+                import importlib.machinery
+                import importlib.util
+                import torch  # noqa: F401  (libtorch must be loaded first)
+                from . import build as _build
+                path = _build.autograd_path()
+                if not os.path.isfile(path):
+                    path = _build.build_autograd()
+                if path and os.path.isfile(path):
+                    loader = importlib.machinery.ExtensionFileLoader(_build.AUTOGRAD_NAME, path)
+                    spec = importlib.util.spec_from_loader(_build.AUTOGRAD_NAME, loader)
+                    mod = importlib.util.module_from_spec(spec)
+                    loader.exec_module(mod)
+                    _cpp = mod
+            except Exception:
+                _cpp = None
+    return _cpp
+
+
 def check(rc):
     if rc != 0:
         raise B2AError(lib().b2a_last_error_string().decode("utf-8", "replace") or "libb2a error %d" % rc)

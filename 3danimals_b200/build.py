@@ -144,6 +144,47 @@ def build_fastcall(force=False):
     return target
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# C++ autograd layer (csrc/autograd_nodes.cpp): torch::autograd::Function nodes over the C-ABI.  Host code only (g++ against the
+# torch headers, linked to libb2a.so); optional - ops.py falls back to its Python `Function`s when the module is absent.
+# ----------------------------------------------------------------------------------------------------------------
+AUTOGRAD_NAME = "_b2a_autograd"
+
+
+def autograd_path():
+    import sysconfig
+    return os.path.join(OUT_DIR, AUTOGRAD_NAME + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_autograd(force=False, verbose=False):
+    import sysconfig
+    src = os.path.join(SRC_DIR, "autograd_nodes.cpp")
+    target = autograd_path()
+    deps = [src, os.path.join(INCLUDE, "b2a.h")]
+    if not force and os.path.isfile(target) and all(os.path.getmtime(target) >= os.path.getmtime(d) for d in deps):
+        return target
+    try:
+        import torch
+        from torch.utils import cpp_extension as ce
+    except Exception:
+        return None
+    if not os.path.isfile(LIB):
+        return None
+    inc = [sysconfig.get_paths().get("include", "")] + ce.include_paths() + ["/usr/local/cuda/include"]
+    torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = ([os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=" + AUTOGRAD_NAME,
+            "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+           + ["-I" + i for i in inc if i] + [src, "-o", target, "-L", OUT_DIR, "-lb2a", "-L", torch_lib, "-ltorch", "-ltorch_cpu", "-ltorch_python", "-lc10",
+                                             "-lc10_cuda", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + torch_lib])
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr[-6000:])
+    if res.returncode != 0:
+        return None
+    return target
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
     print(build_fastcall(force="--force" in sys.argv))
+    print(build_autograd(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

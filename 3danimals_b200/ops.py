@@ -91,6 +91,22 @@ class CallStats:
         self.launches = 0
         self.calls = {}
         self.events = []
+        cpp = _lib.cpp_nodes()
+        if cpp is not None:
+            cpp.reset_stats()
+
+    def total_launches(self):
+        """Kernels launched through the Python nodes and through the C++ autograd layer."""
+        cpp = _lib.cpp_nodes()
+        return self.launches + (cpp.launches() if cpp is not None else 0)
+
+    def all_calls(self):
+        cpp = _lib.cpp_nodes()
+        out = dict(self.calls)
+        if cpp is not None:
+            for k, v in cpp.calls().items():
+                out[k] = out.get(k, 0) + v
+        return out
 
     def durations_ms(self):
         """{(name, tag): [ms, ...]} - call after torch.cuda.synchronize()."""
@@ -101,6 +117,11 @@ class CallStats:
 
 
 stats = CallStats()
+
+
+def _cpp():
+    """The C++ autograd nodes, unless per-call event timing is on (the Python nodes carry the timing hooks)."""
+    return None if stats.timing else _lib.cpp_nodes()
 
 
 _fn_cache = {}
@@ -345,12 +366,22 @@ class _LBS(torch.autograd.Function):
 def lbs_bf(v_pos, bones, angles, chain_ptr, chain_ids, temperature=1.0):
     """The [batch, frames] form skinning() receives: v_pos [B|1,F|1,V,3] (both 1 or both full), bones [B|1,F|1,K,2,3],
     angles [B,F,K,3] -> posed verts [B,F,V,3], posed bones [B,F,K,2,3]."""
+    cpp = _cpp()
+    if cpp is not None:
+        B, Fr, K = angles.shape[0], angles.shape[1], angles.shape[2]
+        V = v_pos.shape[-2]
+        out, posed = cpp.lbs(v_pos.reshape(-1, V, 3), bones.reshape(-1, K, 2, 3), angles.reshape(-1, K, 3), chain_ptr, chain_ids, float(temperature))
+        return out.view(B, Fr, V, 3), posed.view(B, Fr, K, 2, 3)
     out, posed, _ = _LBS.apply(v_pos, bones, angles, chain_ptr, chain_ids, temperature, False, (angles.shape[0], angles.shape[1]))
     return out, posed
 
 
 def lbs(v_pos, bones, angles, chain_ptr, chain_ids, temperature=1.0, want_weights=False):
     """v_pos [Bv,V,3], bones [Bb,K,2,3], angles [B,K,3] -> posed verts [B,V,3], posed bones [B,K,2,3], weights [K,Bw,V]|None."""
+    cpp = _cpp()
+    if cpp is not None and not want_weights:
+        out, posed = cpp.lbs(v_pos, bones, angles, chain_ptr, chain_ids, float(temperature))
+        return out, posed, None
     out, posed, w = _LBS.apply(v_pos, bones, angles, chain_ptr, chain_ids, temperature, want_weights, None)
     return out, posed, (w if want_weights else None)
 
@@ -407,6 +438,9 @@ class _VertexNormals(torch.autograd.Function):
 
 def vertex_normals(v_pos, tri):
     """v_pos [B,V,3], tri [F,3] -> smooth area-weighted vertex normals [B,V,3]."""
+    cpp = _cpp()
+    if cpp is not None:
+        return cpp.vertex_normals(v_pos, _idx32(tri, "tri"))
     return _VertexNormals.apply(v_pos, _idx32(tri, "tri"))
 
 
@@ -677,6 +711,11 @@ def composite_antialias_pair(color_w, bg_w, keep_w, color_n, bg_n, keep_n, rast,
     (render.py:334).  Requires the render's prepared context (ops.antialias_prepare)."""
     if not pair_supported(color_w, color_n, aa_ctx):
         raise _lib.B2AError("composite_antialias_pair: unsupported key combination (use composite_antialias per key)")
+    cpp = _cpp()
+    if (cpp is not None and nchw and color_w.shape[2] % 32 == 0 and int(keep_w) == color_w.shape[-1]
+            and int(keep_n) in (color_n.shape[-1], color_n.shape[-1] + 1)):
+        ow, on = cpp.antialias_pair(color_w, color_n, bg_w, bg_n, pos, int(keep_w), int(keep_n), aa_ctx)
+        return ow, on
     return _AntialiasPair.apply(color_w, color_n, bg_w, bg_n, pos, int(keep_w), int(keep_n), aa_ctx, _f32(rast, "rast"), _idx32(tri, "tri"),
                                 _idx32(opp, "opp"), bool(nchw))
 
@@ -983,7 +1022,13 @@ def render_geometry(v_pos, v_nrm, prior_pos, mtx, w2c, campos, tri, opp, resolut
                     need_aa=True):
     """-> (v_pos_clip [B,V,4], rast [B,H*spp,W*spp,4], aa_ctx | None, dict of g-buffers [B,H,W,3]).  rast is differentiable
     (barycentric gradients of a later ops.interpolate flow into the clip positions, as with nvdiffrast)."""
-    outs = _RenderGeometry.apply(v_pos, v_nrm, prior_pos, mtx, w2c, campos, _idx32(tri, "tri"), _idx32(opp, "opp"), int(resolution[0]),
-                                 int(resolution[1]), int(spp), bool(two_sided), tuple(want), bool(need_aa))
+    cpp = _cpp()
+    if cpp is not None:
+        mask = sum(1 << i for i, k in enumerate(GB_KEYS) if k in want)
+        outs = cpp.render_geometry(v_pos, v_nrm, prior_pos, mtx, w2c, campos, _idx32(tri, "tri"), _idx32(opp, "opp"), int(resolution[0]),
+                                   int(resolution[1]), int(spp), bool(two_sided), mask, bool(need_aa))
+    else:
+        outs = _RenderGeometry.apply(v_pos, v_nrm, prior_pos, mtx, w2c, campos, _idx32(tri, "tri"), _idx32(opp, "opp"), int(resolution[0]),
+                                     int(resolution[1]), int(spp), bool(two_sided), tuple(want), bool(need_aa))
     clip, rast, aa = outs[0], outs[1], outs[2]
     return clip, rast, (aa if aa.numel() else None), dict(zip([k for k in GB_KEYS if k in want], outs[3:]))

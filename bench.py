@@ -393,7 +393,7 @@ def run_ours(args):
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    launches = ops.stats.launches
+    launches = ops.stats.total_launches()
     reduced_per_step = buckets.bytes_reduced // max(args.steps, 1)
     ms_per_step = float(ms.item()) / args.steps
     value = world * B / (ms_per_step * 1e-3)
@@ -628,7 +628,7 @@ def run_c4(args, dev, rank, world):
     torch.cuda.synchronize()
     ops.stats.timing = False
     durs = ops.stats.durations_ms()
-    launches_per_iter = ops.stats.launches // timed_steps     # the graph replays exactly the kernels of one eager iteration
+    launches_per_iter = ops.stats.total_launches() // timed_steps     # the graph replays exactly the kernels of one eager iteration
     with torch.no_grad():
         rot = graphs.captured_render(inst, prior, pipe.AnalyticField(w_kd, True), light, (IMG, IMG), (mvp, w2c, campos), spp=SPP,
                                      render_modes=("shaded", "shading", "kd"))

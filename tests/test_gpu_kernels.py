@@ -536,7 +536,7 @@ def test_composite_antialias_pair_oracle(cuda, image, layout, keep_n):
     assert rel_err(cn.grad.cpu().numpy(), cts[1].grad.numpy()) < TOL
     assert np.abs(pt.grad.numpy()).max() > 0
     assert rel_err(pd.grad.cpu().numpy(), pt.grad.numpy()) < TOL
-    calls = ops.stats.calls
+    calls = ops.stats.all_calls()
     assert calls.get("b2a_antialias_pair_fwd", 0) >= 1
 
 
