@@ -95,6 +95,11 @@ class CallStats:
         if cpp is not None:
             cpp.reset_stats()
 
+    def count(self, name, launches):
+        """A C-ABI call made outside _call (the peer-memory all-reduce in parallel.py)."""
+        self.launches += launches
+        self.calls[name] = self.calls.get(name, 0) + 1
+
     def total_launches(self):
         """Kernels launched through the Python nodes and through the C++ autograd layer."""
         cpp = _lib.cpp_nodes()

@@ -358,7 +358,7 @@ def run_ours(args):
     def reduce_and_wait(d_sdf):
         if buckets.active:
             buckets.view(last, n_sdf).copy_(d_sdf.reshape(-1))
-            buckets.launch_many((last,))
+            buckets.launch_many((last,), inline=True)       # nothing left to overlap with: on the compute stream (peer-memory backend)
             buckets.wait()
 
     def step():
@@ -522,14 +522,20 @@ def run_ours(args):
     if rank == 0:
         run = dict(autograd_threads=args.autograd_threads, mesh_verts=st["V"], mesh_faces=st["F"], covered_pixels=n_cov, warmup_done=nwarm,
                    field=("CoordMLP texture 8x256 + DINO 5x256 (M1b, %s)" % mlp_math) if args.mlps else "analytic (M1a)",
-                   parallelism="image-parallel dp%d; DDP stand-in: %d B of fp32 gradients all-reduced per step in %d buckets (NCCL AVG, side stream, "
-                               "overlapped with the backward; d_sdf in the last bucket)" % (world, reduced_per_step, len(buckets.buckets)),
-                   allreduce_bytes_per_step=reduced_per_step)
+                   parallelism="image-parallel dp%d; DDP stand-in: %d B of fp32 gradients all-reduced (averaged) per step in %d buckets (%s; side "
+                               "stream, overlapped with the backward; d_sdf in the last bucket, reduced after the backward)"
+                               % (world, reduced_per_step, len(buckets.buckets),
+                                  {"p2p": "libb2a peer-memory kernel over NVLink, one launch per bucket set", "nccl": "NCCL AVG, coalesced",
+                                   "none": "single rank: no exchange"}[buckets.backend]),
+                   allreduce_bytes_per_step=reduced_per_step, allreduce_backend=buckets.backend)
         line = dict(metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=args.warmup if args.warmup >= 3 else nwarm,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=W, run=run, clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu, impl="ours")
         print(json.dumps(line))
     if world > 1:
+        if buckets.peer is not None:
+            dist.barrier()
+            buckets.peer.close()
         dist.destroy_process_group()
 
 

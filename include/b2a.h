@@ -341,6 +341,22 @@ int b2a_obj_format(const float* v_pos, int64_t n_pos, const float* v_tex, int64_
                    int64_t n_faces, const char* mtl_name, int64_t name_bytes, char* out, size_t capacity,
                    size_t* written, int threads);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Gradient all-reduce over NVLink peer memory (csrc/allreduce_p2p.cu).  Replaces, for the ranks of one node, the
+ * DistributedDataParallel / accelerate gradient all-reduce the reference's trainer relies on (model/trainer/Trainer.py:170-180,
+ * accelerator.prepare + accelerator.backward): average of n floats over `world` ranks in ONE kernel launch per rank.
+ * b2a_p2p_alloc: a zero-filled device buffer other processes can map, and its 64-byte IPC handle; b2a_p2p_open maps a
+ * peer's buffer into this process on the current device.  b2a_allreduce_p2p: bufs / flags are host arrays of `world`
+ * device pointers (own buffer at index `rank`); flags: 16 zero-initialised 32-bit words per rank per channel;
+ * local_counter: one zero-initialised device word per channel; epoch = 1, 2, 3, ... per channel, equal on all ranks.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_p2p_alloc(size_t bytes, void** ptr, void* handle64);
+int b2a_p2p_open(const void* handle64, void** ptr);
+int b2a_p2p_close(void* ptr);
+int b2a_p2p_free(void* ptr);
+int b2a_allreduce_p2p(const void* const* bufs, const void* const* flags, int rank, int world, int64_t n, int epoch,
+                      void* local_counter, b2a_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
