@@ -49,21 +49,27 @@ __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned target)
     __syncthreads();
 }
 
-// cross-rank barrier: block 0 announces `epoch` in every peer's flag row and waits for every peer's announcement in its own
-__device__ __forceinline__ void rank_barrier(const P2PArgs& a, int phase)
+// cross-rank barrier: block 0 announces `epoch` in every peer's flag row and waits for every peer's announcement in its own.
+// A peer that never arrives (its process died) must not hang this GPU: after SPIN_LIMIT cycles (~10 s) the wait gives up and
+// raises the channel's error word (local_counter[1]), which the host reads when it closes the peer memory.
+constexpr long long SPIN_LIMIT = 20000000000ll;
+__device__ __forceinline__ void rank_barrier(const P2PArgs& a, int phase, unsigned* error_word)
 {
     if (blockIdx.x == 0 && threadIdx.x < a.world) {
         const int peer = threadIdx.x;
         __threadfence_system();
         flag_store(a.flags[peer] + phase * MAX_RANKS + a.rank, a.epoch);
-        while (flag_load(a.flags[a.rank] + phase * MAX_RANKS + peer) < a.epoch) {}
+        const long long t0 = clock64();
+        while (flag_load(a.flags[a.rank] + phase * MAX_RANKS + peer) < a.epoch) {
+            if (clock64() - t0 > SPIN_LIMIT) { atomicExch(error_word, 1u); break; }
+        }
     }
 }
 
 __global__ void __launch_bounds__(512) allreduce_p2p_kernel(P2PArgs a, unsigned* local_counter, unsigned counter_base)
 {
     // phase 0: everybody's gradients are in place (block 0 talks to the peers, then releases this rank's other blocks)
-    rank_barrier(a, 0);
+    rank_barrier(a, 0, local_counter + 1);
     grid_sync(local_counter, counter_base + gridDim.x);
     const int64_t per = (a.n4 + a.world - 1) / a.world;
     const int64_t lo = per * a.rank, hi = lo + per < a.n4 ? lo + per : a.n4;
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(512) allreduce_p2p_kernel(P2PArgs a, unsigned*
     // phase 1: my slice has been written everywhere; wait until every peer's slice has landed here
     __threadfence_system();
     grid_sync(local_counter, counter_base + 2 * gridDim.x);
-    rank_barrier(a, 1);
+    rank_barrier(a, 1, local_counter + 1);
 }
 
 }  // namespace
@@ -129,8 +135,8 @@ B2A_API int b2a_p2p_free(void* ptr)
 }
 
 // bufs / flags: `world` device pointers each (this rank's own at index `rank`): every rank's buffer of n floats (n % 4 == 0, 16-byte
-// aligned) and its 2*8 zero-initialised flag words for this channel; local_counter: this rank's zero-initialised device word for this
-// channel; epoch: 1, 2, 3, ... per channel (the same on every rank for the same collective; a channel always reduces the same n).
+// aligned) and its 2*8 zero-initialised flag words for this channel; local_counter: this rank's two zero-initialised device words for this
+// channel (grid-barrier counter, error word - nonzero after a peer failed to arrive within ~10 s); epoch: 1, 2, 3, ... per channel (the same on every rank for the same collective; a channel always reduces the same n).
 // Averages in place on every rank.  Every rank of the group must launch it; the kernel spins until the peers arrive.
 B2A_API int b2a_allreduce_p2p(const void* const* bufs, const void* const* flags, int rank, int world, int64_t n, int epoch, void* local_counter,
                               b2a_stream_t stream_)

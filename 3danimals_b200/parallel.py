@@ -100,12 +100,12 @@ class PeerMemory:
                             self.ptrs[p] = q.value
             except Exception:       # noqa: BLE001
                 good = False
-        agree = torch.tensor([1.0 if good else 0.0], device=self.device)
+        agree = torch.tensor([1.0 if good else 0.0], device=self.device if dist.get_backend(group) == "nccl" else "cpu")
         dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=group)
         self.ok = bool(agree.item() > 0.5)
         if self.ok:
             self.flat = torch.as_tensor(_DeviceArray(self.own, self.n), device=self.device)
-            self.counters = torch.zeros(self.CHANNELS, dtype=torch.int32, device=self.device)
+            self.counters = torch.zeros(2 * self.CHANNELS, dtype=torch.int32, device=self.device)
             dist.barrier(group=group)
         else:
             self.close()
@@ -121,20 +121,24 @@ class PeerMemory:
             i = len(self.channels)
             bufs = (ctypes.c_void_p * self.world)(*[p + 4 * key[0] for p in self.ptrs])
             flags = (ctypes.c_void_p * self.world)(*[p + 4 * self.n + 64 * i for p in self.ptrs])
-            ch = self.channels[key] = [bufs, flags, self.counters.data_ptr() + 4 * i, 0]
+            ch = self.channels[key] = [bufs, flags, self.counters.data_ptr() + 8 * i, 0]
         ch[3] += 1
         _lib.check(_lib.lib().b2a_allreduce_p2p(ch[0], ch[1], self.rank, self.world, key[1] - key[0], ch[3], ch[2], stream))
         ops.stats.count("b2a_allreduce_p2p", 1)
 
     def close(self):
+        """Unmap the peers' buffers and free this rank's; raises if a collective gave up waiting for a peer (results undefined)."""
         from . import _lib
         lib = _lib.lib()
+        failed = self.ok and self.own is not None and bool(self.counters[1::2].any().item())
         for p, q in enumerate(self.ptrs):
             if q is not None and p != self.rank:
                 lib.b2a_p2p_close(q)
         if self.own is not None:
             lib.b2a_p2p_free(self.own)
         self.ptrs, self.own = [None] * self.world, None
+        if failed:
+            raise _lib.B2AError("b2a_allreduce_p2p: a peer rank did not arrive within the spin limit; reduced gradients are undefined")
 
 
 class GradientBuckets:

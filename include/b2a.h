@@ -348,7 +348,8 @@ int b2a_obj_format(const float* v_pos, int64_t n_pos, const float* v_tex, int64_
  * b2a_p2p_alloc: a zero-filled device buffer other processes can map, and its 64-byte IPC handle; b2a_p2p_open maps a
  * peer's buffer into this process on the current device.  b2a_allreduce_p2p: bufs / flags are host arrays of `world`
  * device pointers (own buffer at index `rank`); flags: 16 zero-initialised 32-bit words per rank per channel;
- * local_counter: one zero-initialised device word per channel; epoch = 1, 2, 3, ... per channel, equal on all ranks.
+ * local_counter: two zero-initialised device words per channel (grid-barrier counter; error word, nonzero after a peer
+ * failed to arrive within ~10 s); epoch = 1, 2, 3, ... per channel, equal on all ranks.
  * ---------------------------------------------------------------------------------------------------------- */
 int b2a_p2p_alloc(size_t bytes, void** ptr, void* handle64);
 int b2a_p2p_open(const void* handle64, void** ptr);
