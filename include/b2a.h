@@ -342,6 +342,18 @@ int b2a_obj_format(const float* v_pos, int64_t n_pos, const float* v_tex, int64_
                    size_t* written, int threads);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Articulation-angle constraints (csrc/articulation.cu).  Replaces InstancePredictorBase.apply_articulation_constraints
+ * (model/predictors/InstancePredictorBase.py:435-511) and Fauna's form (InstancePredictorFauna.py:149-212 + :225-228):
+ * out = post_S(..post_1(tanh(pre_P(..pre_1(x))))), every stage one fp32 multiplication (division where bit j of
+ * post_div_mask is set) by table[stage][bone][axis].  x, out, d_out, d_x: [rows, K, 3]; pre [n_pre,K,3], post [n_post,K,3].
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_articulation_constraints_fwd(const float* x, const float* pre, int n_pre, const float* post, int n_post,
+                                     int post_div_mask, int64_t rows, int K, float* out, b2a_stream_t stream);
+int b2a_articulation_constraints_bwd(const float* x, const float* pre, int n_pre, const float* post, int n_post,
+                                     int post_div_mask, int64_t rows, int K, const float* d_out, float* d_x,
+                                     b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Gradient all-reduce over NVLink peer memory (csrc/allreduce_p2p.cu).  Replaces, for the ranks of one node, the
  * DistributedDataParallel / accelerate gradient all-reduce the reference's trainer relies on (model/trainer/Trainer.py:170-180,
  * accelerator.prepare + accelerator.backward): average of n floats over `world` ranks in ONE kernel launch per rank.

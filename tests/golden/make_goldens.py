@@ -300,6 +300,60 @@ def raster_case():
     np.savez_compressed(os.path.join(OUT, "raster_scenes.npz"), **out)
 
 
+def _reference_methods(path, names):
+    """The named methods of the first class in a reference source file, compiled on their own (the module imports a ViT stack)."""
+    import ast
+    tree = ast.parse(open(path).read())
+    ns = {"torch": torch, "np": np, "print": lambda *a, **k: None}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            mod = ast.Module(body=[node], type_ignores=[])
+            exec(compile(mod, path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def articulation_configs():
+    """(name, cfg_articulation, cfg_additional or None, total_iter): the shipped configs (config/model/*.yaml, config/*.yaml overrides)
+    plus the Fauna-constraint and late-iteration branches no shipped config enables."""
+    from types import SimpleNamespace as NS
+    horse = dict(num_body_bones=8, num_leg_bones=3, num_legs=4, output_multiplier=0.1, static_root_bones=False, constrain_legs=True,
+                 use_fauna_constraints=False, extra_constraints=False, max_arti_angle=60)
+    add = dict(iter_leg_rotation_start=300000, forbid_leg_rotate=True, small_leg_angle=True, reg_body_rotate_mult=0.1)
+    return [("magicpony_horse", NS(**horse), None, 0),
+            ("magicpony_bird", NS(**dict(horse, num_leg_bones=0, static_root_bones=True, max_arti_angle=45)), None, 0),
+            ("ponymation", NS(**dict(horse, extra_constraints=True)), None, 0),
+            ("base_fauna_constraints", NS(**dict(horse, use_fauna_constraints=True, static_root_bones=True)), None, 0),
+            ("fauna_early", NS(**dict(horse, constrain_legs=False)), NS(**add), 1000),
+            ("fauna_late", NS(**dict(horse, constrain_legs=False, static_root_bones=True)), NS(**add), 300001),
+            ("fauna_late_large_legs", NS(**dict(horse, constrain_legs=False)), NS(**dict(add, small_leg_angle=False)), 400000)]
+
+
+def articulation_case():
+    """InstancePredictorBase.apply_articulation_constraints and Fauna's sequence, the reference's own methods on CPU tensors."""
+    from types import SimpleNamespace as NS
+    root = os.path.join(reference_loader.REFERENCE_ROOT, "model", "predictors")
+    (base,) = _reference_methods(os.path.join(root, "InstancePredictorBase.py"), ["apply_articulation_constraints"])
+    f_con, f_reg = _reference_methods(os.path.join(root, "InstancePredictorFauna.py"), ["apply_articulation_constraints", "apply_fauna_articulation_regularizer"])
+    out = {}
+    for name, cfg, add, it in articulation_configs():
+        K = cfg.num_body_bones + cfg.num_leg_bones * cfg.num_legs
+        rng = np.random.RandomState(len(name))
+        x = (rng.randn(3, 2, K, 3) * 8).astype(np.float32)
+        g = rng.randn(3, 2, K, 3).astype(np.float32)
+        xt = torch.from_numpy(x.copy()).requires_grad_(True)
+        self = NS(cfg_articulation=cfg, cfg_additional=add)
+        if add is None:
+            y = base(self, xt * 1.0)                    # the method scales its argument in place: hand it a non-leaf copy
+        else:
+            a = xt * 1.0
+            a *= cfg.output_multiplier                  # InstancePredictorFauna.py:228-229
+            a = a.tanh()
+            y = f_reg(self, f_con(self, a, it), it)
+        y.backward(torch.from_numpy(g))
+        out[name + ":x"], out[name + ":g"], out[name + ":y"], out[name + ":d_x"] = x, g, y.detach().numpy(), xt.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "articulation.npz"), **out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     if "--only-new" not in sys.argv:
@@ -309,6 +363,7 @@ if __name__ == "__main__":
         light_case()
         fauna_bones_case()
     obj_case()
+    articulation_case()
     normals_case()
     raster_case()
     geometry_module_case()

@@ -233,6 +233,34 @@ def test_magicpony_chain_through_reference_callers(ref, cuda):
     print("reference-caller chain: worst relative L2 gradient error per network", worst)
 
 
+def test_articulation_constraints_installed_on_the_reference_class(ref, cuda):
+    """predictors.install puts the one-kernel constraints on the reference's InstancePredictorBase; its own method, run on the same
+    device tensors, is the checker (values and gradient), for the horse config and the bird config (`static_root_bones`)."""
+    P = pkg("predictors")
+    cls = ref.IPB.InstancePredictorBase
+    original = cls.apply_articulation_constraints
+    try:
+        for kw in (dict(), dict(n_legs=0, n_leg_bones=0, mode="z_minmax")):
+            pred = _instance_predictor(ref, cuda, **kw)
+            if kw:
+                pred.cfg_articulation.static_root_bones = True
+            K = pred.num_bones
+            torch.manual_seed(K)
+            x, g = torch.randn(BATCH, 1, K, 3, device=cuda) * 8, torch.randn(BATCH, 1, K, 3, device=cuda)
+            res = []
+            for method in (original, P.apply_articulation_constraints):
+                cls.apply_articulation_constraints = method
+                xr = x.clone().requires_grad_(True)
+                y = pred.apply_articulation_constraints(xr * 1.0)          # the reference method scales its argument in place
+                y.backward(g)
+                res.append((y.detach(), xr.grad))
+            # torch's CUDA division by a scalar multiplies by the reciprocal: one more ulp than the CPU golden comparison
+            assert float((res[0][0] - res[1][0]).abs().max()) <= 4e-7
+            assert float((res[0][1] - res[1][1]).abs().max()) <= 2e-6 * float(res[0][1].abs().max())
+    finally:
+        cls.apply_articulation_constraints = original
+
+
 def test_bird_chain_no_legs_static_root(ref, cuda):
     """train_magicpony_bird.yaml:29-36 - 8 body bones, no legs, `static_root_bones`: forward_articulation + its constraint masks
     through the drop-in; the posed mesh against the oracle."""
