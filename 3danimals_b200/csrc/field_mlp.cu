@@ -32,7 +32,8 @@ namespace {
 
 constexpr int KC = 32;            // K chunk staged per pipeline step (two stages of 48 KB at N = 256: two CTAs per SM)
 constexpr int TILE_M = 128;       // rows per CTA = MMA M
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 256;                   // staging / epilogue threads (warps 0-7)
+constexpr int GEMM_LAUNCH = GEMM_THREADS + 32;      // + the issuer warp (warp 8): bulk copies, proxy fence, tcgen05.mma, commit
 
 // ---------------------------------------------------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
@@ -63,6 +64,16 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// eight consecutive floats of a 32-byte aligned address in ONE 256-bit load (LDG.E.ENL2.256): a whole sector per lane and instruction.
+// With two 128-bit loads every instruction touched 32 half sectors and the LSU data pipe ran at 90 % of its wavefront rate (ncu,
+// profiles/ncu_r2_mlp_wgrad_detail.txt) - the pipe, not HBM, bounded the staging.
+__device__ __forceinline__ void ldg8(const float* p, float (&v)[8])
+{
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
 
 // bulk async copy global -> shared (TMA engine, no tensor map), completion counted on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
@@ -124,13 +135,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// x = hi + lo with both terms bf16 (round to nearest even); packs two consecutive elements
+// x = hi + lo with both terms bf16 (round to nearest even); packs two consecutive elements.  The PACKED conversion
+// (cvt.rn.bf16x2.f32 -> F2FP.BF16.F32.PACK_AB, ALU pipe) - the scalar __float2bfloat16_rn compiles to F2F.BF16.F32 on the
+// conversion pipe (16 lanes per clock and SM), which at 2 conversions per staged element was ~30 % of a wgrad chunk.
+// The bf16 -> f32 widening is a shift / mask.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem)
+{
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));      // first source -> upper half
+    return r;
+}
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo)
 {
-    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-    const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah)), bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-    hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+    hi = pack_bf16x2(a, b);
+    const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+    lo = pack_bf16x2(a - ah, b - bh);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -195,9 +214,13 @@ __device__ __forceinline__ void a_load(const GemmParams& P, int64_t row0, int c,
         const int64_t row = row0 + r;
         const int k0 = c * KC + kg * 8;
         if (row < P.rows && k0 + 8 <= P.K) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(P.A + row * P.lda + k0));
-            const float4 y = __ldg(reinterpret_cast<const float4*>(P.A + row * P.lda + k0) + 1);
-            v[it][0] = x.x; v[it][1] = x.y; v[it][2] = x.z; v[it][3] = x.w; v[it][4] = y.x; v[it][5] = y.y; v[it][6] = y.z; v[it][7] = y.w;
+            const float* src = P.A + row * P.lda + k0;
+            if ((reinterpret_cast<uintptr_t>(src) & 31) == 0) ldg8(src, v[it]);
+            else {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(src));
+                const float4 y = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                v[it][0] = x.x; v[it][1] = x.y; v[it][2] = x.z; v[it][3] = x.w; v[it][4] = y.x; v[it][5] = y.y; v[it][6] = y.z; v[it][7] = y.w;
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < 8; j++) v[it][j] = (row < P.rows && k0 + j < P.K) ? __ldg(P.A + row * P.lda + k0 + j) : 0.f;
@@ -225,7 +248,7 @@ __device__ __forceinline__ void a_store(const GemmParams& P, uint8_t* st, uint32
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmParams P)
+__global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParams P)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     // stage s: [A_hi 8 KB | A_lo 8 KB | B_hi Npad*64 B | B_lo Npad*64 B]
@@ -238,8 +261,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmPara
     const uint32_t tmem_cols = P.Npad <= 32 ? 32u : (P.Npad <= 64 ? 64u : (P.Npad <= 128 ? 128u : 256u));
     const int nchunks = P.Kpad / KC;
 
-    float va[A_ITEMS][8];
-    a_load(P, row0, 0, tid, va);           // chunk 0 is on its way while the barriers / tensor memory are set up
+    // Warps 0-7 stage the activations; warp 8 is the ISSUER (weights' bulk copies, the generic->async proxy fence, the MMAs).
+    // Why a separate warp: fence.proxy.async is a CTA memory barrier, and a memory barrier waits for the executing thread's outstanding
+    // global loads - with the fence in the staging threads every chunk drained the prefetch and paid a full HBM latency.  The staging
+    // threads order their shared-memory stores with the CTA barrier alone; the issuer executes the proxy fence after that barrier (it has
+    // no loads in flight), then issues.  Two chunks of activations stay in flight per staging thread (register double buffer, buffer =
+    // chunk parity = stage).
+    const bool issuer = warp == GEMM_THREADS / 32;
+    float va[2][A_ITEMS][8];
+    if (!issuer) {
+        a_load(P, row0, 0, tid, va[0]);    // chunks 0 and 1 are on their way while the barriers / tensor memory are set up
+        if (nchunks > 1) a_load(P, row0, 1, tid, va[1]);
+    }
     if (tid == 0) {
         mbar_init(&full_b[0], 1); mbar_init(&full_b[1], 1);
         mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
@@ -253,19 +286,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmPara
     const uint32_t tmem_d = tmem_slot;
     const uint32_t idesc = instr_desc(TILE_M, P.Npad, 0, 0);
 
-    for (int c = 0; c < nchunks; c++) {
+    auto chunk = [&](int c, float (&v)[A_ITEMS][8]) {
         const int s = c & 1;
         uint8_t* st = smem + (size_t)s * stage_bytes;
         if (c >= 2) mbar_wait(&mma_done[s], ((c >> 1) - 1) & 1);        // the MMAs that read this stage (chunk c-2) have completed
-        if (tid == 0) {                                                  // weights of this chunk: one bulk copy (hi | lo are adjacent)
-            mbar_expect_tx(&full_b[s], 2 * b_bytes);
-            bulk_g2s(st + 2 * a_bytes, P.packed + (size_t)c * P.Npad * KC * 2, 2 * b_bytes, &full_b[s]);
+        if (issuer) {
+            if (lane == 0) {                                             // weights of this chunk: one bulk copy (hi | lo are adjacent)
+                mbar_expect_tx(&full_b[s], 2 * b_bytes);
+                bulk_g2s(st + 2 * a_bytes, P.packed + (size_t)c * P.Npad * KC * 2, 2 * b_bytes, &full_b[s]);
+            }
+        } else {
+            a_store(P, st, a_bytes, tid, v);                             // activations of chunk c: registers -> hi / lo images
+            if (c + 2 < nchunks) a_load(P, row0, c + 2, tid, v);         // chunk c+2 into the buffer just drained
         }
-        a_store(P, st, a_bytes, tid, va);                                // activations of chunk c: registers -> hi / lo images
-        if (c + 1 < nchunks) a_load(P, row0, c + 1, tid, va);            // chunk c+1: loads in flight across the sync and the MMA issue
-        fence_proxy_async();            // generic-proxy shared stores -> visible to the tensor core's async proxy
         __syncthreads();
-        if (tid == 0) {
+        if (issuer && lane == 0) {
+            fence_proxy_async();        // the staged images (generic-proxy stores, ordered by the barrier) -> visible to the tensor core
             mbar_wait(&full_b[s], (c >> 1) & 1);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(st), a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
@@ -282,6 +318,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmPara
             }
             umma_commit(&mma_done[s]);      // arrives when every MMA issued so far has completed (implies fence::before_thread_sync)
         }
+    };
+    for (int c = 0; c < nchunks; c += 2) {
+        chunk(c, va[0]);
+        if (c + 1 < nchunks) chunk(c + 1, va[1]);
+    }
+    // the ReLU-derivative words of this thread's row (EPI_MASK): requested before the wait for the tensor core, consumed after it
+    const int quad = warp & 3;
+    const int64_t wrow0 = row0 + quad * 32;
+    const int ngroups = (P.Npad + 31) / 32;
+    uint32_t mw[4] = {0u, 0u, 0u, 0u};
+    if (EPI == EPI_MASK && P.mask_bits && !issuer && wrow0 + lane < P.rows) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int g = (warp >> 2) + 2 * i;
+            if (g < ngroups) mw[i] = __ldg(P.mask_bits + (wrow0 + lane) * ngroups + g);
+        }
     }
     // all MMAs done: the last commit covers every earlier one
     mbar_wait(&mma_done[(nchunks - 1) & 1], ((nchunks - 1) >> 1) & 1);
@@ -289,14 +341,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmPara
     tc_fence_after();
 
     // Epilogue.  Warp w reads the 32 accumulator lanes of its quadrant (w % 4): thread t holds 32 consecutive columns of row
-    // 32*(w%4) + t.  The 32 x 32 block goes through a padded shared-memory tile (the pipeline stages are free now) so that global
-    // memory sees whole 128-byte row segments: lane j handles column c0 + j of one row per instruction (4 fully-written sectors
-    // instead of 32 half-written ones); the ReLU-derivative mask is read the same way.  Warps 0-3 take the even column groups, 4-7 the odd.
-    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * 33);
-    const int quad = warp & 3;
-    const int64_t wrow0 = row0 + quad * 32;
-    const int ngroups = (P.Npad + 31) / 32;
-    for (int g = warp >> 2; g < ngroups; g += 2) {
+    // 32*(w%4) + t.  The 32 x 32 block goes through a shared-memory tile (the pipeline stages are free now; rows 36 words apart:
+    // 16-byte aligned and conflict-free for the quarter-warp phases of 128-bit accesses) so that global memory sees whole 128-byte
+    // row segments: 8 lanes x float4 cover one row segment, a warp instruction writes four rows.  Warps 0-3 take the even column
+    // groups, 4-7 the odd.
+    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * 36);
+    const bool vec_out = (P.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(P.out) & 15) == 0;
+    for (int g = issuer ? ngroups : (warp >> 2), gi = 0; g < ngroups; g += 2, gi++) {
         float v[32];
         __syncwarp();
         tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 32), v);
@@ -321,23 +372,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmPara
             }
         }
         if (EPI == EPI_MASK && P.mask_bits) {
-            const int64_t row = wrow0 + lane;
-            const uint32_t w = row < P.rows ? __ldg(P.mask_bits + row * ngroups + g) : 0u;
+            const uint32_t w = gi == 0 ? mw[0] : (gi == 1 ? mw[1] : (gi == 2 ? mw[2] : mw[3]));
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
         }
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j++) tile[lane * 33 + j] = v[j];
+        for (int q = 0; q < 8; q++)
+            *reinterpret_cast<float4*>(tile + lane * 36 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
-        const int col = c0 + lane;
-#pragma unroll 8
-        for (int r = 0; r < 32; r++) {
+        const int rsub = lane >> 3, col = c0 + 4 * (lane & 7);
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int r = it * 4 + rsub;
             const int64_t row = wrow0 + r;
-            if (row < P.rows && col < P.N) {
-                float x = tile[r * 33 + lane];
-                if (EPI == EPI_MASK && !P.mask_bits && !(__ldg(P.mask_src + row * P.ldm + col) > 0.f)) x = 0.f;
-                P.out[row * P.ldo + col] = x;
+            if (row >= P.rows || col >= P.N) continue;
+            float4 x = *reinterpret_cast<const float4*>(tile + r * 36 + 4 * (lane & 7));
+            if (EPI == EPI_MASK && !P.mask_bits) {
+                const float* ms = P.mask_src + row * P.ldm + col;
+                if (!(__ldg(ms) > 0.f)) x.x = 0.f;
+                if (col + 1 < P.N && !(__ldg(ms + 1) > 0.f)) x.y = 0.f;
+                if (col + 2 < P.N && !(__ldg(ms + 2) > 0.f)) x.z = 0.f;
+                if (col + 3 < P.N && !(__ldg(ms + 3) > 0.f)) x.w = 0.f;
+            }
+            float* o = P.out + row * P.ldo + col;
+            if (vec_out && col + 4 <= P.N) *reinterpret_cast<float4*>(o) = x;
+            else {
+                o[0] = x.x;
+                if (col + 1 < P.N) o[1] = x.y;
+                if (col + 2 < P.N) o[2] = x.z;
+                if (col + 3 < P.N) o[3] = x.w;
             }
         }
     }
@@ -346,7 +410,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) mlp_rows_gemm_kernel(GemmPara
     if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
 }
 
-int gemm_smem_bytes(int Npad) { return 2 * (2 * TILE_M * KC * 2 + 2 * Npad * KC * 2); }
+int gemm_smem_bytes(int Npad)
+{
+    const int stages = 2 * (2 * TILE_M * KC * 2 + 2 * Npad * KC * 2), tiles = (GEMM_THREADS / 32) * 32 * 36 * 4;      // the epilogue reuses the stages
+    return stages > tiles ? stages : tiles;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Weight gradient: C[M, N] += sum over rows r of P[r, m] * Q[r, n]   (dW = dz^T . a)
@@ -379,9 +447,13 @@ __device__ __forceinline__ void mn_load(const float* __restrict__ X, int64_t ldx
         const int64_t row = r0 + kg * 8 + kq;
         const int col = col0 + mq * 32 + mg * 8;
         if (row < rows && col + 8 <= ncols) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(X + row * ldx + col));
-            const float4 y = __ldg(reinterpret_cast<const float4*>(X + row * ldx + col) + 1);
-            v[it][0] = x.x; v[it][1] = x.y; v[it][2] = x.z; v[it][3] = x.w; v[it][4] = y.x; v[it][5] = y.y; v[it][6] = y.z; v[it][7] = y.w;
+            const float* src = X + row * ldx + col;
+            if ((reinterpret_cast<uintptr_t>(src) & 31) == 0) ldg8(src, v[it]);
+            else {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(src));
+                const float4 y = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                v[it][0] = x.x; v[it][1] = x.y; v[it][2] = x.z; v[it][3] = x.w; v[it][4] = y.x; v[it][5] = y.y; v[it][6] = y.z; v[it][7] = y.w;
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < 8; j++) v[it][j] = (row < rows && col + j < ncols) ? __ldg(X + row * ldx + col + j) : 0.f;
@@ -414,7 +486,7 @@ __device__ __forceinline__ void mn_store(uint8_t* hi_img, uint8_t* lo_img, int M
 // One CTA covers every 128-row M tile of the result (P is staged Mpad wide, one tensor-memory accumulator per M tile), so each operand
 // is read from HBM exactly once.
 template <int PI, int QI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) mlp_wgrad_kernel(WgradParams W)
+__global__ void __launch_bounds__(GEMM_LAUNCH, 1) mlp_wgrad_kernel(WgradParams W)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int Mpad = PI * 64;                                              // 128 or 256
@@ -432,9 +504,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) mlp_wgrad_kernel(WgradParams 
     const uint32_t acc_cols = W.Npad < 32 ? 32u : (uint32_t)W.Npad;       // columns of one accumulator (a power of two >= 32)
     const uint32_t tmem_cols = acc_cols * mtiles;
 
-    float vp[PI][8], vq[QI][8];
-    mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r_begin, 0, warp, lane, vp);
-    mn_load<QI>(W.Qm, W.ldq, r_end, W.N, r_begin, 0, warp, lane, vq);
+    // two chunks of both operands in flight per thread (register double buffer, buffer = chunk parity = stage), as in the rows GEMM
+    const bool issuer = warp == GEMM_THREADS / 32;       // warp 8: proxy fence + MMAs (see mlp_rows_gemm_kernel)
+    float vp[2][PI][8], vq[2][QI][8];
+    if (!issuer) {
+        mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r_begin, 0, warp, lane, vp[0]);
+        mn_load<QI>(W.Qm, W.ldq, r_end, W.N, r_begin, 0, warp, lane, vq[0]);
+    }
+    if (!issuer && nchunks > 1) {
+        mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r_begin + KC, 0, warp, lane, vp[1]);
+        mn_load<QI>(W.Qm, W.ldq, r_end, W.N, r_begin + KC, 0, warp, lane, vq[1]);
+    }
     if (tid == 0) {
         mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1);
         fence_barrier_init();
@@ -447,20 +527,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) mlp_wgrad_kernel(WgradParams 
     const uint32_t tmem_d = tmem_slot;
     const uint32_t idesc = instr_desc(TILE_M, W.Npad, 1, 1);
 
-    for (int c = 0; c < nchunks; c++) {
+    auto chunk = [&](int c, float (&p)[PI][8], float (&q)[QI][8]) {
         const int s = c & 1;
         uint8_t* st = smem + (size_t)s * stage_bytes;
         if (c >= 2) mbar_wait(&mma_done[s], ((c >> 1) - 1) & 1);
-        mn_store<PI>(st, st + p_bytes, Mpad, W.relu_p, warp, lane, vp);
-        mn_store<QI>(st + 2 * p_bytes, st + 2 * p_bytes + q_bytes, W.Npad, W.relu_q, warp, lane, vq);
-        if (c + 1 < nchunks) {
-            const int64_t r0 = r_begin + (int64_t)(c + 1) * KC;
-            mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r0, 0, warp, lane, vp);
-            mn_load<QI>(W.Qm, W.ldq, r_end, W.N, r0, 0, warp, lane, vq);
+        if (!issuer) {
+            mn_store<PI>(st, st + p_bytes, Mpad, W.relu_p, warp, lane, p);
+            mn_store<QI>(st + 2 * p_bytes, st + 2 * p_bytes + q_bytes, W.Npad, W.relu_q, warp, lane, q);
+            if (c + 2 < nchunks) {
+                const int64_t r0 = r_begin + (int64_t)(c + 2) * KC;
+                mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r0, 0, warp, lane, p);
+                mn_load<QI>(W.Qm, W.ldq, r_end, W.N, r0, 0, warp, lane, q);
+            }
         }
-        fence_proxy_async();
         __syncthreads();
-        if (tid == 0) {
+        if (issuer && lane == 0) {
+            fence_proxy_async();
             tc_fence_after();
             const uint32_t p_hi = smem_u32(st), p_lo = p_hi + p_bytes, q_hi = p_hi + 2 * p_bytes, q_lo = q_hi + q_bytes;
             const uint32_t p_lbo = (uint32_t)Mpad * 16, q_lbo = (uint32_t)W.Npad * 16;
@@ -480,6 +562,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) mlp_wgrad_kernel(WgradParams 
             }
             umma_commit(&mma_done[s]);
         }
+    };
+    for (int c = 0; c < nchunks; c += 2) {
+        chunk(c, vp[0], vq[0]);
+        if (c + 1 < nchunks) chunk(c + 1, vp[1], vq[1]);
     }
     mbar_wait(&mma_done[(nchunks - 1) & 1], ((nchunks - 1) >> 1) & 1);
     __syncwarp();
@@ -487,7 +573,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) mlp_wgrad_kernel(WgradParams 
     // epilogue: thread t of quadrant q holds row m0 + 32q + t, 32 consecutive n: one reduction per element into the shared result
     const int quad = warp & 3;
     const int ngroups = (W.Npad + 31) / 32;
-    for (int gi = warp >> 2; gi < ngroups * mtiles; gi += 2) {
+    for (int gi = issuer ? ngroups * mtiles : (warp >> 2); gi < ngroups * mtiles; gi += 2) {
         const int mt = gi / ngroups, g = gi - mt * ngroups;
         const int m = mt * TILE_M + quad * 32 + lane;
         float v[32];
@@ -632,7 +718,7 @@ B2A_API int b2a_mlp_rows_gemm(const float* A, int64_t lda, int64_t rows, int K, 
 #define MLP_LAUNCH(E)                                                                                                     \
     do {                                                                                                                  \
         B2A_CUDA_OK(cudaFuncSetAttribute(mlp_rows_gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));    \
-        mlp_rows_gemm_kernel<E><<<grid, GEMM_THREADS, smem, stream>>>(P);                                                 \
+        mlp_rows_gemm_kernel<E><<<grid, GEMM_LAUNCH, smem, stream>>>(P);                                                   \
     } while (0)
     if (epilogue == EPI_BIAS) MLP_LAUNCH(EPI_BIAS);
     else if (epilogue == EPI_MASK) MLP_LAUNCH(EPI_MASK);
@@ -668,7 +754,7 @@ B2A_API int b2a_mlp_wgrad(const float* P, int64_t ldp, int relu_p, const float* 
 #define WG_LAUNCH(PI, QI)                                                                                                \
     do {                                                                                                                 \
         B2A_CUDA_OK(cudaFuncSetAttribute(mlp_wgrad_kernel<PI, QI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        mlp_wgrad_kernel<PI, QI><<<grid, GEMM_THREADS, smem, stream>>>(W);                                               \
+        mlp_wgrad_kernel<PI, QI><<<grid, GEMM_LAUNCH, smem, stream>>>(W);                                                 \
     } while (0)
     if (mtiles == 2) {
         if (W.Npad == 256) WG_LAUNCH(4, 4);
