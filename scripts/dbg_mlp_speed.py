@@ -33,6 +33,12 @@ for passes in (3, 1):
     rep("gemm fwd + sign bits out passes=%d" % passes, timed(lambda: lib.b2a_mlp_rows_gemm(A.data_ptr(), 256, rows, 256, Wp.data_ptr(), 256, 1, passes, 0, None, None, None, 0, None, bits.data_ptr(), out.data_ptr(), 256, st)), 2 * mb * 1e6)
     rep("gemm dgrad mask_bits passes=%d" % passes, timed(lambda: lib.b2a_mlp_rows_gemm(A.data_ptr(), 256, rows, 256, Wp.data_ptr(), 256, 0, passes, 1, None, None, None, 0, bits.data_ptr(), None, out.data_ptr(), 256, st)), 2 * mb * 1e6)
     rep("wgrad passes=%d (2 reads)" % passes, timed(lambda: lib.b2a_mlp_wgrad(P2.data_ptr(), 256, 0, A.data_ptr(), 256, 1, rows, 256, 256, passes, o2.data_ptr(), 256, 0, st)), 2 * mb * 1e6)
+seg16 = torch.linspace(0, rows, 17, device=dev).long(); o16 = torch.empty(16, 256, device=dev)
+rep("colsum_segments 16 segments (read)", timed(lambda: lib.b2a_mlp_colsum_segments(A.data_ptr(), 256, seg16.data_ptr(), 16, 256, o16.data_ptr(), st)), mb * 1e6)
+seg1 = torch.tensor([0, rows], device=dev); o1 = torch.empty(1, 256, device=dev)
+rep("colsum_segments 1 segment (read)", timed(lambda: lib.b2a_mlp_colsum_segments(A.data_ptr(), 256, seg1.data_ptr(), 1, 256, o1.data_ptr(), st)), mb * 1e6)
+want = A.double().sum(0)
+print("colsum check: max rel err %.2e / %.2e" % (float((o1[0].double() - want).abs().max() / want.abs().max()), float((o16.double().sum(0) - want).abs().max() / want.abs().max())))
 torch.backends.cuda.matmul.allow_tf32 = True
 rep("cuBLAS tf32 A @ W (read + write)", timed(lambda: torch.mm(A, W, out=out)), 2 * mb * 1e6)
 Ah, Wh = A.bfloat16(), W.bfloat16(); oh = torch.empty(rows, 256, device=dev, dtype=torch.bfloat16)
