@@ -286,16 +286,20 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
     const uint32_t tmem_d = tmem_slot;
     const uint32_t idesc = instr_desc(TILE_M, P.Npad, 0, 0);
 
+    // weights of chunk c: one bulk copy (hi | lo are adjacent) into stage c & 1, issued ONE CHUNK AHEAD of its use (chunk 0 here,
+    // chunk c+1 right after the MMAs of chunk c are issued) - issued in the iteration that consumes it, the issuer sat out the
+    // L2 -> shared latency of 32 KB in front of every chunk's MMAs
+    auto weights = [&](int c) {
+        const int s = c & 1;
+        mbar_expect_tx(&full_b[s], 2 * b_bytes);
+        bulk_g2s(smem + (size_t)s * stage_bytes + 2 * a_bytes, P.packed + (size_t)c * P.Npad * KC * 2, 2 * b_bytes, &full_b[s]);
+    };
+    if (issuer && lane == 0) weights(0);
     auto chunk = [&](int c, float (&v)[A_ITEMS][8]) {
         const int s = c & 1;
         uint8_t* st = smem + (size_t)s * stage_bytes;
         if (c >= 2) mbar_wait(&mma_done[s], ((c >> 1) - 1) & 1);        // the MMAs that read this stage (chunk c-2) have completed
-        if (issuer) {
-            if (lane == 0) {                                             // weights of this chunk: one bulk copy (hi | lo are adjacent)
-                mbar_expect_tx(&full_b[s], 2 * b_bytes);
-                bulk_g2s(st + 2 * a_bytes, P.packed + (size_t)c * P.Npad * KC * 2, 2 * b_bytes, &full_b[s]);
-            }
-        } else {
+        if (!issuer) {
             a_store(P, st, a_bytes, tid, v);                             // activations of chunk c: registers -> hi / lo images
             if (c + 2 < nchunks) a_load(P, row0, c + 2, tid, v);         // chunk c+2 into the buffer just drained
         }
@@ -317,6 +321,10 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
                 }
             }
             umma_commit(&mma_done[s]);      // arrives when every MMA issued so far has completed (implies fence::before_thread_sync)
+            if (c + 1 < nchunks) {          // next chunk's weights go into the other stage: its last readers were the MMAs of chunk c-1
+                if (c >= 1) mbar_wait(&mma_done[s ^ 1], ((c - 1) >> 1) & 1);
+                weights(c + 1);
+            }
         }
     };
     for (int c = 0; c < nchunks; c += 2) {
