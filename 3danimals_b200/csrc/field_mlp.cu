@@ -34,6 +34,8 @@ constexpr int KC = 32;            // K chunk staged per pipeline step (two stage
 constexpr int TILE_M = 128;       // rows per CTA = MMA M
 constexpr int GEMM_THREADS = 256;                   // staging / epilogue threads (warps 0-7)
 constexpr int GEMM_LAUNCH = GEMM_THREADS + 32;      // + the issuer warp (warp 8): bulk copies, proxy fence, tcgen05.mma, commit
+constexpr int WG_WARPS = 16;                        // staging warps of the weight-gradient kernel (one CTA per SM); warp 16 issues
+constexpr int WG_LAUNCH_THREADS = WG_WARPS * 32 + 32;
 
 // ---------------------------------------------------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
@@ -70,7 +72,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // profiles/ncu_r2_mlp_wgrad_detail.txt) - the pipe, not HBM, bounded the staging.
 __device__ __forceinline__ void ldg8(const float* p, float (&v)[8])
 {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(p));
 }
@@ -450,7 +452,7 @@ __device__ __forceinline__ void mn_load(const float* __restrict__ X, int64_t ldx
     const int kq = lane & 7, mg = lane >> 3;
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
-        const int witem = it * (GEMM_THREADS / 32) + warp;        // (k group, quad of mn groups)
+        const int witem = it * WG_WARPS + warp;                   // (k group, quad of mn groups)
         const int kg = witem & (KC / 8 - 1), mq = witem / (KC / 8);
         const int64_t row = r0 + kg * 8 + kq;
         const int col = col0 + mq * 32 + mg * 8;
@@ -474,7 +476,7 @@ __device__ __forceinline__ void mn_store(uint8_t* hi_img, uint8_t* lo_img, int M
     const int kq = lane & 7, mg = lane >> 3;
 #pragma unroll
     for (int it = 0; it < ITEMS; it++) {
-        const int witem = it * (GEMM_THREADS / 32) + warp;
+        const int witem = it * WG_WARPS + warp;
         const int kg = witem & (KC / 8 - 1), mq = witem / (KC / 8);
         if (mq * 32 >= MN) continue;                               // narrow operands: fewer warp items than warps
         if (relu) {
@@ -490,14 +492,16 @@ __device__ __forceinline__ void mn_store(uint8_t* hi_img, uint8_t* lo_img, int M
     }
 }
 
-// PI / QI = P / Q items per thread = (KC/8) * (width/32) / 8 warps: 4 for width 256, 2 for 128, 1 for 64; <= 32 -> 1 (half the warps idle).
+// PI / QI = P / Q items per thread = (KC/8) * (width/32) / 16 warps: 2 for width 256, 1 for 128 and below (then some warps idle).
+// Sixteen staging warps: with eight, a chunk's conversion took 1.8 us of a 2.0 us chunk period on two warps per scheduler (clock64 trace) -
+// the kernel was bound by the issue rate of its own staging code, at 41 % of the HBM rate.
 // One CTA covers every 128-row M tile of the result (P is staged Mpad wide, one tensor-memory accumulator per M tile), so each operand
 // is read from HBM exactly once.
 template <int PI, int QI>
-__global__ void __launch_bounds__(GEMM_LAUNCH, 1) mlp_wgrad_kernel(WgradParams W)
+__global__ void __launch_bounds__(WG_LAUNCH_THREADS, 1) mlp_wgrad_kernel(WgradParams W)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int Mpad = PI * 64;                                              // 128 or 256
+    const int Mpad = PI * 128;                                             // 128 or 256
     const int mtiles = Mpad / TILE_M;
     const uint32_t p_bytes = (uint32_t)KC * Mpad * 2, q_bytes = (uint32_t)KC * W.Npad * 2;
     const uint32_t stage_bytes = 2 * p_bytes + 2 * q_bytes;
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 1) mlp_wgrad_kernel(WgradParams W
     const uint32_t tmem_cols = acc_cols * mtiles;
 
     // two chunks of both operands in flight per thread (register double buffer, buffer = chunk parity = stage), as in the rows GEMM
-    const bool issuer = warp == GEMM_THREADS / 32;       // warp 8: proxy fence + MMAs (see mlp_rows_gemm_kernel)
+    const bool issuer = warp == WG_WARPS;                // the last warp: proxy fence + MMAs (see mlp_rows_gemm_kernel)
     float vp[2][PI][8], vq[2][QI][8];
     if (!issuer) {
         mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r_begin, 0, warp, lane, vp[0]);
@@ -581,7 +585,7 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 1) mlp_wgrad_kernel(WgradParams W
     // epilogue: thread t of quadrant q holds row m0 + 32q + t, 32 consecutive n: one reduction per element into the shared result
     const int quad = warp & 3;
     const int ngroups = (W.Npad + 31) / 32;
-    for (int gi = issuer ? ngroups * mtiles : (warp >> 2); gi < ngroups * mtiles; gi += 2) {
+    for (int gi = issuer ? ngroups * mtiles : (warp >> 2); gi < ngroups * mtiles; gi += WG_WARPS / 4) {
         const int mt = gi / ngroups, g = gi - mt * ngroups;
         const int m = mt * TILE_M + quad * 32 + lane;
         float v[32];
@@ -799,16 +803,14 @@ B2A_API int b2a_mlp_wgrad(const float* P, int64_t ldp, int relu_p, const float* 
 #define WG_LAUNCH(PI, QI)                                                                                                \
     do {                                                                                                                 \
         B2A_CUDA_OK(cudaFuncSetAttribute(mlp_wgrad_kernel<PI, QI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        mlp_wgrad_kernel<PI, QI><<<grid, GEMM_LAUNCH, smem, stream>>>(W);                                                 \
+        mlp_wgrad_kernel<PI, QI><<<grid, WG_LAUNCH_THREADS, smem, stream>>>(W);                                               \
     } while (0)
     if (mtiles == 2) {
-        if (W.Npad == 256) WG_LAUNCH(4, 4);
-        else if (W.Npad == 128) WG_LAUNCH(4, 2);
-        else WG_LAUNCH(4, 1);
-    } else {
-        if (W.Npad == 256) WG_LAUNCH(2, 4);
-        else if (W.Npad == 128) WG_LAUNCH(2, 2);
+        if (W.Npad == 256) WG_LAUNCH(2, 2);
         else WG_LAUNCH(2, 1);
+    } else {
+        if (W.Npad == 256) WG_LAUNCH(1, 2);
+        else WG_LAUNCH(1, 1);
     }
 #undef WG_LAUNCH
     B2A_LAUNCH_OK();
