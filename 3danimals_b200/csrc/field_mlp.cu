@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
     // stage s: [A_hi 8 KB | A_lo 8 KB | B_hi Npad*64 B | B_lo Npad*64 B]
     const uint32_t a_bytes = TILE_M * KC * 2, b_bytes = (uint32_t)P.Npad * KC * 2;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    const uint32_t w_bytes = P.passes == 3 ? 2 * b_bytes : b_bytes;          // one product per element: the hi image only
     __shared__ __align__(8) uint64_t full_b[2], mma_done[2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -293,8 +294,8 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
     // L2 -> shared latency of 32 KB in front of every chunk's MMAs
     auto weights = [&](int c) {
         const int s = c & 1;
-        mbar_expect_tx(&full_b[s], 2 * b_bytes);
-        bulk_g2s(smem + (size_t)s * stage_bytes + 2 * a_bytes, P.packed + (size_t)c * P.Npad * KC * 2, 2 * b_bytes, &full_b[s]);
+        mbar_expect_tx(&full_b[s], w_bytes);
+        bulk_g2s(smem + (size_t)s * stage_bytes + 2 * a_bytes, P.packed + (size_t)c * P.Npad * KC * 2, w_bytes, &full_b[s]);
     };
     if (issuer && lane == 0) weights(0);
     auto chunk = [&](int c, float (&v)[A_ITEMS][8]) {
