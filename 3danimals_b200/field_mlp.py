@@ -124,23 +124,30 @@ class _FieldMLP(torch.autograd.Function):
         dz = torch.zeros(N, cpad, device=dev)
         gz = g.float()
         dz[:, :cout] = gz * out * (1.0 - out) if sigmoid else gz
+        # every weight gradient is accumulated with reductions: ONE zero fill for all of them (16-byte aligned slices of one buffer)
+        sizes = [(w.numel() + 3) // 4 * 4 for w in ws] + [(w_in.numel() + 3) // 4 * 4]
+        pool = torch.zeros(sum(sizes), device=dev)
+        offs = [0]
+        for n_ in sizes:
+            offs.append(offs[-1] + n_)
+        zeros_like = lambda i, w: pool[offs[i]:offs[i] + w.numel()].view(w.shape)
         d_ws = [None] * ctx.n_w
-        d_ws[-1] = torch.zeros_like(ws[-1])
+        d_ws[-1] = zeros_like(ctx.n_w - 1, ws[-1])
         _wgrad(zs[-1], True, dz, False, nf, cout, passes, d_ws[-1], transpose_out=True)          # d_W_out[c, j] = sum_r dz[r, c] relu(z)[r, j]
         dzl = _gemm(dz, cout, _pack(ws[-1], nf, cout, True), nf, False, passes, 1, mask_bits=bits[-1])   # (dz . W_out) * [z_last > 0]
         for i in range(ctx.n_w - 2, 0, -1):                                                    # hidden layers W_i: z_{i+1} = W_i relu(z_i)
-            d_ws[i] = torch.zeros_like(ws[i])
+            d_ws[i] = zeros_like(i, ws[i])
             _wgrad(dzl, False, zs[i], True, nf, nf, passes, d_ws[i])
             dzl = _gemm(dzl, nf, _pack(ws[i], nf, nf, True), nf, False, passes, 1, mask_bits=bits[i])
         # first hidden layer: only its h half [nf, :nf] is a GEMM here; the feature half is the per-image bias (PyTorch side)
-        d_ws[0] = torch.zeros_like(ws[0])
+        d_ws[0] = zeros_like(0, ws[0])
         _wgrad(dzl, False, zs[0], True, nf, nf, passes, d_ws[0])
         d_bias = None
         if ctx.has_bias and need[4]:
             d_bias = torch.empty(ctx.n_img, nf, device=dev)
             _call("b2a_mlp_colsum_segments", (_p(dzl), dzl.stride(0), _p(seg_start), ctx.n_img, nf, _p(d_bias), st))
         dz0 = _gemm(dzl, nf, _pack(ws[0], nf, nf, True), nf, False, passes, 1, mask_bits=bits[0])
-        d_w_in = torch.zeros_like(w_in)
+        d_w_in = zeros_like(ctx.n_w, w_in)
         _wgrad(dz0, False, E, False, nf, kin, passes, d_w_in)
         d_b_in = torch.empty(1, nf, device=dev)                  # column sums of dz0 = one segment [0, N)
         whole = torch.tensor([0, N], dtype=torch.int64, device=dev) if seg_start is None else torch.stack([seg_start[0], seg_start[-1]])
