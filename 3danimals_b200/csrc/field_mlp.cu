@@ -204,6 +204,11 @@ struct GemmParams {
     uint32_t* bits_out;        // EPI_BIAS: (nullable) writes those sign bits of the OUTPUT for the backward pass
 };
 
+// The K-major A image: k group kg (8 k values = 16 bytes per row) starts at kg * A_LBO.  A_LBO = 128 rows * 16 B + 32: with the dense
+// 2048 the four k groups a warp writes in one 128-bit store instruction (lane = (row, kg)) fall on the same banks - a 4-way conflict on
+// every staging store; 32 bytes of padding per group spread them (the descriptor's leading-dimension byte offset is free to choose).
+constexpr uint32_t A_LBO = TILE_M * 16 + 32;
+constexpr uint32_t A_IMG = (KC / 8) * A_LBO;
 constexpr int A_ITEMS = TILE_M * (KC / 8) / GEMM_THREADS;   // (row, 8-wide k group) items per thread and chunk
 
 // global -> registers: the fp32 values of this thread's items of chunk c (issued one chunk ahead of their use)
@@ -229,7 +234,7 @@ __device__ __forceinline__ void a_load(const GemmParams& P, int64_t row0, int c,
         }
     }
 }
-// registers -> hi / lo images of the stage (canonical K-major layout: byte(r, k) = (k/8) * TILE_M*16 + r*16 + (k%8)*2)
+// registers -> hi / lo images of the stage (canonical K-major layout: byte(r, k) = (k/8) * A_LBO + r*16 + (k%8)*2)
 __device__ __forceinline__ void a_store(const GemmParams& P, uint8_t* st, uint32_t a_bytes, int tid, float (&v)[A_ITEMS][8])
 {
 #pragma unroll
@@ -243,7 +248,7 @@ __device__ __forceinline__ void a_store(const GemmParams& P, uint8_t* st, uint32
         uint4 hi, lo;
         split2(v[it][0], v[it][1], hi.x, lo.x); split2(v[it][2], v[it][3], hi.y, lo.y);
         split2(v[it][4], v[it][5], hi.z, lo.z); split2(v[it][6], v[it][7], hi.w, lo.w);
-        const uint32_t off = (uint32_t)kg * (TILE_M * 16) + (uint32_t)r * 16;
+        const uint32_t off = (uint32_t)kg * A_LBO + (uint32_t)r * 16;
         *reinterpret_cast<uint4*>(st + off) = hi;
         *reinterpret_cast<uint4*>(st + a_bytes + off) = lo;
     }
@@ -253,8 +258,8 @@ template <int EPI>
 __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParams P)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // stage s: [A_hi 8 KB | A_lo 8 KB | B_hi Npad*64 B | B_lo Npad*64 B]
-    const uint32_t a_bytes = TILE_M * KC * 2, b_bytes = (uint32_t)P.Npad * KC * 2;
+    // stage s: [A_hi A_IMG | A_lo A_IMG | B_hi Npad*64 B | B_lo Npad*64 B]
+    const uint32_t a_bytes = A_IMG, b_bytes = (uint32_t)P.Npad * KC * 2;
     const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
     const uint32_t w_bytes = P.passes == 3 ? 2 * b_bytes : b_bytes;          // one product per element: the hi image only
     __shared__ __align__(8) uint64_t full_b[2], mma_done[2];
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
             mbar_wait(&full_b[s], (c >> 1) & 1);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(st), a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
-            const uint32_t a_lbo = TILE_M * 16, b_lbo = (uint32_t)P.Npad * 16;
+            const uint32_t a_lbo = A_LBO, b_lbo = (uint32_t)P.Npad * 16;
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ks++) {
                 const uint64_t dah = smem_desc(a_hi + ks * 2 * a_lbo, a_lbo, 128), dal = smem_desc(a_lo + ks * 2 * a_lbo, a_lbo, 128);
@@ -423,7 +428,7 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
 
 int gemm_smem_bytes(int Npad)
 {
-    const int stages = 2 * (2 * TILE_M * KC * 2 + 2 * Npad * KC * 2), tiles = (GEMM_THREADS / 32) * 32 * 36 * 4;      // the epilogue reuses the stages
+    const int stages = 2 * (2 * (int)A_IMG + 2 * Npad * KC * 2), tiles = (GEMM_THREADS / 32) * 32 * 36 * 4;      // the epilogue reuses the stages
     return stages > tiles ? stages : tiles;
 }
 
