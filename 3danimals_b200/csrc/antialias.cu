@@ -1045,8 +1045,83 @@ __global__ void __launch_bounds__(256) aa_up_fwd_kernel(const float* __restrict_
     }
 }
 
-// position-gradient role with up-sampled colour (see aa_bwd_pos_role)
+// Upstream gradient of hi-res pixel `pix`.  POOL: the caller's gradient is that of the spp x spp AVERAGE of the antialiased image
+// (render.py:322-323 util.avg_pool_nhwc) at [H/up, W/up]: every hi-res pixel of a block receives g / (up*up) - avg_pool2d's backward,
+// never materialised at the raster resolution.
+template <bool POOL>
+__device__ __forceinline__ float grad_up(const AAGrad& G, const AAUp& U, int b, int pix, int c)
+{
+    if (c >= G.Cg) return 0.f;
+    int y = pix / U.W, x = pix - y * U.W;
+    if (POOL) { y /= U.up; x /= U.up; }
+    const float g = __ldg(G.d_out + (int64_t)b * G.sb + (int64_t)y * G.sy + (int64_t)x * G.sx + (int64_t)c * G.sc);
+    return POOL ? g / (float)(U.up * U.up) : g;
+}
+
+// Composite (+ antialias) at the raster resolution and AVERAGE over the up x up block in one pass: one thread per low-resolution
+// output pixel.  The hi-res image (64 MB per 4-channel key at 2048^2) is never written or re-read; the per-pixel arithmetic and the
+// row-major summation order are those of aa_up_fwd_kernel followed by avg_pool2d, so the result is bit-identical to that pair.
 template <int C>
+__global__ void __launch_bounds__(256) aa_up_pool_fwd_kernel(const float* __restrict__ color, AAUp U, const float* __restrict__ bg, int Bg, AAContext ctx,
+                                                             int B, int aa, int keep, float* __restrict__ out)
+{
+    constexpr int CI = C - 1;
+    const int64_t n = (int64_t)B * U.lhw;
+    const int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const int b = (int)(li / U.lhw);
+    const int lp = (int)(li - (int64_t)b * U.lhw);
+    const int yl = lp / U.lw, xl = lp - yl * U.lw;
+    float col[CI], acc[C];
+#pragma unroll
+    for (int c = 0; c < CI; c++) col[c] = __ldg(color + li * CI + c);
+#pragma unroll
+    for (int c = 0; c < C; c++) acc[c] = 0.f;
+    for (int dy = 0; dy < U.up; dy++) {
+        for (int dx = 0; dx < U.up; dx++) {
+            const int p = (yl * U.up + dy) * U.W + xl * U.up + dx;
+            const size_t flat = (size_t)b * U.HW + p;
+            float v[C];
+            if (aa_bit(ctx.cover, flat)) {
+#pragma unroll
+                for (int c = 0; c < CI; c++) v[c] = col[c];
+                v[CI] = 1.f;
+            } else {
+                const float* bp = bg ? bg + (Bg == 1 ? (size_t)p : flat) * C : nullptr;
+#pragma unroll
+                for (int c = 0; c < C; c++) v[c] = bp ? __ldg(bp + c) : 0.f;
+            }
+            if (aa && aa_bit(ctx.act, flat)) {
+                const float4 a = __ldg(ctx.rec + flat);
+                const bool k0 = a.x < 0.f, k1 = a.y < 0.f, k2 = a.z > 0.f, k3 = a.w > 0.f;
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    const float own = v[c];
+                    const float cu = k0 ? aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, flat - U.W, c) : own;
+                    const float cl = k1 ? aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, flat - 1, c) : own;
+                    const float cr = k2 ? aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, flat + 1, c) : own;
+                    const float cd = k3 ? aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, flat + U.W, c) : own;
+                    float t = own;
+                    if (k0) t += a.x * (own - cu);
+                    if (k1) t += a.y * (own - cl);
+                    if (k2) t += a.z * (cr - own);
+                    if (k3) t += a.w * (cd - own);
+                    v[c] = t;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; c++) acc[c] += v[c];
+        }
+    }
+    const float area = (float)(U.up * U.up);
+    float* o = out + li * keep;
+#pragma unroll
+    for (int c = 0; c < C; c++)
+        if (c < keep) o[c] = acc[c] / area;
+}
+
+// position-gradient role with up-sampled colour (see aa_bwd_pos_role)
+template <int C, bool POOL>
 __device__ __forceinline__ void aa_up_pos_role(const float* __restrict__ color, const AAUp& U, const float* __restrict__ bg, int Bg, int64_t V,
                                                const AAGrad& G, const AAContext& ctx, float* __restrict__ d_pos, int role_block)
 {
@@ -1064,8 +1139,8 @@ __device__ __forceinline__ void aa_up_pos_role(const float* __restrict__ color, 
         if (on) {
             const int target = a > 0.f ? p : p + (d ? U.W : 1);
             for (int c = sub; c < G.Cg; c += 16)
-                dd += grad_at(G, U.W, b, target, c) * (aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, q1, c) -
-                                                       aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, q0, c));
+                dd += grad_up<POOL>(G, U, b, target, c) * (aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, q1, c) -
+                                                           aa_comp_up<C>(color, U, bg, Bg, ctx.cover, b, q0, c));
         }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) dd += __shfl_xor_sync(0xffffffffu, dd, o);
@@ -1082,13 +1157,13 @@ __device__ __forceinline__ void aa_up_pos_role(const float* __restrict__ color, 
 }
 
 // one thread per LOW-resolution pixel: sums the colour gradient of its up*up hi-res pixels
-template <int C, int CC>
+template <int C, int CC, bool POOL>
 __global__ void __launch_bounds__(256) aa_up_bwd_kernel(const float* __restrict__ color, AAUp U, const float* __restrict__ bg, int Bg, int64_t V,
                                                         AAGrad G, AAContext ctx, int B, int aa, float* __restrict__ d_color,
                                                         float* __restrict__ d_pos, int pos_blocks)
 {
     if ((int)blockIdx.x < pos_blocks) {
-        aa_up_pos_role<C>(color, U, bg, Bg, V, G, ctx, d_pos, (int)blockIdx.x);
+        aa_up_pos_role<C, POOL>(color, U, bg, Bg, V, G, ctx, d_pos, (int)blockIdx.x);
         return;
     }
     const int64_t n = (int64_t)B * U.lhw;
@@ -1107,16 +1182,16 @@ __global__ void __launch_bounds__(256) aa_up_bwd_kernel(const float* __restrict_
             if (!aa_bit(ctx.cover, flat)) continue;
             float v[CC];
 #pragma unroll
-            for (int c = 0; c < CC; c++) v[c] = grad_at(G, U.W, b, p, c);
+            for (int c = 0; c < CC; c++) v[c] = grad_up<POOL>(G, U, b, p, c);
             if (aa && aa_bit(ctx.act, flat)) {
                 const float4 a = __ldg(ctx.rec + flat);
 #pragma unroll
                 for (int c = 0; c < CC; c++) {
                     const float own = v[c];
-                    const float gu = a.x != 0.f ? (a.x > 0.f ? grad_at(G, U.W, b, p - U.W, c) : own) : 0.f;
-                    const float gl = a.y != 0.f ? (a.y > 0.f ? grad_at(G, U.W, b, p - 1, c) : own) : 0.f;
-                    const float gr = a.z != 0.f ? (a.z > 0.f ? own : grad_at(G, U.W, b, p + 1, c)) : 0.f;
-                    const float gd = a.w != 0.f ? (a.w > 0.f ? own : grad_at(G, U.W, b, p + U.W, c)) : 0.f;
+                    const float gu = a.x != 0.f ? (a.x > 0.f ? grad_up<POOL>(G, U, b, p - U.W, c) : own) : 0.f;
+                    const float gl = a.y != 0.f ? (a.y > 0.f ? grad_up<POOL>(G, U, b, p - 1, c) : own) : 0.f;
+                    const float gr = a.z != 0.f ? (a.z > 0.f ? own : grad_up<POOL>(G, U, b, p + 1, c)) : 0.f;
+                    const float gd = a.w != 0.f ? (a.w > 0.f ? own : grad_up<POOL>(G, U, b, p + U.W, c)) : 0.f;
                     float t = own;
                     if (a.x != 0.f) t += a.x * gu;
                     if (a.y != 0.f) t += a.y * gl;
@@ -1423,9 +1498,54 @@ B2A_API int b2a_composite_up_bwd(const float* color, int up, const float* bg, in
     const int pos_blocks = (d_pos && antialias) ? AA_POS_BLOCKS : 0;
     const unsigned grid = b2a_blocks((int64_t)B * U.lhw, 256) + pos_blocks;
     switch (C) {
-        case 2: aa_up_bwd_kernel<2, 1><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
-        case 3: aa_up_bwd_kernel<3, 2><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
-        default: aa_up_bwd_kernel<4, 3><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
+        case 2: aa_up_bwd_kernel<2, 1, false><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
+        case 3: aa_up_bwd_kernel<3, 2, false><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
+        default: aa_up_bwd_kernel<4, 3, false><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
+    }
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+// msaa renders (reference render.py:217-219 nearest up-sampling, :258-268 composite + antialias at [H,W] = the raster resolution,
+// :322-323 util.avg_pool_nhwc(., spp)) in ONE kernel per direction: out [B, H/up, W/up, keep] is the up x up average of the composited
+// (+ antialiased) image, which is never materialised.  d_out: the gradient of that average, any strides (sb, sy, sx, sc over
+// [B, H/up, W/up, Cg]).  Bit-identical to b2a_composite_up_fwd followed by avg_pool2d.
+B2A_API int b2a_composite_up_pool_fwd(const float* color, int up, const float* bg, int Bg, int antialias, int B, int H, int W, int C, int keep,
+                                      float* out, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(color && out && aa_ctx, "null pointer");
+    B2A_CHECK_ARG(B > 0 && H > 0 && W > 0 && (Bg == 1 || Bg == B) && keep >= 1 && keep <= C && up >= 1, "shape");
+    AAContext ctx;
+    AAUp U;
+    B2A_CHECK_ARG(up_args_ok(up, B, H, W, C, aa_ctx, aa_ctx_bytes, &ctx, &U), "needs C in 2..4, H and W multiples of `up`, and a prepared context");
+    const unsigned blocks = b2a_blocks((int64_t)B * U.lhw, 256);
+    switch (C) {
+        case 2: aa_up_pool_fwd_kernel<2><<<blocks, 256, 0, stream>>>(color, U, bg, Bg, ctx, B, antialias, keep, out); break;
+        case 3: aa_up_pool_fwd_kernel<3><<<blocks, 256, 0, stream>>>(color, U, bg, Bg, ctx, B, antialias, keep, out); break;
+        default: aa_up_pool_fwd_kernel<4><<<blocks, 256, 0, stream>>>(color, U, bg, Bg, ctx, B, antialias, keep, out); break;
+    }
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+B2A_API int b2a_composite_up_pool_bwd(const float* color, int up, const float* bg, int Bg, int antialias, const float* d_out, int64_t d_sb,
+                                      int64_t d_sy, int64_t d_sx, int64_t d_sc, int Cg, int B, int64_t V, int H, int W, int C, float* d_color,
+                                      float* d_pos, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(color && d_out && d_color && aa_ctx, "null pointer");
+    B2A_CHECK_ARG(B > 0 && V > 0 && H > 0 && W > 0 && (Bg == 1 || Bg == B) && Cg >= 0 && Cg <= C, "shape");
+    AAContext ctx;
+    AAUp U;
+    B2A_CHECK_ARG(up_args_ok(up, B, H, W, C, aa_ctx, aa_ctx_bytes, &ctx, &U), "needs C in 2..4, H and W multiples of `up`, and a prepared context");
+    AAGrad G{d_out, d_sb, d_sy, d_sx, d_sc, Cg};
+    const int pos_blocks = (d_pos && antialias) ? AA_POS_BLOCKS : 0;
+    const unsigned grid = b2a_blocks((int64_t)B * U.lhw, 256) + pos_blocks;
+    switch (C) {
+        case 2: aa_up_bwd_kernel<2, 1, true><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
+        case 3: aa_up_bwd_kernel<3, 2, true><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
+        default: aa_up_bwd_kernel<4, 3, true><<<grid, 256, 0, stream>>>(color, U, bg, Bg, V, G, ctx, B, antialias, d_color, d_pos, pos_blocks); break;
     }
     B2A_LAUNCH_OK();
     return 0;

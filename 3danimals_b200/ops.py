@@ -66,7 +66,7 @@ def _workspace(nbytes, device):
 # kernels launched by each C-ABI entry point (memsets / memcpys are not kernels) - the source of bench.py's gpu_launches
 KERNELS_PER_CALL = {
     "b2a_mt_count": 4, "b2a_mt_emit": 2, "b2a_mt_bwd": 1, "b2a_estimate_bones": 4, "b2a_lbs_bone_transforms": 2, "b2a_lbs_fwd": 1, "b2a_lbs_bwd": 1,
-    "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1, "b2a_articulation_constraints_fwd": 1, "b2a_articulation_constraints_bwd": 1,
+    "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1, "b2a_composite_up_pool_fwd": 1, "b2a_composite_up_pool_bwd": 1, "b2a_articulation_constraints_fwd": 1, "b2a_articulation_constraints_bwd": 1,
     "b2a_xfm_points_bwd": 1, "b2a_rasterize_fwd": 3, "b2a_rasterize_bwd": 1, "b2a_interpolate_fwd": 1, "b2a_interpolate_bwd": 1,
     "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 2,
     "b2a_antialias_pair_fwd": 1, "b2a_antialias_pair_bwd": 1, "b2a_shade_directional_fwd": 1, "b2a_shade_directional_bwd": 1,
@@ -736,7 +736,7 @@ class _CompositeUp(torch.autograd.Function):
     (b2a_composite_up_fwd/bwd).  antialias=False: composite only (kd / normal / geo_normal)."""
 
     @staticmethod
-    def forward(ctx, color, bg, pos, up, antialias, keep, aa_ctx, H, W):
+    def forward(ctx, color, bg, pos, up, antialias, keep, aa_ctx, H, W, pool):
         color = _f32(color, "color"); pos = _f32(pos, "pos")
         bg = _f32(bg, "background") if bg is not None else None
         B = color.shape[0]
@@ -748,38 +748,45 @@ class _CompositeUp(torch.autograd.Function):
             if bg.shape[1:] != (H, W, Cc) or bg.shape[0] not in (1, B):
                 raise _lib.B2AError("antialias: background shape %s, expected [1|B,%d,%d,%d]" % (tuple(bg.shape), H, W, Cc))
             Bg = bg.shape[0]
+        ctx.save_for_backward(color, bg, pos, aa_ctx)
+        ctx.cfg = (up, bool(antialias), Bg, Cc, int(keep), H, W, bool(pool))
+        if pool:      # the up x up average of the composited image, in the same kernel (no [B,H,W,C] image)
+            out = torch.empty(B, H // up, W // up, keep, device=color.device)
+            _call("b2a_composite_up_pool_fwd", (_p(color), up, _p(bg), Bg, int(antialias), B, H, W, Cc, int(keep), _p(out), _p(aa_ctx), aa_ctx.numel(),
+                                                _stream()), tag="C%d" % Cc)
+            return out
         out = torch.empty(B, H, W, Cc, device=color.device)
         _call("b2a_composite_up_fwd", (_p(color), up, _p(bg), Bg, int(antialias), B, H, W, Cc, _p(out), _p(aa_ctx), aa_ctx.numel(), _stream()),
               tag="C%d" % Cc)
-        ctx.save_for_backward(color, bg, pos, aa_ctx)
-        ctx.cfg = (up, bool(antialias), Bg, Cc, int(keep), H, W)
         return out[..., :keep] if keep < Cc else out
 
     @staticmethod
     def backward(ctx, g):
         color, bg, pos, aa_ctx = ctx.saved_tensors
-        up, antialias, Bg, Cc, keep, H, W = ctx.cfg
+        up, antialias, Bg, Cc, keep, H, W, pool = ctx.cfg
         if g.dtype != torch.float32:
             g = g.float()
         d_color = torch.empty_like(color)
         d_pos = torch.zeros_like(pos) if (ctx.needs_input_grad[2] and antialias) else None
         sb, sy, sx, sc = g.stride()
-        _call("b2a_composite_up_bwd", (_p(color), up, _p(bg), Bg, int(antialias), _p(g), sb, sy, sx, sc, keep, color.shape[0], pos.shape[1], H, W,
-                                        Cc, _p(d_color), _p(d_pos), _p(aa_ctx), aa_ctx.numel(), _stream()), tag="C%d" % Cc)
-        return d_color, None, d_pos, None, None, None, None, None, None
+        _call("b2a_composite_up_pool_bwd" if pool else "b2a_composite_up_bwd",
+              (_p(color), up, _p(bg), Bg, int(antialias), _p(g), sb, sy, sx, sc, keep, color.shape[0], pos.shape[1], H, W,
+               Cc, _p(d_color), _p(d_pos), _p(aa_ctx), aa_ctx.numel(), _stream()), tag="C%d" % Cc)
+        return d_color, None, d_pos, None, None, None, None, None, None, None
 
 
 def composite_up_supported(color, aa_ctx):
     return aa_ctx is not None and 1 <= color.shape[-1] <= 3 and color.dtype == torch.float32
 
 
-def composite_up(color, background, pos, resolution, up=1, antialias_edges=True, keep=None, aa_ctx=None):
-    """color [B,H/up,W/up,C-1] (C <= 4) -> composited (+ antialiased) [B,H,W,keep] at the raster resolution (H,W)."""
+def composite_up(color, background, pos, resolution, up=1, antialias_edges=True, keep=None, aa_ctx=None, pool=False):
+    """color [B,H/up,W/up,C-1] (C <= 4) -> composited (+ antialiased) [B,H,W,keep] at the raster resolution (H,W); pool: the
+    up x up average of that image, [B,H/up,W/up,keep] (the msaa resolve of render.py:322-323, fused)."""
     if not composite_up_supported(color, aa_ctx):
         raise _lib.B2AError("composite_up: needs a prepared context and at most 3 colour channels")
     Cc = color.shape[-1] + 1
     return _CompositeUp.apply(color, background, pos, int(up), bool(antialias_edges), Cc if keep is None else int(keep), aa_ctx,
-                              int(resolution[0]), int(resolution[1]))
+                              int(resolution[0]), int(resolution[1]), bool(pool) and up > 1)
 
 
 # ---------------------------------------------------------------------------------------------------------------

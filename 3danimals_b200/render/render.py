@@ -16,6 +16,7 @@ from .. import field_mlp
 from .. import ops
 
 # A/B switch for measurements: B2A_FUSE_AA_PAIR=0 renders the training pair of keys with two single-key launches
+FUSE_MSAA_RESOLVE = os.environ.get("B2A_FUSE_MSAA_RESOLVE", "1") != "0"
 FUSE_AA_PAIR = os.environ.get("B2A_FUSE_AA_PAIR", "1") != "0"
 
 
@@ -235,7 +236,12 @@ def render_mesh(ctx, mesh, mtx_in, w2c, view_pos, material, lgt, resolution, spp
         if (shade_spp > 1 or key not in _AA_KEYS) and ops.composite_up_supported(color, aa_ctx):
             # msaa / logging keys: the low-resolution colour is up-sampled inside the composite kernel (no [B,H*spp,W*spp,C]
             # copies), un-antialiased keys composite in the same kernel instead of a torch lerp sequence
-            accum = ops.composite_up(color, bg, v_pos_clip, full_res, up=shade_spp, antialias_edges=key in _AA_KEYS, keep=keep, aa_ctx=aa_ctx)
+            pooled = FUSE_MSAA_RESOLVE and spp > 1 and shade_spp == spp
+            accum = ops.composite_up(color, bg, v_pos_clip, full_res, up=shade_spp, antialias_edges=key in _AA_KEYS, keep=keep, aa_ctx=aa_ctx,
+                                     pool=pooled)
+            if pooled:      # the spp x spp average (render.py:322-323) came out of the same kernel
+                out_buffers.append(accum.permute(0, 3, 1, 2))
+                continue
         else:
             accum = ops.composite_antialias(_nearest_up(color, shade_spp), bg, rast, v_pos_clip, tri, opp, antialias_edges=key in _AA_KEYS,
                                             keep=keep, aa_ctx=aa_ctx)

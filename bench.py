@@ -256,7 +256,8 @@ def run_reference(args):
 # ours
 # ----------------------------------------------------------------------------------------------------------------
 GRAD_SET_BYTES = 68 << 20       # fp32 parameter gradients all-reduced per step by the reference under DDP (MagicPony ~68 MB)
-RASTER_BWD_CALLS = ("b2a_antialias_pair_bwd", "b2a_antialias_bwd", "b2a_composite_up_bwd", "b2a_render_geometry_bwd", "b2a_gbuffer_bwd")
+RASTER_BWD_CALLS = ("b2a_antialias_pair_bwd", "b2a_antialias_bwd", "b2a_composite_up_bwd", "b2a_composite_up_pool_bwd", "b2a_render_geometry_bwd",
+                    "b2a_gbuffer_bwd")
 
 
 def algorithmic_bytes(name, tag, st):
@@ -271,6 +272,10 @@ def algorithmic_bytes(name, tag, st):
         C = int(tag[1:]) if tag.startswith("C") and tag[1:].isdigit() else 4
         keep = C if C == 4 else C - 1            # shaded keeps alpha, dino / kd / ... drop it
         return B * HW * 4 * keep + B * st["gHW"] * 4 * (C - 1) + bits
+    if name == "b2a_composite_up_pool_bwd":       # msaa resolve fused: gradient in and out at the g-buffer resolution, coverage + activity bits at the raster's
+        C = int(tag[1:]) if tag.startswith("C") and tag[1:].isdigit() else 4
+        keep = C if C == 4 else C - 1
+        return B * st["gHW"] * 4 * keep + B * st["gHW"] * 4 * (C - 1) + 2 * bits
     # g-buffer / rasterize adjoint + per-vertex finalize + clip-transform adjoint (SURVEY.md §8d phase B, restated for this design):
     # per g-buffer pixel rast 16 B + 12 B per consumed gradient, a 16-byte list entry per covered pixel; per (image, vertex) the
     # read-modify-write of the four gradient rows d_v_pos, d_v_nrm, d_prior, d_clip (2 x (12 + 12 + 12 + 16) = 104 B, SURVEY's own term),

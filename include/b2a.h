@@ -205,6 +205,15 @@ int b2a_composite_up_bwd(const float* color, int up, const float* bg, int Bg, in
                          int64_t d_sb, int64_t d_sy, int64_t d_sx, int64_t d_sc, int Cg, int B, int64_t V, int H, int W,
                          int C, float* d_color, float* d_pos, const void* aa_ctx, size_t aa_ctx_bytes,
                          b2a_stream_t stream);
+/* The same, followed by the spp x spp average of the result (render.py:322-323 util.avg_pool_nhwc) in the same kernel:
+ * out [B,H/up,W/up,keep] (the leading `keep` of the C channels); the raster-resolution image is never materialised.
+ * d_out: gradient of that average, strides over [B,H/up,W/up,Cg].  Bit-identical to b2a_composite_up_fwd + avg_pool2d. */
+int b2a_composite_up_pool_fwd(const float* color, int up, const float* bg, int Bg, int antialias, int B, int H, int W, int C,
+                              int keep, float* out, const void* aa_ctx, size_t aa_ctx_bytes, b2a_stream_t stream);
+int b2a_composite_up_pool_bwd(const float* color, int up, const float* bg, int Bg, int antialias, const float* d_out,
+                              int64_t d_sb, int64_t d_sy, int64_t d_sx, int64_t d_sc, int Cg, int B, int64_t V, int H, int W,
+                              int C, float* d_color, float* d_pos, const void* aa_ctx, size_t aa_ctx_bytes,
+                              b2a_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Directional-light diffuse shading (DirectionalLight.shade, model/render/light.py:186-193):

@@ -579,6 +579,56 @@ def test_composite_up_oracle(cuda, C, keep, up, aa, with_bg):
         assert pd.grad is None or float(pd.grad.abs().max()) == 0
 
 
+@pytest.mark.parametrize("C,keep,up,aa,with_bg", [(4, 4, 2, True, True), (4, 4, 4, True, False), (2, 1, 4, True, True), (4, 3, 2, False, True),
+                                                  (3, 2, 4, True, False)])
+def test_composite_up_pool_oracle(cuda, C, keep, up, aa, with_bg):
+    """The msaa resolve fused into the composite kernel (b2a_composite_up_pool_fwd/bwd) vs the reference's sequence: nearest upsample
+    (render.py:217-219) -> lerp composite -> antialias -> channel slice -> avg_pool (render.py:322-323, util.avg_pool_nhwc); and
+    bit-identical to the unfused library path (composite_up, then avg_pool2d)."""
+    ops = _ops()
+    verts, faces, prior, mvp, w2c, campos, clip = _scene()
+    S = 128
+    s = S // up
+    rast = R.rasterize(clip, faces, (S, S))
+    rng = np.random.RandomState(17)
+    color = rng.rand(3, s, s, C - 1).astype(np.float32)
+    bg = rng.rand(3, S, S, C).astype(np.float32) if with_bg else None
+    opp = R.edge_adjacency(faces, verts.shape[1])
+    ct = torch.from_numpy(color).requires_grad_(True)
+    pt = torch.from_numpy(clip).requires_grad_(True)
+    alpha = torch.from_numpy((rast[..., 3:] > 0).astype(np.float32))
+    bgt = torch.from_numpy(bg) if with_bg else torch.zeros(1, S, S, C)
+    cu = ct.repeat_interleave(up, dim=1).repeat_interleave(up, dim=2)
+    acc = torch.lerp(bgt.expand(3, -1, -1, -1), torch.cat((cu, torch.ones_like(cu[..., :1])), -1), alpha)
+    if aa:
+        acc = T.antialias(acc.contiguous(), torch.from_numpy(rast), pt, torch.from_numpy(faces), torch.from_numpy(opp))
+    ref = torch.nn.functional.avg_pool2d(acc[..., :keep].permute(0, 3, 1, 2), up)
+    g = rng.randn(*ref.shape).astype(np.float32)
+    (ref * torch.from_numpy(g)).sum().backward()
+    res = []
+    for pool in (True, False):
+        cd = dev(color, cuda).requires_grad_(True)
+        pd = dev(clip, cuda).requires_grad_(True)
+        aa_ctx = ops.antialias_prepare(dev(rast, cuda), pd.detach(), dev(faces, cuda), dev(opp, cuda))
+        ops.stats.reset()
+        out = ops.composite_up(cd, dev(bg, cuda) if with_bg else None, pd, (S, S), up=up, antialias_edges=aa, keep=keep, aa_ctx=aa_ctx,
+                               pool=pool).permute(0, 3, 1, 2)
+        if not pool:
+            out = torch.nn.functional.avg_pool2d(out, up)
+        assert tuple(out.shape) == (3, keep, s, s)
+        out.backward(dev(g, cuda))
+        assert ("b2a_composite_up_pool_fwd" in ops.stats.calls) == pool and ("b2a_composite_up_pool_bwd" in ops.stats.calls) == pool
+        res.append((out.detach().cpu().numpy(), cd.grad.cpu().numpy(), None if pd.grad is None else pd.grad.cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0])                                   # fused == unfused, bit for bit
+    assert rel_err(res[0][0], ref.detach().numpy()) < 1e-6                        # the host's avg_pool sums in another order
+    assert rel_err(res[0][1], res[1][1]) < 1e-6 and rel_err(res[0][1], ct.grad.numpy()) < TOL
+    if aa:
+        assert np.abs(pt.grad.numpy()).max() > 0
+        assert rel_err(res[0][2], pt.grad.numpy()) < TOL and rel_err(res[0][2], res[1][2]) < 1e-5
+    else:
+        assert res[0][2] is None or float(np.abs(res[0][2]).max()) == 0
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # fused g-buffer
 # ----------------------------------------------------------------------------------------------------------------
