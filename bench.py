@@ -48,7 +48,7 @@ CONFIGS = {
     "c4": dict(workload="visualize rotation / texture finetune: batch 1, 512x512 at spp 4 (2048^2 internal), DMTet res 256 (17M verts / 100M tets), "
                         "one step = one texture-finetune iteration ['shaded'] fwd+bwd on the fixed mesh, CUDA-graph replay",
                grid_res=256, batch_per_gpu=1, image_res=512, bones=20, dino_dim=16, spp=4,
-               l2="2048^2 internal buffers (67 MB rast + 134 MB of colour / gradient) exceed L2"),
+               l2="2048^2 internal buffers (67 MB rast + 67 MB antialias records + coverage words; the colour / gradient images at that resolution are no longer materialised) exceed L2"),
 }
 SCENE_KW = {
     "c1": dict(),
