@@ -49,7 +49,8 @@ def _stale():
 def _compile(nvcc, src, verbose):
     obj = os.path.join(OUT_DIR, os.path.basename(src)[:-3] + ".o")
     flags = FAST_FLAGS if os.path.basename(src) in FAST_FILES else EXACT_FLAGS
-    cmd = [nvcc] + COMMON_FLAGS + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    extra = os.environ.get("B2A_NVCC_DEFINES", "").split()      # profiling builds, e.g. -DB2A_MLP_TRACE (csrc/field_mlp.cu)
+    cmd = [nvcc] + COMMON_FLAGS + flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
     res = subprocess.run(cmd, capture_output=True, text=True)
     return obj, res
 

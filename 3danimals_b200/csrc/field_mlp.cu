@@ -179,6 +179,17 @@ __global__ void __launch_bounds__(256) mlp_pack_weights_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// clock64 trace of ONE CTA (profiling builds only: B2A_NVCC_DEFINES=-DB2A_MLP_TRACE python 3danimals_b200/build.py --force; read with
+// scripts/dbg_gemm_trace.py / dbg_wgrad_trace.py through b2a_debug_mlp_trace).  Compiles to nothing otherwise.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifdef B2A_MLP_TRACE
+__device__ unsigned long long g_mlp_trace[128];
+#define MLP_STAMP(on, i) do { if (on) g_mlp_trace[(i)] = clock64(); } while (0)
+#else
+#define MLP_STAMP(on, i) do { } while (0)
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Rows GEMM
 // ---------------------------------------------------------------------------------------------------------------------
 enum { EPI_BIAS = 0, EPI_MASK = 1, EPI_SIGMOID = 2 };
@@ -265,6 +276,9 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
     __shared__ __align__(8) uint64_t full_b[2], mma_done[2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool tr = blockIdx.x == 700 && tid == 0, itr = blockIdx.x == 700 && tid == GEMM_THREADS;      // (trace builds) staging thread 0, issuer
+    (void)tr; (void)itr;
+    MLP_STAMP(tr, 0);
     const int64_t row0 = (int64_t)blockIdx.x * TILE_M;
     const uint32_t tmem_cols = P.Npad <= 32 ? 32u : (P.Npad <= 64 ? 64u : (P.Npad <= 128 ? 128u : 256u));
     const int nchunks = P.Kpad / KC;
@@ -293,10 +307,11 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
     tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
     const uint32_t idesc = instr_desc(TILE_M, P.Npad, 0, 0);
+    MLP_STAMP(tr, 1);
 
     // weights of chunk c: one bulk copy (hi | lo are adjacent) into stage c & 1, issued ONE CHUNK AHEAD of its use (chunk 0 here,
-    // chunk c+1 right after the MMAs of chunk c are issued) - issued in the iteration that consumes it, the issuer sat out the
-    // L2 -> shared latency of 32 KB in front of every chunk's MMAs
+    // chunk c+1 at the top of iteration c) - issued in the iteration that consumes it, the issuer sat out the L2 -> shared latency of
+    // 32 KB in front of every chunk's MMAs
     auto weights = [&](int c) {
         const int s = c & 1;
         mbar_expect_tx(&full_b[s], w_bytes);
@@ -307,14 +322,24 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
         const int s = c & 1;
         uint8_t* st = smem + (size_t)s * stage_bytes;
         if (c >= 2) mbar_wait(&mma_done[s], ((c >> 1) - 1) & 1);        // the MMAs that read this stage (chunk c-2) have completed
+        MLP_STAMP(tr && c < 8, 2 + 3 * c);
         if (!issuer) {
             a_store(P, st, a_bytes, tid, v);                             // activations of chunk c: registers -> hi / lo images
             if (c + 2 < nchunks) a_load(P, row0, c + 2, tid, v);         // chunk c+2 into the buffer just drained
+        } else if (lane == 0 && c + 1 < nchunks) {
+            // the NEXT chunk's weights, requested while the staging warps work on this one: the other stage's last readers were the
+            // MMAs of chunk c-1 (the clock64 trace showed the 32 KB copy landing 0.3-0.7 us after the barrier when it was requested
+            // only after this chunk's MMAs - the L2 is the busy unit of this kernel)
+            if (c >= 1) mbar_wait(&mma_done[s ^ 1], ((c - 1) >> 1) & 1);
+            weights(c + 1);
         }
+        MLP_STAMP(tr && c < 8, 3 + 3 * c);
         __syncthreads();
+        MLP_STAMP(tr && c < 8, 4 + 3 * c);
         if (issuer && lane == 0) {
             fence_proxy_async();        // the staged images (generic-proxy stores, ordered by the barrier) -> visible to the tensor core
             mbar_wait(&full_b[s], (c >> 1) & 1);
+            MLP_STAMP(itr && c < 8, 64 + 2 * c);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(st), a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
             const uint32_t a_lbo = A_LBO, b_lbo = (uint32_t)P.Npad * 16;
@@ -329,10 +354,7 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
                 }
             }
             umma_commit(&mma_done[s]);      // arrives when every MMA issued so far has completed (implies fence::before_thread_sync)
-            if (c + 1 < nchunks) {          // next chunk's weights go into the other stage: its last readers were the MMAs of chunk c-1
-                if (c >= 1) mbar_wait(&mma_done[s ^ 1], ((c - 1) >> 1) & 1);
-                weights(c + 1);
-            }
+            MLP_STAMP(itr && c < 8, 65 + 2 * c);
         }
     };
     for (int c = 0; c < nchunks; c += 2) {
@@ -352,9 +374,11 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
         }
     }
     // all MMAs done: the last commit covers every earlier one
+    MLP_STAMP(tr, 40);
     mbar_wait(&mma_done[(nchunks - 1) & 1], ((nchunks - 1) >> 1) & 1);
     __syncwarp();                   // tcgen05.ld is .sync.aligned: the K-tail path of the staging and the spin loop can leave lanes diverged
     tc_fence_after();
+    MLP_STAMP(tr, 41);
 
     // Epilogue.  Warp w reads the 32 accumulator lanes of its quadrant (w % 4): thread t holds 32 consecutive columns of row
     // 32*(w%4) + t.  The 32 x 32 block goes through a shared-memory tile (the pipeline stages are free now; rows 36 words apart:
@@ -421,8 +445,10 @@ __global__ void __launch_bounds__(GEMM_LAUNCH, 2) mlp_rows_gemm_kernel(GemmParam
             }
         }
     }
+    MLP_STAMP(tr, 42);
     tc_fence_before();
     __syncthreads();
+    MLP_STAMP(tr, 43);
     if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
 }
 
@@ -524,6 +550,9 @@ __global__ void __launch_bounds__(WG_LAUNCH_THREADS, 1) mlp_wgrad_kernel(WgradPa
 
     // two chunks of both operands in flight per thread (register double buffer, buffer = chunk parity = stage), as in the rows GEMM
     const bool issuer = warp == WG_WARPS;                // the last warp: proxy fence + MMAs (see mlp_rows_gemm_kernel)
+    const bool wtr = blockIdx.x == 70 && tid == 0;       // (trace builds)
+    (void)wtr;
+    MLP_STAMP(wtr, 96);
     float vp[2][PI][8], vq[2][QI][8];
     if (!issuer) {
         mn_load<PI>(W.Pm, W.ldp, r_end, W.M, r_begin, 0, warp, lane, vp[0]);
@@ -585,9 +614,11 @@ __global__ void __launch_bounds__(WG_LAUNCH_THREADS, 1) mlp_wgrad_kernel(WgradPa
         chunk(c, vp[0], vq[0]);
         if (c + 1 < nchunks) chunk(c + 1, vp[1], vq[1]);
     }
+    MLP_STAMP(wtr, 97);
     mbar_wait(&mma_done[(nchunks - 1) & 1], ((nchunks - 1) >> 1) & 1);
     __syncwarp();
     tc_fence_after();
+    MLP_STAMP(wtr, 98);
     // epilogue: thread t of quadrant q holds row m0 + 32q + t, 32 consecutive n: one reduction per element into the shared result
     const int quad = warp & 3;
     const int ngroups = (W.Npad + 31) / 32;
@@ -610,8 +641,10 @@ __global__ void __launch_bounds__(WG_LAUNCH_THREADS, 1) mlp_wgrad_kernel(WgradPa
             }
         }
     }
+    MLP_STAMP(wtr, 99);
     tc_fence_before();
     __syncthreads();
+    MLP_STAMP(wtr, 100);
     if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
 }
 
@@ -729,6 +762,13 @@ __global__ void __launch_bounds__(256) mlp_colsum256_kernel(const float* __restr
 }
 
 }  // namespace
+
+#ifdef B2A_MLP_TRACE
+B2A_API int b2a_debug_mlp_trace(unsigned long long* out128)
+{
+    return cudaMemcpyFromSymbol(out128, g_mlp_trace, sizeof(unsigned long long) * 128) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 B2A_API int b2a_mlp_packed_bytes(int N, int K, size_t* bytes)
 {
