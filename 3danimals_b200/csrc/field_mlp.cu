@@ -619,22 +619,41 @@ __global__ void __launch_bounds__(WG_LAUNCH_THREADS, 1) mlp_wgrad_kernel(WgradPa
     __syncwarp();
     tc_fence_after();
     MLP_STAMP(wtr, 98);
-    // epilogue: thread t of quadrant q holds row m0 + 32q + t, 32 consecutive n: one reduction per element into the shared result
+    // epilogue: thread t of quadrant q holds row m0 + 32q + t, 32 consecutive n.  The 148 partial results are reduced into the shared
+    // result with 128-bit reductions; the 32 x 32 block goes through a shared-memory tile first (the stages are free now) so that a warp
+    // instruction covers four whole 128-byte lines instead of 32 lines of 16 bytes each - the L2's reduction rate bounds this phase
+    // (2.4 M float4 reductions per launch) - and the CTAs walk the column groups in different orders so that they do not all hit the
+    // same lines at the same time.
     const int quad = warp & 3;
     const int ngroups = (W.Npad + 31) / 32;
-    for (int gi = issuer ? ngroups * mtiles : (warp >> 2); gi < ngroups * mtiles; gi += WG_WARPS / 4) {
+    const int ngi = ngroups * mtiles, step = WG_WARPS / 4;
+    const int iters = (ngi + step - 1) / step;
+    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * 36);
+    for (int k = 0; k < (issuer ? 0 : iters); k++) {
+        const int gi = (warp >> 2) + ((k + (int)blockIdx.x) % iters) * step;
+        if (gi >= ngi) continue;
         const int mt = gi / ngroups, g = gi - mt * ngroups;
-        const int m = mt * TILE_M + quad * 32 + lane;
         float v[32];
         __syncwarp();
         tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(mt * acc_cols + g * 32), v);
-        if (m < W.M) {
-            const int n0 = g * 32;
-            if (!W.transpose_out && n0 + 32 <= W.N && (W.ldo & 3) == 0) {
-                float* o = W.out + (size_t)m * W.ldo + n0;
+        const int n0 = g * 32;
+        if (!W.transpose_out && n0 + 32 <= W.N && (W.ldo & 3) == 0) {
+            __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(o + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            } else {
+            for (int q = 0; q < 8; q++)
+                *reinterpret_cast<float4*>(tile + lane * 36 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int r = it * 4 + (lane >> 3);
+                const int m = mt * TILE_M + quad * 32 + r;
+                if (m < W.M)
+                    atomicAdd(reinterpret_cast<float4*>(W.out + (size_t)m * W.ldo + n0 + 4 * (lane & 7)),
+                              *reinterpret_cast<const float4*>(tile + r * 36 + 4 * (lane & 7)));
+            }
+        } else {
+            const int m = mt * TILE_M + quad * 32 + lane;
+            if (m < W.M) {
 #pragma unroll
                 for (int j = 0; j < 32; j++)
                     if (n0 + j < W.N) atomicAdd(W.transpose_out ? W.out + (size_t)(n0 + j) * W.ldo + m : W.out + (size_t)m * W.ldo + n0 + j, v[j]);
@@ -844,7 +863,8 @@ B2A_API int b2a_mlp_wgrad(const float* P, int64_t ldp, int relu_p, const float* 
     if (per < 8 * KC) per = 8 * KC;
     W.rows_per_cta = per;
     nsplit = (rows + per - 1) / per;
-    const int smem = 2 * (2 * KC * mtiles * TILE_M * 2 + 2 * KC * W.Npad * 2);
+    int smem = 2 * (2 * KC * mtiles * TILE_M * 2 + 2 * KC * W.Npad * 2);
+    if (smem < WG_WARPS * 32 * 36 * 4) smem = WG_WARPS * 32 * 36 * 4;      // the epilogue's transposition tiles reuse the stages
     const dim3 grid((unsigned)nsplit);
 #define WG_LAUNCH(PI, QI)                                                                                                \
     do {                                                                                                                 \

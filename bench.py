@@ -366,9 +366,14 @@ def run_ours(args):
             buckets.launch_many((last,), inline=True)       # nothing left to overlap with: on the compute stream (peer-memory backend)
             buckets.wait()
 
+    # optimizer.zero_grad(set_to_none=True) (PyTorch's default): the field networks' gradients are written, not accumulated into last step's
+    net_params = [p for m in (hp.material, hp.dino_net) if isinstance(m, torch.nn.Module) for p in m.parameters()] if args.mlps else []
+
     def step():
         hp.sdf.grad = None
         hp.angles.grad = None
+        for p in net_params:
+            p.grad = None
         outs = hp.forward()
         buckets.launch_many(standins)
         torch.autograd.backward(list(outs), ups)
@@ -472,6 +477,8 @@ def run_ours(args):
         consumed[slot].record()
         hp.sdf.grad = None
         hp.angles.grad = None
+        for p in net_params:
+            p.grad = None
         t0 = mark("convert", t0)
         outs = hp.forward()
         t0 = mark("forward", t0)
