@@ -789,6 +789,43 @@ __global__ void __launch_bounds__(256) mlp_colsum256_kernel(const float* __restr
     if (t != 0.f) atomicAdd(out + (size_t)sgm * 256 + threadIdx.x, t);
 }
 
+// out[r, :] = src[idx[r], :] for the covered rows of a dense [n, C] image (C floats per row): one thread per (row, 16-byte piece) when
+// rows are 16-byte multiples, else per element.  (torch's index_select took 98 us for 185 k rows of 64 bytes.)
+__global__ void __launch_bounds__(256) rows_gather_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, int64_t N, int C,
+                                                          float* __restrict__ out)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((C & 3) == 0) {
+        const int q = C >> 2;
+        if (t >= N * q) return;
+        const int64_t r = t / q;
+        const int k = (int)(t - r * q);
+        reinterpret_cast<float4*>(out)[t] = __ldg(reinterpret_cast<const float4*>(src + __ldg(idx + r) * C) + k);
+    } else {
+        if (t >= N * C) return;
+        const int64_t r = t / C;
+        out[t] = __ldg(src + __ldg(idx + r) * C + (t - r * C));
+    }
+}
+
+// dst[idx[r], :] = src[r, :] (dst rows not named by idx are left as they are: the caller zero-fills)
+__global__ void __launch_bounds__(256) rows_scatter_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, int64_t N, int C,
+                                                           float* __restrict__ dst)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((C & 3) == 0) {
+        const int q = C >> 2;
+        if (t >= N * q) return;
+        const int64_t r = t / q;
+        const int k = (int)(t - r * q);
+        reinterpret_cast<float4*>(dst + __ldg(idx + r) * C)[k] = __ldg(reinterpret_cast<const float4*>(src) + t);
+    } else {
+        if (t >= N * C) return;
+        const int64_t r = t / C;
+        dst[__ldg(idx + r) * C + (t - r * C)] = __ldg(src + t);
+    }
+}
+
 }  // namespace
 
 #ifdef B2A_MLP_TRACE
@@ -797,6 +834,34 @@ B2A_API int b2a_debug_mlp_trace(unsigned long long* out128)
     return cudaMemcpyFromSymbol(out128, g_mlp_trace, sizeof(unsigned long long) * 128) == cudaSuccess ? 0 : 1;
 }
 #endif
+
+// Covered-row gather / scatter between the dense shaded image [n, C] and the compact rows [N, C] the field networks are evaluated on
+// (3danimals_b200/render/render.py _sample_field; reference: the dense material.sample / dino_net.sample at render.py:54,61).
+// idx [N] int64 row numbers (unique).  scatter: dst is zero-filled here (cudaMemsetAsync) when zero_fill != 0.
+B2A_API int b2a_rows_gather(const float* src, const int64_t* idx, int64_t N, int C, float* out, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(N >= 0 && C > 0 && ((src && idx && out) || N == 0), "arguments");
+    B2A_CHECK_ARG((C & 3) != 0 || ((((uintptr_t)src | (uintptr_t)out) & 15) == 0), "16-byte alignment");
+    if (N == 0) return 0;
+    const int64_t n = (C & 3) == 0 ? N * (C >> 2) : N * C;
+    rows_gather_kernel<<<b2a_blocks(n, 256), 256, 0, stream>>>(src, idx, N, C, out);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+B2A_API int b2a_rows_scatter(const float* src, const int64_t* idx, int64_t N, int C, float* dst, int64_t dst_rows, int zero_fill, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(dst && N >= 0 && C > 0 && dst_rows >= N && ((src && idx) || N == 0), "arguments");
+    B2A_CHECK_ARG((C & 3) != 0 || ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0), "16-byte alignment");
+    if (zero_fill) B2A_CUDA_OK(cudaMemsetAsync(dst, 0, (size_t)dst_rows * C * sizeof(float), stream));
+    if (N == 0) return 0;
+    const int64_t n = (C & 3) == 0 ? N * (C >> 2) : N * C;
+    rows_scatter_kernel<<<b2a_blocks(n, 256), 256, 0, stream>>>(src, idx, N, C, dst);
+    B2A_LAUNCH_OK();
+    return 0;
+}
 
 B2A_API int b2a_mlp_packed_bytes(int N, int K, size_t* bytes)
 {

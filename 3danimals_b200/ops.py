@@ -66,7 +66,7 @@ def _workspace(nbytes, device):
 # kernels launched by each C-ABI entry point (memsets / memcpys are not kernels) - the source of bench.py's gpu_launches
 KERNELS_PER_CALL = {
     "b2a_mt_count": 4, "b2a_mt_emit": 2, "b2a_mt_bwd": 1, "b2a_estimate_bones": 4, "b2a_lbs_bone_transforms": 2, "b2a_lbs_fwd": 1, "b2a_lbs_bwd": 1,
-    "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1, "b2a_composite_up_pool_fwd": 1, "b2a_composite_up_pool_bwd": 1, "b2a_articulation_constraints_fwd": 1, "b2a_articulation_constraints_bwd": 1,
+    "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1, "b2a_rows_gather": 1, "b2a_rows_scatter": 2, "b2a_composite_up_pool_fwd": 1, "b2a_composite_up_pool_bwd": 1, "b2a_articulation_constraints_fwd": 1, "b2a_articulation_constraints_bwd": 1,
     "b2a_xfm_points_bwd": 1, "b2a_rasterize_fwd": 3, "b2a_rasterize_bwd": 1, "b2a_interpolate_fwd": 1, "b2a_interpolate_bwd": 1,
     "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 2,
     "b2a_antialias_pair_fwd": 1, "b2a_antialias_pair_bwd": 1, "b2a_shade_directional_fwd": 1, "b2a_shade_directional_bwd": 1,
@@ -773,6 +773,34 @@ class _CompositeUp(torch.autograd.Function):
               (_p(color), up, _p(bg), Bg, int(antialias), _p(g), sb, sy, sx, sc, keep, color.shape[0], pos.shape[1], H, W,
                Cc, _p(d_color), _p(d_pos), _p(aa_ctx), aa_ctx.numel(), _stream()), tag="C%d" % Cc)
         return d_color, None, d_pos, None, None, None, None, None, None, None
+
+
+class _ScatterRows(torch.autograd.Function):
+    """dense[idx[r]] = rows[r], zero elsewhere (b2a_rows_scatter); backward: the gather of the same rows (b2a_rows_gather)."""
+
+    @staticmethod
+    def forward(ctx, rows, idx, n):
+        rows = _f32(rows, "rows")
+        N, C = rows.shape
+        out = torch.empty(n, C, device=rows.device)
+        _call("b2a_rows_scatter", (_p(rows), _p(idx), N, C, _p(out), n, 1, _stream()))
+        ctx.save_for_backward(idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = _f32(g, "d_dense")
+        out = torch.empty(idx.shape[0], g.shape[1], device=g.device)
+        _call("b2a_rows_gather", (_p(g), _p(idx), idx.shape[0], g.shape[1], _p(out), _stream()))
+        return out, None, None
+
+
+def scatter_rows(rows, idx, n):
+    """rows [N,C] (the field networks' outputs on the covered pixels), idx [N] int64 unique -> dense [n,C], zero at the other rows."""
+    if idx.dtype != torch.int64 or not idx.is_contiguous():
+        idx = idx.long().contiguous()
+    return _ScatterRows.apply(rows, idx, int(n))
 
 
 def composite_up_supported(color, aa_ctx):

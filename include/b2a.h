@@ -301,6 +301,16 @@ int b2a_render_geometry_bwd(const float* rast, int spp, const float* mtx, const 
                             float* d_w2c, float* d_campos, b2a_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Covered-row gather / scatter between a dense shaded image [n, C] and the compact rows [N, C] the field networks are
+ * evaluated on (the reference samples material / dino_net densely, model/render/render.py:54,61; uncovered pixels never
+ * reach an output).  idx [N] int64 unique row numbers.  scatter writes dst[idx[r]] = src[r]; zero_fill != 0 clears dst
+ * [dst_rows, C] first.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2a_rows_gather(const float* src, const int64_t* idx, int64_t N, int C, float* out, b2a_stream_t stream);
+int b2a_rows_scatter(const float* src, const int64_t* idx, int64_t N, int C, float* dst, int64_t dst_rows, int zero_fill,
+                     b2a_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Field MLPs on the tensor cores (tcgen05 + tensor memory).  Replaces the fp32 GEMMs of CoordMLP.forward
  * (model/networks/MLPs.py:34-101) behind material.sample / dino_net.sample (model/render/render.py:54,61) on the covered
  * rows.  Every fp32 operand is split into two bf16 terms and each product is three MMAs with fp32 accumulation

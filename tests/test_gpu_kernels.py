@@ -629,6 +629,26 @@ def test_composite_up_pool_oracle(cuda, C, keep, up, aa, with_bg):
         assert res[0][2] is None or float(np.abs(res[0][2]).max()) == 0
 
 
+@pytest.mark.parametrize("C", [3, 9, 16])
+def test_scatter_rows_matches_index_copy(cuda, C):
+    """ops.scatter_rows (b2a_rows_scatter / b2a_rows_gather) against torch's new_zeros(...).index_copy / its adjoint: the dense <-> covered
+    rows hand-over around the field networks (render._sample_field)."""
+    ops = _ops()
+    torch.manual_seed(C)
+    n, N = 40000, 9000
+    idx = torch.randperm(n, device=cuda)[:N].sort().values
+    rows = torch.randn(N, C, device=cuda)
+    g = torch.randn(n, C, device=cuda)
+    a = rows.clone().requires_grad_(True)
+    b = rows.clone().requires_grad_(True)
+    want = a.new_zeros(n, C).index_copy(0, idx, a)
+    got = ops.scatter_rows(b, idx, n)
+    assert torch.equal(got, want)
+    want.backward(g); got.backward(g)
+    assert torch.equal(a.grad, b.grad)
+    assert ops.scatter_rows(torch.zeros(0, C, device=cuda), idx[:0], 16).abs().sum().item() == 0
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # fused g-buffer
 # ----------------------------------------------------------------------------------------------------------------
