@@ -178,6 +178,40 @@ __global__ void __launch_bounds__(256) mlp_pack_weights_kernel(const float* __re
     }
 }
 
+// All the weight images of a network in ONE launch (a step packs 26: every layer, both orientations - each a 3 us kernel plus a
+// launch gap on a GPU-bound stream).  Jobs travel in the kernel's parameter space.
+constexpr int PACK_MAX_JOBS = 32;
+struct PackJob {
+    const float* W;
+    uint16_t* out;
+    int ldw, N, K, transpose, Npad, Kpad;
+    long long first;                      // running offset of this job's Npad * Kpad elements
+};
+struct PackJobs {
+    PackJob j[PACK_MAX_JOBS];
+    int n;
+    long long total;
+};
+__global__ void __launch_bounds__(256) mlp_pack_many_kernel(const PackJobs J)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < J.total; i += (long long)gridDim.x * blockDim.x) {
+        int q = 0;
+        while (q + 1 < J.n && i >= J.j[q + 1].first) q++;
+        const PackJob& b = J.j[q];
+        const long long e = i - b.first;
+        const int k = (int)(e % b.Kpad), n = (int)(e / b.Kpad);
+        float w = 0.f;
+        if (n < b.N && k < b.K) w = b.transpose ? __ldg(b.W + (size_t)k * b.ldw + n) : __ldg(b.W + (size_t)n * b.ldw + k);
+        const __nv_bfloat16 h = __float2bfloat16_rn(w);
+        const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+        const int c = k / KC, kk = k % KC;
+        const size_t img = (size_t)b.Npad * KC;
+        const size_t off = (size_t)c * 2 * img + (size_t)(kk / 8) * b.Npad * 8 + (size_t)n * 8 + (kk % 8);
+        b.out[off] = __bfloat16_as_ushort(h);
+        b.out[off + img] = __bfloat16_as_ushort(l);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // clock64 trace of ONE CTA (profiling builds only: B2A_NVCC_DEFINES=-DB2A_MLP_TRACE python 3danimals_b200/build.py --force; read with
 // scripts/dbg_gemm_trace.py / dbg_wgrad_trace.py through b2a_debug_mlp_trace).  Compiles to nothing otherwise.
@@ -880,6 +914,32 @@ B2A_API int b2a_mlp_pack_weights(const float* W, int64_t ldw, int N, int K, int 
     B2A_CHECK_ARG(W && packed && packed_bytes >= need && ((uintptr_t)packed & 15) == 0, "packed buffer");
     const int Npad = (N + 15) / 16 * 16, Kpad = (K + KC - 1) / KC * KC;
     mlp_pack_weights_kernel<<<b2a_blocks((int64_t)Npad * Kpad, 256), 256, 0, stream>>>(W, (int)ldw, N, K, transpose, Npad, Kpad, (uint16_t*)packed);
+    B2A_LAUNCH_OK();
+    return 0;
+}
+
+// jobs: HOST array of n x 6 int64 {W (device pointer), ldw, N, K, transpose, packed (device pointer, b2a_mlp_packed_bytes(N, K) bytes,
+// 16-byte aligned)}: b2a_mlp_pack_weights for each, in one launch.  n <= 32.
+B2A_API int b2a_mlp_pack_weights_many(const int64_t* jobs, int n, b2a_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2A_CHECK_ARG(jobs && n > 0 && n <= PACK_MAX_JOBS, "1..32 jobs");
+    PackJobs J;
+    long long total = 0;
+    for (int i = 0; i < n; i++) {
+        const int64_t* q = jobs + 6 * i;
+        PackJob& b = J.j[i];
+        b.W = (const float*)(uintptr_t)q[0]; b.ldw = (int)q[1]; b.N = (int)q[2]; b.K = (int)q[3]; b.transpose = (int)q[4];
+        b.out = (uint16_t*)(uintptr_t)q[5];
+        B2A_CHECK_ARG(b.W && b.out && b.N > 0 && b.N <= 256 && b.K > 0 && ((uintptr_t)b.out & 15) == 0, "job");
+        b.Npad = (b.N + 15) / 16 * 16; b.Kpad = (b.K + KC - 1) / KC * KC;
+        b.first = total;
+        total += (long long)b.Npad * b.Kpad;
+    }
+    J.n = n; J.total = total;
+    unsigned blocks = b2a_blocks(total, 256);
+    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    mlp_pack_many_kernel<<<blocks, 256, 0, stream>>>(J);
     B2A_LAUNCH_OK();
     return 0;
 }

@@ -33,6 +33,20 @@ def _pack(w, n, k, transpose):
     return buf
 
 
+def _pack_many(jobs):
+    """[(w, n, k, transpose), ...] -> the packed images, one allocation and ONE launch (b2a_mlp_pack_weights_many)."""
+    import numpy as np
+    sizes = [(ops._size(ops._L().b2a_mlp_packed_bytes, n, k) + 255) // 256 * 256 for _, n, k, _ in jobs]
+    buf = torch.empty(sum(sizes), dtype=torch.uint8, device=jobs[0][0].device)
+    base, off, views, table = buf.data_ptr(), 0, [], np.empty((len(jobs), 6), np.int64)
+    for i, ((w, n, k, t), sz) in enumerate(zip(jobs, sizes)):
+        table[i] = (w.data_ptr(), w.stride(0), n, k, int(t), base + off)
+        views.append(buf[off:off + sz])
+        off += sz
+    _call("b2a_mlp_pack_weights_many", (table.ctypes.data, len(jobs), _stream()))
+    return views
+
+
 def _gemm(a, k, packed, n, relu, passes, epi, bias=None, bias_rows=None, mask=None, out=None, ldo=None, mask_bits=None, want_bits=False):
     """-> out, or (out, sign bits of out [rows, ceil16(n)/32 words... one uint32 per 32 columns]) with want_bits."""
     rows = a.shape[0]
@@ -88,16 +102,17 @@ class _FieldMLP(torch.autograd.Function):
         _call("b2a_mlp_embed_fwd", (_p(x), x.stride(0), N, n_harm, float(scalar), int(symmetrize), int(concat), _p(E), ldE, st))
         # every pre-activation is kept in fp32 (the weight gradients need relu(z)); its SIGN BITS are written by the same epilogue so
         # that the backward's ReLU-derivative mask reads 32 bytes per row instead of 1 KB
-        z, b = _gemm(E, kin, _pack(w_in, nf, kin, False), nf, False, passes, 0, bias=b_in, want_bits=True)
+        cout = ws[-1].shape[0]
+        packs = _pack_many([(w_in, nf, kin, False)] + [(w, nf, nf, False) for w in ws[:-1]] + [(ws[-1], cout, nf, False)])
+        z, b = _gemm(E, kin, packs[0], nf, False, passes, 0, bias=b_in, want_bits=True)
         zs, bits = [z], [b]
-        z, b = _gemm(zs[-1], nf, _pack(ws[0], nf, nf, False), nf, True, passes, 0, bias=bias_img, bias_rows=img if bias_img is not None else None,
+        z, b = _gemm(zs[-1], nf, packs[1], nf, True, passes, 0, bias=bias_img, bias_rows=img if bias_img is not None else None,
                      want_bits=True)
         zs.append(z); bits.append(b)
-        for w in ws[1:-1]:
-            z, b = _gemm(zs[-1], nf, _pack(w, nf, nf, False), nf, True, passes, 0, want_bits=True)
+        for i in range(1, len(ws) - 1):
+            z, b = _gemm(zs[-1], nf, packs[1 + i], nf, True, passes, 0, want_bits=True)
             zs.append(z); bits.append(b)
-        cout = ws[-1].shape[0]
-        out = _gemm(zs[-1], nf, _pack(ws[-1], cout, nf, False), cout, True, passes, 2 if sigmoid else 0)
+        out = _gemm(zs[-1], nf, packs[-1], cout, True, passes, 2 if sigmoid else 0)
         ctx.save_for_backward(x, E, out, seg_start, w_in, *ws, *zs, *bits)
         ctx.cfg = cfg
         ctx.n_w = len(ws)
@@ -131,14 +146,16 @@ class _FieldMLP(torch.autograd.Function):
         for n_ in sizes:
             offs.append(offs[-1] + n_)
         zeros_like = lambda i, w: pool[offs[i]:offs[i] + w.numel()].view(w.shape)
+        # transposed weight images of every layer for the dgrad GEMMs: one launch (tp[i] for ws[i], tp[-1] for w_in)
+        tp = _pack_many([(ws[i], nf, nf, True) for i in range(ctx.n_w - 1)] + [(ws[-1], nf, cout, True)] + ([(w_in, kin, nf, True)] if need[0] else []))
         d_ws = [None] * ctx.n_w
         d_ws[-1] = zeros_like(ctx.n_w - 1, ws[-1])
         _wgrad(zs[-1], True, dz, False, nf, cout, passes, d_ws[-1], transpose_out=True)          # d_W_out[c, j] = sum_r dz[r, c] relu(z)[r, j]
-        dzl = _gemm(dz, cout, _pack(ws[-1], nf, cout, True), nf, False, passes, 1, mask_bits=bits[-1])   # (dz . W_out) * [z_last > 0]
+        dzl = _gemm(dz, cout, tp[ctx.n_w - 1], nf, False, passes, 1, mask_bits=bits[-1])   # (dz . W_out) * [z_last > 0]
         for i in range(ctx.n_w - 2, 0, -1):                                                    # hidden layers W_i: z_{i+1} = W_i relu(z_i)
             d_ws[i] = zeros_like(i, ws[i])
             _wgrad(dzl, False, zs[i], True, nf, nf, passes, d_ws[i])
-            dzl = _gemm(dzl, nf, _pack(ws[i], nf, nf, True), nf, False, passes, 1, mask_bits=bits[i])
+            dzl = _gemm(dzl, nf, tp[i], nf, False, passes, 1, mask_bits=bits[i])
         # first hidden layer: only its h half [nf, :nf] is a GEMM here; the feature half is the per-image bias (PyTorch side)
         d_ws[0] = zeros_like(0, ws[0])
         _wgrad(dzl, False, zs[0], True, nf, nf, passes, d_ws[0])
@@ -146,7 +163,7 @@ class _FieldMLP(torch.autograd.Function):
         if ctx.has_bias and need[4]:
             d_bias = torch.empty(ctx.n_img, nf, device=dev)
             _call("b2a_mlp_colsum_segments", (_p(dzl), dzl.stride(0), _p(seg_start), ctx.n_img, nf, _p(d_bias), st))
-        dz0 = _gemm(dzl, nf, _pack(ws[0], nf, nf, True), nf, False, passes, 1, mask_bits=bits[0])
+        dz0 = _gemm(dzl, nf, tp[0], nf, False, passes, 1, mask_bits=bits[0])
         d_w_in = zeros_like(ctx.n_w, w_in)
         _wgrad(dz0, False, E, False, nf, kin, passes, d_w_in)
         d_b_in = torch.empty(1, nf, device=dev)                  # column sums of dz0 = one segment [0, N)
@@ -155,7 +172,7 @@ class _FieldMLP(torch.autograd.Function):
         d_b_in = d_b_in.view(nf)
         d_x = None
         if need[0]:
-            dE = _gemm(dz0, nf, _pack(w_in, kin, nf, True), kin, False, passes, 0, ldo=E.shape[1])
+            dE = _gemm(dz0, nf, tp[ctx.n_w], kin, False, passes, 0, ldo=E.shape[1])
             d_x = torch.empty(N, 3, device=dev)
             _call("b2a_mlp_embed_bwd", (_p(x), x.stride(0), N, n_harm, float(scalar), int(symmetrize), int(concat), _p(dE), dE.stride(0), _p(d_x), 3, st))
         return (d_x, None, None, None, d_bias, d_w_in, d_b_in) + tuple(d_ws)

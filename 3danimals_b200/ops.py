@@ -66,7 +66,7 @@ def _workspace(nbytes, device):
 # kernels launched by each C-ABI entry point (memsets / memcpys are not kernels) - the source of bench.py's gpu_launches
 KERNELS_PER_CALL = {
     "b2a_mt_count": 4, "b2a_mt_emit": 2, "b2a_mt_bwd": 1, "b2a_estimate_bones": 4, "b2a_lbs_bone_transforms": 2, "b2a_lbs_fwd": 1, "b2a_lbs_bwd": 1,
-    "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1, "b2a_rows_gather": 1, "b2a_rows_scatter": 2, "b2a_composite_up_pool_fwd": 1, "b2a_composite_up_pool_bwd": 1, "b2a_articulation_constraints_fwd": 1, "b2a_articulation_constraints_bwd": 1,
+    "b2a_lbs_bone_transforms_bwd": 2, "b2a_vertex_normals_fwd": 2, "b2a_vertex_normals_bwd": 2, "b2a_xfm_points_fwd": 1, "b2a_mlp_pack_weights_many": 1, "b2a_rows_gather": 1, "b2a_rows_scatter": 2, "b2a_composite_up_pool_fwd": 1, "b2a_composite_up_pool_bwd": 1, "b2a_articulation_constraints_fwd": 1, "b2a_articulation_constraints_bwd": 1,
     "b2a_xfm_points_bwd": 1, "b2a_rasterize_fwd": 3, "b2a_rasterize_bwd": 1, "b2a_interpolate_fwd": 1, "b2a_interpolate_bwd": 1,
     "b2a_edge_adjacency": 3, "b2a_antialias_prepare": 2, "b2a_antialias_fwd": 1, "b2a_antialias_bwd": 2,
     "b2a_antialias_pair_fwd": 1, "b2a_antialias_pair_bwd": 1, "b2a_shade_directional_fwd": 1, "b2a_shade_directional_bwd": 1,

@@ -325,6 +325,9 @@ int b2a_rows_scatter(const float* src, const int64_t* idx, int64_t N, int C, flo
 int b2a_mlp_packed_bytes(int N, int K, size_t* bytes);
 int b2a_mlp_pack_weights(const float* W, int64_t ldw, int N, int K, int transpose, void* packed, size_t packed_bytes,
                          b2a_stream_t stream);
+/* the same for n <= 32 weight matrices in one launch: jobs = HOST array [n][6] of int64 {W (device pointer), ldw, N, K,
+ * transpose, packed (device pointer)} */
+int b2a_mlp_pack_weights_many(const int64_t* jobs, int n, b2a_stream_t stream);
 int b2a_mlp_rows_gemm(const float* A, int64_t lda, int64_t rows, int K, const void* packed, int N, int relu_on_load,
                       int passes, int epilogue, const float* bias, const int32_t* bias_rows, const float* mask_src,
                       int64_t ldm, const uint32_t* mask_bits, uint32_t* bits_out, float* out, int64_t ldo,

@@ -8,7 +8,7 @@ import subprocess
 from conftest import ROOT, pkg
 
 EXPECTED = {
-    "b2a_articulation_constraints_fwd", "b2a_articulation_constraints_bwd", "b2a_composite_up_pool_fwd", "b2a_composite_up_pool_bwd", "b2a_rows_gather", "b2a_rows_scatter", "b2a_p2p_alloc", "b2a_p2p_open", "b2a_p2p_close", "b2a_p2p_free", "b2a_allreduce_p2p",
+    "b2a_articulation_constraints_fwd", "b2a_articulation_constraints_bwd", "b2a_composite_up_pool_fwd", "b2a_composite_up_pool_bwd", "b2a_mlp_pack_weights_many", "b2a_rows_gather", "b2a_rows_scatter", "b2a_p2p_alloc", "b2a_p2p_open", "b2a_p2p_close", "b2a_p2p_free", "b2a_allreduce_p2p",
     "b2a_version", "b2a_last_error_string", "b2a_mt_workspace_bytes", "b2a_mt_tile_shape", "b2a_mt_count", "b2a_mt_emit", "b2a_mt_bwd",
     "b2a_estimate_bones_workspace_bytes", "b2a_estimate_bones", "b2a_lbs_bone_transforms", "b2a_lbs_fwd", "b2a_lbs_bwd", "b2a_lbs_bone_transforms_bwd", "b2a_vertex_normals_fwd",
     "b2a_vertex_normals_bwd", "b2a_xfm_points_fwd", "b2a_xfm_points_bwd", "b2a_rasterize_workspace_bytes", "b2a_rasterize_fwd",
