@@ -196,8 +196,8 @@ def coord_mlp_rows(net, x, feat, img, n_img):
         w0 = lin[0].weight
         bias_img = torch.nn.functional.linear(torch.relu(feat.float()), w0[:, nf:])          # [n_img, nf]: the feature half, with autograd
         img32 = img.to(torch.int32)
-        seg = torch.zeros(n_img + 1, dtype=torch.int64, device=x.device)
-        seg[1:] = torch.cumsum(torch.bincount(img, minlength=n_img), 0)
+        # first row of every image (img is ascending): a binary search per image instead of a histogram of all the rows
+        seg = torch.searchsorted(img, torch.arange(n_img + 1, dtype=img.dtype, device=x.device))
     cfg = (n_harm, scalar, bool(net.symmetrize), bool(net.embed_concat_pts), passes, sigmoid)
     out = _FieldMLP.apply(x, img32, seg, cfg, bias_img, net.in_layer.weight, net.in_layer.bias, *[m.weight for m in lin])
     if net.min_max is not None:
