@@ -110,7 +110,10 @@ def _sample_field(net, gb_tex_pos, feat, sparse):
         if feat is not None:
             f = feat.index_select(0, img) if feat.shape[0] == B else feat.expand(B, -1).index_select(0, img)
         y = net.sample(x, feat=f)
-    out = ops.scatter_rows(y, idx, B * h * w) if y.dtype == torch.float32 else y.new_zeros(B * h * w, y.shape[-1]).index_copy(0, idx, y)
+    if y.is_cuda and y.dtype == torch.float32:
+        out = ops.scatter_rows(y, idx, B * h * w)
+    else:           # autocast outputs in half precision (and the host-side tests of this glue): torch's own scatter
+        out = y.new_zeros(B * h * w, y.shape[-1]).index_copy(0, idx, y)
     return out.view(B, h, w, y.shape[-1])
 
 
