@@ -22,6 +22,10 @@ def timed(fn, n=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
 
+lib.b2a_mlp_rows_gemm(A.data_ptr(), 256, rows, 256, Wp.data_ptr(), 256, 1, 3, 0, None, None, None, 0, None, None, out.data_ptr(), 256, st)
+ref = torch.relu(A).double() @ W.double().t()
+print("gemm check (3-pass, relu on load): max |err| / max |ref| = %.2e   (B2A_MLP_CLUSTER=%s)" % (float((out.double() - ref).abs().max() / ref.abs().max()), os.environ.get("B2A_MLP_CLUSTER", "-")))
+del ref
 mb = rows * 256 * 4 / 1e6
 print("rows %d: one [rows,256] fp32 matrix = %.1f MB" % (rows, mb))
 def rep(name, us, nbytes): print("%-46s %8.1f us   %6.0f GB/s" % (name, us, nbytes / us / 1e3))
